@@ -1,0 +1,476 @@
+// eggphot_capi.cu — the C ABI of include/eggphot.h: context, device tables, chunked host pipeline.
+//
+// Replaces the block `if (!no_flux) {...}` of src/egg-gencat.cpp:2024-2240 behind plain-C entry
+// points.  No CPU compute path exists here: without a CUDA device every entry point returns
+// EGGPHOT_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/eggphot.h"
+#include "phot_kernels.cuh"
+#include "phot_tables.hpp"
+
+using namespace eggphot;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) {
+        if (p && bytes >= n) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+        if (n == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    cudaError_t upload(const void *src, size_t n) {
+        cudaError_t e = alloc(n);
+        if (e != cudaSuccess || n == 0) return e;
+        return cudaMemcpy(p, src, n, cudaMemcpyHostToDevice);
+    }
+};
+
+constexpr int kSlots = 2;
+
+// device staging of one chunk of galaxies for the host-memory entry point
+struct Slot {
+    cudaStream_t stream = nullptr;
+    DevBuf z, d, m_disk, m_bulge, m2lcor, lir, fpah, mdust, igm_abs, vdisp, lld, llb, osd, osb, irs;
+    DevBuf flux, flux_disk, flux_bulge, rfmag, rfmag_disk, rfmag_bulge, fd64, fb64, rd64, rb64;
+};
+
+} // namespace
+
+struct eggphot_ctx {
+    std::string err;
+    Prepared P;
+    int device = 0, num_sms = 0;
+    bool ready = false;
+    cudaStream_t stream = nullptr;
+    // prepared tables on the device
+    std::vector<DevBuf> blobs;
+    DevBuf xB, xD, xBhi, xBlo, xDhi, xDlo, rowsB, rowsDopt, rowsDir, rowsDpah, opt_use, rfB, rfD, rfW, errflag;
+    int strideB = 0, strideD = 0;
+    FluxParams base{};
+    std::vector<int> grid_blocks; // per group
+    uint64_t launches = 0;
+    uint64_t table_bytes = 0;
+    Slot slots[kSlots];
+    size_t chunk = 0;
+
+    int fail(int code, const std::string &m) { err = m; return code; }
+    int cuda_fail(cudaError_t e, const char *what) {
+        err = std::string(what) + ": " + cudaGetErrorString(e);
+        return EGGPHOT_ERR_CUDA;
+    }
+};
+
+namespace {
+
+template <typename T> std::vector<T> pad_rows(const std::vector<double> &rows, size_t nrow, int n, int stride) {
+    std::vector<T> out(nrow * (size_t)stride, T(0));
+    for (size_t r = 0; r < nrow; ++r)
+        for (int j = 0; j < n; ++j) out[r * stride + j] = (T)rows[r * n + j];
+    return out;
+}
+
+cudaError_t upload_rows(DevBuf &b, const std::vector<double> &rows, size_t nrow, int n, int stride, int precision,
+                        uint64_t &bytes) {
+    if (rows.empty()) return cudaSuccess;
+    cudaError_t e;
+    if (precision == EGGPHOT_FP64) {
+        auto v = pad_rows<double>(rows, nrow, n, stride);
+        e = b.upload(v.data(), v.size() * sizeof(double));
+    } else {
+        auto v = pad_rows<float>(rows, nrow, n, stride);
+        e = b.upload(v.data(), v.size() * sizeof(float));
+    }
+    bytes += b.bytes;
+    return e;
+}
+
+cudaError_t upload_grid(const Grid &g, DevBuf &x, DevBuf &hi, DevBuf &lo, uint64_t &bytes) {
+    if (g.n() == 0) return cudaSuccess;
+    std::vector<float> h(g.n()), l(g.n());
+    for (int j = 0; j < g.n(); ++j) {
+        h[j] = (float)g.x[j];
+        l[j] = (float)(g.x[j] - (double)h[j]);
+    }
+    cudaError_t e = x.upload(g.x.data(), g.n() * sizeof(double));
+    if (e == cudaSuccess) e = hi.upload(h.data(), h.size() * sizeof(float));
+    if (e == cudaSuccess) e = lo.upload(l.data(), l.size() * sizeof(float));
+    bytes += x.bytes + hi.bytes + lo.bytes;
+    return e;
+}
+
+int check_galaxies(eggphot_ctx *c, const eggphot_galaxies *g) {
+    const Prepared &P = c->P;
+    if (!g || !g->z || !g->d || !g->m2lcor) return c->fail(EGGPHOT_ERR_ARG, "galaxy columns z, d, m2lcor are required");
+    if (!g->m_disk && P.disk_mode != DISK_IR) return c->fail(EGGPHOT_ERR_ARG, "m_disk is required");
+    if (P.has_bulge && (!g->m_bulge || !g->opt_sed_bulge)) return c->fail(EGGPHOT_ERR_ARG, "m_bulge and opt_sed_bulge are required");
+    if (P.disk_mode != DISK_IR && !g->opt_sed_disk) return c->fail(EGGPHOT_ERR_ARG, "opt_sed_disk is required");
+    if (P.disk_mode != DISK_OPT) {
+        if (!g->ir_sed) return c->fail(EGGPHOT_ERR_ARG, "ir_sed is required");
+        if (P.ir_kind == EGGPHOT_IR_CS17 ? (!g->fpah || !g->mdust) : !g->lir)
+            return c->fail(EGGPHOT_ERR_ARG, "lir (generic IR library) or fpah+mdust (cs17) are required");
+    }
+    if (P.apply_igm && !g->igm_abs) return c->fail(EGGPHOT_ERR_ARG, "igm_abs is required unless igm is none/constant");
+    if (!P.no_nebular && (!g->vdisp || !g->line_lum_disk))
+        return c->fail(EGGPHOT_ERR_ARG, "vdisp and line_lum_disk are required unless no_nebular is set");
+    return EGGPHOT_OK;
+}
+
+void fill_params(const eggphot_ctx *c, const eggphot_galaxies &g, size_t ngal, const eggphot_outputs &o, FluxParams &p) {
+    p = c->base;
+    p.z = g.z; p.d = g.d; p.m_disk = g.m_disk; p.m_bulge = g.m_bulge; p.m2lcor = g.m2lcor;
+    p.lir = g.lir; p.fpah = g.fpah; p.mdust = g.mdust; p.igm_abs = g.igm_abs; p.vdisp = g.vdisp;
+    p.line_lum_disk = c->P.no_nebular ? nullptr : g.line_lum_disk;
+    p.line_lum_bulge = c->P.no_nebular ? nullptr : g.line_lum_bulge;
+    p.opt_sed_disk = g.opt_sed_disk; p.opt_sed_bulge = g.opt_sed_bulge; p.ir_sed = g.ir_sed;
+    p.ngal = ngal;
+    p.flux = o.flux; p.flux_disk = o.flux_disk; p.flux_bulge = o.flux_bulge;
+    p.rfmag = o.rfmag; p.rfmag_disk = o.rfmag_disk; p.rfmag_bulge = o.rfmag_bulge;
+    p.flux_disk_f64 = o.flux_disk_f64; p.flux_bulge_f64 = o.flux_bulge_f64;
+    p.rfmag_disk_f64 = o.rfmag_disk_f64; p.rfmag_bulge_f64 = o.rfmag_bulge_f64;
+}
+
+int enqueue(eggphot_ctx *c, const eggphot_galaxies &g, size_t ngal, const eggphot_outputs &o, cudaStream_t st) {
+    if (ngal == 0) return EGGPHOT_OK;
+    FluxParams p;
+    fill_params(c, g, ngal, o, p);
+    const bool want_rf = c->P.rfbands.size() && (o.rfmag || o.rfmag_disk || o.rfmag_bulge || o.rfmag_disk_f64 || o.rfmag_bulge_f64);
+    const size_t ngroups = c->P.groups.size();
+    for (size_t gi = 0; gi < std::max<size_t>(ngroups, 1); ++gi) {
+        if (ngroups == 0 && !want_rf) break;
+        if (ngroups) {
+            p.blob = (const uint8_t *)c->blobs[gi].p;
+            p.blob_bytes = (uint32_t)c->P.groups[gi].blob.size();
+            p.nb = (uint32_t)c->P.groups[gi].cols.size();
+        } else {
+            p.blob = nullptr; p.blob_bytes = 0; p.nb = 0;
+        }
+        p.do_rf = want_rf && gi == 0;
+        int blocks = ngroups ? c->grid_blocks[gi] : c->num_sms;
+        blocks = (int)std::min<size_t>((size_t)blocks, ngal);
+        int e = launch_flux_kernel(p, c->P.precision, blocks, st);
+        if (e != 0) return c->cuda_fail((cudaError_t)e, "flux kernel launch");
+        ++c->launches;
+    }
+    return EGGPHOT_OK;
+}
+
+int read_error_flag(eggphot_ctx *c) {
+    int flag = 0;
+    cudaError_t e = cudaMemcpy(&flag, c->errflag.p, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return c->cuda_fail(e, "reading the error flag");
+    if (flag) {
+        int zero = 0;
+        cudaMemcpy(c->errflag.p, &zero, sizeof(int), cudaMemcpyHostToDevice);
+        return c->fail(flag, "a galaxy points to a template outside the library or to an unusable optical SED (use = false)");
+    }
+    return EGGPHOT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const eggphot_filters *rfbands,
+                   const eggphot_opts *opts, eggphot_ctx **out) {
+    if (!out) return EGGPHOT_ERR_ARG;
+    eggphot_ctx *c = new (std::nothrow) eggphot_ctx();
+    *out = c;
+    if (!c) return EGGPHOT_ERR_ARG;
+    if (!libs || !opts) return c->fail(EGGPHOT_ERR_ARG, "libs and opts are required");
+    Status st = prepare(*libs, bands, rfbands, *opts, c->P);
+    if (!st.ok()) return c->fail(st.code, st.msg);
+    const Prepared &P = c->P;
+    if (P.rfbands.size() > 16) return c->fail(EGGPHOT_ERR_UNSUPPORTED, "more than 16 rfbands");
+
+    // ---- device
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return c->fail(EGGPHOT_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count is 0") +
+                                           " (this library has no CPU path)");
+    c->device = opts->device;
+    if ((e = cudaSetDevice(c->device)) != cudaSuccess) return c->cuda_fail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, c->device)) != cudaSuccess) return c->cuda_fail(e, "cudaGetDeviceProperties");
+    if (prop.major < 10) return c->fail(EGGPHOT_ERR_CUDA, "device is not sm_100 class (kernels are built for sm_100a only)");
+    c->num_sms = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return c->cuda_fail(e, "cudaStreamCreate");
+    for (auto &s : c->slots)
+        if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess) return c->cuda_fail(e, "cudaStreamCreate");
+
+    // ---- tables
+    uint64_t tb = 0;
+    const int per16 = P.precision == EGGPHOT_FP64 ? 2 : 4;
+    c->strideB = (P.grid_bulge.n() + per16 - 1) / per16 * per16;
+    c->strideD = (P.grid_disk.n() + per16 - 1) / per16 * per16;
+#define CK(x) do { if ((e = (x)) != cudaSuccess) return c->cuda_fail(e, #x); } while (0)
+    CK(upload_grid(P.grid_bulge, c->xB, c->xBhi, c->xBlo, tb));
+    CK(upload_grid(P.grid_disk, c->xD, c->xDhi, c->xDlo, tb));
+    CK(upload_rows(c->rowsB, P.rows_bulge_opt, P.nopt_sed, P.grid_bulge.n(), c->strideB, P.precision, tb));
+    CK(upload_rows(c->rowsDopt, P.rows_disk_opt, P.nopt_sed, P.grid_disk.n(), c->strideD, P.precision, tb));
+    CK(upload_rows(c->rowsDir, P.rows_disk_ir, P.nir_sed, P.grid_disk.n(), c->strideD, P.precision, tb));
+    CK(upload_rows(c->rowsDpah, P.rows_disk_pah, P.nir_sed, P.grid_disk.n(), c->strideD, P.precision, tb));
+    if (!P.opt_use.empty()) CK(c->opt_use.upload(P.opt_use.data(), P.opt_use.size()));
+    c->blobs.resize(P.groups.size());
+    for (size_t g = 0; g < P.groups.size(); ++g) {
+        CK(c->blobs[g].upload(P.groups[g].blob.data(), P.groups[g].blob.size()));
+        tb += c->blobs[g].bytes;
+    }
+    // rest-frame weights
+    {
+        std::vector<RfDesc> dB(P.rfbands.size()), dD(P.rfbands.size());
+        std::vector<double> w;
+        auto add = [&](const RfWeights &r, RfDesc &d) {
+            d.j0 = r.j0; d.n = (int)r.w.size(); d.off = (int)w.size(); d.covered = r.covered;
+            w.insert(w.end(), r.w.begin(), r.w.end());
+        };
+        for (size_t b = 0; b < P.rfbands.size(); ++b) { add(P.rf_bulge[b], dB[b]); add(P.rf_disk[b], dD[b]); }
+        if (!dB.empty()) {
+            CK(c->rfB.upload(dB.data(), dB.size() * sizeof(RfDesc)));
+            CK(c->rfD.upload(dD.data(), dD.size() * sizeof(RfDesc)));
+            if (w.empty()) w.push_back(0.0);
+            if (P.precision == EGGPHOT_FP64) CK(c->rfW.upload(w.data(), w.size() * sizeof(double)));
+            else {
+                std::vector<float> wf(w.begin(), w.end());
+                CK(c->rfW.upload(wf.data(), wf.size() * sizeof(float)));
+            }
+            tb += c->rfW.bytes;
+        }
+    }
+    int zero = 0;
+    CK(c->errflag.upload(&zero, sizeof(int)));
+    c->table_bytes = tb;
+
+    // ---- launch-invariant parameters
+    FluxParams &p = c->base;
+    std::memset(&p, 0, sizeof(p));
+    p.nband_total = (uint32_t)P.bands.size();
+    p.nrf = (uint32_t)P.rfbands.size();
+    p.nB = P.grid_bulge.n(); p.nD = P.grid_disk.n();
+    p.strideB = c->strideB; p.strideD = c->strideD;
+    p.xB = (const double *)c->xB.p; p.xD = (const double *)c->xD.p;
+    p.xBhi = (const float *)c->xBhi.p; p.xBlo = (const float *)c->xBlo.p;
+    p.xDhi = (const float *)c->xDhi.p; p.xDlo = (const float *)c->xDlo.p;
+    const Grid &gb = P.grid_bulge, &gd = P.grid_disk;
+    p.igmB[0] = gb.lz; p.igmB[1] = gb.l0; p.igmB[2] = gb.l1; p.igmB[3] = gb.l2;
+    p.igmD[0] = gd.lz; p.igmD[1] = gd.l0; p.igmD[2] = gd.l1; p.igmD[3] = gd.l2;
+    p.rowsB = c->rowsB.p; p.rowsDopt = c->rowsDopt.p; p.rowsDir = c->rowsDir.p; p.rowsDpah = c->rowsDpah.p;
+    p.opt_use = (const uint8_t *)c->opt_use.p;
+    p.nopt_sed = P.nopt_sed; p.nir_sed = P.nir_sed;
+    p.ir_kind = P.ir_kind; p.disk_mode = (int)P.disk_mode; p.has_bulge = P.has_bulge; p.apply_igm = P.apply_igm;
+    p.nline = P.no_nebular ? 0 : (int)P.line_lambda.size();
+    p.line_average = P.line_profile == EGGPHOT_LINE_AVERAGE;
+    for (int l = 0; l < p.nline; ++l) p.line_lambda[l] = P.line_lambda[l];
+    p.rfB = (const RfDesc *)c->rfB.p; p.rfD = (const RfDesc *)c->rfD.p; p.rfW = c->rfW.p;
+    p.error_flag = (int32_t *)c->errflag.p;
+
+    // ---- grid size per group: one persistent CTA per resident slot
+    c->grid_blocks.assign(P.groups.size(), c->num_sms);
+    for (size_t g = 0; g < P.groups.size(); ++g) {
+        FluxParams q = p;
+        q.blob_bytes = (uint32_t)P.groups[g].blob.size();
+        q.nb = (uint32_t)P.groups[g].cols.size();
+        if (q.nb > (uint32_t)kMaxGroupBands) return c->fail(EGGPHOT_ERR_UNSUPPORTED, "more than 64 bands in one group");
+        const size_t smem = flux_kernel_smem(q, P.precision);
+        if (smem > (size_t)prop.sharedMemPerBlockOptin)
+            return c->fail(EGGPHOT_ERR_UNSUPPORTED, "band group needs " + std::to_string(smem) + " B of shared memory, device offers " +
+                                                     std::to_string(prop.sharedMemPerBlockOptin));
+        const int occ = flux_kernel_max_blocks_per_sm(q, P.precision);
+        if (occ <= 0) return c->fail(EGGPHOT_ERR_CUDA, "flux kernel cannot be resident (occupancy query failed)");
+        c->grid_blocks[g] = c->num_sms * occ;
+    }
+#undef CK
+    c->ready = true;
+    return EGGPHOT_OK;
+}
+
+void eggphot_destroy(eggphot_ctx *c) {
+    if (!c) return;
+    if (c->stream) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    for (auto &s : c->slots) if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+    delete c;
+}
+
+const char *eggphot_last_error(const eggphot_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+uint32_t eggphot_nband(const eggphot_ctx *c, int which) {
+    if (!c) return 0;
+    return (uint32_t)(which ? c->P.rfbands.size() : c->P.bands.size());
+}
+
+int eggphot_band_order(const eggphot_ctx *c, int which, uint32_t *order, float *lambda) {
+    if (!c) return EGGPHOT_ERR_ARG;
+    const auto &o = which ? c->P.rfband_order : c->P.band_order;
+    const auto &l = which ? c->P.rfband_lambda : c->P.band_lambda;
+    for (size_t k = 0; k < o.size(); ++k) {
+        if (order) order[k] = o[k];
+        if (lambda) lambda[k] = l[k];
+    }
+    return EGGPHOT_OK;
+}
+
+int eggphot_compute_device(eggphot_ctx *c, const eggphot_galaxies *gal, size_t ngal, const eggphot_outputs *out, void *stream) {
+    if (!c || !c->ready) return c ? c->fail(EGGPHOT_ERR_ARG, "context is not ready") : EGGPHOT_ERR_ARG;
+    if (!out) return c->fail(EGGPHOT_ERR_ARG, "outputs are required");
+    int rc = check_galaxies(c, gal);
+    if (rc) return rc;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return c->cuda_fail(e, "cudaSetDevice");
+    c->launches = 0;
+    return enqueue(c, *gal, ngal, *out, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int eggphot_synchronize(eggphot_ctx *c) {
+    if (!c || !c->ready) return EGGPHOT_ERR_ARG;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return c->cuda_fail(e, "synchronize");
+    return read_error_flag(c);
+}
+
+int eggphot_compute(eggphot_ctx *c, const eggphot_galaxies *gal, size_t ngal, const eggphot_outputs *out) {
+    if (!c || !c->ready) return c ? c->fail(EGGPHOT_ERR_ARG, "context is not ready") : EGGPHOT_ERR_ARG;
+    if (!out) return c->fail(EGGPHOT_ERR_ARG, "outputs are required");
+    int rc = check_galaxies(c, gal);
+    if (rc) return rc;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return c->cuda_fail(e, "cudaSetDevice");
+    c->launches = 0;
+    const Prepared &P = c->P;
+    const size_t nb = P.bands.size(), nrf = P.rfbands.size(), nl = P.no_nebular ? 0 : P.line_lambda.size();
+    const size_t chunk = std::min<size_t>(ngal, 1u << 18);
+    if (chunk == 0) return EGGPHOT_OK;
+#define CK(x) do { if ((e = (x)) != cudaSuccess) return c->cuda_fail(e, #x); } while (0)
+    struct Col { DevBuf Slot::*buf; const void *src; size_t elem; };
+    const Col ins[] = {
+        {&Slot::z, gal->z, 4}, {&Slot::d, gal->d, 4}, {&Slot::m_disk, gal->m_disk, 4}, {&Slot::m_bulge, gal->m_bulge, 4},
+        {&Slot::m2lcor, gal->m2lcor, 4}, {&Slot::lir, gal->lir, 4}, {&Slot::fpah, gal->fpah, 4}, {&Slot::mdust, gal->mdust, 4},
+        {&Slot::igm_abs, P.apply_igm ? gal->igm_abs : nullptr, 12}, {&Slot::vdisp, nl ? gal->vdisp : nullptr, 4},
+        {&Slot::lld, nl ? gal->line_lum_disk : nullptr, 4 * nl}, {&Slot::llb, nl ? gal->line_lum_bulge : nullptr, 4 * nl},
+        {&Slot::osd, gal->opt_sed_disk, 8}, {&Slot::osb, gal->opt_sed_bulge, 8}, {&Slot::irs, gal->ir_sed, 8}};
+    struct OCol { DevBuf Slot::*buf; void *dst; size_t elem; };
+    const OCol outs[] = {
+        {&Slot::flux, out->flux, 4 * nb}, {&Slot::flux_disk, out->flux_disk, 4 * nb}, {&Slot::flux_bulge, out->flux_bulge, 4 * nb},
+        {&Slot::rfmag, out->rfmag, 4 * nrf}, {&Slot::rfmag_disk, out->rfmag_disk, 4 * nrf}, {&Slot::rfmag_bulge, out->rfmag_bulge, 4 * nrf},
+        {&Slot::fd64, out->flux_disk_f64, 8 * nb}, {&Slot::fb64, out->flux_bulge_f64, 8 * nb},
+        {&Slot::rd64, out->rfmag_disk_f64, 8 * nrf}, {&Slot::rb64, out->rfmag_bulge_f64, 8 * nrf}};
+    for (auto &s : c->slots) {
+        for (const Col &k : ins) if (k.src && k.elem) CK((s.*(k.buf)).alloc(chunk * k.elem));
+        for (const OCol &k : outs) if (k.dst && k.elem) CK((s.*(k.buf)).alloc(chunk * k.elem));
+    }
+    // chunk k: H2D, kernels, D2H all on slot (k mod 2)'s stream; the two streams overlap each other's
+    // copies and kernels
+    size_t k = 0;
+    for (size_t first = 0; first < ngal; first += chunk, ++k) {
+        Slot &s = c->slots[k % kSlots];
+        const size_t n = std::min(chunk, ngal - first);
+        for (const Col &col : ins)
+            if (col.src && col.elem)
+                CK(cudaMemcpyAsync((s.*(col.buf)).p, (const char *)col.src + first * col.elem, n * col.elem,
+                                   cudaMemcpyHostToDevice, s.stream));
+        eggphot_galaxies dg{};
+        dg.z = (const float *)s.z.p; dg.d = (const float *)s.d.p; dg.m_disk = (const float *)s.m_disk.p;
+        dg.m_bulge = (const float *)s.m_bulge.p; dg.m2lcor = (const float *)s.m2lcor.p; dg.lir = (const float *)s.lir.p;
+        dg.fpah = gal->fpah ? (const float *)s.fpah.p : nullptr; dg.mdust = gal->mdust ? (const float *)s.mdust.p : nullptr;
+        dg.igm_abs = (const float *)s.igm_abs.p; dg.vdisp = (const float *)s.vdisp.p;
+        dg.line_lum_disk = (nl && gal->line_lum_disk) ? (const float *)s.lld.p : nullptr;
+        dg.line_lum_bulge = (nl && gal->line_lum_bulge) ? (const float *)s.llb.p : nullptr;
+        dg.opt_sed_disk = (const uint64_t *)s.osd.p; dg.opt_sed_bulge = (const uint64_t *)s.osb.p; dg.ir_sed = (const uint64_t *)s.irs.p;
+        eggphot_outputs dout{};
+        dout.flux = out->flux ? (float *)s.flux.p : nullptr;
+        dout.flux_disk = out->flux_disk ? (float *)s.flux_disk.p : nullptr;
+        dout.flux_bulge = out->flux_bulge ? (float *)s.flux_bulge.p : nullptr;
+        dout.rfmag = out->rfmag ? (float *)s.rfmag.p : nullptr;
+        dout.rfmag_disk = out->rfmag_disk ? (float *)s.rfmag_disk.p : nullptr;
+        dout.rfmag_bulge = out->rfmag_bulge ? (float *)s.rfmag_bulge.p : nullptr;
+        dout.flux_disk_f64 = out->flux_disk_f64 ? (double *)s.fd64.p : nullptr;
+        dout.flux_bulge_f64 = out->flux_bulge_f64 ? (double *)s.fb64.p : nullptr;
+        dout.rfmag_disk_f64 = out->rfmag_disk_f64 ? (double *)s.rd64.p : nullptr;
+        dout.rfmag_bulge_f64 = out->rfmag_bulge_f64 ? (double *)s.rb64.p : nullptr;
+        rc = enqueue(c, dg, n, dout, s.stream);
+        if (rc) return rc;
+        for (const OCol &col : outs)
+            if (col.dst && col.elem)
+                CK(cudaMemcpyAsync((char *)col.dst + first * col.elem, (s.*(col.buf)).p, n * col.elem,
+                                   cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (auto &s : c->slots) CK(cudaStreamSynchronize(s.stream));
+#undef CK
+    return read_error_flag(c);
+}
+
+uint32_t eggphot_sed_size(const eggphot_ctx *c, int component) {
+    if (!c) return 0;
+    return (uint32_t)(component ? c->P.grid_disk.n() : c->P.grid_bulge.n());
+}
+
+int eggphot_get_seds(eggphot_ctx *c, const eggphot_galaxies *gal, size_t first, size_t count, int component,
+                     float *lam, float *sed) {
+    if (!c || !c->ready) return c ? c->fail(EGGPHOT_ERR_ARG, "context is not ready") : EGGPHOT_ERR_ARG;
+    if (!lam || !sed) return c->fail(EGGPHOT_ERR_ARG, "lam and sed are required");
+    if (component == 0 && !c->P.has_bulge) return c->fail(EGGPHOT_ERR_ARG, "no bulge component (no_stellar)");
+    int rc = check_galaxies(c, gal);
+    if (rc) return rc;
+    if (count == 0) return EGGPHOT_OK;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return c->cuda_fail(e, "cudaSetDevice");
+#define CK(x) do { if ((e = (x)) != cudaSuccess) return c->cuda_fail(e, #x); } while (0)
+    const Prepared &P = c->P;
+    const size_t nl = P.no_nebular ? 0 : P.line_lambda.size();
+    const size_t n = eggphot_sed_size(c, component);
+    // stage just this range of galaxies
+    DevBuf cols[15], dl, ds;
+    const void *src[15] = {gal->z, gal->d, gal->m_disk, gal->m_bulge, gal->m2lcor, gal->lir, gal->fpah, gal->mdust,
+                           P.apply_igm ? gal->igm_abs : nullptr, nl ? gal->vdisp : nullptr, nl ? gal->line_lum_disk : nullptr,
+                           nl ? gal->line_lum_bulge : nullptr, gal->opt_sed_disk, gal->opt_sed_bulge, gal->ir_sed};
+    const size_t elem[15] = {4, 4, 4, 4, 4, 4, 4, 4, 12, 4, 4 * nl, 4 * nl, 8, 8, 8};
+    for (int k = 0; k < 15; ++k)
+        if (src[k] && elem[k]) CK(cols[k].upload((const char *)src[k] + first * elem[k], count * elem[k]));
+    CK(dl.alloc(count * n * sizeof(float)));
+    CK(ds.alloc(count * n * sizeof(float)));
+    eggphot_galaxies dg{};
+    dg.z = (const float *)cols[0].p; dg.d = (const float *)cols[1].p; dg.m_disk = (const float *)cols[2].p;
+    dg.m_bulge = (const float *)cols[3].p; dg.m2lcor = (const float *)cols[4].p; dg.lir = (const float *)cols[5].p;
+    dg.fpah = (const float *)cols[6].p; dg.mdust = (const float *)cols[7].p; dg.igm_abs = (const float *)cols[8].p;
+    dg.vdisp = (const float *)cols[9].p; dg.line_lum_disk = (const float *)cols[10].p; dg.line_lum_bulge = (const float *)cols[11].p;
+    dg.opt_sed_disk = (const uint64_t *)cols[12].p; dg.opt_sed_bulge = (const uint64_t *)cols[13].p; dg.ir_sed = (const uint64_t *)cols[14].p;
+    SedParams q{};
+    eggphot_outputs none{};
+    fill_params(c, dg, count, none, q.fp);
+    q.first = 0; q.count = count; q.component = component;
+    q.lam = (float *)dl.p; q.sed = (float *)ds.p;
+    int le = launch_sed_kernel(q, P.precision, c->stream);
+    if (le) return c->cuda_fail((cudaError_t)le, "sed kernel launch");
+    CK(cudaMemcpyAsync(lam, dl.p, count * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(sed, ds.p, count * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+#undef CK
+    return read_error_flag(c);
+}
+
+int eggphot_get_stats(const eggphot_ctx *c, eggphot_stats *s) {
+    if (!c || !s) return EGGPHOT_ERR_ARG;
+    std::memset(s, 0, sizeof(*s));
+    s->kernel_launches = c->launches;
+    s->ngroups = (uint32_t)c->P.groups.size();
+    s->nodes_disk = (uint32_t)c->P.grid_disk.n();
+    s->nodes_bulge = (uint32_t)c->P.grid_bulge.n();
+    s->nodes_ir = c->P.nir;
+    s->table_bytes = c->table_bytes;
+    return EGGPHOT_OK;
+}
+
+} // extern "C"

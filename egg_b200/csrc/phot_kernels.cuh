@@ -1,0 +1,75 @@
+// phot_kernels.cuh — launch interface between the C-ABI host code and the sm_100a kernels.
+#ifndef EGGPHOT_PHOT_KERNELS_CUH
+#define EGGPHOT_PHOT_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "phot_core.cuh"
+
+namespace eggphot {
+
+constexpr int kMaxLines = 64;
+constexpr int kMaxGroupBands = 64;
+constexpr int kThreads = 512;          // 16 warps per CTA
+constexpr int kWarps = kThreads / 32;
+
+// sparse rest-frame weights of one rfband on one component grid
+struct RfDesc {
+    int32_t j0, n;        // first node and count
+    int32_t off;          // offset into the weight array (elements)
+    int32_t covered;      // SED covers the filter at z = 0
+};
+
+// Everything one launch of the flux kernel reads.  Passed by value (__grid_constant__).
+struct FluxParams {
+    // galaxy columns (device pointers; reference names, src/egg-gencat.cpp:551-603)
+    const float *z, *d, *m_disk, *m_bulge, *m2lcor, *lir, *fpah, *mdust, *igm_abs, *vdisp;
+    const float *line_lum_disk, *line_lum_bulge;
+    const uint64_t *opt_sed_disk, *opt_sed_bulge, *ir_sed;
+    uint64_t ngal;
+    // outputs [ngal][nband_total] / [ngal][nrf]
+    float *flux, *flux_disk, *flux_bulge, *rfmag, *rfmag_disk, *rfmag_bulge;
+    double *flux_disk_f64, *flux_bulge_f64, *rfmag_disk_f64, *rfmag_bulge_f64;
+    uint32_t nband_total, nrf;
+    // band group
+    const uint8_t *blob;   // device copy of BandGroup::blob (16-byte aligned)
+    uint32_t blob_bytes, nb;
+    int32_t do_rf;         // this launch also computes the rest-frame magnitudes
+    // component grids
+    int32_t nB, nD;        // nodes (0 if the component is absent)
+    int32_t strideB, strideD; // row strides in elements (16-byte multiples)
+    const double *xB, *xD; // rest wavelengths, double
+    const float *xBhi, *xBlo, *xDhi, *xDlo; // the same as hi+lo float pairs (fp32 mode)
+    int32_t igmB[4], igmD[4]; // lz, l0, l1, l2
+    // template rows in the kernel's real type
+    const void *rowsB, *rowsDopt, *rowsDir, *rowsDpah;
+    const uint8_t *opt_use;
+    uint32_t nopt_sed, nir_sed;
+    int32_t ir_kind, disk_mode, has_bulge, apply_igm;
+    // emission lines
+    int32_t nline, line_average;
+    float line_lambda[kMaxLines];
+    // rest-frame weights
+    const RfDesc *rfB, *rfD;
+    const void *rfW;       // real
+    int32_t *error_flag;   // set to EGGPHOT_ERR_INDEX if a galaxy points outside a library
+};
+
+// dynamic shared memory the flux kernel needs for these parameters
+size_t flux_kernel_smem(const FluxParams &p, int precision);
+// launches one band group; returns cudaError_t as int
+int launch_flux_kernel(const FluxParams &p, int precision, int grid_blocks, cudaStream_t stream);
+int flux_kernel_max_blocks_per_sm(const FluxParams &p, int precision);
+
+// save_sed: observed-frame lam / sed (f32) of galaxies [first, first+count) of one component
+struct SedParams {
+    FluxParams fp;
+    uint64_t first, count;
+    int32_t component; // 0 bulge, 1 disk
+    float *lam, *sed;  // [count][n]
+};
+int launch_sed_kernel(const SedParams &p, int precision, cudaStream_t stream);
+
+} // namespace eggphot
+#endif

@@ -1,0 +1,535 @@
+// phot_tables.cpp — see phot_tables.hpp.
+#include "phot_tables.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+namespace eggphot {
+
+namespace {
+
+double trapz(const std::vector<double> &x, const std::vector<double> &y) {
+    double s = 0;
+    for (size_t i = 0; i + 1 < x.size(); ++i) s += 0.5 * (y[i] + y[i + 1]) * (x[i + 1] - x[i]);
+    return s;
+}
+
+// [vif] lower_bound(v, x): index of the last element <= x, -1 if none.
+int last_le(const std::vector<double> &v, double x) {
+    return (int)(std::upper_bound(v.begin(), v.end(), x) - v.begin()) - 1;
+}
+
+// value at xq of the piece-wise linear curve (x, y), following merge_add's rules
+// (src/egg-utils.hpp:21-60): own value on a node, interpolation strictly inside the span,
+// nothing before the first or after the last node.
+double curve_at(const std::vector<double> &x, const double *y, double xq) {
+    const int n = (int)x.size();
+    if (n == 0 || xq < x[0] || xq > x[n - 1]) return 0.0;
+    int i = last_le(x, xq);
+    if (x[i] == xq) return y[i];
+    return y[i] + (y[i + 1] - y[i]) * (xq - x[i]) / (x[i + 1] - x[i]);
+}
+
+// average of the piece-wise linear curve over [a, b] ([vif] integrate(x, y, a, b)/(b-a), gencat:526-527)
+double box_integral(const std::vector<double> &x, const std::vector<double> &y, double a, double b) {
+    const int n = (int)x.size();
+    a = std::max(a, x.front());
+    b = std::min(b, x.back());
+    if (!(b > a)) return 0.0;
+    auto val = [&](double q) {
+        int i = std::min(std::max(last_le(x, q), 0), n - 2);
+        return y[i] + (y[i + 1] - y[i]) * (q - x[i]) / (x[i + 1] - x[i]);
+    };
+    double px = a, py = val(a), s = 0;
+    for (int k = std::max(last_le(x, a), 0) + 1; k < n && x[k] < b; ++k) {
+        s += 0.5 * (py + y[k]) * (x[k] - px);
+        px = x[k];
+        py = y[k];
+    }
+    s += 0.5 * (py + val(b)) * (b - px);
+    return s;
+}
+
+double pow2ceil(double v) {
+    if (!(v > 0)) return 1.0;
+    return std::exp2(std::ceil(std::log2(v)));
+}
+
+void align16(std::vector<uint8_t> &b) { b.resize((b.size() + 15) & ~size_t(15), 0); }
+
+// Double-precision band table, the source of both device layouts and of the rfband weights.
+struct BandTableD {
+    BandHeader h{};
+    std::vector<FilterNodeD> nodes;
+    std::vector<uint16_t> bkt;
+};
+
+Status build_band_table(const Filter &f, uint32_t out_col, int bucket_factor, BandTableD &t) {
+    const int nf = (int)f.lam.size();
+    t.h = BandHeader{};
+    t.h.out_col = out_col;
+    t.h.full_first = f.lam.front();
+    t.h.full_last = f.lam.back();
+    // drop the wings where the response is identically zero: they add exactly nothing to the
+    // union-grid trapezoid (both factors of every node product vanish there)
+    int a = -1, b = -1;
+    for (int i = 0; i < nf; ++i)
+        if (f.res[i] != 0.0) { if (a < 0) a = i; b = i; }
+    if (a < 0) { // identically zero response
+        t.h.n = 0;
+        t.h.eff_first = t.h.eff_last = t.h.full_first;
+        t.h.fc = (double)(float)t.h.full_first;
+        t.h.ni = t.h.nc = 1.0;
+        t.h.fcf = (float)t.h.fc; t.h.nif = t.h.ncf = 1.0f;
+        t.nodes.clear();
+        t.bkt.assign(2, 0);
+        t.h.nbkt = 1;
+        return Status();
+    }
+    a = std::max(a - 1, 0);
+    b = std::min(b + 1, nf - 1);
+    if (b == a) { b = std::min(a + 1, nf - 1); a = b - 1; }
+    const int n = b - a + 1;
+    if (n > 65000) return Status::error(EGGPHOT_ERR_UNSUPPORTED, "filter with more than 65000 nodes");
+    t.h.n = (uint32_t)n;
+    t.h.eff_first = f.lam[a];
+    t.h.eff_last = f.lam[b];
+    t.h.fc = (double)(float)(0.5 * (f.lam[a] + f.lam[b]));
+    t.nodes.assign(n, FilterNodeD{});
+    double i0 = 0, c1 = 0, a0 = 0, a1 = 0;
+    for (int i = 0; i < n; ++i) {
+        FilterNodeD &e = t.nodes[i];
+        e.tf = f.lam[a + i] - t.h.fc;
+        e.R = f.res[a + i];
+        e.I0 = i0;
+        e.C1 = c1;
+        if (i + 1 < n) {
+            const double tn = f.lam[a + i + 1] - t.h.fc, rn = f.res[a + i + 1];
+            e.dl = f.lam[a + i + 1] - f.lam[a + i];
+            e.s = e.dl > 0 ? (rn - e.R) / e.dl : 0.0;
+            i0 += 0.5 * (e.R + rn) * e.dl;
+            c1 += 0.5 * (e.R * e.tf + rn * tn) * e.dl;
+            a0 += 0.5 * (std::fabs(e.R) + std::fabs(rn)) * e.dl;
+            a1 += 0.5 * (std::fabs(e.R * e.tf) + std::fabs(rn * tn)) * e.dl;
+        }
+    }
+    // two-sided prefix values: cells up to `split` keep the running sums from the left end, the
+    // others are re-expressed as (minus) the sums from the right end, so that a value deep in a
+    // wing is small and differences inside the wing keep their relative accuracy
+    const double tot0 = i0, tot1 = c1;
+    int split = n - 2;
+    {
+        double run = 0;
+        for (int i = 0; i + 1 < n; ++i) {
+            run += 0.5 * (std::fabs(t.nodes[i].R) + std::fabs(t.nodes[i + 1].R)) * t.nodes[i].dl;
+            if (run >= 0.5 * a0) { split = i; break; }
+        }
+    }
+    {   // accumulate from the right end itself (subtracting the total would re-introduce the cancellation)
+        double r0 = 0, r1 = 0;
+        t.nodes[n - 1].I0 = 0;
+        t.nodes[n - 1].C1 = 0;
+        for (int i = n - 2; i > split; --i) {
+            const FilterNodeD &e = t.nodes[i], &f2 = t.nodes[i + 1];
+            r0 -= 0.5 * (e.R + f2.R) * e.dl;
+            r1 -= 0.5 * (e.R * e.tf + f2.R * f2.tf) * e.dl;
+            t.nodes[i].I0 = r0;
+            t.nodes[i].C1 = r1;
+        }
+    }
+    t.h.split = (uint32_t)split;
+    t.h.tot0 = tot0;
+    t.h.tot1 = tot1;
+    t.h.ni = pow2ceil(4.0 * a0);
+    t.h.nc = pow2ceil(4.0 * a1);
+    {
+        const double q = 8388608.0; // 2^23: high parts of the totals on the grid of the [1,2) table values
+        const double s0 = tot0 / t.h.ni, s1 = tot1 / t.h.nc;
+        t.h.tot0h = (float)(std::nearbyint(s0 * q) / q); t.h.tot0l = (float)(s0 - (double)t.h.tot0h);
+        t.h.tot1h = (float)(std::nearbyint(s1 * q) / q); t.h.tot1l = (float)(s1 - (double)t.h.tot1h);
+    }
+    // bucket table: bkt[k] = last node with tf <= tf0 + k*w
+    int nbkt = std::min(std::max(bucket_factor * n, 1), 65000);
+    const double span = t.nodes[n - 1].tf - t.nodes[0].tf;
+    t.h.nbkt = (uint32_t)nbkt;
+    t.h.tf0 = t.nodes[0].tf;
+    t.h.tfl = t.nodes[n - 1].tf;
+    t.h.bkt_inv_w = span > 0 ? nbkt / span : 0.0;
+    t.h.fcf = (float)t.h.fc; t.h.nif = (float)t.h.ni; t.h.ncf = (float)t.h.nc;
+    t.h.tf0f = (float)t.h.tf0; t.h.tflf = (float)t.h.tfl; t.h.bkt_inv_wf = (float)t.h.bkt_inv_w;
+    t.bkt.assign(nbkt + 1, 0);
+    int i = 0;
+    for (int k = 0; k <= nbkt; ++k) {
+        const double edge = t.nodes[0].tf + span * k / nbkt;
+        while (i + 1 < n && t.nodes[i + 1].tf <= edge) ++i;
+        t.bkt[k] = (uint16_t)i;
+    }
+    t.bkt[nbkt] = (uint16_t)(n - 1);
+    return Status();
+}
+
+size_t band_bytes(const BandTableD &t, int precision) {
+    const size_t node = precision == EGGPHOT_FP64 ? sizeof(double) * 6 : sizeof(FilterNodeF);
+    size_t b = ((size_t)t.h.n * node + 15) & ~size_t(15);
+    b += ((t.bkt.size() * sizeof(uint16_t)) + 15) & ~size_t(15);
+    return b;
+}
+
+void append_band(std::vector<uint8_t> &blob, size_t header_pos, const BandTableD &t, int precision) {
+    BandHeader h = t.h;
+    align16(blob);
+    h.node_off = (uint32_t)blob.size();
+    if (precision == EGGPHOT_FP64) {
+        for (const FilterNodeD &e : t.nodes) {
+            const double v[6] = {e.tf, e.R, e.s, e.dl, e.I0, e.C1};
+            const uint8_t *p = reinterpret_cast<const uint8_t *>(v);
+            blob.insert(blob.end(), p, p + sizeof(v));
+        }
+    } else {
+        for (const FilterNodeD &e : t.nodes) {
+            FilterNodeF o;
+            o.tf = (float)e.tf; o.R = (float)e.R; o.s = (float)e.s; o.dl = (float)e.dl;
+            const double i0 = 1.5 + e.I0 / h.ni, c1 = 1.5 + e.C1 / h.nc;
+            o.I0h = (float)i0; o.I0l = (float)(i0 - (double)o.I0h);
+            o.C1h = (float)c1; o.C1l = (float)(c1 - (double)o.C1h);
+            const uint8_t *p = reinterpret_cast<const uint8_t *>(&o);
+            blob.insert(blob.end(), p, p + sizeof(o));
+        }
+    }
+    align16(blob);
+    h.bkt_off = (uint32_t)blob.size();
+    const uint8_t *p = reinterpret_cast<const uint8_t *>(t.bkt.data());
+    blob.insert(blob.end(), p, p + t.bkt.size() * sizeof(uint16_t));
+    align16(blob);
+    std::memcpy(blob.data() + header_pos, &h, sizeof(h));
+}
+
+// Rest-frame weights of one band on one grid: the same interval arithmetic as the kernels, in
+// double, at z = 0, applied to the two hat functions of each interval.
+RfWeights rf_weights(const BandTableD &t, const Grid &g) {
+    RfWeights r;
+    const int N = g.n();
+    r.covered = N >= 2 && g.x.front() <= t.h.full_first && g.x.back() >= t.h.full_last;
+    if (!r.covered || t.h.n < 2) return r;
+    int jlo = std::max(last_le(g.x, t.h.eff_first), 0);
+    int jhi = (int)(std::lower_bound(g.x.begin(), g.x.end(), t.h.eff_last) - g.x.begin());
+    jhi = std::min(jhi, N - 1);
+    if (jhi <= jlo) return r;
+    r.j0 = jlo;
+    r.w.assign(jhi - jlo + 1, 0.0);
+    const int n = (int)t.h.n;
+    const double tfa = t.nodes[0].tf, tfb = t.nodes[n - 1].tf;
+    BandScal<double> bs{};
+    bs.inv_ni = bs.inv_nc = bs.ni = bs.nc = bs.ni_nc = 1.0;
+    bs.tot0h = t.h.tot0; bs.tot1h = t.h.tot1; bs.tot0l = bs.tot1l = 0.0; bs.split = (int)t.h.split;
+    auto tfget = [&](int i) { return t.nodes[i].tf; };
+    struct NodeEval { double tt, te, u; int cell; NodeQ<double> q; double s, dl; };
+    auto eval = [&](int j) {
+        NodeEval e;
+        e.tt = g.x[j] - t.h.fc;
+        e.te = std::min(std::max(e.tt, tfa), tfb);
+        e.cell = find_cell<double>(tfget, t.bkt.data(), (int)t.h.nbkt, t.h.tf0, t.h.bkt_inv_w, n, e.te);
+        node_quantities(t.nodes[e.cell], e.te, bs, e.q, e.u);
+        e.s = t.nodes[e.cell].s;
+        e.dl = t.nodes[e.cell].dl;
+        return e;
+    };
+    NodeEval L = eval(jlo);
+    for (int j = jlo; j < jhi; ++j) {
+        NodeEval Rr = eval(j + 1);
+        r.w[j - jlo] += interval_flux(L.tt, L.te, 1.0, L.q, L.s, L.dl, L.u, L.cell, Rr.tt, Rr.te, 0.0, Rr.q, Rr.cell, bs);
+        r.w[j + 1 - jlo] += interval_flux(L.tt, L.te, 0.0, L.q, L.s, L.dl, L.u, L.cell, Rr.tt, Rr.te, 1.0, Rr.q, Rr.cell, bs);
+        L = Rr;
+    }
+    return r;
+}
+
+Status make_grid_thresholds(Grid &g, bool apply_igm, const char *what) {
+    g.lz = g.l0 = g.l1 = g.l2 = 0;
+    if (!apply_igm) return Status();
+    const int lz = last_le(g.x, 0.0600);
+    if (lz < 0)
+        return Status::error(EGGPHOT_ERR_GRID, std::string("IGM absorption requested but the ") + what +
+                             " wavelength grid has no node at or below 0.06 um (the reference would index past the SED, "
+                             "src/egg-gencat.cpp:2123-2130); use igm=none");
+    g.lz = lz;
+    g.l0 = last_le(g.x, 0.0912);
+    g.l1 = last_le(g.x, 0.1026);
+    g.l2 = last_le(g.x, 0.1216);
+    return Status();
+}
+
+} // namespace
+
+Status prepare_filters(const eggphot_filters *raw, const eggphot_opts &opts, std::vector<Filter> &sorted,
+                       std::vector<uint32_t> &order, std::vector<float> &lambda) {
+    sorted.clear(); order.clear(); lambda.clear();
+    if (!raw || raw->nband == 0) return Status();
+    if (!raw->npts || !raw->lam || !raw->res) return Status::error(EGGPHOT_ERR_ARG, "null filter arrays");
+    const bool adjust = opts.trim_filters || opts.filter_flambda || opts.filter_photons; // gencat:361
+    std::vector<Filter> fil(raw->nband);
+    for (uint32_t b = 0; b < raw->nband; ++b) {
+        const uint32_t n = raw->npts[b];
+        if (n < 2 || !raw->lam[b] || !raw->res[b])
+            return Status::error(EGGPHOT_ERR_FILTER, "filter " + std::to_string(b) + " is empty");
+        Filter &f = fil[b];
+        f.lam.assign(raw->lam[b], raw->lam[b] + n);
+        f.res.assign(raw->res[b], raw->res[b] + n);
+        for (uint32_t i = 0; i + 1 < n; ++i)
+            if (!(f.lam[i + 1] >= f.lam[i]))
+                return Status::error(EGGPHOT_ERR_FILTER, "filter " + std::to_string(b) +
+                                     ": wavelengths are not sorted in increasing order");
+        if (adjust) {
+            if (opts.trim_filters) { // gencat:334-340
+                const double mx = *std::max_element(f.res.begin(), f.res.end());
+                int a = -1, e = -1;
+                for (uint32_t i = 0; i < n; ++i)
+                    if (f.res[i] / mx > 1e-3) { if (a < 0) a = (int)i; e = (int)i; }
+                if (a < 0) return Status::error(EGGPHOT_ERR_FILTER, "filter has no usable data");
+                f.lam = std::vector<double>(f.lam.begin() + a, f.lam.begin() + e + 1);
+                f.res = std::vector<double>(f.res.begin() + a, f.res.begin() + e + 1);
+                if (f.lam.size() < 2) return Status::error(EGGPHOT_ERR_FILTER, "filter has no usable data");
+            }
+            if (opts.filter_flambda) for (size_t i = 0; i < f.lam.size(); ++i) f.res[i] /= f.lam[i] * f.lam[i];
+            if (opts.filter_photons) for (size_t i = 0; i < f.lam.size(); ++i) f.res[i] *= f.lam[i];
+            std::vector<double> lr(f.lam.size());
+            for (size_t i = 0; i < lr.size(); ++i) lr[i] = f.lam[i] * f.res[i];
+            const double norm = trapz(f.lam, f.res);
+            f.rlam = trapz(f.lam, lr) / norm;
+            if (opts.filter_normalize) for (double &r : f.res) r /= norm;
+        } else {
+            std::vector<double> lr(n);
+            for (uint32_t i = 0; i < n; ++i) lr[i] = f.lam[i] * f.res[i];
+            f.rlam = trapz(f.lam, lr); // [vif] get_filter: raw response, no renormalisation (KAT-1)
+        }
+    }
+    // sort by the f32 reference wavelength (vec1f lambda, gencat:367-372)
+    order.resize(raw->nband);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(),
+                     [&](uint32_t i, uint32_t j) { return (float)fil[i].rlam < (float)fil[j].rlam; });
+    for (uint32_t k : order) {
+        sorted.push_back(std::move(fil[k]));
+        lambda.push_back((float)sorted.back().rlam);
+    }
+    return Status();
+}
+
+Status prepare_opt_lib(const eggphot_libs &L, const eggphot_opts &opts, uint32_t &nopt,
+                       std::vector<float> &lam, std::vector<float> &sed) {
+    const size_t nsed = (size_t)L.nuv * L.nvj, nin = L.nopt;
+    if (!L.opt_lam || !L.opt_sed || !L.opt_use || nsed == 0 || nin < 2)
+        return Status::error(EGGPHOT_ERR_ARG, "optical library arrays are missing");
+    const std::string imf = opts.opt_lib_imf ? opts.opt_lib_imf : "salpeter";
+    double fimf = 1.0;
+    if (imf == "chabrier" || imf == "kroupa") fimf = std::pow(10.0, -0.2); // gencat:461-463
+    else if (imf != "salpeter") return Status::error(EGGPHOT_ERR_LIBRARY, "unknown IMF '" + imf + "'");
+    size_t first = nsed;
+    for (size_t s = 0; s < nsed; ++s) if (L.opt_use[s]) { first = s; break; }
+    if (first == nsed) // gencat:537-541
+        return Status::error(EGGPHOT_ERR_LIBRARY, "the provided optical SED library does not contain any valid SED");
+    std::vector<float> fs(L.opt_sed, L.opt_sed + nsed * nin);
+    if (fimf != 1.0) for (float &v : fs) v = (float)(v * fimf);
+
+    std::vector<double> olam(nin);
+    for (size_t l = 0; l < nin; ++l) olam[l] = L.opt_lam[first * nin + l];
+    long id1 = -1, id2 = -1;
+    const double step = opts.opt_lib_min_step;
+    if (step > 0 && nin >= 3) { // gencat:478-488
+        for (size_t l = 0; l < nin; ++l) {
+            const double d = l == 0 ? olam[1] - olam[0]
+                           : l == nin - 1 ? olam[nin - 1] - olam[nin - 2]
+                           : 0.5 * (olam[l + 1] - olam[l - 1]);
+            if (d < step) { if (id1 < 0) id1 = (long)l; id2 = (long)l; }
+        }
+    }
+    if (id1 < 0) {
+        nopt = (uint32_t)nin;
+        lam.assign(L.opt_lam, L.opt_lam + nsed * nin);
+        sed = std::move(fs);
+        return Status();
+    }
+    // gencat:491-508
+    std::vector<double> nl(olam.begin(), olam.begin() + id1);
+    long nnew = (long)std::floor((olam[id2] - olam[id1]) / step) - 1;
+    if (nnew < 0) nnew = 0;
+    for (long k = 0; k < nnew; ++k) nl.push_back(olam[id1] + 0.5 * step + step * (double)k);
+    nl.insert(nl.end(), olam.begin() + id2 + 1, olam.end());
+    const size_t nout = nl.size();
+    nopt = (uint32_t)nout;
+    lam.assign(nsed * nout, 0.0f);
+    sed.assign(nsed * nout, 0.0f);
+    std::vector<double> row(nin);
+    for (size_t s = 0; s < nsed; ++s) {
+        if (!L.opt_use[s]) continue; // gencat:515-519
+        for (size_t l = 0; l < nin; ++l) row[l] = fs[s * nin + l];
+        for (size_t l = 0; l < nout; ++l) lam[s * nout + l] = (float)nl[l];
+        for (long l = 0; l < id1; ++l) sed[s * nout + l] = (float)row[l];
+        for (long k = 0; k < nnew; ++k) {
+            const double c = nl[id1 + k];
+            sed[s * nout + id1 + k] = (float)(box_integral(olam, row, c - 0.5 * step, c + 0.5 * step) / step);
+        }
+        for (size_t l = id2 + 1; l < nin; ++l) sed[s * nout + id1 + nnew + (l - id2 - 1)] = (float)row[l];
+    }
+    return Status();
+}
+
+Status prepare(const eggphot_libs &L, const eggphot_filters *bands, const eggphot_filters *rfbands,
+               const eggphot_opts &opts, Prepared &P) {
+    P = Prepared();
+    if (opts.precision != EGGPHOT_FP32C && opts.precision != EGGPHOT_FP64)
+        return Status::error(EGGPHOT_ERR_ARG, "precision must be EGGPHOT_FP32C or EGGPHOT_FP64");
+    P.precision = opts.precision;
+    const std::string igm = opts.igm ? opts.igm : "inoue14";
+    if (igm != "none" && igm != "constant" && igm != "madau95" && igm != "inoue14") // gencat:286-289
+        return Status::error(EGGPHOT_ERR_ARG, "unknown IGM prescription '" + igm +
+                             "'; possible values are: 'none', 'constant', 'madau95', or 'inoue14'");
+    P.apply_igm = igm != "none" && igm != "constant"; // gencat:2122
+    P.no_stellar = opts.no_stellar;
+    P.no_dust = opts.no_dust;
+    P.no_nebular = opts.no_nebular || opts.nline == 0;
+    P.line_profile = opts.line_profile;
+    if (opts.no_stellar && opts.no_dust) // gencat:247-249 turns the whole stage off
+        return Status::error(EGGPHOT_ERR_ARG, "no_stellar and no_dust together disable the flux stage (no_flux)");
+    if (opts.sed2flux_nodes != EGGPHOT_NODES_MERGED)
+        return Status::error(EGGPHOT_ERR_UNSUPPORTED, "only sed2flux_nodes=merged is implemented on the device");
+    if (opts.nline && opts.line_lambda) P.line_lambda.assign(opts.line_lambda, opts.line_lambda + opts.nline);
+    if (P.line_lambda.size() > 64) return Status::error(EGGPHOT_ERR_UNSUPPORTED, "more than 64 emission lines");
+
+    Status st = prepare_filters(bands, opts, P.bands, P.band_order, P.band_lambda);
+    if (!st.ok()) return st;
+    st = prepare_filters(rfbands, opts, P.rfbands, P.rfband_order, P.rfband_lambda);
+    if (!st.ok()) return st;
+
+    // ---- libraries
+    P.has_bulge = !opts.no_stellar; // gencat:2206
+    P.disk_mode = opts.no_dust ? DISK_OPT : (opts.no_stellar ? DISK_IR : DISK_BOTH); // gencat:2104-2119
+    std::vector<double> xo, xi;
+    if (!opts.no_stellar) {
+        st = prepare_opt_lib(L, opts, P.nopt, P.opt_lam, P.opt_sed);
+        if (!st.ok()) return st;
+        P.nopt_sed = L.nuv * L.nvj;
+        P.opt_use.assign(L.opt_use, L.opt_use + P.nopt_sed);
+        // all used templates must share one wavelength grid (the reference's own re-binning assumes
+        // it, gencat:475-476); a per-template grid would make the merged grid galaxy-dependent
+        const float *ref = nullptr;
+        for (uint32_t s = 0; s < P.nopt_sed; ++s) {
+            if (!P.opt_use[s]) continue;
+            const float *row = P.opt_lam.data() + (size_t)s * P.nopt;
+            if (!ref) ref = row;
+            else if (std::memcmp(ref, row, P.nopt * sizeof(float)) != 0)
+                return Status::error(EGGPHOT_ERR_GRID, "optical templates do not share one wavelength grid");
+        }
+        xo.assign(ref, ref + P.nopt);
+        for (size_t i = 0; i + 1 < xo.size(); ++i)
+            if (!(xo[i + 1] > xo[i])) return Status::error(EGGPHOT_ERR_GRID, "optical wavelength grid is not strictly increasing");
+    }
+    if (!opts.no_dust) {
+        if (!L.ir_lam || !L.ir_sed || L.nir_sed == 0 || L.nir < 2)
+            return Status::error(EGGPHOT_ERR_LIBRARY, "missing LAM and/or SED columns in the IR library"); // gencat:438-441
+        if (L.ir_kind == EGGPHOT_IR_CS17 && !L.ir_pah)
+            return Status::error(EGGPHOT_ERR_LIBRARY, "cs17 IR library needs the PAH column");
+        P.ir_kind = L.ir_kind;
+        P.nir_sed = L.nir_sed;
+        P.nir = L.nir;
+        for (uint32_t s = 1; s < L.nir_sed; ++s)
+            if (std::memcmp(L.ir_lam, L.ir_lam + (size_t)s * L.nir, L.nir * sizeof(double)) != 0)
+                return Status::error(EGGPHOT_ERR_GRID, "IR templates do not share one wavelength grid");
+        xi.assign(L.ir_lam, L.ir_lam + L.nir);
+        for (size_t i = 0; i + 1 < xi.size(); ++i)
+            if (!(xi[i + 1] > xi[i])) return Status::error(EGGPHOT_ERR_GRID, "IR wavelength grid is not strictly increasing");
+    }
+
+    // ---- grids
+    if (P.has_bulge) {
+        P.grid_bulge.x = xo;
+        st = make_grid_thresholds(P.grid_bulge, P.apply_igm, "optical");
+        if (!st.ok()) return st;
+    }
+    if (P.disk_mode == DISK_OPT) P.grid_disk.x = xo;
+    else if (P.disk_mode == DISK_IR) P.grid_disk.x = xi;
+    else { // union grid of merge_add: equal abscissae collapse into one node (egg-utils.hpp:55-60)
+        P.grid_disk.x.resize(xo.size() + xi.size());
+        auto e = std::set_union(xo.begin(), xo.end(), xi.begin(), xi.end(), P.grid_disk.x.begin());
+        P.grid_disk.x.resize(e - P.grid_disk.x.begin());
+    }
+    st = make_grid_thresholds(P.grid_disk, P.apply_igm, P.disk_mode == DISK_IR ? "IR" : "disk");
+    if (!st.ok()) return st;
+
+    // ---- template rows  Y = x * L(x)
+    auto resample = [&](const std::vector<double> &xs, const double *ys, const Grid &g, double *dst) {
+        for (int j = 0; j < g.n(); ++j) dst[j] = g.x[j] * curve_at(xs, ys, g.x[j]);
+    };
+    std::vector<double> tmp;
+    if (!opts.no_stellar) {
+        const int nb = P.grid_bulge.n();
+        P.rows_bulge_opt.assign((size_t)P.nopt_sed * nb, 0.0);
+        if (P.disk_mode != DISK_IR) P.rows_disk_opt.assign((size_t)P.nopt_sed * P.grid_disk.n(), 0.0);
+        tmp.resize(P.nopt);
+        for (uint32_t s = 0; s < P.nopt_sed; ++s) {
+            if (!P.opt_use[s]) continue;
+            for (uint32_t l = 0; l < P.nopt; ++l) tmp[l] = P.opt_sed[(size_t)s * P.nopt + l];
+            for (int j = 0; j < nb; ++j) P.rows_bulge_opt[(size_t)s * nb + j] = xo[j] * tmp[j];
+            if (P.disk_mode == DISK_OPT)
+                std::copy_n(&P.rows_bulge_opt[(size_t)s * nb], nb, &P.rows_disk_opt[(size_t)s * nb]);
+            else if (P.disk_mode == DISK_BOTH)
+                resample(xo, tmp.data(), P.grid_disk, &P.rows_disk_opt[(size_t)s * P.grid_disk.n()]);
+        }
+    }
+    if (!opts.no_dust) {
+        const int nd = P.grid_disk.n();
+        P.rows_disk_ir.assign((size_t)P.nir_sed * nd, 0.0);
+        if (P.ir_kind == EGGPHOT_IR_CS17) P.rows_disk_pah.assign((size_t)P.nir_sed * nd, 0.0);
+        for (uint32_t s = 0; s < P.nir_sed; ++s) {
+            resample(xi, L.ir_sed + (size_t)s * P.nir, P.grid_disk, &P.rows_disk_ir[(size_t)s * nd]);
+            if (P.ir_kind == EGGPHOT_IR_CS17)
+                resample(xi, L.ir_pah + (size_t)s * P.nir, P.grid_disk, &P.rows_disk_pah[(size_t)s * nd]);
+        }
+    }
+
+    // ---- band tables, packed into groups under the shared-memory budget
+    const size_t budget = opts.smem_table_budget ? opts.smem_table_budget
+                                                 : (P.precision == EGGPHOT_FP64 ? 120u * 1024 : 72u * 1024);
+    const size_t hard_cap = 190u * 1024;
+    const int bfac = P.precision == EGGPHOT_FP64 ? 1 : 2;
+    std::vector<BandTableD> tabs(P.bands.size());
+    for (size_t b = 0; b < P.bands.size(); ++b) {
+        st = build_band_table(P.bands[b], (uint32_t)b, bfac, tabs[b]);
+        if (!st.ok()) return st;
+        if (band_bytes(tabs[b], P.precision) + sizeof(BandHeader) > hard_cap)
+            return Status::error(EGGPHOT_ERR_UNSUPPORTED, "filter " + std::to_string(P.band_order[b]) +
+                                 " has too many nodes for the shared-memory band tables");
+    }
+    size_t b0 = 0;
+    while (b0 < tabs.size()) {
+        size_t b1 = b0, bytes = 0;
+        while (b1 < tabs.size()) {
+            const size_t add = band_bytes(tabs[b1], P.precision) + sizeof(BandHeader);
+            if (b1 > b0 && bytes + add > budget) break;
+            bytes += add;
+            ++b1;
+        }
+        BandGroup g;
+        g.blob.assign((b1 - b0) * sizeof(BandHeader), 0);
+        for (size_t b = b0; b < b1; ++b) {
+            g.cols.push_back((uint32_t)b);
+            append_band(g.blob, (b - b0) * sizeof(BandHeader), tabs[b], P.precision);
+        }
+        P.groups.push_back(std::move(g));
+        b0 = b1;
+    }
+
+    // ---- rest-frame weights
+    for (size_t b = 0; b < P.rfbands.size(); ++b) {
+        BandTableD t;
+        st = build_band_table(P.rfbands[b], (uint32_t)b, 2, t);
+        if (!st.ok()) return st;
+        P.rf_bulge.push_back(P.has_bulge ? rf_weights(t, P.grid_bulge) : RfWeights());
+        P.rf_disk.push_back(rf_weights(t, P.grid_disk));
+    }
+    return Status();
+}
+
+} // namespace eggphot

@@ -1,0 +1,188 @@
+// emul.cpp — TEST-ONLY sequential walk of the device algorithm on the host.
+//
+// Not part of the product and never loaded by egg_b200/: it exists so that the table builder
+// (phot_tables.cpp) and the interval arithmetic (phot_core.cuh) — the exact code the CUDA kernels
+// compile — can be checked against the oracle in the CPU-only test tier, in both arithmetic
+// modes, before any GPU time is spent.  The warp orchestration of phot_kernels.cu (passes,
+// shuffles, reductions) is replaced by plain loops; everything numeric is shared.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../egg_b200/csrc/phot_tables.hpp"
+
+using namespace eggphot;
+
+namespace {
+
+template <typename real> struct Pos;
+template <> struct Pos<float> {
+    static float at(const Grid &g, int j, double opz, float fc) {
+        const float hi = (float)g.x[j], lo = (float)(g.x[j] - (double)hi);
+        const float oh = (float)opz, ol = (float)(opz - (double)oh);
+        return node_pos(hi, lo, oh, ol, fc);
+    }
+};
+template <> struct Pos<double> {
+    static double at(const Grid &g, int j, double opz, double fc) { return node_pos(g.x[j], opz, fc); }
+};
+
+int last_le(const std::vector<double> &x, double v) {
+    return (int)(std::upper_bound(x.begin(), x.end(), v) - x.begin()) - 1;
+}
+
+void add_lines(const Prepared &P, const Grid &g, std::vector<double> &S, const float *ll, double vdisp, double inv) {
+    const int n = g.n(), nl = (int)P.line_lambda.size();
+    std::vector<int> b0(nl, 1), b1(nl, 0);
+    for (int l = 0; l < nl; ++l) {
+        if (ll[l] == 0.0f) continue;
+        const double l0 = P.line_lambda[l], lw = l0 * (vdisp / 2.998e5);
+        int lo = last_le(g.x, l0 - 10 * lw), hi = last_le(g.x, l0 + 10 * lw) + 1;
+        if (hi == 0 || lo == n - 1) continue;
+        b0[l] = lo < 0 ? 0 : lo;
+        b1[l] = hi >= n ? n - 1 : hi;
+    }
+    for (int l = 0; l < nl; ++l)
+        for (int j = b0[l]; j <= b1[l]; ++j) {
+            bool owner = true;
+            for (int k = 0; k < l; ++k) owner = owner && !(b0[k] <= j && j <= b1[k]);
+            if (!owner) continue;
+            const double xj = g.x[j], xm = j > 0 ? g.x[j - 1] : 0.0, xp = j < n - 1 ? g.x[j + 1] : 0.0;
+            const double llow = j != 0 ? 0.5 * (xm + xj) : xj - 0.5 * (xp - xj);
+            const double lup = j != n - 1 ? 0.5 * (xj + xp) : xj + 0.5 * (xj - xm);
+            double acc = 0;
+            for (int k = l; k < nl; ++k)
+                if (b0[k] <= j && j <= b1[k]) {
+                    const double l0 = P.line_lambda[k], lw = l0 * (vdisp / 2.998e5);
+                    acc += line_bin(llow, lup, l0, lw, (double)ll[k] * l0, P.line_profile == EGGPHOT_LINE_AVERAGE);
+                }
+            S[j] += xj * acc * inv;
+        }
+}
+
+template <typename real>
+void run(const Prepared &P, const eggphot_galaxies &G, size_t ngal, double *fd, double *fb, double *rd, double *rb) {
+    const size_t nb = P.bands.size(), nrf = P.rfbands.size();
+    const int nl = P.no_nebular ? 0 : (int)P.line_lambda.size();
+    const int nD = P.grid_disk.n(), nB = P.grid_bulge.n();
+    std::vector<double> SDd(nD), SBd(nB);
+    std::vector<real> SD(nD), SB(nB);
+    for (size_t g = 0; g < ngal; ++g) {
+        const double z = G.z[g], d = G.d[g], opz = 1.0 + z;
+        const double aflux = EGGPHOT_LSUN2UJY * (1.0 + z) / (d * d);
+        const double a_b = P.has_bulge ? std::pow(10.0, (double)(G.m_bulge[g] - G.m2lcor[g])) : 0.0;
+        const double a_d = P.disk_mode != DISK_IR ? std::pow(10.0, (double)(G.m_disk[g] - G.m2lcor[g])) : 0.0;
+        double c1 = 0, c2 = 0;
+        if (P.disk_mode != DISK_OPT) {
+            if (P.ir_kind == EGGPHOT_IR_CS17) { c1 = (1.0 - (double)G.fpah[g]) * G.mdust[g]; c2 = (double)G.fpah[g] * G.mdust[g]; }
+            else c1 = G.lir[g];
+        }
+        float ig[3] = {1, 1, 1};
+        if (P.apply_igm) for (int k = 0; k < 3; ++k) ig[k] = G.igm_abs[3 * g + k];
+        // SEDs in the kernel's real type, built with the kernel's operation order
+        const real ad = (real)a_d, rc1 = (real)c1, rc2 = (real)c2;
+        for (int j = 0; j < nD; ++j) {
+            real v = 0;
+            const size_t ro = P.disk_mode != DISK_IR ? (size_t)G.opt_sed_disk[g] * nD + j : 0;
+            const size_t ri = P.disk_mode != DISK_OPT ? (size_t)G.ir_sed[g] * nD + j : 0;
+            if (P.disk_mode == DISK_BOTH) v = ad * (real)P.rows_disk_opt[ro] + rc1 * (real)P.rows_disk_ir[ri];
+            else if (P.disk_mode == DISK_OPT) v = ad * (real)P.rows_disk_opt[ro];
+            else v = rc1 * (real)P.rows_disk_ir[ri];
+            if (P.disk_mode != DISK_OPT && P.ir_kind == EGGPHOT_IR_CS17) v += rc2 * (real)P.rows_disk_pah[ri];
+            if (P.apply_igm)
+                v *= igm_factor<real>(j, P.grid_disk.lz, P.grid_disk.l0, P.grid_disk.l1, P.grid_disk.l2, ig[0], ig[1], ig[2]);
+            SD[j] = v;
+        }
+        for (int j = 0; j < nB; ++j) {
+            real v = (real)P.rows_bulge_opt[(size_t)G.opt_sed_bulge[g] * nB + j];
+            if (P.apply_igm)
+                v *= igm_factor<real>(j, P.grid_bulge.lz, P.grid_bulge.l0, P.grid_bulge.l1, P.grid_bulge.l2, ig[0], ig[1], ig[2]);
+            SB[j] = v;
+        }
+        if (nl) {
+            for (int j = 0; j < nD; ++j) SDd[j] = 0;
+            add_lines(P, P.grid_disk, SDd, G.line_lum_disk + g * nl, G.vdisp[g], 1.0);
+            for (int j = 0; j < nD; ++j) if (SDd[j] != 0) SD[j] += (real)SDd[j];
+            if (P.has_bulge && G.line_lum_bulge) {
+                for (int j = 0; j < nB; ++j) SBd[j] = 0;
+                add_lines(P, P.grid_bulge, SBd, G.line_lum_bulge + g * nl, G.vdisp[g], a_b > 0 ? 1.0 / a_b : 0.0);
+                for (int j = 0; j < nB; ++j) if (SBd[j] != 0) SB[j] += (real)SBd[j];
+            }
+        }
+        for (const BandGroup &grp : P.groups) {
+            const uint8_t *blob = grp.blob.data();
+            const BandHeader *hdr = reinterpret_cast<const BandHeader *>(blob);
+            for (size_t bi = 0; bi < grp.cols.size(); ++bi) {
+                const BandHeader &h = hdr[bi];
+                for (int comp = P.has_bulge ? 0 : 1; comp < 2; ++comp) {
+                    const Grid &gr = comp ? P.grid_disk : P.grid_bulge;
+                    const std::vector<real> &S = comp ? SD : SB;
+                    const int n = gr.n();
+                    double f = 0;
+                    const bool covered = n >= 2 && gr.x[0] * opz <= h.full_first && gr.x[n - 1] * opz >= h.full_last;
+                    if (covered && h.n >= 2) {
+                        int jlo = std::max(last_le(gr.x, h.eff_first / opz * (1.0 - 1e-15)), 0);
+                        int jhi = (int)(std::lower_bound(gr.x.begin(), gr.x.end(), h.eff_last / opz * (1.0 + 1e-15)) - gr.x.begin());
+                        jhi = std::min(jhi, n - 1);
+                        BandView<real> bv;
+                        make_band_view(blob, h, bv);
+                        CompSum<real> acc;
+                        acc.clear();
+                        NodeState<real> L, R;
+                        if (jhi > jlo) eval_node<real>(bv, Pos<real>::at(gr, jlo, opz, bv.fc), S[jlo], L);
+                        for (int j = jlo; j < jhi; ++j) {
+                            eval_node<real>(bv, Pos<real>::at(gr, j + 1, opz, bv.fc), S[j + 1], R);
+                            acc.add(eval_interval<real>(bv, L, R));
+                            L = R;
+                        }
+                        f = ((double)acc.s + (double)acc.c) * aflux * (comp ? 1.0 : a_b);
+                    }
+                    if (!std::isfinite(f)) f = 0;
+                    (comp ? fd : fb)[g * nb + h.out_col] = f;
+                }
+            }
+        }
+        const double arf = EGGPHOT_LSUN2UJY / (1e-5 * 1e-5);
+        for (size_t r = 0; r < nrf; ++r)
+            for (int comp = P.has_bulge ? 0 : 1; comp < 2; ++comp) {
+                const RfWeights &w = comp ? P.rf_disk[r] : P.rf_bulge[r];
+                const std::vector<real> &S = comp ? SD : SB;
+                CompSum<real> acc;
+                acc.clear();
+                for (size_t k = 0; k < w.w.size(); ++k) acc.add(S[w.j0 + k] * (real)w.w[k]);
+                double fl = w.covered ? ((double)acc.s + (double)acc.c) * arf * (comp ? 1.0 : a_b) : NAN;
+                double m = -2.5 * std::log10(fl) + 23.9;
+                (comp ? rd : rb)[g * nrf + r] = std::isfinite(m) ? m : 99.0;
+            }
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+// Returns 0 on success, else the eggphot status; msg (>= 256 bytes) receives the error text.
+// Outputs are double: component fluxes [ngal][nband] and magnitudes [ngal][nrf] in sorted band order.
+int emul_compute(const eggphot_libs *libs, const eggphot_filters *bands, const eggphot_filters *rfbands,
+                 const eggphot_opts *opts, const eggphot_galaxies *gal, size_t ngal, double *flux_disk,
+                 double *flux_bulge, double *rfmag_disk, double *rfmag_bulge, uint32_t *order, float *lambda, char *msg) {
+    Prepared P;
+    Status st = prepare(*libs, bands, rfbands, *opts, P);
+    if (!st.ok()) {
+        std::strncpy(msg, st.msg.c_str(), 255);
+        msg[255] = 0;
+        return st.code;
+    }
+    for (size_t k = 0; k < P.band_order.size(); ++k) { if (order) order[k] = P.band_order[k]; if (lambda) lambda[k] = P.band_lambda[k]; }
+    if (P.precision == EGGPHOT_FP64) run<double>(P, *gal, ngal, flux_disk, flux_bulge, rfmag_disk, rfmag_bulge);
+    else run<float>(P, *gal, ngal, flux_disk, flux_bulge, rfmag_disk, rfmag_bulge);
+    return 0;
+}
+
+int emul_ngroups(const eggphot_libs *libs, const eggphot_filters *bands, const eggphot_opts *opts) {
+    Prepared P;
+    Status st = prepare(*libs, bands, nullptr, *opts, P);
+    return st.ok() ? (int)P.groups.size() : -st.code;
+}
+}
