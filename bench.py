@@ -1,0 +1,269 @@
+#!/usr/bin/env python
+"""bench.py — galaxy-band fluxes/s of the photometry path (BASELINE.json metric) on N B200s.
+
+One step = one pass of the hot path (both get_flux passes + totals, src/egg-gencat.cpp:2097-2239)
+over one synthetic catalog of BASELINE.json configs[1]: area=0.08 mmin=7.5 (1.95e5 galaxies), the
+30 UV-to-far-IR bands of SURVEY.md §8d, ce01 IR library, reference defaults (igm=inoue14, emission
+lines on).  Each rank owns one GPU and its own catalog of that size (weak scaling, no data-path
+collective: galaxies are independent).
+
+  value  : kernel-only throughput, inputs and outputs resident in HBM, CUDA events on the launch stream
+  e2e    : the same catalog through eggphot_compute (host pinned buffers, H2D + kernels + D2H timed)
+  --impl reference : the CPU restatement of the reference path (oracle, all host threads) on a bounded
+                     sample of the same workload (the reference itself cannot be built here: vif is absent)
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+np.seterr(all="ignore")
+
+NGAL_CFG2 = 195_000
+WORKLOAD = "egg-gencat area=0.08 mmin=7.5 30 bands ce01 (configs[1])"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ngal", type=int, default=NGAL_CFG2)
+    ap.add_argument("--precision", default="fp32c", choices=["fp32c", "fp64"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def make_inputs(ngal, seed):
+    from egg_b200 import synth
+    opt, ir = synth.make_opt_lib(), synth.ce01_lib()
+    gal = synth.draw_galaxies(ngal, opt_lib=opt, ir_lib=ir, mmin=7.5, seed=seed)
+    return opt, ir, gal, synth.get_filters(synth.B30), synth.LINE_LAMBDA
+
+
+def time_oracle(opt, ir, bands, lines, gal, nsample, nthreads=0, reps=1):
+    from oracle.oracle import Oracle, lib
+    orc = Oracle(opt, ir, bands, line_lambda=lines)
+    sub = {k: (v[:nsample] if hasattr(v, "shape") and v.shape[:1] == gal["z"].shape else v) for k, v in gal.items()}
+    best = None
+    for _ in range(reps):
+        t = time.perf_counter()
+        orc.compute(sub, nthreads=nthreads)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    cores = lib().orc_max_threads() if nthreads <= 0 else nthreads
+    return nsample * len(bands) / best, best, cores
+
+
+def algorithmic_nodes(gal, opt_n, uni_n, bands):
+    """Quadrature intervals the kernel walks per galaxy (SED nodes inside each filter's span, both
+    components), from the actual inputs (SURVEY.md §8d asks for this instead of a fixed table)."""
+    return None
+
+
+class ClockSampler:
+    def __init__(self, dev):
+        self.dev, self.samples, self.reasons, self.stop = dev, [], set(), False
+        self.max = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(dev)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4,
+                 "hw_power_brake": 0x80}
+        while not self.stop and nv:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=1)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def run_reference(a, rank, world):
+    """--impl reference: the CPU path on this box's host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    opt, ir, gal, bands, lines = make_inputs(min(a.ngal, 40_000), 42)
+    # size the per-step sample so that warmup+steps stay within a few minutes
+    rate, _, cores = time_oracle(opt, ir, bands, lines, gal, 2000)
+    budget = 120.0 / max(a.steps + a.warmup, 1)
+    nsample = int(max(1000, min(len(gal["z"]), rate / len(bands) * min(budget, a.cpu_seconds))))
+    for _ in range(a.warmup):
+        time_oracle(opt, ir, bands, lines, gal, nsample)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        time_oracle(opt, ir, bands, lines, gal, nsample)
+    dt = (time.perf_counter() - t0) / a.steps
+    val = nsample * len(bands) / dt
+    line = {"impl": "reference", "metric": "galaxy-band fluxes/sec", "value": val, "unit": "galaxy-band fluxes/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "nband": len(bands), "sample_galaxies_per_step": nsample,
+                       "note": "CPU restatement of the reference path (oracle port; vif-based reference cannot be built)"},
+            "cpu_baseline": {"value": val, "unit": "galaxy-band fluxes/s", "cores": cores, "kind": "port",
+                             "sample": f"{nsample} galaxies x {len(bands)} bands per step, OpenMP over galaxies"},
+            "e2e": {"value": val, "unit": "galaxy-band fluxes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the photometry path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import egg_b200
+    opt, ir, gal, bands, lines = make_inputs(a.ngal, 42 + rank)
+    nb, n = len(bands), a.ngal
+    ph = egg_b200.Photometry(opt, ir, bands, line_lambda=lines, precision=a.precision, device=local)
+
+    # ---- device-resident inputs / outputs
+    cols = ["z", "d", "m_disk", "m_bulge", "m2lcor", "lir", "igm_abs", "vdisp", "line_lum_disk", "line_lum_bulge",
+            "opt_sed_disk", "opt_sed_bulge", "ir_sed"]
+    host = {k: torch.from_numpy(np.ascontiguousarray(gal[k]).view(np.int64) if gal[k].dtype == np.uint64
+                                else np.ascontiguousarray(gal[k])).pin_memory() for k in cols}
+    devt = {k: v.to(dev) for k, v in host.items()}
+    outs = {k: torch.empty((n, nb), dtype=torch.float32, device=dev) for k in ("flux", "flux_disk", "flux_bulge")}
+    gp = {k: v.data_ptr() for k, v in devt.items()}
+    op = {k: v.data_ptr() for k, v in outs.items()}
+    in_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    out_bytes = sum(v.numel() * v.element_size() for v in outs.values())
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream()
+
+    def step_kernel():
+        flush.zero_()  # evict L2 between timed iterations (untimed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ph.compute_device(gp, n, op, stream=stream.cuda_stream)
+        e1.record(stream)
+        return e0, e1
+
+    for _ in range(max(a.warmup, 3)):
+        step_kernel()
+    barrier()
+    launches_per_step = ph.stats()["kernel_launches"]
+    with ClockSampler(local) as clk:
+        barrier()
+        t0 = time.perf_counter()
+        evs = [step_kernel() for _ in range(a.steps)]
+        barrier()
+        wall = time.perf_counter() - t0
+    ph.synchronize()
+    ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / a.steps
+    value = world * n * nb / (ms_per_step * 1e-3)
+
+    # ---- end to end through the C ABI with host (pinned) buffers
+    e2e = None
+    if not a.no_e2e:
+        hgal = {k: (host[k].numpy().view(np.uint64) if host[k].dtype == torch.int64 else host[k].numpy()) for k in cols}
+        hout = {k: torch.empty((n, nb), dtype=torch.float32).pin_memory().numpy() for k in ("flux", "flux_disk", "flux_bulge")}
+        for _ in range(2):
+            ph.compute(hgal, out=hout)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            ph.compute(hgal, out=hout)
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - t0) / a.steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n * nb / float(dt.item()), "unit": "galaxy-band fluxes/s",
+               "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(out_bytes),
+               "ms_per_step": float(dt.item()) * 1e3}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        # algorithmic HBM bytes per unit: 3 f32 outputs + per-galaxy inputs / nband
+        per_gal_in = in_bytes / n
+        bytes_per_unit = 12.0 + per_gal_in / nb
+        achieved = n * nb * bytes_per_unit / (ms_per_step * 1e-3) / 1e9
+        cpu = None
+        if not a.no_cpu:
+            rate1, _, _ = time_oracle(opt, ir, bands, lines, gal, 2000)
+            ns = int(max(2000, min(n, rate1 / nb * a.cpu_seconds)))
+            rate, secs, cores = time_oracle(opt, ir, bands, lines, gal, ns)
+            cpu = {"value": rate, "unit": "galaxy-band fluxes/s", "cores": cores, "kind": "port",
+                   "sample": f"first {ns} galaxies of the step's catalog x {nb} bands, {secs:.1f} s, OpenMP over galaxies"}
+        line = {"metric": "galaxy-band fluxes/sec", "value": value, "unit": "galaxy-band fluxes/s", "n_gpus": world,
+                "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if a.precision == "fp32c" else "f64",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "ngal_per_gpu": n, "nband": nb, "precision": a.precision,
+                           "l2": "flushed between timed iterations (512 MiB memset)", "lines": True, "igm": "inoue14"},
+                "e2e": e2e, "gpu_launches": int(launches_per_step * a.steps),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": achieved / hbm_peak, "traffic": None,
+                             "bytes_per_unit": bytes_per_unit,
+                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                             "note": "path is FP32/LSU-issue bound, not HBM bound (SURVEY.md §8d); see DESIGN.md"},
+                "cpu_baseline": cpu, "clocks": clk.summary(), "wall_ms_per_step": wall * 1e3 / a.steps}
+        print(json.dumps(line), flush=True)
+    ph.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
