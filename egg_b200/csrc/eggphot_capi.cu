@@ -57,10 +57,11 @@ struct eggphot_ctx {
     cudaStream_t stream = nullptr;
     // prepared tables on the device
     std::vector<DevBuf> blobs;
-    DevBuf xB, xD, xBhi, xBlo, xDhi, xDlo, rowsB, rowsDopt, rowsDir, rowsDpah, opt_use, rfB, rfD, rfW, errflag;
+    DevBuf xB, xD, xBhi, xBlo, xDhi, xDlo, rowsB, rowsDopt, rowsDir, rowsDpah, opt_use, rfB, rfD, rfW, errflag, scratch;
     int strideB = 0, strideD = 0;
     FluxParams base{};
-    std::vector<int> grid_blocks; // per group
+    int grid_blocks = 0;
+    size_t scratch_region_bytes = 0;
     uint64_t launches = 0;
     uint64_t table_bytes = 0;
     Slot slots[kSlots];
@@ -142,28 +143,19 @@ void fill_params(const eggphot_ctx *c, const eggphot_galaxies &g, size_t ngal, c
     p.rfmag_disk_f64 = o.rfmag_disk_f64; p.rfmag_bulge_f64 = o.rfmag_bulge_f64;
 }
 
-int enqueue(eggphot_ctx *c, const eggphot_galaxies &g, size_t ngal, const eggphot_outputs &o, cudaStream_t st) {
+int enqueue(eggphot_ctx *c, const eggphot_galaxies &g, size_t ngal, const eggphot_outputs &o, cudaStream_t st, int region) {
     if (ngal == 0) return EGGPHOT_OK;
     FluxParams p;
     fill_params(c, g, ngal, o, p);
-    const bool want_rf = c->P.rfbands.size() && (o.rfmag || o.rfmag_disk || o.rfmag_bulge || o.rfmag_disk_f64 || o.rfmag_bulge_f64);
-    const size_t ngroups = c->P.groups.size();
-    for (size_t gi = 0; gi < std::max<size_t>(ngroups, 1); ++gi) {
-        if (ngroups == 0 && !want_rf) break;
-        if (ngroups) {
-            p.blob = (const uint8_t *)c->blobs[gi].p;
-            p.blob_bytes = (uint32_t)c->P.groups[gi].blob.size();
-            p.nb = (uint32_t)c->P.groups[gi].cols.size();
-        } else {
-            p.blob = nullptr; p.blob_bytes = 0; p.nb = 0;
-        }
-        p.do_rf = want_rf && gi == 0;
-        int blocks = ngroups ? c->grid_blocks[gi] : c->num_sms;
-        blocks = (int)std::min<size_t>((size_t)blocks, ngal);
-        int e = launch_flux_kernel(p, c->P.precision, blocks, st);
-        if (e != 0) return c->cuda_fail((cudaError_t)e, "flux kernel launch");
-        ++c->launches;
-    }
+    // kernels of different regions may overlap (the two chunk streams of eggphot_compute); each has its own scratch
+    p.scratch = (char *)c->scratch.p + (size_t)region * c->scratch_region_bytes;
+    p.do_rf = c->P.rfbands.size() && (o.rfmag || o.rfmag_disk || o.rfmag_bulge || o.rfmag_disk_f64 || o.rfmag_bulge_f64);
+    if (p.ngroups == 0 && !p.do_rf) return EGGPHOT_OK;
+    const size_t nbatch = (ngal + kBatch - 1) / kBatch;
+    const int blocks = (int)std::min<size_t>((size_t)c->grid_blocks, nbatch);
+    int e = launch_flux_kernel(p, c->P.precision, blocks, st);
+    if (e != 0) return c->cuda_fail((cudaError_t)e, "flux kernel launch");
+    ++c->launches;
     return EGGPHOT_OK;
 }
 
@@ -277,20 +269,29 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
     p.rfB = (const RfDesc *)c->rfB.p; p.rfD = (const RfDesc *)c->rfD.p; p.rfW = c->rfW.p;
     p.error_flag = (int32_t *)c->errflag.p;
 
-    // ---- grid size per group: one persistent CTA per resident slot
-    c->grid_blocks.assign(P.groups.size(), c->num_sms);
+    // ---- band groups, occupancy, scratch
+    if (P.groups.size() > (size_t)kMaxGroups) return c->fail(EGGPHOT_ERR_UNSUPPORTED, "more than 16 band groups; raise smem_table_budget");
+    p.ngroups = (uint32_t)P.groups.size();
+    p.max_blob = 0;
     for (size_t g = 0; g < P.groups.size(); ++g) {
-        FluxParams q = p;
-        q.blob_bytes = (uint32_t)P.groups[g].blob.size();
-        q.nb = (uint32_t)P.groups[g].cols.size();
-        if (q.nb > (uint32_t)kMaxGroupBands) return c->fail(EGGPHOT_ERR_UNSUPPORTED, "more than 64 bands in one group");
-        const size_t smem = flux_kernel_smem(q, P.precision);
+        p.groups[g].blob = (const uint8_t *)c->blobs[g].p;
+        p.groups[g].bytes = (uint32_t)P.groups[g].blob.size();
+        p.groups[g].nb = (uint32_t)P.groups[g].cols.size();
+        if (p.groups[g].nb > (uint32_t)kMaxGroupBands) return c->fail(EGGPHOT_ERR_UNSUPPORTED, "more than 64 bands in one group");
+        p.max_blob = std::max(p.max_blob, p.groups[g].bytes);
+    }
+    {
+        const size_t smem = flux_kernel_smem(p, P.precision);
         if (smem > (size_t)prop.sharedMemPerBlockOptin)
-            return c->fail(EGGPHOT_ERR_UNSUPPORTED, "band group needs " + std::to_string(smem) + " B of shared memory, device offers " +
-                                                     std::to_string(prop.sharedMemPerBlockOptin));
-        const int occ = flux_kernel_max_blocks_per_sm(q, P.precision);
+            return c->fail(EGGPHOT_ERR_UNSUPPORTED, "band tables need " + std::to_string(smem) + " B of shared memory, device offers " +
+                                                     std::to_string(prop.sharedMemPerBlockOptin) + "; lower smem_table_budget");
+        const int occ = flux_kernel_max_blocks_per_sm(p, P.precision);
         if (occ <= 0) return c->fail(EGGPHOT_ERR_CUDA, "flux kernel cannot be resident (occupancy query failed)");
-        c->grid_blocks[g] = c->num_sms * occ;
+        c->grid_blocks = c->num_sms * occ;
+        const size_t rs = P.precision == EGGPHOT_FP64 ? 8 : 4;
+        c->scratch_region_bytes = ((size_t)c->grid_blocks * kBatch * (size_t)(c->strideD + c->strideB) * rs + 255) & ~size_t(255);
+        CK(c->scratch.alloc(c->scratch_region_bytes * (kSlots + 1)));
+        p.scratch = c->scratch.p;
     }
 #undef CK
     c->ready = true;
@@ -330,7 +331,7 @@ int eggphot_compute_device(eggphot_ctx *c, const eggphot_galaxies *gal, size_t n
     cudaError_t e = cudaSetDevice(c->device);
     if (e != cudaSuccess) return c->cuda_fail(e, "cudaSetDevice");
     c->launches = 0;
-    return enqueue(c, *gal, ngal, *out, stream ? (cudaStream_t)stream : c->stream);
+    return enqueue(c, *gal, ngal, *out, (cudaStream_t)stream, 0);
 }
 
 int eggphot_synchronize(eggphot_ctx *c) {
@@ -400,7 +401,7 @@ int eggphot_compute(eggphot_ctx *c, const eggphot_galaxies *gal, size_t ngal, co
         dout.flux_bulge_f64 = out->flux_bulge_f64 ? (double *)s.fb64.p : nullptr;
         dout.rfmag_disk_f64 = out->rfmag_disk_f64 ? (double *)s.rd64.p : nullptr;
         dout.rfmag_bulge_f64 = out->rfmag_bulge_f64 ? (double *)s.rb64.p : nullptr;
-        rc = enqueue(c, dg, n, dout, s.stream);
+        rc = enqueue(c, dg, n, dout, s.stream, 1 + (int)(k % kSlots));
         if (rc) return rc;
         for (const OCol &col : outs)
             if (col.dst && col.elem)

@@ -65,6 +65,7 @@ struct __attribute__((aligned(16))) BandHeader {
     double tot0, tot1;            // band totals of the two prefix tables (see `split`)
     float fcf, nif, ncf, tf0f, tflf, bkt_inv_wf; // f32 mirrors of the above
     float tot0h, tot0l, tot1h, tot1l; // tot0/NI, tot1/NC as hi+lo; hi is a multiple of 2^-23
+    float inv_nif, inv_ncf, ni_ncf, cost; // 1/NI, 1/NC, NI/NC; cost = scheduling weight (typical node count)
     uint32_t n;                   // nodes in the effective span (>= 2), or 0 if the response is identically 0
     uint32_t nbkt;                // buckets
     uint32_t node_off;            // byte offset of the FilterNode array
@@ -73,7 +74,7 @@ struct __attribute__((aligned(16))) BandHeader {
     uint32_t split;               // cells 0..split accumulate from the left end, cells > split from the right
     uint32_t pad[2];
 };
-static_assert(sizeof(BandHeader) == 176, "BandHeader layout");
+static_assert(sizeof(BandHeader) == 192, "BandHeader layout");
 
 template <typename real> struct NodeOf;
 template <> struct NodeOf<float> { typedef FilterNodeF type; };
@@ -130,7 +131,11 @@ EGG_HD float interval_flux(float tl, float tel, float Sl, const NodeQ<float> &ql
                            int il, float tr, float ter, float Sr, const NodeQ<float> &qr, int ir,
                            const BandScal<float> &bs) {
     const float dt = tr - tl;
+#if defined(__CUDA_ARCH__)
+    const float sigma = dt > 0.0f ? __fdividef(Sr - Sl, dt) : 0.0f; // 2 ulp; enters only the slope term
+#else
     const float sigma = dt > 0.0f ? (Sr - Sl) / dt : 0.0f;
+#endif
     // prefix values left of `split` are measured from the band's left end, right of it from the
     // right end (so that a far wing is not differenced against the whole band): an interval that
     // straddles the split adds the band total.  All high parts are multiples of 2^-23 below 1 in
@@ -176,26 +181,20 @@ template <typename real> struct CompSum {
     EGG_HD real value() const { return s + c; }
 };
 
-// Cell lookup: largest i in [0, n-2] with tf[i] <= te, starting from the bucket table.
-// tfget(i) returns tf of node i.  te must lie inside [tf[0], tf[n-1]].
+// Cell lookup: largest i in [0, n-2] with tf[i] <= te.  bkt[k] is the last node at or below the
+// start of bucket k, so the answer is found by a short forward scan from there (buckets are finer
+// than the node spacing on average); the backward guard only fires when the rounding of k lands one
+// bucket too far.  tfget(i) returns tf of node i.  te must lie inside [tf[0], tf[n-1]].
 template <typename real, typename TfGet>
 EGG_HD int find_cell(TfGet tfget, const uint16_t *bkt, int nbkt, real tf0, real inv_w, int n, real te) {
     int k = (int)((te - tf0) * inv_w);
     k = k < 0 ? 0 : (k > nbkt - 1 ? nbkt - 1 : k);
     int lo = bkt[k];
-    int hi = (int)bkt[k + 1] + 1;
-    if (hi > n - 1) hi = n - 1;
-    // rounding of k can be off by one bucket at the bucket edges
-    if (tfget(lo) > te) lo = k > 0 ? bkt[k - 1] : 0;
-    if (hi < n - 1 && tfget(hi) <= te) hi = n - 1;
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (tfget(mid) <= te) lo = mid; else hi = mid;
-    }
     if (lo > n - 2) lo = n - 2;
+    while (lo > 0 && tfget(lo) > te) --lo;
+    while (lo < n - 2 && tfget(lo + 1) <= te) ++lo;
     return lo;
 }
-
 
 // Band seen through the kernel's real type.
 template <typename real> struct BandView {
@@ -208,7 +207,7 @@ template <typename real> struct BandView {
 EGG_HD void make_band_view(const uint8_t *blob, const BandHeader &h, BandView<float> &v) {
     v.nodes = reinterpret_cast<const FilterNodeF *>(blob + h.node_off);
     v.bkt = reinterpret_cast<const uint16_t *>(blob + h.bkt_off);
-    v.bs.ni = h.nif; v.bs.nc = h.ncf; v.bs.inv_ni = 1.0f / h.nif; v.bs.inv_nc = 1.0f / h.ncf; v.bs.ni_nc = h.nif / h.ncf;
+    v.bs.ni = h.nif; v.bs.nc = h.ncf; v.bs.inv_ni = h.inv_nif; v.bs.inv_nc = h.inv_ncf; v.bs.ni_nc = h.ni_ncf;
     v.bs.tot0h = h.tot0h; v.bs.tot0l = h.tot0l; v.bs.tot1h = h.tot1h; v.bs.tot1l = h.tot1l; v.bs.split = (int)h.split;
     v.fc = h.fcf; v.tf0 = h.tf0f; v.tfl = h.tflf; v.bkt_inv_w = h.bkt_inv_wf;
     v.n = (int)h.n; v.nbkt = (int)h.nbkt;

@@ -1,24 +1,21 @@
 // phot_kernels.cu — sm_100a kernels of the photometry path.
 //
-// flux_kernel<real> replaces the two get_flux passes and the totals of src/egg-gencat.cpp:2097-2239
-// for one group of bands.  One persistent CTA walks galaxies g = blockIdx.x, +gridDim.x, ...;
-// per galaxy it
-//   0. derives the per-galaxy scalars ((1+z), K(1+z)/d^2, 10^(M - m2lcor), L_IR ...) and asks the TMA
-//      engine (cp.async.bulk, SASS UBLKCP) for the galaxy's template rows;
-//   1. while those land: finds, per (band, component), the SED nodes overlapping the filter span and
-//      the node windows of the emission lines; then builds the rest-frame SEDs of the disk
-//      (optical + IR on the merge_add grid, IGM applied) and of the bulge in shared memory
-//      (get_opt_sed / get_ir_sed / merge_add / IGM block, src/egg-gencat.cpp:708-712, 2039-2057, 2118-2140);
-//   2. deposits the emission lines (add_emission_line, :2078-2095) with a deterministic owner rule;
-//   3. integrates: 32 lanes = 32 consecutive SED nodes, each lane finds its node's filter cell,
-//      forms the cumulative quantities K0/K1 (phot_core.cuh), gets its right neighbour's by warp
-//      shuffle, and adds the interval's contribution to a compensated per-lane sum; warps split the
-//      galaxy's passes evenly and reduce by shuffle;  rest-frame magnitudes are dot products with
-//      precomputed z = 0 weights (:2150-2158);
-//   4. scales, applies the reference's data conditions (uncovered band -> 0, non-finite mag -> 99),
-//      forms the totals (:2238-2239) and writes the f32 catalog columns.
-// The band tables of the group (filter nodes with prefix sums, bucket index) are staged once per
-// CTA into shared memory by TMA bulk copies.
+// flux_kernel<real> replaces the two get_flux passes and the totals of src/egg-gencat.cpp:2097-2239.
+// One persistent CTA walks batches of kBatch galaxies.  Per batch it
+//   A. derives the per-galaxy scalars ((1+z), K(1+z)/d^2, 10^(M - m2lcor), L_IR ...), builds the
+//      rest-frame SEDs of every disk (optical + IR on the merge_add grid, IGM applied) and bulge
+//      (get_opt_sed / get_ir_sed / merge_add / IGM block, src/egg-gencat.cpp:708-712, 2039-2057,
+//      2118-2140) into a per-CTA scratch that stays in L2, and deposits the emission lines
+//      (add_emission_line, :2078-2095) with a deterministic owner rule;
+//   B. for each band group: stages the group's filter tables (nodes with two-sided prefix sums,
+//      bucket index) into shared memory with TMA bulk copies (cp.async.bulk, SASS UBLKCP); warps pull
+//      (band, component, galaxy) items off a shared counter; an item = 32 lanes on 32 consecutive SED
+//      nodes, each lane finds its node's filter cell, forms the cumulative quantities K0/K1
+//      (phot_core.cuh), gets its right neighbour's by warp shuffle and adds the interval's
+//      contribution to a compensated per-lane sum, reduced by shuffle; rest-frame magnitudes are dot
+//      products with precomputed z = 0 weights (:2150-2158);
+//   C. applies the reference's data conditions (uncovered band -> 0, non-finite mag -> 99), forms
+//      the totals (:2238-2239) and writes the f32 catalog columns with coalesced stores.
 #include "phot_kernels.cuh"
 
 #include <cooperative_groups.h>
@@ -172,295 +169,264 @@ template <> struct GridAcc<double> {
 };
 
 struct SmemLayout {
-    uint32_t blob, bufA, bufB, bufC, bufS, total;
+    uint32_t tab, res, rfres, lb, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(const FluxParams &p, size_t rs) {
+__host__ __device__ inline SmemLayout smem_layout(const FluxParams &p) {
     SmemLayout L;
     auto up = [](size_t v) { return (uint32_t)((v + 127) & ~size_t(127)); };
     uint32_t o = 0;
-    L.blob = o; o += up(p.blob_bytes);
-    const uint32_t rowD = up((size_t)p.strideD * rs), rowB = up((size_t)p.strideB * rs);
-    L.bufA = o; o += rowD;                                   // disk: first row, becomes the disk SED
-    L.bufB = o; if (p.disk_mode == 0) o += rowD;             // disk: IR row when both are present
-    L.bufC = o; if (p.disk_mode != 1 && p.ir_kind == EGGPHOT_IR_CS17) o += rowD; // cs17 PAH row
-    L.bufS = o; if (p.has_bulge) o += rowB;                  // bulge row, becomes the bulge SED
+    L.tab = o; o += up(p.max_blob);                                              // band tables of the current group
+    L.res = o; o += up((size_t)kBatch * p.nband_total * 2 * sizeof(double));     // [gal][col][comp] scaled fluxes
+    L.rfres = o; o += up((size_t)kBatch * p.nrf * 2 * sizeof(double));           // [gal][rf][comp] rest-frame fluxes
+    L.lb = o; o += up((size_t)kBatch * 2 * (p.nline > 0 ? p.nline : 0) * 2 * sizeof(int)); // line windows
     L.total = o;
     return L;
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
+// One persistent CTA carries a batch of kBatch galaxies through phases A (rest-frame SEDs into a
+// per-CTA global scratch that stays in L2), B (for each band group: tables -> shared memory by TMA,
+// warps pull (galaxy, band, component) items off a shared counter and integrate them) and C
+// (totals, data conditions, coalesced stores).
 template <typename real>
 __global__ void __launch_bounds__(kThreads, 1) flux_kernel(const __grid_constant__ FluxParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ GalScal sc[2];
-    __shared__ int it_jlo[kMaxItems], it_jhi[kMaxItems], it_pend[kMaxItems + 1]; // pend: inclusive scan of passes
-    __shared__ CompSum<real> part[kMaxItems + kWarps];
-    __shared__ int ln_b0[2][kMaxLines], ln_b1[2][kMaxLines];
-    __shared__ double rfres[2][16];
-    __shared__ __align__(8) uint64_t bar_tab, bar_rows;
-    __shared__ int total_passes;
+    __shared__ GalScal sc[kBatch];
+    __shared__ __align__(8) uint64_t bar_tab;
+    __shared__ int item_ctr[kMaxGroups];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const SmemLayout L = smem_layout(p, sizeof(real));
-    const uint8_t *blob = smem + L.blob;
-    real *SD = reinterpret_cast<real *>(smem + L.bufA);
-    real *bufB = reinterpret_cast<real *>(smem + L.bufB);
-    real *bufC = reinterpret_cast<real *>(smem + L.bufC);
-    real *SB = reinterpret_cast<real *>(smem + L.bufS);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const SmemLayout L = smem_layout(p);
+    const uint8_t *blob = smem + L.tab;
+    double *res = reinterpret_cast<double *>(smem + L.res);
+    double *rfres = reinterpret_cast<double *>(smem + L.rfres);
+    int *lb = reinterpret_cast<int *>(smem + L.lb); // [gal][comp][line][2]
     const BandHeader *hdr = reinterpret_cast<const BandHeader *>(blob);
     const int ncomp = p.has_bulge ? 2 : 1;
-    const int nitems = (int)p.nb * ncomp;
     const bool cs17 = p.ir_kind == EGGPHOT_IR_CS17;
+    const int nbt = (int)p.nband_total, nrf = p.do_rf ? (int)p.nrf : 0;
+    const int sstride = p.strideD + p.strideB;
+    real *scr = reinterpret_cast<real *>(p.scratch) + (size_t)blockIdx.x * kBatch * sstride;
+    const real *rO = reinterpret_cast<const real *>(p.rowsDopt), *rI = reinterpret_cast<const real *>(p.rowsDir);
+    const real *rP = reinterpret_cast<const real *>(p.rowsDpah), *rB = reinterpret_cast<const real *>(p.rowsB);
 
-    // stage the band tables once per CTA
     if (tid == 0) {
         mbar_init(&bar_tab, 1);
-        mbar_init(&bar_rows, 1);
         fence_mbar_init();
     }
     __syncthreads();
-    if (tid == 0) {
-        mbar_expect_tx(&bar_tab, p.blob_bytes);
-        for (uint32_t o = 0; o < p.blob_bytes; o += 32768u) {
-            const uint32_t n = min(32768u, p.blob_bytes - o);
-            bulk_g2s(smem + L.blob + o, p.blob + o, n, &bar_tab);
-        }
-    }
-    mbar_wait(&bar_tab, 0);
+    uint32_t tab_phase = 0;
+    int loaded = -1;
 
-    uint32_t iter = 0;
-    for (uint64_t g = blockIdx.x; g < p.ngal; g += gridDim.x, ++iter) {
-        const int par = iter & 1;
-        GalScal &s = sc[par];
-        // ---- phase 0: scalars + TMA requests for the template rows
-        if (tid == 0) {
-            gal_scalars(p, g, s);
-            fence_proxy_async(); // order the previous galaxy's generic-proxy accesses before the async writes
-            const uint32_t rbD = (uint32_t)p.strideD * sizeof(real), rbB = (uint32_t)p.strideB * sizeof(real);
-            uint32_t bytes = rbD;
-            if (p.disk_mode == 0) bytes += rbD;
-            if (p.disk_mode != 1 && cs17) bytes += rbD;
-            if (p.has_bulge) bytes += rbB;
-            mbar_expect_tx(&bar_rows, bytes);
-            const real *rO = reinterpret_cast<const real *>(p.rowsDopt), *rI = reinterpret_cast<const real *>(p.rowsDir);
-            const real *rP = reinterpret_cast<const real *>(p.rowsDpah), *rB = reinterpret_cast<const real *>(p.rowsB);
-            if (p.disk_mode == 2) bulk_g2s(SD, rI + (size_t)s.row_i * p.strideD, rbD, &bar_rows);
-            else bulk_g2s(SD, rO + (size_t)s.row_d * p.strideD, rbD, &bar_rows);
-            if (p.disk_mode == 0) bulk_g2s(bufB, rI + (size_t)s.row_i * p.strideD, rbD, &bar_rows);
-            if (p.disk_mode != 1 && cs17) bulk_g2s(bufC, rP + (size_t)s.row_i * p.strideD, rbD, &bar_rows);
-            if (p.has_bulge) bulk_g2s(SB, rB + (size_t)s.row_b * p.strideB, rbB, &bar_rows);
-        }
-        __syncthreads(); // #1: scalars visible
+    const uint64_t nbatch = (p.ngal + kBatch - 1) / kBatch;
+    for (uint64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+        const uint64_t g0 = batch * kBatch;
+        const int ng = (int)min((uint64_t)kBatch, p.ngal - g0);
 
-        // ---- phase 1a: node windows per (band, component); emission-line windows
-        if (tid < nitems) {
-            const int bi = tid / ncomp, comp = p.has_bulge ? (tid % ncomp) : 1; // 0 bulge, 1 disk
-            const BandHeader &h = hdr[bi];
-            const double *x = comp ? p.xD : p.xB;
-            const int n = comp ? p.nD : p.nB;
-            // [vif] sed2flux: NaN (-> flux 0, src/egg-gencat.cpp:2198) unless the SED covers the filter
-            const bool covered = n >= 2 && __ldg(x) * s.opz <= h.full_first && __ldg(x + n - 1) * s.opz >= h.full_last;
-            int jlo = 0, jhi = 0;
-            if (covered && h.n >= 2) {
-                jlo = max(last_le(x, n, h.eff_first / s.opz * (1.0 - 1e-15)), 0);
-                jhi = min(first_ge(x, n, h.eff_last / s.opz * (1.0 + 1e-15)), n - 1);
-            }
-            it_jlo[tid] = jlo;
-            it_jhi[tid] = covered ? jhi : -1; // -1 marks "not covered"
-        } else if (tid >= 128 && tid < 128 + 2 * kMaxLines) {
-            const int c = (tid - 128) / kMaxLines, l = (tid - 128) % kMaxLines; // c: 0 bulge, 1 disk
-            const float *ll = c ? p.line_lum_disk : p.line_lum_bulge;
-            const bool have = c ? true : (bool)p.has_bulge;
-            if (l < p.nline) {
-                int b0 = 1, b1 = 0; // empty
-                if (have && ll != nullptr && ll[g * p.nline + l] != 0.0f) {
-                    const double *x = c ? p.xD : p.xB;
-                    const int n = c ? p.nD : p.nB;
-                    const double l0 = (double)p.line_lambda[l], lw = l0 * (s.vdisp / 2.998e5);
-                    // [vif] bounds(lam, a, b) = {last <= a, first > b}  (src/egg-gencat.cpp:2081-2084)
-                    int lo = last_le(x, n, l0 - 10 * lw);
-                    int hi = last_le(x, n, l0 + 10 * lw) + 1; // first > b, n if none
-                    if (!(hi == 0 || lo == n - 1)) {
-                        b0 = lo < 0 ? 0 : lo;
-                        b1 = hi >= n ? n - 1 : hi;
-                    }
-                }
-                ln_b0[c][l] = b0;
-                ln_b1[c][l] = b1;
-            }
-        }
-        // ---- phase 1b: rest-frame SEDs in place (rows have landed)
-        mbar_wait(&bar_rows, iter & 1);
-        {
+        // ---- phase A1: per-galaxy scalars, one thread per galaxy
+        if (tid < ng) gal_scalars(p, g0 + tid, sc[tid]);
+        if (tid >= 32 && tid < 32 + kMaxGroups) item_ctr[tid - 32] = 0;
+        for (int i = tid; i < ng * nbt * 2; i += kThreads) res[i] = 0.0;
+        __syncthreads();
+
+        // ---- phase A2: rest-frame SEDs (get_opt_sed / get_ir_sed / merge_add / IGM) into the scratch;
+        //      emission-line windows
+        for (int gi = 0; gi < ng; ++gi) {
+            const GalScal &s = sc[gi];
+            real *SD = scr + (size_t)gi * sstride, *SB = SD + p.strideD;
             const real a_d = (real)s.a_disk, c1 = (real)s.c1, c2 = (real)s.c2;
-            const real g0 = s.igm[0], g1 = s.igm[1], g2 = s.igm[2];
+            const real g0f = s.igm[0], g1f = s.igm[1], g2f = s.igm[2];
+            const real *ro = rO + (size_t)s.row_d * p.strideD, *ri = rI + (size_t)s.row_i * p.strideD;
+            const real *rp = rP + (size_t)s.row_i * p.strideD;
             for (int j = tid; j < p.nD; j += kThreads) {
                 real v;
-                if (p.disk_mode == 0) v = a_d * SD[j] + c1 * bufB[j];
-                else if (p.disk_mode == 1) v = a_d * SD[j];
-                else v = c1 * SD[j];
-                if (p.disk_mode != 1 && cs17) v += c2 * bufC[j];
-                if (p.apply_igm) v *= igm_factor<real>(j, p.igmD[0], p.igmD[1], p.igmD[2], p.igmD[3], g0, g1, g2);
+                if (p.disk_mode == 0) v = a_d * __ldg(ro + j) + c1 * __ldg(ri + j);
+                else if (p.disk_mode == 1) v = a_d * __ldg(ro + j);
+                else v = c1 * __ldg(ri + j);
+                if (p.disk_mode != 1 && cs17) v += c2 * __ldg(rp + j);
+                if (p.apply_igm) v *= igm_factor<real>(j, p.igmD[0], p.igmD[1], p.igmD[2], p.igmD[3], g0f, g1f, g2f);
                 SD[j] = v;
             }
-            if (p.has_bulge && p.apply_igm)
-                for (int j = tid; j < p.igmB[3]; j += kThreads)
-                    SB[j] *= igm_factor<real>(j, p.igmB[0], p.igmB[1], p.igmB[2], p.igmB[3], g0, g1, g2);
+            if (p.has_bulge) {
+                const real *rb = rB + (size_t)s.row_b * p.strideB;
+                for (int j = tid; j < p.nB; j += kThreads) {
+                    real v = __ldg(rb + j);
+                    if (p.apply_igm) v *= igm_factor<real>(j, p.igmB[0], p.igmB[1], p.igmB[2], p.igmB[3], g0f, g1f, g2f);
+                    SB[j] = v;
+                }
+            }
         }
-        __syncthreads(); // #2
-
-        // ---- phase 2: emission lines; pass bookkeeping
-        if (p.nline) {
-            for (int idx = tid; idx < 2 * p.nline * kLineSlots; idx += kThreads) {
-                const int c = idx / (p.nline * kLineSlots), rem = idx % (p.nline * kLineSlots);
-                const int l = rem / kLineSlots, w = rem % kLineSlots;
-                const float *ll = c ? p.line_lum_disk : p.line_lum_bulge;
-                if (ll == nullptr || (c == 0 && !p.has_bulge)) continue;
+        for (int idx = tid; idx < ng * 2 * p.nline; idx += kThreads) {
+            const int gi = idx / (2 * p.nline), rem = idx % (2 * p.nline);
+            const int c = rem / p.nline, l = rem % p.nline; // c: 0 bulge, 1 disk
+            const GalScal &s = sc[gi];
+            const float *ll = c ? p.line_lum_disk : p.line_lum_bulge;
+            int b0 = 1, b1 = 0; // empty
+            if ((c || p.has_bulge) && ll != nullptr && ll[(g0 + gi) * p.nline + l] != 0.0f) {
                 const double *x = c ? p.xD : p.xB;
                 const int n = c ? p.nD : p.nB;
-                real *S = c ? SD : SB;
-                // bulge SED carries no mass scale (applied at the end), so its line term is divided by it
-                const double inv = c ? 1.0 : (s.a_bulge > 0 ? 1.0 / s.a_bulge : 0.0);
-                for (int j = ln_b0[c][l] + w; j <= ln_b1[c][l]; j += kLineSlots) {
-                    bool owner = true; // the first line whose window holds node j adds all of them, in order
-                    for (int k = 0; k < l; ++k) owner = owner && !(ln_b0[c][k] <= j && j <= ln_b1[c][k]);
-                    if (!owner) continue;
-                    const double xj = __ldg(x + j);
-                    const double xm = j > 0 ? __ldg(x + j - 1) : 0.0, xp = j < n - 1 ? __ldg(x + j + 1) : 0.0;
-                    const double llow = j != 0 ? 0.5 * (xm + xj) : xj - 0.5 * (xp - xj);       // :2090
-                    const double lup = j != n - 1 ? 0.5 * (xj + xp) : xj + 0.5 * (xj - xm);   // :2091
-                    double acc = 0.0;
-                    for (int k = l; k < p.nline; ++k) {
-                        if (ln_b0[c][k] <= j && j <= ln_b1[c][k]) {
-                            const double l0 = (double)p.line_lambda[k], lw = l0 * (s.vdisp / 2.998e5);
-                            acc += line_bin(llow, lup, l0, lw, (double)ll[g * p.nline + k] * l0, p.line_average);
-                        }
-                    }
-                    S[j] += (real)(xj * acc * inv);
+                const double l0 = (double)p.line_lambda[l], lw = l0 * (s.vdisp / 2.998e5);
+                // [vif] bounds(lam, a, b) = {last <= a, first > b}  (src/egg-gencat.cpp:2081-2084)
+                const int lo = last_le(x, n, l0 - 10 * lw);
+                const int hi = last_le(x, n, l0 + 10 * lw) + 1; // first > b, n if none
+                if (!(hi == 0 || lo == n - 1)) {
+                    b0 = lo < 0 ? 0 : lo;
+                    b1 = hi >= n ? n - 1 : hi;
                 }
             }
+            lb[2 * idx] = b0;
+            lb[2 * idx + 1] = b1;
         }
-        if (warp == kWarps - 1) { // inclusive scan of the pass counts (31 intervals per pass)
-            int carry = 0;
-            for (int base = 0; base < nitems; base += 32) {
-                const int it = base + lane;
-                int np = 0;
-                if (it < nitems && it_jhi[it] > it_jlo[it]) np = (it_jhi[it] - it_jlo[it] + 30) / 31;
-                int v = np;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int u = __shfl_up_sync(kFull, v, o);
-                    if (lane >= o) v += u;
-                }
-                if (it < nitems) it_pend[it] = carry + v;
-                carry += __shfl_sync(kFull, v, 31);
-            }
-            if (lane == 0) total_passes = carry;
-        }
-        __syncthreads(); // #3
+        __syncthreads();
 
-        // ---- phase 3: quadrature
-        {
-            const int P = total_passes;
-            const int per = (P + kWarps - 1) / kWarps;
-            int pcur = warp * per;
-            const int pstop = min(pcur + per, P);
-            GridAcc<real> gaB, gaD;
-            if constexpr (sizeof(real) == 4) {
-                const float oh = (float)s.opz, ol = (float)(s.opz - (double)oh);
-                gaB.hi = p.xBhi; gaB.lo = p.xBlo; gaB.opz_hi = oh; gaB.opz_lo = ol;
-                gaD.hi = p.xDhi; gaD.lo = p.xDlo; gaD.opz_hi = oh; gaD.opz_lo = ol;
-            } else {
-                gaB.x = p.xB; gaB.opz = s.opz;
-                gaD.x = p.xD; gaD.opz = s.opz;
-            }
-            int it = 0;
-            if (pcur < pstop) { // first item with pend > pcur
-                int cnt = 0;
-                for (int base = 0; base < nitems; base += 32) {
-                    const int k = base + lane;
-                    cnt += __popc(__ballot_sync(kFull, k < nitems && it_pend[k] <= pcur));
+        // ---- phase A3: emission lines (add_emission_line, src/egg-gencat.cpp:2078-2095).  The first line
+        //      whose window holds node j adds the contributions of all lines at j, in line order: no two
+        //      threads touch the same node and the sum order is fixed.
+        for (int idx = tid; idx < ng * 2 * p.nline * kLineSlots; idx += kThreads) {
+            const int w = idx % kLineSlots, q = idx / kLineSlots; // q = (gi, c, l)
+            const int gi = q / (2 * p.nline), rem = q % (2 * p.nline);
+            const int c = rem / p.nline, l = rem % p.nline;
+            const int *wb = lb + 2 * (gi * 2 + c) * p.nline; // windows of this (galaxy, component)
+            const int b0 = wb[2 * l], b1 = wb[2 * l + 1];
+            if (b0 + w > b1) continue;
+            const GalScal &s = sc[gi];
+            const float *ll = (c ? p.line_lum_disk : p.line_lum_bulge) + (g0 + gi) * p.nline;
+            const double *x = c ? p.xD : p.xB;
+            const int n = c ? p.nD : p.nB;
+            real *S = scr + (size_t)gi * sstride + (c ? 0 : p.strideD);
+            // the bulge SED carries no mass scale (applied at the end), so its line term is divided by it
+            const double inv = c ? 1.0 : (s.a_bulge > 0 ? 1.0 / s.a_bulge : 0.0);
+            for (int j = b0 + w; j <= b1; j += kLineSlots) {
+                bool owner = true;
+                for (int k = 0; k < l; ++k) owner = owner && !(wb[2 * k] <= j && j <= wb[2 * k + 1]);
+                if (!owner) continue;
+                const double xj = __ldg(x + j);
+                const double xm = j > 0 ? __ldg(x + j - 1) : 0.0, xp = j < n - 1 ? __ldg(x + j + 1) : 0.0;
+                const double llow = j != 0 ? 0.5 * (xm + xj) : xj - 0.5 * (xp - xj);       // :2090
+                const double lup = j != n - 1 ? 0.5 * (xj + xp) : xj + 0.5 * (xj - xm);   // :2091
+                double acc = 0.0;
+                for (int k = l; k < p.nline; ++k) {
+                    if (wb[2 * k] <= j && j <= wb[2 * k + 1]) {
+                        const double l0 = (double)p.line_lambda[k], lw = l0 * (s.vdisp / 2.998e5);
+                        acc += line_bin(llow, lup, l0, lw, (double)ll[k] * l0, p.line_average);
+                    }
                 }
-                it = cnt;
+                S[j] += (real)(xj * acc * inv);
             }
-            while (pcur < pstop) {
-                while (it_pend[it] <= pcur) ++it;
-                const int pbeg = it ? it_pend[it - 1] : 0;
-                const int pend = min(it_pend[it], pstop);
-                const int bi = it / ncomp, comp = p.has_bulge ? (it % ncomp) : 1;
-                BandView<real> bv;
-                make_band_view(blob, hdr[bi], bv);
-                const real *S = comp ? SD : SB;
-                const GridAcc<real> &ga = comp ? gaD : gaB;
-                const int jlo = it_jlo[it], jhi = it_jhi[it];
-                CompSum<real> acc;
-                acc.clear();
-                for (int k = pcur - pbeg; k < pend - pbeg; ++k) {
-                    int j = jlo + 31 * k + lane;
-                    const bool live = lane < 31 && j < jhi;
-                    j = min(j, jhi);
-                    NodeState<real> nl, nr;
-                    eval_node<real>(bv, ga.pos(j, bv.fc), S[j], nl);
-                    shfl_node(nl, nr);
-                    const real T = eval_interval<real>(bv, nl, nr);
-                    if (live) acc.add(T);
+        }
+        __syncthreads();
+
+        // ---- phase B: band groups
+        for (int grp = 0; grp < (int)p.ngroups || (grp == 0 && nrf > 0); ++grp) {
+            const int nb = grp < (int)p.ngroups ? (int)p.groups[grp].nb : 0;
+            if (nb > 0 && loaded != grp) {
+                if (tid == 0) {
+                    fence_proxy_async(); // earlier generic-proxy reads of the table region precede the async writes
+                    const uint32_t bytes = p.groups[grp].bytes;
+                    mbar_expect_tx(&bar_tab, bytes);
+                    for (uint32_t o = 0; o < bytes; o += 32768u)
+                        bulk_g2s(smem + L.tab + o, p.groups[grp].blob + o, min(32768u, bytes - o), &bar_tab);
                 }
-                acc = warp_reduce(acc);
-                if (lane == 0) part[it + warp] = acc;
-                pcur = pend;
+                mbar_wait(&bar_tab, tab_phase);
+                tab_phase ^= 1;
+                loaded = grp;
             }
-            // rest-frame magnitudes: dot products with the z = 0 weights
-            if (p.do_rf) {
-                for (int r = warp; r < (int)p.nrf * ncomp; r += kWarps) {
-                    const int rb = r / ncomp, comp = p.has_bulge ? (r % ncomp) : 1;
+            const int nband_items = nb * ncomp * ng;
+            const int nitems = nband_items + (grp == 0 ? nrf * ncomp * ng : 0);
+            for (;;) {
+                int idx = 0;
+                if (lane == 0) idx = atomicAdd(&item_ctr[grp], 1);
+                idx = __shfl_sync(kFull, idx, 0);
+                if (idx >= nitems) break;
+                if (idx < nband_items) {
+                    // (band, component, galaxy): bands are stored in decreasing order of expected work
+                    const int gi = idx % ng, t2 = idx / ng;
+                    const int comp = p.has_bulge ? (t2 % ncomp) : 1, bi = t2 / ncomp; // comp: 0 bulge, 1 disk
+                    const BandHeader &h = hdr[bi];
+                    const GalScal &s = sc[gi];
+                    const double *x = comp ? p.xD : p.xB;
+                    const int n = comp ? p.nD : p.nB;
+                    // [vif] sed2flux: NaN (-> flux 0, src/egg-gencat.cpp:2198) unless the SED covers the filter
+                    const bool covered = n >= 2 && __ldg(x) * s.opz <= h.full_first && __ldg(x + n - 1) * s.opz >= h.full_last;
+                    if (!covered || h.n < 2) continue;
+                    int jb = 0;
+                    if (lane == 0) jb = max(last_le(x, n, h.eff_first / s.opz * (1.0 - 1e-15)), 0);
+                    if (lane == 1) jb = min(first_ge(x, n, h.eff_last / s.opz * (1.0 + 1e-15)), n - 1);
+                    const int jlo = __shfl_sync(kFull, jb, 0), jhi = __shfl_sync(kFull, jb, 1);
+                    if (jhi <= jlo) continue;
+                    BandView<real> bv;
+                    make_band_view(blob, h, bv);
+                    const real *S = scr + (size_t)gi * sstride + (comp ? 0 : p.strideD);
+                    GridAcc<real> ga;
+                    if constexpr (sizeof(real) == 4) {
+                        const float oh = (float)s.opz;
+                        ga.hi = comp ? p.xDhi : p.xBhi; ga.lo = comp ? p.xDlo : p.xBlo;
+                        ga.opz_hi = oh; ga.opz_lo = (float)(s.opz - (double)oh);
+                    } else {
+                        ga.x = x; ga.opz = s.opz;
+                    }
+                    CompSum<real> acc;
+                    acc.clear();
+                    int j = min(jlo + lane, jhi);
+                    real tc = ga.pos(j, bv.fc), Sc = S[j];
+                    for (int jbase = jlo; jbase < jhi; jbase += 31) {
+                        const bool live = lane < 31 && jbase + lane < jhi;
+                        // next pass's inputs first: their latency hides behind this pass's arithmetic
+                        const int jn = min(jbase + 31 + lane, jhi);
+                        const real tn = ga.pos(jn, bv.fc), Sn = S[jn];
+                        NodeState<real> nl, nr;
+                        eval_node<real>(bv, tc, Sc, nl);
+                        shfl_node(nl, nr);
+                        const real T = eval_interval<real>(bv, nl, nr);
+                        if (live) acc.add(T);
+                        tc = tn; Sc = Sn;
+                    }
+                    acc = warp_reduce(acc);
+                    if (lane == 0) {
+                        double f = ((double)acc.s + (double)acc.c) * s.aflux * (comp ? 1.0 : s.a_bulge);
+                        if (!isfinite(f)) f = 0.0; // src/egg-gencat.cpp:2198
+                        res[(gi * nbt + (int)h.out_col) * 2 + comp] = f;
+                    }
+                } else {
+                    // rest-frame magnitude: dot product with the z = 0 weights (src/egg-gencat.cpp:2150-2158)
+                    const int r = idx - nband_items;
+                    const int gi = r % ng, t2 = r / ng;
+                    const int comp = p.has_bulge ? (t2 % ncomp) : 1, rb = t2 / ncomp;
                     const RfDesc dsc = comp ? p.rfD[rb] : p.rfB[rb];
-                    const real *S = comp ? SD : SB;
+                    const real *S = scr + (size_t)gi * sstride + (comp ? 0 : p.strideD);
                     const real *W = reinterpret_cast<const real *>(p.rfW) + dsc.off;
                     CompSum<real> acc;
                     acc.clear();
                     for (int k = lane; k < dsc.n; k += 32) acc.add(S[dsc.j0 + k] * __ldg(W + k));
                     acc = warp_reduce(acc);
                     if (lane == 0)
-                        rfres[comp][rb] = dsc.covered ? (double)acc.s + (double)acc.c : __longlong_as_double(0x7ff8000000000000LL);
+                        rfres[(gi * nrf + rb) * 2 + comp] = dsc.covered ? ((double)acc.s + (double)acc.c) * (comp ? 1.0 : sc[gi].a_bulge)
+                                                                         : __longlong_as_double(0x7ff8000000000000LL);
                 }
             }
+            __syncthreads(); // every item of the group is done; the table region may be overwritten
         }
-        __syncthreads(); // #4
 
-        // ---- phase 4: scale, data conditions, totals, store
-        if (tid < (int)p.nb) {
-            const int P = total_passes, per = max((P + kWarps - 1) / kWarps, 1);
-            double f[2] = {0.0, 0.0};
-            for (int comp = p.has_bulge ? 0 : 1; comp < 2; ++comp) {
-                const int it = p.has_bulge ? tid * 2 + comp : tid;
-                const int pbeg = it ? it_pend[it - 1] : 0, pend = it_pend[it];
-                if (pend > pbeg) {
-                    CompSum<real> tot;
-                    tot.clear();
-                    for (int w = pbeg / per; w <= (pend - 1) / per; ++w) tot.add(part[it + w]);
-                    f[comp] = ((double)tot.s + (double)tot.c) * s.aflux * (comp ? 1.0 : s.a_bulge);
-                }
-                if (!isfinite(f[comp])) f[comp] = 0.0; // src/egg-gencat.cpp:2198
-            }
-            const size_t o = (size_t)g * p.nband_total + hdr[tid].out_col;
-            const float fd = (float)f[1], fb = (float)f[0];
+        // ---- phase C: totals (src/egg-gencat.cpp:2238-2239) and coalesced stores
+        for (int i = tid; i < ng * nbt; i += kThreads) {
+            const float fb = (float)res[2 * i], fd = (float)res[2 * i + 1];
+            const size_t o = (size_t)g0 * nbt + i;
             if (p.flux_disk) p.flux_disk[o] = fd;
             if (p.flux_bulge) p.flux_bulge[o] = fb;
-            if (p.flux) p.flux[o] = fd + fb; // vec2f sum (src/egg-gencat.cpp:2238)
-            if (p.flux_disk_f64) p.flux_disk_f64[o] = f[1];
-            if (p.flux_bulge_f64) p.flux_bulge_f64[o] = f[0];
-        } else if (p.do_rf && tid >= 64 && tid < 64 + (int)p.nrf) {
-            const int rb = tid - 64;
+            if (p.flux) p.flux[o] = fd + fb; // vec2f sum
+            if (p.flux_disk_f64) p.flux_disk_f64[o] = res[2 * i + 1];
+            if (p.flux_bulge_f64) p.flux_bulge_f64[o] = res[2 * i];
+        }
+        for (int i = tid; i < ng * nrf; i += kThreads) {
             // [vif] lsun2uJy(0, 1e-5, ...) then uJy2mag; non-finite -> +99 (src/egg-gencat.cpp:2152-2156)
             const double arf = EGGPHOT_LSUN2UJY / (1e-5 * 1e-5);
-            double mg[2] = {0.0, 0.0};
+            double mg[2] = {0.0, 0.0}; // the bulge column stays 0 when there is no bulge pass (no_stellar)
             for (int comp = p.has_bulge ? 0 : 1; comp < 2; ++comp) {
-                const double fl = rfres[comp][rb] * arf * (comp ? 1.0 : s.a_bulge);
-                const double m = -2.5 * log10(fl) + 23.9;
+                const double m = -2.5 * log10(rfres[2 * i + comp] * arf) + 23.9;
                 mg[comp] = isfinite(m) ? m : 99.0;
             }
-            const size_t o = (size_t)g * p.nrf + rb;
-            const float md = (float)mg[1], mb = (float)mg[0]; // bulge column stays 0 when there is no bulge pass
+            const size_t o = (size_t)g0 * nrf + i;
+            const float md = (float)mg[1], mb = (float)mg[0];
             if (p.rfmag_disk) p.rfmag_disk[o] = md;
             if (p.rfmag_bulge) p.rfmag_bulge[o] = mb;
             if (p.rfmag) // uJy2mag(mag2uJy(disk) + mag2uJy(bulge)) on the f32 columns (src/egg-gencat.cpp:2239)
@@ -468,8 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1) flux_kernel(const __grid_constant
             if (p.rfmag_disk_f64) p.rfmag_disk_f64[o] = mg[1];
             if (p.rfmag_bulge_f64) p.rfmag_bulge_f64[o] = mg[0];
         }
-        // no barrier needed here: the next iteration writes the other parity of sc[], and everything
-        // else it touches before its barrier #1 (TMA into the row buffers) is ordered by barrier #4
+        __syncthreads(); // res / sc are rewritten by the next batch
     }
 }
 
@@ -547,9 +512,7 @@ __global__ void __launch_bounds__(256) sed_kernel(const __grid_constant__ SedPar
 
 } // namespace
 
-size_t flux_kernel_smem(const FluxParams &p, int precision) {
-    return smem_layout(p, precision == EGGPHOT_FP64 ? 8 : 4).total;
-}
+size_t flux_kernel_smem(const FluxParams &p, int) { return smem_layout(p).total; }
 
 template <typename real> static int launch_t(const FluxParams &p, size_t smem, int blocks, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(flux_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -13,6 +13,14 @@ constexpr int kMaxLines = 64;
 constexpr int kMaxGroupBands = 64;
 constexpr int kThreads = 512;          // 16 warps per CTA
 constexpr int kWarps = kThreads / 32;
+constexpr int kBatch = 16;             // galaxies a CTA carries through all band groups at a time
+constexpr int kMaxGroups = 16;
+constexpr int kMaxRf = 16;
+
+struct GroupDesc {
+    const uint8_t *blob;   // device copy of BandGroup::blob (16-byte aligned)
+    uint32_t bytes, nb;
+};
 
 // sparse rest-frame weights of one rfband on one component grid
 struct RfDesc {
@@ -32,10 +40,12 @@ struct FluxParams {
     float *flux, *flux_disk, *flux_bulge, *rfmag, *rfmag_disk, *rfmag_bulge;
     double *flux_disk_f64, *flux_bulge_f64, *rfmag_disk_f64, *rfmag_bulge_f64;
     uint32_t nband_total, nrf;
-    // band group
-    const uint8_t *blob;   // device copy of BandGroup::blob (16-byte aligned)
-    uint32_t blob_bytes, nb;
-    int32_t do_rf;         // this launch also computes the rest-frame magnitudes
+    // band groups: each is staged into shared memory in turn while a batch of galaxies is resident
+    uint32_t ngroups, max_blob;
+    GroupDesc groups[kMaxGroups];
+    int32_t do_rf;         // also compute the rest-frame magnitudes
+    // per-CTA scratch for the rest-frame SEDs of a batch: [grid][kBatch][strideD + strideB] real (stays in L2)
+    void *scratch;
     // component grids
     int32_t nB, nD;        // nodes (0 if the component is absent)
     int32_t strideB, strideD; // row strides in elements (16-byte multiples)
@@ -58,7 +68,7 @@ struct FluxParams {
 
 // dynamic shared memory the flux kernel needs for these parameters
 size_t flux_kernel_smem(const FluxParams &p, int precision);
-// launches one band group; returns cudaError_t as int
+// launches the flux kernel over all band groups; returns cudaError_t as int
 int launch_flux_kernel(const FluxParams &p, int precision, int grid_blocks, cudaStream_t stream);
 int flux_kernel_max_blocks_per_sm(const FluxParams &p, int precision);
 

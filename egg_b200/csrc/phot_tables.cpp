@@ -83,6 +83,7 @@ Status build_band_table(const Filter &f, uint32_t out_col, int bucket_factor, Ba
         t.h.fc = (double)(float)t.h.full_first;
         t.h.ni = t.h.nc = 1.0;
         t.h.fcf = (float)t.h.fc; t.h.nif = t.h.ncf = 1.0f;
+        t.h.inv_nif = t.h.inv_ncf = t.h.ni_ncf = 1.0f;
         t.nodes.clear();
         t.bkt.assign(2, 0);
         t.h.nbkt = 1;
@@ -159,6 +160,7 @@ Status build_band_table(const Filter &f, uint32_t out_col, int bucket_factor, Ba
     t.h.bkt_inv_w = span > 0 ? nbkt / span : 0.0;
     t.h.fcf = (float)t.h.fc; t.h.nif = (float)t.h.ni; t.h.ncf = (float)t.h.nc;
     t.h.tf0f = (float)t.h.tf0; t.h.tflf = (float)t.h.tfl; t.h.bkt_inv_wf = (float)t.h.bkt_inv_w;
+    t.h.inv_nif = (float)(1.0 / t.h.ni); t.h.inv_ncf = (float)(1.0 / t.h.nc); t.h.ni_ncf = (float)(t.h.ni / t.h.nc);
     t.bkt.assign(nbkt + 1, 0);
     int i = 0;
     for (int k = 0; k <= nbkt; ++k) {
@@ -490,9 +492,8 @@ Status prepare(const eggphot_libs &L, const eggphot_filters *bands, const eggpho
     }
 
     // ---- band tables, packed into groups under the shared-memory budget
-    const size_t budget = opts.smem_table_budget ? opts.smem_table_budget
-                                                 : (P.precision == EGGPHOT_FP64 ? 120u * 1024 : 72u * 1024);
-    const size_t hard_cap = 190u * 1024;
+    const size_t budget = opts.smem_table_budget ? opts.smem_table_budget : 196u * 1024;
+    const size_t hard_cap = 204u * 1024;
     const int bfac = P.precision == EGGPHOT_FP64 ? 1 : 2;
     std::vector<BandTableD> tabs(P.bands.size());
     for (size_t b = 0; b < P.bands.size(); ++b) {
@@ -513,9 +514,19 @@ Status prepare(const eggphot_libs &L, const eggphot_filters *bands, const eggpho
         }
         BandGroup g;
         g.blob.assign((b1 - b0) * sizeof(BandHeader), 0);
+        // inside a group the bands are stored by decreasing expected work (SED nodes under the
+        // filter at z = 1): warps pull items in storage order, long ones first
+        std::vector<size_t> ord;
         for (size_t b = b0; b < b1; ++b) {
-            g.cols.push_back((uint32_t)b);
-            append_band(g.blob, (b - b0) * sizeof(BandHeader), tabs[b], P.precision);
+            const Grid &gd = P.grid_disk;
+            const int lo = last_le(gd.x, tabs[b].h.eff_first / 2.0), hi = last_le(gd.x, tabs[b].h.eff_last / 2.0);
+            tabs[b].h.cost = (float)std::max(hi - lo, 1);
+            ord.push_back(b);
+        }
+        std::stable_sort(ord.begin(), ord.end(), [&](size_t i, size_t j) { return tabs[i].h.cost > tabs[j].h.cost; });
+        for (size_t k = 0; k < ord.size(); ++k) {
+            g.cols.push_back((uint32_t)ord[k]);
+            append_band(g.blob, k * sizeof(BandHeader), tabs[ord[k]], P.precision);
         }
         P.groups.push_back(std::move(g));
         b0 = b1;

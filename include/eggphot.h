@@ -141,7 +141,9 @@ int eggphot_band_order(const eggphot_ctx *ctx, int which, uint32_t *order, float
 int eggphot_compute(eggphot_ctx *ctx, const eggphot_galaxies *gal, size_t ngal, const eggphot_outputs *out);
 
 /* Same computation for columns already resident in DEVICE memory of ctx's device; enqueues on
- * `stream` (a cudaStream_t; NULL = the context's own stream) and returns without synchronising. */
+ * `stream` (a cudaStream_t; NULL = the CUDA legacy default stream) and returns without
+ * synchronising.  Calls on one context must not overlap each other on the device (they share the
+ * context's SED scratch): enqueue them on one stream. */
 int eggphot_compute_device(eggphot_ctx *ctx, const eggphot_galaxies *gal, size_t ngal,
                            const eggphot_outputs *out, void *stream);
 int eggphot_synchronize(eggphot_ctx *ctx);
