@@ -57,7 +57,7 @@ struct eggphot_ctx {
     cudaStream_t stream = nullptr;
     // prepared tables on the device
     std::vector<DevBuf> blobs;
-    DevBuf xB, xD, xBhi, xBlo, xDhi, xDlo, rowsB, rowsDopt, rowsDir, rowsDpah, opt_use, rfB, rfD, rfW, errflag, scratch;
+    DevBuf xB, xD, xBhl, xDhl, lutB, lutD, rowsB, rowsDopt, rowsDir, rowsDpah, opt_use, rfB, rfD, rfW, errflag, scratch;
     int strideB = 0, strideD = 0;
     FluxParams base{};
     int grid_blocks = 0;
@@ -98,17 +98,17 @@ cudaError_t upload_rows(DevBuf &b, const std::vector<double> &rows, size_t nrow,
     return e;
 }
 
-cudaError_t upload_grid(const Grid &g, DevBuf &x, DevBuf &hi, DevBuf &lo, uint64_t &bytes) {
+cudaError_t upload_grid(const Grid &g, DevBuf &x, DevBuf &hl, DevBuf &lut, uint64_t &bytes) {
     if (g.n() == 0) return cudaSuccess;
-    std::vector<float> h(g.n()), l(g.n());
+    std::vector<float> h(2 * (size_t)g.n());
     for (int j = 0; j < g.n(); ++j) {
-        h[j] = (float)g.x[j];
-        l[j] = (float)(g.x[j] - (double)h[j]);
+        h[2 * j] = (float)g.x[j];
+        h[2 * j + 1] = (float)(g.x[j] - (double)h[2 * j]);
     }
     cudaError_t e = x.upload(g.x.data(), g.n() * sizeof(double));
-    if (e == cudaSuccess) e = hi.upload(h.data(), h.size() * sizeof(float));
-    if (e == cudaSuccess) e = lo.upload(l.data(), l.size() * sizeof(float));
-    bytes += x.bytes + hi.bytes + lo.bytes;
+    if (e == cudaSuccess) e = hl.upload(h.data(), h.size() * sizeof(float));
+    if (e == cudaSuccess) e = lut.upload(g.lut.data(), g.lut.size() * sizeof(uint16_t));
+    bytes += x.bytes + hl.bytes + lut.bytes;
     return e;
 }
 
@@ -209,8 +209,8 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
     c->strideB = (P.grid_bulge.n() + per16 - 1) / per16 * per16;
     c->strideD = (P.grid_disk.n() + per16 - 1) / per16 * per16;
 #define CK(x) do { if ((e = (x)) != cudaSuccess) return c->cuda_fail(e, #x); } while (0)
-    CK(upload_grid(P.grid_bulge, c->xB, c->xBhi, c->xBlo, tb));
-    CK(upload_grid(P.grid_disk, c->xD, c->xDhi, c->xDlo, tb));
+    CK(upload_grid(P.grid_bulge, c->xB, c->xBhl, c->lutB, tb));
+    CK(upload_grid(P.grid_disk, c->xD, c->xDhl, c->lutD, tb));
     CK(upload_rows(c->rowsB, P.rows_bulge_opt, P.nopt_sed, P.grid_bulge.n(), c->strideB, P.precision, tb));
     CK(upload_rows(c->rowsDopt, P.rows_disk_opt, P.nopt_sed, P.grid_disk.n(), c->strideD, P.precision, tb));
     CK(upload_rows(c->rowsDir, P.rows_disk_ir, P.nir_sed, P.grid_disk.n(), c->strideD, P.precision, tb));
@@ -254,8 +254,10 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
     p.nB = P.grid_bulge.n(); p.nD = P.grid_disk.n();
     p.strideB = c->strideB; p.strideD = c->strideD;
     p.xB = (const double *)c->xB.p; p.xD = (const double *)c->xD.p;
-    p.xBhi = (const float *)c->xBhi.p; p.xBlo = (const float *)c->xBlo.p;
-    p.xDhi = (const float *)c->xDhi.p; p.xDlo = (const float *)c->xDlo.p;
+    p.xBhl = (const float2 *)c->xBhl.p; p.xDhl = (const float2 *)c->xDhl.p;
+    p.lutB = (const uint16_t *)c->lutB.p; p.lutD = (const uint16_t *)c->lutD.p;
+    p.lutB_n = (int)P.grid_bulge.lut.size(); p.lutD_n = (int)P.grid_disk.lut.size();
+    p.lutB_e0 = P.grid_bulge.lut_e0; p.lutD_e0 = P.grid_disk.lut_e0;
     const Grid &gb = P.grid_bulge, &gd = P.grid_disk;
     p.igmB[0] = gb.lz; p.igmB[1] = gb.l0; p.igmB[2] = gb.l1; p.igmB[3] = gb.l2;
     p.igmD[0] = gd.lz; p.igmD[1] = gd.l0; p.igmD[2] = gd.l1; p.igmD[3] = gd.l2;
@@ -265,7 +267,12 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
     p.ir_kind = P.ir_kind; p.disk_mode = (int)P.disk_mode; p.has_bulge = P.has_bulge; p.apply_igm = P.apply_igm;
     p.nline = P.no_nebular ? 0 : (int)P.line_lambda.size();
     p.line_average = P.line_profile == EGGPHOT_LINE_AVERAGE;
-    for (int l = 0; l < p.nline; ++l) p.line_lambda[l] = P.line_lambda[l];
+    {   // lines sorted by wavelength: their node windows are then ordered too (see phase A3 of the kernel)
+        std::vector<int> ord(p.nline);
+        for (int l = 0; l < p.nline; ++l) ord[l] = l;
+        std::stable_sort(ord.begin(), ord.end(), [&](int i, int j) { return P.line_lambda[i] < P.line_lambda[j]; });
+        for (int l = 0; l < p.nline; ++l) { p.line_lambda[l] = P.line_lambda[ord[l]]; p.line_col[l] = (uint8_t)ord[l]; }
+    }
     p.rfB = (const RfDesc *)c->rfB.p; p.rfD = (const RfDesc *)c->rfD.p; p.rfW = c->rfW.p;
     p.error_flag = (int32_t *)c->errflag.p;
 

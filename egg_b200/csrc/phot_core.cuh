@@ -182,16 +182,19 @@ template <typename real> struct CompSum {
 };
 
 // Cell lookup: largest i in [0, n-2] with tf[i] <= te.  bkt[k] is the last node at or below the
-// start of bucket k, so the answer is found by a short forward scan from there (buckets are finer
-// than the node spacing on average); the backward guard only fires when the rounding of k lands one
-// bucket too far.  tfget(i) returns tf of node i.  te must lie inside [tf[0], tf[n-1]].
+// start of bucket k, so the answer is a short forward scan away (buckets are finer than the node
+// spacing); the backward guard only fires when the rounding of k lands one bucket too far.
+// tfget(i) returns tf of node i.  te must lie inside [tf[0], tf[n-1]].
 template <typename real, typename TfGet>
 EGG_HD int find_cell(TfGet tfget, const uint16_t *bkt, int nbkt, real tf0, real inv_w, int n, real te) {
     int k = (int)((te - tf0) * inv_w);
     k = k < 0 ? 0 : (k > nbkt - 1 ? nbkt - 1 : k);
     int lo = bkt[k];
-    if (lo > n - 2) lo = n - 2;
-    while (lo > 0 && tfget(lo) > te) --lo;
+    lo = lo > n - 2 ? n - 2 : lo;
+    if (tfget(lo) > te) {
+        do { --lo; } while (lo > 0 && tfget(lo) > te);
+        return lo < 0 ? 0 : lo;
+    }
     while (lo < n - 2 && tfget(lo + 1) <= te) ++lo;
     return lo;
 }
@@ -228,6 +231,9 @@ EGG_HD float node_pos(float xhi, float xlo, float opz_hi, float opz_lo, float fc
 }
 EGG_HD double node_pos(double x, double opz, double fc) { return fma(x, opz, -fc); }
 
+EGG_HD float clampr(float t, float lo, float hi) { return fminf(fmaxf(t, lo), hi); }
+EGG_HD double clampr(double t, double lo, double hi) { return fmin(fmax(t, lo), hi); }
+
 // Everything an interval needs to know about one of its end nodes.
 template <typename real> struct NodeState {
     real t;   // true position
@@ -242,7 +248,7 @@ template <typename real>
 EGG_HD void eval_node(const BandView<real> &b, real t, real S, NodeState<real> &ns) {
     ns.t = t;
     ns.S = S;
-    const real te = t < b.tf0 ? b.tf0 : (t > b.tfl ? b.tfl : t);
+    const real te = clampr(t, b.tf0, b.tfl);
     const typename NodeOf<real>::type *nodes = b.nodes;
     int c = find_cell<real>([nodes](int i) { return nodes[i].tf; }, b.bkt, b.nbkt, b.tf0, b.bkt_inv_w, b.n, te);
     const typename NodeOf<real>::type e = nodes[c];
@@ -254,8 +260,8 @@ EGG_HD void eval_node(const BandView<real> &b, real t, real S, NodeState<real> &
 
 template <typename real>
 EGG_HD real eval_interval(const BandView<real> &b, const NodeState<real> &l, const NodeState<real> &r) {
-    const real tel = l.t < b.tf0 ? b.tf0 : (l.t > b.tfl ? b.tfl : l.t);
-    const real ter = r.t < b.tf0 ? b.tf0 : (r.t > b.tfl ? b.tfl : r.t);
+    const real tel = clampr(l.t, b.tf0, b.tfl);
+    const real ter = clampr(r.t, b.tf0, b.tfl);
     return interval_flux(l.t, tel, l.S, l.q, l.s, l.dl, l.u, l.cell, r.t, ter, r.S, r.q, r.cell, b.bs);
 }
 
@@ -269,6 +275,24 @@ EGG_HD real igm_factor(int j, int lz, int l0, int l1, int l2, real a0, real a1, 
 EGG_HD double line_bin(double llow, double lup, double l0, double lw, double amp, int average) {
     const double is = 0.70710678118654752440 / lw;
     const double v = 0.5 * amp * (erf((lup - l0) * is) - erf((llow - l0) * is));
+    return average ? v / (lup - llow) : v;
+}
+
+// The same with the erf difference in the kernel's precision (the arguments are still formed in
+// double: they are differences of nearly equal wavelengths).
+template <typename real> EGG_HD double line_bin_t(double llow, double lup, double l0, double lw, double amp, int average);
+template <> EGG_HD double line_bin_t<double>(double llow, double lup, double l0, double lw, double amp, int average) {
+    return line_bin(llow, lup, l0, lw, amp, average);
+}
+template <> EGG_HD double line_bin_t<float>(double llow, double lup, double l0, double lw, double amp, int average) {
+    const double is = 0.70710678118654752440 / lw;
+    const float a = (float)((lup - l0) * is), b = (float)((llow - l0) * is);
+    // erf(a) - erf(b): use erfc on the far side so that a bin deep in a wing keeps its relative accuracy
+    float d;
+    if (b >= 0.0f) d = erfcf(b) - erfcf(a);
+    else if (a <= 0.0f) d = erfcf(-a) - erfcf(-b);
+    else d = erff(a) - erff(b);
+    const double v = 0.5 * amp * (double)d;
     return average ? v / (lup - llow) : v;
 }
 

@@ -22,6 +22,7 @@
 #include <cstdio>
 
 #include "../../include/eggphot.h"
+#include "phot_tables.hpp"
 
 namespace eggphot {
 
@@ -106,6 +107,27 @@ __device__ void gal_scalars(const FluxParams &p, uint64_t g, GalScal &s) {
 }
 
 // ---- small helpers ---------------------------------------------------------------------------------
+// last j in [0, n) with x[j] <= v (-1 if none), started from the log2 lookup of the grid: the table
+// entry is at most a couple of nodes away, and the two scans make the answer exact in double.
+__device__ __forceinline__ int lut_last_le(const double *__restrict__ x, int n, const uint16_t *__restrict__ lut,
+                                           int nlut, int e0, double v) {
+    int k = (int)((__log2f((float)v) - (float)e0) * (float)kLutPerOctave);
+    k = max(0, min(k, nlut - 1));
+    int j = __ldg(lut + k);
+    while (j >= 0 && __ldg(x + j) > v) --j;
+    while (j + 1 < n && __ldg(x + j + 1) <= v) ++j;
+    return j;
+}
+// first j in [0, n) with x[j] >= v (n if none)
+__device__ __forceinline__ int lut_first_ge(const double *__restrict__ x, int n, const uint16_t *__restrict__ lut,
+                                            int nlut, int e0, double v) {
+    int k = (int)((__log2f((float)v) - (float)e0) * (float)kLutPerOctave);
+    k = max(0, min(k, nlut - 1));
+    int j = __ldg(lut + k); // candidate for the last node < v
+    while (j >= 0 && __ldg(x + j) >= v) --j;
+    while (j + 1 < n && __ldg(x + j + 1) < v) ++j;
+    return j + 1;
+}
 // last j in [0, n) with x[j] <= v, -1 if none
 __device__ __forceinline__ int last_le(const double *__restrict__ x, int n, double v) {
     int lo = -1, hi = n;
@@ -156,10 +178,11 @@ template <typename real> __device__ __forceinline__ CompSum<real> warp_reduce(Co
 // rest grid access in the kernel's precision
 template <typename real> struct GridAcc;
 template <> struct GridAcc<float> {
-    const float *hi, *lo;
+    const float2 *hl;
     float opz_hi, opz_lo;
     __device__ __forceinline__ float pos(int j, float fc) const {
-        return node_pos(__ldg(hi + j), __ldg(lo + j), opz_hi, opz_lo, fc);
+        const float2 v = __ldg(hl + j);
+        return node_pos(v.x, v.y, opz_hi, opz_lo, fc);
     }
 };
 template <> struct GridAcc<double> {
@@ -262,13 +285,15 @@ __global__ void __launch_bounds__(kThreads, 1) flux_kernel(const __grid_constant
             const GalScal &s = sc[gi];
             const float *ll = c ? p.line_lum_disk : p.line_lum_bulge;
             int b0 = 1, b1 = 0; // empty
-            if ((c || p.has_bulge) && ll != nullptr && ll[(g0 + gi) * p.nline + l] != 0.0f) {
+            if ((c || p.has_bulge) && ll != nullptr && ll[(g0 + gi) * p.nline + p.line_col[l]] != 0.0f) {
                 const double *x = c ? p.xD : p.xB;
                 const int n = c ? p.nD : p.nB;
+                const uint16_t *lut = c ? p.lutD : p.lutB;
+                const int nlut = c ? p.lutD_n : p.lutB_n, e0 = c ? p.lutD_e0 : p.lutB_e0;
                 const double l0 = (double)p.line_lambda[l], lw = l0 * (s.vdisp / 2.998e5);
                 // [vif] bounds(lam, a, b) = {last <= a, first > b}  (src/egg-gencat.cpp:2081-2084)
-                const int lo = last_le(x, n, l0 - 10 * lw);
-                const int hi = last_le(x, n, l0 + 10 * lw) + 1; // first > b, n if none
+                const int lo = lut_last_le(x, n, lut, nlut, e0, l0 - 10 * lw);
+                const int hi = lut_last_le(x, n, lut, nlut, e0, l0 + 10 * lw) + 1; // first > b, n if none
                 if (!(hi == 0 || lo == n - 1)) {
                     b0 = lo < 0 ? 0 : lo;
                     b1 = hi >= n ? n - 1 : hi;
@@ -279,9 +304,10 @@ __global__ void __launch_bounds__(kThreads, 1) flux_kernel(const __grid_constant
         }
         __syncthreads();
 
-        // ---- phase A3: emission lines (add_emission_line, src/egg-gencat.cpp:2078-2095).  The first line
-        //      whose window holds node j adds the contributions of all lines at j, in line order: no two
-        //      threads touch the same node and the sum order is fixed.
+        // ---- phase A3: emission lines (add_emission_line, src/egg-gencat.cpp:2078-2095).  Lines are sorted
+        //      by wavelength, so their node windows [b0, b1] are ordered as well.  The first line whose
+        //      window holds node j adds the contributions of all lines at j, in that order: no two threads
+        //      touch the same node and the sum order is fixed.
         for (int idx = tid; idx < ng * 2 * p.nline * kLineSlots; idx += kThreads) {
             const int w = idx % kLineSlots, q = idx / kLineSlots; // q = (gi, c, l)
             const int gi = q / (2 * p.nline), rem = q % (2 * p.nline);
@@ -296,19 +322,23 @@ __global__ void __launch_bounds__(kThreads, 1) flux_kernel(const __grid_constant
             real *S = scr + (size_t)gi * sstride + (c ? 0 : p.strideD);
             // the bulge SED carries no mass scale (applied at the end), so its line term is divided by it
             const double inv = c ? 1.0 : (s.a_bulge > 0 ? 1.0 / s.a_bulge : 0.0);
+            int kprev = l - 1; // nearest earlier line with a non-empty window
+            while (kprev >= 0 && wb[2 * kprev] > wb[2 * kprev + 1]) --kprev;
+            const int prev_b1 = kprev >= 0 ? wb[2 * kprev + 1] : -1;
             for (int j = b0 + w; j <= b1; j += kLineSlots) {
-                bool owner = true;
-                for (int k = 0; k < l; ++k) owner = owner && !(wb[2 * k] <= j && j <= wb[2 * k + 1]);
-                if (!owner) continue;
+                if (j <= prev_b1) continue; // an earlier line owns this node
                 const double xj = __ldg(x + j);
                 const double xm = j > 0 ? __ldg(x + j - 1) : 0.0, xp = j < n - 1 ? __ldg(x + j + 1) : 0.0;
                 const double llow = j != 0 ? 0.5 * (xm + xj) : xj - 0.5 * (xp - xj);       // :2090
                 const double lup = j != n - 1 ? 0.5 * (xj + xp) : xj + 0.5 * (xj - xm);   // :2091
                 double acc = 0.0;
                 for (int k = l; k < p.nline; ++k) {
-                    if (wb[2 * k] <= j && j <= wb[2 * k + 1]) {
+                    const int k0 = wb[2 * k], k1 = wb[2 * k + 1];
+                    if (k0 > k1) continue; // empty window
+                    if (k0 > j) break;     // windows are ordered: no later line reaches back to j
+                    if (j <= k1) {
                         const double l0 = (double)p.line_lambda[k], lw = l0 * (s.vdisp / 2.998e5);
-                        acc += line_bin(llow, lup, l0, lw, (double)ll[k] * l0, p.line_average);
+                        acc += line_bin_t<real>(llow, lup, l0, lw, (double)ll[p.line_col[k]] * l0, p.line_average);
                     }
                 }
                 S[j] += (real)(xj * acc * inv);
@@ -331,17 +361,18 @@ __global__ void __launch_bounds__(kThreads, 1) flux_kernel(const __grid_constant
                 tab_phase ^= 1;
                 loaded = grp;
             }
-            const int nband_items = nb * ncomp * ng;
-            const int nitems = nband_items + (grp == 0 ? nrf * ncomp * ng : 0);
+            const int nband_items = nb * ncomp * kBatch;
+            const int nitems = nband_items + (grp == 0 ? nrf * ncomp * kBatch : 0);
             for (;;) {
                 int idx = 0;
                 if (lane == 0) idx = atomicAdd(&item_ctr[grp], 1);
                 idx = __shfl_sync(kFull, idx, 0);
                 if (idx >= nitems) break;
                 if (idx < nband_items) {
-                    // (band, component, galaxy): bands are stored in decreasing order of expected work
-                    const int gi = idx % ng, t2 = idx / ng;
-                    const int comp = p.has_bulge ? (t2 % ncomp) : 1, bi = t2 / ncomp; // comp: 0 bulge, 1 disk
+                    // (band, component, galaxy slot): bands are stored in decreasing order of expected work
+                    const int gi = idx & (kBatch - 1), t2 = idx / kBatch;
+                    if (gi >= ng) continue;
+                    const int comp = p.has_bulge ? (t2 & 1) : 1, bi = p.has_bulge ? (t2 >> 1) : t2; // comp: 0 bulge, 1 disk
                     const BandHeader &h = hdr[bi];
                     const GalScal &s = sc[gi];
                     const double *x = comp ? p.xD : p.xB;
@@ -349,10 +380,11 @@ __global__ void __launch_bounds__(kThreads, 1) flux_kernel(const __grid_constant
                     // [vif] sed2flux: NaN (-> flux 0, src/egg-gencat.cpp:2198) unless the SED covers the filter
                     const bool covered = n >= 2 && __ldg(x) * s.opz <= h.full_first && __ldg(x + n - 1) * s.opz >= h.full_last;
                     if (!covered || h.n < 2) continue;
-                    int jb = 0;
-                    if (lane == 0) jb = max(last_le(x, n, h.eff_first / s.opz * (1.0 - 1e-15)), 0);
-                    if (lane == 1) jb = min(first_ge(x, n, h.eff_last / s.opz * (1.0 + 1e-15)), n - 1);
-                    const int jlo = __shfl_sync(kFull, jb, 0), jhi = __shfl_sync(kFull, jb, 1);
+                    const uint16_t *lut = comp ? p.lutD : p.lutB;
+                    const int nlut = comp ? p.lutD_n : p.lutB_n, e0 = comp ? p.lutD_e0 : p.lutB_e0;
+                    const double iopz = 1.0 / s.opz;
+                    const int jlo = max(lut_last_le(x, n, lut, nlut, e0, h.eff_first * iopz * (1.0 - 1e-15)), 0);
+                    const int jhi = min(lut_first_ge(x, n, lut, nlut, e0, h.eff_last * iopz * (1.0 + 1e-15)), n - 1);
                     if (jhi <= jlo) continue;
                     BandView<real> bv;
                     make_band_view(blob, h, bv);
@@ -360,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) flux_kernel(const __grid_constant
                     GridAcc<real> ga;
                     if constexpr (sizeof(real) == 4) {
                         const float oh = (float)s.opz;
-                        ga.hi = comp ? p.xDhi : p.xBhi; ga.lo = comp ? p.xDlo : p.xBlo;
+                        ga.hl = comp ? p.xDhl : p.xBhl;
                         ga.opz_hi = oh; ga.opz_lo = (float)(s.opz - (double)oh);
                     } else {
                         ga.x = x; ga.opz = s.opz;
@@ -390,8 +422,9 @@ __global__ void __launch_bounds__(kThreads, 1) flux_kernel(const __grid_constant
                 } else {
                     // rest-frame magnitude: dot product with the z = 0 weights (src/egg-gencat.cpp:2150-2158)
                     const int r = idx - nband_items;
-                    const int gi = r % ng, t2 = r / ng;
-                    const int comp = p.has_bulge ? (t2 % ncomp) : 1, rb = t2 / ncomp;
+                    const int gi = r & (kBatch - 1), t2 = r / kBatch;
+                    if (gi >= ng) continue;
+                    const int comp = p.has_bulge ? (t2 & 1) : 1, rb = p.has_bulge ? (t2 >> 1) : t2;
                     const RfDesc dsc = comp ? p.rfD[rb] : p.rfB[rb];
                     const real *S = scr + (size_t)gi * sstride + (comp ? 0 : p.strideD);
                     const real *W = reinterpret_cast<const real *>(p.rfW) + dsc.off;

@@ -11,7 +11,7 @@ namespace eggphot {
 
 constexpr int kMaxLines = 64;
 constexpr int kMaxGroupBands = 64;
-constexpr int kThreads = 512;          // 16 warps per CTA
+constexpr int kThreads = 768;          // 24 warps per CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kBatch = 16;             // galaxies a CTA carries through all band groups at a time
 constexpr int kMaxGroups = 16;
@@ -50,7 +50,9 @@ struct FluxParams {
     int32_t nB, nD;        // nodes (0 if the component is absent)
     int32_t strideB, strideD; // row strides in elements (16-byte multiples)
     const double *xB, *xD; // rest wavelengths, double
-    const float *xBhi, *xBlo, *xDhi, *xDlo; // the same as hi+lo float pairs (fp32 mode)
+    const float2 *xBhl, *xDhl; // the same as (hi, lo) float pairs (fp32 mode)
+    const uint16_t *lutB, *lutD; // log2-spaced "last node <= v" lookups (Grid::lut)
+    int32_t lutB_n, lutD_n, lutB_e0, lutD_e0;
     int32_t igmB[4], igmD[4]; // lz, l0, l1, l2
     // template rows in the kernel's real type
     const void *rowsB, *rowsDopt, *rowsDir, *rowsDpah;
@@ -59,7 +61,8 @@ struct FluxParams {
     int32_t ir_kind, disk_mode, has_bulge, apply_igm;
     // emission lines
     int32_t nline, line_average;
-    float line_lambda[kMaxLines];
+    float line_lambda[kMaxLines];   // sorted by wavelength
+    uint8_t line_col[kMaxLines];    // column of the caller's line_lum arrays for each sorted line
     // rest-frame weights
     const RfDesc *rfB, *rfD;
     const void *rfW;       // real

@@ -265,6 +265,20 @@ Status make_grid_thresholds(Grid &g, bool apply_igm, const char *what) {
 
 } // namespace
 
+void Grid::build_lut() {
+    lut.clear();
+    if (x.empty()) return;
+    lut_e0 = (int)std::floor(std::log2(x.front())) - 1;
+    const int nk = (int)std::ceil((std::log2(x.back()) - lut_e0) * kLutPerOctave) + 2;
+    lut.resize(nk);
+    int j = -1;
+    for (int k = 0; k < nk; ++k) {
+        const double edge = std::exp2(lut_e0 + (double)k / kLutPerOctave);
+        while (j + 1 < n() && x[j + 1] <= edge) ++j;
+        lut[k] = (uint16_t)std::max(j, 0);
+    }
+}
+
 Status prepare_filters(const eggphot_filters *raw, const eggphot_opts &opts, std::vector<Filter> &sorted,
                        std::vector<uint32_t> &order, std::vector<float> &lambda) {
     sorted.clear(); order.clear(); lambda.clear();
@@ -459,6 +473,10 @@ Status prepare(const eggphot_libs &L, const eggphot_filters *bands, const eggpho
     }
     st = make_grid_thresholds(P.grid_disk, P.apply_igm, P.disk_mode == DISK_IR ? "IR" : "disk");
     if (!st.ok()) return st;
+    if (P.grid_disk.n() > 65000 || P.grid_bulge.n() > 65000)
+        return Status::error(EGGPHOT_ERR_UNSUPPORTED, "SED wavelength grid with more than 65000 nodes");
+    P.grid_bulge.build_lut();
+    P.grid_disk.build_lut();
 
     // ---- template rows  Y = x * L(x)
     auto resample = [&](const std::vector<double> &xs, const double *ys, const Grid &g, double *dst) {
@@ -494,7 +512,7 @@ Status prepare(const eggphot_libs &L, const eggphot_filters *bands, const eggpho
     // ---- band tables, packed into groups under the shared-memory budget
     const size_t budget = opts.smem_table_budget ? opts.smem_table_budget : 196u * 1024;
     const size_t hard_cap = 204u * 1024;
-    const int bfac = P.precision == EGGPHOT_FP64 ? 1 : 2;
+    const int bfac = P.precision == EGGPHOT_FP64 ? 2 : 4;
     std::vector<BandTableD> tabs(P.bands.size());
     for (size_t b = 0; b < P.bands.size(); ++b) {
         st = build_band_table(P.bands[b], (uint32_t)b, bfac, tabs[b]);

@@ -36,10 +36,16 @@ struct Filter {
 };
 
 // A rest-frame wavelength grid shared by all templates of a component.
+constexpr int kLutPerOctave = 64;
+
 struct Grid {
     std::vector<double> x;    // um, strictly increasing
     int lz = 0, l0 = 0, l1 = 0, l2 = 0; // IGM index thresholds (last node <= 0.06/0.0912/0.1026/0.1216 um)
+    // log2-spaced lookup for "last node <= v": lut[k] = last j with x[j] <= 2^(lut_e0 + k/kLutPerOctave)
+    std::vector<uint16_t> lut;
+    int lut_e0 = 0;
     int n() const { return (int)x.size(); }
+    void build_lut();
 };
 
 enum DiskMode { DISK_BOTH = 0, DISK_OPT = 1, DISK_IR = 2 };
