@@ -72,7 +72,8 @@ struct __attribute__((aligned(16))) BandHeader {
     uint32_t bkt_off;             // byte offset of the uint16 bucket array (nbkt + 1 entries)
     uint32_t out_col;             // column in the sorted band list
     uint32_t split;               // cells 0..split accumulate from the left end, cells > split from the right
-    uint32_t pad[2];
+    uint32_t tflo_off;            // fp32 tables: byte offset of the float array of low parts of tf
+    uint32_t pad;
 };
 static_assert(sizeof(BandHeader) == 192, "BandHeader layout");
 
@@ -83,10 +84,13 @@ template <> struct NodeOf<double> { typedef FilterNodeD type; };
 // Cumulative quantities at one SED node (the only things an interval needs from its two ends).
 template <typename real> struct NodeQ;
 template <> struct NodeQ<float> {
-    float k0h, k0l, k1h, k1l; // K0, K1 in offset/scaled units, hi+lo
+    float i0h, i0l, c1h, c1l; // prefix values of the node's filter cell (offset/scaled, hi+lo)
+    float p0;                 // integral of R over the part of the cell left of the node
+    float hru;                // R_i * u^2 / 2
+    float R;                  // R_i (used by the node's own interval only; never shuffled)
 };
 template <> struct NodeQ<double> {
-    double k0, k1;
+    double i0, c1, p0, hru, R;
 };
 
 // Per-band scalars the arithmetic needs.
@@ -100,37 +104,42 @@ template <typename real> struct BandScal {
     int split;     // last cell whose prefix values are measured from the left end
 };
 
-// K0/K1 at effective position te (already clamped into the band's effective span) inside cell `e`.
-// Also returns u = te - tf_i.
-EGG_HD void node_quantities(const FilterNodeF &e, float te, const BandScal<float> &bs, NodeQ<float> &q, float &u) {
-    u = te - e.tf;
+// What an interval needs from one of its end nodes, te being the node's effective position (clamped
+// into the band's effective span), `e` its filter cell and u = te - tf_i.  With
+//     K0(t) = I0_i + p0,            p0 = (R_i + rho(t))/2 * u
+//     K1(t) = C1_i + p0*t - R_i*u^2/2         (the same trapezoid with a virtual node at t, rewritten)
+// the moment about the LEFT node of an interval becomes
+//     K1(t_r) - K1(t_l) - t_l*(K0(t_r) - K0(t_l)) = [dC1 - t_l*dI0] + p0_r*(t_r - t_l) - hru_r + hru_l
+// in which only table values are differenced against each other (exactly, thanks to the hi+lo
+// storage) and every other term is small and well conditioned.
+EGG_HD void node_quantities(const FilterNodeF &e, float u, NodeQ<float> &q) {
     const float rho = fmaf(e.s, u, e.R);
-    const float p0 = 0.5f * (e.R + rho) * u * bs.inv_ni;
-    const float p1 = 0.5f * fmaf(e.R, e.tf, rho * te) * u * bs.inv_nc;
-    // FastTwoSum(|hi| >= |p|): hi parts live in [1,2), partial cells are at most the band integral / NI <= 1/4
-    const float s0 = e.I0h + p0;
-    q.k0h = s0;
-    q.k0l = e.I0l + (p0 - (s0 - e.I0h));
-    const float s1 = e.C1h + p1;
-    q.k1h = s1;
-    q.k1l = e.C1l + (p1 - (s1 - e.C1h));
+    q.i0h = e.I0h; q.i0l = e.I0l; q.c1h = e.C1h; q.c1l = e.C1l;
+    q.p0 = 0.5f * (e.R + rho) * u;
+    q.hru = 0.5f * e.R * u * u;
+    q.R = e.R;
 }
-EGG_HD void node_quantities(const FilterNodeD &e, double te, const BandScal<double> &, NodeQ<double> &q, double &u) {
-    u = te - e.tf;
+EGG_HD void node_quantities(const FilterNodeD &e, double u, NodeQ<double> &q) {
     const double rho = fma(e.s, u, e.R);
-    q.k0 = e.I0 + 0.5 * (e.R + rho) * u;
-    q.k1 = e.C1 + 0.5 * fma(e.R, e.tf, rho * te) * u;
+    q.i0 = e.I0; q.c1 = e.C1;
+    q.p0 = 0.5 * (e.R + rho) * u;
+    q.hru = 0.5 * e.R * u * u;
+    q.R = e.R;
 }
 
+EGG_HD float rl_R(const NodeQ<float> &q, float, float) { return q.R; }
+EGG_HD double rl_R(const NodeQ<double> &q, double, double) { return q.R; }
+
 // Contribution T_j of one SED interval.
-//   left node : true position tl, effective (clamped) position tel, value Sl, quantities ql,
-//               its filter cell (s, dl) and offset ul = tel - tf_i, cell index il
-//   right node: tr, ter, Sr, qr, cell index ir
+//   left node : true position tl (+ low part tll in fp32), offset ul inside its filter cell, value Sl,
+//               quantities ql, its filter cell (s, dl), cell index il
+//   right node: tr (+ trl), Sr, qr, cell index ir
+//   dte = effective (clamped) interval width;  xr = effective right position minus TRUE left position
 // Returns S_l*q + sigma*m in the band's natural units (response * wavelength * S).
-EGG_HD float interval_flux(float tl, float tel, float Sl, const NodeQ<float> &ql, float s_l, float dl_l, float ul,
-                           int il, float tr, float ter, float Sr, const NodeQ<float> &qr, int ir,
+EGG_HD float interval_flux(float tl, float tll, float Sl, const NodeQ<float> &ql, float s_l, float dl_l, float ul,
+                           int il, float tr, float trl, float Sr, const NodeQ<float> &qr, int ir, float dte, float xr,
                            const BandScal<float> &bs) {
-    const float dt = tr - tl;
+    const float dt = (tr - tl) + (trl - tll);
 #if defined(__CUDA_ARCH__)
     const float sigma = dt > 0.0f ? __fdividef(Sr - Sl, dt) : 0.0f; // 2 ulp; enters only the slope term
 #else
@@ -141,30 +150,41 @@ EGG_HD float interval_flux(float tl, float tel, float Sl, const NodeQ<float> &ql
     // straddles the split adds the band total.  All high parts are multiples of 2^-23 below 1 in
     // magnitude, so these sums stay exact.
     const bool cross = il <= bs.split && ir > bs.split;
-    const float d0h = (qr.k0h - ql.k0h) + (cross ? bs.tot0h : 0.0f);
-    const float d0l = (qr.k0l - ql.k0l) + (cross ? bs.tot0l : 0.0f);
-    const float d1h = (qr.k1h - ql.k1h) + (cross ? bs.tot1h : 0.0f);
-    const float d1l = (qr.k1l - ql.k1l) + (cross ? bs.tot1l : 0.0f);
-    const float q = (d0h + d0l) * bs.ni;
-    // m = NC*dK1 - tl*NI*dK0 - corr, evaluated as NC*[ (dK1h - tau*dK0h) + (dK1l - tau*dK0l) ]
-    const float tau = tl * bs.ni_nc;
-    const float r = fmaf(-tau, d0h, d1h) + fmaf(-tau, d0l, d1l);
-    const float bmt = (ir == il) ? (ter - tel) : (dl_l - ul); // B - t_l
+    const float d0h = (qr.i0h - ql.i0h) + (cross ? bs.tot0h : 0.0f);
+    const float d0l = (qr.i0l - ql.i0l) + (cross ? bs.tot0l : 0.0f);
+    const float d1h = (qr.c1h - ql.c1h) + (cross ? bs.tot1h : 0.0f);
+    const float d1l = (qr.c1l - ql.c1l) + (cross ? bs.tot1l : 0.0f);
+    const float q = fmaf(d0h + d0l, bs.ni, qr.p0 - ql.p0);
+    // [dC1 - t_l*dI0] in table units: NC*[ (dC1h - tau*dI0h) + (dC1l - tau*dI0l) ], tau = t_l*NI/NC in hi+lo
+    const float tauh = tl * bs.ni_nc, taul = tll * bs.ni_nc;
+    const float r = fmaf(-tauh, d0h, d1h) + fmaf(-tauh, d0l, fmaf(-taul, d0h, d1l));
+    const float bmt = (ir == il) ? dte : (dl_l - ul); // B - t_l
     const float corr = 0.5f * s_l * ul * bmt * (bmt + ul);
-    const float m = fmaf(r, bs.nc, -corr);
-    return fmaf(Sl, q, sigma * m);
+    const float m = fmaf(r, bs.nc, fmaf(qr.p0, xr, (ql.hru - qr.hru) - corr));
+    // both ends in one filter cell: the union grid has no node in between, so the interval is a single
+    // trapezoid; evaluated directly it keeps full relative accuracy for a narrow SED feature inside a
+    // wide filter cell (the general form would difference two partial-cell integrals there)
+    const float rho_l = fmaf(s_l, ul, rl_R(ql, s_l, ul)), rho_r = fmaf(s_l, dte, rho_l);
+    const float Sel = fmaf(sigma, xr - dte, Sl), Ser = fmaf(sigma, xr, Sl); // S at the effective ends
+    const float same = 0.5f * fmaf(rho_l, Sel, rho_r * Ser) * dte;
+    return ir == il ? same : fmaf(Sl, q, sigma * m);
 }
-EGG_HD double interval_flux(double tl, double tel, double Sl, const NodeQ<double> &ql, double s_l, double dl_l,
-                            double ul, int il, double tr, double ter, double Sr, const NodeQ<double> &qr, int ir,
-                            const BandScal<double> &bs) {
+EGG_HD double interval_flux(double tl, double, double Sl, const NodeQ<double> &ql, double s_l, double dl_l,
+                            double ul, int il, double tr, double, double Sr, const NodeQ<double> &qr, int ir, double dte,
+                            double xr, const BandScal<double> &bs) {
     const double dt = tr - tl;
     const double sigma = dt > 0.0 ? (Sr - Sl) / dt : 0.0;
     const bool cross = il <= bs.split && ir > bs.split;
-    const double q = (qr.k0 - ql.k0) + (cross ? bs.tot0h : 0.0);
-    const double r = fma(-tl, q, (qr.k1 - ql.k1) + (cross ? bs.tot1h : 0.0));
-    const double bmt = (ir == il) ? (ter - tel) : (dl_l - ul);
+    const double d0 = (qr.i0 - ql.i0) + (cross ? bs.tot0h : 0.0);
+    const double d1 = (qr.c1 - ql.c1) + (cross ? bs.tot1h : 0.0);
+    const double q = d0 + (qr.p0 - ql.p0);
+    const double bmt = (ir == il) ? dte : (dl_l - ul);
     const double corr = 0.5 * s_l * ul * bmt * (bmt + ul);
-    return fma(Sl, q, sigma * (r - corr));
+    const double m = fma(-tl, d0, d1) + fma(qr.p0, xr, (ql.hru - qr.hru) - corr);
+    const double rho_l = fma(s_l, ul, rl_R(ql, s_l, ul)), rho_r = fma(s_l, dte, rho_l);
+    const double Sel = fma(sigma, xr - dte, Sl), Ser = fma(sigma, xr, Sl);
+    const double same = 0.5 * fma(rho_l, Sel, rho_r * Ser) * dte;
+    return ir == il ? same : fma(Sl, q, sigma * m);
 }
 
 // Compensated accumulation (TwoSum, branch-free): the "compensated sum" of the fp32 mode.
@@ -202,6 +222,7 @@ EGG_HD int find_cell(TfGet tfget, const uint16_t *bkt, int nbkt, real tf0, real 
 // Band seen through the kernel's real type.
 template <typename real> struct BandView {
     const typename NodeOf<real>::type *nodes;
+    const float *tflo; // fp32: low parts of the node positions
     const uint16_t *bkt;
     BandScal<real> bs;
     real fc, tf0, tfl, bkt_inv_w;
@@ -209,6 +230,7 @@ template <typename real> struct BandView {
 };
 EGG_HD void make_band_view(const uint8_t *blob, const BandHeader &h, BandView<float> &v) {
     v.nodes = reinterpret_cast<const FilterNodeF *>(blob + h.node_off);
+    v.tflo = reinterpret_cast<const float *>(blob + h.tflo_off);
     v.bkt = reinterpret_cast<const uint16_t *>(blob + h.bkt_off);
     v.bs.ni = h.nif; v.bs.nc = h.ncf; v.bs.inv_ni = h.inv_nif; v.bs.inv_nc = h.inv_ncf; v.bs.ni_nc = h.ni_ncf;
     v.bs.tot0h = h.tot0h; v.bs.tot0l = h.tot0l; v.bs.tot1h = h.tot1h; v.bs.tot1l = h.tot1l; v.bs.split = (int)h.split;
@@ -217,6 +239,7 @@ EGG_HD void make_band_view(const uint8_t *blob, const BandHeader &h, BandView<fl
 }
 EGG_HD void make_band_view(const uint8_t *blob, const BandHeader &h, BandView<double> &v) {
     v.nodes = reinterpret_cast<const FilterNodeD *>(blob + h.node_off);
+    v.tflo = nullptr;
     v.bkt = reinterpret_cast<const uint16_t *>(blob + h.bkt_off);
     v.bs.ni = v.bs.nc = v.bs.inv_ni = v.bs.inv_nc = v.bs.ni_nc = 1.0;
     v.bs.tot0h = h.tot0; v.bs.tot1h = h.tot1; v.bs.tot0l = v.bs.tot1l = 0.0; v.bs.split = (int)h.split;
@@ -225,44 +248,60 @@ EGG_HD void make_band_view(const uint8_t *blob, const BandHeader &h, BandView<do
 }
 
 // Observed-frame, band-centred position of a rest-frame node: x*(1+z) - fc.
-// fp32: x and (1+z) are carried as hi+lo pairs so that the only rounding is on the (small) result.
-EGG_HD float node_pos(float xhi, float xlo, float opz_hi, float opz_lo, float fc) {
-    return fmaf(xhi, opz_hi, -fc) + fmaf(xhi, opz_lo, xlo * opz_hi);
+// fp32: x and (1+z) come as hi+lo pairs and the result is returned as a hi+lo pair (error-free
+// product and sum), because what the quadrature needs is the position RELATIVE to filter nodes and
+// to neighbouring SED nodes, i.e. differences ~1e-3 of numbers ~0.1-1: a single f32 would leave
+// ~1e-5 of relative noise on every interval width, which shows on SEDs with sharp features.
+EGG_HD void node_pos(float xhi, float xlo, float opz_hi, float opz_lo, float fc, float &th, float &tl) {
+    const float ph = xhi * opz_hi;
+    const float pe = fmaf(xhi, opz_hi, -ph);      // exact product error
+    th = ph - fc;
+    const float bb = th - ph;
+    const float e2 = (ph - (th - bb)) + (-fc - bb); // exact sum error
+    tl = fmaf(xlo, opz_hi, fmaf(xhi, opz_lo, pe + e2));
 }
-EGG_HD double node_pos(double x, double opz, double fc) { return fma(x, opz, -fc); }
+EGG_HD void node_pos(double x, double opz, double fc, double &th, double &tl) { th = fma(x, opz, -fc); tl = 0.0; }
 
 EGG_HD float clampr(float t, float lo, float hi) { return fminf(fmaxf(t, lo), hi); }
 EGG_HD double clampr(double t, double lo, double hi) { return fmin(fmax(t, lo), hi); }
 
 // Everything an interval needs to know about one of its end nodes.
 template <typename real> struct NodeState {
-    real t;   // true position
-    real S;   // SED value (x * L) at the node
-    real u;   // te - tf[cell], te = t clamped into the effective span
+    real t, tl; // true position, hi + lo (lo is 0 in fp64)
+    real S;     // SED value (x * L) at the node
+    real u;     // te - tf[cell], te = t clamped into the effective span
     real s, dl; // slope and width of the filter cell
     int cell;
     NodeQ<real> q;
 };
 
+EGG_HD float cell_offset(const BandView<float> &b, int c, float tf, float te, float tel) { return (te - tf) + (tel - b.tflo[c]); }
+EGG_HD double cell_offset(const BandView<double> &, int, double tf, double te, double) { return te - tf; }
+
 template <typename real>
-EGG_HD void eval_node(const BandView<real> &b, real t, real S, NodeState<real> &ns) {
+EGG_HD void eval_node(const BandView<real> &b, real t, real tl, real S, NodeState<real> &ns) {
     ns.t = t;
+    ns.tl = tl;
     ns.S = S;
     const real te = clampr(t, b.tf0, b.tfl);
+    const real tel = te == t ? tl : real(0); // a clamped node sits exactly on the span end
     const typename NodeOf<real>::type *nodes = b.nodes;
     int c = find_cell<real>([nodes](int i) { return nodes[i].tf; }, b.bkt, b.nbkt, b.tf0, b.bkt_inv_w, b.n, te);
     const typename NodeOf<real>::type e = nodes[c];
     ns.cell = c;
     ns.s = e.s;
     ns.dl = e.dl;
-    node_quantities(e, te, b.bs, ns.q, ns.u);
+    ns.u = cell_offset(b, c, e.tf, te, tel);
+    node_quantities(e, ns.u, ns.q);
 }
 
 template <typename real>
 EGG_HD real eval_interval(const BandView<real> &b, const NodeState<real> &l, const NodeState<real> &r) {
-    const real tel = clampr(l.t, b.tf0, b.tfl);
-    const real ter = clampr(r.t, b.tf0, b.tfl);
-    return interval_flux(l.t, tel, l.S, l.q, l.s, l.dl, l.u, l.cell, r.t, ter, r.S, r.q, r.cell, b.bs);
+    const real tel = clampr(l.t, b.tf0, b.tfl), ter = clampr(r.t, b.tf0, b.tfl);
+    const real terl = ter == r.t ? r.tl : real(0), tell = tel == l.t ? l.tl : real(0);
+    const real dte = (ter - tel) + (terl - tell);
+    const real xr = (ter - l.t) + (terl - l.tl);
+    return interval_flux(l.t, l.tl, l.S, l.q, l.s, l.dl, l.u, l.cell, r.t, r.tl, r.S, r.q, r.cell, dte, xr, b.bs);
 }
 
 // IGM factor of node j (src/egg-gencat.cpp:2128-2139): [0,lz) -> 0, [lz,l0) -> a0, [l0,l1) -> a1, [l1,l2) -> a2

@@ -149,19 +149,25 @@ __device__ __forceinline__ int first_ge(const double *__restrict__ x, int n, dou
 
 __device__ __forceinline__ void shfl_node(const NodeState<float> &a, NodeState<float> &r) {
     r.t = __shfl_down_sync(kFull, a.t, 1);
+    r.tl = __shfl_down_sync(kFull, a.tl, 1);
     r.S = __shfl_down_sync(kFull, a.S, 1);
     r.cell = __shfl_down_sync(kFull, a.cell, 1);
-    r.q.k0h = __shfl_down_sync(kFull, a.q.k0h, 1);
-    r.q.k0l = __shfl_down_sync(kFull, a.q.k0l, 1);
-    r.q.k1h = __shfl_down_sync(kFull, a.q.k1h, 1);
-    r.q.k1l = __shfl_down_sync(kFull, a.q.k1l, 1);
+    r.q.i0h = __shfl_down_sync(kFull, a.q.i0h, 1);
+    r.q.i0l = __shfl_down_sync(kFull, a.q.i0l, 1);
+    r.q.c1h = __shfl_down_sync(kFull, a.q.c1h, 1);
+    r.q.c1l = __shfl_down_sync(kFull, a.q.c1l, 1);
+    r.q.p0 = __shfl_down_sync(kFull, a.q.p0, 1);
+    r.q.hru = __shfl_down_sync(kFull, a.q.hru, 1);
 }
 __device__ __forceinline__ void shfl_node(const NodeState<double> &a, NodeState<double> &r) {
     r.t = __shfl_down_sync(kFull, a.t, 1);
+    r.tl = 0.0;
     r.S = __shfl_down_sync(kFull, a.S, 1);
     r.cell = __shfl_down_sync(kFull, a.cell, 1);
-    r.q.k0 = __shfl_down_sync(kFull, a.q.k0, 1);
-    r.q.k1 = __shfl_down_sync(kFull, a.q.k1, 1);
+    r.q.i0 = __shfl_down_sync(kFull, a.q.i0, 1);
+    r.q.c1 = __shfl_down_sync(kFull, a.q.c1, 1);
+    r.q.p0 = __shfl_down_sync(kFull, a.q.p0, 1);
+    r.q.hru = __shfl_down_sync(kFull, a.q.hru, 1);
 }
 
 template <typename real> __device__ __forceinline__ CompSum<real> warp_reduce(CompSum<real> a) {
@@ -180,15 +186,15 @@ template <typename real> struct GridAcc;
 template <> struct GridAcc<float> {
     const float2 *hl;
     float opz_hi, opz_lo;
-    __device__ __forceinline__ float pos(int j, float fc) const {
+    __device__ __forceinline__ void pos(int j, float fc, float &th, float &tl) const {
         const float2 v = __ldg(hl + j);
-        return node_pos(v.x, v.y, opz_hi, opz_lo, fc);
+        node_pos(v.x, v.y, opz_hi, opz_lo, fc, th, tl);
     }
 };
 template <> struct GridAcc<double> {
     const double *x;
     double opz;
-    __device__ __forceinline__ double pos(int j, double fc) const { return node_pos(__ldg(x + j), opz, fc); }
+    __device__ __forceinline__ void pos(int j, double fc, double &th, double &tl) const { node_pos(__ldg(x + j), opz, fc, th, tl); }
 };
 
 struct SmemLayout {
@@ -400,18 +406,21 @@ __global__ void __launch_bounds__(kThreads, 1) flux_kernel(const __grid_constant
                     CompSum<real> acc;
                     acc.clear();
                     int j = min(jlo + lane, jhi);
-                    real tc = ga.pos(j, bv.fc), Sc = S[j];
+                    real tc, tcl, Sc = S[j];
+                    ga.pos(j, bv.fc, tc, tcl);
                     for (int jbase = jlo; jbase < jhi; jbase += 31) {
                         const bool live = lane < 31 && jbase + lane < jhi;
                         // next pass's inputs first: their latency hides behind this pass's arithmetic
                         const int jn = min(jbase + 31 + lane, jhi);
-                        const real tn = ga.pos(jn, bv.fc), Sn = S[jn];
+                        real tn, tnl;
+                        const real Sn = S[jn];
+                        ga.pos(jn, bv.fc, tn, tnl);
                         NodeState<real> nl, nr;
-                        eval_node<real>(bv, tc, Sc, nl);
+                        eval_node<real>(bv, tc, tcl, Sc, nl);
                         shfl_node(nl, nr);
                         const real T = eval_interval<real>(bv, nl, nr);
                         if (live) acc.add(T);
-                        tc = tn; Sc = Sn;
+                        tc = tn; tcl = tnl; Sc = Sn;
                     }
                     acc = warp_reduce(acc);
                     if (lane == 0) {

@@ -175,6 +175,7 @@ Status build_band_table(const Filter &f, uint32_t out_col, int bucket_factor, Ba
 size_t band_bytes(const BandTableD &t, int precision) {
     const size_t node = precision == EGGPHOT_FP64 ? sizeof(double) * 6 : sizeof(FilterNodeF);
     size_t b = ((size_t)t.h.n * node + 15) & ~size_t(15);
+    if (precision != EGGPHOT_FP64) b += ((size_t)t.h.n * sizeof(float) + 15) & ~size_t(15);
     b += ((t.bkt.size() * sizeof(uint16_t)) + 15) & ~size_t(15);
     return b;
 }
@@ -190,6 +191,8 @@ void append_band(std::vector<uint8_t> &blob, size_t header_pos, const BandTableD
             blob.insert(blob.end(), p, p + sizeof(v));
         }
     } else {
+        std::vector<float> tflo;
+        for (const FilterNodeD &e : t.nodes) tflo.push_back((float)(e.tf - (double)(float)e.tf));
         for (const FilterNodeD &e : t.nodes) {
             FilterNodeF o;
             o.tf = (float)e.tf; o.R = (float)e.R; o.s = (float)e.s; o.dl = (float)e.dl;
@@ -199,6 +202,10 @@ void append_band(std::vector<uint8_t> &blob, size_t header_pos, const BandTableD
             const uint8_t *p = reinterpret_cast<const uint8_t *>(&o);
             blob.insert(blob.end(), p, p + sizeof(o));
         }
+        align16(blob);
+        h.tflo_off = (uint32_t)blob.size();
+        const uint8_t *p = reinterpret_cast<const uint8_t *>(tflo.data());
+        blob.insert(blob.end(), p, p + tflo.size() * sizeof(float));
     }
     align16(blob);
     h.bkt_off = (uint32_t)blob.size();
@@ -233,7 +240,8 @@ RfWeights rf_weights(const BandTableD &t, const Grid &g) {
         e.tt = g.x[j] - t.h.fc;
         e.te = std::min(std::max(e.tt, tfa), tfb);
         e.cell = find_cell<double>(tfget, t.bkt.data(), (int)t.h.nbkt, t.h.tf0, t.h.bkt_inv_w, n, e.te);
-        node_quantities(t.nodes[e.cell], e.te, bs, e.q, e.u);
+        e.u = e.te - t.nodes[e.cell].tf;
+        node_quantities(t.nodes[e.cell], e.u, e.q);
         e.s = t.nodes[e.cell].s;
         e.dl = t.nodes[e.cell].dl;
         return e;
@@ -241,8 +249,9 @@ RfWeights rf_weights(const BandTableD &t, const Grid &g) {
     NodeEval L = eval(jlo);
     for (int j = jlo; j < jhi; ++j) {
         NodeEval Rr = eval(j + 1);
-        r.w[j - jlo] += interval_flux(L.tt, L.te, 1.0, L.q, L.s, L.dl, L.u, L.cell, Rr.tt, Rr.te, 0.0, Rr.q, Rr.cell, bs);
-        r.w[j + 1 - jlo] += interval_flux(L.tt, L.te, 0.0, L.q, L.s, L.dl, L.u, L.cell, Rr.tt, Rr.te, 1.0, Rr.q, Rr.cell, bs);
+        const double dte = Rr.te - L.te, xr = Rr.te - L.tt;
+        r.w[j - jlo] += interval_flux(L.tt, 0.0, 1.0, L.q, L.s, L.dl, L.u, L.cell, Rr.tt, 0.0, 0.0, Rr.q, Rr.cell, dte, xr, bs);
+        r.w[j + 1 - jlo] += interval_flux(L.tt, 0.0, 0.0, L.q, L.s, L.dl, L.u, L.cell, Rr.tt, 0.0, 1.0, Rr.q, Rr.cell, dte, xr, bs);
         L = Rr;
     }
     return r;

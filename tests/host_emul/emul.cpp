@@ -18,14 +18,14 @@ namespace {
 
 template <typename real> struct Pos;
 template <> struct Pos<float> {
-    static float at(const Grid &g, int j, double opz, float fc) {
+    static void at(const Grid &g, int j, double opz, float fc, float &th, float &tl) {
         const float hi = (float)g.x[j], lo = (float)(g.x[j] - (double)hi);
         const float oh = (float)opz, ol = (float)(opz - (double)oh);
-        return node_pos(hi, lo, oh, ol, fc);
+        node_pos(hi, lo, oh, ol, fc, th, tl);
     }
 };
 template <> struct Pos<double> {
-    static double at(const Grid &g, int j, double opz, double fc) { return node_pos(g.x[j], opz, fc); }
+    static void at(const Grid &g, int j, double opz, double fc, double &th, double &tl) { node_pos(g.x[j], opz, fc, th, tl); }
 };
 
 int last_le(const std::vector<double> &x, double v) {
@@ -130,9 +130,11 @@ void run(const Prepared &P, const eggphot_galaxies &G, size_t ngal, double *fd, 
                         CompSum<real> acc;
                         acc.clear();
                         NodeState<real> L, R;
-                        if (jhi > jlo) eval_node<real>(bv, Pos<real>::at(gr, jlo, opz, bv.fc), S[jlo], L);
+                        real th, tl;
+                        if (jhi > jlo) { Pos<real>::at(gr, jlo, opz, bv.fc, th, tl); eval_node<real>(bv, th, tl, S[jlo], L); }
                         for (int j = jlo; j < jhi; ++j) {
-                            eval_node<real>(bv, Pos<real>::at(gr, j + 1, opz, bv.fc), S[j + 1], R);
+                            Pos<real>::at(gr, j + 1, opz, bv.fc, th, tl);
+                            eval_node<real>(bv, th, tl, S[j + 1], R);
                             acc.add(eval_interval<real>(bv, L, R));
                             L = R;
                         }

@@ -1,0 +1,52 @@
+"""CPU tier: the device algorithm (table builder + interval arithmetic of egg_b200/csrc, walked
+sequentially by tests/host_emul) against the oracle, both arithmetic modes, every parity case."""
+import numpy as np
+import pytest
+
+import cases
+import emul
+from oracle.oracle import Oracle
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+@pytest.mark.parametrize("prec", ["fp32c", "fp64"])
+def test_device_algorithm_matches_oracle(name, prec):
+    c = cases.make(name, ngal=64)
+    ref = Oracle(c["opt"], c["ir"], c["bands"], c["rfbands"], line_lambda=c["lines"], **c["opts"]).compute(c["gal"], f64=True)
+    out = emul.compute(c["opt"], c["ir"], c["bands"], c["rfbands"], c["gal"], line_lambda=c["lines"], precision=prec, **c["opts"])
+    for k in ("flux_disk", "flux_bulge"):
+        e = cases.rel_err(out[k], ref[k], cases.FLOOR[prec])
+        assert e.max() < cases.TOL[prec], f"{name} {k}: {e.max():.2e}"
+    for k in ("rfmag_disk", "rfmag_bulge"):
+        if ref[k].size:
+            assert np.abs(out[k] - ref[k]).max() < cases.MAGTOL[prec], f"{name} {k}"
+
+
+def test_band_order_is_the_sorted_reference_wavelength():
+    c = cases.make("b30_rf3_defaults", ngal=2)
+    orc = Oracle(c["opt"], c["ir"], c["bands"], c["rfbands"])
+    out = emul.compute(c["opt"], c["ir"], c["bands"], c["rfbands"], c["gal"], no_nebular=True)
+    assert list(out["band_order"]) == list(orc.band_order)
+    np.testing.assert_array_equal(out["lambda"], orc.lambda_)
+    assert np.all(np.diff(out["lambda"]) >= 0)
+
+
+def test_uncovered_bands_are_zero_and_covered_ones_are_not():
+    c = cases.make("b30_rf3_defaults", ngal=32)
+    out = emul.compute(c["opt"], c["ir"], c["bands"], c["rfbands"], c["gal"], line_lambda=c["lines"])
+    # the optical grid ends at 160 um rest, SPIRE filters at 1000 um observed: below z = 5.25 a bulge does
+    # not cover them and its flux is 0 (src/egg-gencat.cpp:2198), while the disk (with the IR template) does
+    lowz = c["gal"]["z"] < 5.0
+    assert lowz.sum() > 10
+    assert np.all(out["flux_bulge"][lowz][:, -3:] == 0.0)
+    assert np.all(out["flux_disk"][:, -3:] > 0.0)
+
+
+def test_f32_storage_of_the_reference_moves_fluxes_by_less_than_the_fp32_tolerance():
+    """The reference keeps its per-galaxy temporaries in vec1f; emulating that rounding in the oracle
+    bounds how far the real egg binary can sit from the all-double contract."""
+    c = cases.make("b30_no_nebular", ngal=64)
+    a = Oracle(c["opt"], c["ir"], c["bands"], **c["opts"]).compute(c["gal"], f64=True)
+    b = Oracle(c["opt"], c["ir"], c["bands"], emulate_f32=True, **c["opts"]).compute(c["gal"], f64=True)
+    e = cases.rel_err(b["flux_disk"], a["flux_disk"], floor_frac=1e-6)
+    assert np.quantile(e, 0.99) < 1e-5
