@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(256) sed_kernel(const __grid_constant__ SedPar
     if ((int)threadIdx.x < p.nline) {
         const int l = threadIdx.x;
         int b0 = 1, b1 = 0;
-        if (ll != nullptr && ll[g * p.nline + l] != 0.0f) {
+        if (ll != nullptr && ll[g * p.nline + p.line_col[l]] != 0.0f) {
             const double l0 = (double)p.line_lambda[l], lw = l0 * (s.vdisp / 2.998e5);
             int lo = last_le(x, n, l0 - 10 * lw), hi = last_le(x, n, l0 + 10 * lw) + 1;
             if (!(hi == 0 || lo == n - 1)) { b0 = lo < 0 ? 0 : lo; b1 = hi >= n ? n - 1 : hi; }
@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(256) sed_kernel(const __grid_constant__ SedPar
                 for (int k = l; k < p.nline; ++k)
                     if (b0s[k] <= j && j <= b1s[k]) {
                         const double l0 = (double)p.line_lambda[k], lw = l0 * (s.vdisp / 2.998e5);
-                        acc += line_bin(llow, lup, l0, lw, (double)ll[g * p.nline + k] * l0, p.line_average);
+                        acc += line_bin(llow, lup, l0, lw, (double)ll[g * p.nline + p.line_col[k]] * l0, p.line_average);
                     }
                 S[j] += xj * acc;
             }
