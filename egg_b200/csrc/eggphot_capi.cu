@@ -57,7 +57,7 @@ struct eggphot_ctx {
     cudaStream_t stream = nullptr;
     // prepared tables on the device
     std::vector<DevBuf> blobs;
-    DevBuf xB, xD, xBhl, xDhl, lutB, lutD, rowsB, rowsDopt, rowsDir, rowsDpah, opt_use, rfB, rfD, rfW, errflag, scratch;
+    DevBuf xB, xD, xBhl, xDhl, lutB, lutD, rowsB, rowsDopt, rowsDir, rowsDpah, opt_use, rfB, rfD, rfW, errflag, scratch, u_oleft, u_ofrac, u_prevopt, u_isopt;
     int strideB = 0, strideD = 0;
     FluxParams base{};
     int grid_blocks = 0;
@@ -216,6 +216,16 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
     CK(upload_rows(c->rowsDir, P.rows_disk_ir, P.nir_sed, P.grid_disk.n(), c->strideD, P.precision, tb));
     CK(upload_rows(c->rowsDpah, P.rows_disk_pah, P.nir_sed, P.grid_disk.n(), c->strideD, P.precision, tb));
     if (!P.opt_use.empty()) CK(c->opt_use.upload(P.opt_use.data(), P.opt_use.size()));
+    if (!P.u_oleft.empty()) {
+        CK(c->u_oleft.upload(P.u_oleft.data(), P.u_oleft.size() * sizeof(int32_t)));
+        CK(c->u_prevopt.upload(P.u_prevopt.data(), P.u_prevopt.size() * sizeof(uint16_t)));
+        CK(c->u_isopt.upload(P.u_isopt.data(), P.u_isopt.size()));
+        if (P.precision == EGGPHOT_FP64) CK(c->u_ofrac.upload(P.u_ofrac.data(), P.u_ofrac.size() * sizeof(double)));
+        else {
+            std::vector<float> f(P.u_ofrac.begin(), P.u_ofrac.end());
+            CK(c->u_ofrac.upload(f.data(), f.size() * sizeof(float)));
+        }
+    }
     c->blobs.resize(P.groups.size());
     for (size_t g = 0; g < P.groups.size(); ++g) {
         CK(c->blobs[g].upload(P.groups[g].blob.data(), P.groups[g].blob.size()));
@@ -263,6 +273,8 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
     p.igmD[0] = gd.lz; p.igmD[1] = gd.l0; p.igmD[2] = gd.l1; p.igmD[3] = gd.l2;
     p.rowsB = c->rowsB.p; p.rowsDopt = c->rowsDopt.p; p.rowsDir = c->rowsDir.p; p.rowsDpah = c->rowsDpah.p;
     p.opt_use = (const uint8_t *)c->opt_use.p;
+    p.u_oleft = (const int32_t *)c->u_oleft.p; p.u_ofrac = c->u_ofrac.p;
+    p.u_prevopt = (const uint16_t *)c->u_prevopt.p; p.u_isopt = (const uint8_t *)c->u_isopt.p;
     p.nopt_sed = P.nopt_sed; p.nir_sed = P.nir_sed;
     p.ir_kind = P.ir_kind; p.disk_mode = (int)P.disk_mode; p.has_bulge = P.has_bulge; p.apply_igm = P.apply_igm;
     p.nline = P.no_nebular ? 0 : (int)P.line_lambda.size();
@@ -296,7 +308,7 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
         if (occ <= 0) return c->fail(EGGPHOT_ERR_CUDA, "flux kernel cannot be resident (occupancy query failed)");
         c->grid_blocks = c->num_sms * occ;
         const size_t rs = P.precision == EGGPHOT_FP64 ? 8 : 4;
-        c->scratch_region_bytes = ((size_t)c->grid_blocks * kBatch * (size_t)(c->strideD + c->strideB) * rs + 255) & ~size_t(255);
+        c->scratch_region_bytes = ((size_t)c->grid_blocks * kBatch * (size_t)(2 * c->strideD + c->strideB) * rs + 255) & ~size_t(255);
         CK(c->scratch.alloc(c->scratch_region_bytes * (kSlots + 1)));
         p.scratch = c->scratch.p;
     }

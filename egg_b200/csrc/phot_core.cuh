@@ -66,6 +66,7 @@ struct __attribute__((aligned(16))) BandHeader {
     float fcf, nif, ncf, tf0f, tflf, bkt_inv_wf; // f32 mirrors of the above
     float tot0h, tot0l, tot1h, tot1l; // tot0/NI, tot1/NC as hi+lo; hi is a multiple of 2^-23
     float inv_nif, inv_ncf, ni_ncf, cost; // 1/NI, 1/NC, NI/NC; cost = scheduling weight (typical node count)
+    float l2first, l2last;        // log2(eff_first), log2(eff_last) in lookup buckets (x kLutPerOctave)
     uint32_t n;                   // nodes in the effective span (>= 2), or 0 if the response is identically 0
     uint32_t nbkt;                // buckets
     uint32_t node_off;            // byte offset of the FilterNode array
@@ -73,9 +74,9 @@ struct __attribute__((aligned(16))) BandHeader {
     uint32_t out_col;             // column in the sorted band list
     uint32_t split;               // cells 0..split accumulate from the left end, cells > split from the right
     uint32_t tflo_off;            // fp32 tables: byte offset of the float array of low parts of tf
-    uint32_t pad;
+    uint32_t pad[3];
 };
-static_assert(sizeof(BandHeader) == 192, "BandHeader layout");
+static_assert(sizeof(BandHeader) == 208, "BandHeader layout");
 
 template <typename real> struct NodeOf;
 template <> struct NodeOf<float> { typedef FilterNodeF type; };
@@ -87,7 +88,7 @@ template <> struct NodeQ<float> {
     float i0h, i0l, c1h, c1l; // prefix values of the node's filter cell (offset/scaled, hi+lo)
     float p0;                 // integral of R over the part of the cell left of the node
     float hru;                // R_i * u^2 / 2
-    float R;                  // R_i (used by the node's own interval only; never shuffled)
+    float R;                  // R_i (used by the node's own interval only; never exchanged)
 };
 template <> struct NodeQ<double> {
     double i0, c1, p0, hru, R;
@@ -127,23 +128,32 @@ EGG_HD void node_quantities(const FilterNodeD &e, double u, NodeQ<double> &q) {
     q.R = e.R;
 }
 
-EGG_HD float rl_R(const NodeQ<float> &q, float, float) { return q.R; }
-EGG_HD double rl_R(const NodeQ<double> &q, double, double) { return q.R; }
+// Geometry of one SED interval against the band: everything that does not depend on the SED values.
+// The contribution of an SED with end values (S_l, S_r) is then
+//     general   : S_l*q + sigma*m,                         sigma = (S_r - S_l)/(t_r - t_l)
+//     same cell : (rho_l*S(tel) + rho_r*S(ter))/2 * dte    (both ends in one filter cell: the union grid has no
+//                 node in between, the interval is a single trapezoid; evaluated directly it is exact, cannot go
+//                 negative for non-negative R and S, and keeps full relative accuracy for a narrow SED feature
+//                 inside a wide filter cell)
+// so that several SEDs sampled on the same nodes (disk, and bulge resampled on the disk grid) share it.
+template <typename real> struct IntervalW {
+    real q, m, inv_dt;
+    real rho_l, rho_r, dte, xs, xr; // xs / xr: effective left / right end minus the TRUE left position
+    bool same;
+};
 
-// Contribution T_j of one SED interval.
-//   left node : true position tl (+ low part tll in fp32), offset ul inside its filter cell, value Sl,
-//               quantities ql, its filter cell (s, dl), cell index il
-//   right node: tr (+ trl), Sr, qr, cell index ir
+//   left node : true position tl (+ low part tll in fp32), offset ul inside its filter cell, quantities ql,
+//               its filter cell (s, dl), cell index il
+//   right node: tr (+ trl), qr, cell index ir
 //   dte = effective (clamped) interval width;  xr = effective right position minus TRUE left position
-// Returns S_l*q + sigma*m in the band's natural units (response * wavelength * S).
-EGG_HD float interval_flux(float tl, float tll, float Sl, const NodeQ<float> &ql, float s_l, float dl_l, float ul,
-                           int il, float tr, float trl, float Sr, const NodeQ<float> &qr, int ir, float dte, float xr,
-                           const BandScal<float> &bs) {
+EGG_HD void interval_weights(float tl, float tll, const NodeQ<float> &ql, float s_l, float dl_l, float ul, int il,
+                             float tr, float trl, const NodeQ<float> &qr, int ir, float dte, float xr,
+                             const BandScal<float> &bs, IntervalW<float> &w) {
     const float dt = (tr - tl) + (trl - tll);
 #if defined(__CUDA_ARCH__)
-    const float sigma = dt > 0.0f ? __fdividef(Sr - Sl, dt) : 0.0f; // 2 ulp; enters only the slope term
+    w.inv_dt = dt > 0.0f ? __frcp_rn(dt) : 0.0f;
 #else
-    const float sigma = dt > 0.0f ? (Sr - Sl) / dt : 0.0f;
+    w.inv_dt = dt > 0.0f ? 1.0f / dt : 0.0f;
 #endif
     // prefix values left of `split` are measured from the band's left end, right of it from the
     // right end (so that a far wing is not differenced against the whole band): an interval that
@@ -154,37 +164,50 @@ EGG_HD float interval_flux(float tl, float tll, float Sl, const NodeQ<float> &ql
     const float d0l = (qr.i0l - ql.i0l) + (cross ? bs.tot0l : 0.0f);
     const float d1h = (qr.c1h - ql.c1h) + (cross ? bs.tot1h : 0.0f);
     const float d1l = (qr.c1l - ql.c1l) + (cross ? bs.tot1l : 0.0f);
-    const float q = fmaf(d0h + d0l, bs.ni, qr.p0 - ql.p0);
+    w.q = fmaf(d0h + d0l, bs.ni, qr.p0 - ql.p0);
     // [dC1 - t_l*dI0] in table units: NC*[ (dC1h - tau*dI0h) + (dC1l - tau*dI0l) ], tau = t_l*NI/NC in hi+lo
     const float tauh = tl * bs.ni_nc, taul = tll * bs.ni_nc;
     const float r = fmaf(-tauh, d0h, d1h) + fmaf(-tauh, d0l, fmaf(-taul, d0h, d1l));
     const float bmt = (ir == il) ? dte : (dl_l - ul); // B - t_l
     const float corr = 0.5f * s_l * ul * bmt * (bmt + ul);
-    const float m = fmaf(r, bs.nc, fmaf(qr.p0, xr, (ql.hru - qr.hru) - corr));
-    // both ends in one filter cell: the union grid has no node in between, so the interval is a single
-    // trapezoid; evaluated directly it keeps full relative accuracy for a narrow SED feature inside a
-    // wide filter cell (the general form would difference two partial-cell integrals there)
-    const float rho_l = fmaf(s_l, ul, rl_R(ql, s_l, ul)), rho_r = fmaf(s_l, dte, rho_l);
-    const float Sel = fmaf(sigma, xr - dte, Sl), Ser = fmaf(sigma, xr, Sl); // S at the effective ends
-    const float same = 0.5f * fmaf(rho_l, Sel, rho_r * Ser) * dte;
-    return ir == il ? same : fmaf(Sl, q, sigma * m);
+    w.m = fmaf(r, bs.nc, fmaf(qr.p0, xr, (ql.hru - qr.hru) - corr));
+    w.rho_l = fmaf(s_l, ul, ql.R);
+    w.rho_r = fmaf(s_l, dte, w.rho_l);
+    w.dte = dte; w.xr = xr; w.xs = xr - dte;
+    w.same = ir == il;
 }
-EGG_HD double interval_flux(double tl, double, double Sl, const NodeQ<double> &ql, double s_l, double dl_l,
-                            double ul, int il, double tr, double, double Sr, const NodeQ<double> &qr, int ir, double dte,
-                            double xr, const BandScal<double> &bs) {
+EGG_HD void interval_weights(double tl, double, const NodeQ<double> &ql, double s_l, double dl_l, double ul, int il,
+                             double tr, double, const NodeQ<double> &qr, int ir, double dte, double xr,
+                             const BandScal<double> &bs, IntervalW<double> &w) {
     const double dt = tr - tl;
-    const double sigma = dt > 0.0 ? (Sr - Sl) / dt : 0.0;
+    w.inv_dt = dt > 0.0 ? 1.0 / dt : 0.0;
     const bool cross = il <= bs.split && ir > bs.split;
     const double d0 = (qr.i0 - ql.i0) + (cross ? bs.tot0h : 0.0);
     const double d1 = (qr.c1 - ql.c1) + (cross ? bs.tot1h : 0.0);
-    const double q = d0 + (qr.p0 - ql.p0);
+    w.q = d0 + (qr.p0 - ql.p0);
     const double bmt = (ir == il) ? dte : (dl_l - ul);
     const double corr = 0.5 * s_l * ul * bmt * (bmt + ul);
-    const double m = fma(-tl, d0, d1) + fma(qr.p0, xr, (ql.hru - qr.hru) - corr);
-    const double rho_l = fma(s_l, ul, rl_R(ql, s_l, ul)), rho_r = fma(s_l, dte, rho_l);
-    const double Sel = fma(sigma, xr - dte, Sl), Ser = fma(sigma, xr, Sl);
-    const double same = 0.5 * fma(rho_l, Sel, rho_r * Ser) * dte;
-    return ir == il ? same : fma(Sl, q, sigma * m);
+    w.m = fma(-tl, d0, d1) + fma(qr.p0, xr, (ql.hru - qr.hru) - corr);
+    w.rho_l = fma(s_l, ul, ql.R);
+    w.rho_r = fma(s_l, dte, w.rho_l);
+    w.dte = dte; w.xr = xr; w.xs = xr - dte;
+    w.same = ir == il;
+}
+
+// Contribution of an SED with end values (Sl, Sr) to the interval; also returns its slope.
+EGG_HD float interval_apply(const IntervalW<float> &w, float Sl, float Sr, float &sigma) {
+    sigma = (Sr - Sl) * w.inv_dt;
+    const float gen = fmaf(Sl, w.q, sigma * w.m);
+    const float Sel = fmaf(sigma, w.xs, Sl), Ser = fmaf(sigma, w.xr, Sl);
+    const float same = 0.5f * fmaf(w.rho_l, Sel, w.rho_r * Ser) * w.dte;
+    return w.same ? same : gen;
+}
+EGG_HD double interval_apply(const IntervalW<double> &w, double Sl, double Sr, double &sigma) {
+    sigma = (Sr - Sl) * w.inv_dt;
+    const double gen = fma(Sl, w.q, sigma * w.m);
+    const double Sel = fma(sigma, w.xs, Sl), Ser = fma(sigma, w.xr, Sl);
+    const double same = 0.5 * fma(w.rho_l, Sel, w.rho_r * Ser) * w.dte;
+    return w.same ? same : gen;
 }
 
 // Compensated accumulation (TwoSum, branch-free): the "compensated sum" of the fp32 mode.
@@ -215,7 +238,11 @@ EGG_HD int find_cell(TfGet tfget, const uint16_t *bkt, int nbkt, real tf0, real 
         do { --lo; } while (lo > 0 && tfget(lo) > te);
         return lo < 0 ? 0 : lo;
     }
-    while (lo < n - 2 && tfget(lo + 1) <= te) ++lo;
+    // buckets are finer than the cells: one or two steps almost always settle it
+    if (lo < n - 2 && tfget(lo + 1) <= te) ++lo;
+    if (lo < n - 2 && tfget(lo + 1) <= te) {
+        do { ++lo; } while (lo < n - 2 && tfget(lo + 1) <= te);
+    }
     return lo;
 }
 
@@ -296,12 +323,30 @@ EGG_HD void eval_node(const BandView<real> &b, real t, real tl, real S, NodeStat
 }
 
 template <typename real>
-EGG_HD real eval_interval(const BandView<real> &b, const NodeState<real> &l, const NodeState<real> &r) {
+EGG_HD void eval_weights(const BandView<real> &b, const NodeState<real> &l, const NodeState<real> &r, IntervalW<real> &w) {
     const real tel = clampr(l.t, b.tf0, b.tfl), ter = clampr(r.t, b.tf0, b.tfl);
     const real terl = ter == r.t ? r.tl : real(0), tell = tel == l.t ? l.tl : real(0);
     const real dte = (ter - tel) + (terl - tell);
     const real xr = (ter - l.t) + (terl - l.tl);
-    return interval_flux(l.t, l.tl, l.S, l.q, l.s, l.dl, l.u, l.cell, r.t, r.tl, r.S, r.q, r.cell, dte, xr, b.bs);
+    interval_weights(l.t, l.tl, l.q, l.s, l.dl, l.u, l.cell, r.t, r.tl, r.q, r.cell, dte, xr, b.bs, w);
+}
+template <typename real>
+EGG_HD real eval_interval(const BandView<real> &b, const NodeState<real> &l, const NodeState<real> &r) {
+    IntervalW<real> w;
+    eval_weights(b, l, r, w);
+    real sigma;
+    return interval_apply(w, l.S, r.S, sigma);
+}
+
+// A second SED on the same weights: the bulge's optical template lives on a SUBSET of the disk grid's
+// nodes (merge_add's union grid).  Resampled linearly onto the disk grid it is the same function, so its
+// integral against R is unchanged; what changes is the trapezoid's error term, sum over union cells of
+// s_R*sigma_S*h^3/6, because the extra (IR-only) nodes split union cells the reference does not split.
+// Undoing the split at an IR-only node at distance h1 from the previous node the reference keeps (optical
+// node or filter node) and h2 from the next node of the fine union grid adds  s*sigma*h1*h2*(h1+h2)/2.
+template <typename real>
+EGG_HD real unsplit_correction(real s_cell, real sigma, real h1, real h2) {
+    return real(0.5) * s_cell * sigma * h1 * h2 * (h1 + h2);
 }
 
 // IGM factor of node j (src/egg-gencat.cpp:2128-2139): [0,lz) -> 0, [lz,l0) -> a0, [l0,l1) -> a1, [l1,l2) -> a2

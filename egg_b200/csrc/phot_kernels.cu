@@ -65,6 +65,8 @@ struct GalScal {
     double a_disk;   // 10^(m_disk  - m2lcor)
     double c1, c2;   // IR: L_IR (generic, :2055) or Mdust(1-fPAH), Mdust fPAH (cs17, :2047-2051)
     double vdisp;
+    double iopz;     // 1/(1+z)
+    float l2opz;     // log2(1+z) * kLutPerOctave
     float igm[3];
     uint32_t row_b, row_d, row_i;
 };
@@ -72,6 +74,8 @@ struct GalScal {
 __device__ void gal_scalars(const FluxParams &p, uint64_t g, GalScal &s) {
     const double z = p.z[g], d = p.d[g];
     s.opz = 1.0 + z;
+    s.iopz = 1.0 / s.opz;
+    s.l2opz = (float)(log2(s.opz) * kLutPerOctave);
     s.aflux = EGGPHOT_LSUN2UJY * (1.0 + z) / (d * d);
     const float m2l = p.m2lcor[g];
     // the reference passes the FLOAT difference m[i]-out.m2lcor[i] to e10 (src/egg-gencat.cpp:2106, 2114)
@@ -109,9 +113,10 @@ __device__ void gal_scalars(const FluxParams &p, uint64_t g, GalScal &s) {
 // ---- small helpers ---------------------------------------------------------------------------------
 // last j in [0, n) with x[j] <= v (-1 if none), started from the log2 lookup of the grid: the table
 // entry is at most a couple of nodes away, and the two scans make the answer exact in double.
+__device__ __forceinline__ float lut_pos(double v, int e0) { return (__log2f((float)v) - (float)e0) * (float)kLutPerOctave; }
 __device__ __forceinline__ int lut_last_le(const double *__restrict__ x, int n, const uint16_t *__restrict__ lut,
-                                           int nlut, int e0, double v) {
-    int k = (int)((__log2f((float)v) - (float)e0) * (float)kLutPerOctave);
+                                           int nlut, float kpos, double v) {
+    int k = (int)kpos;
     k = max(0, min(k, nlut - 1));
     int j = __ldg(lut + k);
     while (j >= 0 && __ldg(x + j) > v) --j;
@@ -120,8 +125,8 @@ __device__ __forceinline__ int lut_last_le(const double *__restrict__ x, int n, 
 }
 // first j in [0, n) with x[j] >= v (n if none)
 __device__ __forceinline__ int lut_first_ge(const double *__restrict__ x, int n, const uint16_t *__restrict__ lut,
-                                            int nlut, int e0, double v) {
-    int k = (int)((__log2f((float)v) - (float)e0) * (float)kLutPerOctave);
+                                            int nlut, float kpos, double v) {
+    int k = (int)kpos;
     k = max(0, min(k, nlut - 1));
     int j = __ldg(lut + k); // candidate for the last node < v
     while (j >= 0 && __ldg(x + j) >= v) --j;
@@ -217,8 +222,8 @@ __host__ __device__ inline SmemLayout smem_layout(const FluxParams &p) {
 // per-CTA global scratch that stays in L2), B (for each band group: tables -> shared memory by TMA,
 // warps pull (galaxy, band, component) items off a shared counter and integrate them) and C
 // (totals, data conditions, coalesced stores).
-template <typename real>
-__global__ void __launch_bounds__(kThreads, 1) flux_kernel(const __grid_constant__ FluxParams p) {
+template <typename real, int NT>
+__global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ FluxParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ GalScal sc[kBatch];
     __shared__ __align__(8) uint64_t bar_tab;
@@ -234,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) flux_kernel(const __grid_constant
     const int ncomp = p.has_bulge ? 2 : 1;
     const bool cs17 = p.ir_kind == EGGPHOT_IR_CS17;
     const int nbt = (int)p.nband_total, nrf = p.do_rf ? (int)p.nrf : 0;
-    const int sstride = p.strideD + p.strideB;
+    const int sstride = 2 * p.strideD + p.strideB; // disk | bulge on its own grid | bulge on the disk grid
     real *scr = reinterpret_cast<real *>(p.scratch) + (size_t)blockIdx.x * kBatch * sstride;
     const real *rO = reinterpret_cast<const real *>(p.rowsDopt), *rI = reinterpret_cast<const real *>(p.rowsDir);
     const real *rP = reinterpret_cast<const real *>(p.rowsDpah), *rB = reinterpret_cast<const real *>(p.rowsB);
@@ -255,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) flux_kernel(const __grid_constant
         // ---- phase A1: per-galaxy scalars, one thread per galaxy
         if (tid < ng) gal_scalars(p, g0 + tid, sc[tid]);
         if (tid >= 32 && tid < 32 + kMaxGroups) item_ctr[tid - 32] = 0;
-        for (int i = tid; i < ng * nbt * 2; i += kThreads) res[i] = 0.0;
+        for (int i = tid; i < ng * nbt * 2; i += NT) res[i] = 0.0;
         __syncthreads();
 
         // ---- phase A2: rest-frame SEDs (get_opt_sed / get_ir_sed / merge_add / IGM) into the scratch;
@@ -267,25 +272,25 @@ __global__ void __launch_bounds__(kThreads, 1) flux_kernel(const __grid_constant
             const real g0f = s.igm[0], g1f = s.igm[1], g2f = s.igm[2];
             const real *ro = rO + (size_t)s.row_d * p.strideD, *ri = rI + (size_t)s.row_i * p.strideD;
             const real *rp = rP + (size_t)s.row_i * p.strideD;
-            for (int j = tid; j < p.nD; j += kThreads) {
+            for (int j = tid; j < p.nD; j += NT) {
                 real v;
                 if (p.disk_mode == 0) v = a_d * __ldg(ro + j) + c1 * __ldg(ri + j);
                 else if (p.disk_mode == 1) v = a_d * __ldg(ro + j);
                 else v = c1 * __ldg(ri + j);
                 if (p.disk_mode != 1 && cs17) v += c2 * __ldg(rp + j);
-                if (p.apply_igm) v *= igm_factor<real>(j, p.igmD[0], p.igmD[1], p.igmD[2], p.igmD[3], g0f, g1f, g2f);
+                if (p.apply_igm && j < p.igmD[3]) v *= igm_factor<real>(j, p.igmD[0], p.igmD[1], p.igmD[2], p.igmD[3], g0f, g1f, g2f);
                 SD[j] = v;
             }
             if (p.has_bulge) {
                 const real *rb = rB + (size_t)s.row_b * p.strideB;
-                for (int j = tid; j < p.nB; j += kThreads) {
+                for (int j = tid; j < p.nB; j += NT) {
                     real v = __ldg(rb + j);
-                    if (p.apply_igm) v *= igm_factor<real>(j, p.igmB[0], p.igmB[1], p.igmB[2], p.igmB[3], g0f, g1f, g2f);
+                    if (p.apply_igm && j < p.igmB[3]) v *= igm_factor<real>(j, p.igmB[0], p.igmB[1], p.igmB[2], p.igmB[3], g0f, g1f, g2f);
                     SB[j] = v;
                 }
             }
         }
-        for (int idx = tid; idx < ng * 2 * p.nline; idx += kThreads) {
+        for (int idx = tid; idx < ng * 2 * p.nline; idx += NT) {
             const int gi = idx / (2 * p.nline), rem = idx % (2 * p.nline);
             const int c = rem / p.nline, l = rem % p.nline; // c: 0 bulge, 1 disk
             const GalScal &s = sc[gi];
@@ -298,8 +303,8 @@ __global__ void __launch_bounds__(kThreads, 1) flux_kernel(const __grid_constant
                 const int nlut = c ? p.lutD_n : p.lutB_n, e0 = c ? p.lutD_e0 : p.lutB_e0;
                 const double l0 = (double)p.line_lambda[l], lw = l0 * (s.vdisp / 2.998e5);
                 // [vif] bounds(lam, a, b) = {last <= a, first > b}  (src/egg-gencat.cpp:2081-2084)
-                const int lo = lut_last_le(x, n, lut, nlut, e0, l0 - 10 * lw);
-                const int hi = lut_last_le(x, n, lut, nlut, e0, l0 + 10 * lw) + 1; // first > b, n if none
+                const int lo = lut_last_le(x, n, lut, nlut, lut_pos(l0 - 10 * lw, e0), l0 - 10 * lw);
+                const int hi = lut_last_le(x, n, lut, nlut, lut_pos(l0 + 10 * lw, e0), l0 + 10 * lw) + 1; // first > b, n if none
                 if (!(hi == 0 || lo == n - 1)) {
                     b0 = lo < 0 ? 0 : lo;
                     b1 = hi >= n ? n - 1 : hi;
@@ -314,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) flux_kernel(const __grid_constant
         //      by wavelength, so their node windows [b0, b1] are ordered as well.  The first line whose
         //      window holds node j adds the contributions of all lines at j, in that order: no two threads
         //      touch the same node and the sum order is fixed.
-        for (int idx = tid; idx < ng * 2 * p.nline * kLineSlots; idx += kThreads) {
+        for (int idx = tid; idx < ng * 2 * p.nline * kLineSlots; idx += NT) {
             const int w = idx % kLineSlots, q = idx / kLineSlots; // q = (gi, c, l)
             const int gi = q / (2 * p.nline), rem = q % (2 * p.nline);
             const int c = rem / p.nline, l = rem % p.nline;
@@ -352,6 +357,26 @@ __global__ void __launch_bounds__(kThreads, 1) flux_kernel(const __grid_constant
         }
         __syncthreads();
 
+        // ---- phase A4: the bulge SED resampled on the disk grid (the same piece-wise linear function; lets
+        //      the quadrature of phase B serve both components from one set of interval weights)
+        if (p.has_bulge) {
+            const real *ofrac = reinterpret_cast<const real *>(p.u_ofrac);
+            for (int gi = 0; gi < ng; ++gi) {
+                const real *SB = scr + (size_t)gi * sstride + p.strideD;
+                real *SU = scr + (size_t)gi * sstride + p.strideD + p.strideB;
+                for (int j = tid; j < p.nD; j += NT) {
+                    const int o = __ldg(p.u_oleft + j);
+                    real v = real(0);
+                    if (o >= 0) {
+                        v = SB[o];
+                        if (!__ldg(p.u_isopt + j)) v = fma(__ldg(ofrac + j), SB[o + 1] - v, v);
+                    }
+                    SU[j] = v;
+                }
+            }
+            __syncthreads();
+        }
+
         // ---- phase B: band groups
         for (int grp = 0; grp < (int)p.ngroups || (grp == 0 && nrf > 0); ++grp) {
             const int nb = grp < (int)p.ngroups ? (int)p.groups[grp].nb : 0;
@@ -367,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) flux_kernel(const __grid_constant
                 tab_phase ^= 1;
                 loaded = grp;
             }
-            const int nband_items = nb * ncomp * kBatch;
+            const int nband_items = nb * kBatch;
             const int nitems = nband_items + (grp == 0 ? nrf * ncomp * kBatch : 0);
             for (;;) {
                 int idx = 0;
@@ -375,58 +400,85 @@ __global__ void __launch_bounds__(kThreads, 1) flux_kernel(const __grid_constant
                 idx = __shfl_sync(kFull, idx, 0);
                 if (idx >= nitems) break;
                 if (idx < nband_items) {
-                    // (band, component, galaxy slot): bands are stored in decreasing order of expected work
-                    const int gi = idx & (kBatch - 1), t2 = idx / kBatch;
+                    // (band, galaxy slot), both components: bands are stored in decreasing order of expected work
+                    const int gi = idx & (kBatch - 1), bi = idx / kBatch;
                     if (gi >= ng) continue;
-                    const int comp = p.has_bulge ? (t2 & 1) : 1, bi = p.has_bulge ? (t2 >> 1) : t2; // comp: 0 bulge, 1 disk
                     const BandHeader &h = hdr[bi];
                     const GalScal &s = sc[gi];
-                    const double *x = comp ? p.xD : p.xB;
-                    const int n = comp ? p.nD : p.nB;
+                    const double *x = p.xD;
+                    const int n = p.nD;
                     // [vif] sed2flux: NaN (-> flux 0, src/egg-gencat.cpp:2198) unless the SED covers the filter
                     const bool covered = n >= 2 && __ldg(x) * s.opz <= h.full_first && __ldg(x + n - 1) * s.opz >= h.full_last;
                     if (!covered || h.n < 2) continue;
-                    const uint16_t *lut = comp ? p.lutD : p.lutB;
-                    const int nlut = comp ? p.lutD_n : p.lutB_n, e0 = comp ? p.lutD_e0 : p.lutB_e0;
-                    const double iopz = 1.0 / s.opz;
-                    const int jlo = max(lut_last_le(x, n, lut, nlut, e0, h.eff_first * iopz * (1.0 - 1e-15)), 0);
-                    const int jhi = min(lut_first_ge(x, n, lut, nlut, e0, h.eff_last * iopz * (1.0 + 1e-15)), n - 1);
+                    const bool bulge_on = p.has_bulge && p.nB >= 2 && __ldg(p.xB) * s.opz <= h.full_first &&
+                                          __ldg(p.xB + p.nB - 1) * s.opz >= h.full_last;
+                    // rest-frame ends of the filter span; their lookup buckets come from log2(lambda) - log2(1+z)
+                    const float koff = (float)p.lutD_e0 * (float)kLutPerOctave + s.l2opz;
+                    const int jlo = max(lut_last_le(x, n, p.lutD, p.lutD_n, h.l2first - koff, h.eff_first * s.iopz * (1.0 - 1e-15)), 0);
+                    const int jhi = min(lut_first_ge(x, n, p.lutD, p.lutD_n, h.l2last - koff, h.eff_last * s.iopz * (1.0 + 1e-15)), n - 1);
                     if (jhi <= jlo) continue;
                     BandView<real> bv;
                     make_band_view(blob, h, bv);
-                    const real *S = scr + (size_t)gi * sstride + (comp ? 0 : p.strideD);
+                    const real *SD = scr + (size_t)gi * sstride;
+                    const real *SU = SD + p.strideD + p.strideB;
                     GridAcc<real> ga;
                     if constexpr (sizeof(real) == 4) {
                         const float oh = (float)s.opz;
-                        ga.hl = comp ? p.xDhl : p.xBhl;
+                        ga.hl = p.xDhl;
                         ga.opz_hi = oh; ga.opz_lo = (float)(s.opz - (double)oh);
                     } else {
                         ga.x = x; ga.opz = s.opz;
                     }
-                    CompSum<real> acc;
-                    acc.clear();
+                    CompSum<real> accd, accb;
+                    accd.clear();
+                    accb.clear();
                     int j = min(jlo + lane, jhi);
-                    real tc, tcl, Sc = S[j];
+                    real tc, tcl, Sc = SD[j], Bc = bulge_on ? SU[j] : real(0);
                     ga.pos(j, bv.fc, tc, tcl);
                     for (int jbase = jlo; jbase < jhi; jbase += 31) {
                         const bool live = lane < 31 && jbase + lane < jhi;
                         // next pass's inputs first: their latency hides behind this pass's arithmetic
                         const int jn = min(jbase + 31 + lane, jhi);
                         real tn, tnl;
-                        const real Sn = S[jn];
+                        const real Sn = SD[jn], Bn = bulge_on ? SU[jn] : real(0);
                         ga.pos(jn, bv.fc, tn, tnl);
                         NodeState<real> nl, nr;
                         eval_node<real>(bv, tc, tcl, Sc, nl);
                         shfl_node(nl, nr);
-                        const real T = eval_interval<real>(bv, nl, nr);
-                        if (live) acc.add(T);
-                        tc = tn; tcl = tnl; Sc = Sn;
+                        IntervalW<real> w;
+                        eval_weights<real>(bv, nl, nr, w);
+                        real sg;
+                        const real T = interval_apply(w, nl.S, nr.S, sg);
+                        if (live) accd.add(T);
+                        if (bulge_on) {
+                            const real Br = __shfl_down_sync(kFull, Bc, 1);
+                            real TB = interval_apply(w, Bc, Br, sg);
+                            // an IR-only left node strictly inside the filter span splits a union cell the optical
+                            // grid does not split: undo it (unsplit_correction)
+                            const int jj = min(jbase + lane, jhi);
+                            const bool fix = live && !__ldg(p.u_isopt + jj) && nl.t > bv.tf0 && nl.t < bv.tfl;
+                            if (__any_sync(kFull, fix)) {
+                                real tp, tpl;
+                                ga.pos(fix ? (int)__ldg(p.u_prevopt + jj) : jj, bv.fc, tp, tpl);
+                                const real h1 = min((nl.t - tp) + (nl.tl - tpl), nl.u);
+                                const real h2 = min((nr.t - nl.t) + (nr.tl - nl.tl), nl.dl - nl.u);
+                                if (fix) TB += unsplit_correction<real>(nl.s, sg, h1, h2);
+                            }
+                            if (live) accb.add(TB);
+                        }
+                        tc = tn; tcl = tnl; Sc = Sn; Bc = Bn;
                     }
-                    acc = warp_reduce(acc);
+                    accd = warp_reduce(accd);
+                    if (bulge_on) accb = warp_reduce(accb);
                     if (lane == 0) {
-                        double f = ((double)acc.s + (double)acc.c) * s.aflux * (comp ? 1.0 : s.a_bulge);
+                        double f = ((double)accd.s + (double)accd.c) * s.aflux;
                         if (!isfinite(f)) f = 0.0; // src/egg-gencat.cpp:2198
-                        res[(gi * nbt + (int)h.out_col) * 2 + comp] = f;
+                        res[(gi * nbt + (int)h.out_col) * 2 + 1] = f;
+                        if (bulge_on) {
+                            double fb = ((double)accb.s + (double)accb.c) * s.aflux * s.a_bulge;
+                            if (!isfinite(fb)) fb = 0.0;
+                            res[(gi * nbt + (int)h.out_col) * 2] = fb;
+                        }
                     }
                 } else {
                     // rest-frame magnitude: dot product with the z = 0 weights (src/egg-gencat.cpp:2150-2158)
@@ -450,7 +502,7 @@ __global__ void __launch_bounds__(kThreads, 1) flux_kernel(const __grid_constant
         }
 
         // ---- phase C: totals (src/egg-gencat.cpp:2238-2239) and coalesced stores
-        for (int i = tid; i < ng * nbt; i += kThreads) {
+        for (int i = tid; i < ng * nbt; i += NT) {
             const float fb = (float)res[2 * i], fd = (float)res[2 * i + 1];
             const size_t o = (size_t)g0 * nbt + i;
             if (p.flux_disk) p.flux_disk[o] = fd;
@@ -459,7 +511,7 @@ __global__ void __launch_bounds__(kThreads, 1) flux_kernel(const __grid_constant
             if (p.flux_disk_f64) p.flux_disk_f64[o] = res[2 * i + 1];
             if (p.flux_bulge_f64) p.flux_bulge_f64[o] = res[2 * i];
         }
-        for (int i = tid; i < ng * nrf; i += kThreads) {
+        for (int i = tid; i < ng * nrf; i += NT) {
             // [vif] lsun2uJy(0, 1e-5, ...) then uJy2mag; non-finite -> +99 (src/egg-gencat.cpp:2152-2156)
             const double arf = EGGPHOT_LSUN2UJY / (1e-5 * 1e-5);
             double mg[2] = {0.0, 0.0}; // the bulge column stays 0 when there is no bulge pass (no_stellar)
@@ -556,10 +608,15 @@ __global__ void __launch_bounds__(256) sed_kernel(const __grid_constant__ SedPar
 
 size_t flux_kernel_smem(const FluxParams &p, int) { return smem_layout(p).total; }
 
+template <typename real> struct Threads;
+template <> struct Threads<float> { static constexpr int n = 1024; };  // 64 registers per thread
+template <> struct Threads<double> { static constexpr int n = 640; };  // up to 102 registers per thread
+
 template <typename real> static int launch_t(const FluxParams &p, size_t smem, int blocks, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(flux_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    constexpr int NT = Threads<real>::n;
+    cudaError_t e = cudaFuncSetAttribute(flux_kernel<real, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    flux_kernel<real><<<blocks, kThreads, smem, st>>>(p);
+    flux_kernel<real, NT><<<blocks, NT, smem, st>>>(p);
     return (int)cudaGetLastError();
 }
 
@@ -569,18 +626,17 @@ int launch_flux_kernel(const FluxParams &p, int precision, int grid_blocks, cuda
                                      : launch_t<float>(p, smem, grid_blocks, stream);
 }
 
+template <typename real> static int occupancy_t(size_t smem) {
+    constexpr int NT = Threads<real>::n;
+    int nb = 0;
+    cudaError_t e = cudaFuncSetAttribute(flux_kernel<real, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, flux_kernel<real, NT>, NT, smem);
+    return e == cudaSuccess ? nb : -(int)e;
+}
+
 int flux_kernel_max_blocks_per_sm(const FluxParams &p, int precision) {
     const size_t smem = flux_kernel_smem(p, precision);
-    int nb = 0;
-    cudaError_t e;
-    if (precision == EGGPHOT_FP64) {
-        e = cudaFuncSetAttribute(flux_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, flux_kernel<double>, kThreads, smem);
-    } else {
-        e = cudaFuncSetAttribute(flux_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, flux_kernel<float>, kThreads, smem);
-    }
-    return e == cudaSuccess ? nb : -(int)e;
+    return precision == EGGPHOT_FP64 ? occupancy_t<double>(smem) : occupancy_t<float>(smem);
 }
 
 int launch_sed_kernel(const SedParams &q, int precision, cudaStream_t stream) {

@@ -11,8 +11,6 @@ namespace eggphot {
 
 constexpr int kMaxLines = 64;
 constexpr int kMaxGroupBands = 64;
-constexpr int kThreads = 768;          // 24 warps per CTA
-constexpr int kWarps = kThreads / 32;
 constexpr int kBatch = 16;             // galaxies a CTA carries through all band groups at a time
 constexpr int kMaxGroups = 16;
 constexpr int kMaxRf = 16;
@@ -44,7 +42,8 @@ struct FluxParams {
     uint32_t ngroups, max_blob;
     GroupDesc groups[kMaxGroups];
     int32_t do_rf;         // also compute the rest-frame magnitudes
-    // per-CTA scratch for the rest-frame SEDs of a batch: [grid][kBatch][strideD + strideB] real (stays in L2)
+    // per-CTA scratch for the rest-frame SEDs of a batch: [grid][kBatch][2*strideD + strideB] real (stays in L2):
+    // disk SED, bulge SED on its own grid, bulge SED resampled on the disk grid
     void *scratch;
     // component grids
     int32_t nB, nD;        // nodes (0 if the component is absent)
@@ -56,6 +55,11 @@ struct FluxParams {
     int32_t igmB[4], igmD[4]; // lz, l0, l1, l2
     // template rows in the kernel's real type
     const void *rowsB, *rowsDopt, *rowsDir, *rowsDpah;
+    // disk grid -> optical grid maps (Prepared::u_*), for the bulge evaluated on the disk grid
+    const int32_t *u_oleft;
+    const void *u_ofrac;   // real
+    const uint16_t *u_prevopt;
+    const uint8_t *u_isopt;
     const uint8_t *opt_use;
     uint32_t nopt_sed, nir_sed;
     int32_t ir_kind, disk_mode, has_bulge, apply_igm;

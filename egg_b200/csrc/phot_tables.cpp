@@ -161,6 +161,7 @@ Status build_band_table(const Filter &f, uint32_t out_col, int bucket_factor, Ba
     t.h.fcf = (float)t.h.fc; t.h.nif = (float)t.h.ni; t.h.ncf = (float)t.h.nc;
     t.h.tf0f = (float)t.h.tf0; t.h.tflf = (float)t.h.tfl; t.h.bkt_inv_wf = (float)t.h.bkt_inv_w;
     t.h.inv_nif = (float)(1.0 / t.h.ni); t.h.inv_ncf = (float)(1.0 / t.h.nc); t.h.ni_ncf = (float)(t.h.ni / t.h.nc);
+    t.h.l2first = (float)(std::log2(t.h.eff_first) * kLutPerOctave); t.h.l2last = (float)(std::log2(t.h.eff_last) * kLutPerOctave);
     t.bkt.assign(nbkt + 1, 0);
     int i = 0;
     for (int k = 0; k <= nbkt; ++k) {
@@ -250,8 +251,11 @@ RfWeights rf_weights(const BandTableD &t, const Grid &g) {
     for (int j = jlo; j < jhi; ++j) {
         NodeEval Rr = eval(j + 1);
         const double dte = Rr.te - L.te, xr = Rr.te - L.tt;
-        r.w[j - jlo] += interval_flux(L.tt, 0.0, 1.0, L.q, L.s, L.dl, L.u, L.cell, Rr.tt, 0.0, 0.0, Rr.q, Rr.cell, dte, xr, bs);
-        r.w[j + 1 - jlo] += interval_flux(L.tt, 0.0, 0.0, L.q, L.s, L.dl, L.u, L.cell, Rr.tt, 0.0, 1.0, Rr.q, Rr.cell, dte, xr, bs);
+        IntervalW<double> w;
+        double sg;
+        interval_weights(L.tt, 0.0, L.q, L.s, L.dl, L.u, L.cell, Rr.tt, 0.0, Rr.q, Rr.cell, dte, xr, bs, w);
+        r.w[j - jlo] += interval_apply(w, 1.0, 0.0, sg);
+        r.w[j + 1 - jlo] += interval_apply(w, 0.0, 1.0, sg);
         L = Rr;
     }
     return r;
@@ -515,6 +519,23 @@ Status prepare(const eggphot_libs &L, const eggphot_filters *bands, const eggpho
             resample(xi, L.ir_sed + (size_t)s * P.nir, P.grid_disk, &P.rows_disk_ir[(size_t)s * nd]);
             if (P.ir_kind == EGGPHOT_IR_CS17)
                 resample(xi, L.ir_pah + (size_t)s * P.nir, P.grid_disk, &P.rows_disk_pah[(size_t)s * nd]);
+        }
+    }
+
+    // ---- map of the disk grid onto the optical (bulge) grid
+    if (P.has_bulge) {
+        const int nd = P.grid_disk.n(), nb = P.grid_bulge.n();
+        P.u_oleft.assign(nd, -1); P.u_ofrac.assign(nd, 0.0); P.u_prevopt.assign(nd, 0); P.u_isopt.assign(nd, 0);
+        int o = -1, po = 0;
+        for (int j = 0; j < nd; ++j) {
+            const double xj = P.grid_disk.x[j];
+            while (o + 1 < nb && P.grid_bulge.x[o + 1] <= xj) ++o;
+            P.u_oleft[j] = o;
+            if (o >= 0 && P.grid_bulge.x[o] == xj) { P.u_isopt[j] = 1; po = j; }
+            else if (o >= 0 && o + 1 < nb)
+                P.u_ofrac[j] = (xj - P.grid_bulge.x[o]) / (P.grid_bulge.x[o + 1] - P.grid_bulge.x[o]);
+            P.u_prevopt[j] = (uint16_t)po;
+            if (o < 0 || (o + 1 >= nb && !P.u_isopt[j])) P.u_oleft[j] = -1; // outside the optical span: no bulge light
         }
     }
 

@@ -89,6 +89,15 @@ struct Prepared {
     std::vector<double> rows_disk_ir;    // IR templates (generic SED / cs17 DUST) on grid_disk (empty if DISK_OPT)
     std::vector<double> rows_disk_pah;   // cs17 PAH on grid_disk
 
+    // bulge evaluated on the disk grid (see phot_core.cuh, "second SED on the same weights"): for every
+    // disk-grid node the optical node at or before it (index into grid_bulge, -1 before the first), its
+    // fractional position inside that optical interval (0 on an optical node) and the disk-grid index of
+    // that optical node
+    std::vector<int32_t> u_oleft;
+    std::vector<double> u_ofrac;
+    std::vector<uint16_t> u_prevopt;
+    std::vector<uint8_t> u_isopt;
+
     std::vector<BandGroup> groups;
     std::vector<RfWeights> rf_bulge, rf_disk;    // [nrf]
 };

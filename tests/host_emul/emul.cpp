@@ -110,39 +110,65 @@ void run(const Prepared &P, const eggphot_galaxies &G, size_t ngal, double *fd, 
                 for (int j = 0; j < nB; ++j) if (SBd[j] != 0) SB[j] += (real)SBd[j];
             }
         }
+        // the bulge SED resampled on the disk grid (kernel phase A4): same piece-wise linear function
+        std::vector<real> SBU(nD, real(0));
+        if (P.has_bulge)
+            for (int j = 0; j < nD; ++j) {
+                const int o = P.u_oleft[j];
+                if (o < 0) continue;
+                SBU[j] = P.u_isopt[j] ? SB[o] : SB[o] + (real)P.u_ofrac[j] * (SB[o + 1] - SB[o]);
+            }
         for (const BandGroup &grp : P.groups) {
             const uint8_t *blob = grp.blob.data();
             const BandHeader *hdr = reinterpret_cast<const BandHeader *>(blob);
             for (size_t bi = 0; bi < grp.cols.size(); ++bi) {
                 const BandHeader &h = hdr[bi];
-                for (int comp = P.has_bulge ? 0 : 1; comp < 2; ++comp) {
-                    const Grid &gr = comp ? P.grid_disk : P.grid_bulge;
-                    const std::vector<real> &S = comp ? SD : SB;
-                    const int n = gr.n();
-                    double f = 0;
-                    const bool covered = n >= 2 && gr.x[0] * opz <= h.full_first && gr.x[n - 1] * opz >= h.full_last;
-                    if (covered && h.n >= 2) {
-                        int jlo = std::max(last_le(gr.x, h.eff_first / opz * (1.0 - 1e-15)), 0);
-                        int jhi = (int)(std::lower_bound(gr.x.begin(), gr.x.end(), h.eff_last / opz * (1.0 + 1e-15)) - gr.x.begin());
-                        jhi = std::min(jhi, n - 1);
-                        BandView<real> bv;
-                        make_band_view(blob, h, bv);
-                        CompSum<real> acc;
-                        acc.clear();
-                        NodeState<real> L, R;
-                        real th, tl;
-                        if (jhi > jlo) { Pos<real>::at(gr, jlo, opz, bv.fc, th, tl); eval_node<real>(bv, th, tl, S[jlo], L); }
-                        for (int j = jlo; j < jhi; ++j) {
-                            Pos<real>::at(gr, j + 1, opz, bv.fc, th, tl);
-                            eval_node<real>(bv, th, tl, S[j + 1], R);
-                            acc.add(eval_interval<real>(bv, L, R));
-                            L = R;
+                const Grid &gr = P.grid_disk;
+                const int n = gr.n();
+                double fdv = 0, fbv = 0;
+                const bool covered = n >= 2 && gr.x[0] * opz <= h.full_first && gr.x[n - 1] * opz >= h.full_last;
+                const bool bulge_on = P.has_bulge && nB >= 2 && P.grid_bulge.x[0] * opz <= h.full_first &&
+                                      P.grid_bulge.x[nB - 1] * opz >= h.full_last;
+                if (covered && h.n >= 2) {
+                    int jlo = std::max(last_le(gr.x, h.eff_first / opz * (1.0 - 1e-15)), 0);
+                    int jhi = (int)(std::lower_bound(gr.x.begin(), gr.x.end(), h.eff_last / opz * (1.0 + 1e-15)) - gr.x.begin());
+                    jhi = std::min(jhi, n - 1);
+                    BandView<real> bv;
+                    make_band_view(blob, h, bv);
+                    CompSum<real> accd, accb;
+                    accd.clear(); accb.clear();
+                    NodeState<real> L, R;
+                    real th, tl;
+                    if (jhi > jlo) { Pos<real>::at(gr, jlo, opz, bv.fc, th, tl); eval_node<real>(bv, th, tl, SD[jlo], L); }
+                    for (int j = jlo; j < jhi; ++j) {
+                        Pos<real>::at(gr, j + 1, opz, bv.fc, th, tl);
+                        eval_node<real>(bv, th, tl, SD[j + 1], R);
+                        IntervalW<real> w;
+                        eval_weights<real>(bv, L, R, w);
+                        real sg;
+                        accd.add(interval_apply(w, L.S, R.S, sg));
+                        if (bulge_on) {
+                            real T = interval_apply(w, SBU[j], SBU[j + 1], sg);
+                            // left node is IR-only and strictly inside the filter span: undo the split it makes
+                            if (!P.u_isopt[j] && L.t > bv.tf0 && L.t < bv.tfl) {
+                                real tph, tpl;
+                                Pos<real>::at(gr, P.u_prevopt[j], opz, bv.fc, tph, tpl);
+                                const real h1 = std::min((L.t - tph) + (L.tl - tpl), L.u);
+                                const real dtr = (R.t - L.t) + (R.tl - L.tl);
+                                const real h2 = std::min(dtr, L.dl - L.u);
+                                T += unsplit_correction<real>(L.s, sg, h1, h2);
+                            }
+                            accb.add(T);
                         }
-                        f = ((double)acc.s + (double)acc.c) * aflux * (comp ? 1.0 : a_b);
+                        L = R;
                     }
-                    if (!std::isfinite(f)) f = 0;
-                    (comp ? fd : fb)[g * nb + h.out_col] = f;
+                    fdv = ((double)accd.s + (double)accd.c) * aflux;
+                    fbv = ((double)accb.s + (double)accb.c) * aflux * a_b;
                 }
+                if (!std::isfinite(fdv)) fdv = 0;
+                if (!std::isfinite(fbv)) fbv = 0;
+                fd[g * nb + h.out_col] = fdv;
+                if (P.has_bulge) fb[g * nb + h.out_col] = fbv;
             }
         }
         const double arf = EGGPHOT_LSUN2UJY / (1e-5 * 1e-5);
