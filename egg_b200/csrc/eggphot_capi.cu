@@ -57,7 +57,7 @@ struct eggphot_ctx {
     cudaStream_t stream = nullptr;
     // prepared tables on the device
     std::vector<DevBuf> blobs;
-    DevBuf xB, xD, xBhl, xDhl, lutB, lutD, rowsB, rowsDopt, rowsDir, rowsDpah, opt_use, rfB, rfD, rfW, errflag, scratch, u_oleft, u_ofrac, u_prevopt, u_isopt;
+    DevBuf xB, xD, xBhl, xDhl, lutB, lutD, rowsB, rowsDopt, rowsDir, rowsDpah, opt_use, rfB, rfD, rfW, errflag, scratch, u_oleft, u_ofrac, u_prevopt, u_isopt, u_dprev;
     int strideB = 0, strideD = 0;
     FluxParams base{};
     int grid_blocks = 0;
@@ -220,10 +220,13 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
         CK(c->u_oleft.upload(P.u_oleft.data(), P.u_oleft.size() * sizeof(int32_t)));
         CK(c->u_prevopt.upload(P.u_prevopt.data(), P.u_prevopt.size() * sizeof(uint16_t)));
         CK(c->u_isopt.upload(P.u_isopt.data(), P.u_isopt.size()));
-        if (P.precision == EGGPHOT_FP64) CK(c->u_ofrac.upload(P.u_ofrac.data(), P.u_ofrac.size() * sizeof(double)));
-        else {
-            std::vector<float> f(P.u_ofrac.begin(), P.u_ofrac.end());
+        if (P.precision == EGGPHOT_FP64) {
+            CK(c->u_ofrac.upload(P.u_ofrac.data(), P.u_ofrac.size() * sizeof(double)));
+            CK(c->u_dprev.upload(P.u_dprev.data(), P.u_dprev.size() * sizeof(double)));
+        } else {
+            std::vector<float> f(P.u_ofrac.begin(), P.u_ofrac.end()), d(P.u_dprev.begin(), P.u_dprev.end());
             CK(c->u_ofrac.upload(f.data(), f.size() * sizeof(float)));
+            CK(c->u_dprev.upload(d.data(), d.size() * sizeof(float)));
         }
     }
     c->blobs.resize(P.groups.size());
@@ -274,7 +277,7 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
     p.rowsB = c->rowsB.p; p.rowsDopt = c->rowsDopt.p; p.rowsDir = c->rowsDir.p; p.rowsDpah = c->rowsDpah.p;
     p.opt_use = (const uint8_t *)c->opt_use.p;
     p.u_oleft = (const int32_t *)c->u_oleft.p; p.u_ofrac = c->u_ofrac.p;
-    p.u_prevopt = (const uint16_t *)c->u_prevopt.p; p.u_isopt = (const uint8_t *)c->u_isopt.p;
+    p.u_prevopt = (const uint16_t *)c->u_prevopt.p; p.u_isopt = (const uint8_t *)c->u_isopt.p; p.u_dprev = c->u_dprev.p;
     p.nopt_sed = P.nopt_sed; p.nir_sed = P.nir_sed;
     p.ir_kind = P.ir_kind; p.disk_mode = (int)P.disk_mode; p.has_bulge = P.has_bulge; p.apply_igm = P.apply_igm;
     p.nline = P.no_nebular ? 0 : (int)P.line_lambda.size();
@@ -296,6 +299,7 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
         p.groups[g].blob = (const uint8_t *)c->blobs[g].p;
         p.groups[g].bytes = (uint32_t)P.groups[g].blob.size();
         p.groups[g].nb = (uint32_t)P.groups[g].cols.size();
+        p.groups[g].base = g ? p.groups[g - 1].base + p.groups[g - 1].nb : 0;
         if (p.groups[g].nb > (uint32_t)kMaxGroupBands) return c->fail(EGGPHOT_ERR_UNSUPPORTED, "more than 64 bands in one group");
         p.max_blob = std::max(p.max_blob, p.groups[g].bytes);
     }

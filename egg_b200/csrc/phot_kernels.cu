@@ -175,6 +175,15 @@ __device__ __forceinline__ void shfl_node(const NodeState<double> &a, NodeState<
     r.q.hru = __shfl_down_sync(kFull, a.q.hru, 1);
 }
 
+// lane sums -> one double: each lane's compensated pair is folded exactly into a double first, then five
+// shuffle-add steps in a fixed order (bit-reproducible)
+template <typename real> __device__ __forceinline__ double warp_total(const CompSum<real> &a) {
+    double v = (double)a.s + (double)a.c;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(kFull, v, o);
+    return v;
+}
+
 template <typename real> __device__ __forceinline__ CompSum<real> warp_reduce(CompSum<real> a) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -203,7 +212,7 @@ template <> struct GridAcc<double> {
 };
 
 struct SmemLayout {
-    uint32_t tab, res, rfres, lb, total;
+    uint32_t tab, res, rfres, lb, win, wflag, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(const FluxParams &p) {
     SmemLayout L;
@@ -213,6 +222,8 @@ __host__ __device__ inline SmemLayout smem_layout(const FluxParams &p) {
     L.res = o; o += up((size_t)kBatch * p.nband_total * 2 * sizeof(double));     // [gal][col][comp] scaled fluxes
     L.rfres = o; o += up((size_t)kBatch * p.nrf * 2 * sizeof(double));           // [gal][rf][comp] rest-frame fluxes
     L.lb = o; o += up((size_t)kBatch * 2 * (p.nline > 0 ? p.nline : 0) * 2 * sizeof(int)); // line windows
+    L.win = o; o += up((size_t)kBatch * p.nband_total * sizeof(uint32_t));                // node windows (jlo | jhi << 16)
+    L.wflag = o; o += up((size_t)kBatch * p.nband_total);                                // bit 0: bulge covered
     L.total = o;
     return L;
 }
@@ -235,6 +246,8 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
     double *res = reinterpret_cast<double *>(smem + L.res);
     double *rfres = reinterpret_cast<double *>(smem + L.rfres);
     int *lb = reinterpret_cast<int *>(smem + L.lb); // [gal][comp][line][2]
+    uint32_t *win = reinterpret_cast<uint32_t *>(smem + L.win); // [band in group order][gal]
+    uint8_t *wflag = smem + L.wflag;
     const BandHeader *hdr = reinterpret_cast<const BandHeader *>(blob);
     const int ncomp = p.has_bulge ? 2 : 1;
     const bool cs17 = p.ir_kind == EGGPHOT_IR_CS17;
@@ -289,6 +302,33 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                     SB[j] = v;
                 }
             }
+        }
+        // node windows of every (band, galaxy): one thread each instead of one warp each later
+        for (int idx = tid; idx < nbt * kBatch; idx += NT) {
+            const int gi = idx & (kBatch - 1), fb = idx / kBatch;
+            uint32_t wv = 0;
+            uint8_t fl = 0;
+            if (gi < ng) {
+                int grp = 0;
+                while (grp + 1 < (int)p.ngroups && fb >= (int)p.groups[grp + 1].base) ++grp;
+                const BandHeader *gh = reinterpret_cast<const BandHeader *>(p.groups[grp].blob) + (fb - (int)p.groups[grp].base);
+                const double full_first = __ldg(&gh->full_first), full_last = __ldg(&gh->full_last);
+                const GalScal &s = sc[gi];
+                const double *x = p.xD;
+                const int n = p.nD;
+                // [vif] sed2flux: NaN (-> flux 0, src/egg-gencat.cpp:2198) unless the SED covers the filter
+                const bool covered = n >= 2 && __ldg(x) * s.opz <= full_first && __ldg(x + n - 1) * s.opz >= full_last;
+                if (covered && __ldg(&gh->n) >= 2) {
+                    // rest-frame ends of the filter span; their lookup buckets come from log2(lambda) - log2(1+z)
+                    const float koff = (float)p.lutD_e0 * (float)kLutPerOctave + s.l2opz;
+                    const int jlo = max(lut_last_le(x, n, p.lutD, p.lutD_n, __ldg(&gh->l2first) - koff, __ldg(&gh->eff_first) * s.iopz * (1.0 - 1e-15)), 0);
+                    const int jhi = min(lut_first_ge(x, n, p.lutD, p.lutD_n, __ldg(&gh->l2last) - koff, __ldg(&gh->eff_last) * s.iopz * (1.0 + 1e-15)), n - 1);
+                    if (jhi > jlo) wv = (uint32_t)jlo | ((uint32_t)jhi << 16);
+                    if (p.has_bulge && p.nB >= 2 && __ldg(p.xB) * s.opz <= full_first && __ldg(p.xB + p.nB - 1) * s.opz >= full_last) fl = 1;
+                }
+            }
+            win[idx] = wv;
+            wflag[idx] = fl;
         }
         for (int idx = tid; idx < ng * 2 * p.nline; idx += NT) {
             const int gi = idx / (2 * p.nline), rem = idx % (2 * p.nline);
@@ -406,17 +446,10 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                     const BandHeader &h = hdr[bi];
                     const GalScal &s = sc[gi];
                     const double *x = p.xD;
-                    const int n = p.nD;
-                    // [vif] sed2flux: NaN (-> flux 0, src/egg-gencat.cpp:2198) unless the SED covers the filter
-                    const bool covered = n >= 2 && __ldg(x) * s.opz <= h.full_first && __ldg(x + n - 1) * s.opz >= h.full_last;
-                    if (!covered || h.n < 2) continue;
-                    const bool bulge_on = p.has_bulge && p.nB >= 2 && __ldg(p.xB) * s.opz <= h.full_first &&
-                                          __ldg(p.xB + p.nB - 1) * s.opz >= h.full_last;
-                    // rest-frame ends of the filter span; their lookup buckets come from log2(lambda) - log2(1+z)
-                    const float koff = (float)p.lutD_e0 * (float)kLutPerOctave + s.l2opz;
-                    const int jlo = max(lut_last_le(x, n, p.lutD, p.lutD_n, h.l2first - koff, h.eff_first * s.iopz * (1.0 - 1e-15)), 0);
-                    const int jhi = min(lut_first_ge(x, n, p.lutD, p.lutD_n, h.l2last - koff, h.eff_last * s.iopz * (1.0 + 1e-15)), n - 1);
-                    if (jhi <= jlo) continue;
+                    const uint32_t wv = win[((int)p.groups[grp].base + bi) * kBatch + gi];
+                    if (wv == 0) continue; // not covered, empty response or empty window: flux stays 0
+                    const int jlo = (int)(wv & 0xffffu), jhi = (int)(wv >> 16);
+                    const bool bulge_on = wflag[((int)p.groups[grp].base + bi) * kBatch + gi] != 0;
                     BandView<real> bv;
                     make_band_view(blob, h, bv);
                     const real *SD = scr + (size_t)gi * sstride;
@@ -433,14 +466,16 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                     accd.clear();
                     accb.clear();
                     int j = min(jlo + lane, jhi);
-                    real tc, tcl, Sc = SD[j], Bc = bulge_on ? SU[j] : real(0);
+                    const real *dprev = reinterpret_cast<const real *>(p.u_dprev);
+                    const real opzr = (real)s.opz;
+                    real tc, tcl, Sc = SD[j], Bc = bulge_on ? SU[j] : real(0), Dc = bulge_on ? __ldg(dprev + j) : real(0);
                     ga.pos(j, bv.fc, tc, tcl);
                     for (int jbase = jlo; jbase < jhi; jbase += 31) {
                         const bool live = lane < 31 && jbase + lane < jhi;
                         // next pass's inputs first: their latency hides behind this pass's arithmetic
                         const int jn = min(jbase + 31 + lane, jhi);
                         real tn, tnl;
-                        const real Sn = SD[jn], Bn = bulge_on ? SU[jn] : real(0);
+                        const real Sn = SD[jn], Bn = bulge_on ? SU[jn] : real(0), Dn = bulge_on ? __ldg(dprev + jn) : real(0);
                         ga.pos(jn, bv.fc, tn, tnl);
                         NodeState<real> nl, nr;
                         eval_node<real>(bv, tc, tcl, Sc, nl);
@@ -454,28 +489,23 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                             const real Br = __shfl_down_sync(kFull, Bc, 1);
                             real TB = interval_apply(w, Bc, Br, sg);
                             // an IR-only left node strictly inside the filter span splits a union cell the optical
-                            // grid does not split: undo it (unsplit_correction)
-                            const int jj = min(jbase + lane, jhi);
-                            const bool fix = live && !__ldg(p.u_isopt + jj) && nl.t > bv.tf0 && nl.t < bv.tfl;
-                            if (__any_sync(kFull, fix)) {
-                                real tp, tpl;
-                                ga.pos(fix ? (int)__ldg(p.u_prevopt + jj) : jj, bv.fc, tp, tpl);
-                                const real h1 = min((nl.t - tp) + (nl.tl - tpl), nl.u);
-                                const real h2 = min((nr.t - nl.t) + (nr.tl - nl.tl), nl.dl - nl.u);
-                                if (fix) TB += unsplit_correction<real>(nl.s, sg, h1, h2);
-                            }
+                            // grid does not split: undo it (unsplit_correction); Dc = rest-frame distance back to
+                            // the previous optical node, 0 on an optical node
+                            const bool fix = Dc > real(0) && nl.t > bv.tf0 && nl.t < bv.tfl;
+                            const real h1 = min(Dc * opzr, nl.u);
+                            const real h2 = min((nr.t - nl.t) + (nr.tl - nl.tl), nl.dl - nl.u);
+                            if (fix) TB += unsplit_correction<real>(nl.s, sg, h1, h2);
                             if (live) accb.add(TB);
                         }
-                        tc = tn; tcl = tnl; Sc = Sn; Bc = Bn;
+                        tc = tn; tcl = tnl; Sc = Sn; Bc = Bn; Dc = Dn;
                     }
-                    accd = warp_reduce(accd);
-                    if (bulge_on) accb = warp_reduce(accb);
+                    const double totd = warp_total(accd), totb = bulge_on ? warp_total(accb) : 0.0;
                     if (lane == 0) {
-                        double f = ((double)accd.s + (double)accd.c) * s.aflux;
+                        double f = totd * s.aflux;
                         if (!isfinite(f)) f = 0.0; // src/egg-gencat.cpp:2198
                         res[(gi * nbt + (int)h.out_col) * 2 + 1] = f;
                         if (bulge_on) {
-                            double fb = ((double)accb.s + (double)accb.c) * s.aflux * s.a_bulge;
+                            double fb = totb * s.aflux * s.a_bulge;
                             if (!isfinite(fb)) fb = 0.0;
                             res[(gi * nbt + (int)h.out_col) * 2] = fb;
                         }

@@ -18,6 +18,7 @@ constexpr int kMaxRf = 16;
 struct GroupDesc {
     const uint8_t *blob;   // device copy of BandGroup::blob (16-byte aligned)
     uint32_t bytes, nb;
+    uint32_t base, pad; // index of the group's first band in group order
 };
 
 // sparse rest-frame weights of one rfband on one component grid
@@ -58,6 +59,7 @@ struct FluxParams {
     // disk grid -> optical grid maps (Prepared::u_*), for the bulge evaluated on the disk grid
     const int32_t *u_oleft;
     const void *u_ofrac;   // real
+    const void *u_dprev;   // real: rest-frame distance back to the previous optical node, 0 on optical nodes
     const uint16_t *u_prevopt;
     const uint8_t *u_isopt;
     const uint8_t *opt_use;

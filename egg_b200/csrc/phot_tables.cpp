@@ -526,6 +526,7 @@ Status prepare(const eggphot_libs &L, const eggphot_filters *bands, const eggpho
     if (P.has_bulge) {
         const int nd = P.grid_disk.n(), nb = P.grid_bulge.n();
         P.u_oleft.assign(nd, -1); P.u_ofrac.assign(nd, 0.0); P.u_prevopt.assign(nd, 0); P.u_isopt.assign(nd, 0);
+        P.u_dprev.assign(nd, 0.0);
         int o = -1, po = 0;
         for (int j = 0; j < nd; ++j) {
             const double xj = P.grid_disk.x[j];
@@ -535,6 +536,7 @@ Status prepare(const eggphot_libs &L, const eggphot_filters *bands, const eggpho
             else if (o >= 0 && o + 1 < nb)
                 P.u_ofrac[j] = (xj - P.grid_bulge.x[o]) / (P.grid_bulge.x[o + 1] - P.grid_bulge.x[o]);
             P.u_prevopt[j] = (uint16_t)po;
+            P.u_dprev[j] = P.u_isopt[j] ? 0.0 : xj - P.grid_disk.x[po];
             if (o < 0 || (o + 1 >= nb && !P.u_isopt[j])) P.u_oleft[j] = -1; // outside the optical span: no bulge light
         }
     }

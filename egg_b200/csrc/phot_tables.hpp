@@ -96,6 +96,7 @@ struct Prepared {
     std::vector<int32_t> u_oleft;
     std::vector<double> u_ofrac;
     std::vector<uint16_t> u_prevopt;
+    std::vector<double> u_dprev;   // rest-frame distance back to that optical node (0 on an optical node)
     std::vector<uint8_t> u_isopt;
 
     std::vector<BandGroup> groups;
