@@ -375,7 +375,10 @@ int eggphot_compute(eggphot_ctx *c, const eggphot_galaxies *gal, size_t ngal, co
     c->launches = 0;
     const Prepared &P = c->P;
     const size_t nb = P.bands.size(), nrf = P.rfbands.size(), nl = P.no_nebular ? 0 : P.line_lambda.size();
-    const size_t chunk = std::min<size_t>(ngal, 1u << 18);
+    // chunks: large enough to fill every SM several times over, small enough that the copies of one
+    // chunk overlap the kernel of the other (two streams): an eighth of the catalog, within [2^15, 2^18]
+    size_t chunk = std::min<size_t>(std::max<size_t>((ngal + 7) / 8, 1u << 15), 1u << 18);
+    chunk = std::min(chunk, ngal);
     if (chunk == 0) return EGGPHOT_OK;
 #define CK(x) do { if ((e = (x)) != cudaSuccess) return c->cuda_fail(e, #x); } while (0)
     struct Col { DevBuf Slot::*buf; const void *src; size_t elem; };

@@ -20,6 +20,7 @@
 
 #include <cooperative_groups.h>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/eggphot.h"
 #include "phot_tables.hpp"
@@ -642,8 +643,18 @@ template <typename real> struct Threads;
 template <> struct Threads<float> { static constexpr int n = 1024; };  // 64 registers per thread
 template <> struct Threads<double> { static constexpr int n = 640; };  // up to 102 registers per thread
 
-template <typename real> static int launch_t(const FluxParams &p, size_t smem, int blocks, cudaStream_t st) {
-    constexpr int NT = Threads<real>::n;
+// The thread count trades registers per thread against warps in flight; both variants of the fp32
+// kernel are built and EGGPHOT_THREADS (768 | 1024) selects one for experiments (default 1024).
+static int fp32_threads() {
+    static int nt = [] {
+        const char *e = getenv("EGGPHOT_THREADS");
+        const int v = e ? atoi(e) : 0;
+        return v == 768 ? 768 : 1024;
+    }();
+    return nt;
+}
+
+template <typename real, int NT> static int launch_nt(const FluxParams &p, size_t smem, int blocks, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(flux_kernel<real, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     flux_kernel<real, NT><<<blocks, NT, smem, st>>>(p);
@@ -652,12 +663,12 @@ template <typename real> static int launch_t(const FluxParams &p, size_t smem, i
 
 int launch_flux_kernel(const FluxParams &p, int precision, int grid_blocks, cudaStream_t stream) {
     const size_t smem = flux_kernel_smem(p, precision);
-    return precision == EGGPHOT_FP64 ? launch_t<double>(p, smem, grid_blocks, stream)
-                                     : launch_t<float>(p, smem, grid_blocks, stream);
+    if (precision == EGGPHOT_FP64) return launch_nt<double, Threads<double>::n>(p, smem, grid_blocks, stream);
+    return fp32_threads() == 768 ? launch_nt<float, 768>(p, smem, grid_blocks, stream)
+                                 : launch_nt<float, 1024>(p, smem, grid_blocks, stream);
 }
 
-template <typename real> static int occupancy_t(size_t smem) {
-    constexpr int NT = Threads<real>::n;
+template <typename real, int NT> static int occupancy_nt(size_t smem) {
     int nb = 0;
     cudaError_t e = cudaFuncSetAttribute(flux_kernel<real, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, flux_kernel<real, NT>, NT, smem);
@@ -666,7 +677,8 @@ template <typename real> static int occupancy_t(size_t smem) {
 
 int flux_kernel_max_blocks_per_sm(const FluxParams &p, int precision) {
     const size_t smem = flux_kernel_smem(p, precision);
-    return precision == EGGPHOT_FP64 ? occupancy_t<double>(smem) : occupancy_t<float>(smem);
+    if (precision == EGGPHOT_FP64) return occupancy_nt<double, Threads<double>::n>(smem);
+    return fp32_threads() == 768 ? occupancy_nt<float, 768>(smem) : occupancy_nt<float, 1024>(smem);
 }
 
 int launch_sed_kernel(const SedParams &q, int precision, cudaStream_t stream) {
