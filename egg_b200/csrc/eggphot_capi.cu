@@ -57,7 +57,7 @@ struct eggphot_ctx {
     cudaStream_t stream = nullptr;
     // prepared tables on the device
     std::vector<DevBuf> blobs;
-    DevBuf xB, xD, xBhl, xDhl, lutB, lutD, rowsB, rowsDopt, rowsDir, rowsDpah, opt_use, rfB, rfD, rfW, errflag, scratch, u_oleft, u_ofrac, u_prevopt, u_isopt, u_dprev;
+    DevBuf xB, xD, gridD, dxo, lutB, lutD, rowsB, rowsDopt, rowsDir, rowsDpah, opt_use, rfB, rfD, rfW, errflag, scratch, u_oleft, u_ofrac, u_isopt;
     int strideB = 0, strideD = 0;
     FluxParams base{};
     int grid_blocks = 0;
@@ -98,17 +98,11 @@ cudaError_t upload_rows(DevBuf &b, const std::vector<double> &rows, size_t nrow,
     return e;
 }
 
-cudaError_t upload_grid(const Grid &g, DevBuf &x, DevBuf &hl, DevBuf &lut, uint64_t &bytes) {
+cudaError_t upload_grid(const Grid &g, DevBuf &x, DevBuf &lut, uint64_t &bytes) {
     if (g.n() == 0) return cudaSuccess;
-    std::vector<float> h(2 * (size_t)g.n());
-    for (int j = 0; j < g.n(); ++j) {
-        h[2 * j] = (float)g.x[j];
-        h[2 * j + 1] = (float)(g.x[j] - (double)h[2 * j]);
-    }
     cudaError_t e = x.upload(g.x.data(), g.n() * sizeof(double));
-    if (e == cudaSuccess) e = hl.upload(h.data(), h.size() * sizeof(float));
     if (e == cudaSuccess) e = lut.upload(g.lut.data(), g.lut.size() * sizeof(uint16_t));
-    bytes += x.bytes + hl.bytes + lut.bytes;
+    bytes += x.bytes + lut.bytes;
     return e;
 }
 
@@ -209,8 +203,14 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
     c->strideB = (P.grid_bulge.n() + per16 - 1) / per16 * per16;
     c->strideD = (P.grid_disk.n() + per16 - 1) / per16 * per16;
 #define CK(x) do { if ((e = (x)) != cudaSuccess) return c->cuda_fail(e, #x); } while (0)
-    CK(upload_grid(P.grid_bulge, c->xB, c->xBhl, c->lutB, tb));
-    CK(upload_grid(P.grid_disk, c->xD, c->xDhl, c->lutD, tb));
+    CK(upload_grid(P.grid_bulge, c->xB, c->lutB, tb));
+    CK(upload_grid(P.grid_disk, c->xD, c->lutD, tb));
+    {   // disk grid as {x, 1/dx} pairs (+ one padding record: phase B reads x of node j + 1)
+        std::vector<double> g2(2 * ((size_t)P.grid_disk.n() + 1), 0.0);
+        for (int j = 0; j < P.grid_disk.n(); ++j) { g2[2 * j] = P.grid_disk.x[j]; g2[2 * j + 1] = P.grid_disk.idx[j]; }
+        CK(c->gridD.upload(g2.data(), g2.size() * sizeof(double)));
+        tb += c->gridD.bytes;
+    }
     CK(upload_rows(c->rowsB, P.rows_bulge_opt, P.nopt_sed, P.grid_bulge.n(), c->strideB, P.precision, tb));
     CK(upload_rows(c->rowsDopt, P.rows_disk_opt, P.nopt_sed, P.grid_disk.n(), c->strideD, P.precision, tb));
     CK(upload_rows(c->rowsDir, P.rows_disk_ir, P.nir_sed, P.grid_disk.n(), c->strideD, P.precision, tb));
@@ -218,15 +218,14 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
     if (!P.opt_use.empty()) CK(c->opt_use.upload(P.opt_use.data(), P.opt_use.size()));
     if (!P.u_oleft.empty()) {
         CK(c->u_oleft.upload(P.u_oleft.data(), P.u_oleft.size() * sizeof(int32_t)));
-        CK(c->u_prevopt.upload(P.u_prevopt.data(), P.u_prevopt.size() * sizeof(uint16_t)));
         CK(c->u_isopt.upload(P.u_isopt.data(), P.u_isopt.size()));
         if (P.precision == EGGPHOT_FP64) {
             CK(c->u_ofrac.upload(P.u_ofrac.data(), P.u_ofrac.size() * sizeof(double)));
-            CK(c->u_dprev.upload(P.u_dprev.data(), P.u_dprev.size() * sizeof(double)));
+            CK(c->dxo.upload(P.u_dxo.data(), P.u_dxo.size() * sizeof(double)));
         } else {
-            std::vector<float> f(P.u_ofrac.begin(), P.u_ofrac.end()), d(P.u_dprev.begin(), P.u_dprev.end());
+            std::vector<float> f(P.u_ofrac.begin(), P.u_ofrac.end()), d(P.u_dxo.begin(), P.u_dxo.end());
             CK(c->u_ofrac.upload(f.data(), f.size() * sizeof(float)));
-            CK(c->u_dprev.upload(d.data(), d.size() * sizeof(float)));
+            CK(c->dxo.upload(d.data(), d.size() * sizeof(float)));
         }
     }
     c->blobs.resize(P.groups.size());
@@ -267,7 +266,7 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
     p.nB = P.grid_bulge.n(); p.nD = P.grid_disk.n();
     p.strideB = c->strideB; p.strideD = c->strideD;
     p.xB = (const double *)c->xB.p; p.xD = (const double *)c->xD.p;
-    p.xBhl = (const float2 *)c->xBhl.p; p.xDhl = (const float2 *)c->xDhl.p;
+    p.gridD = (const double2 *)c->gridD.p; p.dxo = c->dxo.p;
     p.lutB = (const uint16_t *)c->lutB.p; p.lutD = (const uint16_t *)c->lutD.p;
     p.lutB_n = (int)P.grid_bulge.lut.size(); p.lutD_n = (int)P.grid_disk.lut.size();
     p.lutB_e0 = P.grid_bulge.lut_e0; p.lutD_e0 = P.grid_disk.lut_e0;
@@ -277,7 +276,7 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
     p.rowsB = c->rowsB.p; p.rowsDopt = c->rowsDopt.p; p.rowsDir = c->rowsDir.p; p.rowsDpah = c->rowsDpah.p;
     p.opt_use = (const uint8_t *)c->opt_use.p;
     p.u_oleft = (const int32_t *)c->u_oleft.p; p.u_ofrac = c->u_ofrac.p;
-    p.u_prevopt = (const uint16_t *)c->u_prevopt.p; p.u_isopt = (const uint8_t *)c->u_isopt.p; p.u_dprev = c->u_dprev.p;
+    p.u_isopt = (const uint8_t *)c->u_isopt.p;
     p.nopt_sed = P.nopt_sed; p.nir_sed = P.nir_sed;
     p.ir_kind = P.ir_kind; p.disk_mode = (int)P.disk_mode; p.has_bulge = P.has_bulge; p.apply_igm = P.apply_igm;
     p.nline = P.no_nebular ? 0 : (int)P.line_lambda.size();

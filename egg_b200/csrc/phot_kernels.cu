@@ -7,12 +7,13 @@
 //      (get_opt_sed / get_ir_sed / merge_add / IGM block, src/egg-gencat.cpp:708-712, 2039-2057,
 //      2118-2140) into a per-CTA scratch that stays in L2, and deposits the emission lines
 //      (add_emission_line, :2078-2095) with a deterministic owner rule;
-//   B. for each band group: stages the group's filter tables (nodes with two-sided prefix sums,
-//      bucket index) into shared memory with TMA bulk copies (cp.async.bulk, SASS UBLKCP); warps pull
-//      (band, component, galaxy) items off a shared counter; an item = 32 lanes on 32 consecutive SED
-//      nodes, each lane finds its node's filter cell, forms the cumulative quantities K0/K1
-//      (phot_core.cuh), gets its right neighbour's by warp shuffle and adds the interval's
-//      contribution to a compensated per-lane sum, reduced by shuffle; rest-frame magnitudes are dot
+//   B. for each band group: stages the group's filter tables (per filter cell: node position, Lambda,
+//      K0, R/2, slope, width; bucket index) into shared memory with TMA bulk copies (cp.async.bulk, SASS
+//      UBLKCP); warps pull (band, galaxy) items off a shared counter; an item = 32 lanes on 32 consecutive
+//      SED nodes: each lane finds its node's filter cell, evaluates the band's piece-wise quadratic
+//      Lambda there and multiplies it by the curvature of each component's SED at that node, formed from
+//      the node's own three SED values (phot_core.cuh, "curvature form": no data is exchanged between
+//      lanes); per-lane double sums, one shuffle reduction per item; rest-frame magnitudes are dot
 //      products with precomputed z = 0 weights (:2150-2158);
 //   C. applies the reference's data conditions (uncovered band -> 0, non-finite mag -> 99), forms
 //      the totals (:2238-2239) and writes the f32 catalog columns with coalesced stores.
@@ -153,33 +154,8 @@ __device__ __forceinline__ int first_ge(const double *__restrict__ x, int n, dou
     return hi;
 }
 
-__device__ __forceinline__ void shfl_node(const NodeState<float> &a, NodeState<float> &r) {
-    r.t = __shfl_down_sync(kFull, a.t, 1);
-    r.tl = __shfl_down_sync(kFull, a.tl, 1);
-    r.S = __shfl_down_sync(kFull, a.S, 1);
-    r.cell = __shfl_down_sync(kFull, a.cell, 1);
-    r.q.i0h = __shfl_down_sync(kFull, a.q.i0h, 1);
-    r.q.i0l = __shfl_down_sync(kFull, a.q.i0l, 1);
-    r.q.c1h = __shfl_down_sync(kFull, a.q.c1h, 1);
-    r.q.c1l = __shfl_down_sync(kFull, a.q.c1l, 1);
-    r.q.p0 = __shfl_down_sync(kFull, a.q.p0, 1);
-    r.q.hru = __shfl_down_sync(kFull, a.q.hru, 1);
-}
-__device__ __forceinline__ void shfl_node(const NodeState<double> &a, NodeState<double> &r) {
-    r.t = __shfl_down_sync(kFull, a.t, 1);
-    r.tl = 0.0;
-    r.S = __shfl_down_sync(kFull, a.S, 1);
-    r.cell = __shfl_down_sync(kFull, a.cell, 1);
-    r.q.i0 = __shfl_down_sync(kFull, a.q.i0, 1);
-    r.q.c1 = __shfl_down_sync(kFull, a.q.c1, 1);
-    r.q.p0 = __shfl_down_sync(kFull, a.q.p0, 1);
-    r.q.hru = __shfl_down_sync(kFull, a.q.hru, 1);
-}
-
-// lane sums -> one double: each lane's compensated pair is folded exactly into a double first, then five
-// shuffle-add steps in a fixed order (bit-reproducible)
-template <typename real> __device__ __forceinline__ double warp_total(const CompSum<real> &a) {
-    double v = (double)a.s + (double)a.c;
+// lane sums -> one double: five shuffle-add steps in a fixed order (bit-reproducible)
+__device__ __forceinline__ double warp_total(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(kFull, v, o);
     return v;
@@ -196,24 +172,30 @@ template <typename real> __device__ __forceinline__ CompSum<real> warp_reduce(Co
     return a;
 }
 
-// rest grid access in the kernel's precision
-template <typename real> struct GridAcc;
-template <> struct GridAcc<float> {
-    const float2 *hl;
-    float opz_hi, opz_lo;
-    __device__ __forceinline__ void pos(int j, float fc, float &th, float &tl) const {
-        const float2 v = __ldg(hl + j);
-        node_pos(v.x, v.y, opz_hi, opz_lo, fc, th, tl);
+// find_cell (phot_core.cuh) for a full warp: the forward scan runs as a warp-uniform loop on a vote instead of
+// a per-lane data-dependent loop.  The warp executes the longest lane's scan either way, and the lanes provably
+// stay converged for the shuffle reduction that follows the node loop (with the per-lane loop nvcc 12.9 emitted
+// neither a reconvergence barrier after it nor a WARPSYNC before the shuffles, and lanes read stale registers).
+template <typename Cell>
+__device__ __forceinline__ int find_cell_warp(const Cell *cells, const uint16_t *bkt, int nbkt, double f_first, float inv_w, double t) {
+    int k = (int)((float)(t - f_first) * inv_w);
+    k = max(0, min(k, nbkt - 1));
+    int c = bkt[k];
+    bool up = t >= cells[c + 1].f;
+    while (__any_sync(kFull, up)) {
+        c += up ? 1 : 0;
+        up = t >= cells[c + 1].f;
     }
-};
-template <> struct GridAcc<double> {
-    const double *x;
-    double opz;
-    __device__ __forceinline__ void pos(int j, double fc, double &th, double &tl) const { node_pos(__ldg(x + j), opz, fc, th, tl); }
-};
+    return c;
+}
+
+// observed width of the rest-frame interval that starts at node j: (x_{j+1} - x_j)(1+z).  fp32: from the
+// stored inverse width (it only enters the trapezoid-error term); fp64: from the node positions.
+__device__ __forceinline__ float node_dt(const double2 *g, int j, double2 gn, float opz) { (void)g; (void)j; return __fdividef(opz, (float)gn.y); }
+__device__ __forceinline__ double node_dt(const double2 *g, int j, double2 gn, double opz) { return (__ldg(&g[j + 1].x) - gn.x) * opz; }
 
 struct SmemLayout {
-    uint32_t tab, res, rfres, lb, win, wflag, total;
+    uint32_t tab, res, rfres, lb, win, wmid, wflag, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(const FluxParams &p) {
     SmemLayout L;
@@ -224,6 +206,7 @@ __host__ __device__ inline SmemLayout smem_layout(const FluxParams &p) {
     L.rfres = o; o += up((size_t)kBatch * p.nrf * 2 * sizeof(double));           // [gal][rf][comp] rest-frame fluxes
     L.lb = o; o += up((size_t)kBatch * 2 * (p.nline > 0 ? p.nline : 0) * 2 * sizeof(int)); // line windows
     L.win = o; o += up((size_t)kBatch * p.nband_total * sizeof(uint32_t));                // node windows (jlo | jhi << 16)
+    L.wmid = o; o += up((size_t)kBatch * p.nband_total * sizeof(uint16_t));               // node left of the band's split
     L.wflag = o; o += up((size_t)kBatch * p.nband_total);                                // bit 0: bulge covered
     L.total = o;
     return L;
@@ -248,6 +231,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
     double *rfres = reinterpret_cast<double *>(smem + L.rfres);
     int *lb = reinterpret_cast<int *>(smem + L.lb); // [gal][comp][line][2]
     uint32_t *win = reinterpret_cast<uint32_t *>(smem + L.win); // [band in group order][gal]
+    uint16_t *wmid = reinterpret_cast<uint16_t *>(smem + L.wmid);
     uint8_t *wflag = smem + L.wflag;
     const BandHeader *hdr = reinterpret_cast<const BandHeader *>(blob);
     const int ncomp = p.has_bulge ? 2 : 1;
@@ -308,6 +292,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
         for (int idx = tid; idx < nbt * kBatch; idx += NT) {
             const int gi = idx & (kBatch - 1), fb = idx / kBatch;
             uint32_t wv = 0;
+            uint16_t wm = 0;
             uint8_t fl = 0;
             if (gi < ng) {
                 int grp = 0;
@@ -324,11 +309,23 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                     const float koff = (float)p.lutD_e0 * (float)kLutPerOctave + s.l2opz;
                     const int jlo = max(lut_last_le(x, n, p.lutD, p.lutD_n, __ldg(&gh->l2first) - koff, __ldg(&gh->eff_first) * s.iopz * (1.0 - 1e-15)), 0);
                     const int jhi = min(lut_first_ge(x, n, p.lutD, p.lutD_n, __ldg(&gh->l2last) - koff, __ldg(&gh->eff_last) * s.iopz * (1.0 + 1e-15)), n - 1);
-                    if (jhi > jlo) wv = (uint32_t)jlo | ((uint32_t)jhi << 16);
+                    if (jhi > jlo) {
+                        wv = (uint32_t)jlo | ((uint32_t)jhi << 16);
+                        // b = last node of [jlo, jhi) left of the band's split node, by the same expression phase B
+                        // uses to place a node in a filter cell (the two must agree on which gauge a node is in)
+                        const double fc = __ldg(&gh->fc), fs = __ldg(&gh->f_split);
+                        int lo = jlo, hi = jhi; // t(lo) < fs (or lo = jlo), t(hi) >= fs (or hi = jhi)
+                        while (hi - lo > 1) {
+                            const int mid = (lo + hi) >> 1;
+                            if (fma(s.opz, __ldg(x + mid), -fc) < fs) lo = mid; else hi = mid;
+                        }
+                        wm = (uint16_t)lo;
+                    }
                     if (p.has_bulge && p.nB >= 2 && __ldg(p.xB) * s.opz <= full_first && __ldg(p.xB + p.nB - 1) * s.opz >= full_last) fl = 1;
                 }
             }
             win[idx] = wv;
+            wmid[idx] = wm;
             wflag[idx] = fl;
         }
         for (int idx = tid; idx < ng * 2 * p.nline; idx += NT) {
@@ -446,67 +443,55 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                     if (gi >= ng) continue;
                     const BandHeader &h = hdr[bi];
                     const GalScal &s = sc[gi];
-                    const double *x = p.xD;
                     const uint32_t wv = win[((int)p.groups[grp].base + bi) * kBatch + gi];
                     if (wv == 0) continue; // not covered, empty response or empty window: flux stays 0
                     const int jlo = (int)(wv & 0xffffu), jhi = (int)(wv >> 16);
-                    const bool bulge_on = wflag[((int)p.groups[grp].base + bi) * kBatch + gi] != 0;
+                    const int widx = ((int)p.groups[grp].base + bi) * kBatch + gi;
+                    const bool bulge_on = wflag[widx] != 0;
                     BandView<real> bv;
-                    make_band_view(blob, h, bv);
+                    make_band_view<real>(blob, h, bv);
                     const real *SD = scr + (size_t)gi * sstride;
                     const real *SU = SD + p.strideD + p.strideB;
-                    GridAcc<real> ga;
-                    if constexpr (sizeof(real) == 4) {
-                        const float oh = (float)s.opz;
-                        ga.hl = p.xDhl;
-                        ga.opz_hi = oh; ga.opz_lo = (float)(s.opz - (double)oh);
-                    } else {
-                        ga.x = x; ga.opz = s.opz;
-                    }
-                    CompSum<real> accd, accb;
-                    accd.clear();
-                    accb.clear();
-                    int j = min(jlo + lane, jhi);
-                    const real *dprev = reinterpret_cast<const real *>(p.u_dprev);
-                    const real opzr = (real)s.opz;
-                    real tc, tcl, Sc = SD[j], Bc = bulge_on ? SU[j] : real(0), Dc = bulge_on ? __ldg(dprev + j) : real(0);
-                    ga.pos(j, bv.fc, tc, tcl);
-                    for (int jbase = jlo; jbase < jhi; jbase += 31) {
-                        const bool live = lane < 31 && jbase + lane < jhi;
-                        // next pass's inputs first: their latency hides behind this pass's arithmetic
-                        const int jn = min(jbase + 31 + lane, jhi);
-                        real tn, tnl;
-                        const real Sn = SD[jn], Bn = bulge_on ? SU[jn] : real(0), Dn = bulge_on ? __ldg(dprev + jn) : real(0);
-                        ga.pos(jn, bv.fc, tn, tnl);
-                        NodeState<real> nl, nr;
-                        eval_node<real>(bv, tc, tcl, Sc, nl);
-                        shfl_node(nl, nr);
-                        IntervalW<real> w;
-                        eval_weights<real>(bv, nl, nr, w);
-                        real sg;
-                        const real T = interval_apply(w, nl.S, nr.S, sg);
-                        if (live) accd.add(T);
+                    const double2 *gx = p.gridD;
+                    const real *dxo = reinterpret_cast<const real *>(p.dxo);
+                    const double opz = s.opz;
+                    const real opzr = (real)opz;
+                    double accd = 0.0, accb = 0.0; // sum Lambda_j k_j
+                    real cd = real(0), cb = real(0); // sum rho_j gamma_j
+                    for (int j0 = jlo + 1; j0 < jhi; j0 += 32) {
+                        const bool live = j0 + lane < jhi;
+                        const int j = live ? j0 + lane : jhi - 1;
+                        const double2 gn = __ldg(gx + j);
+                        const double idxm = __ldg(&gx[j - 1].y);
+                        const real Sm = SD[j - 1], S0 = SD[j], Sp = SD[j + 1];
+                        const double t = fma(opz, gn.x, -bv.fc);
+                        const int c = find_cell_warp(bv.cells, bv.bkt, bv.nbkt, bv.f_first, bv.bkt_inv_w, t);
+                        const typename CellOf<real>::type e = bv.cells[c];
+                        double u;
+                        const double lam = live ? lambda_in_cell(e, t, u) : (u = 0.0, 0.0);
+                        const double r0 = slope(S0, Sp, gn.y), rm = slope(Sm, S0, idxm);
+                        accd = fma(lam, r0 - rm, accd);
+                        const real ur = (real)u, sr = (real)e.s, dlr = (real)e.dl;
+                        cd = fma((real)r0, gamma_term<real>(sr, dlr, ur, node_dt(gx, j, gn, opzr)), cd);
                         if (bulge_on) {
-                            const real Br = __shfl_down_sync(kFull, Bc, 1);
-                            real TB = interval_apply(w, Bc, Br, sg);
-                            // an IR-only left node strictly inside the filter span splits a union cell the optical
-                            // grid does not split: undo it (unsplit_correction); Dc = rest-frame distance back to
-                            // the previous optical node, 0 on an optical node
-                            const bool fix = Dc > real(0) && nl.t > bv.tf0 && nl.t < bv.tfl;
-                            const real h1 = min(Dc * opzr, nl.u);
-                            const real h2 = min((nr.t - nl.t) + (nr.tl - nl.tl), nl.dl - nl.u);
-                            if (fix) TB += unsplit_correction<real>(nl.s, sg, h1, h2);
-                            if (live) accb.add(TB);
+                            const real Bm = SU[j - 1], B0 = SU[j], Bp = SU[j + 1];
+                            const double b0 = slope(B0, Bp, gn.y), bm = slope(Bm, B0, idxm);
+                            accb = fma(lam, b0 - bm, accb);
+                            cb = fma((real)b0, gamma_term<real>(sr, dlr, ur, __ldg(dxo + j) * opzr), cb);
                         }
-                        tc = tn; tcl = tnl; Sc = Sn; Bc = Bn; Dc = Dn;
                     }
-                    const double totd = warp_total(accd), totb = bulge_on ? warp_total(accb) : 0.0;
+                    const double totd = warp_total(fma(-0.5, (double)cd, accd));
+                    const double totb = bulge_on ? warp_total(fma(-0.5, (double)cb, accb)) : 0.0;
                     if (lane == 0) {
-                        double f = totd * s.aflux;
+                        // end terms at the SED interval [b, b+1] that holds the band's split node
+                        const int b = (int)wmid[widx];
+                        const double2 gb = __ldg(gx + b);
+                        const double tb1 = fma(opz, __ldg(&gx[b + 1].x), -bv.fc);
+                        double f = band_total(bv, s.iopz, totd, 0.0, (double)SD[b + 1], slope(SD[b], SD[b + 1], gb.y), tb1) * s.aflux;
                         if (!isfinite(f)) f = 0.0; // src/egg-gencat.cpp:2198
                         res[(gi * nbt + (int)h.out_col) * 2 + 1] = f;
                         if (bulge_on) {
-                            double fb = totb * s.aflux * s.a_bulge;
+                            double fb = band_total(bv, s.iopz, totb, 0.0, (double)SU[b + 1], slope(SU[b], SU[b + 1], gb.y), tb1) * s.aflux * s.a_bulge;
                             if (!isfinite(fb)) fb = 0.0;
                             res[(gi * nbt + (int)h.out_col) * 2] = fb;
                         }

@@ -50,7 +50,8 @@ struct FluxParams {
     int32_t nB, nD;        // nodes (0 if the component is absent)
     int32_t strideB, strideD; // row strides in elements (16-byte multiples)
     const double *xB, *xD; // rest wavelengths, double
-    const float2 *xBhl, *xDhl; // the same as (hi, lo) float pairs (fp32 mode)
+    const double2 *gridD;  // disk grid as {x_j, 1/(x_{j+1} - x_j)} (Grid::idx)
+    const void *dxo;       // real: rest-frame distance from an optical node to the next one, 0 elsewhere (Prepared::u_dxo)
     const uint16_t *lutB, *lutD; // log2-spaced "last node <= v" lookups (Grid::lut)
     int32_t lutB_n, lutD_n, lutB_e0, lutD_e0;
     int32_t igmB[4], igmD[4]; // lz, l0, l1, l2
@@ -59,8 +60,6 @@ struct FluxParams {
     // disk grid -> optical grid maps (Prepared::u_*), for the bulge evaluated on the disk grid
     const int32_t *u_oleft;
     const void *u_ofrac;   // real
-    const void *u_dprev;   // real: rest-frame distance back to the previous optical node, 0 on optical nodes
-    const uint16_t *u_prevopt;
     const uint8_t *u_isopt;
     const uint8_t *opt_use;
     uint32_t nopt_sed, nir_sed;

@@ -52,17 +52,12 @@ double box_integral(const std::vector<double> &x, const std::vector<double> &y, 
     return s;
 }
 
-double pow2ceil(double v) {
-    if (!(v > 0)) return 1.0;
-    return std::exp2(std::ceil(std::log2(v)));
-}
-
 void align16(std::vector<uint8_t> &b) { b.resize((b.size() + 15) & ~size_t(15), 0); }
 
-// Double-precision band table, the source of both device layouts and of the rfband weights.
+// Double-precision band table, the source of both device layouts.
 struct BandTableD {
     BandHeader h{};
-    std::vector<FilterNodeD> nodes;
+    std::vector<FilterCellD> cells; // n + 1 records: cells 0..n-2, the open cell n-1, the sentinel n
     std::vector<uint16_t> bkt;
 };
 
@@ -80,12 +75,9 @@ Status build_band_table(const Filter &f, uint32_t out_col, int bucket_factor, Ba
     if (a < 0) { // identically zero response
         t.h.n = 0;
         t.h.eff_first = t.h.eff_last = t.h.full_first;
-        t.h.fc = (double)(float)t.h.full_first;
-        t.h.ni = t.h.nc = 1.0;
-        t.h.fcf = (float)t.h.fc; t.h.nif = t.h.ncf = 1.0f;
-        t.h.inv_nif = t.h.inv_ncf = t.h.ni_ncf = 1.0f;
-        t.nodes.clear();
-        t.bkt.assign(2, 0);
+        t.h.fc = t.h.full_first;
+        t.cells.clear();
+        t.bkt.assign(1, 0);
         t.h.nbkt = 1;
         return Status();
     }
@@ -97,86 +89,81 @@ Status build_band_table(const Filter &f, uint32_t out_col, int bucket_factor, Ba
     t.h.n = (uint32_t)n;
     t.h.eff_first = f.lam[a];
     t.h.eff_last = f.lam[b];
-    t.h.fc = (double)(float)(0.5 * (f.lam[a] + f.lam[b]));
-    t.nodes.assign(n, FilterNodeD{});
-    double i0 = 0, c1 = 0, a0 = 0, a1 = 0;
+    t.h.fc = 0.5 * (f.lam[a] + f.lam[b]);
+    t.cells.assign(n + 1, FilterCellD{});
+    // K0 = cumulative trapezoid of R; Lambda = L - G/6 advances by dl (K0 + R dl/2) per cell (phot_core.cuh)
+    long double k0 = 0, lam = 0;
     for (int i = 0; i < n; ++i) {
-        FilterNodeD &e = t.nodes[i];
-        e.tf = f.lam[a + i] - t.h.fc;
-        e.R = f.res[a + i];
-        e.I0 = i0;
-        e.C1 = c1;
+        FilterCellD &e = t.cells[i];
+        e.f = f.lam[a + i] - t.h.fc;
+        e.k0 = (double)k0;
+        e.lam = (double)lam;
         if (i + 1 < n) {
-            const double tn = f.lam[a + i + 1] - t.h.fc, rn = f.res[a + i + 1];
+            const double R = f.res[a + i], rn = f.res[a + i + 1];
             e.dl = f.lam[a + i + 1] - f.lam[a + i];
-            e.s = e.dl > 0 ? (rn - e.R) / e.dl : 0.0;
-            i0 += 0.5 * (e.R + rn) * e.dl;
-            c1 += 0.5 * (e.R * e.tf + rn * tn) * e.dl;
-            a0 += 0.5 * (std::fabs(e.R) + std::fabs(rn)) * e.dl;
-            a1 += 0.5 * (std::fabs(e.R * e.tf) + std::fabs(rn * tn)) * e.dl;
+            e.s = e.dl > 0 ? (rn - R) / e.dl : 0.0;
+            e.hr = 0.5 * R;
+            lam += (long double)e.dl * (k0 + 0.5L * (long double)R * e.dl);
+            k0 += 0.5L * ((long double)R + rn) * e.dl;
+        } else { // open cell right of the last node
+            e.hr = 0.0;
+            e.s = 0.0;
+            e.dl = 1e30;
         }
     }
-    // two-sided prefix values: cells up to `split` keep the running sums from the left end, the
-    // others are re-expressed as (minus) the sums from the right end, so that a value deep in a
-    // wing is small and differences inside the wing keep their relative accuracy
-    const double tot0 = i0, tot1 = c1;
-    int split = n - 2;
+    t.cells[n] = FilterCellD{1e300, 0, 0, 0, 0, 1e30};
+    t.h.f_first = t.cells[0].f;
+    t.h.f_last = t.cells[n - 1].f;
+    t.h.tot0 = t.cells[n - 1].k0;
+    t.h.asym0 = t.cells[n - 1].lam - t.h.tot0 * t.h.f_last;
+    // two-sided gauge (phot_core.cuh): cells from the half-mass node on are re-expressed relative to the
+    // right end, accumulated from that end itself (subtracting the asymptote would cancel in the far wing)
+    int split = n - 1;
     {
-        double run = 0;
+        double a0 = 0, run = 0;
+        for (int i = 0; i + 1 < n; ++i) a0 += 0.5 * (std::fabs(f.res[a + i]) + std::fabs(f.res[a + i + 1])) * t.cells[i].dl;
         for (int i = 0; i + 1 < n; ++i) {
-            run += 0.5 * (std::fabs(t.nodes[i].R) + std::fabs(t.nodes[i + 1].R)) * t.nodes[i].dl;
-            if (run >= 0.5 * a0) { split = i; break; }
+            run += 0.5 * (std::fabs(f.res[a + i]) + std::fabs(f.res[a + i + 1])) * t.cells[i].dl;
+            if (run >= 0.5 * a0) { split = i + 1; break; }
         }
     }
-    {   // accumulate from the right end itself (subtracting the total would re-introduce the cancellation)
-        double r0 = 0, r1 = 0;
-        t.nodes[n - 1].I0 = 0;
-        t.nodes[n - 1].C1 = 0;
-        for (int i = n - 2; i > split; --i) {
-            const FilterNodeD &e = t.nodes[i], &f2 = t.nodes[i + 1];
-            r0 -= 0.5 * (e.R + f2.R) * e.dl;
-            r1 -= 0.5 * (e.R * e.tf + f2.R * f2.tf) * e.dl;
-            t.nodes[i].I0 = r0;
-            t.nodes[i].C1 = r1;
+    {
+        long double k0r = 0, lamr = 0;
+        t.cells[n - 1].k0 = 0;
+        t.cells[n - 1].lam = 0;
+        for (int i = n - 2; i >= split; --i) {
+            const double R = f.res[a + i], rn = f.res[a + i + 1], dl = t.cells[i].dl;
+            k0r -= 0.5L * ((long double)R + rn) * dl;
+            lamr -= (long double)dl * (k0r + 0.5L * (long double)R * dl);
+            t.cells[i].k0 = (double)k0r;
+            t.cells[i].lam = (double)lamr;
         }
     }
     t.h.split = (uint32_t)split;
-    t.h.tot0 = tot0;
-    t.h.tot1 = tot1;
-    t.h.ni = pow2ceil(4.0 * a0);
-    t.h.nc = pow2ceil(4.0 * a1);
-    {
-        const double q = 8388608.0; // 2^23: high parts of the totals on the grid of the [1,2) table values
-        const double s0 = tot0 / t.h.ni, s1 = tot1 / t.h.nc;
-        t.h.tot0h = (float)(std::nearbyint(s0 * q) / q); t.h.tot0l = (float)(s0 - (double)t.h.tot0h);
-        t.h.tot1h = (float)(std::nearbyint(s1 * q) / q); t.h.tot1l = (float)(s1 - (double)t.h.tot1h);
-    }
-    // bucket table: bkt[k] = last node with tf <= tf0 + k*w
-    int nbkt = std::min(std::max(bucket_factor * n, 1), 65000);
-    const double span = t.nodes[n - 1].tf - t.nodes[0].tf;
+    t.h.f_split = t.cells[split].f;
+    // bucket table: bkt[k] = last node with f <= f_first + k*w
+    const int nbkt = std::min(std::max(bucket_factor * n, 1), 65000);
+    const double span = t.h.f_last - t.h.f_first;
     t.h.nbkt = (uint32_t)nbkt;
-    t.h.tf0 = t.nodes[0].tf;
-    t.h.tfl = t.nodes[n - 1].tf;
-    t.h.bkt_inv_w = span > 0 ? nbkt / span : 0.0;
-    t.h.fcf = (float)t.h.fc; t.h.nif = (float)t.h.ni; t.h.ncf = (float)t.h.nc;
-    t.h.tf0f = (float)t.h.tf0; t.h.tflf = (float)t.h.tfl; t.h.bkt_inv_wf = (float)t.h.bkt_inv_w;
-    t.h.inv_nif = (float)(1.0 / t.h.ni); t.h.inv_ncf = (float)(1.0 / t.h.nc); t.h.ni_ncf = (float)(t.h.ni / t.h.nc);
-    t.h.l2first = (float)(std::log2(t.h.eff_first) * kLutPerOctave); t.h.l2last = (float)(std::log2(t.h.eff_last) * kLutPerOctave);
-    t.bkt.assign(nbkt + 1, 0);
+    t.h.bkt_inv_w = span > 0 ? (float)(nbkt / span) : 0.0f;
+    if (!(t.h.bkt_inv_w * span < nbkt)) t.h.bkt_inv_w = std::nextafter(t.h.bkt_inv_w, 0.0f);
+    t.h.l2first = (float)(std::log2(t.h.eff_first) * kLutPerOctave);
+    t.h.l2last = (float)(std::log2(t.h.eff_last) * kLutPerOctave);
+    t.bkt.assign(nbkt, 0);
     int i = 0;
-    for (int k = 0; k <= nbkt; ++k) {
-        const double edge = t.nodes[0].tf + span * k / nbkt;
-        while (i + 1 < n && t.nodes[i + 1].tf <= edge) ++i;
+    for (int k = 0; k < nbkt; ++k) {
+        // the kernel forms the bucket index as (int)((float)(t - f_first) * bkt_inv_w); its two float roundings
+        // move the product by less than 2^-22 of itself, so an offset that yields index k is at least
+        // k / bkt_inv_w * (1 - 2^-22): nodes up to that (slightly lowered) edge can never overshoot t
+        const double edge = t.h.f_first + (t.h.bkt_inv_w > 0 ? (double)k / (double)t.h.bkt_inv_w * (1.0 - 2.4e-7) : 0.0);
+        while (i + 1 < n && t.cells[i + 1].f <= edge) ++i;
         t.bkt[k] = (uint16_t)i;
     }
-    t.bkt[nbkt] = (uint16_t)(n - 1);
     return Status();
 }
 
-size_t band_bytes(const BandTableD &t, int precision) {
-    const size_t node = precision == EGGPHOT_FP64 ? sizeof(double) * 6 : sizeof(FilterNodeF);
-    size_t b = ((size_t)t.h.n * node + 15) & ~size_t(15);
-    if (precision != EGGPHOT_FP64) b += ((size_t)t.h.n * sizeof(float) + 15) & ~size_t(15);
+size_t band_bytes(const BandTableD &t, int) {
+    size_t b = ((size_t)(t.h.n ? t.h.n + 1 : 0) * sizeof(FilterCellD) + 15) & ~size_t(15);
     b += ((t.bkt.size() * sizeof(uint16_t)) + 15) & ~size_t(15);
     return b;
 }
@@ -184,29 +171,18 @@ size_t band_bytes(const BandTableD &t, int precision) {
 void append_band(std::vector<uint8_t> &blob, size_t header_pos, const BandTableD &t, int precision) {
     BandHeader h = t.h;
     align16(blob);
-    h.node_off = (uint32_t)blob.size();
-    if (precision == EGGPHOT_FP64) {
-        for (const FilterNodeD &e : t.nodes) {
-            const double v[6] = {e.tf, e.R, e.s, e.dl, e.I0, e.C1};
-            const uint8_t *p = reinterpret_cast<const uint8_t *>(v);
-            blob.insert(blob.end(), p, p + sizeof(v));
-        }
-    } else {
-        std::vector<float> tflo;
-        for (const FilterNodeD &e : t.nodes) tflo.push_back((float)(e.tf - (double)(float)e.tf));
-        for (const FilterNodeD &e : t.nodes) {
-            FilterNodeF o;
-            o.tf = (float)e.tf; o.R = (float)e.R; o.s = (float)e.s; o.dl = (float)e.dl;
-            const double i0 = 1.5 + e.I0 / h.ni, c1 = 1.5 + e.C1 / h.nc;
-            o.I0h = (float)i0; o.I0l = (float)(i0 - (double)o.I0h);
-            o.C1h = (float)c1; o.C1l = (float)(c1 - (double)o.C1h);
+    h.cell_off = (uint32_t)blob.size();
+    for (const FilterCellD &e : t.cells) {
+        if (precision == EGGPHOT_FP64) {
+            const uint8_t *p = reinterpret_cast<const uint8_t *>(&e);
+            blob.insert(blob.end(), p, p + sizeof(e));
+        } else {
+            FilterCellF o{};
+            o.f = e.f; o.lam = e.lam; o.k0 = e.k0; o.hr = e.hr;
+            o.s = (float)e.s; o.dl = (float)e.dl;
             const uint8_t *p = reinterpret_cast<const uint8_t *>(&o);
             blob.insert(blob.end(), p, p + sizeof(o));
         }
-        align16(blob);
-        h.tflo_off = (uint32_t)blob.size();
-        const uint8_t *p = reinterpret_cast<const uint8_t *>(tflo.data());
-        blob.insert(blob.end(), p, p + tflo.size() * sizeof(float));
     }
     align16(blob);
     h.bkt_off = (uint32_t)blob.size();
@@ -216,47 +192,42 @@ void append_band(std::vector<uint8_t> &blob, size_t header_pos, const BandTableD
     std::memcpy(blob.data() + header_pos, &h, sizeof(h));
 }
 
-// Rest-frame weights of one band on one grid: the same interval arithmetic as the kernels, in
-// double, at z = 0, applied to the two hat functions of each interval.
-RfWeights rf_weights(const BandTableD &t, const Grid &g) {
+// Rest-frame weights of one band on one grid (flux_rf = sum_j S_j w_j): the union-node trapezoid of
+// [vif] sed2flux walked directly in double at z = 0, applied to the hat function of every node.
+RfWeights rf_weights(const Filter &f, const Grid &g) {
     RfWeights r;
-    const int N = g.n();
-    r.covered = N >= 2 && g.x.front() <= t.h.full_first && g.x.back() >= t.h.full_last;
-    if (!r.covered || t.h.n < 2) return r;
-    int jlo = std::max(last_le(g.x, t.h.eff_first), 0);
-    int jhi = (int)(std::lower_bound(g.x.begin(), g.x.end(), t.h.eff_last) - g.x.begin());
+    const int N = g.n(), nf = (int)f.lam.size();
+    r.covered = N >= 2 && nf >= 2 && g.x.front() <= f.lam.front() && g.x.back() >= f.lam.back();
+    if (!r.covered) return r;
+    const int jlo = std::max(last_le(g.x, f.lam.front()), 0);
+    int jhi = (int)(std::lower_bound(g.x.begin(), g.x.end(), f.lam.back()) - g.x.begin());
     jhi = std::min(jhi, N - 1);
     if (jhi <= jlo) return r;
     r.j0 = jlo;
     r.w.assign(jhi - jlo + 1, 0.0);
-    const int n = (int)t.h.n;
-    const double tfa = t.nodes[0].tf, tfb = t.nodes[n - 1].tf;
-    BandScal<double> bs{};
-    bs.inv_ni = bs.inv_nc = bs.ni = bs.nc = bs.ni_nc = 1.0;
-    bs.tot0h = t.h.tot0; bs.tot1h = t.h.tot1; bs.tot0l = bs.tot1l = 0.0; bs.split = (int)t.h.split;
-    auto tfget = [&](int i) { return t.nodes[i].tf; };
-    struct NodeEval { double tt, te, u; int cell; NodeQ<double> q; double s, dl; };
-    auto eval = [&](int j) {
-        NodeEval e;
-        e.tt = g.x[j] - t.h.fc;
-        e.te = std::min(std::max(e.tt, tfa), tfb);
-        e.cell = find_cell<double>(tfget, t.bkt.data(), (int)t.h.nbkt, t.h.tf0, t.h.bkt_inv_w, n, e.te);
-        e.u = e.te - t.nodes[e.cell].tf;
-        node_quantities(t.nodes[e.cell], e.u, e.q);
-        e.s = t.nodes[e.cell].s;
-        e.dl = t.nodes[e.cell].dl;
-        return e;
+    // union nodes: filter nodes and the SED nodes strictly inside the filter span
+    std::vector<double> u(f.lam);
+    for (int j = jlo; j <= jhi; ++j)
+        if (g.x[j] > f.lam.front() && g.x[j] < f.lam.back()) u.push_back(g.x[j]);
+    std::sort(u.begin(), u.end());
+    u.erase(std::unique(u.begin(), u.end()), u.end());
+    auto hat = [&](double q, int &j, double &al) { // S(q) = (1 - al) S_j + al S_{j+1}
+        j = std::min(std::max(last_le(g.x, q), jlo), jhi - 1);
+        al = (q - g.x[j]) / (g.x[j + 1] - g.x[j]);
     };
-    NodeEval L = eval(jlo);
-    for (int j = jlo; j < jhi; ++j) {
-        NodeEval Rr = eval(j + 1);
-        const double dte = Rr.te - L.te, xr = Rr.te - L.tt;
-        IntervalW<double> w;
-        double sg;
-        interval_weights(L.tt, 0.0, L.q, L.s, L.dl, L.u, L.cell, Rr.tt, 0.0, Rr.q, Rr.cell, dte, xr, bs, w);
-        r.w[j - jlo] += interval_apply(w, 1.0, 0.0, sg);
-        r.w[j + 1 - jlo] += interval_apply(w, 0.0, 1.0, sg);
-        L = Rr;
+    for (size_t k = 0; k + 1 < u.size(); ++k) {
+        const double h = u[k + 1] - u[k];
+        // the filter cell that holds this union cell (a repeated filter wavelength is a jump of R: the
+        // cell on its left ends with the first value, the cell on its right starts with the last)
+        const int i = std::min(std::max(last_le(f.lam, 0.5 * (u[k] + u[k + 1])), 0), nf - 2);
+        const double d = f.lam[i + 1] - f.lam[i], sl = d > 0 ? (f.res[i + 1] - f.res[i]) / d : 0.0;
+        for (int e = 0; e < 2; ++e) {
+            const double q = u[k + e], w = 0.5 * h * (f.res[i] + sl * (q - f.lam[i]));
+            int j; double al;
+            hat(q, j, al);
+            r.w[j - jlo] += w * (1.0 - al);
+            r.w[j + 1 - jlo] += w * al;
+        }
     }
     return r;
 }
@@ -280,6 +251,8 @@ Status make_grid_thresholds(Grid &g, bool apply_igm, const char *what) {
 
 void Grid::build_lut() {
     lut.clear();
+    idx.assign(x.size(), 0.0);
+    for (size_t j = 0; j + 1 < x.size(); ++j) idx[j] = 1.0 / (x[j + 1] - x[j]);
     if (x.empty()) return;
     lut_e0 = (int)std::floor(std::log2(x.front())) - 1;
     const int nk = (int)std::ceil((std::log2(x.back()) - lut_e0) * kLutPerOctave) + 2;
@@ -525,20 +498,24 @@ Status prepare(const eggphot_libs &L, const eggphot_filters *bands, const eggpho
     // ---- map of the disk grid onto the optical (bulge) grid
     if (P.has_bulge) {
         const int nd = P.grid_disk.n(), nb = P.grid_bulge.n();
-        P.u_oleft.assign(nd, -1); P.u_ofrac.assign(nd, 0.0); P.u_prevopt.assign(nd, 0); P.u_isopt.assign(nd, 0);
-        P.u_dprev.assign(nd, 0.0);
-        int o = -1, po = 0;
+        P.u_oleft.assign(nd, -1); P.u_ofrac.assign(nd, 0.0); P.u_isopt.assign(nd, 0);
+        int o = -1;
         for (int j = 0; j < nd; ++j) {
             const double xj = P.grid_disk.x[j];
             while (o + 1 < nb && P.grid_bulge.x[o + 1] <= xj) ++o;
             P.u_oleft[j] = o;
-            if (o >= 0 && P.grid_bulge.x[o] == xj) { P.u_isopt[j] = 1; po = j; }
+            if (o >= 0 && P.grid_bulge.x[o] == xj) P.u_isopt[j] = 1;
             else if (o >= 0 && o + 1 < nb)
                 P.u_ofrac[j] = (xj - P.grid_bulge.x[o]) / (P.grid_bulge.x[o + 1] - P.grid_bulge.x[o]);
-            P.u_prevopt[j] = (uint16_t)po;
-            P.u_dprev[j] = P.u_isopt[j] ? 0.0 : xj - P.grid_disk.x[po];
             if (o < 0 || (o + 1 >= nb && !P.u_isopt[j])) P.u_oleft[j] = -1; // outside the optical span: no bulge light
         }
+        P.u_dxo.assign(nd, 0.0);
+        int next = -1; // disk-grid index of the next optical node
+        for (int j = nd - 1; j >= 0; --j)
+            if (P.u_isopt[j]) {
+                if (next >= 0) P.u_dxo[j] = P.grid_disk.x[next] - P.grid_disk.x[j];
+                next = j;
+            }
     }
 
     // ---- band tables, packed into groups under the shared-memory budget
@@ -584,11 +561,8 @@ Status prepare(const eggphot_libs &L, const eggphot_filters *bands, const eggpho
 
     // ---- rest-frame weights
     for (size_t b = 0; b < P.rfbands.size(); ++b) {
-        BandTableD t;
-        st = build_band_table(P.rfbands[b], (uint32_t)b, 2, t);
-        if (!st.ok()) return st;
-        P.rf_bulge.push_back(P.has_bulge ? rf_weights(t, P.grid_bulge) : RfWeights());
-        P.rf_disk.push_back(rf_weights(t, P.grid_disk));
+        P.rf_bulge.push_back(P.has_bulge ? rf_weights(P.rfbands[b], P.grid_bulge) : RfWeights());
+        P.rf_disk.push_back(rf_weights(P.rfbands[b], P.grid_disk));
     }
     return Status();
 }

@@ -44,8 +44,9 @@ struct Grid {
     // log2-spaced lookup for "last node <= v": lut[k] = last j with x[j] <= 2^(lut_e0 + k/kLutPerOctave)
     std::vector<uint16_t> lut;
     int lut_e0 = 0;
+    std::vector<double> idx;  // 1/(x[j+1]-x[j]) (0 for the last node): rest-frame slopes are differences times this
     int n() const { return (int)x.size(); }
-    void build_lut();
+    void build_lut();         // also fills idx
 };
 
 enum DiskMode { DISK_BOTH = 0, DISK_OPT = 1, DISK_IR = 2 };
@@ -89,15 +90,14 @@ struct Prepared {
     std::vector<double> rows_disk_ir;    // IR templates (generic SED / cs17 DUST) on grid_disk (empty if DISK_OPT)
     std::vector<double> rows_disk_pah;   // cs17 PAH on grid_disk
 
-    // bulge evaluated on the disk grid (see phot_core.cuh, "second SED on the same weights"): for every
-    // disk-grid node the optical node at or before it (index into grid_bulge, -1 before the first), its
-    // fractional position inside that optical interval (0 on an optical node) and the disk-grid index of
-    // that optical node
+    // bulge evaluated on the disk grid (the same piece-wise linear function, so that both components share
+    // one evaluation of Lambda per node): for every disk-grid node the optical node at or before it (index
+    // into grid_bulge, -1 before the first) and its fractional position inside that optical interval
     std::vector<int32_t> u_oleft;
     std::vector<double> u_ofrac;
-    std::vector<uint16_t> u_prevopt;
-    std::vector<double> u_dprev;   // rest-frame distance back to that optical node (0 on an optical node)
     std::vector<uint8_t> u_isopt;
+    std::vector<double> u_dxo;     // rest-frame distance from an optical node to the next optical node, 0 on the
+                                   // other nodes: the bulge's union cells start at optical nodes only
 
     std::vector<BandGroup> groups;
     std::vector<RfWeights> rf_bulge, rf_disk;    // [nrf]

@@ -1,10 +1,10 @@
 // emul.cpp — TEST-ONLY sequential walk of the device algorithm on the host.
 //
 // Not part of the product and never loaded by egg_b200/: it exists so that the table builder
-// (phot_tables.cpp) and the interval arithmetic (phot_core.cuh) — the exact code the CUDA kernels
-// compile — can be checked against the oracle in the CPU-only test tier, in both arithmetic
-// modes, before any GPU time is spent.  The warp orchestration of phot_kernels.cu (passes,
-// shuffles, reductions) is replaced by plain loops; everything numeric is shared.
+// (phot_tables.cpp) and the curvature-form arithmetic (phot_core.cuh) — the exact code the CUDA
+// kernels compile — can be checked against the oracle in the CPU-only test tier, in both
+// arithmetic modes, before any GPU time is spent.  The warp orchestration of phot_kernels.cu
+// (passes, reductions) is replaced by plain loops; everything numeric is shared.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -15,18 +15,6 @@
 using namespace eggphot;
 
 namespace {
-
-template <typename real> struct Pos;
-template <> struct Pos<float> {
-    static void at(const Grid &g, int j, double opz, float fc, float &th, float &tl) {
-        const float hi = (float)g.x[j], lo = (float)(g.x[j] - (double)hi);
-        const float oh = (float)opz, ol = (float)(opz - (double)oh);
-        node_pos(hi, lo, oh, ol, fc, th, tl);
-    }
-};
-template <> struct Pos<double> {
-    static void at(const Grid &g, int j, double opz, double fc, double &th, double &tl) { node_pos(g.x[j], opz, fc, th, tl); }
-};
 
 int last_le(const std::vector<double> &x, double v) {
     return (int)(std::upper_bound(x.begin(), x.end(), v) - x.begin()) - 1;
@@ -133,37 +121,35 @@ void run(const Prepared &P, const eggphot_galaxies &G, size_t ngal, double *fd, 
                     int jlo = std::max(last_le(gr.x, h.eff_first / opz * (1.0 - 1e-15)), 0);
                     int jhi = (int)(std::lower_bound(gr.x.begin(), gr.x.end(), h.eff_last / opz * (1.0 + 1e-15)) - gr.x.begin());
                     jhi = std::min(jhi, n - 1);
-                    BandView<real> bv;
-                    make_band_view(blob, h, bv);
-                    CompSum<real> accd, accb;
-                    accd.clear(); accb.clear();
-                    NodeState<real> L, R;
-                    real th, tl;
-                    if (jhi > jlo) { Pos<real>::at(gr, jlo, opz, bv.fc, th, tl); eval_node<real>(bv, th, tl, SD[jlo], L); }
-                    for (int j = jlo; j < jhi; ++j) {
-                        Pos<real>::at(gr, j + 1, opz, bv.fc, th, tl);
-                        eval_node<real>(bv, th, tl, SD[j + 1], R);
-                        IntervalW<real> w;
-                        eval_weights<real>(bv, L, R, w);
-                        real sg;
-                        accd.add(interval_apply(w, L.S, R.S, sg));
-                        if (bulge_on) {
-                            real T = interval_apply(w, SBU[j], SBU[j + 1], sg);
-                            // left node is IR-only and strictly inside the filter span: undo the split it makes
-                            if (!P.u_isopt[j] && L.t > bv.tf0 && L.t < bv.tfl) {
-                                real tph, tpl;
-                                Pos<real>::at(gr, P.u_prevopt[j], opz, bv.fc, tph, tpl);
-                                const real h1 = std::min((L.t - tph) + (L.tl - tpl), L.u);
-                                const real dtr = (R.t - L.t) + (R.tl - L.tl);
-                                const real h2 = std::min(dtr, L.dl - L.u);
-                                T += unsplit_correction<real>(L.s, sg, h1, h2);
+                    if (jhi > jlo) {
+                        BandView<real> bv;
+                        make_band_view<real>(blob, h, bv);
+                        const real opzr = (real)opz;
+                        double accd = 0, accb = 0;
+                        real cd = 0, cb = 0;
+                        for (int j = jlo + 1; j < jhi; ++j) {
+                            const double t = std::fma(opz, gr.x[j], -bv.fc);
+                            const int c = find_cell(bv.cells, bv.bkt, bv.nbkt, bv.f_first, bv.bkt_inv_w, t);
+                            double u;
+                            const double lam = lambda_in_cell(bv.cells[c], t, u);
+                            const double r0 = slope(SD[j], SD[j + 1], gr.idx[j]), rm = slope(SD[j - 1], SD[j], gr.idx[j - 1]);
+                            accd = std::fma(lam, r0 - rm, accd);
+                            const real ur = (real)u, sr = (real)bv.cells[c].s, dlr = (real)bv.cells[c].dl;
+                            cd += (real)r0 * gamma_term<real>(sr, dlr, ur, (real)(1.0 / gr.idx[j]) * opzr);
+                            if (bulge_on) {
+                                const double b0 = slope(SBU[j], SBU[j + 1], gr.idx[j]), bm = slope(SBU[j - 1], SBU[j], gr.idx[j - 1]);
+                                accb = std::fma(lam, b0 - bm, accb);
+                                cb += (real)b0 * gamma_term<real>(sr, dlr, ur, (real)P.u_dxo[j] * opzr);
                             }
-                            accb.add(T);
                         }
-                        L = R;
+                        // the SED interval that holds the split node: b = last node left of it (jlo <= b < jhi)
+                        int b = jlo;
+                        while (b + 1 < jhi && std::fma(opz, gr.x[b + 1], -bv.fc) < bv.f_split) ++b;
+                        const double tb1 = std::fma(opz, gr.x[b + 1], -bv.fc), iopz = 1.0 / opz;
+                        fdv = band_total(bv, iopz, accd, (double)cd, (double)SD[b + 1], slope(SD[b], SD[b + 1], gr.idx[b]), tb1) * aflux;
+                        if (bulge_on)
+                            fbv = band_total(bv, iopz, accb, (double)cb, (double)SBU[b + 1], slope(SBU[b], SBU[b + 1], gr.idx[b]), tb1) * aflux * a_b;
                     }
-                    fdv = ((double)accd.s + (double)accd.c) * aflux;
-                    fbv = ((double)accb.s + (double)accb.c) * aflux * a_b;
                 }
                 if (!std::isfinite(fdv)) fdv = 0;
                 if (!std::isfinite(fbv)) fbv = 0;
