@@ -57,7 +57,7 @@ struct eggphot_ctx {
     cudaStream_t stream = nullptr;
     // prepared tables on the device
     std::vector<DevBuf> blobs;
-    DevBuf xB, xD, gridD, dxo, lutB, lutD, rowsB, rowsDopt, rowsDir, rowsDpah, opt_use, rfB, rfD, rfW, errflag, scratch, u_oleft, u_ofrac, u_isopt;
+    DevBuf xB, xD, gridrec, lutB, lutD, rowsB, rowsDopt, rowsDir, rowsDpah, opt_use, rfB, rfD, rfW, errflag, scratch, u_oleft, u_ofrac, u_isopt;
     int strideB = 0, strideD = 0;
     FluxParams base{};
     int grid_blocks = 0;
@@ -199,17 +199,27 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
 
     // ---- tables
     uint64_t tb = 0;
-    const int per16 = P.precision == EGGPHOT_FP64 ? 2 : 4;
+    const int per16 = 4; // rows are read four elements at a time in both precisions
     c->strideB = (P.grid_bulge.n() + per16 - 1) / per16 * per16;
     c->strideD = (P.grid_disk.n() + per16 - 1) / per16 * per16;
 #define CK(x) do { if ((e = (x)) != cudaSuccess) return c->cuda_fail(e, #x); } while (0)
     CK(upload_grid(P.grid_bulge, c->xB, c->lutB, tb));
     CK(upload_grid(P.grid_disk, c->xD, c->lutD, tb));
-    {   // disk grid as {x, 1/dx} pairs (+ one padding record: phase B reads x of node j + 1)
-        std::vector<double> g2(2 * ((size_t)P.grid_disk.n() + 1), 0.0);
-        for (int j = 0; j < P.grid_disk.n(); ++j) { g2[2 * j] = P.grid_disk.x[j]; g2[2 * j + 1] = P.grid_disk.idx[j]; }
-        CK(c->gridD.upload(g2.data(), g2.size() * sizeof(double)));
-        tb += c->gridD.bytes;
+    {   // disk grid records for phase B (+ one padding record: x of node b + 1 is read)
+        const Grid &g = P.grid_disk;
+        const int n = g.n();
+        auto dxo = [&](int j) { return j < (int)P.u_dxo.size() ? P.u_dxo[j] : 0.0; };
+        auto dx = [&](int j) { return j + 1 < n ? g.x[j + 1] - g.x[j] : 0.0; };
+        if (P.precision == EGGPHOT_FP64) {
+            std::vector<GridRecD> r((size_t)n + 1, GridRecD{0, 0, 0, 0});
+            for (int j = 0; j < n; ++j) r[j] = GridRecD{g.x[j], g.idx[j], dx(j), dxo(j)};
+            CK(c->gridrec.upload(r.data(), r.size() * sizeof(GridRecD)));
+        } else {
+            std::vector<GridRecF> r((size_t)n + 1, GridRecF{0, 0, 0, 0, 0, 0});
+            for (int j = 0; j < n; ++j) r[j] = GridRecF{g.x[j], g.idx[j], (float)dx(j), (float)dxo(j), (float)g.idx[j], 0.0f};
+            CK(c->gridrec.upload(r.data(), r.size() * sizeof(GridRecF)));
+        }
+        tb += c->gridrec.bytes;
     }
     CK(upload_rows(c->rowsB, P.rows_bulge_opt, P.nopt_sed, P.grid_bulge.n(), c->strideB, P.precision, tb));
     CK(upload_rows(c->rowsDopt, P.rows_disk_opt, P.nopt_sed, P.grid_disk.n(), c->strideD, P.precision, tb));
@@ -217,15 +227,17 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
     CK(upload_rows(c->rowsDpah, P.rows_disk_pah, P.nir_sed, P.grid_disk.n(), c->strideD, P.precision, tb));
     if (!P.opt_use.empty()) CK(c->opt_use.upload(P.opt_use.data(), P.opt_use.size()));
     if (!P.u_oleft.empty()) {
-        CK(c->u_oleft.upload(P.u_oleft.data(), P.u_oleft.size() * sizeof(int32_t)));
-        CK(c->u_isopt.upload(P.u_isopt.data(), P.u_isopt.size()));
-        if (P.precision == EGGPHOT_FP64) {
-            CK(c->u_ofrac.upload(P.u_ofrac.data(), P.u_ofrac.size() * sizeof(double)));
-            CK(c->dxo.upload(P.u_dxo.data(), P.u_dxo.size() * sizeof(double)));
-        } else {
-            std::vector<float> f(P.u_ofrac.begin(), P.u_ofrac.end()), d(P.u_dxo.begin(), P.u_dxo.end());
+        // (padded to a multiple of four entries: phase A4 reads them four at a time)
+        const size_t n4 = (P.u_oleft.size() + 3) & ~size_t(3);
+        std::vector<int32_t> ol(P.u_oleft); ol.resize(n4, -1);
+        std::vector<uint8_t> io(P.u_isopt); io.resize(n4, 0);
+        std::vector<double> fr(P.u_ofrac); fr.resize(n4, 0.0);
+        CK(c->u_oleft.upload(ol.data(), ol.size() * sizeof(int32_t)));
+        CK(c->u_isopt.upload(io.data(), io.size()));
+        if (P.precision == EGGPHOT_FP64) CK(c->u_ofrac.upload(fr.data(), fr.size() * sizeof(double)));
+        else {
+            std::vector<float> f(fr.begin(), fr.end());
             CK(c->u_ofrac.upload(f.data(), f.size() * sizeof(float)));
-            CK(c->dxo.upload(d.data(), d.size() * sizeof(float)));
         }
     }
     c->blobs.resize(P.groups.size());
@@ -266,7 +278,7 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
     p.nB = P.grid_bulge.n(); p.nD = P.grid_disk.n();
     p.strideB = c->strideB; p.strideD = c->strideD;
     p.xB = (const double *)c->xB.p; p.xD = (const double *)c->xD.p;
-    p.gridD = (const double2 *)c->gridD.p; p.dxo = c->dxo.p;
+    p.gridrec = c->gridrec.p;
     p.lutB = (const uint16_t *)c->lutB.p; p.lutD = (const uint16_t *)c->lutD.p;
     p.lutB_n = (int)P.grid_bulge.lut.size(); p.lutD_n = (int)P.grid_disk.lut.size();
     p.lutB_e0 = P.grid_bulge.lut_e0; p.lutD_e0 = P.grid_disk.lut_e0;

@@ -5,13 +5,14 @@
 // :2197 is the trapezoid rule applied to g = R * S on the UNION of the filter nodes and the SED
 // nodes inside the filter span, with R and S each interpolated linearly between their own nodes
 // (node set A).  The reference walks that union node by node (~1000 nodes per
-// galaxy-band).  Here the sum is transformed so that each SED node costs one evaluation of a
-// per-band piece-wise quadratic and one multiply-add per galaxy component, whatever the number of
-// filter nodes, and so that nothing is exchanged between neighbouring nodes.
+// galaxy-band).  Here the sum is transformed into  T = sum_j S_j W_j  over the SED nodes of the
+// band's window, with weights W_j that depend on (redshift, band) only — every component of a
+// galaxy shares them — and that cost one evaluation of a per-band piece-wise quadratic per node,
+// whatever the number of filter nodes.
 //
-// Derivation ("curvature form").  Let t_j be the observed positions of the SED nodes, S linear on
-// [t_j, t_{j+1}] with slope sigma_j; K0 = cumulative integral of R, L = cumulative integral of K0
-// (K0 = L = 0 left of the filter; K0 = tot0 and L linear right of it).  On one SED interval
+// Derivation.  Let t_j be the observed positions of the SED nodes, S linear on [t_j, t_{j+1}] with
+// slope sigma_j; K0 = cumulative integral of R, L = cumulative integral of K0 (K0 = L = 0 left of
+// the filter; K0 = tot0 and L linear right of it).  On one SED interval
 //     union trapezoid = exact integral + (sigma_j/6) * sum over the union cells inside of s_cell * h^3
 // (R*S is quadratic in a union cell, second derivative 2 s sigma; the trapezoid error is h^3 f''/12).
 //  * exact integral, by parts:     [K0 S] - sigma_j (L(t_{j+1}) - L(t_j))
@@ -20,36 +21,31 @@
 //    (u = offset of t in its cell):  sum s h^3 = G(t_{j+1}) - G(t_j) - 3 gamma_j,
 //        gamma_j = s_c b u (b - u),   b = min(t_{j+1} - f_c, dl_c)
 //    (c = filter cell of t_j; b - u is the distance from t_j to the next union node).
-// Summing over the intervals of a window jlo..jhi with t_jlo <= f_first and t_jhi >= f_last, and
-// summing by parts once more, everything collects on the nodes:
+// With Lambda = L - G/6, which inside filter cell c is the QUADRATIC
+//     Lambda(t) = Lambda_c + u (K0_c + u R_c/2)        (the cubic terms of L and G/6 cancel),
+// and E_j = (Lambda(t_{j+1}) - Lambda(t_j) + gamma_j/2) / (t_{j+1} - t_j), the sum over the intervals of a
+// window jlo..jhi (t_jlo <= f_first, t_jhi >= f_last), re-collected on the nodes, is
 //
-//     T = tot0 S_jhi - Lambda(t_jhi) sigma_{jhi-1} + sum_{jlo<j<jhi} Lambda(t_j) (sigma_j - sigma_{j-1})
-//         - 1/2 sum_{jlo<j<jhi} sigma_j gamma_j
+//     T = sum_{j=jlo..jhi} S_j W_j,      W_j = E_j - E_{j-1},   E_{jlo-1} = 0,  E_jhi = tot0
 //
-// with Lambda = L - G/6, which inside filter cell c is the QUADRATIC
-//     Lambda(t) = Lambda_c + u (K0_c + u R_c/2)        (the cubic terms of L and G/6 cancel).
-// Node jlo contributes nothing (Lambda = 0 and u = 0 left of the filter).  In rest-frame units
-// sigma_j = rho_j/(1+z) with rho_j = (S_{j+1}-S_j)/(x_{j+1}-x_j), so the curvature
-// k_j = rho_j - rho_{j-1} depends on the galaxy only, Lambda(t_j) on (z, band) only.
-// The result equals the union-node trapezoid in exact arithmetic.
+// (the [K0 S] terms telescope to tot0 S_jhi).  Lambda = 0 and u = 0 at jlo (left of the filter).  The result
+// equals the union-node trapezoid in exact arithmetic; W_j is the quadrature weight of node j.
 //
-// Two-sided gauge.  sum_j k_j (alpha + beta t_j) telescopes to end terms, so Lambda may be shifted
-// by a linear function.  Cells left of a split node m (the half-mass point of the band) keep the
-// Lambda above, which vanishes towards the left end; cells right of it store
-// Lambda - (lam_end + tot0 (t - f_last)), which vanishes towards the right end.  A far wing of the
-// filter then only ever multiplies small table values, however bright the SED is there (a Lyman
-// break seen through the 1e-7 red wing of a blue band).  Re-collecting the end terms moves them to
-// the SED interval [t_b, t_{b+1}] that holds the split (b = last node with t_b < f_m):
+// Two-sided gauge.  Adding a linear function to Lambda shifts every E by a constant and leaves the
+// W untouched.  Cells left of a split node m (the half-mass point of the band) keep the Lambda above,
+// which vanishes towards the left end; cells right of it store Lambda - asym(t), asym(t) = lam_end +
+// tot0 (t - f_last), which vanishes towards the right end (there E_jhi = 0).  A far wing of the filter
+// then only ever differences small table values, however bright the SED is there (a Lyman break seen
+// through the 1e-7 red wing of a blue band).  Only the SED interval [t_b, t_{b+1}] that holds the split
+// (b = last node with t_b < f_m) mixes the gauges: E_b takes Lambda~(t_{b+1}) + asym(t_{b+1}), and
+// node b+1 sees E_b - tot0.
 //
-//     T = tot0 S_{b+1} - asym(t_{b+1}) sigma_b + sum_{jlo<j<jhi} Lambda~(t_j) (sigma_j - sigma_{j-1})
-//         - 1/2 sum_{jlo<j<jhi} sigma_j gamma_j,          asym(t) = lam_end + tot0 (t - f_last).
-//
-// Numerics.  sum Lambda_j k_j is a second difference of a function that grows like tot0*W across
-// the band: its terms are ~W/dx (10^2..10^4) times larger than the result.  It is therefore
-// evaluated in IEEE double in BOTH arithmetic modes (B200 issues FP64 at half the FP32 rate), with
-// the differences S_{j+1}-S_j taken exactly; what distinguishes the fp32 mode is that the SEDs are
-// built and stored in float and the small trapezoid-error term (sum sigma gamma, <~1e-3 of the
-// flux) is evaluated in float.
+// Numerics.  The E_j are first differences of a function that grows like tot0*W across the band
+// and the W_j differences of those: they are formed in IEEE double in BOTH arithmetic modes (B200
+// issues FP64 at half the FP32 rate), then rounded to the mode's real type.  The W_j of a
+// non-negative response are non-negative up to the small trapezoid-error term, so sum S_j W_j has no
+// cancellation: in the fp32 mode the SEDs, the gamma terms and the products S_j W_j are float, the
+// per-lane partial sums are added across lanes in double.
 #ifndef EGGPHOT_PHOT_CORE_CUH
 #define EGGPHOT_PHOT_CORE_CUH
 
@@ -101,9 +97,25 @@ struct __attribute__((aligned(16))) BandHeader {
     uint32_t cell_off;            // byte offset of the FilterCell array (n + 1 records)
     uint32_t bkt_off;             // byte offset of the uint16 bucket array (nbkt entries)
     uint32_t out_col;             // column in the sorted band list
-    uint32_t split;               // index of the split node
+    uint32_t split;               // index of the split node; bit 31: one probe settles the cell lookup (buckets are
+                                  // narrower than every cell)
 };
 static_assert(sizeof(BandHeader) == 128, "BandHeader layout");
+
+// One node of a rest-frame SED grid as phase B reads it (32 bytes, two 128-bit loads).
+struct __attribute__((aligned(16))) GridRecF {
+    double x, idx;        // wavelength, 1/(x[j+1] - x[j]) (0 for the last node)
+    float dx, dxo, idxf;  // x[j+1] - x[j]; distance to the next OPTICAL node if j is one, else 0 (the bulge's
+    float pad;            // union cells start at optical nodes only); idx as float
+};
+struct __attribute__((aligned(16))) GridRecD {
+    double x, idx, dx, dxo;
+};
+template <typename real> struct GridRecOf;
+template <> struct GridRecOf<float> { typedef GridRecF type; };
+template <> struct GridRecOf<double> { typedef GridRecD type; };
+EGG_HD float grid_idx(const GridRecF &g) { return g.idxf; }
+EGG_HD double grid_idx(const GridRecD &g) { return g.idx; }
 
 // Band seen through the kernel's real type.
 template <typename real> struct BandView {
@@ -112,6 +124,7 @@ template <typename real> struct BandView {
     double fc, f_first, f_split, tot0, asym0;
     float bkt_inv_w;
     int n, nbkt;
+    bool one_probe;
 };
 template <typename real> EGG_HD void make_band_view(const uint8_t *blob, const BandHeader &h, BandView<real> &v) {
     v.cells = reinterpret_cast<const typename CellOf<real>::type *>(blob + h.cell_off);
@@ -119,6 +132,7 @@ template <typename real> EGG_HD void make_band_view(const uint8_t *blob, const B
     v.fc = h.fc; v.f_first = h.f_first; v.f_split = h.f_split; v.tot0 = h.tot0; v.asym0 = h.asym0;
     v.bkt_inv_w = h.bkt_inv_w;
     v.n = (int)h.n; v.nbkt = (int)h.nbkt;
+    v.one_probe = (h.split >> 31) != 0;
 }
 
 // Filter cell of the centred position t, f_first <= t: the largest c with f_c <= t.  bkt[k] is the
@@ -145,20 +159,6 @@ template <typename Cell> EGG_HD double lambda_in_cell(const Cell &e, double t, d
 template <typename real> EGG_HD real gamma_term(real s, real dl, real u, real dt) {
     const real b = (dt + u) < dl ? (dt + u) : dl;
     return s * b * u * (b - u);
-}
-
-// Rest-frame slope of an SED between two nodes, the difference taken exactly (both values are
-// exactly representable in double) — see "Numerics" above.
-EGG_HD double slope(float s0, float s1, double inv_dx) { return ((double)s1 - (double)s0) * inv_dx; }
-EGG_HD double slope(double s0, double s1, double inv_dx) { return (s1 - s0) * inv_dx; }
-
-// The band total from the pieces:  acc = sum Lambda~_j k_j,  corr = sum rho_j gamma_j (interior nodes),
-// S_b1 = SED value at node b+1, rho_b = slope of the interval [b, b+1] that holds the split,
-// t_b1 = centred position of node b+1.
-template <typename real>
-EGG_HD double band_total(const BandView<real> &b, double inv_opz, double acc, double corr, double S_b1, double rho_b, double t_b1) {
-    const double asym = fma(b.tot0, t_b1, b.asym0);
-    return fma(b.tot0, S_b1, inv_opz * (fma(-asym, rho_b, acc) - 0.5 * corr));
 }
 
 // IGM factor of node j (src/egg-gencat.cpp:2128-2139): [0,lz) -> 0, [lz,l0) -> a0, [l0,l1) -> a1, [l1,l2) -> a2

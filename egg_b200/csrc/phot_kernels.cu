@@ -30,7 +30,6 @@ namespace eggphot {
 
 namespace {
 
-constexpr int kMaxItems = 2 * kMaxGroupBands;
 constexpr int kLineSlots = 16;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -172,42 +171,72 @@ template <typename real> __device__ __forceinline__ CompSum<real> warp_reduce(Co
     return a;
 }
 
-// find_cell (phot_core.cuh) for a full warp: the forward scan runs as a warp-uniform loop on a vote instead of
-// a per-lane data-dependent loop.  The warp executes the longest lane's scan either way, and the lanes provably
-// stay converged for the shuffle reduction that follows the node loop (with the per-lane loop nvcc 12.9 emitted
-// neither a reconvergence barrier after it nor a WARPSYNC before the shuffles, and lanes read stale registers).
-template <typename Cell>
-__device__ __forceinline__ int find_cell_warp(const Cell *cells, const uint16_t *bkt, int nbkt, double f_first, float inv_w, double t) {
-    int k = (int)((float)(t - f_first) * inv_w);
-    k = max(0, min(k, nbkt - 1));
-    int c = bkt[k];
-    bool up = t >= cells[c + 1].f;
+// find_cell (phot_core.cuh) for a full warp.  When the band's buckets are narrower than its cells one probe
+// settles it; otherwise the forward scan runs as a warp-uniform loop on a vote instead of a per-lane
+// data-dependent loop: the warp executes the longest lane's scan either way, and the lanes provably stay
+// converged for the shuffles that follow (with a per-lane loop nvcc 12.9 emitted neither a reconvergence
+// barrier after it nor a WARPSYNC before the shuffles, and lanes read stale registers).
+template <typename real>
+__device__ __forceinline__ int find_cell_warp(const BandView<real> &b, double t) {
+    int k = (int)((float)(t - b.f_first) * b.bkt_inv_w);
+    k = max(0, min(k, b.nbkt - 1));
+    int c = b.bkt[k];
+    bool up = t >= b.cells[c + 1].f;
+    if (b.one_probe) return c + (up ? 1 : 0);
     while (__any_sync(kFull, up)) {
         c += up ? 1 : 0;
-        up = t >= cells[c + 1].f;
+        up = t >= b.cells[c + 1].f;
     }
     return c;
 }
 
-// observed width of the rest-frame interval that starts at node j: (x_{j+1} - x_j)(1+z).  fp32: from the
-// stored inverse width (it only enters the trapezoid-error term); fp64: from the node positions.
-__device__ __forceinline__ float node_dt(const double2 *g, int j, double2 gn, float opz) { (void)g; (void)j; return __fdividef(opz, (float)gn.y); }
-__device__ __forceinline__ double node_dt(const double2 *g, int j, double2 gn, double opz) { return (__ldg(&g[j + 1].x) - gn.x) * opz; }
+// four consecutive elements of a 16-byte aligned row
+template <typename real> struct Quad { real v[4]; };
+__device__ __forceinline__ Quad<float> ldg4(const float *p) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(p));
+    return Quad<float>{{a.x, a.y, a.z, a.w}};
+}
+__device__ __forceinline__ Quad<double> ldg4(const double *p) {
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    return Quad<double>{{a.x, a.y, b.x, b.y}};
+}
+__device__ __forceinline__ void st4(float *p, const Quad<float> &q) { *reinterpret_cast<float4 *>(p) = make_float4(q.v[0], q.v[1], q.v[2], q.v[3]); }
+__device__ __forceinline__ void st4(double *p, const Quad<double> &q) {
+    reinterpret_cast<double2 *>(p)[0] = make_double2(q.v[0], q.v[1]);
+    reinterpret_cast<double2 *>(p)[1] = make_double2(q.v[2], q.v[3]);
+}
+template <typename real> struct Pair;
+template <> struct Pair<float> { typedef float2 type; };
+template <> struct Pair<double> { typedef double2 type; };
+__device__ __forceinline__ GridRecF ldg_grid(const GridRecF *g) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(g)), b = __ldg(reinterpret_cast<const float4 *>(g) + 1);
+    GridRecF r;
+    r.x = __hiloint2double(__float_as_int(a.y), __float_as_int(a.x));
+    r.idx = __hiloint2double(__float_as_int(a.w), __float_as_int(a.z));
+    r.dx = b.x; r.dxo = b.y; r.idxf = b.z; r.pad = 0.0f;
+    return r;
+}
+__device__ __forceinline__ GridRecD ldg_grid(const GridRecD *g) {
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(g)), b = __ldg(reinterpret_cast<const double2 *>(g) + 1);
+    return GridRecD{a.x, a.y, b.x, b.y};
+}
 
 struct SmemLayout {
-    uint32_t tab, res, rfres, lb, win, wmid, wflag, total;
+    uint32_t tab, res, rfres, lb, lt, win, wmid, wflag, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(const FluxParams &p) {
     SmemLayout L;
     auto up = [](size_t v) { return (uint32_t)((v + 127) & ~size_t(127)); };
+    const size_t nl = p.nline > 0 ? p.nline : 0;
     uint32_t o = 0;
     L.tab = o; o += up(p.max_blob);                                              // band tables of the current group
     L.res = o; o += up((size_t)kBatch * p.nband_total * 2 * sizeof(double));     // [gal][col][comp] scaled fluxes
     L.rfres = o; o += up((size_t)kBatch * p.nrf * 2 * sizeof(double));           // [gal][rf][comp] rest-frame fluxes
-    L.lb = o; o += up((size_t)kBatch * 2 * (p.nline > 0 ? p.nline : 0) * 2 * sizeof(int)); // line windows
-    L.win = o; o += up((size_t)kBatch * p.nband_total * sizeof(uint32_t));                // node windows (jlo | jhi << 16)
-    L.wmid = o; o += up((size_t)kBatch * p.nband_total * sizeof(uint16_t));               // node left of the band's split
-    L.wflag = o; o += up((size_t)kBatch * p.nband_total);                                // bit 0: bulge covered
+    L.lb = o; o += up((size_t)kBatch * 2 * nl * 2 * sizeof(int));                // line windows [b0, b1]
+    L.lt = o; o += up((size_t)kBatch * 2 * nl * 2 * sizeof(int));                // line tasks {first owned node, task offset}
+    L.win = o; o += up((size_t)kBatch * p.nband_total * sizeof(uint32_t));       // node windows (jlo | jhi << 16)
+    L.wmid = o; o += up((size_t)kBatch * p.nband_total * sizeof(uint16_t));      // node left of the band's split
+    L.wflag = o; o += up((size_t)kBatch * p.nband_total);                        // bit 0: bulge covered
     L.total = o;
     return L;
 }
@@ -215,21 +244,27 @@ __host__ __device__ inline SmemLayout smem_layout(const FluxParams &p) {
 // ---- the kernel ------------------------------------------------------------------------------------
 // One persistent CTA carries a batch of kBatch galaxies through phases A (rest-frame SEDs into a
 // per-CTA global scratch that stays in L2), B (for each band group: tables -> shared memory by TMA,
-// warps pull (galaxy, band, component) items off a shared counter and integrate them) and C
-// (totals, data conditions, coalesced stores).
+// warps pull (galaxy, band) items off a shared counter and integrate both components) and C (totals,
+// data conditions, coalesced stores).
+// Scratch of one galaxy: [nD pairs {disk SED, bulge SED resampled on the disk grid}][bulge SED on its own grid].
 template <typename real, int NT>
 __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ FluxParams p) {
+    typedef typename Pair<real>::type real2;
+    typedef typename GridRecOf<real>::type GridRec;
+    typedef typename CellOf<real>::type Cell;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ GalScal sc[kBatch];
     __shared__ __align__(8) uint64_t bar_tab;
     __shared__ int item_ctr[kMaxGroups];
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT / 32;
     const SmemLayout L = smem_layout(p);
     const uint8_t *blob = smem + L.tab;
     double *res = reinterpret_cast<double *>(smem + L.res);
     double *rfres = reinterpret_cast<double *>(smem + L.rfres);
     int *lb = reinterpret_cast<int *>(smem + L.lb); // [gal][comp][line][2]
+    int *lt = reinterpret_cast<int *>(smem + L.lt); // [gal][comp][line][2]
     uint32_t *win = reinterpret_cast<uint32_t *>(smem + L.win); // [band in group order][gal]
     uint16_t *wmid = reinterpret_cast<uint16_t *>(smem + L.wmid);
     uint8_t *wflag = smem + L.wflag;
@@ -237,10 +272,12 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
     const int ncomp = p.has_bulge ? 2 : 1;
     const bool cs17 = p.ir_kind == EGGPHOT_IR_CS17;
     const int nbt = (int)p.nband_total, nrf = p.do_rf ? (int)p.nrf : 0;
-    const int sstride = 2 * p.strideD + p.strideB; // disk | bulge on its own grid | bulge on the disk grid
+    const int nD = p.nD, nB = p.nB, nline = p.nline;
+    const int sstride = 2 * p.strideD + p.strideB;
     real *scr = reinterpret_cast<real *>(p.scratch) + (size_t)blockIdx.x * kBatch * sstride;
     const real *rO = reinterpret_cast<const real *>(p.rowsDopt), *rI = reinterpret_cast<const real *>(p.rowsDir);
     const real *rP = reinterpret_cast<const real *>(p.rowsDpah), *rB = reinterpret_cast<const real *>(p.rowsB);
+    const GridRec *grid = reinterpret_cast<const GridRec *>(p.gridrec);
 
     if (tid == 0) {
         mbar_init(&bar_tab, 1);
@@ -261,34 +298,62 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
         for (int i = tid; i < ng * nbt * 2; i += NT) res[i] = 0.0;
         __syncthreads();
 
-        // ---- phase A2: rest-frame SEDs (get_opt_sed / get_ir_sed / merge_add / IGM) into the scratch;
-        //      emission-line windows
-        for (int gi = 0; gi < ng; ++gi) {
-            const GalScal &s = sc[gi];
-            real *SD = scr + (size_t)gi * sstride, *SB = SD + p.strideD;
-            const real a_d = (real)s.a_disk, c1 = (real)s.c1, c2 = (real)s.c2;
-            const real g0f = s.igm[0], g1f = s.igm[1], g2f = s.igm[2];
-            const real *ro = rO + (size_t)s.row_d * p.strideD, *ri = rI + (size_t)s.row_i * p.strideD;
-            const real *rp = rP + (size_t)s.row_i * p.strideD;
-            for (int j = tid; j < p.nD; j += NT) {
-                real v;
-                if (p.disk_mode == 0) v = a_d * __ldg(ro + j) + c1 * __ldg(ri + j);
-                else if (p.disk_mode == 1) v = a_d * __ldg(ro + j);
-                else v = c1 * __ldg(ri + j);
-                if (p.disk_mode != 1 && cs17) v += c2 * __ldg(rp + j);
-                if (p.apply_igm && j < p.igmD[3]) v *= igm_factor<real>(j, p.igmD[0], p.igmD[1], p.igmD[2], p.igmD[3], g0f, g1f, g2f);
-                SD[j] = v;
-            }
-            if (p.has_bulge) {
-                const real *rb = rB + (size_t)s.row_b * p.strideB;
-                for (int j = tid; j < p.nB; j += NT) {
-                    real v = __ldg(rb + j);
-                    if (p.apply_igm && j < p.igmB[3]) v *= igm_factor<real>(j, p.igmB[0], p.igmB[1], p.igmB[2], p.igmB[3], g0f, g1f, g2f);
-                    SB[j] = v;
+        // ---- phase A2: rest-frame SEDs (get_opt_sed / get_ir_sed / merge_add / IGM).  A warp takes 128
+        //      consecutive nodes of one galaxy at a time, four per lane with 128-bit row loads.
+        {
+            const int ncD = (nD + 127) >> 7, ncB = p.has_bulge ? (nB + 127) >> 7 : 0, nc = ncD + ncB;
+            for (int task = warp; task < ng * nc; task += NW) {
+                const int gi = task / nc, ch = task - gi * nc;
+                const GalScal &s = sc[gi];
+                real *DU = scr + (size_t)gi * sstride, *SB = DU + 2 * p.strideD;
+                const real g0f = s.igm[0], g1f = s.igm[1], g2f = s.igm[2];
+                if (ch < ncD) {
+                    const int j0 = (ch << 7) + 4 * lane;
+                    if (j0 < nD) {
+                        const real a_d = (real)s.a_disk, c1 = (real)s.c1, c2 = (real)s.c2;
+                        Quad<real> v;
+                        if (p.disk_mode == 0) {
+                            const Quad<real> o = ldg4(rO + (size_t)s.row_d * p.strideD + j0), i = ldg4(rI + (size_t)s.row_i * p.strideD + j0);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) v.v[k] = a_d * o.v[k] + c1 * i.v[k];
+                        } else if (p.disk_mode == 1) {
+                            const Quad<real> o = ldg4(rO + (size_t)s.row_d * p.strideD + j0);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) v.v[k] = a_d * o.v[k];
+                        } else {
+                            const Quad<real> i = ldg4(rI + (size_t)s.row_i * p.strideD + j0);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) v.v[k] = c1 * i.v[k];
+                        }
+                        if (p.disk_mode != 1 && cs17) {
+                            const Quad<real> q = ldg4(rP + (size_t)s.row_i * p.strideD + j0);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) v.v[k] += c2 * q.v[k];
+                        }
+                        if (p.apply_igm && j0 < p.igmD[3]) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                v.v[k] *= igm_factor<real>(j0 + k, p.igmD[0], p.igmD[1], p.igmD[2], p.igmD[3], g0f, g1f, g2f);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (j0 + k < nD) DU[2 * (j0 + k)] = v.v[k];
+                    }
+                } else {
+                    const int j0 = ((ch - ncD) << 7) + 4 * lane;
+                    if (j0 < nB) {
+                        Quad<real> v = ldg4(rB + (size_t)s.row_b * p.strideB + j0);
+                        if (p.apply_igm && j0 < p.igmB[3]) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                v.v[k] *= igm_factor<real>(j0 + k, p.igmB[0], p.igmB[1], p.igmB[2], p.igmB[3], g0f, g1f, g2f);
+                        }
+                        st4(SB + j0, v); // rows are zero-padded to the stride: the tail stores zeros
+                    }
                 }
             }
         }
-        // node windows of every (band, galaxy): one thread each instead of one warp each later
+        // node windows of every (band, galaxy): one thread each
         for (int idx = tid; idx < nbt * kBatch; idx += NT) {
             const int gi = idx & (kBatch - 1), fb = idx / kBatch;
             uint32_t wv = 0;
@@ -301,7 +366,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                 const double full_first = __ldg(&gh->full_first), full_last = __ldg(&gh->full_last);
                 const GalScal &s = sc[gi];
                 const double *x = p.xD;
-                const int n = p.nD;
+                const int n = nD;
                 // [vif] sed2flux: NaN (-> flux 0, src/egg-gencat.cpp:2198) unless the SED covers the filter
                 const bool covered = n >= 2 && __ldg(x) * s.opz <= full_first && __ldg(x + n - 1) * s.opz >= full_last;
                 if (covered && __ldg(&gh->n) >= 2) {
@@ -321,26 +386,26 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                         }
                         wm = (uint16_t)lo;
                     }
-                    if (p.has_bulge && p.nB >= 2 && __ldg(p.xB) * s.opz <= full_first && __ldg(p.xB + p.nB - 1) * s.opz >= full_last) fl = 1;
+                    if (p.has_bulge && nB >= 2 && __ldg(p.xB) * s.opz <= full_first && __ldg(p.xB + nB - 1) * s.opz >= full_last) fl = 1;
                 }
             }
             win[idx] = wv;
             wmid[idx] = wm;
             wflag[idx] = fl;
         }
-        for (int idx = tid; idx < ng * 2 * p.nline; idx += NT) {
-            const int gi = idx / (2 * p.nline), rem = idx % (2 * p.nline);
-            const int c = rem / p.nline, l = rem % p.nline; // c: 0 bulge, 1 disk
+        // emission-line windows ([vif] bounds, src/egg-gencat.cpp:2081-2084): one thread per (galaxy, component, line)
+        for (int idx = tid; idx < ng * 2 * nline; idx += NT) {
+            const int gi = idx / (2 * nline), rem = idx - gi * 2 * nline;
+            const int c = rem >= nline, l = rem - c * nline; // c: 0 bulge, 1 disk
             const GalScal &s = sc[gi];
             const float *ll = c ? p.line_lum_disk : p.line_lum_bulge;
             int b0 = 1, b1 = 0; // empty
-            if ((c || p.has_bulge) && ll != nullptr && ll[(g0 + gi) * p.nline + p.line_col[l]] != 0.0f) {
+            if ((c || p.has_bulge) && ll != nullptr && ll[(g0 + gi) * nline + p.line_col[l]] != 0.0f) {
                 const double *x = c ? p.xD : p.xB;
-                const int n = c ? p.nD : p.nB;
+                const int n = c ? nD : nB;
                 const uint16_t *lut = c ? p.lutD : p.lutB;
                 const int nlut = c ? p.lutD_n : p.lutB_n, e0 = c ? p.lutD_e0 : p.lutB_e0;
                 const double l0 = (double)p.line_lambda[l], lw = l0 * (s.vdisp / 2.998e5);
-                // [vif] bounds(lam, a, b) = {last <= a, first > b}  (src/egg-gencat.cpp:2081-2084)
                 const int lo = lut_last_le(x, n, lut, nlut, lut_pos(l0 - 10 * lw, e0), l0 - 10 * lw);
                 const int hi = lut_last_le(x, n, lut, nlut, lut_pos(l0 + 10 * lw, e0), l0 + 10 * lw) + 1; // first > b, n if none
                 if (!(hi == 0 || lo == n - 1)) {
@@ -353,67 +418,106 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
         }
         __syncthreads();
 
-        // ---- phase A3: emission lines (add_emission_line, src/egg-gencat.cpp:2078-2095).  Lines are sorted
-        //      by wavelength, so their node windows [b0, b1] are ordered as well.  The first line whose
-        //      window holds node j adds the contributions of all lines at j, in that order: no two threads
-        //      touch the same node and the sum order is fixed.
-        for (int idx = tid; idx < ng * 2 * p.nline * kLineSlots; idx += NT) {
-            const int w = idx % kLineSlots, q = idx / kLineSlots; // q = (gi, c, l)
-            const int gi = q / (2 * p.nline), rem = q % (2 * p.nline);
-            const int c = rem / p.nline, l = rem % p.nline;
-            const int *wb = lb + 2 * (gi * 2 + c) * p.nline; // windows of this (galaxy, component)
-            const int b0 = wb[2 * l], b1 = wb[2 * l + 1];
-            if (b0 + w > b1) continue;
-            const GalScal &s = sc[gi];
-            const float *ll = (c ? p.line_lum_disk : p.line_lum_bulge) + (g0 + gi) * p.nline;
-            const double *x = c ? p.xD : p.xB;
-            const int n = c ? p.nD : p.nB;
-            real *S = scr + (size_t)gi * sstride + (c ? 0 : p.strideD);
-            // the bulge SED carries no mass scale (applied at the end), so its line term is divided by it
-            const double inv = c ? 1.0 : (s.a_bulge > 0 ? 1.0 / s.a_bulge : 0.0);
-            int kprev = l - 1; // nearest earlier line with a non-empty window
-            while (kprev >= 0 && wb[2 * kprev] > wb[2 * kprev + 1]) --kprev;
-            const int prev_b1 = kprev >= 0 ? wb[2 * kprev + 1] : -1;
-            for (int j = b0 + w; j <= b1; j += kLineSlots) {
-                if (j <= prev_b1) continue; // an earlier line owns this node
-                const double xj = __ldg(x + j);
-                const double xm = j > 0 ? __ldg(x + j - 1) : 0.0, xp = j < n - 1 ? __ldg(x + j + 1) : 0.0;
-                const double llow = j != 0 ? 0.5 * (xm + xj) : xj - 0.5 * (xp - xj);       // :2090
-                const double lup = j != n - 1 ? 0.5 * (xj + xp) : xj + 0.5 * (xj - xm);   // :2091
-                double acc = 0.0;
-                for (int k = l; k < p.nline; ++k) {
-                    const int k0 = wb[2 * k], k1 = wb[2 * k + 1];
-                    if (k0 > k1) continue; // empty window
-                    if (k0 > j) break;     // windows are ordered: no later line reaches back to j
-                    if (j <= k1) {
-                        const double l0 = (double)p.line_lambda[k], lw = l0 * (s.vdisp / 2.998e5);
-                        acc += line_bin_t<real>(llow, lup, l0, lw, (double)ll[p.line_col[k]] * l0, p.line_average);
+        // ---- phase A3: emission lines (add_emission_line, src/egg-gencat.cpp:2078-2095), one warp per (galaxy,
+        //      component).  Lines are sorted by wavelength, so their node windows [b0, b1] are ordered as well.
+        //      The first line whose window holds node j owns it and adds the contributions of all lines at j,
+        //      in that order: no two lanes touch the same node and the sum order is fixed.  The owned nodes of
+        //      all lines are numbered consecutively (prefix sum) and dealt to the lanes.
+        if (nline > 0) {
+            for (int task = warp; task < ng * 2; task += NW) {
+                const int gi = task >> 1, c = task & 1;
+                const float *llp = c ? p.line_lum_disk : p.line_lum_bulge;
+                if ((!c && !p.has_bulge) || llp == nullptr) continue;
+                const int *wb = lb + 2 * task * nline;
+                int *wt = lt + 2 * task * nline;
+                int carry_b1 = -1, total = 0;
+                for (int base = 0; base < nline; base += 32) {
+                    const int l = base + lane;
+                    int b0 = 1, b1 = 0;
+                    if (l < nline) { b0 = wb[2 * l]; b1 = wb[2 * l + 1]; }
+                    const bool ne = b0 <= b1;
+                    int m = ne ? b1 : -1; // inclusive running maximum of b1 over the lines so far
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(kFull, m, o);
+                        if (lane >= o) m = max(m, t);
                     }
+                    int prev = __shfl_up_sync(kFull, m, 1);
+                    prev = max(lane ? prev : -1, carry_b1);
+                    const int start = max(b0, prev + 1);
+                    const int cnt = ne ? max(0, b1 - start + 1) : 0;
+                    int inc = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(kFull, inc, o);
+                        if (lane >= o) inc += t;
+                    }
+                    if (l < nline) { wt[2 * l] = start; wt[2 * l + 1] = total + inc - cnt; }
+                    total += __shfl_sync(kFull, inc, 31);
+                    carry_b1 = max(carry_b1, __shfl_sync(kFull, m, 31));
                 }
-                S[j] += (real)(xj * acc * inv);
-            }
-        }
-        __syncthreads();
-
-        // ---- phase A4: the bulge SED resampled on the disk grid (the same piece-wise linear function; lets
-        //      the quadrature of phase B serve both components from one set of interval weights)
-        if (p.has_bulge) {
-            const real *ofrac = reinterpret_cast<const real *>(p.u_ofrac);
-            for (int gi = 0; gi < ng; ++gi) {
-                const real *SB = scr + (size_t)gi * sstride + p.strideD;
-                real *SU = scr + (size_t)gi * sstride + p.strideD + p.strideB;
-                for (int j = tid; j < p.nD; j += NT) {
-                    const int o = __ldg(p.u_oleft + j);
-                    real v = real(0);
-                    if (o >= 0) {
-                        v = SB[o];
-                        if (!__ldg(p.u_isopt + j)) v = fma(__ldg(ofrac + j), SB[o + 1] - v, v);
+                __syncwarp();
+                const GalScal &s = sc[gi];
+                const float *ll = llp + (g0 + gi) * nline;
+                const double *x = c ? p.xD : p.xB;
+                const int n = c ? nD : nB;
+                real *S = scr + (size_t)gi * sstride + (c ? 0 : 2 * p.strideD);
+                const int sstep = c ? 2 : 1;
+                // the bulge SED carries no mass scale (applied at the end), so its line term is divided by it
+                const double inv = c ? 1.0 : (s.a_bulge > 0 ? 1.0 / s.a_bulge : 0.0);
+                for (int t = lane; t < total; t += 32) {
+                    int lo = 0, hi = nline; // last line whose task offset is <= t and that owns nodes
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (wt[2 * mid + 1] <= t) lo = mid; else hi = mid;
                     }
-                    SU[j] = v;
+                    const int l = lo, j = wt[2 * l] + (t - wt[2 * l + 1]);
+                    const double xj = __ldg(x + j);
+                    const double xm = j > 0 ? __ldg(x + j - 1) : 0.0, xp = j < n - 1 ? __ldg(x + j + 1) : 0.0;
+                    const double llow = j != 0 ? 0.5 * (xm + xj) : xj - 0.5 * (xp - xj);       // :2090
+                    const double lup = j != n - 1 ? 0.5 * (xj + xp) : xj + 0.5 * (xj - xm);   // :2091
+                    double acc = 0.0;
+                    for (int k = l; k < nline; ++k) {
+                        const int k0 = wb[2 * k], k1 = wb[2 * k + 1];
+                        if (k0 > k1) continue; // empty window
+                        if (k0 > j) break;     // windows are ordered: no later line reaches back to j
+                        if (j <= k1) {
+                            const double l0 = (double)p.line_lambda[k], lw = l0 * (s.vdisp / 2.998e5);
+                            acc += line_bin_t<real>(llow, lup, l0, lw, (double)ll[p.line_col[k]] * l0, p.line_average);
+                        }
+                    }
+                    S[(size_t)j * sstep] += (real)(xj * acc * inv);
                 }
             }
             __syncthreads();
         }
+
+        // ---- phase A4: the bulge SED resampled on the disk grid (the same piece-wise linear function; lets
+        //      phase B serve both components from one set of weights)
+        if (p.has_bulge) {
+            const real *ofrac = reinterpret_cast<const real *>(p.u_ofrac);
+            const int ncD = (nD + 127) >> 7;
+            for (int task = warp; task < ng * ncD; task += NW) {
+                const int gi = task / ncD, j0 = ((task - gi * ncD) << 7) + 4 * lane;
+                if (j0 >= nD) continue;
+                real *DU = scr + (size_t)gi * sstride;
+                const real *SB = DU + 2 * p.strideD;
+                const int4 o4 = __ldg(reinterpret_cast<const int4 *>(p.u_oleft + j0));
+                const uint32_t io = __ldg(reinterpret_cast<const uint32_t *>(p.u_isopt + j0));
+                const Quad<real> fr = ldg4(ofrac + j0);
+                const int oo[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    real v = real(0);
+                    if (oo[k] >= 0) {
+                        v = SB[oo[k]];
+                        if (!((io >> (8 * k)) & 0xffu)) v = fma(fr.v[k], SB[oo[k] + 1] - v, v);
+                    }
+                    if (j0 + k < nD) DU[2 * (j0 + k) + 1] = v;
+                }
+            }
+        }
+        __syncthreads();
 
         // ---- phase B: band groups
         for (int grp = 0; grp < (int)p.ngroups || (grp == 0 && nrf > 0); ++grp) {
@@ -441,57 +545,61 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                     // (band, galaxy slot), both components: bands are stored in decreasing order of expected work
                     const int gi = idx & (kBatch - 1), bi = idx / kBatch;
                     if (gi >= ng) continue;
+                    const int widx = ((int)p.groups[grp].base + bi) * kBatch + gi;
+                    const uint32_t wv = win[widx];
+                    if (wv == 0) continue; // not covered, empty response or empty window: flux stays 0
+                    const int jlo = (int)(wv & 0xffffu), jhi = (int)(wv >> 16), b = (int)wmid[widx];
+                    const bool bulge_on = wflag[widx] != 0;
                     const BandHeader &h = hdr[bi];
                     const GalScal &s = sc[gi];
-                    const uint32_t wv = win[((int)p.groups[grp].base + bi) * kBatch + gi];
-                    if (wv == 0) continue; // not covered, empty response or empty window: flux stays 0
-                    const int jlo = (int)(wv & 0xffffu), jhi = (int)(wv >> 16);
-                    const int widx = ((int)p.groups[grp].base + bi) * kBatch + gi;
-                    const bool bulge_on = wflag[widx] != 0;
                     BandView<real> bv;
                     make_band_view<real>(blob, h, bv);
-                    const real *SD = scr + (size_t)gi * sstride;
-                    const real *SU = SD + p.strideD + p.strideB;
-                    const double2 *gx = p.gridD;
-                    const real *dxo = reinterpret_cast<const real *>(p.dxo);
+                    const real2 *DU = reinterpret_cast<const real2 *>(scr + (size_t)gi * sstride);
                     const double opz = s.opz;
                     const real opzr = (real)opz;
-                    double accd = 0.0, accb = 0.0; // sum Lambda_j k_j
-                    real cd = real(0), cb = real(0); // sum rho_j gamma_j
-                    for (int j0 = jlo + 1; j0 < jhi; j0 += 32) {
-                        const bool live = j0 + lane < jhi;
-                        const int j = live ? j0 + lane : jhi - 1;
-                        const double2 gn = __ldg(gx + j);
-                        const double idxm = __ldg(&gx[j - 1].y);
-                        const real Sm = SD[j - 1], S0 = SD[j], Sp = SD[j + 1];
-                        const double t = fma(opz, gn.x, -bv.fc);
-                        const int c = find_cell_warp(bv.cells, bv.bkt, bv.nbkt, bv.f_first, bv.bkt_inv_w, t);
-                        const typename CellOf<real>::type e = bv.cells[c];
-                        double u;
-                        const double lam = live ? lambda_in_cell(e, t, u) : (u = 0.0, 0.0);
-                        const double r0 = slope(S0, Sp, gn.y), rm = slope(Sm, S0, idxm);
-                        accd = fma(lam, r0 - rm, accd);
-                        const real ur = (real)u, sr = (real)e.s, dlr = (real)e.dl;
-                        cd = fma((real)r0, gamma_term<real>(sr, dlr, ur, node_dt(gx, j, gn, opzr)), cd);
+                    // the SED interval [b, b+1] holds the band's split node (phot_core.cuh, two-sided gauge)
+                    const double tot0z = bv.tot0 * opz;
+                    const double asym_b1 = fma(bv.tot0, fma(opz, __ldg(&grid[b + 1].x), -bv.fc), bv.asym0);
+                    real accd = real(0), accb = real(0);
+                    // lane l of a pass sits on node jb + l; lanes 1..30 own their node, lanes 0 and 31 only supply
+                    // their neighbours' Lambda / E
+                    for (int jb = jlo - 1; jb < jhi; jb += 30) {
+                        const int j = jb + lane;
+                        const int jc = min(max(j, jlo), jhi);
+                        const GridRec g = ldg_grid(grid + jc);
+                        const real2 su = DU[jc];
+                        const double t = fma(opz, g.x, -bv.fc);
+                        const int c = find_cell_warp<real>(bv, t);
+                        const Cell e = bv.cells[c];
+                        const bool inner = j > jlo && j < jhi;
+                        const double u = t - e.f;
+                        const double lam = inner ? fma(u, fma(u, e.hr, e.k0), e.lam) : 0.0; // 0 at both ends of the window
+                        const real ur = inner ? (real)u : real(0);
+                        const real sr = (real)e.s, dlr = (real)e.dl, gidx = grid_idx(g);
+                        double dlam = __shfl_down_sync(kFull, lam, 1) - lam;
+                        if (j == b) dlam += asym_b1;
+                        const double E = (j >= jlo && j < jhi) ? dlam * g.idx : 0.0;
+                        double Ep = __shfl_up_sync(kFull, E, 1);
+                        if (j == b + 1) Ep -= tot0z;
+                        const real W = (real)(E - Ep);
+                        const bool own = lane >= 1 && lane <= 30 && j <= jhi;
+                        const real gD = gamma_term<real>(sr, dlr, ur, (real)g.dx * opzr) * gidx;
+                        const real gDp = __shfl_up_sync(kFull, gD, 1);
+                        accd = fma(su.x, own ? fma(real(0.5), gD - gDp, W) : real(0), accd);
                         if (bulge_on) {
-                            const real Bm = SU[j - 1], B0 = SU[j], Bp = SU[j + 1];
-                            const double b0 = slope(B0, Bp, gn.y), bm = slope(Bm, B0, idxm);
-                            accb = fma(lam, b0 - bm, accb);
-                            cb = fma((real)b0, gamma_term<real>(sr, dlr, ur, __ldg(dxo + j) * opzr), cb);
+                            const real gB = gamma_term<real>(sr, dlr, ur, (real)g.dxo * opzr) * gidx;
+                            const real gBp = __shfl_up_sync(kFull, gB, 1);
+                            accb = fma(su.y, own ? fma(real(0.5), gB - gBp, W) : real(0), accb);
                         }
                     }
-                    const double totd = warp_total(fma(-0.5, (double)cd, accd));
-                    const double totb = bulge_on ? warp_total(fma(-0.5, (double)cb, accb)) : 0.0;
+                    const double totd = warp_total((double)accd);
+                    const double totb = bulge_on ? warp_total((double)accb) : 0.0;
                     if (lane == 0) {
-                        // end terms at the SED interval [b, b+1] that holds the band's split node
-                        const int b = (int)wmid[widx];
-                        const double2 gb = __ldg(gx + b);
-                        const double tb1 = fma(opz, __ldg(&gx[b + 1].x), -bv.fc);
-                        double f = band_total(bv, s.iopz, totd, 0.0, (double)SD[b + 1], slope(SD[b], SD[b + 1], gb.y), tb1) * s.aflux;
+                        double f = totd * s.iopz * s.aflux;
                         if (!isfinite(f)) f = 0.0; // src/egg-gencat.cpp:2198
                         res[(gi * nbt + (int)h.out_col) * 2 + 1] = f;
                         if (bulge_on) {
-                            double fb = band_total(bv, s.iopz, totb, 0.0, (double)SU[b + 1], slope(SU[b], SU[b + 1], gb.y), tb1) * s.aflux * s.a_bulge;
+                            double fb = totb * s.iopz * s.aflux * s.a_bulge;
                             if (!isfinite(fb)) fb = 0.0;
                             res[(gi * nbt + (int)h.out_col) * 2] = fb;
                         }
@@ -503,11 +611,12 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                     if (gi >= ng) continue;
                     const int comp = p.has_bulge ? (t2 & 1) : 1, rb = p.has_bulge ? (t2 >> 1) : t2;
                     const RfDesc dsc = comp ? p.rfD[rb] : p.rfB[rb];
-                    const real *S = scr + (size_t)gi * sstride + (comp ? 0 : p.strideD);
+                    const real *S = scr + (size_t)gi * sstride + (comp ? 0 : 2 * p.strideD);
+                    const int sstep = comp ? 2 : 1;
                     const real *W = reinterpret_cast<const real *>(p.rfW) + dsc.off;
                     CompSum<real> acc;
                     acc.clear();
-                    for (int k = lane; k < dsc.n; k += 32) acc.add(S[dsc.j0 + k] * __ldg(W + k));
+                    for (int k = lane; k < dsc.n; k += 32) acc.add(S[(size_t)(dsc.j0 + k) * sstep] * __ldg(W + k));
                     acc = warp_reduce(acc);
                     if (lane == 0)
                         rfres[(gi * nrf + rb) * 2 + comp] = dsc.covered ? ((double)acc.s + (double)acc.c) * (comp ? 1.0 : sc[gi].a_bulge)

@@ -44,14 +44,13 @@ struct FluxParams {
     GroupDesc groups[kMaxGroups];
     int32_t do_rf;         // also compute the rest-frame magnitudes
     // per-CTA scratch for the rest-frame SEDs of a batch: [grid][kBatch][2*strideD + strideB] real (stays in L2):
-    // disk SED, bulge SED on its own grid, bulge SED resampled on the disk grid
+    // nD pairs {disk SED, bulge SED resampled on the disk grid}, then the bulge SED on its own grid
     void *scratch;
     // component grids
     int32_t nB, nD;        // nodes (0 if the component is absent)
     int32_t strideB, strideD; // row strides in elements (16-byte multiples)
     const double *xB, *xD; // rest wavelengths, double
-    const double2 *gridD;  // disk grid as {x_j, 1/(x_{j+1} - x_j)} (Grid::idx)
-    const void *dxo;       // real: rest-frame distance from an optical node to the next one, 0 elsewhere (Prepared::u_dxo)
+    const void *gridrec;   // disk grid as GridRecF / GridRecD records (phot_core.cuh), one padding record at the end
     const uint16_t *lutB, *lutD; // log2-spaced "last node <= v" lookups (Grid::lut)
     int32_t lutB_n, lutD_n, lutB_e0, lutD_e0;
     int32_t igmB[4], igmD[4]; // lz, l0, l1, l2

@@ -141,9 +141,19 @@ Status build_band_table(const Filter &f, uint32_t out_col, int bucket_factor, Ba
     }
     t.h.split = (uint32_t)split;
     t.h.f_split = t.cells[split].f;
-    // bucket table: bkt[k] = last node with f <= f_first + k*w
-    const int nbkt = std::min(std::max(bucket_factor * n, 1), 65000);
+    // bucket table: bkt[k] = last node with f <= f_first + k*w.  When buckets narrower than every cell are
+    // affordable, a bucket holds at most one node and one probe settles the lookup (bit 31 of `split`).
     const double span = t.h.f_last - t.h.f_first;
+    double min_dl = span;
+    for (int i = 0; i + 1 < n; ++i) min_dl = std::min(min_dl, t.cells[i].dl);
+    int nbkt = std::min(std::max(bucket_factor * n, 1), 65000);
+    if (min_dl > 0 && span > 0) {
+        const double need = std::ceil(span / min_dl * 1.02) + 1;
+        if (need <= 8.0 * n && need <= 65000.0) {
+            nbkt = std::max((int)need, 1);
+            t.h.split |= 0x80000000u;
+        }
+    }
     t.h.nbkt = (uint32_t)nbkt;
     t.h.bkt_inv_w = span > 0 ? (float)(nbkt / span) : 0.0f;
     if (!(t.h.bkt_inv_w * span < nbkt)) t.h.bkt_inv_w = std::nextafter(t.h.bkt_inv_w, 0.0f);

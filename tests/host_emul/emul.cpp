@@ -125,30 +125,51 @@ void run(const Prepared &P, const eggphot_galaxies &G, size_t ngal, double *fd, 
                         BandView<real> bv;
                         make_band_view<real>(blob, h, bv);
                         const real opzr = (real)opz;
-                        double accd = 0, accb = 0;
-                        real cd = 0, cb = 0;
+                        // b = last node of [jlo, jhi) left of the band's split node
+                        int b = jlo;
+                        while (b + 1 < jhi && std::fma(opz, gr.x[b + 1], -bv.fc) < bv.f_split) ++b;
+                        const double asym_b1 = std::fma(bv.tot0, std::fma(opz, gr.x[b + 1], -bv.fc), bv.asym0), tot0z = bv.tot0 * opz;
+                        // per node: Lambda (0 at both ends of the window) and the gamma terms of both components
+                        const int N = jhi - jlo + 1;
+                        std::vector<double> lam(N, 0.0);
+                        std::vector<real> gD(N, real(0)), gB(N, real(0));
                         for (int j = jlo + 1; j < jhi; ++j) {
                             const double t = std::fma(opz, gr.x[j], -bv.fc);
                             const int c = find_cell(bv.cells, bv.bkt, bv.nbkt, bv.f_first, bv.bkt_inv_w, t);
                             double u;
-                            const double lam = lambda_in_cell(bv.cells[c], t, u);
-                            const double r0 = slope(SD[j], SD[j + 1], gr.idx[j]), rm = slope(SD[j - 1], SD[j], gr.idx[j - 1]);
-                            accd = std::fma(lam, r0 - rm, accd);
+                            lam[j - jlo] = lambda_in_cell(bv.cells[c], t, u);
                             const real ur = (real)u, sr = (real)bv.cells[c].s, dlr = (real)bv.cells[c].dl;
-                            cd += (real)r0 * gamma_term<real>(sr, dlr, ur, (real)(1.0 / gr.idx[j]) * opzr);
-                            if (bulge_on) {
-                                const double b0 = slope(SBU[j], SBU[j + 1], gr.idx[j]), bm = slope(SBU[j - 1], SBU[j], gr.idx[j - 1]);
-                                accb = std::fma(lam, b0 - bm, accb);
-                                cb += (real)b0 * gamma_term<real>(sr, dlr, ur, (real)P.u_dxo[j] * opzr);
-                            }
+                            const real dxr = (real)(gr.x[j + 1] - gr.x[j]);
+                            gD[j - jlo] = gamma_term<real>(sr, dlr, ur, dxr * opzr) * (real)gr.idx[j];
+                            if (bulge_on) gB[j - jlo] = gamma_term<real>(sr, dlr, ur, (real)P.u_dxo[j] * opzr) * (real)gr.idx[j];
                         }
-                        // the SED interval that holds the split node: b = last node left of it (jlo <= b < jhi)
-                        int b = jlo;
-                        while (b + 1 < jhi && std::fma(opz, gr.x[b + 1], -bv.fc) < bv.f_split) ++b;
-                        const double tb1 = std::fma(opz, gr.x[b + 1], -bv.fc), iopz = 1.0 / opz;
-                        fdv = band_total(bv, iopz, accd, (double)cd, (double)SD[b + 1], slope(SD[b], SD[b + 1], gr.idx[b]), tb1) * aflux;
-                        if (bulge_on)
-                            fbv = band_total(bv, iopz, accb, (double)cb, (double)SBU[b + 1], slope(SBU[b], SBU[b + 1], gr.idx[b]), tb1) * aflux * a_b;
+                        // E_j for jlo <= j < jhi (0 outside); W_j = E_j - E_{j-1} (+ the float gamma terms)
+                        // the kernel keeps one partial sum per lane (node j sits on lane (j - jlo) % 30 + 1 of its pass)
+                        // in the mode's real type and adds the lanes in double
+                        real accd[32] = {0}, accb[32] = {0};
+                        double Ep = 0;
+                        real gDp = 0, gBp = 0;
+                        for (int j = jlo; j <= jhi; ++j) {
+                            const int k = j - jlo;
+                            double E = 0;
+                            if (j < jhi) {
+                                double dlam = lam[k + 1] - lam[k];
+                                if (j == b) dlam += asym_b1;
+                                E = dlam * gr.idx[j];
+                            }
+                            double Eprev = Ep;
+                            if (j == b + 1) Eprev -= tot0z;
+                            const real W = (real)(E - Eprev);
+                            const int ln = k % 30 + 1;
+                            accd[ln] = std::fma((real)SD[j], W + real(0.5) * (gD[k] - gDp), accd[ln]);
+                            if (bulge_on) accb[ln] = std::fma((real)SBU[j], W + real(0.5) * (gB[k] - gBp), accb[ln]);
+                            Ep = E; gDp = gD[k]; gBp = gB[k];
+                        }
+                        const double iopz = 1.0 / opz;
+                        double sd = 0, sb = 0;
+                        for (int l = 0; l < 32; ++l) { sd += (double)accd[l]; sb += (double)accb[l]; }
+                        fdv = sd * iopz * aflux;
+                        if (bulge_on) fbv = sb * iopz * aflux * a_b;
                     }
                 }
                 if (!std::isfinite(fdv)) fdv = 0;
