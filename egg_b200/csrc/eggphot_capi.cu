@@ -57,7 +57,7 @@ struct eggphot_ctx {
     cudaStream_t stream = nullptr;
     // prepared tables on the device
     std::vector<DevBuf> blobs;
-    DevBuf xB, xD, gridrec, lutB, lutD, rowsB, rowsDopt, rowsDir, rowsDpah, opt_use, rfB, rfD, rfW, errflag, scratch, u_oleft, u_ofrac, u_isopt;
+    DevBuf xB, xD, gridA, gridB, lutB, lutD, rowsB, rowsDopt, rowsDir, rowsDpah, opt_use, rfB, rfD, rfW, errflag, scratch, u_oleft, u_ofrac, u_isopt;
     int strideB = 0, strideD = 0;
     FluxParams base{};
     int grid_blocks = 0;
@@ -210,16 +210,19 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
         const int n = g.n();
         auto dxo = [&](int j) { return j < (int)P.u_dxo.size() ? P.u_dxo[j] : 0.0; };
         auto dx = [&](int j) { return j + 1 < n ? g.x[j + 1] - g.x[j] : 0.0; };
+        std::vector<GridA> ra((size_t)n + 1, GridA{0, 0});
+        for (int j = 0; j < n; ++j) ra[j] = GridA{g.x[j], g.idx[j]};
+        CK(c->gridA.upload(ra.data(), ra.size() * sizeof(GridA)));
         if (P.precision == EGGPHOT_FP64) {
-            std::vector<GridRecD> r((size_t)n + 1, GridRecD{0, 0, 0, 0});
-            for (int j = 0; j < n; ++j) r[j] = GridRecD{g.x[j], g.idx[j], dx(j), dxo(j)};
-            CK(c->gridrec.upload(r.data(), r.size() * sizeof(GridRecD)));
+            std::vector<GridBD> r((size_t)n + 1, GridBD{0, 0});
+            for (int j = 0; j < n; ++j) r[j] = GridBD{dx(j), dxo(j)};
+            CK(c->gridB.upload(r.data(), r.size() * sizeof(GridBD)));
         } else {
-            std::vector<GridRecF> r((size_t)n + 1, GridRecF{0, 0, 0, 0, 0, 0});
-            for (int j = 0; j < n; ++j) r[j] = GridRecF{g.x[j], g.idx[j], (float)dx(j), (float)dxo(j), (float)g.idx[j], 0.0f};
-            CK(c->gridrec.upload(r.data(), r.size() * sizeof(GridRecF)));
+            std::vector<GridBF> r((size_t)n + 1, GridBF{0, 0, 0, 0});
+            for (int j = 0; j < n; ++j) r[j] = GridBF{(float)dx(j), (float)dxo(j), (float)g.idx[j], 0.0f};
+            CK(c->gridB.upload(r.data(), r.size() * sizeof(GridBF)));
         }
-        tb += c->gridrec.bytes;
+        tb += c->gridA.bytes + c->gridB.bytes;
     }
     CK(upload_rows(c->rowsB, P.rows_bulge_opt, P.nopt_sed, P.grid_bulge.n(), c->strideB, P.precision, tb));
     CK(upload_rows(c->rowsDopt, P.rows_disk_opt, P.nopt_sed, P.grid_disk.n(), c->strideD, P.precision, tb));
@@ -278,7 +281,7 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
     p.nB = P.grid_bulge.n(); p.nD = P.grid_disk.n();
     p.strideB = c->strideB; p.strideD = c->strideD;
     p.xB = (const double *)c->xB.p; p.xD = (const double *)c->xD.p;
-    p.gridrec = c->gridrec.p;
+    p.gridA = c->gridA.p; p.gridB = c->gridB.p;
     p.lutB = (const uint16_t *)c->lutB.p; p.lutD = (const uint16_t *)c->lutD.p;
     p.lutB_n = (int)P.grid_bulge.lut.size(); p.lutD_n = (int)P.grid_disk.lut.size();
     p.lutB_e0 = P.grid_bulge.lut_e0; p.lutD_e0 = P.grid_disk.lut_e0;

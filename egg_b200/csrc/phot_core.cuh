@@ -60,25 +60,16 @@
 
 namespace eggphot {
 
-// One filter cell [f_c, f_{c+1}) of a band table; record n-1 is the open cell right of the last
-// node (K0 = tot0, R = 0) and record n is a sentinel with f = +inf.
-struct __attribute__((aligned(16))) FilterCellF {
-    double f;    // centred position of node c:  lambda_c - fc
-    double lam;  // Lambda at the node
-    double k0;   // K0 at the node (cumulative trapezoid of R)
-    double hr;   // R_c / 2
-    float s;     // slope of R in the cell (0 in zero-width cells and in the open cell)
-    float dl;    // cell width (huge in the open cell)
-    float pad[2];
-};
-struct __attribute__((aligned(16))) FilterCellD {
-    double f, lam, k0, hr, s, dl;
-};
-static_assert(sizeof(FilterCellF) == 48 && sizeof(FilterCellD) == 48, "filter cell layout");
-
-template <typename real> struct CellOf;
-template <> struct CellOf<float> { typedef FilterCellF type; };
-template <> struct CellOf<double> { typedef FilterCellD type; };
+// Band tables are structure-of-arrays in shared memory (a warp's lanes sit on neighbouring filter cells:
+// 8-byte strides spread them over the banks).  Per band, n = nodes of the effective span:
+//   f[n+1]   double  centred node positions lambda_c - fc; f[n] = +inf (sentinel of the cell scan)
+//   lam[n]   double  Lambda at the node, k0[n] double K0 at the node (two-sided gauge, see above);
+//                    entry n-1 is the open cell right of the last node (lam = k0 = 0 in its gauge)
+//   hr[n]    real    R_c / 2 (0 in the open cell)
+//   sdl[n]   real x2 slope of R in the cell (0 in zero-width cells and in the open cell), cell width (huge in the
+//                    open cell)
+//   bkt[nbkt] uint16 last node at or below the start of each bucket
+template <typename real> struct alignas(2 * sizeof(real)) Pair2 { real x, y; };
 
 // Header of one band inside a group blob (device layout; offsets are bytes from the blob start).
 struct __attribute__((aligned(16))) BandHeader {
@@ -94,32 +85,31 @@ struct __attribute__((aligned(16))) BandHeader {
     float l2first, l2last;        // log2(eff_first), log2(eff_last) in lookup buckets (x kLutPerOctave)
     uint32_t n;                   // nodes in the effective span (>= 2), or 0 if the response is identically 0
     uint32_t nbkt;                // buckets
-    uint32_t cell_off;            // byte offset of the FilterCell array (n + 1 records)
-    uint32_t bkt_off;             // byte offset of the uint16 bucket array (nbkt entries)
+    uint32_t f_off, lam_off, k0_off, hr_off, sdl_off, bkt_off; // byte offsets of the arrays
     uint32_t out_col;             // column in the sorted band list
     uint32_t split;               // index of the split node; bit 31: one probe settles the cell lookup (buckets are
                                   // narrower than every cell)
 };
-static_assert(sizeof(BandHeader) == 128, "BandHeader layout");
+static_assert(sizeof(BandHeader) == 144, "BandHeader layout");
 
-// One node of a rest-frame SED grid as phase B reads it (32 bytes, two 128-bit loads).
-struct __attribute__((aligned(16))) GridRecF {
-    double x, idx;        // wavelength, 1/(x[j+1] - x[j]) (0 for the last node)
-    float dx, dxo, idxf;  // x[j+1] - x[j]; distance to the next OPTICAL node if j is one, else 0 (the bulge's
-    float pad;            // union cells start at optical nodes only); idx as float
-};
-struct __attribute__((aligned(16))) GridRecD {
-    double x, idx, dx, dxo;
-};
-template <typename real> struct GridRecOf;
-template <> struct GridRecOf<float> { typedef GridRecF type; };
-template <> struct GridRecOf<double> { typedef GridRecD type; };
-EGG_HD float grid_idx(const GridRecF &g) { return g.idxf; }
-EGG_HD double grid_idx(const GridRecD &g) { return g.idx; }
+// One node of the rest-frame disk grid as phase B reads it: two arrays of 16-byte records, so that a
+// warp's loads are contiguous.  GridA {x, idx}: wavelength and 1/(x[j+1] - x[j]) (0 for the last node).
+// GridB: x[j+1] - x[j]; the distance to the next OPTICAL node if j is one, else 0 (the bulge's union cells
+// start at optical nodes only); fp32 additionally idx as float.
+struct __attribute__((aligned(16))) GridA { double x, idx; };
+struct __attribute__((aligned(16))) GridBF { float dx, dxo, idxf, pad; };
+struct __attribute__((aligned(16))) GridBD { double dx, dxo; };
+template <typename real> struct GridBOf;
+template <> struct GridBOf<float> { typedef GridBF type; };
+template <> struct GridBOf<double> { typedef GridBD type; };
+EGG_HD float grid_idx(const GridA &, const GridBF &b) { return b.idxf; }
+EGG_HD double grid_idx(const GridA &a, const GridBD &) { return a.idx; }
 
 // Band seen through the kernel's real type.
 template <typename real> struct BandView {
-    const typename CellOf<real>::type *cells;
+    const double *f, *lam, *k0;
+    const real *hr;
+    const Pair2<real> *sdl;
     const uint16_t *bkt;
     double fc, f_first, f_split, tot0, asym0;
     float bkt_inv_w;
@@ -127,7 +117,11 @@ template <typename real> struct BandView {
     bool one_probe;
 };
 template <typename real> EGG_HD void make_band_view(const uint8_t *blob, const BandHeader &h, BandView<real> &v) {
-    v.cells = reinterpret_cast<const typename CellOf<real>::type *>(blob + h.cell_off);
+    v.f = reinterpret_cast<const double *>(blob + h.f_off);
+    v.lam = reinterpret_cast<const double *>(blob + h.lam_off);
+    v.k0 = reinterpret_cast<const double *>(blob + h.k0_off);
+    v.hr = reinterpret_cast<const real *>(blob + h.hr_off);
+    v.sdl = reinterpret_cast<const Pair2<real> *>(blob + h.sdl_off);
     v.bkt = reinterpret_cast<const uint16_t *>(blob + h.bkt_off);
     v.fc = h.fc; v.f_first = h.f_first; v.f_split = h.f_split; v.tot0 = h.tot0; v.asym0 = h.asym0;
     v.bkt_inv_w = h.bkt_inv_w;
@@ -136,23 +130,23 @@ template <typename real> EGG_HD void make_band_view(const uint8_t *blob, const B
 }
 
 // Filter cell of the centred position t, f_first <= t: the largest c with f_c <= t.  bkt[k] is the
-// last node at or below the start of bucket k and the bucket index never overshoots (bkt_inv_w is
-// rounded down by more than the float rounding of the product), so a forward scan settles it; the
-// sentinel record (f = +inf) ends the scan in the open cell.
-template <typename Cell>
-EGG_HD int find_cell(const Cell *cells, const uint16_t *bkt, int nbkt, double f_first, float inv_w, double t) {
-    int k = (int)((float)(t - f_first) * inv_w);
-    k = k < 0 ? 0 : (k > nbkt - 1 ? nbkt - 1 : k);
-    int c = bkt[k];
-    while (t >= cells[c + 1].f) ++c;
+// last node at or below the start of bucket k and the bucket index never overshoots (the table is built
+// against slightly lowered bucket edges), so a forward scan settles it; the sentinel f[n] = +inf ends
+// the scan in the open cell.
+template <typename real> EGG_HD int find_cell(const BandView<real> &b, double t) {
+    int k = (int)((float)(t - b.f_first) * b.bkt_inv_w);
+    k = k < 0 ? 0 : (k > b.nbkt - 1 ? b.nbkt - 1 : k);
+    int c = b.bkt[k];
+    while (t >= b.f[c + 1]) ++c;
     return c;
 }
 
-// Lambda(t) in a cell and the offset u of t inside it.
-template <typename Cell> EGG_HD double lambda_in_cell(const Cell &e, double t, double &u) {
-    u = t - e.f;
-    return fma(u, fma(u, e.hr, e.k0), e.lam);
+// Lambda(t) in cell c and the offset u of t inside it.
+template <typename real> EGG_HD double lambda_in_cell(const BandView<real> &b, int c, double t, double &u) {
+    u = t - b.f[c];
+    return fma(u, fma(u, (double)b.hr[c], b.k0[c]), b.lam[c]);
 }
+
 // gamma = s b u (b - u), b = min(dt + u, dl): the trapezoid-error term of the union cell that starts at
 // an SED node at offset u inside a filter cell of slope s and width dl, the next node of the same SED
 // being dt further (0 for a node that does not start an interval of this SED: gamma = 0).

@@ -181,11 +181,11 @@ __device__ __forceinline__ int find_cell_warp(const BandView<real> &b, double t)
     int k = (int)((float)(t - b.f_first) * b.bkt_inv_w);
     k = max(0, min(k, b.nbkt - 1));
     int c = b.bkt[k];
-    bool up = t >= b.cells[c + 1].f;
+    bool up = t >= b.f[c + 1];
     if (b.one_probe) return c + (up ? 1 : 0);
     while (__any_sync(kFull, up)) {
         c += up ? 1 : 0;
-        up = t >= b.cells[c + 1].f;
+        up = t >= b.f[c + 1];
     }
     return c;
 }
@@ -205,20 +205,22 @@ __device__ __forceinline__ void st4(double *p, const Quad<double> &q) {
     reinterpret_cast<double2 *>(p)[0] = make_double2(q.v[0], q.v[1]);
     reinterpret_cast<double2 *>(p)[1] = make_double2(q.v[2], q.v[3]);
 }
+__device__ __forceinline__ float2 make_pair2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ double2 make_pair2(double a, double b) { return make_double2(a, b); }
 template <typename real> struct Pair;
 template <> struct Pair<float> { typedef float2 type; };
 template <> struct Pair<double> { typedef double2 type; };
-__device__ __forceinline__ GridRecF ldg_grid(const GridRecF *g) {
-    const float4 a = __ldg(reinterpret_cast<const float4 *>(g)), b = __ldg(reinterpret_cast<const float4 *>(g) + 1);
-    GridRecF r;
-    r.x = __hiloint2double(__float_as_int(a.y), __float_as_int(a.x));
-    r.idx = __hiloint2double(__float_as_int(a.w), __float_as_int(a.z));
-    r.dx = b.x; r.dxo = b.y; r.idxf = b.z; r.pad = 0.0f;
-    return r;
+__device__ __forceinline__ GridA ldg_grid(const GridA *g) {
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(g));
+    return GridA{a.x, a.y};
 }
-__device__ __forceinline__ GridRecD ldg_grid(const GridRecD *g) {
-    const double2 a = __ldg(reinterpret_cast<const double2 *>(g)), b = __ldg(reinterpret_cast<const double2 *>(g) + 1);
-    return GridRecD{a.x, a.y, b.x, b.y};
+__device__ __forceinline__ GridBF ldg_grid(const GridBF *g) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(g));
+    return GridBF{a.x, a.y, a.z, a.w};
+}
+__device__ __forceinline__ GridBD ldg_grid(const GridBD *g) {
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(g));
+    return GridBD{a.x, a.y};
 }
 
 struct SmemLayout {
@@ -250,8 +252,7 @@ __host__ __device__ inline SmemLayout smem_layout(const FluxParams &p) {
 template <typename real, int NT>
 __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ FluxParams p) {
     typedef typename Pair<real>::type real2;
-    typedef typename GridRecOf<real>::type GridRec;
-    typedef typename CellOf<real>::type Cell;
+    typedef typename GridBOf<real>::type GridB;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ GalScal sc[kBatch];
     __shared__ __align__(8) uint64_t bar_tab;
@@ -277,7 +278,8 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
     real *scr = reinterpret_cast<real *>(p.scratch) + (size_t)blockIdx.x * kBatch * sstride;
     const real *rO = reinterpret_cast<const real *>(p.rowsDopt), *rI = reinterpret_cast<const real *>(p.rowsDir);
     const real *rP = reinterpret_cast<const real *>(p.rowsDpah), *rB = reinterpret_cast<const real *>(p.rowsB);
-    const GridRec *grid = reinterpret_cast<const GridRec *>(p.gridrec);
+    const GridA *gridA = reinterpret_cast<const GridA *>(p.gridA);
+    const GridB *gridB = reinterpret_cast<const GridB *>(p.gridB);
 
     if (tid == 0) {
         mbar_init(&bar_tab, 1);
@@ -298,59 +300,23 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
         for (int i = tid; i < ng * nbt * 2; i += NT) res[i] = 0.0;
         __syncthreads();
 
-        // ---- phase A2: rest-frame SEDs (get_opt_sed / get_ir_sed / merge_add / IGM).  A warp takes 128
-        //      consecutive nodes of one galaxy at a time, four per lane with 128-bit row loads.
-        {
-            const int ncD = (nD + 127) >> 7, ncB = p.has_bulge ? (nB + 127) >> 7 : 0, nc = ncD + ncB;
-            for (int task = warp; task < ng * nc; task += NW) {
-                const int gi = task / nc, ch = task - gi * nc;
+        // ---- phase A2a: bulge SEDs on their own grid (get_opt_sed + IGM, src/egg-gencat.cpp:708-712, 2122-2140).
+        //      A warp takes 128 consecutive nodes of one galaxy at a time, four per lane.
+        if (p.has_bulge) {
+            const int ncB = (nB + 127) >> 7;
+            for (int task = warp; task < ng * ncB; task += NW) {
+                const int gi = task / ncB, j0 = ((task - gi * ncB) << 7) + 4 * lane;
+                if (j0 >= nB) continue;
                 const GalScal &s = sc[gi];
-                real *DU = scr + (size_t)gi * sstride, *SB = DU + 2 * p.strideD;
-                const real g0f = s.igm[0], g1f = s.igm[1], g2f = s.igm[2];
-                if (ch < ncD) {
-                    const int j0 = (ch << 7) + 4 * lane;
-                    if (j0 < nD) {
-                        const real a_d = (real)s.a_disk, c1 = (real)s.c1, c2 = (real)s.c2;
-                        Quad<real> v;
-                        if (p.disk_mode == 0) {
-                            const Quad<real> o = ldg4(rO + (size_t)s.row_d * p.strideD + j0), i = ldg4(rI + (size_t)s.row_i * p.strideD + j0);
+                real *SB = scr + (size_t)gi * sstride + 2 * p.strideD;
+                Quad<real> v = ldg4(rB + (size_t)s.row_b * p.strideB + j0);
+                if (p.apply_igm && j0 < p.igmB[3]) {
+                    const real g0f = s.igm[0], g1f = s.igm[1], g2f = s.igm[2];
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) v.v[k] = a_d * o.v[k] + c1 * i.v[k];
-                        } else if (p.disk_mode == 1) {
-                            const Quad<real> o = ldg4(rO + (size_t)s.row_d * p.strideD + j0);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) v.v[k] = a_d * o.v[k];
-                        } else {
-                            const Quad<real> i = ldg4(rI + (size_t)s.row_i * p.strideD + j0);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) v.v[k] = c1 * i.v[k];
-                        }
-                        if (p.disk_mode != 1 && cs17) {
-                            const Quad<real> q = ldg4(rP + (size_t)s.row_i * p.strideD + j0);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) v.v[k] += c2 * q.v[k];
-                        }
-                        if (p.apply_igm && j0 < p.igmD[3]) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                v.v[k] *= igm_factor<real>(j0 + k, p.igmD[0], p.igmD[1], p.igmD[2], p.igmD[3], g0f, g1f, g2f);
-                        }
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (j0 + k < nD) DU[2 * (j0 + k)] = v.v[k];
-                    }
-                } else {
-                    const int j0 = ((ch - ncD) << 7) + 4 * lane;
-                    if (j0 < nB) {
-                        Quad<real> v = ldg4(rB + (size_t)s.row_b * p.strideB + j0);
-                        if (p.apply_igm && j0 < p.igmB[3]) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                v.v[k] *= igm_factor<real>(j0 + k, p.igmB[0], p.igmB[1], p.igmB[2], p.igmB[3], g0f, g1f, g2f);
-                        }
-                        st4(SB + j0, v); // rows are zero-padded to the stride: the tail stores zeros
-                    }
+                    for (int k = 0; k < 4; ++k)
+                        v.v[k] *= igm_factor<real>(j0 + k, p.igmB[0], p.igmB[1], p.igmB[2], p.igmB[3], g0f, g1f, g2f);
                 }
+                st4(SB + j0, v); // rows are zero-padded to the stride: the tail stores zeros
             }
         }
         // node windows of every (band, galaxy): one thread each
@@ -423,11 +389,10 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
         //      The first line whose window holds node j owns it and adds the contributions of all lines at j,
         //      in that order: no two lanes touch the same node and the sum order is fixed.  The owned nodes of
         //      all lines are numbered consecutively (prefix sum) and dealt to the lanes.
-        if (nline > 0) {
-            for (int task = warp; task < ng * 2; task += NW) {
-                const int gi = task >> 1, c = task & 1;
-                const float *llp = c ? p.line_lum_disk : p.line_lum_bulge;
-                if ((!c && !p.has_bulge) || llp == nullptr) continue;
+        auto deposit_lines = [&](const int c) { // c: 0 bulge (before it is resampled on the disk grid), 1 disk
+            const float *llp = c ? p.line_lum_disk : p.line_lum_bulge;
+            for (int gi = warp; gi < ng; gi += NW) {
+                const int task = 2 * gi + c;
                 const int *wb = lb + 2 * task * nline;
                 int *wt = lt + 2 * task * nline;
                 int carry_b1 = -1, total = 0;
@@ -489,35 +454,75 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                     S[(size_t)j * sstep] += (real)(xj * acc * inv);
                 }
             }
+        };
+        if (nline > 0 && p.has_bulge && p.line_lum_bulge != nullptr) {
+            deposit_lines(0);
             __syncthreads();
         }
 
-        // ---- phase A4: the bulge SED resampled on the disk grid (the same piece-wise linear function; lets
-        //      phase B serve both components from one set of weights)
-        if (p.has_bulge) {
+        // ---- phase A2b: disk SEDs (get_opt_sed / get_ir_sed / merge_add / IGM, src/egg-gencat.cpp:2104-2140) and the
+        //      bulge SED resampled on the disk grid (the same piece-wise linear function; lets phase B serve both
+        //      components from one set of weights), two nodes per lane, stored as {disk, bulge} pairs
+        {
             const real *ofrac = reinterpret_cast<const real *>(p.u_ofrac);
-            const int ncD = (nD + 127) >> 7;
+            const int ncD = (nD + 63) >> 6;
             for (int task = warp; task < ng * ncD; task += NW) {
-                const int gi = task / ncD, j0 = ((task - gi * ncD) << 7) + 4 * lane;
+                const int gi = task / ncD, j0 = ((task - gi * ncD) << 6) + 2 * lane;
                 if (j0 >= nD) continue;
+                const GalScal &s = sc[gi];
                 real *DU = scr + (size_t)gi * sstride;
-                const real *SB = DU + 2 * p.strideD;
-                const int4 o4 = __ldg(reinterpret_cast<const int4 *>(p.u_oleft + j0));
-                const uint32_t io = __ldg(reinterpret_cast<const uint32_t *>(p.u_isopt + j0));
-                const Quad<real> fr = ldg4(ofrac + j0);
-                const int oo[4] = {o4.x, o4.y, o4.z, o4.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    real v = real(0);
-                    if (oo[k] >= 0) {
-                        v = SB[oo[k]];
-                        if (!((io >> (8 * k)) & 0xffu)) v = fma(fr.v[k], SB[oo[k] + 1] - v, v);
-                    }
-                    if (j0 + k < nD) DU[2 * (j0 + k) + 1] = v;
+                real2 v;
+                if (p.disk_mode == 0) {
+                    const real2 o = __ldg(reinterpret_cast<const real2 *>(rO + (size_t)s.row_d * p.strideD + j0));
+                    const real2 i = __ldg(reinterpret_cast<const real2 *>(rI + (size_t)s.row_i * p.strideD + j0));
+                    const real a_d = (real)s.a_disk, c1 = (real)s.c1;
+                    v.x = a_d * o.x + c1 * i.x; v.y = a_d * o.y + c1 * i.y;
+                } else if (p.disk_mode == 1) {
+                    const real2 o = __ldg(reinterpret_cast<const real2 *>(rO + (size_t)s.row_d * p.strideD + j0));
+                    const real a_d = (real)s.a_disk;
+                    v.x = a_d * o.x; v.y = a_d * o.y;
+                } else {
+                    const real2 i = __ldg(reinterpret_cast<const real2 *>(rI + (size_t)s.row_i * p.strideD + j0));
+                    const real c1 = (real)s.c1;
+                    v.x = c1 * i.x; v.y = c1 * i.y;
                 }
+                if (p.disk_mode != 1 && cs17) {
+                    const real2 q = __ldg(reinterpret_cast<const real2 *>(rP + (size_t)s.row_i * p.strideD + j0));
+                    const real c2 = (real)s.c2;
+                    v.x += c2 * q.x; v.y += c2 * q.y;
+                }
+                if (p.apply_igm && j0 < p.igmD[3]) {
+                    const real g0f = s.igm[0], g1f = s.igm[1], g2f = s.igm[2];
+                    v.x *= igm_factor<real>(j0, p.igmD[0], p.igmD[1], p.igmD[2], p.igmD[3], g0f, g1f, g2f);
+                    v.y *= igm_factor<real>(j0 + 1, p.igmD[0], p.igmD[1], p.igmD[2], p.igmD[3], g0f, g1f, g2f);
+                }
+                real2 w;
+                w.x = real(0); w.y = real(0);
+                if (p.has_bulge) {
+                    const real *SB = DU + 2 * p.strideD;
+                    const int2 o2 = __ldg(reinterpret_cast<const int2 *>(p.u_oleft + j0));
+                    const uint32_t io = __ldg(reinterpret_cast<const uint16_t *>(p.u_isopt + j0));
+                    const real2 fr = __ldg(reinterpret_cast<const real2 *>(ofrac + j0));
+                    if (o2.x >= 0) {
+                        w.x = SB[o2.x];
+                        if (!(io & 0xffu)) w.x = fma(fr.x, SB[o2.x + 1] - w.x, w.x);
+                    }
+                    if (o2.y >= 0) {
+                        w.y = SB[o2.y];
+                        if (!(io >> 8)) w.y = fma(fr.y, SB[o2.y + 1] - w.y, w.y);
+                    }
+                }
+                // the row stride is a multiple of four: node j0 + 1 <= stride - 1 always has room
+                real2 *dst = reinterpret_cast<real2 *>(DU) + j0;
+                dst[0] = make_pair2(v.x, w.x);
+                dst[1] = make_pair2(v.y, w.y);
             }
         }
         __syncthreads();
+        if (nline > 0 && p.line_lum_disk != nullptr) {
+            deposit_lines(1);
+            __syncthreads();
+        }
 
         // ---- phase B: band groups
         for (int grp = 0; grp < (int)p.ngroups || (grp == 0 && nrf > 0); ++grp) {
@@ -559,23 +564,24 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                     const real opzr = (real)opz;
                     // the SED interval [b, b+1] holds the band's split node (phot_core.cuh, two-sided gauge)
                     const double tot0z = bv.tot0 * opz;
-                    const double asym_b1 = fma(bv.tot0, fma(opz, __ldg(&grid[b + 1].x), -bv.fc), bv.asym0);
+                    const double asym_b1 = fma(bv.tot0, fma(opz, __ldg(&gridA[b + 1].x), -bv.fc), bv.asym0);
                     real accd = real(0), accb = real(0);
                     // lane l of a pass sits on node jb + l; lanes 1..30 own their node, lanes 0 and 31 only supply
                     // their neighbours' Lambda / E
                     for (int jb = jlo - 1; jb < jhi; jb += 30) {
                         const int j = jb + lane;
                         const int jc = min(max(j, jlo), jhi);
-                        const GridRec g = ldg_grid(grid + jc);
+                        const GridA g = ldg_grid(gridA + jc);
+                        const GridB gb = ldg_grid(gridB + jc);
                         const real2 su = DU[jc];
                         const double t = fma(opz, g.x, -bv.fc);
                         const int c = find_cell_warp<real>(bv, t);
-                        const Cell e = bv.cells[c];
                         const bool inner = j > jlo && j < jhi;
-                        const double u = t - e.f;
-                        const double lam = inner ? fma(u, fma(u, e.hr, e.k0), e.lam) : 0.0; // 0 at both ends of the window
+                        const double u = t - bv.f[c];
+                        const double lam = inner ? fma(u, fma(u, (double)bv.hr[c], bv.k0[c]), bv.lam[c]) : 0.0; // 0 at both window ends
                         const real ur = inner ? (real)u : real(0);
-                        const real sr = (real)e.s, dlr = (real)e.dl, gidx = grid_idx(g);
+                        const Pair2<real> sd = bv.sdl[c];
+                        const real sr = sd.x, dlr = sd.y, gidx = grid_idx(g, gb);
                         double dlam = __shfl_down_sync(kFull, lam, 1) - lam;
                         if (j == b) dlam += asym_b1;
                         const double E = (j >= jlo && j < jhi) ? dlam * g.idx : 0.0;
@@ -583,11 +589,11 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                         if (j == b + 1) Ep -= tot0z;
                         const real W = (real)(E - Ep);
                         const bool own = lane >= 1 && lane <= 30 && j <= jhi;
-                        const real gD = gamma_term<real>(sr, dlr, ur, (real)g.dx * opzr) * gidx;
+                        const real gD = gamma_term<real>(sr, dlr, ur, (real)gb.dx * opzr) * gidx;
                         const real gDp = __shfl_up_sync(kFull, gD, 1);
                         accd = fma(su.x, own ? fma(real(0.5), gD - gDp, W) : real(0), accd);
                         if (bulge_on) {
-                            const real gB = gamma_term<real>(sr, dlr, ur, (real)g.dxo * opzr) * gidx;
+                            const real gB = gamma_term<real>(sr, dlr, ur, (real)gb.dxo * opzr) * gidx;
                             const real gBp = __shfl_up_sync(kFull, gB, 1);
                             accb = fma(su.y, own ? fma(real(0.5), gB - gBp, W) : real(0), accb);
                         }

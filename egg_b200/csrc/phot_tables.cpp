@@ -55,6 +55,9 @@ double box_integral(const std::vector<double> &x, const std::vector<double> &y, 
 void align16(std::vector<uint8_t> &b) { b.resize((b.size() + 15) & ~size_t(15), 0); }
 
 // Double-precision band table, the source of both device layouts.
+struct FilterCellD {
+    double f, lam, k0, hr, s, dl;
+};
 struct BandTableD {
     BandHeader h{};
     std::vector<FilterCellD> cells; // n + 1 records: cells 0..n-2, the open cell n-1, the sentinel n
@@ -172,32 +175,42 @@ Status build_band_table(const Filter &f, uint32_t out_col, int bucket_factor, Ba
     return Status();
 }
 
-size_t band_bytes(const BandTableD &t, int) {
-    size_t b = ((size_t)(t.h.n ? t.h.n + 1 : 0) * sizeof(FilterCellD) + 15) & ~size_t(15);
-    b += ((t.bkt.size() * sizeof(uint16_t)) + 15) & ~size_t(15);
-    return b;
+size_t up16(size_t v) { return (v + 15) & ~size_t(15); }
+
+size_t band_bytes(const BandTableD &t, int precision) {
+    const size_t n = t.h.n, rs = precision == EGGPHOT_FP64 ? 8 : 4;
+    if (n == 0) return up16(t.bkt.size() * sizeof(uint16_t));
+    return up16((n + 1) * 8) + 2 * up16(n * 8) + up16(n * rs) + up16(n * 2 * rs) + up16(t.bkt.size() * sizeof(uint16_t));
+}
+
+template <typename T, typename Get> uint32_t append_array(std::vector<uint8_t> &blob, size_t count, Get get) {
+    align16(blob);
+    const uint32_t off = (uint32_t)blob.size();
+    for (size_t i = 0; i < count; ++i) {
+        const T v = (T)get(i);
+        const uint8_t *p = reinterpret_cast<const uint8_t *>(&v);
+        blob.insert(blob.end(), p, p + sizeof(T));
+    }
+    return off;
 }
 
 void append_band(std::vector<uint8_t> &blob, size_t header_pos, const BandTableD &t, int precision) {
     BandHeader h = t.h;
-    align16(blob);
-    h.cell_off = (uint32_t)blob.size();
-    for (const FilterCellD &e : t.cells) {
+    const size_t n = t.h.n;
+    const auto &c = t.cells;
+    if (n > 0) {
+        h.f_off = append_array<double>(blob, n + 1, [&](size_t i) { return c[i].f; });
+        h.lam_off = append_array<double>(blob, n, [&](size_t i) { return c[i].lam; });
+        h.k0_off = append_array<double>(blob, n, [&](size_t i) { return c[i].k0; });
         if (precision == EGGPHOT_FP64) {
-            const uint8_t *p = reinterpret_cast<const uint8_t *>(&e);
-            blob.insert(blob.end(), p, p + sizeof(e));
+            h.hr_off = append_array<double>(blob, n, [&](size_t i) { return c[i].hr; });
+            h.sdl_off = append_array<double>(blob, 2 * n, [&](size_t i) { return i & 1 ? c[i / 2].dl : c[i / 2].s; });
         } else {
-            FilterCellF o{};
-            o.f = e.f; o.lam = e.lam; o.k0 = e.k0; o.hr = e.hr;
-            o.s = (float)e.s; o.dl = (float)e.dl;
-            const uint8_t *p = reinterpret_cast<const uint8_t *>(&o);
-            blob.insert(blob.end(), p, p + sizeof(o));
+            h.hr_off = append_array<float>(blob, n, [&](size_t i) { return c[i].hr; });
+            h.sdl_off = append_array<float>(blob, 2 * n, [&](size_t i) { return i & 1 ? c[i / 2].dl : c[i / 2].s; });
         }
     }
-    align16(blob);
-    h.bkt_off = (uint32_t)blob.size();
-    const uint8_t *p = reinterpret_cast<const uint8_t *>(t.bkt.data());
-    blob.insert(blob.end(), p, p + t.bkt.size() * sizeof(uint16_t));
+    h.bkt_off = append_array<uint16_t>(blob, t.bkt.size(), [&](size_t i) { return t.bkt[i]; });
     align16(blob);
     std::memcpy(blob.data() + header_pos, &h, sizeof(h));
 }

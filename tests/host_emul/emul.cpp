@@ -135,10 +135,10 @@ void run(const Prepared &P, const eggphot_galaxies &G, size_t ngal, double *fd, 
                         std::vector<real> gD(N, real(0)), gB(N, real(0));
                         for (int j = jlo + 1; j < jhi; ++j) {
                             const double t = std::fma(opz, gr.x[j], -bv.fc);
-                            const int c = find_cell(bv.cells, bv.bkt, bv.nbkt, bv.f_first, bv.bkt_inv_w, t);
+                            const int c = find_cell<real>(bv, t);
                             double u;
-                            lam[j - jlo] = lambda_in_cell(bv.cells[c], t, u);
-                            const real ur = (real)u, sr = (real)bv.cells[c].s, dlr = (real)bv.cells[c].dl;
+                            lam[j - jlo] = lambda_in_cell<real>(bv, c, t, u);
+                            const real ur = (real)u, sr = bv.sdl[c].x, dlr = bv.sdl[c].y;
                             const real dxr = (real)(gr.x[j + 1] - gr.x[j]);
                             gD[j - jlo] = gamma_term<real>(sr, dlr, ur, dxr * opzr) * (real)gr.idx[j];
                             if (bulge_on) gB[j - jlo] = gamma_term<real>(sr, dlr, ur, (real)P.u_dxo[j] * opzr) * (real)gr.idx[j];
