@@ -218,9 +218,9 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
             for (int j = 0; j < n; ++j) r[j] = GridBD{dx(j), dxo(j)};
             CK(c->gridB.upload(r.data(), r.size() * sizeof(GridBD)));
         } else {
-            std::vector<GridBF> r((size_t)n + 1, GridBF{0, 0, 0, 0});
-            for (int j = 0; j < n; ++j) r[j] = GridBF{(float)dx(j), (float)dxo(j), (float)g.idx[j], 0.0f};
-            CK(c->gridB.upload(r.data(), r.size() * sizeof(GridBF)));
+            std::vector<float> r((size_t)n + 1, 0.0f);
+            for (int j = 0; j < n; ++j) r[j] = (float)dxo(j);
+            CK(c->gridB.upload(r.data(), r.size() * sizeof(float)));
         }
         tb += c->gridA.bytes + c->gridB.bytes;
     }

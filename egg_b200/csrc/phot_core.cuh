@@ -69,7 +69,11 @@ namespace eggphot {
 //   sdl[n]   real x2 slope of R in the cell (0 in zero-width cells and in the open cell), cell width (huge in the
 //                    open cell)
 //   bkt[nbkt] uint16 last node at or below the start of each bucket
+// The per-cell arrays are stored with one padding slot after every 16 entries (cell c lives in slot
+// c + c/16): lanes on every 2nd / 4th / ... cell (a filter sampled more finely than the SED) then fall on
+// distinct banks instead of colliding every 16 cells.
 template <typename real> struct alignas(2 * sizeof(real)) Pair2 { real x, y; };
+EGG_HD int cell_slot(int c) { return c + (c >> 4); }
 
 // Header of one band inside a group blob (device layout; offsets are bytes from the blob start).
 struct __attribute__((aligned(16))) BandHeader {
@@ -92,18 +96,13 @@ struct __attribute__((aligned(16))) BandHeader {
 };
 static_assert(sizeof(BandHeader) == 144, "BandHeader layout");
 
-// One node of the rest-frame disk grid as phase B reads it: two arrays of 16-byte records, so that a
-// warp's loads are contiguous.  GridA {x, idx}: wavelength and 1/(x[j+1] - x[j]) (0 for the last node).
-// GridB: x[j+1] - x[j]; the distance to the next OPTICAL node if j is one, else 0 (the bulge's union cells
-// start at optical nodes only); fp32 additionally idx as float.
+// One node of the rest-frame disk grid as phase B reads it.  GridA {x, idx}: wavelength and
+// 1/(x[j+1] - x[j]) (0 for the last node), one 16-byte record per node so that a warp's loads are contiguous.
+// The trapezoid-error term also needs the width x[j+1] - x[j] and the distance to the next OPTICAL node if j
+// is one, else 0 (the bulge's union cells start at optical nodes only): fp64 reads both from GridBD, fp32
+// reads only the latter (a float array) and takes the width as 1/idx.
 struct __attribute__((aligned(16))) GridA { double x, idx; };
-struct __attribute__((aligned(16))) GridBF { float dx, dxo, idxf, pad; };
 struct __attribute__((aligned(16))) GridBD { double dx, dxo; };
-template <typename real> struct GridBOf;
-template <> struct GridBOf<float> { typedef GridBF type; };
-template <> struct GridBOf<double> { typedef GridBD type; };
-EGG_HD float grid_idx(const GridA &, const GridBF &b) { return b.idxf; }
-EGG_HD double grid_idx(const GridA &a, const GridBD &) { return a.idx; }
 
 // Band seen through the kernel's real type.
 template <typename real> struct BandView {
@@ -137,14 +136,15 @@ template <typename real> EGG_HD int find_cell(const BandView<real> &b, double t)
     int k = (int)((float)(t - b.f_first) * b.bkt_inv_w);
     k = k < 0 ? 0 : (k > b.nbkt - 1 ? b.nbkt - 1 : k);
     int c = b.bkt[k];
-    while (t >= b.f[c + 1]) ++c;
+    while (t >= b.f[cell_slot(c + 1)]) ++c;
     return c;
 }
 
 // Lambda(t) in cell c and the offset u of t inside it.
 template <typename real> EGG_HD double lambda_in_cell(const BandView<real> &b, int c, double t, double &u) {
-    u = t - b.f[c];
-    return fma(u, fma(u, (double)b.hr[c], b.k0[c]), b.lam[c]);
+    const int cs = cell_slot(c);
+    u = t - b.f[cs];
+    return fma(u, fma(u, (double)b.hr[cs], b.k0[cs]), b.lam[cs]);
 }
 
 // gamma = s b u (b - u), b = min(dt + u, dl): the trapezoid-error term of the union cell that starts at

@@ -171,22 +171,37 @@ template <typename real> __device__ __forceinline__ CompSum<real> warp_reduce(Co
     return a;
 }
 
-// find_cell (phot_core.cuh) for a full warp.  When the band's buckets are narrower than its cells one probe
-// settles it; otherwise the forward scan runs as a warp-uniform loop on a vote instead of a per-lane
-// data-dependent loop: the warp executes the longest lane's scan either way, and the lanes provably stay
-// converged for the shuffles that follow (with a per-lane loop nvcc 12.9 emitted neither a reconvergence
+// find_cell (phot_core.cuh) for a full warp; also returns the node position, slope and width of the cell found.
+// When the band's buckets are narrower than its cells (one_probe) the cell is the bucket's or the next one, told
+// by the width of the first.  Otherwise the forward scan runs as a warp-uniform loop on a vote instead of a
+// per-lane data-dependent loop: the warp executes the longest lane's scan either way, and the lanes provably
+// stay converged for the shuffles that follow (with a per-lane loop nvcc 12.9 emitted neither a reconvergence
 // barrier after it nor a WARPSYNC before the shuffles, and lanes read stale registers).
 template <typename real>
-__device__ __forceinline__ int find_cell_warp(const BandView<real> &b, double t) {
+__device__ __forceinline__ int find_cell_warp(const BandView<real> &b, double t, double &fcell, Pair2<real> &sd) {
     int k = (int)((float)(t - b.f_first) * b.bkt_inv_w);
     k = max(0, min(k, b.nbkt - 1));
     int c = b.bkt[k];
-    bool up = t >= b.f[c + 1];
-    if (b.one_probe) return c + (up ? 1 : 0);
+    if (b.one_probe) {
+        int cs = cell_slot(c);
+        fcell = b.f[cs];
+        sd = b.sdl[cs];
+        // (real): in fp32 a node within float rounding of a cell boundary may take either cell; Lambda is
+        // continuous there and the error is far below the mode's resolution
+        if ((real)(t - fcell) >= sd.y) {
+            cs = cell_slot(++c);
+            fcell = b.f[cs];
+            sd = b.sdl[cs];
+        }
+        return c;
+    }
+    bool up = t >= b.f[cell_slot(c + 1)];
     while (__any_sync(kFull, up)) {
         c += up ? 1 : 0;
-        up = t >= b.f[c + 1];
+        up = t >= b.f[cell_slot(c + 1)];
     }
+    fcell = b.f[cell_slot(c)];
+    sd = b.sdl[cell_slot(c)];
     return c;
 }
 
@@ -213,10 +228,6 @@ template <> struct Pair<double> { typedef double2 type; };
 __device__ __forceinline__ GridA ldg_grid(const GridA *g) {
     const double2 a = __ldg(reinterpret_cast<const double2 *>(g));
     return GridA{a.x, a.y};
-}
-__device__ __forceinline__ GridBF ldg_grid(const GridBF *g) {
-    const float4 a = __ldg(reinterpret_cast<const float4 *>(g));
-    return GridBF{a.x, a.y, a.z, a.w};
 }
 __device__ __forceinline__ GridBD ldg_grid(const GridBD *g) {
     const double2 a = __ldg(reinterpret_cast<const double2 *>(g));
@@ -252,7 +263,6 @@ __host__ __device__ inline SmemLayout smem_layout(const FluxParams &p) {
 template <typename real, int NT>
 __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ FluxParams p) {
     typedef typename Pair<real>::type real2;
-    typedef typename GridBOf<real>::type GridB;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ GalScal sc[kBatch];
     __shared__ __align__(8) uint64_t bar_tab;
@@ -279,7 +289,6 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
     const real *rO = reinterpret_cast<const real *>(p.rowsDopt), *rI = reinterpret_cast<const real *>(p.rowsDir);
     const real *rP = reinterpret_cast<const real *>(p.rowsDpah), *rB = reinterpret_cast<const real *>(p.rowsB);
     const GridA *gridA = reinterpret_cast<const GridA *>(p.gridA);
-    const GridB *gridB = reinterpret_cast<const GridB *>(p.gridB);
 
     if (tid == 0) {
         mbar_init(&bar_tab, 1);
@@ -513,9 +522,13 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                     }
                 }
                 // the row stride is a multiple of four: node j0 + 1 <= stride - 1 always has room
-                real2 *dst = reinterpret_cast<real2 *>(DU) + j0;
-                dst[0] = make_pair2(v.x, w.x);
-                dst[1] = make_pair2(v.y, w.y);
+                if constexpr (sizeof(real) == 4) {
+                    *reinterpret_cast<float4 *>(DU + 2 * j0) = make_float4(v.x, w.x, v.y, w.y);
+                } else {
+                    real2 *dst = reinterpret_cast<real2 *>(DU) + j0;
+                    dst[0] = make_pair2(v.x, w.x);
+                    dst[1] = make_pair2(v.y, w.y);
+                }
             }
         }
         __syncthreads();
@@ -572,16 +585,25 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                         const int j = jb + lane;
                         const int jc = min(max(j, jlo), jhi);
                         const GridA g = ldg_grid(gridA + jc);
-                        const GridB gb = ldg_grid(gridB + jc);
                         const real2 su = DU[jc];
+                        real dt, dto, gidx; // observed widths to the next disk / optical node; 1/dx in the mode's type
+                        if constexpr (sizeof(real) == 4) {
+                            gidx = (float)g.idx;
+                            dt = __fdividef(opzr, gidx);
+                            dto = __ldg(reinterpret_cast<const float *>(p.gridB) + jc) * opzr;
+                        } else {
+                            const GridBD gb = ldg_grid(reinterpret_cast<const GridBD *>(p.gridB) + jc);
+                            gidx = g.idx; dt = gb.dx * opzr; dto = gb.dxo * opzr;
+                        }
                         const double t = fma(opz, g.x, -bv.fc);
-                        const int c = find_cell_warp<real>(bv, t);
+                        double fcell;
+                        Pair2<real> sd;
+                        const int cs = cell_slot(find_cell_warp<real>(bv, t, fcell, sd));
                         const bool inner = j > jlo && j < jhi;
-                        const double u = t - bv.f[c];
-                        const double lam = inner ? fma(u, fma(u, (double)bv.hr[c], bv.k0[c]), bv.lam[c]) : 0.0; // 0 at both window ends
+                        const double u = t - fcell;
+                        const double lam = inner ? fma(u, fma(u, (double)bv.hr[cs], bv.k0[cs]), bv.lam[cs]) : 0.0; // 0 at both window ends
                         const real ur = inner ? (real)u : real(0);
-                        const Pair2<real> sd = bv.sdl[c];
-                        const real sr = sd.x, dlr = sd.y, gidx = grid_idx(g, gb);
+                        const real sr = sd.x, dlr = sd.y;
                         double dlam = __shfl_down_sync(kFull, lam, 1) - lam;
                         if (j == b) dlam += asym_b1;
                         const double E = (j >= jlo && j < jhi) ? dlam * g.idx : 0.0;
@@ -589,11 +611,11 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                         if (j == b + 1) Ep -= tot0z;
                         const real W = (real)(E - Ep);
                         const bool own = lane >= 1 && lane <= 30 && j <= jhi;
-                        const real gD = gamma_term<real>(sr, dlr, ur, (real)gb.dx * opzr) * gidx;
+                        const real gD = gamma_term<real>(sr, dlr, ur, dt) * gidx;
                         const real gDp = __shfl_up_sync(kFull, gD, 1);
                         accd = fma(su.x, own ? fma(real(0.5), gD - gDp, W) : real(0), accd);
                         if (bulge_on) {
-                            const real gB = gamma_term<real>(sr, dlr, ur, (real)gb.dxo * opzr) * gidx;
+                            const real gB = gamma_term<real>(sr, dlr, ur, dto) * gidx;
                             const real gBp = __shfl_up_sync(kFull, gB, 1);
                             accb = fma(su.y, own ? fma(real(0.5), gB - gBp, W) : real(0), accb);
                         }

@@ -50,7 +50,8 @@ struct FluxParams {
     int32_t nB, nD;        // nodes (0 if the component is absent)
     int32_t strideB, strideD; // row strides in elements (16-byte multiples)
     const double *xB, *xD; // rest wavelengths, double
-    const void *gridA, *gridB; // disk grid as GridA / GridBF|GridBD records (phot_core.cuh), one padding record at the end
+    const void *gridA, *gridB; // disk grid: GridA records; fp64 GridBD records, fp32 a float array of dxo
+                               // (phot_core.cuh); one padding record at the end
     const uint16_t *lutB, *lutD; // log2-spaced "last node <= v" lookups (Grid::lut)
     int32_t lutB_n, lutD_n, lutB_e0, lutD_e0;
     int32_t igmB[4], igmD[4]; // lz, l0, l1, l2

@@ -180,7 +180,8 @@ size_t up16(size_t v) { return (v + 15) & ~size_t(15); }
 size_t band_bytes(const BandTableD &t, int precision) {
     const size_t n = t.h.n, rs = precision == EGGPHOT_FP64 ? 8 : 4;
     if (n == 0) return up16(t.bkt.size() * sizeof(uint16_t));
-    return up16((n + 1) * 8) + 2 * up16(n * 8) + up16(n * rs) + up16(n * 2 * rs) + up16(t.bkt.size() * sizeof(uint16_t));
+    const size_t sf = cell_slot((int)n) + 1, sc = cell_slot((int)n - 1) + 1; // padded slots (phot_core.cuh)
+    return up16(sf * 8) + 2 * up16(sc * 8) + up16(sc * rs) + up16(sc * 2 * rs) + up16(t.bkt.size() * sizeof(uint16_t));
 }
 
 template <typename T, typename Get> uint32_t append_array(std::vector<uint8_t> &blob, size_t count, Get get) {
@@ -193,21 +194,32 @@ template <typename T, typename Get> uint32_t append_array(std::vector<uint8_t> &
     }
     return off;
 }
+// per-cell array of `width` values per cell, cell c stored in slot cell_slot(c)
+template <typename T, typename Get> uint32_t append_cells(std::vector<uint8_t> &blob, size_t ncell, int width, Get get) {
+    align16(blob);
+    const uint32_t off = (uint32_t)blob.size();
+    const size_t nslot = cell_slot((int)ncell - 1) + 1;
+    blob.resize(blob.size() + nslot * width * sizeof(T), 0);
+    T *dst = reinterpret_cast<T *>(blob.data() + off);
+    for (size_t c = 0; c < ncell; ++c)
+        for (int w = 0; w < width; ++w) dst[(size_t)cell_slot((int)c) * width + w] = (T)get(c, w);
+    return off;
+}
 
 void append_band(std::vector<uint8_t> &blob, size_t header_pos, const BandTableD &t, int precision) {
     BandHeader h = t.h;
     const size_t n = t.h.n;
     const auto &c = t.cells;
     if (n > 0) {
-        h.f_off = append_array<double>(blob, n + 1, [&](size_t i) { return c[i].f; });
-        h.lam_off = append_array<double>(blob, n, [&](size_t i) { return c[i].lam; });
-        h.k0_off = append_array<double>(blob, n, [&](size_t i) { return c[i].k0; });
+        h.f_off = append_cells<double>(blob, n + 1, 1, [&](size_t i, int) { return c[i].f; });
+        h.lam_off = append_cells<double>(blob, n, 1, [&](size_t i, int) { return c[i].lam; });
+        h.k0_off = append_cells<double>(blob, n, 1, [&](size_t i, int) { return c[i].k0; });
         if (precision == EGGPHOT_FP64) {
-            h.hr_off = append_array<double>(blob, n, [&](size_t i) { return c[i].hr; });
-            h.sdl_off = append_array<double>(blob, 2 * n, [&](size_t i) { return i & 1 ? c[i / 2].dl : c[i / 2].s; });
+            h.hr_off = append_cells<double>(blob, n, 1, [&](size_t i, int) { return c[i].hr; });
+            h.sdl_off = append_cells<double>(blob, n, 2, [&](size_t i, int w) { return w ? c[i].dl : c[i].s; });
         } else {
-            h.hr_off = append_array<float>(blob, n, [&](size_t i) { return c[i].hr; });
-            h.sdl_off = append_array<float>(blob, 2 * n, [&](size_t i) { return i & 1 ? c[i / 2].dl : c[i / 2].s; });
+            h.hr_off = append_cells<float>(blob, n, 1, [&](size_t i, int) { return c[i].hr; });
+            h.sdl_off = append_cells<float>(blob, n, 2, [&](size_t i, int w) { return w ? c[i].dl : c[i].s; });
         }
     }
     h.bkt_off = append_array<uint16_t>(blob, t.bkt.size(), [&](size_t i) { return t.bkt[i]; });
@@ -553,33 +565,51 @@ Status prepare(const eggphot_libs &L, const eggphot_filters *bands, const eggpho
             return Status::error(EGGPHOT_ERR_UNSUPPORTED, "filter " + std::to_string(P.band_order[b]) +
                                  " has too many nodes for the shared-memory band tables");
     }
-    size_t b0 = 0;
-    while (b0 < tabs.size()) {
-        size_t b1 = b0, bytes = 0;
-        while (b1 < tabs.size()) {
-            const size_t add = band_bytes(tabs[b1], P.precision) + sizeof(BandHeader);
-            if (b1 > b0 && bytes + add > budget) break;
-            bytes += add;
-            ++b1;
-        }
-        BandGroup g;
-        g.blob.assign((b1 - b0) * sizeof(BandHeader), 0);
-        // inside a group the bands are stored by decreasing expected work (SED nodes under the
-        // filter at z = 1): warps pull items in storage order, long ones first
-        std::vector<size_t> ord;
-        for (size_t b = b0; b < b1; ++b) {
+    // bands need not be contiguous in a group: first-fit-decreasing into as few groups as the budget allows
+    // (fewer groups = fewer table loads and barriers per batch of galaxies)
+    {
+        std::vector<size_t> size(tabs.size()), bysize(tabs.size());
+        size_t total = 0;
+        for (size_t b = 0; b < tabs.size(); ++b) {
+            size[b] = band_bytes(tabs[b], P.precision) + sizeof(BandHeader) + 16;
+            total += size[b];
+            bysize[b] = b;
             const Grid &gd = P.grid_disk;
             const int lo = last_le(gd.x, tabs[b].h.eff_first / 2.0), hi = last_le(gd.x, tabs[b].h.eff_last / 2.0);
             tabs[b].h.cost = (float)std::max(hi - lo, 1);
-            ord.push_back(b);
         }
-        std::stable_sort(ord.begin(), ord.end(), [&](size_t i, size_t j) { return tabs[i].h.cost > tabs[j].h.cost; });
-        for (size_t k = 0; k < ord.size(); ++k) {
-            g.cols.push_back((uint32_t)ord[k]);
-            append_band(g.blob, k * sizeof(BandHeader), tabs[ord[k]], P.precision);
+        std::stable_sort(bysize.begin(), bysize.end(), [&](size_t i, size_t j) { return size[i] > size[j]; });
+        std::vector<std::vector<size_t>> bins;
+        for (size_t ng = std::max<size_t>((total + budget - 1) / budget, 1); !tabs.empty(); ++ng) {
+            bins.assign(ng, {});
+            std::vector<size_t> fill(ng, 0);
+            bool ok = true;
+            for (size_t b : bysize) {
+                size_t best = ng;
+                for (size_t g = 0; g < ng; ++g) // the emptiest group that still has room: keeps the groups even
+                    if (fill[g] + size[b] <= budget && (best == ng || fill[g] < fill[best])) best = g;
+                if (best == ng) {
+                    if (size[b] > budget && ng >= tabs.size()) { best = 0; for (size_t g = 1; g < ng; ++g) if (fill[g] < fill[best]) best = g; }
+                    else { ok = false; break; }
+                }
+                bins[best].push_back(b);
+                fill[best] += size[b];
+            }
+            if (ok) break;
         }
-        P.groups.push_back(std::move(g));
-        b0 = b1;
+        for (auto &bin : bins) {
+            if (bin.empty()) continue;
+            // inside a group the bands are stored by decreasing expected work (SED nodes under the
+            // filter at z = 1): warps pull items in storage order, long ones first
+            std::stable_sort(bin.begin(), bin.end(), [&](size_t i, size_t j) { return tabs[i].h.cost > tabs[j].h.cost; });
+            BandGroup g;
+            g.blob.assign(bin.size() * sizeof(BandHeader), 0);
+            for (size_t k = 0; k < bin.size(); ++k) {
+                g.cols.push_back((uint32_t)bin[k]);
+                append_band(g.blob, k * sizeof(BandHeader), tabs[bin[k]], P.precision);
+            }
+            P.groups.push_back(std::move(g));
+        }
     }
 
     // ---- rest-frame weights

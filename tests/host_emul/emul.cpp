@@ -138,7 +138,7 @@ void run(const Prepared &P, const eggphot_galaxies &G, size_t ngal, double *fd, 
                             const int c = find_cell<real>(bv, t);
                             double u;
                             lam[j - jlo] = lambda_in_cell<real>(bv, c, t, u);
-                            const real ur = (real)u, sr = bv.sdl[c].x, dlr = bv.sdl[c].y;
+                            const real ur = (real)u, sr = bv.sdl[cell_slot(c)].x, dlr = bv.sdl[cell_slot(c)].y;
                             const real dxr = (real)(gr.x[j + 1] - gr.x[j]);
                             gD[j - jlo] = gamma_term<real>(sr, dlr, ur, dxr * opzr) * (real)gr.idx[j];
                             if (bulge_on) gB[j - jlo] = gamma_term<real>(sr, dlr, ur, (real)P.u_dxo[j] * opzr) * (real)gr.idx[j];
