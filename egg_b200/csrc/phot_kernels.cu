@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
     __shared__ GalScal sc[kBatch];
     __shared__ __align__(8) uint64_t bar_tab;
     __shared__ int item_ctr[kMaxGroups];
+    __shared__ int any_bulge_line; // some bulge of the batch has an emission line with flux (normally none)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = NT / 32;
@@ -306,6 +307,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
         // ---- phase A1: per-galaxy scalars, one thread per galaxy
         if (tid < ng) gal_scalars(p, g0 + tid, sc[tid]);
         if (tid >= 32 && tid < 32 + kMaxGroups) item_ctr[tid - 32] = 0;
+        if (tid == 64) any_bulge_line = 0;
         for (int i = tid; i < ng * nbt * 2; i += NT) res[i] = 0.0;
         __syncthreads();
 
@@ -390,6 +392,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
             }
             lb[2 * idx] = b0;
             lb[2 * idx + 1] = b1;
+            if (!c && b0 <= b1) any_bulge_line = 1;
         }
         __syncthreads();
 
@@ -400,7 +403,9 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
         //      all lines are numbered consecutively (prefix sum) and dealt to the lanes.
         auto deposit_lines = [&](const int c) { // c: 0 bulge (before it is resampled on the disk grid), 1 disk
             const float *llp = c ? p.line_lum_disk : p.line_lum_bulge;
-            for (int gi = warp; gi < ng; gi += NW) {
+            // two warps per galaxy: both number the owned nodes (identical results) and take alternate 32-node slices
+            for (int ht = warp; ht < 2 * ng; ht += NW) {
+                const int gi = ht >> 1, half = ht & 1;
                 const int task = 2 * gi + c;
                 const int *wb = lb + 2 * task * nline;
                 int *wt = lt + 2 * task * nline;
@@ -439,7 +444,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                 const int sstep = c ? 2 : 1;
                 // the bulge SED carries no mass scale (applied at the end), so its line term is divided by it
                 const double inv = c ? 1.0 : (s.a_bulge > 0 ? 1.0 / s.a_bulge : 0.0);
-                for (int t = lane; t < total; t += 32) {
+                for (int t = lane + 32 * half; t < total; t += 64) {
                     int lo = 0, hi = nline; // last line whose task offset is <= t and that owns nodes
                     while (hi - lo > 1) {
                         const int mid = (lo + hi) >> 1;
@@ -464,7 +469,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                 }
             }
         };
-        if (nline > 0 && p.has_bulge && p.line_lum_bulge != nullptr) {
+        if (any_bulge_line) { // block-uniform: written before the barrier above
             deposit_lines(0);
             __syncthreads();
         }
