@@ -73,12 +73,12 @@ struct GalScal {
 };
 
 __device__ void gal_scalars(const FluxParams &p, uint64_t g, GalScal &s) {
-    const double z = p.z[g], d = p.d[g];
+    const double z = __ldcs(p.z + g), d = __ldcs(p.d + g); // galaxy columns are read once: streaming loads
     s.opz = 1.0 + z;
     s.iopz = 1.0 / s.opz;
     s.l2opz = (float)(log2(s.opz) * kLutPerOctave);
     s.aflux = EGGPHOT_LSUN2UJY * (1.0 + z) / (d * d);
-    const float m2l = p.m2lcor[g];
+    const float m2l = __ldcs(p.m2lcor + g);
     // the reference passes the FLOAT difference m[i]-out.m2lcor[i] to e10 (src/egg-gencat.cpp:2106, 2114)
     s.a_bulge = p.has_bulge ? exp10((double)(p.m_bulge[g] - m2l)) : 0.0;
     s.a_disk = p.disk_mode != 2 ? exp10((double)(p.m_disk[g] - m2l)) : 0.0;
@@ -105,7 +105,7 @@ __device__ void gal_scalars(const FluxParams &p, uint64_t g, GalScal &s) {
         if (rd >= p.nopt_sed || !p.opt_use[rd]) { bad = true; rd = 0; }
     }
     s.row_b = (uint32_t)rb; s.row_d = (uint32_t)rd; s.row_i = (uint32_t)ri;
-    if (p.apply_igm) { s.igm[0] = p.igm_abs[3 * g]; s.igm[1] = p.igm_abs[3 * g + 1]; s.igm[2] = p.igm_abs[3 * g + 2]; }
+    if (p.apply_igm) { s.igm[0] = __ldcs(p.igm_abs + 3 * g); s.igm[1] = __ldcs(p.igm_abs + 3 * g + 1); s.igm[2] = __ldcs(p.igm_abs + 3 * g + 2); }
     else s.igm[0] = s.igm[1] = s.igm[2] = 1.0f;
     s.vdisp = p.nline ? (double)p.vdisp[g] : 0.0;
     if (bad) atomicExch(p.error_flag, EGGPHOT_ERR_INDEX);
@@ -543,7 +543,12 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
         }
 
         // ---- phase B: band groups
-        for (int grp = 0; grp < (int)p.ngroups || (grp == 0 && nrf > 0); ++grp) {
+        // consecutive batches walk the groups in opposite orders: the tables of the group a batch ends with are
+        // still in shared memory when the next batch starts with it (one table load less per batch)
+        const int ngl = max((int)p.ngroups, nrf > 0 ? 1 : 0);
+        const bool rev = ((batch - blockIdx.x) / gridDim.x) & 1;
+        for (int gstep = 0; gstep < ngl; ++gstep) {
+            const int grp = rev ? ngl - 1 - gstep : gstep;
             const int nb = grp < (int)p.ngroups ? (int)p.groups[grp].nb : 0;
             if (nb > 0 && loaded != grp) {
                 if (tid == 0) {
@@ -663,11 +668,12 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
         for (int i = tid; i < ng * nbt; i += NT) {
             const float fb = (float)res[2 * i], fd = (float)res[2 * i + 1];
             const size_t o = (size_t)g0 * nbt + i;
-            if (p.flux_disk) p.flux_disk[o] = fd;
-            if (p.flux_bulge) p.flux_bulge[o] = fb;
-            if (p.flux) p.flux[o] = fd + fb; // vec2f sum
-            if (p.flux_disk_f64) p.flux_disk_f64[o] = res[2 * i + 1];
-            if (p.flux_bulge_f64) p.flux_bulge_f64[o] = res[2 * i];
+            // streaming stores: the catalog columns are written once and must not evict the scratch from L2
+            if (p.flux_disk) __stcs(p.flux_disk + o, fd);
+            if (p.flux_bulge) __stcs(p.flux_bulge + o, fb);
+            if (p.flux) __stcs(p.flux + o, fd + fb); // vec2f sum
+            if (p.flux_disk_f64) __stcs(p.flux_disk_f64 + o, res[2 * i + 1]);
+            if (p.flux_bulge_f64) __stcs(p.flux_bulge_f64 + o, res[2 * i]);
         }
         for (int i = tid; i < ng * nrf; i += NT) {
             // [vif] lsun2uJy(0, 1e-5, ...) then uJy2mag; non-finite -> +99 (src/egg-gencat.cpp:2152-2156)
@@ -679,12 +685,12 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
             }
             const size_t o = (size_t)g0 * nrf + i;
             const float md = (float)mg[1], mb = (float)mg[0];
-            if (p.rfmag_disk) p.rfmag_disk[o] = md;
-            if (p.rfmag_bulge) p.rfmag_bulge[o] = mb;
+            if (p.rfmag_disk) __stcs(p.rfmag_disk + o, md);
+            if (p.rfmag_bulge) __stcs(p.rfmag_bulge + o, mb);
             if (p.rfmag) // uJy2mag(mag2uJy(disk) + mag2uJy(bulge)) on the f32 columns (src/egg-gencat.cpp:2239)
-                p.rfmag[o] = (float)(-2.5 * log10(exp10(0.4 * (23.9 - (double)md)) + exp10(0.4 * (23.9 - (double)mb))) + 23.9);
-            if (p.rfmag_disk_f64) p.rfmag_disk_f64[o] = mg[1];
-            if (p.rfmag_bulge_f64) p.rfmag_bulge_f64[o] = mg[0];
+                __stcs(p.rfmag + o, (float)(-2.5 * log10(exp10(0.4 * (23.9 - (double)md)) + exp10(0.4 * (23.9 - (double)mb))) + 23.9));
+            if (p.rfmag_disk_f64) __stcs(p.rfmag_disk_f64 + o, mg[1]);
+            if (p.rfmag_bulge_f64) __stcs(p.rfmag_bulge_f64 + o, mg[0]);
         }
         __syncthreads(); // res / sc are rewritten by the next batch
     }

@@ -11,7 +11,10 @@ namespace eggphot {
 
 constexpr int kMaxLines = 64;
 constexpr int kMaxGroupBands = 64;
-constexpr int kBatch = 16;             // galaxies a CTA carries through all band groups at a time
+#ifndef EGG_KBATCH
+#define EGG_KBATCH 16
+#endif
+constexpr int kBatch = EGG_KBATCH;     // galaxies a CTA carries through all band groups at a time (power of two)
 constexpr int kMaxGroups = 16;
 constexpr int kMaxRf = 16;
 

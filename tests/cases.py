@@ -30,6 +30,8 @@ CASES = {
                           {"opt_lib_imf": "chabrier", "trim_filters": True, "filter_photons": True}),
     "b4_flambda_nonorm": ("opt", "ce01", synth.B4, [], {"filter_flambda": True, "filter_normalize": False,
                                                         "opt_lib_min_step": 0.0}),
+    # the reference's bulges carry no lines (src/egg-gencat.cpp:1886-1976) but get_flux would add them: exercise it
+    "b23_bulge_lines": ("opt", "ce01", synth.B23, synth.RF3, {"_bulge_lines": 0.3}),
 }
 
 
@@ -37,6 +39,10 @@ def make(name, ngal=96, seed=11):
     ok, ik, bands, rf, opts = CASES[name]
     L = libs()
     gal = synth.draw_galaxies(ngal, opt_lib=L[ok], ir_lib=L[ik], mmin=7.5, seed=seed)
+    opts = dict(opts)
+    frac = opts.pop("_bulge_lines", None)
+    if frac is not None:
+        gal["line_lum_bulge"] = (frac * gal["line_lum_disk"]).astype(np.float32)
     return dict(opt=L[ok], ir=L[ik], bands=synth.get_filters(bands), rfbands=synth.get_filters(rf),
                 opts=dict(opts), gal=gal, lines=synth.LINE_LAMBDA)
 

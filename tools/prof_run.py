@@ -8,6 +8,9 @@ import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 import egg_b200  # noqa: E402
+from egg_b200 import photometry  # noqa: E402
+if os.environ.get('EGGPHOT_LIB'):
+    photometry.load_library(os.environ['EGGPHOT_LIB'])
 from egg_b200 import synth  # noqa: E402
 
 np.seterr(all="ignore")
