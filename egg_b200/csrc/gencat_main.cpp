@@ -1,0 +1,482 @@
+// gencat_main.cpp — egg-gencat-b200: the photometry stage of egg-gencat as a stand-alone program.
+//
+// Keeps egg-gencat's `key=value` command line (src/egg-gencat.cpp:137-149; `-key=value` is equally
+// valid, a bare `key` means true, lists are `[a,b,c]`) and its column-oriented FITS layout
+// (src/egg-gencat.cpp:2253-2286) for the block `if (!no_flux) {...}` (:2024-2240).  The galaxy
+// generation before that block (:610-2022: stochastic draws) is not rebuilt: the per-galaxy columns
+// it produces are read from an existing egg catalog, `input_props=<catalog.fits>` — every egg output
+// catalog holds them next to the fluxes, so any catalog of a real egg install can be re-computed.
+//
+// All computation happens in libeggphot.so on the GPU(s); there is no CPU path.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <regex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/eggphot.h"
+#include "fitscol.hpp"
+
+namespace {
+
+void note(const std::string &m) { std::cout << "note: " << m << std::endl; }
+void warning(const std::string &m) { std::cerr << "warning: " << m << std::endl; }
+void error(const std::string &m) { std::cerr << "error: " << m << std::endl; }
+
+#ifndef EGG_SHARE_DIR
+#define EGG_SHARE_DIR ""
+#endif
+#ifndef FILTER_DB_DIR
+#define FILTER_DB_DIR ""
+#endif
+
+std::string env_or(const char *name, const std::string &dflt) {
+    const char *e = std::getenv(name);
+    return e && *e ? std::string(e) : dflt;
+}
+std::string with_slash(std::string d) {
+    if (!d.empty() && d.back() != '/') d += '/';
+    return d;
+}
+std::string remove_extension(const std::string &f) {
+    const size_t sl = f.find_last_of('/'), dot = f.find_last_of('.');
+    return (dot == std::string::npos || (sl != std::string::npos && dot < sl)) ? f : f.substr(0, dot);
+}
+std::string basename_of(const std::string &f) {
+    const size_t sl = f.find_last_of('/');
+    return sl == std::string::npos ? f : f.substr(sl + 1);
+}
+
+// ---- read_args ------------------------------------------------------------------------------------
+struct Args {
+    std::map<std::string, std::string> kv;
+    bool has(const std::string &k) const { return kv.count(k) != 0; }
+    std::string str(const std::string &k, const std::string &d = "") const { return has(k) ? kv.at(k) : d; }
+    bool flag(const std::string &k) const {
+        if (!has(k)) return false;
+        const std::string v = kv.at(k);
+        return !(v == "0" || v == "false");
+    }
+    double num(const std::string &k, double d) const { return has(k) ? std::atof(kv.at(k).c_str()) : d; }
+    std::vector<std::string> list(const std::string &k, const std::vector<std::string> &d) const {
+        if (!has(k)) return d;
+        std::string v = kv.at(k);
+        if (!v.empty() && v.front() == '[') v = v.substr(1);
+        if (!v.empty() && v.back() == ']') v.pop_back();
+        std::vector<std::string> out;
+        std::string item;
+        for (char c : v) {
+            if (c == ',') { if (!item.empty()) out.push_back(item); item.clear(); }
+            else if (c != ' ' && c != '"' && c != '\'') item += c;
+        }
+        if (!item.empty()) out.push_back(item);
+        return out;
+    }
+};
+
+Args read_args(int argc, char *argv[]) {
+    Args a;
+    for (int i = 1; i < argc; ++i) {
+        std::string s = argv[i];
+        while (!s.empty() && s[0] == '-') s = s.substr(1);
+        const size_t eq = s.find('=');
+        if (eq == std::string::npos) a.kv[s] = "1";
+        else a.kv[s.substr(0, eq)] = s.substr(eq + 1);
+    }
+    if (a.has("list_band")) a.kv["list_bands"] = a.kv["list_band"]; // the manual uses both spellings
+    return a;
+}
+
+// ---- filters ---------------------------------------------------------------------------------------
+struct Curve {
+    std::string name;
+    std::vector<double> lam, res;
+};
+
+double trapz(const std::vector<double> &x, const std::vector<double> &y) {
+    double s = 0;
+    for (size_t i = 0; i + 1 < x.size(); ++i) s += 0.5 * (y[i] + y[i + 1]) * (x[i + 1] - x[i]);
+    return s;
+}
+
+bool read_curve(const std::string &path, Curve &c) {
+    fitscol::Table t = fitscol::read_table(path);
+    const fitscol::Column *l = t.find("LAM"), *r = t.find("RES");
+    if (!l || !r) { error("filter file '" + path + "' has no LAM/RES columns"); return false; }
+    c.lam = fitscol::as_double(*l);
+    c.res = fitscol::as_double(*r);
+    if (c.lam.size() != c.res.size() || c.lam.size() < 2) { error("filter file '" + path + "' is empty or inconsistent"); return false; }
+    return true;
+}
+
+// [vif] get_filters: plain names from the data base, `name:file:path`, `name:range:lmin:lmax`
+// (doc/doc-egg-gencat.tex:254-260)
+bool get_filters(const std::vector<std::pair<std::string, std::string>> &db, const std::vector<std::string> &bands,
+                 std::vector<Curve> &out) {
+    for (const std::string &b : bands) {
+        Curve c;
+        std::vector<std::string> part;
+        {
+            std::string item;
+            for (char ch : b) { if (ch == ':') { part.push_back(item); item.clear(); } else item += ch; }
+            part.push_back(item);
+        }
+        c.name = part[0];
+        if (part.size() >= 3 && part[1] == "file") {
+            std::string path = part[2];
+            for (size_t k = 3; k < part.size(); ++k) path += ":" + part[k];
+            if (!read_curve(path, c)) return false;
+        } else if (part.size() == 4 && part[1] == "range") {
+            const double lo = std::atof(part[2].c_str()), hi = std::atof(part[3].c_str());
+            if (!(hi > lo)) { error("band '" + b + "': bad wavelength range"); return false; }
+            c.lam = {lo, hi}; // top-hat of unit integral
+            c.res = {1.0 / (hi - lo), 1.0 / (hi - lo)};
+        } else {
+            bool found = false;
+            for (const auto &e : db)
+                if (e.first == b) { found = read_curve(e.second, c); if (!found) return false; break; }
+            if (!found) {
+                error("unknown filter '" + b + "'");
+                std::string near;
+                for (const auto &e : db)
+                    if (e.first.find(b.substr(0, b.find('-'))) == 0) near += " " + e.first;
+                if (!near.empty()) note("filters of the same instrument:" + near);
+                return false;
+            }
+        }
+        out.push_back(std::move(c));
+    }
+    return true;
+}
+
+int list_bands(const std::string &pattern, const std::string &db_file) {
+    if (pattern == "1") std::cout << "List of available bands:" << std::endl;
+    else std::cout << "List of available bands (filter: '" << pattern << "'):" << std::endl;
+    std::ifstream probe(db_file);
+    if (!probe) { error("could not find filter database file '" + db_file + "'"); return 1; }
+    struct Row { std::string name; float rlam, width; };
+    std::vector<Row> rows;
+    const std::regex re(pattern == "1" ? ".*" : pattern, std::regex::extended);
+    for (const auto &e : fitscol::read_filter_db(db_file)) {
+        if (pattern != "1" && !std::regex_search(e.first, re)) continue;
+        Curve c;
+        if (!read_curve(e.second, c)) continue;
+        const double mx = *std::max_element(c.res.begin(), c.res.end());
+        if (mx <= 0) { warning("zero transmission for filter " + e.first); continue; }
+        std::vector<double> lr(c.lam.size());
+        for (size_t i = 0; i < lr.size(); ++i) lr[i] = c.lam[i] * c.res[i];
+        size_t a = c.lam.size(), b = 0;
+        for (size_t i = 0; i < c.res.size(); ++i)
+            if (c.res[i] > 0.5 * mx) { a = std::min(a, i); b = i; }
+        rows.push_back({e.first, (float)trapz(c.lam, lr), (float)(c.lam[b] - c.lam[a])}); // src/egg-gencat.cpp:195-199
+    }
+    std::stable_sort(rows.begin(), rows.end(), [](const Row &x, const Row &y) {
+        const std::string ix = x.name.substr(0, x.name.find('-')), iy = y.name.substr(0, y.name.find('-'));
+        return ix != iy ? ix < iy : x.rlam < y.rlam;
+    });
+    auto fmt = [](float v) { char b[32]; std::snprintf(b, sizeof b, "%g", v); return std::string(b); };
+    size_t wn = 0, wl = 0;
+    for (const Row &r : rows) { wn = std::max(wn, r.name.size()); wl = std::max(wl, (fmt(r.rlam) + " um, ").size()); }
+    for (const Row &r : rows) {
+        std::string n = r.name, l = fmt(r.rlam) + " um, ";
+        n.resize(wn, ' ');
+        l.resize(wl, ' ');
+        std::cout << " - " << n << "  ref-lam = " << l << "FWHM = " << fmt(r.width) << " um" << std::endl;
+    }
+    return 0;
+}
+
+void print_help() {
+    std::cout <<
+        "egg-gencat-b200: the photometry stage of egg-gencat (fluxes and rest-frame magnitudes) on NVIDIA B200\n"
+        "usage: egg-gencat-b200 input_props=catalog.fits [options]\n\n"
+        "  input_props=FILE   egg catalog holding the per-galaxy columns (Z D M_DISK M_BULGE M2LCOR OPT_SED_DISK\n"
+        "                     OPT_SED_BULGE IR_SED LIR FPAH MDUST IGM_ABS VDISP LINE_LUM_DISK LINE_LUM_BULGE LINE_LAMBDA)\n"
+        "  bands=[...]        bands for observed fluxes (default: the 23 bands of egg-gencat)\n"
+        "  rfbands=[...]      bands for rest-frame absolute magnitudes (default: none)\n"
+        "  filter_db=FILE     filter data base (db.dat); default $EGG_FILTERS_PATH/db.dat\n"
+        "  opt_lib=FILE ir_lib=FILE opt_lib_imf=salpeter|chabrier|kroupa opt_lib_min_step=0.001\n"
+        "  igm=none|constant|madau95|inoue14 (default inoue14)\n"
+        "  no_stellar no_dust no_nebular no_flux save_sed\n"
+        "  trim_filters filter_flambda filter_photons filter_normalize\n"
+        "  out=FILE verbose help list_bands[=regex]\n"
+        "  precision=fp32c|fp64   arithmetic mode (1e-5 / 1e-10 per band against the reference algorithm)\n"
+        "  gpus=N                 shard the galaxies over N GPUs of this box\n"
+        "Catalog generation options of egg-gencat (area, mmin, zmin, ...) are accepted and ignored: this program\n"
+        "replaces the block `if (!no_flux)` of egg-gencat only.\n";
+}
+
+struct Shard {
+    int device = 0;
+    size_t first = 0, count = 0;
+    int status = 0;
+    std::string msg;
+};
+
+} // namespace
+
+int main(int argc, char *argv[]) {
+    const Args a = read_args(argc, argv);
+    if (a.flag("help")) { print_help(); return 0; }
+    const bool verbose = a.flag("verbose");
+    const std::string share = with_slash(env_or("EGG_SHARE_DIR", EGG_SHARE_DIR));
+    const std::string fdir = with_slash(env_or("EGG_FILTERS_PATH", std::string(FILTER_DB_DIR).empty() ? share + "filter-db" : FILTER_DB_DIR));
+    const std::string filter_db_file = a.str("filter_db", fdir + "db.dat");
+    try {
+        if (a.has("list_bands")) return list_bands(a.str("list_bands"), filter_db_file);
+
+        // ---- options (names and defaults of src/egg-gencat.cpp:22-133)
+        const std::string igm = a.str("igm", "inoue14");
+        if (igm != "none" && igm != "constant" && igm != "madau95" && igm != "inoue14") { // :286-289
+            error("unknown IGM prescription '" + igm + "'");
+            error("possible values are: 'none', 'constant', 'madau95', or 'inoue14'");
+            return 1;
+        }
+        bool no_flux = a.flag("no_flux");
+        const bool no_stellar = a.flag("no_stellar"), no_dust = a.flag("no_dust"), no_nebular = a.flag("no_nebular");
+        if (no_dust && no_stellar) no_flux = true; // :247-249
+        const bool save_sed = a.flag("save_sed");
+        std::string out_file = a.str("out");
+        if (out_file.empty()) {
+            char buf[32];
+            const time_t t = time(nullptr);
+            strftime(buf, sizeof buf, "%Y%m%d", localtime(&t));
+            out_file = std::string("egg-") + buf + ".fits"; // :259-261
+        }
+        if (verbose) note("will save catalog in '" + out_file + "'");
+        const std::string input = a.str("input_props", a.str("input_cat"));
+        if (input.empty()) {
+            error("this program replaces the photometry stage of egg-gencat only (src/egg-gencat.cpp:2024-2240)");
+            error("pass input_props=<egg catalog> holding the per-galaxy columns; generating them (area=, mmin=, ...) is out of scope");
+            return 1;
+        }
+        for (const char *k : {"area", "mmin", "maglim", "zmin", "zmax", "seed", "ra0", "dec0", "mass_func", "no_pos", "no_clust"})
+            if (a.has(k) && verbose) note(std::string("option '") + k + "' only affects catalog generation and is ignored");
+        const std::vector<std::string> dflt_bands = {"vimos-u", "hst-f435w", "hst-f606w", "hst-f775w", "hst-f814w", "hst-f850lp",
+            "hst-f105w", "hst-f125w", "hst-f140w", "hst-f160w", "hawki-Ks", "spitzer-irac1", "spitzer-irac2", "spitzer-irac3",
+            "spitzer-irac4", "spitzer-irs16", "spitzer-mips24", "herschel-pacs70", "herschel-pacs100", "herschel-pacs160",
+            "herschel-spire250", "herschel-spire350", "herschel-spire500"}; // :125-130
+        const std::vector<std::string> bands = a.list("bands", dflt_bands), rfbands = a.list("rfbands", {});
+        const std::string ir_lib_file = a.str("ir_lib", share + "ir_lib_cs17.fits"); // :88
+        const std::string opt_lib_file = a.str("opt_lib", share + (igm == "constant" ? "opt_lib_fast.fits" : "opt_lib_fast_noigm.fits")); // :296-302
+        const std::string imf = a.str("opt_lib_imf", "salpeter");
+        const std::string precision = a.str("precision", "fp32c");
+        if (precision != "fp32c" && precision != "fp64") { error("precision must be fp32c or fp64"); return 1; }
+        const int gpus = std::max(1, (int)a.num("gpus", 1));
+
+        // ---- catalog
+        if (verbose) note("reading galaxy properties from '" + input + "'...");
+        fitscol::Table cat = fitscol::read_table(input);
+        auto need = [&](const char *name) -> const fitscol::Column & {
+            const fitscol::Column *c = cat.find(name);
+            if (!c) throw std::runtime_error(std::string("catalog '") + input + "' has no column " + name);
+            return *c;
+        };
+        const std::vector<float> z = fitscol::as_float(need("Z")), d = fitscol::as_float(need("D"));
+        const size_t ngal = z.size();
+        const std::vector<float> m2lcor = fitscol::as_float(need("M2LCOR"));
+        std::vector<float> m_disk, m_bulge, lir, fpah, mdust, igm_abs, vdisp, lld, llb, line_lambda;
+        std::vector<uint64_t> osd, osb, irs;
+        if (!no_stellar) {
+            m_disk = fitscol::as_float(need("M_DISK")); m_bulge = fitscol::as_float(need("M_BULGE"));
+            osd = fitscol::as_u64(need("OPT_SED_DISK")); osb = fitscol::as_u64(need("OPT_SED_BULGE"));
+        }
+        const bool cs17 = basename_of(ir_lib_file) == "ir_lib_cs17.fits"; // :401
+        if (!no_dust) {
+            irs = fitscol::as_u64(need("IR_SED"));
+            if (cs17) { fpah = fitscol::as_float(need("FPAH")); mdust = fitscol::as_float(need("MDUST")); }
+            else lir = fitscol::as_float(need("LIR"));
+        }
+        if (igm == "madau95" || igm == "inoue14") igm_abs = fitscol::as_float(need("IGM_ABS"));
+        bool nebular = !no_nebular;
+        if (nebular && !cat.find("LINE_LAMBDA")) {
+            error("the catalog has no emission line columns (LINE_LAMBDA, LINE_LUM_DISK, VDISP); pass no_nebular to ignore lines");
+            return 1;
+        }
+        if (nebular) {
+            line_lambda = fitscol::as_float(need("LINE_LAMBDA"));
+            vdisp = fitscol::as_float(need("VDISP"));
+            lld = fitscol::as_float(need("LINE_LUM_DISK"));
+            if (cat.find("LINE_LUM_BULGE")) llb = fitscol::as_float(need("LINE_LUM_BULGE"));
+            if (lld.size() != ngal * line_lambda.size()) { error("LINE_LUM_DISK is not [ngal, nline]"); return 1; }
+        }
+        for (const auto *v : {&d, &m2lcor})
+            if (v->size() != ngal) { error("catalog columns have inconsistent lengths"); return 1; }
+
+        if (no_flux) {
+            if (verbose) note("no_flux: writing the catalog unchanged");
+            fitscol::write_table(out_file, cat);
+            return 0;
+        }
+
+        // ---- filters and libraries (src/egg-gencat.cpp:316-327, 401-458)
+        if (verbose) note("initializing filters...");
+        const auto db = fitscol::read_filter_db(filter_db_file);
+        std::vector<Curve> fb, fr;
+        if (!get_filters(db, bands, fb) || !get_filters(db, rfbands, fr)) return 1;
+        if (verbose) note("initializing SED libraries...");
+        eggphot_libs L{};
+        std::vector<float> olam, osed;
+        std::vector<uint8_t> ouse;
+        std::vector<double> ilam, ised, ipah;
+        if (!no_stellar) {
+            fitscol::Table t = fitscol::read_table(opt_lib_file);
+            const fitscol::Column *cl = t.find("LAM"), *cs = t.find("SED"), *cu = t.find("USE");
+            if (!cl || !cs || !cu || cl->dims.size() != 3) { error("optical library '" + opt_lib_file + "' must hold LAM, SED [nuv][nvj][nlam] and USE"); return 1; }
+            olam = fitscol::as_float(*cl); osed = fitscol::as_float(*cs); ouse = fitscol::as_bool(*cu);
+            L.nuv = (uint32_t)cl->dims[0]; L.nvj = (uint32_t)cl->dims[1]; L.nopt = (uint32_t)cl->dims[2];
+            L.opt_lam = olam.data(); L.opt_sed = osed.data(); L.opt_use = ouse.data();
+        }
+        if (!no_dust) {
+            fitscol::Table t = fitscol::read_table(ir_lib_file);
+            const fitscol::Column *cl = t.find("LAM"), *cs = t.find(cs17 ? "DUST" : "SED"), *cp = t.find("PAH");
+            if (!cl || !cs || (cs17 && !cp)) { error("missing LAM and/or SED columns in the IR library file"); return 1; } // :438-441
+            if (cs->dims.size() > 2) { error("IR library must contain either 1D or 2D columns LAM and SED"); return 1; }
+            ilam = fitscol::as_double(*cl); ised = fitscol::as_double(*cs);
+            if (cs17) ipah = fitscol::as_double(*cp);
+            L.ir_kind = cs17 ? EGGPHOT_IR_CS17 : EGGPHOT_IR_GENERIC;
+            L.nir_sed = cs->dims.size() == 2 ? (uint32_t)cs->dims[0] : 1;
+            L.nir = (uint32_t)cs->dims.back();
+            L.ir_lam = ilam.data(); L.ir_sed = ised.data(); L.ir_pah = cs17 ? ipah.data() : nullptr;
+        }
+        auto pack = [](const std::vector<Curve> &f, std::vector<uint32_t> &n, std::vector<const double *> &l, std::vector<const double *> &r) {
+            for (const Curve &c : f) { n.push_back((uint32_t)c.lam.size()); l.push_back(c.lam.data()); r.push_back(c.res.data()); }
+            return eggphot_filters{(uint32_t)f.size(), n.data(), l.data(), r.data()};
+        };
+        std::vector<uint32_t> nb_, nr_;
+        std::vector<const double *> lb_, rb_, lr_, rr_;
+        const eggphot_filters B = pack(fb, nb_, lb_, rb_), R = pack(fr, nr_, lr_, rr_);
+        eggphot_opts O{};
+        O.precision = precision == "fp64" ? EGGPHOT_FP64 : EGGPHOT_FP32C;
+        O.igm = igm.c_str();
+        O.no_stellar = no_stellar; O.no_dust = no_dust; O.no_nebular = !nebular;
+        O.opt_lib_imf = imf.c_str();
+        O.opt_lib_min_step = a.num("opt_lib_min_step", 0.001);
+        O.filter_flambda = a.flag("filter_flambda"); O.filter_photons = a.flag("filter_photons");
+        O.filter_normalize = a.flag("filter_normalize"); O.trim_filters = a.flag("trim_filters");
+        O.nline = (uint32_t)line_lambda.size(); O.line_lambda = line_lambda.data();
+
+        // ---- compute: one context (and host thread) per GPU, contiguous shards, no exchange between them
+        const size_t nband = fb.size(), nrf = fr.size();
+        std::vector<float> flux(ngal * nband), flux_disk(ngal * nband), flux_bulge(ngal * nband);
+        std::vector<float> rfmag(ngal * nrf), rfmag_disk(ngal * nrf), rfmag_bulge(ngal * nrf);
+        std::vector<uint32_t> order(nband), rforder(nrf);
+        std::vector<float> lambda(nband), rflambda(nrf);
+        if (verbose) note("computing fluxes" + std::string(nrf ? " and absolute magnitudes" : "") + " on " + std::to_string(gpus) + " GPU(s)...");
+        std::vector<Shard> shards(gpus);
+        std::vector<eggphot_ctx *> ctxs(gpus, nullptr);
+        auto galaxies = [&](size_t first) {
+            eggphot_galaxies G{};
+            auto off = [&](const std::vector<float> &v, size_t stride) { return v.empty() ? nullptr : v.data() + first * stride; };
+            auto offu = [&](const std::vector<uint64_t> &v) { return v.empty() ? nullptr : v.data() + first; };
+            G.z = off(z, 1); G.d = off(d, 1); G.m_disk = off(m_disk, 1); G.m_bulge = off(m_bulge, 1); G.m2lcor = off(m2lcor, 1);
+            G.opt_sed_disk = offu(osd); G.opt_sed_bulge = offu(osb); G.ir_sed = offu(irs);
+            G.lir = off(lir, 1); G.fpah = off(fpah, 1); G.mdust = off(mdust, 1); G.igm_abs = off(igm_abs, 3);
+            G.vdisp = off(vdisp, 1); G.line_lum_disk = off(lld, line_lambda.size()); G.line_lum_bulge = off(llb, line_lambda.size());
+            return G;
+        };
+        auto work = [&](int g) {
+            Shard &s = shards[g];
+            s.device = g;
+            s.first = ngal * (size_t)g / gpus;
+            s.count = ngal * (size_t)(g + 1) / gpus - s.first;
+            eggphot_opts Og = O;
+            Og.device = g;
+            s.status = eggphot_create(&L, &B, nrf ? &R : nullptr, &Og, &ctxs[g]);
+            if (s.status) { s.msg = ctxs[g] ? eggphot_last_error(ctxs[g]) : "allocation failed"; return; }
+            const eggphot_galaxies G = galaxies(s.first);
+            eggphot_outputs F{};
+            F.flux = flux.data() + s.first * nband; F.flux_disk = flux_disk.data() + s.first * nband; F.flux_bulge = flux_bulge.data() + s.first * nband;
+            if (nrf) { F.rfmag = rfmag.data() + s.first * nrf; F.rfmag_disk = rfmag_disk.data() + s.first * nrf; F.rfmag_bulge = rfmag_bulge.data() + s.first * nrf; }
+            s.status = eggphot_compute(ctxs[g], &G, s.count, &F);
+            if (s.status) s.msg = eggphot_last_error(ctxs[g]);
+        };
+        {
+            std::vector<std::thread> th;
+            for (int g = 1; g < gpus; ++g) th.emplace_back(work, g);
+            work(0);
+            for (auto &t : th) t.join();
+        }
+        for (const Shard &s : shards)
+            if (s.status) {
+                error("GPU " + std::to_string(s.device) + ": " + s.msg);
+                for (auto *c : ctxs) eggphot_destroy(c);
+                return 1;
+            }
+        eggphot_band_order(ctxs[0], 0, order.data(), lambda.data());
+        if (nrf) eggphot_band_order(ctxs[0], 1, rforder.data(), rflambda.data());
+
+        // ---- save_sed (src/egg-gencat.cpp:2059-2072, 2164-2236): all bulges, then all disks; lam then sed, f32
+        if (save_sed) {
+            const std::string seds_file = remove_extension(out_file) + "-seds.dat";
+            if (verbose) note("will save spectra in '" + seds_file + "'");
+            std::ofstream f(seds_file, std::ios::binary);
+            if (!f) { error("could not write '" + seds_file + "'"); return 1; }
+            std::vector<uint64_t> start[2] = {std::vector<uint64_t>(ngal, 0), std::vector<uint64_t>(ngal, 0)};
+            std::vector<uint64_t> nbyte[2] = {std::vector<uint64_t>(ngal, 0), std::vector<uint64_t>(ngal, 0)};
+            const eggphot_galaxies G = galaxies(0);
+            uint64_t pos = 0;
+            for (int comp = no_stellar ? 1 : 0; comp < 2; ++comp) { // bulge pass first (:2206-2212)
+                const size_t n = eggphot_sed_size(ctxs[0], comp), chunk = 4096;
+                std::vector<float> lam(chunk * n), sed(chunk * n);
+                for (size_t first = 0; first < ngal; first += chunk) {
+                    const size_t cnt = std::min(chunk, ngal - first);
+                    if (eggphot_get_seds(ctxs[0], &G, first, cnt, comp, lam.data(), sed.data())) {
+                        error(eggphot_last_error(ctxs[0]));
+                        return 1;
+                    }
+                    for (size_t k = 0; k < cnt; ++k) {
+                        f.write(reinterpret_cast<const char *>(lam.data() + k * n), (std::streamsize)(n * sizeof(float)));
+                        f.write(reinterpret_cast<const char *>(sed.data() + k * n), (std::streamsize)(n * sizeof(float)));
+                        start[comp][first + k] = pos;
+                        nbyte[comp][first + k] = 2 * n * sizeof(float);
+                        pos += 2 * n * sizeof(float);
+                    }
+                }
+            }
+            fitscol::Table lk;
+            std::vector<uint64_t> id(ngal);
+            if (const fitscol::Column *c = cat.find("ID")) id = fitscol::as_u64(*c);
+            else for (size_t i = 0; i < ngal; ++i) id[i] = i;
+            lk.set(fitscol::make_u64("ID", id));
+            lk.set(fitscol::make_u64("BULGE_START", start[0])); lk.set(fitscol::make_u64("BULGE_NBYTE", nbyte[0]));
+            lk.set(fitscol::make_u64("DISK_START", start[1])); lk.set(fitscol::make_u64("DISK_NBYTE", nbyte[1]));
+            lk.set(fitscol::make_u64("ELEM_SIZE", {sizeof(float)}));
+            fitscol::write_table(remove_extension(seds_file) + "-lookup.fits", lk);
+        }
+        for (auto *c : ctxs) eggphot_destroy(c);
+
+        // ---- output (src/egg-gencat.cpp:2249-2286): pass the catalog through, (re)write the flux groups
+        if (verbose) note("saving catalog...");
+        std::string cmd;
+        for (int i = 0; i < argc; ++i) cmd += std::string(i ? " " : "") + argv[i];
+        cat.set(fitscol::make_string("CMD", cmd));
+        const std::vector<long> d2 = {(long)ngal, (long)nband}, r2 = {(long)ngal, (long)nrf};
+        if (nband) {
+            std::vector<std::string> names;
+            for (uint32_t k : order) names.push_back(fb[k].name);
+            cat.set(fitscol::make_f32("FLUX", flux, d2)); cat.set(fitscol::make_f32("FLUX_DISK", flux_disk, d2));
+            cat.set(fitscol::make_f32("FLUX_BULGE", flux_bulge, d2));
+            cat.set(fitscol::make_strings("BANDS", names)); cat.set(fitscol::make_f32("LAMBDA", lambda));
+        }
+        if (nrf) {
+            std::vector<std::string> names;
+            for (uint32_t k : rforder) names.push_back(fr[k].name);
+            cat.set(fitscol::make_f32("RFMAG", rfmag, r2)); cat.set(fitscol::make_f32("RFMAG_DISK", rfmag_disk, r2));
+            cat.set(fitscol::make_f32("RFMAG_BULGE", rfmag_bulge, r2));
+            cat.set(fitscol::make_strings("RFBANDS", names)); cat.set(fitscol::make_f32("RFLAMBDA", rflambda));
+        }
+        fitscol::write_table(out_file, cat);
+        return 0;
+    } catch (const std::exception &e) {
+        error(e.what());
+        return 1;
+    }
+}

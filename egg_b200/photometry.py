@@ -157,6 +157,10 @@ class Photometry:
     def synchronize(self):
         self._check(self._L.eggphot_synchronize(self._ctx))
 
+    def sed_size(self, component):
+        """nodes of one component's SED ('bulge' | 'disk'): the length of each save_sed array."""
+        return int(self._L.eggphot_sed_size(self._ctx, {"bulge": 0, "disk": 1}[component]))
+
     def get_seds(self, gal, first, count, component):
         """save_sed payload (src/egg-gencat.cpp:2161-2179): (lam, sed) f32 [count][n], component 'bulge'|'disk'."""
         comp = {"bulge": 0, "disk": 1}[component]

@@ -1,0 +1,144 @@
+"""egg-gencat-b200, the stand-alone drop-in for the photometry stage (egg_b200/csrc/gencat_main.cpp).
+
+CPU tier: the command-line contract of egg-gencat that needs no device — `list_bands` against the
+reference's own documented output (KAT-1, doc/doc-egg-gencat.tex:32-55: this pins the C++ FITS
+reader and the reference-wavelength / FWHM rules of src/egg-gencat.cpp:195-199), user errors with
+exit code 1 (src/egg-gencat.cpp:286-289), and the loud failure without a GPU.
+GPU tier: a full run from FITS inputs to the FITS output column groups and the save_sed files."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+from egg_b200 import fitscol, synth
+from test_oracle_kat import KAT1
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "egg_b200", "egg-gencat-b200")
+
+
+def _need_cli():
+    if not os.path.exists(CLI):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "egg_b200", "csrc"), "-s", "all"])
+
+
+def _filter_db(tmp_path, names):
+    """A filter data base in the reference's layout (db.dat + one-row LAM/RES tables) from the packed curves."""
+    pack = synth.load_pack()
+    d = tmp_path / "filter-db"
+    (d / "f").mkdir(parents=True, exist_ok=True)
+    lines = []
+    for n in names:
+        lam, res = pack[f"filter/{n}/lam"], pack[f"filter/{n}/res"]  # original dtypes: four curves are f32 ('E')
+        fitscol.write_table(str(d / "f" / f"{n}.fits"), {"LAM": lam, "RES": res})
+        lines.append(f"{n}=f/{n}.fits")
+    (d / "db.dat").write_text("\n".join(lines) + "\n")
+    return str(d / "db.dat")
+
+
+def _run(*args):
+    return subprocess.run([CLI, *args], capture_output=True, text=True)
+
+
+def test_list_bands_reproduces_the_reference_manual(tmp_path):
+    _need_cli()
+    db = _filter_db(tmp_path, sorted(KAT1) + ["hst-f160w"])
+    for pattern, want in (("jwst-", [n for n in sorted(KAT1) if n.startswith("jwst-")]),
+                          ("-Ks", [n for n in sorted(KAT1) if n.endswith("-Ks")])):
+        r = _run(f"list_bands={pattern}", f"filter_db={db}")
+        assert r.returncode == 0, r.stderr
+        lines = r.stdout.strip().splitlines()
+        assert lines[0] == f"List of available bands (filter: '{pattern}'):"
+        got = {}
+        for ln in lines[1:]:
+            name = ln.split()[1]
+            got[name] = (ln.split("ref-lam = ")[1].split(" um")[0], ln.split("FWHM = ")[1].split(" um")[0])
+        assert sorted(got) == want
+        for n in want:  # the digits printed in doc/doc-egg-gencat.tex:32-55
+            assert got[n] == (f"{KAT1[n][0]:g}", f"{KAT1[n][1]:g}"), (n, got[n])
+        # sorted by instrument, then by reference wavelength (src/egg-gencat.cpp:208-215)
+        order = [ln.split()[1] for ln in lines[1:]]
+        key = [(n.split("-")[0], KAT1[n][0]) for n in order]
+        assert key == sorted(key)
+
+
+def test_user_errors_exit_1_like_the_reference(tmp_path):
+    _need_cli()
+    r = _run("igm=foo")
+    assert r.returncode == 1 and "unknown IGM prescription 'foo'" in r.stderr
+    r = _run("area=0.08", "mmin=9")
+    assert r.returncode == 1 and "input_props" in r.stderr          # catalog generation is out of scope
+    r = _run("list_bands", f"filter_db={tmp_path}/nope.dat")
+    assert r.returncode == 1 and "could not find filter database file" in r.stderr
+    assert _run("help").returncode == 0
+
+
+def _write_inputs(tmp_path, ngal=300, bands=synth.B4 + ["spitzer-irac1", "herschel-pacs100"], rf=synth.RF3):
+    L = cases.libs()
+    opt, ir = L["opt"], L["ce01"]
+    gal = synth.draw_galaxies(ngal, opt_lib=opt, ir_lib=ir, mmin=7.5, seed=5)
+    db = _filter_db(tmp_path, bands + rf)
+    fitscol.write_table(str(tmp_path / "opt_lib.fits"), {k.upper(): np.asarray(v) for k, v in opt.items()})
+    fitscol.write_table(str(tmp_path / "ir_lib_ce01.fits"), {"LAM": np.asarray(ir["lam"]), "SED": np.asarray(ir["sed"])})
+    cat = {"ID": np.arange(ngal, dtype=np.uint64), "RA": np.zeros(ngal), "DEC": np.zeros(ngal)}
+    for k in ("z", "d", "m_disk", "m_bulge", "m2lcor", "lir", "igm_abs", "vdisp", "line_lum_disk", "line_lum_bulge",
+              "opt_sed_disk", "opt_sed_bulge", "ir_sed"):
+        cat[k.upper()] = np.asarray(gal[k])
+    cat["LINES"] = np.array(synth.LINES)
+    cat["LINE_LAMBDA"] = synth.LINE_LAMBDA
+    fitscol.write_table(str(tmp_path / "cat.fits"), cat)
+    args = [f"input_props={tmp_path}/cat.fits", f"filter_db={db}", f"opt_lib={tmp_path}/opt_lib.fits",
+            f"ir_lib={tmp_path}/ir_lib_ce01.fits", "bands=[" + ",".join(bands) + "]", "rfbands=[" + ",".join(rf) + "]"]
+    return opt, ir, gal, bands, rf, args
+
+
+def test_without_a_gpu_the_stage_fails_loudly(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    _need_cli()
+    *_, args = _write_inputs(tmp_path, ngal=8)
+    r = _run(*args, f"out={tmp_path}/out.fits")
+    assert r.returncode == 1 and "CUDA" in r.stderr and not os.path.exists(tmp_path / "out.fits")
+
+
+@pytest.mark.gpu
+def test_full_run_writes_the_reference_column_groups(tmp_path):
+    import egg_b200
+    from oracle.oracle import Oracle
+    _need_cli()
+    opt, ir, gal, bands, rf, args = _write_inputs(tmp_path)
+    out = str(tmp_path / "out.fits")
+    r = _run(*args, f"out={out}", "save_sed", "verbose")
+    assert r.returncode == 0, r.stderr
+    t = fitscol.read_table(out)
+    names = list(t)
+    for grp in (["FLUX", "FLUX_DISK", "FLUX_BULGE", "BANDS", "LAMBDA"], ["RFMAG", "RFMAG_DISK", "RFMAG_BULGE", "RFBANDS", "RFLAMBDA"]):
+        assert [n for n in names if n in grp] == grp                 # src/egg-gencat.cpp:2266-2286
+    assert t["Z"].shape == (300,) and t["FLUX"].shape == (300, len(bands)) and t["FLUX"].dtype == np.float32
+    ph = egg_b200.Photometry(opt, ir, synth.get_filters(bands), synth.get_filters(rf), line_lambda=synth.LINE_LAMBDA)
+    py = ph.compute(gal)
+    assert list(t["BANDS"]) == [bands[k] for k in ph.band_order]     # sorted by reference wavelength (:367-378)
+    np.testing.assert_array_equal(t["LAMBDA"], ph.lambda_)
+    for k in ("FLUX", "FLUX_DISK", "FLUX_BULGE", "RFMAG", "RFMAG_DISK", "RFMAG_BULGE"):
+        np.testing.assert_array_equal(t[k], py[k.lower()])           # same library underneath: identical
+    ref = Oracle(opt, ir, synth.get_filters(bands), synth.get_filters(rf), line_lambda=synth.LINE_LAMBDA).compute(gal, f64=True)
+    assert cases.rel_err(t["FLUX_DISK"], ref["flux_disk"], 1e-5).max() < 2e-5
+    # save_sed: all bulges then all disks, lam then sed as f32 (src/egg-gencat.cpp:2164-2193, 2230-2235)
+    lk = fitscol.read_table(str(tmp_path / "out-seds-lookup.fits"))
+    raw = np.fromfile(str(tmp_path / "out-seds.dat"), dtype=np.float32)
+    nb, nd = ph.sed_size("bulge"), ph.sed_size("disk")
+    assert int(lk["ELEM_SIZE"].ravel()[0]) == 4 and raw.size == 300 * 2 * (nb + nd)
+    assert lk["BULGE_START"][0] == 0 and lk["DISK_START"][0] == 300 * 8 * nb and lk["DISK_NBYTE"][7] == 8 * nd
+    lam, sed = ph.get_seds(gal, 7, 1, "disk")
+    o = int(lk["DISK_START"][7]) // 4
+    np.testing.assert_array_equal(raw[o:o + nd], lam[0])
+    np.testing.assert_array_equal(raw[o + nd:o + 2 * nd], sed[0])
+    ph.close()
+    # two shards on one device count as two "GPUs" only where two exist; one GPU: gpus=1 is the same file
+    r = _run(*args, f"out={tmp_path}/fp64.fits", "precision=fp64")
+    assert r.returncode == 0, r.stderr
+    t64 = fitscol.read_table(str(tmp_path / "fp64.fits"))
+    assert cases.rel_err(t64["FLUX_DISK"], ref["flux_disk"], 1e-6).max() < 2e-7   # f32 column of the fp64 result
