@@ -72,43 +72,48 @@ struct GalScal {
     uint32_t row_b, row_d, row_i;
 };
 
-__device__ void gal_scalars(const FluxParams &p, uint64_t g, GalScal &s) {
-    const double z = __ldcs(p.z + g), d = __ldcs(p.d + g); // galaxy columns are read once: streaming loads
-    s.opz = 1.0 + z;
-    s.iopz = 1.0 / s.opz;
-    s.l2opz = (float)(log2(s.opz) * kLutPerOctave);
-    s.aflux = EGGPHOT_LSUN2UJY * (1.0 + z) / (d * d);
-    const float m2l = __ldcs(p.m2lcor + g);
+// The scalars of one galaxy in four independent pieces (one thread each in the flux kernel, so that the
+// double-precision log2 / exp10 / divisions of a batch run side by side): piece < 0 computes all of them.
+__device__ void gal_scalars(const FluxParams &p, uint64_t g, GalScal &s, int piece = -1) {
+    if (piece < 0 || piece == 0) {
+        const double z = __ldcs(p.z + g), d = __ldcs(p.d + g); // galaxy columns are read once: streaming loads
+        s.opz = 1.0 + z;
+        s.iopz = 1.0 / s.opz;
+        s.l2opz = (float)(log2(s.opz) * kLutPerOctave);
+        s.aflux = EGGPHOT_LSUN2UJY * (1.0 + z) / (d * d);
+    }
     // the reference passes the FLOAT difference m[i]-out.m2lcor[i] to e10 (src/egg-gencat.cpp:2106, 2114)
-    s.a_bulge = p.has_bulge ? exp10((double)(p.m_bulge[g] - m2l)) : 0.0;
-    s.a_disk = p.disk_mode != 2 ? exp10((double)(p.m_disk[g] - m2l)) : 0.0;
-    s.c1 = s.c2 = 0.0;
-    bool bad = false;
-    uint64_t ri = 0, rb = 0, rd = 0;
-    if (p.disk_mode != 1) {
-        ri = p.ir_sed[g];
-        if (ri >= p.nir_sed) { bad = true; ri = 0; }
-        if (p.ir_kind == EGGPHOT_IR_CS17) {
-            const double fp = p.fpah[g], md = p.mdust[g];
-            s.c1 = (1.0 - fp) * md;
-            s.c2 = fp * md;
-        } else {
-            s.c1 = p.lir[g];
+    if (piece < 0 || piece == 1) s.a_bulge = p.has_bulge ? exp10((double)(p.m_bulge[g] - __ldcs(p.m2lcor + g))) : 0.0;
+    if (piece < 0 || piece == 2) s.a_disk = p.disk_mode != 2 ? exp10((double)(p.m_disk[g] - __ldcs(p.m2lcor + g))) : 0.0;
+    if (piece < 0 || piece == 3) {
+        s.c1 = s.c2 = 0.0;
+        bool bad = false;
+        uint64_t ri = 0, rb = 0, rd = 0;
+        if (p.disk_mode != 1) {
+            ri = p.ir_sed[g];
+            if (ri >= p.nir_sed) { bad = true; ri = 0; }
+            if (p.ir_kind == EGGPHOT_IR_CS17) {
+                const double fp = p.fpah[g], md = p.mdust[g];
+                s.c1 = (1.0 - fp) * md;
+                s.c2 = fp * md;
+            } else {
+                s.c1 = p.lir[g];
+            }
         }
+        if (p.has_bulge) {
+            rb = p.opt_sed_bulge[g];
+            if (rb >= p.nopt_sed || !p.opt_use[rb]) { bad = true; rb = 0; }
+        }
+        if (p.disk_mode != 2) {
+            rd = p.opt_sed_disk[g];
+            if (rd >= p.nopt_sed || !p.opt_use[rd]) { bad = true; rd = 0; }
+        }
+        s.row_b = (uint32_t)rb; s.row_d = (uint32_t)rd; s.row_i = (uint32_t)ri;
+        if (p.apply_igm) { s.igm[0] = __ldcs(p.igm_abs + 3 * g); s.igm[1] = __ldcs(p.igm_abs + 3 * g + 1); s.igm[2] = __ldcs(p.igm_abs + 3 * g + 2); }
+        else s.igm[0] = s.igm[1] = s.igm[2] = 1.0f;
+        s.vdisp = p.nline ? (double)p.vdisp[g] : 0.0;
+        if (bad) atomicExch(p.error_flag, EGGPHOT_ERR_INDEX);
     }
-    if (p.has_bulge) {
-        rb = p.opt_sed_bulge[g];
-        if (rb >= p.nopt_sed || !p.opt_use[rb]) { bad = true; rb = 0; }
-    }
-    if (p.disk_mode != 2) {
-        rd = p.opt_sed_disk[g];
-        if (rd >= p.nopt_sed || !p.opt_use[rd]) { bad = true; rd = 0; }
-    }
-    s.row_b = (uint32_t)rb; s.row_d = (uint32_t)rd; s.row_i = (uint32_t)ri;
-    if (p.apply_igm) { s.igm[0] = __ldcs(p.igm_abs + 3 * g); s.igm[1] = __ldcs(p.igm_abs + 3 * g + 1); s.igm[2] = __ldcs(p.igm_abs + 3 * g + 2); }
-    else s.igm[0] = s.igm[1] = s.igm[2] = 1.0f;
-    s.vdisp = p.nline ? (double)p.vdisp[g] : 0.0;
-    if (bad) atomicExch(p.error_flag, EGGPHOT_ERR_INDEX);
 }
 
 // ---- small helpers ---------------------------------------------------------------------------------
@@ -304,10 +309,10 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
         const uint64_t g0 = batch * kBatch;
         const int ng = (int)min((uint64_t)kBatch, p.ngal - g0);
 
-        // ---- phase A1: per-galaxy scalars, one thread per galaxy
-        if (tid < ng) gal_scalars(p, g0 + tid, sc[tid]);
-        if (tid >= 32 && tid < 32 + kMaxGroups) item_ctr[tid - 32] = 0;
-        if (tid == 64) any_bulge_line = 0;
+        // ---- phase A1: per-galaxy scalars, four threads per galaxy (one per piece), spread over four warps
+        if ((tid & 31) < kBatch && (tid >> 5) < 4 && (tid & 31) < ng) gal_scalars(p, g0 + (tid & 31), sc[tid & 31], tid >> 5);
+        if (tid >= 128 && tid < 128 + kMaxGroups) item_ctr[tid - 128] = 0;
+        if (tid == 160) any_bulge_line = 0;
         for (int i = tid; i < ng * nbt * 2; i += NT) res[i] = 0.0;
         __syncthreads();
 
@@ -478,61 +483,55 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
         //      bulge SED resampled on the disk grid (the same piece-wise linear function; lets phase B serve both
         //      components from one set of weights), two nodes per lane, stored as {disk, bulge} pairs
         {
+            // a task = 64 consecutive nodes (two per lane) for up to four galaxies: the disk -> optical maps of the
+            // nodes are loaded once per task (they are most of what this phase reads, and L1 is too small to keep them)
             const real *ofrac = reinterpret_cast<const real *>(p.u_ofrac);
-            const int ncD = (nD + 63) >> 6;
-            for (int task = warp; task < ng * ncD; task += NW) {
-                const int gi = task / ncD, j0 = ((task - gi * ncD) << 6) + 2 * lane;
+            const int ncD = (nD + 63) >> 6, nq = (ng + 3) >> 2;
+            for (int task = warp; task < ncD * nq; task += NW) {
+                const int q = task / ncD, j0 = ((task - q * ncD) << 6) + 2 * lane;
                 if (j0 >= nD) continue;
-                const GalScal &s = sc[gi];
-                real *DU = scr + (size_t)gi * sstride;
-                real2 v;
-                if (p.disk_mode == 0) {
-                    const real2 o = __ldg(reinterpret_cast<const real2 *>(rO + (size_t)s.row_d * p.strideD + j0));
-                    const real2 i = __ldg(reinterpret_cast<const real2 *>(rI + (size_t)s.row_i * p.strideD + j0));
-                    const real a_d = (real)s.a_disk, c1 = (real)s.c1;
-                    v.x = a_d * o.x + c1 * i.x; v.y = a_d * o.y + c1 * i.y;
-                } else if (p.disk_mode == 1) {
-                    const real2 o = __ldg(reinterpret_cast<const real2 *>(rO + (size_t)s.row_d * p.strideD + j0));
-                    const real a_d = (real)s.a_disk;
-                    v.x = a_d * o.x; v.y = a_d * o.y;
-                } else {
-                    const real2 i = __ldg(reinterpret_cast<const real2 *>(rI + (size_t)s.row_i * p.strideD + j0));
-                    const real c1 = (real)s.c1;
-                    v.x = c1 * i.x; v.y = c1 * i.y;
-                }
-                if (p.disk_mode != 1 && cs17) {
-                    const real2 q = __ldg(reinterpret_cast<const real2 *>(rP + (size_t)s.row_i * p.strideD + j0));
-                    const real c2 = (real)s.c2;
-                    v.x += c2 * q.x; v.y += c2 * q.y;
-                }
-                if (p.apply_igm && j0 < p.igmD[3]) {
-                    const real g0f = s.igm[0], g1f = s.igm[1], g2f = s.igm[2];
-                    v.x *= igm_factor<real>(j0, p.igmD[0], p.igmD[1], p.igmD[2], p.igmD[3], g0f, g1f, g2f);
-                    v.y *= igm_factor<real>(j0 + 1, p.igmD[0], p.igmD[1], p.igmD[2], p.igmD[3], g0f, g1f, g2f);
-                }
-                real2 w;
-                w.x = real(0); w.y = real(0);
+                int2 o2 = make_int2(-1, -1);
+                uint32_t io = 0;
+                real2 fr = make_pair2(real(0), real(0));
                 if (p.has_bulge) {
-                    const real *SB = DU + 2 * p.strideD;
-                    const int2 o2 = __ldg(reinterpret_cast<const int2 *>(p.u_oleft + j0));
-                    const uint32_t io = __ldg(reinterpret_cast<const uint16_t *>(p.u_isopt + j0));
-                    const real2 fr = __ldg(reinterpret_cast<const real2 *>(ofrac + j0));
-                    if (o2.x >= 0) {
-                        w.x = SB[o2.x];
-                        if (!(io & 0xffu)) w.x = fma(fr.x, SB[o2.x + 1] - w.x, w.x);
-                    }
-                    if (o2.y >= 0) {
-                        w.y = SB[o2.y];
-                        if (!(io >> 8)) w.y = fma(fr.y, SB[o2.y + 1] - w.y, w.y);
-                    }
+                    o2 = __ldg(reinterpret_cast<const int2 *>(p.u_oleft + j0));
+                    io = __ldg(reinterpret_cast<const uint16_t *>(p.u_isopt + j0));
+                    fr = __ldg(reinterpret_cast<const real2 *>(ofrac + j0));
                 }
-                // the row stride is a multiple of four: node j0 + 1 <= stride - 1 always has room
-                if constexpr (sizeof(real) == 4) {
-                    *reinterpret_cast<float4 *>(DU + 2 * j0) = make_float4(v.x, w.x, v.y, w.y);
-                } else {
-                    real2 *dst = reinterpret_cast<real2 *>(DU) + j0;
-                    dst[0] = make_pair2(v.x, w.x);
-                    dst[1] = make_pair2(v.y, w.y);
+                const int ox = max(o2.x, 0), oy = max(o2.y, 0), ox1 = min(ox + 1, nB - 1), oy1 = min(oy + 1, nB - 1);
+                const bool igm_here = p.apply_igm && j0 < p.igmD[3];
+#pragma unroll 2
+                for (int gi = 4 * q; gi < min(4 * q + 4, ng); ++gi) {
+                    const GalScal &s = sc[gi];
+                    real *DU = scr + (size_t)gi * sstride;
+                    const real *SB = DU + 2 * p.strideD;
+                    real2 o = make_pair2(real(0), real(0)), i = o, pq = o;
+                    if (p.disk_mode != 2) o = __ldg(reinterpret_cast<const real2 *>(rO + (size_t)s.row_d * p.strideD + j0));
+                    if (p.disk_mode != 1) i = __ldg(reinterpret_cast<const real2 *>(rI + (size_t)s.row_i * p.strideD + j0));
+                    if (p.disk_mode != 1 && cs17) pq = __ldg(reinterpret_cast<const real2 *>(rP + (size_t)s.row_i * p.strideD + j0));
+                    // branch-free gather of the two optical nodes around each disk node (clamped: always in range)
+                    real bx0 = real(0), bx1 = real(0), by0 = real(0), by1 = real(0);
+                    if (p.has_bulge) { bx0 = SB[ox]; bx1 = SB[ox1]; by0 = SB[oy]; by1 = SB[oy1]; }
+                    const real a_d = (real)s.a_disk, c1 = (real)s.c1, c2 = (real)s.c2;
+                    real2 v;
+                    v.x = a_d * o.x + c1 * i.x; v.y = a_d * o.y + c1 * i.y; // absent terms are zero
+                    if (p.disk_mode != 1 && cs17) { v.x += c2 * pq.x; v.y += c2 * pq.y; }
+                    if (igm_here) {
+                        const real g0f = s.igm[0], g1f = s.igm[1], g2f = s.igm[2];
+                        v.x *= igm_factor<real>(j0, p.igmD[0], p.igmD[1], p.igmD[2], p.igmD[3], g0f, g1f, g2f);
+                        v.y *= igm_factor<real>(j0 + 1, p.igmD[0], p.igmD[1], p.igmD[2], p.igmD[3], g0f, g1f, g2f);
+                    }
+                    real2 w;
+                    w.x = o2.x < 0 ? real(0) : ((io & 0xffu) ? bx0 : fma(fr.x, bx1 - bx0, bx0));
+                    w.y = o2.y < 0 ? real(0) : ((io >> 8) ? by0 : fma(fr.y, by1 - by0, by0));
+                    // the row stride is a multiple of four: node j0 + 1 <= stride - 1 always has room
+                    if constexpr (sizeof(real) == 4) {
+                        *reinterpret_cast<float4 *>(DU + 2 * j0) = make_float4(v.x, w.x, v.y, w.y);
+                    } else {
+                        real2 *dst = reinterpret_cast<real2 *>(DU) + j0;
+                        dst[0] = make_pair2(v.x, w.x);
+                        dst[1] = make_pair2(v.y, w.y);
+                    }
                 }
             }
         }
