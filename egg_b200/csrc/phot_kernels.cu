@@ -259,6 +259,13 @@ __host__ __device__ inline SmemLayout smem_layout(const FluxParams &p) {
     return L;
 }
 
+// Optional per-phase cycle counters (build with -DEGG_PHASE_TIMING: thread 0 of CTAs 0 and 77 prints them)
+#ifdef EGG_PHASE_TIMING
+#define EGG_PHASE(tag) if (tid == 0) { const long long tn_ = clock64(); ph_t[PH_##tag] += tn_ - ph_last; ph_last = tn_; }
+#else
+#define EGG_PHASE(tag)
+#endif
+
 // ---- the kernel ------------------------------------------------------------------------------------
 // One persistent CTA carries a batch of kBatch galaxies through phases A (rest-frame SEDs into a
 // per-CTA global scratch that stays in L2), B (for each band group: tables -> shared memory by TMA,
@@ -304,6 +311,10 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
     uint32_t tab_phase = 0;
     int loaded = -1;
 
+#ifdef EGG_PHASE_TIMING
+    enum { PH_A1, PH_A2a_win, PH_Blines, PH_A2b, PH_A3lines, PH_TMA, PH_B, PH_C, PH_N };
+    long long ph_t[PH_N] = {0}, ph_last = clock64();
+#endif
     const uint64_t nbatch = (p.ngal + kBatch - 1) / kBatch;
     for (uint64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
         const uint64_t g0 = batch * kBatch;
@@ -315,6 +326,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
         if (tid == 160) any_bulge_line = 0;
         for (int i = tid; i < ng * nbt * 2; i += NT) res[i] = 0.0;
         __syncthreads();
+        EGG_PHASE(A1)
 
         // ---- phase A2a: bulge SEDs on their own grid (get_opt_sed + IGM, src/egg-gencat.cpp:708-712, 2122-2140).
         //      A warp takes 128 consecutive nodes of one galaxy at a time, four per lane.
@@ -400,6 +412,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
             if (!c && b0 <= b1) any_bulge_line = 1;
         }
         __syncthreads();
+        EGG_PHASE(A2a_win)
 
         // ---- phase A3: emission lines (add_emission_line, src/egg-gencat.cpp:2078-2095), one warp per (galaxy,
         //      component).  Lines are sorted by wavelength, so their node windows [b0, b1] are ordered as well.
@@ -477,6 +490,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
         if (any_bulge_line) { // block-uniform: written before the barrier above
             deposit_lines(0);
             __syncthreads();
+            EGG_PHASE(Blines)
         }
 
         // ---- phase A2b: disk SEDs (get_opt_sed / get_ir_sed / merge_add / IGM, src/egg-gencat.cpp:2104-2140) and the
@@ -536,9 +550,11 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
             }
         }
         __syncthreads();
+        EGG_PHASE(A2b)
         if (nline > 0 && p.line_lum_disk != nullptr) {
             deposit_lines(1);
             __syncthreads();
+            EGG_PHASE(A3lines)
         }
 
         // ---- phase B: band groups
@@ -560,6 +576,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                 mbar_wait(&bar_tab, tab_phase);
                 tab_phase ^= 1;
                 loaded = grp;
+                EGG_PHASE(TMA)
             }
             const int nband_items = nb * kBatch;
             const int nitems = nband_items + (grp == 0 ? nrf * ncomp * kBatch : 0);
@@ -661,6 +678,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                 }
             }
             __syncthreads(); // every item of the group is done; the table region may be overwritten
+            EGG_PHASE(B)
         }
 
         // ---- phase C: totals (src/egg-gencat.cpp:2238-2239) and coalesced stores
@@ -692,7 +710,13 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
             if (p.rfmag_bulge_f64) __stcs(p.rfmag_bulge_f64 + o, mg[0]);
         }
         __syncthreads(); // res / sc are rewritten by the next batch
+        EGG_PHASE(C)
     }
+#ifdef EGG_PHASE_TIMING
+    if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
+        printf("PHASES cta %d: A1 %lld A2a+win %lld bulge-lines %lld A2b %lld A3 %lld TMA %lld B %lld C %lld\n", (int)blockIdx.x, ph_t[PH_A1],
+               ph_t[PH_A2a_win], ph_t[PH_Blines], ph_t[PH_A2b], ph_t[PH_A3lines], ph_t[PH_TMA], ph_t[PH_B], ph_t[PH_C]);
+#endif
 }
 
 // ---- save_sed (src/egg-gencat.cpp:2161-2179): one CTA per galaxy, observed-frame lam and sed as f32 ----

@@ -19,8 +19,10 @@ prec = sys.argv[2] if len(sys.argv) > 2 else "fp32c"
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 opt, ir = synth.make_opt_lib(), synth.ce01_lib()
 gal = synth.draw_galaxies(n, opt_lib=opt, ir_lib=ir, mmin=7.5)
-bands = synth.get_filters(synth.B30)
-ph = egg_b200.Photometry(opt, ir, bands, line_lambda=synth.LINE_LAMBDA, precision=prec)
+bset = [b for b in synth.B30 if b not in os.environ.get("EGGPHOT_DROP_BANDS", "").split(",")]
+bands = synth.get_filters(bset)
+ph = egg_b200.Photometry(opt, ir, bands, line_lambda=synth.LINE_LAMBDA, precision=prec,
+                         smem_table_budget=int(os.environ.get("EGGPHOT_BUDGET", "0")))
 cols = ["z", "d", "m_disk", "m_bulge", "m2lcor", "lir", "igm_abs", "vdisp", "line_lum_disk", "line_lum_bulge",
         "opt_sed_disk", "opt_sed_bulge", "ir_sed"]
 dev = {k: torch.from_numpy(np.ascontiguousarray(gal[k]).view(np.int64) if gal[k].dtype == np.uint64
