@@ -210,6 +210,12 @@ __device__ __forceinline__ int find_cell_warp(const BandView<real> &b, double t,
     return c;
 }
 
+__device__ __forceinline__ float rcp_approx(float x) { // one MUFU.RCP, no range fix-ups
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // four consecutive elements of a 16-byte aligned row
 template <typename real> struct Quad { real v[4]; };
 __device__ __forceinline__ Quad<float> ldg4(const float *p) {
@@ -615,7 +621,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                         real dt, dto, gidx; // observed widths to the next disk / optical node; 1/dx in the mode's type
                         if constexpr (sizeof(real) == 4) {
                             gidx = (float)g.idx;
-                            dt = __fdividef(opzr, gidx);
+                            dt = opzr * rcp_approx(gidx); // 1/idx = x[j+1] - x[j]; inf at the grid's last node (unused there)
                             dto = __ldg(reinterpret_cast<const float *>(p.gridB) + jc) * opzr;
                         } else {
                             const GridBD gb = ldg_grid(reinterpret_cast<const GridBD *>(p.gridB) + jc);
@@ -632,7 +638,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                         const real sr = sd.x, dlr = sd.y;
                         double dlam = __shfl_down_sync(kFull, lam, 1) - lam;
                         if (j == b) dlam += asym_b1;
-                        const double E = (j >= jlo && j < jhi) ? dlam * g.idx : 0.0;
+                        const double E = dlam * g.idx; // 0 left of jlo and from jhi on: Lambda is 0 on both sides there
                         double Ep = __shfl_up_sync(kFull, E, 1);
                         if (j == b + 1) Ep -= tot0z;
                         const real W = (real)(E - Ep);
