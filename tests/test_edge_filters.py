@@ -1,0 +1,78 @@
+"""Awkward filters through the device algorithm: shapes that stress the cell lookup, the two-sided gauge and
+the window ends of the weights form (phot_core.cuh).  CPU tier: the host emulation (same tables, same
+arithmetic) against the oracle; GPU tier: the CUDA path against the oracle on the same inputs."""
+import numpy as np
+import pytest
+
+import cases
+import emul
+from egg_b200 import synth
+from oracle.oracle import Oracle
+
+
+def _edge_bands():
+    rng = np.random.default_rng(7)
+    bands = {}
+    # top-hat with two nodes (the `name:range:lo:hi` band of doc/doc-egg-gencat.tex:254): R jumps at both ends
+    bands["tophat2"] = (np.array([0.60, 0.75]), np.array([1.0 / 0.15, 1.0 / 0.15]))
+    # narrower than the SED spacing there (0.002 um): the window can be a single SED interval
+    bands["narrow"] = (np.array([1.2501, 1.2504, 1.2507, 1.2510]), np.array([0.0, 900.0, 1100.0, 0.0]))
+    # repeated wavelengths = jumps of the response (zero-width cells; the one-probe lookup must switch itself off)
+    lam = np.array([2.0, 2.1, 2.1, 2.3, 2.3, 2.5])
+    bands["jumps"] = (lam, np.array([0.0, 0.2, 1.0, 1.0, 0.3, 0.0]))
+    # wildly uneven sampling: 400 nodes in 1% of the span, 6 in the rest
+    lam = np.sort(np.concatenate([np.linspace(3.0, 4.5, 6), np.linspace(3.60, 3.615, 400)]))
+    bands["uneven"] = (lam, np.exp(-0.5 * ((lam - 3.6) / 0.4) ** 2) * (1 + 0.3 * np.sin(900 * lam)))
+    # far red leak 1e-7 of the peak, separated from the main lobe by zeros
+    lam = np.concatenate([np.linspace(0.40, 0.50, 60), np.linspace(0.52, 0.95, 30), np.linspace(0.96, 1.05, 40)])
+    res = np.concatenate([np.exp(-0.5 * ((lam[:60] - 0.45) / 0.02) ** 2), np.zeros(30), 1e-7 * np.ones(40)])
+    bands["redleak"] = (lam, res)
+    # small negative responses in noisy wings (six curves of the data base have them)
+    lam = np.linspace(5.0, 9.0, 333)
+    bands["negative"] = (lam, np.exp(-1.5 * (lam - 7) ** 2) - 0.02 + 0.03 * rng.standard_normal(333))
+    # finely sampled and wide: thousands of cells per SED interval in the far IR
+    lam = np.linspace(60.0, 240.0, 3500)
+    bands["fine_fir"] = (lam, np.clip(1 - ((lam - 150) / 85) ** 4, 0, None) * (1 + 0.1 * np.cos(lam)))
+    # reaches beyond the optical grid (160 um rest): bulge uncovered at low z, covered at high z
+    bands["edge160"] = (np.linspace(150.0, 400.0, 50), np.hanning(50) + 1e-3)
+    return bands
+
+
+def _inputs(ngal=48):
+    L = cases.libs()
+    gal = synth.draw_galaxies(ngal, opt_lib=L["opt"], ir_lib=L["ce01"], mmin=7.5, seed=23)
+    bands = _edge_bands()
+    return L["opt"], L["ce01"], gal, list(bands), [bands[k] for k in bands]
+
+
+def _check(out, ref, prec, names, order):
+    for k in ("flux_disk", "flux_bulge"):
+        e = cases.rel_err(out[k], ref[k], cases.FLOOR[prec])
+        worst = np.unravel_index(np.argmax(e), e.shape)
+        assert e.max() < cases.TOL[prec], f"{k} {prec}: {e.max():.2e} in band {names[order[worst[1]]]}"
+
+
+@pytest.mark.parametrize("prec", ["fp32c", "fp64"])
+@pytest.mark.parametrize("opts", [{}, {"igm": "none", "no_nebular": True}, {"trim_filters": True, "filter_normalize": True}])
+def test_device_algorithm_on_awkward_filters(prec, opts):
+    opt, ir, gal, names, bands = _inputs()
+    O = Oracle(opt, ir, bands, line_lambda=synth.LINE_LAMBDA, **opts)
+    ref = O.compute(gal, f64=True)
+    out = emul.compute(opt, ir, bands, [], gal, line_lambda=synth.LINE_LAMBDA, precision=prec, **opts)
+    assert list(out["band_order"]) == list(O.band_order)
+    _check(out, ref, prec, names, list(O.band_order))
+    # every band is exercised: somewhere the disk has flux in it
+    assert (np.abs(ref["flux_disk"]).max(axis=0) > 0).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["fp32c", "fp64"])
+def test_cuda_on_awkward_filters(prec):
+    import egg_b200
+    opt, ir, gal, names, bands = _inputs(ngal=130)
+    O = Oracle(opt, ir, bands, line_lambda=synth.LINE_LAMBDA)
+    ref = O.compute(gal, f64=True)
+    ph = egg_b200.Photometry(opt, ir, bands, line_lambda=synth.LINE_LAMBDA, precision=prec)
+    out = ph.compute(gal, f64=True)
+    ph.close()
+    _check({k: out[k + "_f64"] for k in ("flux_disk", "flux_bulge")}, ref, prec, names, list(O.band_order))
