@@ -177,33 +177,32 @@ template <typename real> __device__ __forceinline__ CompSum<real> warp_reduce(Co
 }
 
 // find_cell (phot_core.cuh) for a full warp; also returns the node position, slope and width of the cell found.
-// When the band's buckets are narrower than its cells (one_probe) the cell is the bucket's or the next one, told
-// by the width of the first.  Otherwise the forward scan runs as a warp-uniform loop on a vote instead of a
+// When the band's buckets are narrower than its cells (one_probe) the cell is the bucket's or the next one: fp32
+// reads that off the bucket record, fp64 probes the next node position.  Otherwise the forward scan runs as a warp-uniform loop on a vote instead of a
 // per-lane data-dependent loop: the warp executes the longest lane's scan either way, and the lanes provably
 // stay converged for the shuffles that follow (with a per-lane loop nvcc 12.9 emitted neither a reconvergence
 // barrier after it nor a WARPSYNC before the shuffles, and lanes read stale registers).
 template <typename real>
 __device__ __forceinline__ int find_cell_warp(const BandView<real> &b, double t, double &fcell, Pair2<real> &sd) {
-    int k = (int)((float)(t - b.f_first) * b.bkt_inv_w);
-    k = max(0, min(k, b.nbkt - 1));
-    int c = b.bkt[k];
+    int c;
     if (b.one_probe) {
-        int cs = cell_slot(c);
-        fcell = b.f[cs];
-        sd = b.sdl[cs];
-        // (real): in fp32 a node within float rounding of a cell boundary may take either cell; Lambda is
-        // continuous there and the error is far below the mode's resolution
-        if ((real)(t - fcell) >= sd.y) {
-            cs = cell_slot(++c);
-            fcell = b.f[cs];
-            sd = b.sdl[cs];
+        if constexpr (sizeof(real) == 4) {
+            c = find_cell_quick(b, t); // the bucket record alone tells the cell (phot_core.cuh)
+        } else {
+            int k = (int)((float)(t - b.f_first) * b.bkt_inv_w);
+            k = max(0, min(k, b.nbkt - 1));
+            c = (int)(b.bkt[k] & 0xffffu);
+            c += t >= b.f[cell_slot(c + 1)] ? 1 : 0;
         }
-        return c;
-    }
-    bool up = t >= b.f[cell_slot(c + 1)];
-    while (__any_sync(kFull, up)) {
-        c += up ? 1 : 0;
-        up = t >= b.f[cell_slot(c + 1)];
+    } else {
+        int k = (int)((float)(t - b.f_first) * b.bkt_inv_w);
+        k = max(0, min(k, b.nbkt - 1));
+        c = (int)(b.bkt[k] & 0xffffu);
+        bool up = t >= b.f[cell_slot(c + 1)];
+        while (__any_sync(kFull, up)) {
+            c += up ? 1 : 0;
+            up = t >= b.f[cell_slot(c + 1)];
+        }
     }
     fcell = b.f[cell_slot(c)];
     sd = b.sdl[cell_slot(c)];
@@ -613,19 +612,35 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                     real accd = real(0), accb = real(0);
                     // lane l of a pass sits on node jb + l; lanes 1..30 own their node, lanes 0 and 31 only supply
                     // their neighbours' Lambda / E
+                    // the node data of the next pass are requested before this pass's arithmetic: they come from L2
+                    // (grid arrays, scratch) and their latency would otherwise head every pass's dependency chain
+                    struct NodeIn { GridA g; real2 su; real dxo_or_dx, dxo; };
+                    auto fetch = [&](int jb_, NodeIn &n) {
+                        const int jc_ = min(max(jb_ + lane, jlo), jhi);
+                        n.g = ldg_grid(gridA + jc_);
+                        n.su = DU[jc_];
+                        if constexpr (sizeof(real) == 4) {
+                            n.dxo = __ldg(reinterpret_cast<const float *>(p.gridB) + jc_);
+                            n.dxo_or_dx = real(0);
+                        } else {
+                            const GridBD gb = ldg_grid(reinterpret_cast<const GridBD *>(p.gridB) + jc_);
+                            n.dxo_or_dx = gb.dx; n.dxo = gb.dxo;
+                        }
+                    };
+                    NodeIn cur, nxt;
+                    fetch(jlo - 1, cur);
                     for (int jb = jlo - 1; jb < jhi; jb += 30) {
                         const int j = jb + lane;
-                        const int jc = min(max(j, jlo), jhi);
-                        const GridA g = ldg_grid(gridA + jc);
-                        const real2 su = DU[jc];
+                        if (jb + 30 < jhi) fetch(jb + 30, nxt);
+                        const GridA g = cur.g;
+                        const real2 su = cur.su;
                         real dt, dto, gidx; // observed widths to the next disk / optical node; 1/dx in the mode's type
                         if constexpr (sizeof(real) == 4) {
                             gidx = (float)g.idx;
                             dt = opzr * rcp_approx(gidx); // 1/idx = x[j+1] - x[j]; inf at the grid's last node (unused there)
-                            dto = __ldg(reinterpret_cast<const float *>(p.gridB) + jc) * opzr;
+                            dto = cur.dxo * opzr;
                         } else {
-                            const GridBD gb = ldg_grid(reinterpret_cast<const GridBD *>(p.gridB) + jc);
-                            gidx = g.idx; dt = gb.dx * opzr; dto = gb.dxo * opzr;
+                            gidx = g.idx; dt = cur.dxo_or_dx * opzr; dto = cur.dxo * opzr;
                         }
                         const double t = fma(opz, g.x, -bv.fc);
                         double fcell;
@@ -651,6 +666,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                             const real gBp = __shfl_up_sync(kFull, gB, 1);
                             accb = fma(su.y, own ? fma(real(0.5), gB - gBp, W) : real(0), accb);
                         }
+                        cur = nxt;
                     }
                     const double totd = warp_total((double)accd);
                     const double totb = bulge_on ? warp_total((double)accb) : 0.0;
