@@ -114,7 +114,7 @@ template <typename real> struct BandView {
     const uint32_t *bkt;
     double fc, f_first, f_split, tot0, asym0;
     float bkt_inv_w;
-    int n, nbkt;
+    int n, nbkt, split;
     bool one_probe;
 };
 template <typename real> EGG_HD void make_band_view(const uint8_t *blob, const BandHeader &h, BandView<real> &v) {
@@ -128,6 +128,7 @@ template <typename real> EGG_HD void make_band_view(const uint8_t *blob, const B
     v.bkt_inv_w = h.bkt_inv_w;
     v.n = (int)h.n; v.nbkt = (int)h.nbkt;
     v.one_probe = (h.split >> 31) != 0;
+    v.split = (int)(h.split & 0x7fffffffu);
 }
 
 // Filter cell of the centred position t, f_first <= t: the largest c with f_c <= t.  bkt[k] holds the last node
@@ -144,6 +145,8 @@ template <typename real> EGG_HD int find_cell_scan(const BandView<real> &b, doub
 // cell is known without reading any node position.  The position inside the bucket is formed in float: a node
 // within ~1e-4 of a cell width of a filter node may take the neighbouring cell, where Lambda's quadratic is
 // continued past its knot; Lambda is continuous across knots and the effect on a weight is < 1e-7 of it.
+// The one knot where that does not hold is the split node (the gauge changes there): keep_gauge() below pins
+// the side to the exact decision made when the window was laid out.
 EGG_HD int find_cell_quick(const BandView<float> &b, double t) {
     const float kf = (float)(t - b.f_first) * b.bkt_inv_w;
     int k = (int)kf;
@@ -155,6 +158,12 @@ EGG_HD int find_cell_quick(const BandView<float> &b, double t) {
 }
 EGG_HD int find_cell(const BandView<float> &b, double t) { return b.one_probe ? find_cell_quick(b, t) : find_cell_scan(b, t); }
 EGG_HD int find_cell(const BandView<double> &b, double t) { return find_cell_scan(b, t); }
+// A node left of the band's split node (j <= b, decided in double when the window was laid out) must use a
+// left-gauge cell, every other node a right-gauge cell: the table values of the two sides differ by asym(t).
+EGG_HD int keep_gauge(int c, bool left_of_split, int split) {
+    const int l = c < split - 1 ? c : split - 1;
+    return left_of_split ? (l > 0 ? l : 0) : (c > split ? c : split);
+}
 
 // Lambda(t) in cell c and the offset u of t inside it.
 template <typename real> EGG_HD double lambda_in_cell(const BandView<real> &b, int c, double t, double &u) {

@@ -183,7 +183,7 @@ template <typename real> __device__ __forceinline__ CompSum<real> warp_reduce(Co
 // stay converged for the shuffles that follow (with a per-lane loop nvcc 12.9 emitted neither a reconvergence
 // barrier after it nor a WARPSYNC before the shuffles, and lanes read stale registers).
 template <typename real>
-__device__ __forceinline__ int find_cell_warp(const BandView<real> &b, double t, double &fcell, Pair2<real> &sd) {
+__device__ __forceinline__ int find_cell_warp(const BandView<real> &b, double t, bool left_of_split, double &fcell, Pair2<real> &sd) {
     int c;
     if (b.one_probe) {
         if constexpr (sizeof(real) == 4) {
@@ -204,6 +204,7 @@ __device__ __forceinline__ int find_cell_warp(const BandView<real> &b, double t,
             up = t >= b.f[cell_slot(c + 1)];
         }
     }
+    c = keep_gauge(c, left_of_split, b.split); // exact at the split node whatever the lookup's rounding
     fcell = b.f[cell_slot(c)];
     sd = b.sdl[cell_slot(c)];
     return c;
@@ -645,7 +646,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                         const double t = fma(opz, g.x, -bv.fc);
                         double fcell;
                         Pair2<real> sd;
-                        const int cs = cell_slot(find_cell_warp<real>(bv, t, fcell, sd));
+                        const int cs = cell_slot(find_cell_warp<real>(bv, t, j <= b, fcell, sd));
                         const bool inner = j > jlo && j < jhi;
                         const double u = t - fcell;
                         const double lam = inner ? fma(u, fma(u, (double)bv.hr[cs], bv.k0[cs]), bv.lam[cs]) : 0.0; // 0 at both window ends

@@ -154,3 +154,15 @@ def test_full_size_properties():
     # m_bulge - m2lcor is formed in f32 (src/egg-gencat.cpp:2106): +1 can move it by one ulp of ~10 -> 2.2e-6 in 10^m
     assert np.abs(ratio / 10.0 - 1.0).max() < 5e-6
     ph.close()
+
+
+@pytest.mark.parametrize("name", ["b30_rf3_defaults", "b4_chabrier_flags"])
+def test_large_sample_has_no_outliers(name):
+    """4000 galaxies per case, both modes: rare lookup events (a node on a filter node, on the split node, on a
+    bucket edge) show up only in large samples (tools/parity_report.py is the same check over every case)."""
+    c = cases.make(name, ngal=4000, seed=77)
+    ref = Oracle(c["opt"], c["ir"], c["bands"], c["rfbands"], line_lambda=c["lines"], **c["opts"]).compute(c["gal"], f64=True)
+    for prec in ("fp32c", "fp64"):
+        out = _run(c, prec)
+        for k in ("flux_disk", "flux_bulge"):
+            assert cases.rel_err(out[k + "_f64"], ref[k], cases.FLOOR[prec]).max() < cases.TOL[prec], (prec, k)
