@@ -68,9 +68,7 @@ namespace eggphot {
 //   hr[n]    real    R_c / 2 (0 in the open cell)
 //   sdl[n]   real x2 slope of R in the cell (0 in zero-width cells and in the open cell), cell width (huge in the
 //                    open cell)
-//   bkt[nbkt] uint32 low half: last node at or below the start of the bucket; high half: where inside the bucket
-//                    the next node sits, in 1/65535 of the bucket width (0xffff: no node inside), meaningful when
-//                    the buckets are narrower than every cell ("one probe")
+//   bkt[nbkt] uint16 last node at or below the start of each bucket
 // The per-cell arrays are stored with one padding slot after every 16 entries (cell c lives in slot
 // c + c/16): lanes on every 2nd / 4th / ... cell (a filter sampled more finely than the SED) then fall on
 // distinct banks instead of colliding every 16 cells.
@@ -111,10 +109,10 @@ template <typename real> struct BandView {
     const double *f, *lam, *k0;
     const real *hr;
     const Pair2<real> *sdl;
-    const uint32_t *bkt;
+    const uint16_t *bkt;
     double fc, f_first, f_split, tot0, asym0;
     float bkt_inv_w;
-    int n, nbkt, split;
+    int n, nbkt;
     bool one_probe;
 };
 template <typename real> EGG_HD void make_band_view(const uint8_t *blob, const BandHeader &h, BandView<real> &v) {
@@ -123,46 +121,27 @@ template <typename real> EGG_HD void make_band_view(const uint8_t *blob, const B
     v.k0 = reinterpret_cast<const double *>(blob + h.k0_off);
     v.hr = reinterpret_cast<const real *>(blob + h.hr_off);
     v.sdl = reinterpret_cast<const Pair2<real> *>(blob + h.sdl_off);
-    v.bkt = reinterpret_cast<const uint32_t *>(blob + h.bkt_off);
+    v.bkt = reinterpret_cast<const uint16_t *>(blob + h.bkt_off);
     v.fc = h.fc; v.f_first = h.f_first; v.f_split = h.f_split; v.tot0 = h.tot0; v.asym0 = h.asym0;
     v.bkt_inv_w = h.bkt_inv_w;
     v.n = (int)h.n; v.nbkt = (int)h.nbkt;
     v.one_probe = (h.split >> 31) != 0;
-    v.split = (int)(h.split & 0x7fffffffu);
 }
 
-// Filter cell of the centred position t, f_first <= t: the largest c with f_c <= t.  bkt[k] holds the last node
-// at or below the start of bucket k and the bucket index never overshoots (the table is built against slightly
-// lowered bucket edges), so a forward scan settles it; the sentinel f[n] = +inf ends the scan in the open cell.
-template <typename real> EGG_HD int find_cell_scan(const BandView<real> &b, double t) {
+// Filter cell of the centred position t, f_first <= t: the largest c with f_c <= t, decided in double in both
+// modes.  (Which side of a filter node an SED node falls on must be exact: the split node separates the two
+// gauges, and next to a steep filter edge a node one cell off would weigh a bright SED with the wrong slope.
+// A float decision was tried: 1 entry in 1e5 off by 5e-4.)  bkt[k] holds the last node at or below the start of
+// bucket k and the bucket index never overshoots (the table is built against slightly lowered bucket edges), so
+// a forward scan settles it; the sentinel f[n] = +inf ends the scan in the open cell.  When the buckets are
+// narrower than every cell (one_probe) the scan is a single comparison.
+template <typename real> EGG_HD int find_cell(const BandView<real> &b, double t) {
     int k = (int)((float)(t - b.f_first) * b.bkt_inv_w);
     k = k < 0 ? 0 : (k > b.nbkt - 1 ? b.nbkt - 1 : k);
-    int c = (int)(b.bkt[k] & 0xffffu);
+    int c = b.bkt[k];
+    if (b.one_probe) return c + (t >= b.f[cell_slot(c + 1)] ? 1 : 0);
     while (t >= b.f[cell_slot(c + 1)]) ++c;
     return c;
-}
-// The fp32 mode's lookup in a one-probe band: the bucket record itself says where its (only) node sits, so the
-// cell is known without reading any node position.  The position inside the bucket is formed in float: a node
-// within ~1e-4 of a cell width of a filter node may take the neighbouring cell, where Lambda's quadratic is
-// continued past its knot; Lambda is continuous across knots and the effect on a weight is < 1e-7 of it.
-// The one knot where that does not hold is the split node (the gauge changes there): keep_gauge() below pins
-// the side to the exact decision made when the window was laid out.
-EGG_HD int find_cell_quick(const BandView<float> &b, double t) {
-    const float kf = (float)(t - b.f_first) * b.bkt_inv_w;
-    int k = (int)kf;
-    k = k < 0 ? 0 : (k > b.nbkt - 1 ? b.nbkt - 1 : k);
-    const uint32_t rec = b.bkt[k];
-    const float frac = kf - (float)k;
-    const uint32_t q = frac > 0.0f ? (uint32_t)(frac * 65535.0f) : 0u;
-    return (int)(rec & 0xffffu) + (q >= (rec >> 16) ? 1 : 0);
-}
-EGG_HD int find_cell(const BandView<float> &b, double t) { return b.one_probe ? find_cell_quick(b, t) : find_cell_scan(b, t); }
-EGG_HD int find_cell(const BandView<double> &b, double t) { return find_cell_scan(b, t); }
-// A node left of the band's split node (j <= b, decided in double when the window was laid out) must use a
-// left-gauge cell, every other node a right-gauge cell: the table values of the two sides differ by asym(t).
-EGG_HD int keep_gauge(int c, bool left_of_split, int split) {
-    const int l = c < split - 1 ? c : split - 1;
-    return left_of_split ? (l > 0 ? l : 0) : (c > split ? c : split);
 }
 
 // Lambda(t) in cell c and the offset u of t inside it.

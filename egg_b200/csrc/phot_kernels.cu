@@ -176,37 +176,22 @@ template <typename real> __device__ __forceinline__ CompSum<real> warp_reduce(Co
     return a;
 }
 
-// find_cell (phot_core.cuh) for a full warp; also returns the node position, slope and width of the cell found.
-// When the band's buckets are narrower than its cells (one_probe) the cell is the bucket's or the next one: fp32
-// reads that off the bucket record, fp64 probes the next node position.  Otherwise the forward scan runs as a warp-uniform loop on a vote instead of a
-// per-lane data-dependent loop: the warp executes the longest lane's scan either way, and the lanes provably
-// stay converged for the shuffles that follow (with a per-lane loop nvcc 12.9 emitted neither a reconvergence
-// barrier after it nor a WARPSYNC before the shuffles, and lanes read stale registers).
+// find_cell (phot_core.cuh) for a full warp.  When the band's buckets are narrower than its cells one comparison
+// settles it; otherwise the forward scan runs as a warp-uniform loop on a vote instead of a per-lane
+// data-dependent loop: the warp executes the longest lane's scan either way, and the lanes provably stay
+// converged for the shuffles that follow (with a per-lane loop nvcc 12.9 emitted neither a reconvergence barrier
+// after it nor a WARPSYNC before the shuffles, and lanes read stale registers).
 template <typename real>
-__device__ __forceinline__ int find_cell_warp(const BandView<real> &b, double t, bool left_of_split, double &fcell, Pair2<real> &sd) {
-    int c;
-    if (b.one_probe) {
-        if constexpr (sizeof(real) == 4) {
-            c = find_cell_quick(b, t); // the bucket record alone tells the cell (phot_core.cuh)
-        } else {
-            int k = (int)((float)(t - b.f_first) * b.bkt_inv_w);
-            k = max(0, min(k, b.nbkt - 1));
-            c = (int)(b.bkt[k] & 0xffffu);
-            c += t >= b.f[cell_slot(c + 1)] ? 1 : 0;
-        }
-    } else {
-        int k = (int)((float)(t - b.f_first) * b.bkt_inv_w);
-        k = max(0, min(k, b.nbkt - 1));
-        c = (int)(b.bkt[k] & 0xffffu);
-        bool up = t >= b.f[cell_slot(c + 1)];
-        while (__any_sync(kFull, up)) {
-            c += up ? 1 : 0;
-            up = t >= b.f[cell_slot(c + 1)];
-        }
+__device__ __forceinline__ int find_cell_warp(const BandView<real> &b, double t) {
+    int k = (int)((float)(t - b.f_first) * b.bkt_inv_w);
+    k = max(0, min(k, b.nbkt - 1));
+    int c = b.bkt[k];
+    bool up = t >= b.f[cell_slot(c + 1)];
+    if (b.one_probe) return c + (up ? 1 : 0);
+    while (__any_sync(kFull, up)) {
+        c += up ? 1 : 0;
+        up = t >= b.f[cell_slot(c + 1)];
     }
-    c = keep_gauge(c, left_of_split, b.split); // exact at the split node whatever the lookup's rounding
-    fcell = b.f[cell_slot(c)];
-    sd = b.sdl[cell_slot(c)];
     return c;
 }
 
@@ -644,11 +629,10 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                             gidx = g.idx; dt = cur.dxo_or_dx * opzr; dto = cur.dxo * opzr;
                         }
                         const double t = fma(opz, g.x, -bv.fc);
-                        double fcell;
-                        Pair2<real> sd;
-                        const int cs = cell_slot(find_cell_warp<real>(bv, t, j <= b, fcell, sd));
+                        const int cs = cell_slot(find_cell_warp<real>(bv, t));
+                        const Pair2<real> sd = bv.sdl[cs];
                         const bool inner = j > jlo && j < jhi;
-                        const double u = t - fcell;
+                        const double u = t - bv.f[cs];
                         const double lam = inner ? fma(u, fma(u, (double)bv.hr[cs], bv.k0[cs]), bv.lam[cs]) : 0.0; // 0 at both window ends
                         const real ur = inner ? (real)u : real(0);
                         const real sr = sd.x, dlr = sd.y;

@@ -61,7 +61,7 @@ struct FilterCellD {
 struct BandTableD {
     BandHeader h{};
     std::vector<FilterCellD> cells; // n + 1 records: cells 0..n-2, the open cell n-1, the sentinel n
-    std::vector<uint32_t> bkt;
+    std::vector<uint16_t> bkt;
 };
 
 Status build_band_table(const Filter &f, uint32_t out_col, int bucket_factor, BandTableD &t) {
@@ -170,14 +170,7 @@ Status build_band_table(const Filter &f, uint32_t out_col, int bucket_factor, Ba
         // k / bkt_inv_w * (1 - 2^-22): nodes up to that (slightly lowered) edge can never overshoot t
         const double edge = t.h.f_first + (t.h.bkt_inv_w > 0 ? (double)k / (double)t.h.bkt_inv_w * (1.0 - 2.4e-7) : 0.0);
         while (i + 1 < n && t.cells[i + 1].f <= edge) ++i;
-        // where the next node sits inside the bucket (true, not lowered, bucket edges), see find_cell_quick
-        uint32_t q = 0xffffu;
-        if (t.h.bkt_inv_w > 0 && i + 1 < n) {
-            const double w = 1.0 / (double)t.h.bkt_inv_w, lo = t.h.f_first + k * w;
-            const double pos = (t.cells[i + 1].f - lo) / w;
-            if (pos < 1.0) q = (uint32_t)std::min(65534.0, std::max(0.0, std::ceil(pos * 65535.0)));
-        }
-        t.bkt[k] = (uint32_t)i | (q << 16);
+        t.bkt[k] = (uint16_t)i;
     }
     return Status();
 }
@@ -186,9 +179,9 @@ size_t up16(size_t v) { return (v + 15) & ~size_t(15); }
 
 size_t band_bytes(const BandTableD &t, int precision) {
     const size_t n = t.h.n, rs = precision == EGGPHOT_FP64 ? 8 : 4;
-    if (n == 0) return up16(t.bkt.size() * sizeof(uint32_t));
+    if (n == 0) return up16(t.bkt.size() * sizeof(uint16_t));
     const size_t sf = cell_slot((int)n) + 1, sc = cell_slot((int)n - 1) + 1; // padded slots (phot_core.cuh)
-    return up16(sf * 8) + 2 * up16(sc * 8) + up16(sc * rs) + up16(sc * 2 * rs) + up16(t.bkt.size() * sizeof(uint32_t));
+    return up16(sf * 8) + 2 * up16(sc * 8) + up16(sc * rs) + up16(sc * 2 * rs) + up16(t.bkt.size() * sizeof(uint16_t));
 }
 
 template <typename T, typename Get> uint32_t append_array(std::vector<uint8_t> &blob, size_t count, Get get) {
@@ -229,7 +222,7 @@ void append_band(std::vector<uint8_t> &blob, size_t header_pos, const BandTableD
             h.sdl_off = append_cells<float>(blob, n, 2, [&](size_t i, int w) { return w ? c[i].dl : c[i].s; });
         }
     }
-    h.bkt_off = append_array<uint32_t>(blob, t.bkt.size(), [&](size_t i) { return t.bkt[i]; });
+    h.bkt_off = append_array<uint16_t>(blob, t.bkt.size(), [&](size_t i) { return t.bkt[i]; });
     align16(blob);
     std::memcpy(blob.data() + header_pos, &h, sizeof(h));
 }

@@ -135,7 +135,7 @@ void run(const Prepared &P, const eggphot_galaxies &G, size_t ngal, double *fd, 
                         std::vector<real> gD(N, real(0)), gB(N, real(0));
                         for (int j = jlo + 1; j < jhi; ++j) {
                             const double t = std::fma(opz, gr.x[j], -bv.fc);
-                            const int c = keep_gauge(find_cell(bv, t), j <= b, bv.split);
+                            const int c = find_cell<real>(bv, t);
                             double u;
                             lam[j - jlo] = lambda_in_cell<real>(bv, c, t, u);
                             const real ur = (real)u, sr = bv.sdl[cell_slot(c)].x, dlr = bv.sdl[cell_slot(c)].y;
