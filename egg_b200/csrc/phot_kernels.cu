@@ -148,16 +148,6 @@ __device__ __forceinline__ int last_le(const double *__restrict__ x, int n, doub
     }
     return lo;
 }
-// first j in [0, n) with x[j] >= v, n if none
-__device__ __forceinline__ int first_ge(const double *__restrict__ x, int n, double v) {
-    int lo = -1, hi = n;
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(x + mid) >= v) hi = mid; else lo = mid;
-    }
-    return hi;
-}
-
 // lane sums -> one double: five shuffle-add steps in a fixed order (bit-reproducible)
 __device__ __forceinline__ double warp_total(double v) {
 #pragma unroll
@@ -270,6 +260,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
     __shared__ GalScal sc[kBatch];
     __shared__ __align__(8) uint64_t bar_tab;
     __shared__ int item_ctr[kMaxGroups];
+    __shared__ int a2a_ctr;        // task counter of phase A2a
     __shared__ int any_bulge_line; // some bulge of the batch has an emission line with flux (normally none)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -314,30 +305,11 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
         // ---- phase A1: per-galaxy scalars, four threads per galaxy (one per piece), spread over four warps
         if ((tid & 31) < kBatch && (tid >> 5) < 4 && (tid & 31) < ng) gal_scalars(p, g0 + (tid & 31), sc[tid & 31], tid >> 5);
         if (tid >= 128 && tid < 128 + kMaxGroups) item_ctr[tid - 128] = 0;
-        if (tid == 160) any_bulge_line = 0;
+        if (tid == 160) { any_bulge_line = 0; a2a_ctr = 0; }
         for (int i = tid; i < ng * nbt * 2; i += NT) res[i] = 0.0;
         __syncthreads();
         EGG_PHASE(A1)
 
-        // ---- phase A2a: bulge SEDs on their own grid (get_opt_sed + IGM, src/egg-gencat.cpp:708-712, 2122-2140).
-        //      A warp takes 128 consecutive nodes of one galaxy at a time, four per lane.
-        if (p.has_bulge) {
-            const int ncB = (nB + 127) >> 7;
-            for (int task = warp; task < ng * ncB; task += NW) {
-                const int gi = task / ncB, j0 = ((task - gi * ncB) << 7) + 4 * lane;
-                if (j0 >= nB) continue;
-                const GalScal &s = sc[gi];
-                real *SB = scr + (size_t)gi * sstride + 2 * p.strideD;
-                Quad<real> v = ldg4(rB + (size_t)s.row_b * p.strideB + j0);
-                if (p.apply_igm && j0 < p.igmB[3]) {
-                    const real g0f = s.igm[0], g1f = s.igm[1], g2f = s.igm[2];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        v.v[k] *= igm_factor<real>(j0 + k, p.igmB[0], p.igmB[1], p.igmB[2], p.igmB[3], g0f, g1f, g2f);
-                }
-                st4(SB + j0, v); // rows are zero-padded to the stride: the tail stores zeros
-            }
-        }
         // node windows of every (band, galaxy): one thread each
         for (int idx = tid; idx < nbt * kBatch; idx += NT) {
             const int gi = idx & (kBatch - 1), fb = idx / kBatch;
@@ -401,6 +373,31 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
             lb[2 * idx] = b0;
             lb[2 * idx + 1] = b1;
             if (!c && b0 <= b1) any_bulge_line = 1;
+        }
+        // ---- phase A2a: bulge SEDs on their own grid (get_opt_sed + IGM, src/egg-gencat.cpp:708-712, 2122-2140).
+        //      A warp takes 128 consecutive nodes of one galaxy at a time, four per lane.  Tasks are pulled off a
+        //      counter: the warps that had no window to lay out above (a chain of dependent lookups, latency-bound)
+        //      start here at once and take most of them.
+        if (p.has_bulge) {
+            const int ncB = (nB + 127) >> 7;
+            for (;;) {
+                int task = 0;
+                if (lane == 0) task = atomicAdd(&a2a_ctr, 1);
+                task = __shfl_sync(kFull, task, 0);
+                if (task >= ng * ncB) break;
+                const int gi = task / ncB, j0 = ((task - gi * ncB) << 7) + 4 * lane;
+                if (j0 >= nB) continue;
+                const GalScal &s = sc[gi];
+                real *SB = scr + (size_t)gi * sstride + 2 * p.strideD;
+                Quad<real> v = ldg4(rB + (size_t)s.row_b * p.strideB + j0);
+                if (p.apply_igm && j0 < p.igmB[3]) {
+                    const real g0f = s.igm[0], g1f = s.igm[1], g2f = s.igm[2];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        v.v[k] *= igm_factor<real>(j0 + k, p.igmB[0], p.igmB[1], p.igmB[2], p.igmB[3], g0f, g1f, g2f);
+                }
+                st4(SB + j0, v); // rows are zero-padded to the stride: the tail stores zeros
+            }
         }
         __syncthreads();
         EGG_PHASE(A2a_win)
@@ -721,7 +718,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
     }
 #ifdef EGG_PHASE_TIMING
     if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
-        printf("PHASES cta %d: A1 %lld A2a+win %lld bulge-lines %lld A2b %lld A3 %lld TMA %lld B %lld C %lld\n", (int)blockIdx.x, ph_t[PH_A1],
+        printf("PHASES cta %d: A1 %lld win+A2a %lld bulge-lines %lld A2b %lld A3 %lld TMA %lld B %lld C %lld\n", (int)blockIdx.x, ph_t[PH_A1],
                ph_t[PH_A2a_win], ph_t[PH_Blines], ph_t[PH_A2b], ph_t[PH_A3lines], ph_t[PH_TMA], ph_t[PH_B], ph_t[PH_C]);
 #endif
 }
