@@ -142,3 +142,19 @@ def test_full_run_writes_the_reference_column_groups(tmp_path):
     assert r.returncode == 0, r.stderr
     t64 = fitscol.read_table(str(tmp_path / "fp64.fits"))
     assert cases.rel_err(t64["FLUX_DISK"], ref["flux_disk"], 1e-6).max() < 2e-7   # f32 column of the fp64 result
+
+
+@pytest.mark.gpu
+def test_two_gpu_shards_give_the_same_catalog(tmp_path):
+    """gpus=2: two contiguous shards, one context and host thread per GPU, no exchange."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _need_cli()
+    *_, args = _write_inputs(tmp_path, ngal=3001)
+    assert _run(*args, f"out={tmp_path}/one.fits").returncode == 0
+    r = _run(*args, f"out={tmp_path}/two.fits", "gpus=2")
+    assert r.returncode == 0, r.stderr
+    a, b = fitscol.read_table(str(tmp_path / "one.fits")), fitscol.read_table(str(tmp_path / "two.fits"))
+    for k in ("FLUX", "FLUX_DISK", "FLUX_BULGE", "RFMAG", "RFMAG_DISK", "RFMAG_BULGE"):
+        np.testing.assert_array_equal(a[k], b[k])
