@@ -40,19 +40,33 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3"],
+                    help="BASELINE.json configs[0..2]; the contract's bench line is cfg2 (= configs[1], the default)")
     return ap.parse_args()
 
 
-def make_inputs(ngal, seed):
+WORKLOADS = {
+    "cfg1": "egg-gencat area=0.08 mmin=9.0 4 HST bands ce01 (configs[0])",
+    "cfg2": WORKLOAD,
+    "cfg3": "egg-gencat COSMOS-like, opt_lib hd (re-binned) + cs17, 40 bands + UVJ rfbands (configs[2])",
+}
+
+
+def make_inputs(ngal, seed, workload="cfg2"):
+    """-> optical lib, IR lib, galaxy columns, bands, line list, rfbands (all synthetic)"""
     from egg_b200 import synth
+    if workload == "cfg3":
+        opt, ir = synth.make_opt_lib(seed=3, hd=True), synth.make_cs17_lib()
+        gal = synth.draw_galaxies(ngal, opt_lib=opt, ir_lib=ir, mmin=8.0, seed=seed)
+        return opt, ir, gal, synth.get_filters(synth.B40), synth.LINE_LAMBDA, synth.get_filters(synth.RF3)
     opt, ir = synth.make_opt_lib(), synth.ce01_lib()
-    gal = synth.draw_galaxies(ngal, opt_lib=opt, ir_lib=ir, mmin=7.5, seed=seed)
-    return opt, ir, gal, synth.get_filters(synth.B30), synth.LINE_LAMBDA
+    gal = synth.draw_galaxies(ngal, opt_lib=opt, ir_lib=ir, mmin=9.0 if workload == "cfg1" else 7.5, seed=seed)
+    return opt, ir, gal, synth.get_filters(synth.B4 if workload == "cfg1" else synth.B30), synth.LINE_LAMBDA, []
 
 
-def time_oracle(opt, ir, bands, lines, gal, nsample, nthreads=0, reps=1):
+def time_oracle(opt, ir, bands, lines, gal, nsample, nthreads=0, reps=1, rfb=()):
     from oracle.oracle import Oracle, lib
-    orc = Oracle(opt, ir, bands, line_lambda=lines)
+    orc = Oracle(opt, ir, bands, rfb, line_lambda=lines)
     sub = {k: (v[:nsample] if hasattr(v, "shape") and v.shape[:1] == gal["z"].shape else v) for k, v in gal.items()}
     best = None
     for _ in range(reps):
@@ -120,7 +134,7 @@ def run_reference(a, rank, world):
     """--impl reference: the CPU path on this box's host cores, bounded sample per step."""
     if rank != 0:
         return
-    opt, ir, gal, bands, lines = make_inputs(min(a.ngal, 40_000), 42)
+    opt, ir, gal, bands, lines, _ = make_inputs(min(a.ngal, 40_000), 42, a.workload)
     # size the per-step sample so that warmup+steps stay within a few minutes
     rate, _, cores = time_oracle(opt, ir, bands, lines, gal, 2000)
     budget = 120.0 / max(a.steps + a.warmup, 1)
@@ -135,7 +149,7 @@ def run_reference(a, rank, world):
     line = {"impl": "reference", "metric": "galaxy-band fluxes/sec", "value": val, "unit": "galaxy-band fluxes/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "nband": len(bands), "sample_galaxies_per_step": nsample,
+            "config": {"workload": WORKLOADS[a.workload], "nband": len(bands), "sample_galaxies_per_step": nsample,
                        "note": "CPU restatement of the reference path (oracle port; vif-based reference cannot be built)"},
             "cpu_baseline": {"value": val, "unit": "galaxy-band fluxes/s", "cores": cores, "kind": "port",
                              "sample": f"{nsample} galaxies x {len(bands)} bands per step, OpenMP over galaxies"},
@@ -165,17 +179,18 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     import egg_b200
-    opt, ir, gal, bands, lines = make_inputs(a.ngal, 42 + rank)
+    opt, ir, gal, bands, lines, rfb = make_inputs(a.ngal, 42 + rank, a.workload)
     nb, n = len(bands), a.ngal
-    ph = egg_b200.Photometry(opt, ir, bands, line_lambda=lines, precision=a.precision, device=local)
+    ph = egg_b200.Photometry(opt, ir, bands, rfb, line_lambda=lines, precision=a.precision, device=local)
 
     # ---- device-resident inputs / outputs
     cols = ["z", "d", "m_disk", "m_bulge", "m2lcor", "lir", "igm_abs", "vdisp", "line_lum_disk", "line_lum_bulge",
-            "opt_sed_disk", "opt_sed_bulge", "ir_sed"]
+            "opt_sed_disk", "opt_sed_bulge", "ir_sed"] + (["fpah", "mdust"] if a.workload == "cfg3" else [])
     host = {k: torch.from_numpy(np.ascontiguousarray(gal[k]).view(np.int64) if gal[k].dtype == np.uint64
                                 else np.ascontiguousarray(gal[k])).pin_memory() for k in cols}
     devt = {k: v.to(dev) for k, v in host.items()}
     outs = {k: torch.empty((n, nb), dtype=torch.float32, device=dev) for k in ("flux", "flux_disk", "flux_bulge")}
+    outs.update({k: torch.empty((n, len(rfb)), dtype=torch.float32, device=dev) for k in ("rfmag", "rfmag_disk", "rfmag_bulge") if rfb})
     gp = {k: v.data_ptr() for k, v in devt.items()}
     op = {k: v.data_ptr() for k, v in outs.items()}
     in_bytes = sum(v.numel() * v.element_size() for v in host.values())
@@ -219,7 +234,7 @@ def main():
     e2e = None
     if not a.no_e2e:
         hgal = {k: (host[k].numpy().view(np.uint64) if host[k].dtype == torch.int64 else host[k].numpy()) for k in cols}
-        hout = {k: torch.empty((n, nb), dtype=torch.float32).pin_memory().numpy() for k in ("flux", "flux_disk", "flux_bulge")}
+        hout = {k: torch.empty(tuple(v.shape), dtype=torch.float32).pin_memory().numpy() for k, v in outs.items()}
         for _ in range(2):
             ph.compute(hgal, out=hout)
         barrier()
@@ -243,20 +258,20 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         # algorithmic HBM bytes per unit: 3 f32 outputs + per-galaxy inputs / nband
         per_gal_in = in_bytes / n
-        bytes_per_unit = 12.0 + per_gal_in / nb
+        bytes_per_unit = out_bytes / n / nb + per_gal_in / nb  # catalog columns out + in, per galaxy-band flux
         achieved = n * nb * bytes_per_unit / (ms_per_step * 1e-3) / 1e9
         cpu = None
         if not a.no_cpu:
-            rate1, _, _ = time_oracle(opt, ir, bands, lines, gal, 2000)
+            rate1, _, _ = time_oracle(opt, ir, bands, lines, gal, 2000, rfb=rfb)
             ns = int(max(2000, min(n, rate1 / nb * a.cpu_seconds)))
-            rate, secs, cores = time_oracle(opt, ir, bands, lines, gal, ns)
+            rate, secs, cores = time_oracle(opt, ir, bands, lines, gal, ns, rfb=rfb)
             cpu = {"value": rate, "unit": "galaxy-band fluxes/s", "cores": cores, "kind": "port",
                    "sample": f"first {ns} galaxies of the step's catalog x {nb} bands, {secs:.1f} s, OpenMP over galaxies"}
         line = {"metric": "galaxy-band fluxes/sec", "value": value, "unit": "galaxy-band fluxes/s", "n_gpus": world,
                 "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32" if a.precision == "fp32c" else "f64",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "ngal_per_gpu": n, "nband": nb,
+                "config": {"workload": WORKLOADS[a.workload], "ngal_per_gpu": n, "nband": nb, "nrfband": len(rfb),
                            "precision": a.precision + (" (SEDs and products f32, quadrature weights f64)" if a.precision == "fp32c" else ""),
                            "l2": "flushed between timed iterations (512 MiB memset)", "lines": True, "igm": "inoue14"},
                 "e2e": e2e, "gpu_launches": int(launches_per_step * a.steps),
