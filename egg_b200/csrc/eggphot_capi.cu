@@ -200,7 +200,8 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
     // ---- tables
     uint64_t tb = 0;
     const int per16 = 4; // rows are read four elements at a time in both precisions
-    c->strideB = (P.grid_bulge.n() + per16 - 1) / per16 * per16;
+    // one spare (zero) element after the last bulge node: phase A2b reads the right neighbour of every optical node
+    c->strideB = (P.grid_bulge.n() + 1 + per16 - 1) / per16 * per16;
     c->strideD = (P.grid_disk.n() + per16 - 1) / per16 * per16;
 #define CK(x) do { if ((e = (x)) != cudaSuccess) return c->cuda_fail(e, #x); } while (0)
     CK(upload_grid(P.grid_bulge, c->xB, c->lutB, tb));

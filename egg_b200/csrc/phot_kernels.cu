@@ -191,6 +191,18 @@ __device__ __forceinline__ float rcp_approx(float x) { // one MUFU.RCP, no range
     return r;
 }
 
+// 16 bytes of a 16-byte aligned row: four floats or two doubles
+template <typename real> struct Vec16 { real v[16 / sizeof(real)]; };
+__device__ __forceinline__ Vec16<float> ldg16(const float *p) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(p));
+    return Vec16<float>{{a.x, a.y, a.z, a.w}};
+}
+__device__ __forceinline__ Vec16<double> ldg16(const double *p) {
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+    return Vec16<double>{{a.x, a.y}};
+}
+__device__ __forceinline__ void st16(float *p, const Vec16<float> &q) { *reinterpret_cast<float4 *>(p) = make_float4(q.v[0], q.v[1], q.v[2], q.v[3]); }
+__device__ __forceinline__ void st16(double *p, const Vec16<double> &q) { *reinterpret_cast<double2 *>(p) = make_double2(q.v[0], q.v[1]); }
 // four consecutive elements of a 16-byte aligned row
 template <typename real> struct Quad { real v[4]; };
 __device__ __forceinline__ Quad<float> ldg4(const float *p) {
@@ -379,14 +391,14 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
         //      counter: the warps that had no window to lay out above (a chain of dependent lookups, latency-bound)
         //      start here at once and take most of them.
         if (p.has_bulge) {
-            const int ncB = (nB + 127) >> 7;
+            const int ncB = (p.strideB + 127) >> 7; // to the stride: the spare element after the last node is zeroed
             for (;;) {
                 int task = 0;
                 if (lane == 0) task = atomicAdd(&a2a_ctr, 1);
                 task = __shfl_sync(kFull, task, 0);
                 if (task >= ng * ncB) break;
                 const int gi = task / ncB, j0 = ((task - gi * ncB) << 7) + 4 * lane;
-                if (j0 >= nB) continue;
+                if (j0 >= p.strideB) continue;
                 const GalScal &s = sc[gi];
                 real *SB = scr + (size_t)gi * sstride + 2 * p.strideD;
                 Quad<real> v = ldg4(rB + (size_t)s.row_b * p.strideB + j0);
@@ -485,57 +497,79 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
         //      bulge SED resampled on the disk grid (the same piece-wise linear function; lets phase B serve both
         //      components from one set of weights), two nodes per lane, stored as {disk, bulge} pairs
         {
-            // a task = 64 consecutive nodes (two per lane) for up to four galaxies: the disk -> optical maps of the
-            // nodes are loaded once per task (they are most of what this phase reads, and L1 is too small to keep them)
+#ifndef EGG_EXP_SKIP_A2B
+            // a task = 32 x NPL consecutive nodes (16 bytes of a row per lane: four nodes in fp32, two in fp64) for up
+            // to four galaxies: the disk -> optical maps of the nodes are loaded once per task (L1 is too small to
+            // keep them).  Nodes that are optical nodes themselves carry a zero fraction: fma(0, b1 - b0, b0) = b0.
+            constexpr int NPL = 16 / (int)sizeof(real), LG = NPL == 4 ? 7 : 6;
             const real *ofrac = reinterpret_cast<const real *>(p.u_ofrac);
-            const int ncD = (nD + 63) >> 6, nq = (ng + 3) >> 2;
+            const int ncD = (nD + 32 * NPL - 1) >> LG, nq = (ng + 3) >> 2;
             for (int task = warp; task < ncD * nq; task += NW) {
-                const int q = task / ncD, j0 = ((task - q * ncD) << 6) + 2 * lane;
+                const int q = task / ncD, j0 = ((task - q * ncD) << LG) + NPL * lane;
                 if (j0 >= nD) continue;
-                int2 o2 = make_int2(-1, -1);
-                uint32_t io = 0;
-                real2 fr = make_pair2(real(0), real(0));
+                int ol[NPL], oa[NPL];
+                Vec16<real> fr;
+#pragma unroll
+                for (int k = 0; k < NPL; ++k) { ol[k] = -1; fr.v[k] = real(0); }
                 if (p.has_bulge) {
-                    o2 = __ldg(reinterpret_cast<const int2 *>(p.u_oleft + j0));
-                    io = __ldg(reinterpret_cast<const uint16_t *>(p.u_isopt + j0));
-                    fr = __ldg(reinterpret_cast<const real2 *>(ofrac + j0));
+                    if constexpr (NPL == 4) {
+                        const int4 o4 = __ldg(reinterpret_cast<const int4 *>(p.u_oleft + j0));
+                        ol[0] = o4.x; ol[1] = o4.y; ol[2] = o4.z; ol[3] = o4.w;
+                    } else {
+                        const int2 o2 = __ldg(reinterpret_cast<const int2 *>(p.u_oleft + j0));
+                        ol[0] = o2.x; ol[1] = o2.y;
+                    }
+                    fr = ldg16(ofrac + j0);
                 }
-                const int ox = max(o2.x, 0), oy = max(o2.y, 0), ox1 = min(ox + 1, nB - 1), oy1 = min(oy + 1, nB - 1);
+#pragma unroll
+                for (int k = 0; k < NPL; ++k) oa[k] = max(ol[k], 0);
                 const bool igm_here = p.apply_igm && j0 < p.igmD[3];
-#pragma unroll 2
+#pragma unroll 1
                 for (int gi = 4 * q; gi < min(4 * q + 4, ng); ++gi) {
                     const GalScal &s = sc[gi];
                     real *DU = scr + (size_t)gi * sstride;
                     const real *SB = DU + 2 * p.strideD;
-                    real2 o = make_pair2(real(0), real(0)), i = o, pq = o;
-                    if (p.disk_mode != 2) o = __ldg(reinterpret_cast<const real2 *>(rO + (size_t)s.row_d * p.strideD + j0));
-                    if (p.disk_mode != 1) i = __ldg(reinterpret_cast<const real2 *>(rI + (size_t)s.row_i * p.strideD + j0));
-                    if (p.disk_mode != 1 && cs17) pq = __ldg(reinterpret_cast<const real2 *>(rP + (size_t)s.row_i * p.strideD + j0));
-                    // branch-free gather of the two optical nodes around each disk node (clamped: always in range)
-                    real bx0 = real(0), bx1 = real(0), by0 = real(0), by1 = real(0);
-                    if (p.has_bulge) { bx0 = SB[ox]; bx1 = SB[ox1]; by0 = SB[oy]; by1 = SB[oy1]; }
+                    Vec16<real> o, i, pq;
+#pragma unroll
+                    for (int k = 0; k < NPL; ++k) o.v[k] = i.v[k] = pq.v[k] = real(0);
+                    if (p.disk_mode != 2) o = ldg16(rO + (size_t)s.row_d * p.strideD + j0);
+                    if (p.disk_mode != 1) i = ldg16(rI + (size_t)s.row_i * p.strideD + j0);
+                    if (p.disk_mode != 1 && cs17) pq = ldg16(rP + (size_t)s.row_i * p.strideD + j0);
+                    // branch-free gather of the two optical nodes around each disk node (the row has a spare element
+                    // after the last node: oa + 1 is always in range, and the last node has a zero fraction)
+                    real b0[NPL], b1[NPL];
+#pragma unroll
+                    for (int k = 0; k < NPL; ++k) b0[k] = b1[k] = real(0);
+                    if (p.has_bulge) {
+#pragma unroll
+                        for (int k = 0; k < NPL; ++k) { b0[k] = SB[oa[k]]; b1[k] = SB[oa[k] + 1]; }
+                    }
                     const real a_d = (real)s.a_disk, c1 = (real)s.c1, c2 = (real)s.c2;
-                    real2 v;
-                    v.x = a_d * o.x + c1 * i.x; v.y = a_d * o.y + c1 * i.y; // absent terms are zero
-                    if (p.disk_mode != 1 && cs17) { v.x += c2 * pq.x; v.y += c2 * pq.y; }
+                    real v[NPL], w[NPL];
+#pragma unroll
+                    for (int k = 0; k < NPL; ++k) {
+                        v[k] = a_d * o.v[k] + c1 * i.v[k]; // absent terms are zero
+                        if (p.disk_mode != 1 && cs17) v[k] += c2 * pq.v[k];
+                    }
                     if (igm_here) {
                         const real g0f = s.igm[0], g1f = s.igm[1], g2f = s.igm[2];
-                        v.x *= igm_factor<real>(j0, p.igmD[0], p.igmD[1], p.igmD[2], p.igmD[3], g0f, g1f, g2f);
-                        v.y *= igm_factor<real>(j0 + 1, p.igmD[0], p.igmD[1], p.igmD[2], p.igmD[3], g0f, g1f, g2f);
+#pragma unroll
+                        for (int k = 0; k < NPL; ++k)
+                            v[k] *= igm_factor<real>(j0 + k, p.igmD[0], p.igmD[1], p.igmD[2], p.igmD[3], g0f, g1f, g2f);
                     }
-                    real2 w;
-                    w.x = o2.x < 0 ? real(0) : ((io & 0xffu) ? bx0 : fma(fr.x, bx1 - bx0, bx0));
-                    w.y = o2.y < 0 ? real(0) : ((io >> 8) ? by0 : fma(fr.y, by1 - by0, by0));
-                    // the row stride is a multiple of four: node j0 + 1 <= stride - 1 always has room
-                    if constexpr (sizeof(real) == 4) {
-                        *reinterpret_cast<float4 *>(DU + 2 * j0) = make_float4(v.x, w.x, v.y, w.y);
-                    } else {
-                        real2 *dst = reinterpret_cast<real2 *>(DU) + j0;
-                        dst[0] = make_pair2(v.x, w.x);
-                        dst[1] = make_pair2(v.y, w.y);
+#pragma unroll
+                    for (int k = 0; k < NPL; ++k) w[k] = ol[k] < 0 ? real(0) : fma(fr.v[k], b1[k] - b0[k], b0[k]);
+                    // the row stride is a multiple of four: nodes j0 .. j0 + NPL - 1 <= stride - 1 always have room
+                    Vec16<real> st;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                        for (int k = 0; k < NPL / 2; ++k) { st.v[2 * k] = v[h * (NPL / 2) + k]; st.v[2 * k + 1] = w[h * (NPL / 2) + k]; }
+                        st16(DU + 2 * j0 + h * NPL, st);
                     }
                 }
             }
+#endif
         }
         __syncthreads();
         EGG_PHASE(A2b)
