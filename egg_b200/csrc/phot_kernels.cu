@@ -272,7 +272,8 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
     __shared__ GalScal sc[kBatch];
     __shared__ __align__(8) uint64_t bar_tab;
     __shared__ int item_ctr[kMaxGroups];
-    __shared__ int a2a_ctr;        // task counter of phase A2a
+    __shared__ int a2a_ctr, a2b_ctr; // task counters of phases A2a and A2b
+    __shared__ int jneed[kBatch][2]; // first and last disk-grid node that any band of the galaxy reads
     __shared__ int any_bulge_line; // some bulge of the batch has an emission line with flux (normally none)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -317,7 +318,12 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
         // ---- phase A1: per-galaxy scalars, four threads per galaxy (one per piece), spread over four warps
         if ((tid & 31) < kBatch && (tid >> 5) < 4 && (tid & 31) < ng) gal_scalars(p, g0 + (tid & 31), sc[tid & 31], tid >> 5);
         if (tid >= 128 && tid < 128 + kMaxGroups) item_ctr[tid - 128] = 0;
-        if (tid == 160) { any_bulge_line = 0; a2a_ctr = 0; }
+        if (tid == 160) { any_bulge_line = 0; a2a_ctr = 0; a2b_ctr = 0; }
+        if (tid >= 192 && tid < 192 + kBatch) { // the rest-frame bands read fixed node ranges
+            int lo = nD, hi = -1;
+            for (int r = 0; r < nrf; ++r) { lo = min(lo, (int)p.rfD[r].j0); hi = max(hi, (int)(p.rfD[r].j0 + p.rfD[r].n - 1)); }
+            jneed[tid - 192][0] = lo; jneed[tid - 192][1] = hi;
+        }
         for (int i = tid; i < ng * nbt * 2; i += NT) res[i] = 0.0;
         __syncthreads();
         EGG_PHASE(A1)
@@ -345,6 +351,8 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                     const int jhi = min(lut_first_ge(x, n, p.lutD, p.lutD_n, __ldg(&gh->l2last) - koff, __ldg(&gh->eff_last) * s.iopz * (1.0 + 1e-15)), n - 1);
                     if (jhi > jlo) {
                         wv = (uint32_t)jlo | ((uint32_t)jhi << 16);
+                        atomicMin(&jneed[gi][0], jlo);
+                        atomicMax(&jneed[gi][1], jhi);
                         // b = last node of [jlo, jhi) left of the band's split node, by the same expression phase B
                         // uses to place a node in a filter cell (the two must agree on which gauge a node is in)
                         const double fc = __ldg(&gh->fc), fs = __ldg(&gh->f_split);
@@ -495,7 +503,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
 
         // ---- phase A2b: disk SEDs (get_opt_sed / get_ir_sed / merge_add / IGM, src/egg-gencat.cpp:2104-2140) and the
         //      bulge SED resampled on the disk grid (the same piece-wise linear function; lets phase B serve both
-        //      components from one set of weights), two nodes per lane, stored as {disk, bulge} pairs
+        //      components from one set of weights), stored as {disk, bulge} pairs
         {
 #ifndef EGG_EXP_SKIP_A2B
             // a task = 32 x NPL consecutive nodes (16 bytes of a row per lane: four nodes in fp32, two in fp64) for up
@@ -503,10 +511,17 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
             // keep them).  Nodes that are optical nodes themselves carry a zero fraction: fma(0, b1 - b0, b0) = b0.
             constexpr int NPL = 16 / (int)sizeof(real), LG = NPL == 4 ? 7 : 6;
             const real *ofrac = reinterpret_cast<const real *>(p.u_ofrac);
+            // Only the nodes some band of the galaxy reads are built (jneed: union of its node windows).
             const int ncD = (nD + 32 * NPL - 1) >> LG, nq = (ng + 3) >> 2;
-            for (int task = warp; task < ncD * nq; task += NW) {
-                const int q = task / ncD, j0 = ((task - q * ncD) << LG) + NPL * lane;
-                if (j0 >= nD) continue;
+            for (;;) {
+                int task = 0;
+                if (lane == 0) task = atomicAdd(&a2b_ctr, 1);
+                task = __shfl_sync(kFull, task, 0);
+                if (task >= ncD * nq) break;
+                const int q = task / ncD, c0 = (task - q * ncD) << LG, j0 = c0 + NPL * lane;
+                int glo = nD, ghi = -1; // the quad's union
+                for (int gi = 4 * q; gi < min(4 * q + 4, ng); ++gi) { glo = min(glo, jneed[gi][0]); ghi = max(ghi, jneed[gi][1]); }
+                if (c0 > ghi || c0 + 32 * NPL <= glo || j0 >= nD) continue;
                 int ol[NPL], oa[NPL];
                 Vec16<real> fr;
 #pragma unroll
@@ -526,6 +541,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                 const bool igm_here = p.apply_igm && j0 < p.igmD[3];
 #pragma unroll 1
                 for (int gi = 4 * q; gi < min(4 * q + 4, ng); ++gi) {
+                    if (c0 > jneed[gi][1] || c0 + 32 * NPL <= jneed[gi][0]) continue; // warp-uniform
                     const GalScal &s = sc[gi];
                     real *DU = scr + (size_t)gi * sstride;
                     const real *SB = DU + 2 * p.strideD;
