@@ -93,6 +93,8 @@ struct __attribute__((aligned(16))) BandHeader {
     uint32_t out_col;             // column in the sorted band list
     uint32_t split;               // index of the split node; bit 31: one probe settles the cell lookup (buckets are
                                   // narrower than every cell)
+    float l2split;                // log2(fc + f_split) in lookup buckets: where the split node is looked up
+    uint32_t pad_;
 };
 static_assert(sizeof(BandHeader) == 144, "BandHeader layout");
 

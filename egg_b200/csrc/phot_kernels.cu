@@ -356,11 +356,12 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                         // b = last node of [jlo, jhi) left of the band's split node, by the same expression phase B
                         // uses to place a node in a filter cell (the two must agree on which gauge a node is in)
                         const double fc = __ldg(&gh->fc), fs = __ldg(&gh->f_split);
-                        int lo = jlo, hi = jhi; // t(lo) < fs (or lo = jlo), t(hi) >= fs (or hi = jhi)
-                        while (hi - lo > 1) {
-                            const int mid = (lo + hi) >> 1;
-                            if (fma(s.opz, __ldg(x + mid), -fc) < fs) lo = mid; else hi = mid;
-                        }
+                        // first guess from the wavelength lookup table, settled with the exact predicate
+                        int k = (int)(__ldg(&gh->l2split) - koff);
+                        k = max(0, min(k, p.lutD_n - 1));
+                        int lo = max(jlo, min((int)__ldg(p.lutD + k), jhi - 1));
+                        while (lo > jlo && !(fma(s.opz, __ldg(x + lo), -fc) < fs)) --lo;
+                        while (lo + 1 < jhi && fma(s.opz, __ldg(x + lo + 1), -fc) < fs) ++lo;
                         wm = (uint16_t)lo;
                     }
                     if (p.has_bulge && nB >= 2 && __ldg(p.xB) * s.opz <= full_first && __ldg(p.xB + nB - 1) * s.opz >= full_last) fl = 1;
@@ -393,31 +394,6 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
             lb[2 * idx] = b0;
             lb[2 * idx + 1] = b1;
             if (!c && b0 <= b1) any_bulge_line = 1;
-        }
-        // ---- phase A2a: bulge SEDs on their own grid (get_opt_sed + IGM, src/egg-gencat.cpp:708-712, 2122-2140).
-        //      A warp takes 128 consecutive nodes of one galaxy at a time, four per lane.  Tasks are pulled off a
-        //      counter: the warps that had no window to lay out above (a chain of dependent lookups, latency-bound)
-        //      start here at once and take most of them.
-        if (p.has_bulge) {
-            const int ncB = (p.strideB + 127) >> 7; // to the stride: the spare element after the last node is zeroed
-            for (;;) {
-                int task = 0;
-                if (lane == 0) task = atomicAdd(&a2a_ctr, 1);
-                task = __shfl_sync(kFull, task, 0);
-                if (task >= ng * ncB) break;
-                const int gi = task / ncB, j0 = ((task - gi * ncB) << 7) + 4 * lane;
-                if (j0 >= p.strideB) continue;
-                const GalScal &s = sc[gi];
-                real *SB = scr + (size_t)gi * sstride + 2 * p.strideD;
-                Quad<real> v = ldg4(rB + (size_t)s.row_b * p.strideB + j0);
-                if (p.apply_igm && j0 < p.igmB[3]) {
-                    const real g0f = s.igm[0], g1f = s.igm[1], g2f = s.igm[2];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        v.v[k] *= igm_factor<real>(j0 + k, p.igmB[0], p.igmB[1], p.igmB[2], p.igmB[3], g0f, g1f, g2f);
-                }
-                st4(SB + j0, v); // rows are zero-padded to the stride: the tail stores zeros
-            }
         }
         __syncthreads();
         EGG_PHASE(A2a_win)
@@ -495,7 +471,34 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                 }
             }
         };
-        if (any_bulge_line) { // block-uniform: written before the barrier above
+        // ---- phase A2a: bulge SEDs on their own grid (get_opt_sed + IGM, src/egg-gencat.cpp:708-712, 2122-2140).
+        //      Only when some bulge of the batch has an emission line (normally none): the lines are deposited on the
+        //      bulge's own grid before it is resampled.  Otherwise phase A2b and the rest-frame items read the
+        //      template row itself.  A warp takes 128 consecutive nodes of one galaxy at a time, four per lane.
+        const bool use_sb = any_bulge_line != 0; // block-uniform: written before the barrier above
+        if (use_sb) {
+            const int ncB = (p.strideB + 127) >> 7; // to the stride: the spare element after the last node is zeroed
+            for (;;) {
+                int task = 0;
+                if (lane == 0) task = atomicAdd(&a2a_ctr, 1);
+                task = __shfl_sync(kFull, task, 0);
+                if (task >= ng * ncB) break;
+                const int gi = task / ncB, j0 = ((task - gi * ncB) << 7) + 4 * lane;
+                if (j0 >= p.strideB) continue;
+                const GalScal &s = sc[gi];
+                real *SB = scr + (size_t)gi * sstride + 2 * p.strideD;
+                Quad<real> v = ldg4(rB + (size_t)s.row_b * p.strideB + j0);
+                if (p.apply_igm && j0 < p.igmB[3]) {
+                    const real g0f = s.igm[0], g1f = s.igm[1], g2f = s.igm[2];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        v.v[k] *= igm_factor<real>(j0 + k, p.igmB[0], p.igmB[1], p.igmB[2], p.igmB[3], g0f, g1f, g2f);
+                }
+                st4(SB + j0, v); // rows are zero-padded to the stride: the tail stores zeros
+            }
+        }
+        if (use_sb) {
+            __syncthreads();
             deposit_lines(0);
             __syncthreads();
             EGG_PHASE(Blines)
@@ -557,8 +560,22 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
 #pragma unroll
                     for (int k = 0; k < NPL; ++k) b0[k] = b1[k] = real(0);
                     if (p.has_bulge) {
+                        if (use_sb) {
 #pragma unroll
-                        for (int k = 0; k < NPL; ++k) { b0[k] = SB[oa[k]]; b1[k] = SB[oa[k] + 1]; }
+                            for (int k = 0; k < NPL; ++k) { b0[k] = SB[oa[k]]; b1[k] = SB[oa[k] + 1]; }
+                        } else { // the template row itself (get_opt_sed + IGM, src/egg-gencat.cpp:708-712, 2122-2140)
+                            const real *R = rB + (size_t)s.row_b * p.strideB;
+#pragma unroll
+                            for (int k = 0; k < NPL; ++k) { b0[k] = __ldg(R + oa[k]); b1[k] = __ldg(R + oa[k] + 1); }
+                            if (p.apply_igm && oa[0] < p.igmB[3]) {
+                                const real g0f = s.igm[0], g1f = s.igm[1], g2f = s.igm[2];
+#pragma unroll
+                                for (int k = 0; k < NPL; ++k) {
+                                    b0[k] *= igm_factor<real>(oa[k], p.igmB[0], p.igmB[1], p.igmB[2], p.igmB[3], g0f, g1f, g2f);
+                                    b1[k] *= igm_factor<real>(oa[k] + 1, p.igmB[0], p.igmB[1], p.igmB[2], p.igmB[3], g0f, g1f, g2f);
+                                }
+                            }
+                        }
                     }
                     const real a_d = (real)s.a_disk, c1 = (real)s.c1, c2 = (real)s.c2;
                     real v[NPL], w[NPL];
@@ -724,7 +741,19 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                     const real *W = reinterpret_cast<const real *>(p.rfW) + dsc.off;
                     CompSum<real> acc;
                     acc.clear();
-                    for (int k = lane; k < dsc.n; k += 32) acc.add(S[(size_t)(dsc.j0 + k) * sstep] * __ldg(W + k));
+                    if (comp || use_sb) {
+                        for (int k = lane; k < dsc.n; k += 32) acc.add(S[(size_t)(dsc.j0 + k) * sstep] * __ldg(W + k));
+                    } else { // no bulge SED in the scratch: the template row with the IGM factors
+                        const GalScal &s = sc[gi];
+                        const real *R = rB + (size_t)s.row_b * p.strideB;
+                        const real g0f = s.igm[0], g1f = s.igm[1], g2f = s.igm[2];
+                        for (int k = lane; k < dsc.n; k += 32) {
+                            const int j = dsc.j0 + k;
+                            real v = __ldg(R + j);
+                            if (p.apply_igm && j < p.igmB[3]) v *= igm_factor<real>(j, p.igmB[0], p.igmB[1], p.igmB[2], p.igmB[3], g0f, g1f, g2f);
+                            acc.add(v * __ldg(W + k));
+                        }
+                    }
                     acc = warp_reduce(acc);
                     if (lane == 0)
                         rfres[(gi * nrf + rb) * 2 + comp] = dsc.covered ? ((double)acc.s + (double)acc.c) * (comp ? 1.0 : sc[gi].a_bulge)

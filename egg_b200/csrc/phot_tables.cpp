@@ -162,6 +162,7 @@ Status build_band_table(const Filter &f, uint32_t out_col, int bucket_factor, Ba
     if (!(t.h.bkt_inv_w * span < nbkt)) t.h.bkt_inv_w = std::nextafter(t.h.bkt_inv_w, 0.0f);
     t.h.l2first = (float)(std::log2(t.h.eff_first) * kLutPerOctave);
     t.h.l2last = (float)(std::log2(t.h.eff_last) * kLutPerOctave);
+    t.h.l2split = (float)(std::log2(std::max(t.h.fc + t.h.f_split, 1e-300)) * kLutPerOctave);
     t.bkt.assign(nbkt, 0);
     int i = 0;
     for (int k = 0; k < nbkt; ++k) {
