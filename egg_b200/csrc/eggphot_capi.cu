@@ -145,7 +145,7 @@ int enqueue(eggphot_ctx *c, const eggphot_galaxies &g, size_t ngal, const eggpho
     p.scratch = (char *)c->scratch.p + (size_t)region * c->scratch_region_bytes;
     p.do_rf = c->P.rfbands.size() && (o.rfmag || o.rfmag_disk || o.rfmag_bulge || o.rfmag_disk_f64 || o.rfmag_bulge_f64);
     if (p.ngroups == 0 && !p.do_rf) return EGGPHOT_OK;
-    const size_t nbatch = (ngal + kBatch - 1) / kBatch;
+    const size_t nbatch = (ngal + p.batch - 1) / p.batch;
     const int blocks = (int)std::min<size_t>((size_t)c->grid_blocks, nbatch);
     int e = launch_flux_kernel(p, c->P.precision, blocks, st);
     if (e != 0) return c->cuda_fail((cudaError_t)e, "flux kernel launch");
@@ -281,6 +281,7 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
     p.nrf = (uint32_t)P.rfbands.size();
     p.nB = P.grid_bulge.n(); p.nD = P.grid_disk.n();
     p.strideB = c->strideB; p.strideD = c->strideD;
+    p.batch = batch_of(P.precision);
     p.xB = (const double *)c->xB.p; p.xD = (const double *)c->xD.p;
     p.gridA = c->gridA.p; p.gridB = c->gridB.p;
     p.lutB = (const uint16_t *)c->lutB.p; p.lutD = (const uint16_t *)c->lutD.p;
@@ -327,7 +328,7 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
         if (occ <= 0) return c->fail(EGGPHOT_ERR_CUDA, "flux kernel cannot be resident (occupancy query failed)");
         c->grid_blocks = c->num_sms * occ;
         const size_t rs = P.precision == EGGPHOT_FP64 ? 8 : 4;
-        c->scratch_region_bytes = ((size_t)c->grid_blocks * kBatch * (size_t)(2 * c->strideD + c->strideB) * rs + 255) & ~size_t(255);
+        c->scratch_region_bytes = ((size_t)c->grid_blocks * p.batch * (size_t)(2 * c->strideD + c->strideB) * rs + 255) & ~size_t(255);
         CK(c->scratch.alloc(c->scratch_region_bytes * (kSlots + 1)));
         p.scratch = c->scratch.p;
     }

@@ -241,13 +241,13 @@ __host__ __device__ inline SmemLayout smem_layout(const FluxParams &p) {
     const size_t nl = p.nline > 0 ? p.nline : 0;
     uint32_t o = 0;
     L.tab = o; o += up(p.max_blob);                                              // band tables of the current group
-    L.res = o; o += up((size_t)kBatch * p.nband_total * 2 * sizeof(double));     // [gal][col][comp] scaled fluxes
-    L.rfres = o; o += up((size_t)kBatch * p.nrf * 2 * sizeof(double));           // [gal][rf][comp] rest-frame fluxes
-    L.lb = o; o += up((size_t)kBatch * 2 * nl * 2 * sizeof(int));                // line windows [b0, b1]
-    L.lt = o; o += up((size_t)kBatch * 2 * nl * 2 * sizeof(int));                // line tasks {first owned node, task offset}
-    L.win = o; o += up((size_t)kBatch * p.nband_total * sizeof(uint32_t));       // node windows (jlo | jhi << 16)
-    L.wmid = o; o += up((size_t)kBatch * p.nband_total * sizeof(uint16_t));      // node left of the band's split
-    L.wflag = o; o += up((size_t)kBatch * p.nband_total);                        // bit 0: bulge covered
+    L.res = o; o += up((size_t)p.batch * p.nband_total * 2 * sizeof(double));     // [gal][col][comp] scaled fluxes
+    L.rfres = o; o += up((size_t)p.batch * p.nrf * 2 * sizeof(double));           // [gal][rf][comp] rest-frame fluxes
+    L.lb = o; o += up((size_t)p.batch * 2 * nl * 2 * sizeof(int));                // line windows [b0, b1]
+    L.lt = o; o += up((size_t)p.batch * 2 * nl * 2 * sizeof(int));                // line tasks {first owned node, task offset}
+    L.win = o; o += up((size_t)p.batch * p.nband_total * sizeof(uint32_t));       // node windows (jlo | jhi << 16)
+    L.wmid = o; o += up((size_t)p.batch * p.nband_total * sizeof(uint16_t));      // node left of the band's split
+    L.wflag = o; o += up((size_t)p.batch * p.nband_total);                        // bit 0: bulge covered
     L.total = o;
     return L;
 }
@@ -268,6 +268,7 @@ __host__ __device__ inline SmemLayout smem_layout(const FluxParams &p) {
 template <typename real, int NT>
 __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ FluxParams p) {
     typedef typename Pair<real>::type real2;
+    constexpr int kBatch = sizeof(real) == 4 ? kBatchF32 : kBatchF64;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ GalScal sc[kBatch];
     __shared__ __align__(8) uint64_t bar_tab;

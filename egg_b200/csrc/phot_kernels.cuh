@@ -11,10 +11,6 @@ namespace eggphot {
 
 constexpr int kMaxLines = 64;
 constexpr int kMaxGroupBands = 64;
-#ifndef EGG_KBATCH
-#define EGG_KBATCH 16
-#endif
-constexpr int kBatch = EGG_KBATCH;     // galaxies a CTA carries through all band groups at a time (power of two)
 constexpr int kMaxGroups = 16;
 constexpr int kMaxRf = 16;
 
@@ -46,7 +42,8 @@ struct FluxParams {
     uint32_t ngroups, max_blob;
     GroupDesc groups[kMaxGroups];
     int32_t do_rf;         // also compute the rest-frame magnitudes
-    // per-CTA scratch for the rest-frame SEDs of a batch: [grid][kBatch][2*strideD + strideB] real (stays in L2):
+    int32_t batch;         // galaxies per batch (batch_of(precision))
+    // per-CTA scratch for the rest-frame SEDs of a batch: [grid][batch][2*strideD + strideB] real (stays in L2):
     // nD pairs {disk SED, bulge SED resampled on the disk grid}, then the bulge SED on its own grid
     void *scratch;
     // component grids

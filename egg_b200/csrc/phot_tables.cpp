@@ -555,8 +555,15 @@ Status prepare(const eggphot_libs &L, const eggphot_filters *bands, const eggpho
     }
 
     // ---- band tables, packed into groups under the shared-memory budget
-    const size_t budget = opts.smem_table_budget ? opts.smem_table_budget : 196u * 1024;
-    const size_t hard_cap = 204u * 1024;
+    // default: what the other shared-memory arrays of the flux kernel (phot_kernels.cu, smem_layout: per galaxy of a
+    // batch the flux accumulators, node windows and line windows) leave of the 227 KB a CTA can have
+    size_t budget = opts.smem_table_budget;
+    if (!budget) {
+        const size_t nb = P.bands.size(), nr = P.rfbands.size(), nl = P.no_nebular ? 0 : P.line_lambda.size();
+        const size_t other = (size_t)batch_of(P.precision) * (nb * (16 + 7) + nr * 16 + nl * 32) + 8 * 128 + 4096;
+        budget = other + 64u * 1024 < 232448u ? 232448u - other : 64u * 1024;
+    }
+    const size_t hard_cap = opts.smem_table_budget ? std::max<size_t>(budget, 204u * 1024) : budget; // of one band
     const int bfac = P.precision == EGGPHOT_FP64 ? 2 : 4;
     std::vector<BandTableD> tabs(P.bands.size());
     for (size_t b = 0; b < P.bands.size(); ++b) {
