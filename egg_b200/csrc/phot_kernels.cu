@@ -125,18 +125,20 @@ __device__ __forceinline__ int lut_last_le(const double *__restrict__ x, int n, 
     int k = (int)kpos;
     k = max(0, min(k, nlut - 1));
     int j = __ldg(lut + k);
-    while (j >= 0 && __ldg(x + j) > v) --j;
-    while (j + 1 < n && __ldg(x + j + 1) <= v) ++j;
+    // both neighbours of the guess are requested at once: the guess is normally right or off by one
+    double a = __ldg(x + max(j, 0)), b = __ldg(x + min(j + 1, n - 1));
+    while (j >= 0 && a > v) { --j; b = a; a = __ldg(x + max(j, 0)); }
+    while (j + 1 < n && b <= v) { ++j; b = __ldg(x + min(j + 1, n - 1)); }
     return j;
 }
-// first j in [0, n) with x[j] >= v (n if none)
 __device__ __forceinline__ int lut_first_ge(const double *__restrict__ x, int n, const uint16_t *__restrict__ lut,
                                             int nlut, float kpos, double v) {
     int k = (int)kpos;
     k = max(0, min(k, nlut - 1));
     int j = __ldg(lut + k); // candidate for the last node < v
-    while (j >= 0 && __ldg(x + j) >= v) --j;
-    while (j + 1 < n && __ldg(x + j + 1) < v) ++j;
+    double a = __ldg(x + max(j, 0)), b = __ldg(x + min(j + 1, n - 1));
+    while (j >= 0 && a >= v) { --j; b = a; a = __ldg(x + max(j, 0)); }
+    while (j + 1 < n && b < v) { ++j; b = __ldg(x + min(j + 1, n - 1)); }
     return j + 1;
 }
 // last j in [0, n) with x[j] <= v, -1 if none
@@ -361,8 +363,9 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                         int k = (int)(__ldg(&gh->l2split) - koff);
                         k = max(0, min(k, p.lutD_n - 1));
                         int lo = max(jlo, min((int)__ldg(p.lutD + k), jhi - 1));
-                        while (lo > jlo && !(fma(s.opz, __ldg(x + lo), -fc) < fs)) --lo;
-                        while (lo + 1 < jhi && fma(s.opz, __ldg(x + lo + 1), -fc) < fs) ++lo;
+                        double xa = __ldg(x + lo), xb = __ldg(x + min(lo + 1, n - 1));
+                        while (lo > jlo && !(fma(s.opz, xa, -fc) < fs)) { --lo; xb = xa; xa = __ldg(x + lo); }
+                        while (lo + 1 < jhi && fma(s.opz, xb, -fc) < fs) { ++lo; xb = __ldg(x + min(lo + 1, n - 1)); }
                         wm = (uint16_t)lo;
                     }
                     if (p.has_bulge && nB >= 2 && __ldg(p.xB) * s.opz <= full_first && __ldg(p.xB + nB - 1) * s.opz >= full_last) fl = 1;
