@@ -457,6 +457,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                         if (wt[2 * mid + 1] <= t) lo = mid; else hi = mid;
                     }
                     const int l = lo, j = wt[2 * l] + (t - wt[2 * l + 1]);
+                    const real s_old = S[(size_t)j * sstep]; // requested with the wavelengths: one round trip, not two
                     const double xj = __ldg(x + j);
                     const double xm = j > 0 ? __ldg(x + j - 1) : 0.0, xp = j < n - 1 ? __ldg(x + j + 1) : 0.0;
                     const double llow = j != 0 ? 0.5 * (xm + xj) : xj - 0.5 * (xp - xj);       // :2090
@@ -471,7 +472,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                             acc += line_bin_t<real>(llow, lup, l0, lw, (double)ll[p.line_col[k]] * l0, p.line_average);
                         }
                     }
-                    S[(size_t)j * sstep] += (real)(xj * acc * inv);
+                    S[(size_t)j * sstep] = s_old + (real)(xj * acc * inv);
                 }
             }
         };
