@@ -722,16 +722,25 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                         }
                         cur = nxt;
                     }
-                    const double totd = warp_total((double)accd);
-                    const double totb = bulge_on ? warp_total((double)accb) : 0.0;
-                    if (lane == 0) {
-                        double f = totd * s.iopz * s.aflux;
-                        if (!isfinite(f)) f = 0.0; // src/egg-gencat.cpp:2198
-                        res[(gi * nbt + (int)h.out_col) * 2 + 1] = f;
-                        if (bulge_on) {
-                            double fb = totb * s.iopz * s.aflux * s.a_bulge;
-                            if (!isfinite(fb)) fb = 0.0;
-                            res[(gi * nbt + (int)h.out_col) * 2] = fb;
+                    if (bulge_on) {
+                        // both totals in five shuffle steps: the halves of the warp first swap what the other needs,
+                        // then lanes 0-15 reduce the disk and lanes 16-31 the bulge (same pairs, same order of
+                        // additions as warp_total: bit-identical)
+                        const bool lo = lane < 16;
+                        double v = (lo ? (double)accd : (double)accb) + __shfl_xor_sync(kFull, lo ? (double)accb : (double)accd, 16);
+#pragma unroll
+                        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+                        if ((lane & 15) == 0) {
+                            double f = v * s.iopz * s.aflux * (lo ? 1.0 : s.a_bulge);
+                            if (!isfinite(f)) f = 0.0; // src/egg-gencat.cpp:2198
+                            res[(gi * nbt + (int)h.out_col) * 2 + (lo ? 1 : 0)] = f;
+                        }
+                    } else {
+                        const double totd = warp_total((double)accd);
+                        if (lane == 0) {
+                            double f = totd * s.iopz * s.aflux;
+                            if (!isfinite(f)) f = 0.0;
+                            res[(gi * nbt + (int)h.out_col) * 2 + 1] = f;
                         }
                     }
                 } else {
