@@ -57,7 +57,7 @@ struct eggphot_ctx {
     cudaStream_t stream = nullptr;
     // prepared tables on the device
     std::vector<DevBuf> blobs;
-    DevBuf xB, xD, gridA, gridB, lutB, lutD, rowsB, rowsDopt, rowsDir, rowsDpah, opt_use, rfB, rfD, rfW, errflag, scratch, u_oleft, u_ofrac, u_isopt;
+    DevBuf xB, xD, gridA, gridB, lutB, lutD, rowsB, rowsDopt, rowsDir, rowsDpah, opt_use, rfB, rfD, rfW, errflag, scratch, u_oleft, u_ofrac;
     int strideB = 0, strideD = 0;
     FluxParams base{};
     int grid_blocks = 0;
@@ -234,10 +234,8 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
         // (padded to a multiple of four entries: phase A4 reads them four at a time)
         const size_t n4 = (P.u_oleft.size() + 3) & ~size_t(3);
         std::vector<int32_t> ol(P.u_oleft); ol.resize(n4, -1);
-        std::vector<uint8_t> io(P.u_isopt); io.resize(n4, 0);
         std::vector<double> fr(P.u_ofrac); fr.resize(n4, 0.0);
         CK(c->u_oleft.upload(ol.data(), ol.size() * sizeof(int32_t)));
-        CK(c->u_isopt.upload(io.data(), io.size()));
         if (P.precision == EGGPHOT_FP64) CK(c->u_ofrac.upload(fr.data(), fr.size() * sizeof(double)));
         else {
             std::vector<float> f(fr.begin(), fr.end());
@@ -293,7 +291,6 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
     p.rowsB = c->rowsB.p; p.rowsDopt = c->rowsDopt.p; p.rowsDir = c->rowsDir.p; p.rowsDpah = c->rowsDpah.p;
     p.opt_use = (const uint8_t *)c->opt_use.p;
     p.u_oleft = (const int32_t *)c->u_oleft.p; p.u_ofrac = c->u_ofrac.p;
-    p.u_isopt = (const uint8_t *)c->u_isopt.p;
     p.nopt_sed = P.nopt_sed; p.nir_sed = P.nir_sed;
     p.ir_kind = P.ir_kind; p.disk_mode = (int)P.disk_mode; p.has_bulge = P.has_bulge; p.apply_igm = P.apply_igm;
     p.nline = P.no_nebular ? 0 : (int)P.line_lambda.size();

@@ -513,7 +513,6 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
         //      bulge SED resampled on the disk grid (the same piece-wise linear function; lets phase B serve both
         //      components from one set of weights), stored as {disk, bulge} pairs
         {
-#ifndef EGG_EXP_SKIP_A2B
             // a task = 32 x NPL consecutive nodes (16 bytes of a row per lane: four nodes in fp32, two in fp64) for up
             // to four galaxies: the disk -> optical maps of the nodes are loaded once per task (L1 is too small to
             // keep them).  Nodes that are optical nodes themselves carry a zero fraction: fma(0, b1 - b0, b0) = b0.
@@ -607,7 +606,6 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                     }
                 }
             }
-#endif
         }
         __syncthreads();
         EGG_PHASE(A2b)

@@ -60,7 +60,6 @@ struct FluxParams {
     // disk grid -> optical grid maps (Prepared::u_*), for the bulge evaluated on the disk grid
     const int32_t *u_oleft;
     const void *u_ofrac;   // real
-    const uint8_t *u_isopt;
     const uint8_t *opt_use;
     uint32_t nopt_sed, nir_sed;
     int32_t ir_kind, disk_mode, has_bulge, apply_igm;
