@@ -78,12 +78,14 @@ def time_oracle(opt, ir, bands, lines, gal, nsample, nthreads=0, reps=1, rfb=())
     return nsample * len(bands) / best, best, cores
 
 
-def measured_traffic(ngal):
+def measured_traffic(ngal, workload="cfg2", precision="fp32c"):
     """DRAM bytes (read + write) of one flux_kernel launch from the committed `ncu --set full` capture of
-    this same command (profiles/r1_flux_kernel_traffic.json), or None if the capture is for another size."""
+    this same command (profiles/r1_flux_kernel_traffic.json: configs[1], fp32 mode), or None for any other
+    size, workload or precision."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "r1_flux_kernel_traffic.json")))
-        return float(t["dram_bytes_per_launch"]) if int(t["ngal"]) == int(ngal) else None
+        same = int(t["ngal"]) == int(ngal) and workload == "cfg2" and precision == "fp32c"
+        return float(t["dram_bytes_per_launch"]) if same else None
     except Exception:
         return None
 
@@ -276,7 +278,7 @@ def main():
                            "l2": "flushed between timed iterations (512 MiB memset)", "lines": True, "igm": "inoue14"},
                 "e2e": e2e, "gpu_launches": int(launches_per_step * a.steps),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": achieved / hbm_peak, "traffic": measured_traffic(n),
+                             "frac": achieved / hbm_peak, "traffic": measured_traffic(n, a.workload, a.precision),
                              "bytes_per_unit": bytes_per_unit,
                              "algorithmic_bytes_per_launch": n * nb * bytes_per_unit,
                              "peak_source": "MEASURED_PEAKS.json (hbm_gbs, measured copy)" if peaks else "fallback",

@@ -23,13 +23,21 @@ keys = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active
 for k in keys:
     if k in d:
         print(f"{k:75s} {d[k][0]:>16s} {d[k][1]}")
-st = []
+keys2 = ["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum",
+         "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_atom.sum",
+         "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_st.sum"]
+for k in keys2:
+    if k in d:
+        print(f"{k:75s} {d[k][0]:>16s} {d[k][1]}")
+# warp states from the PC samples (the per-issue ratios of newer ncu versions carry the same information)
+st, tot = [], 0.0
 for n, (val, unit) in d.items():
-    if "issue_stalled" in n and n.endswith("_per_warp_active.pct") and "not_issued" not in n:
+    if n.startswith("smsp__pcsamp_warps_issue_stalled_") and not n.endswith("_not_issued"):
         try:
-            st.append((float(val), n))
+            st.append((float(val.replace(",", "")), n))
+            tot += float(val.replace(",", ""))
         except ValueError:
             pass
-print("--- stall reasons (% of warp-active cycles)")
+print("--- warp states (% of PC samples)")
 for val, n in sorted(st, reverse=True)[:12]:
-    print(f"{val:8.2f}  {n.replace('smsp__average_warps_issue_stalled_', '').replace('_per_warp_active.pct', '')}")
+    print(f"{100 * val / max(tot, 1):8.2f}  {n.replace('smsp__pcsamp_warps_issue_stalled_', '')}")
