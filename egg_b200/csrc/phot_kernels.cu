@@ -220,8 +220,6 @@ __device__ __forceinline__ void st4(double *p, const Quad<double> &q) {
     reinterpret_cast<double2 *>(p)[0] = make_double2(q.v[0], q.v[1]);
     reinterpret_cast<double2 *>(p)[1] = make_double2(q.v[2], q.v[3]);
 }
-__device__ __forceinline__ float2 make_pair2(float a, float b) { return make_float2(a, b); }
-__device__ __forceinline__ double2 make_pair2(double a, double b) { return make_double2(a, b); }
 template <typename real> struct Pair;
 template <> struct Pair<float> { typedef float2 type; };
 template <> struct Pair<double> { typedef double2 type; };
