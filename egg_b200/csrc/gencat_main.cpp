@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "../../include/eggphot.h"
+#include "../../include/eggprops.h"
 #include "fitscol.hpp"
 
 namespace {
@@ -196,7 +197,10 @@ int list_bands(const std::string &pattern, const std::string &db_file) {
 void print_help() {
     std::cout <<
         "egg-gencat-b200: the photometry stage of egg-gencat (fluxes and rest-frame magnitudes) on NVIDIA B200\n"
-        "usage: egg-gencat-b200 input_props=catalog.fits [options]\n\n"
+        "usage: egg-gencat-b200 input_props=catalog.fits [options]\n"
+        "       egg-gencat-b200 input_cat=catalog.fits [options]\n\n"
+        "  input_cat=FILE     catalog holding ID RA DEC Z M PASSIVE: every other property is generated on the GPU\n"
+        "                     (src/egg-gencat.cpp:1360-2022; seed=42 no_random no_passive_lir magdis_tdust ms_disp=0.3)\n"
         "  input_props=FILE   egg catalog holding the per-galaxy columns (Z D M_DISK M_BULGE M2LCOR OPT_SED_DISK\n"
         "                     OPT_SED_BULGE IR_SED LIR FPAH MDUST IGM_ABS VDISP LINE_LUM_DISK LINE_LUM_BULGE LINE_LAMBDA)\n"
         "  bands=[...]        bands for observed fluxes (default: the 23 bands of egg-gencat)\n"
@@ -251,13 +255,14 @@ int main(int argc, char *argv[]) {
             out_file = std::string("egg-") + buf + ".fits"; // :259-261
         }
         if (verbose) note("will save catalog in '" + out_file + "'");
+        const bool from_cat = !a.has("input_props") && a.has("input_cat");
         const std::string input = a.str("input_props", a.str("input_cat"));
         if (input.empty()) {
             error("this program replaces the photometry stage of egg-gencat only (src/egg-gencat.cpp:2024-2240)");
-            error("pass input_props=<egg catalog> holding the per-galaxy columns; generating them (area=, mmin=, ...) is out of scope");
+            error("pass input_props=<egg catalog> holding the per-galaxy columns, or input_cat=<catalog with Z, M, PASSIVE>; drawing galaxies from the mass functions (area=, mmin=, ...) is out of scope");
             return 1;
         }
-        for (const char *k : {"area", "mmin", "maglim", "zmin", "zmax", "seed", "ra0", "dec0", "mass_func", "no_pos", "no_clust"})
+        for (const char *k : {"area", "mmin", "maglim", "zmin", "zmax", "ra0", "dec0", "mass_func", "no_pos", "no_clust"})
             if (a.has(k) && verbose) note(std::string("option '") + k + "' only affects catalog generation and is ignored");
         const std::vector<std::string> dflt_bands = {"vimos-u", "hst-f435w", "hst-f606w", "hst-f775w", "hst-f814w", "hst-f850lp",
             "hst-f105w", "hst-f125w", "hst-f140w", "hst-f160w", "hawki-Ks", "spitzer-irac1", "spitzer-irac2", "spitzer-irac3",
@@ -274,6 +279,98 @@ int main(int argc, char *argv[]) {
         // ---- catalog
         if (verbose) note("reading galaxy properties from '" + input + "'...");
         fitscol::Table cat = fitscol::read_table(input);
+        if (from_cat) {
+            // ---- galaxy properties on the GPU (src/egg-gencat.cpp:714-779 for the input, :1360-2022 for the recipes)
+            for (const char *k : {"Z", "M", "PASSIVE"})
+                if (!cat.find(k)) { error(std::string("input catalog has no column ") + k + " (needed: ID RA DEC Z M PASSIVE)"); return 1; }
+            const std::vector<float> cz = fitscol::as_float(*cat.find("Z")), cm = fitscol::as_float(*cat.find("M"));
+            const std::vector<uint8_t> cp = fitscol::as_bool(*cat.find("PASSIVE"));
+            const size_t n = cz.size();
+            if (cm.size() != n || cp.size() != n) { error("catalog columns have inconsistent lengths"); return 1; }
+            size_t nbad = 0;
+            for (size_t i = 0; i < n; ++i) nbad += !(cz[i] > 0) || !(cm[i] > 4) || cm[i] > 13;
+            if (nbad) { // :769-774
+                error("input catalog contains " + std::to_string(nbad) + " unphysical galax" + (nbad == 1 ? "y" : "ies"));
+                note("must have z > 0 and 4 < m < 13");
+                return 1;
+            }
+            if (verbose) note("found " + std::to_string(n) + " galaxies");
+            for (const char *k : {"LIR", "TDUST", "IR8"})
+                if (cat.find(k)) { error(std::string("user-provided ") + k + " values in the input catalog are not supported"); return 1; }
+            eggprops_libs PL{};
+            std::vector<float> buv, bvj, av;
+            std::vector<uint8_t> use;
+            std::vector<double> ct, cld, clp, c8d, c8p;
+            if (!no_stellar) {
+                fitscol::Table t = fitscol::read_table(opt_lib_file);
+                const fitscol::Column *cu = t.find("BUV"), *cv = t.find("BVJ"), *ca = t.find("AV"), *cs = t.find("USE");
+                if (!cu || !cv || !ca || !cs || cu->dims.size() != 2) { error("optical library '" + opt_lib_file + "' must hold BUV, BVJ [2][n], AV and USE"); return 1; }
+                buv = fitscol::as_float(*cu); bvj = fitscol::as_float(*cv); av = fitscol::as_float(*ca); use = fitscol::as_bool(*cs);
+                PL.nuv = (uint32_t)cu->dims[1]; PL.nvj = (uint32_t)cv->dims[1];
+                PL.buv = buv.data(); PL.bvj = bvj.data(); PL.av = av.data(); PL.use = use.data();
+            }
+            {
+                fitscol::Table t = fitscol::read_table(ir_lib_file);
+                const std::string base = basename_of(ir_lib_file);
+                const fitscol::Column *cs = t.find(base == "ir_lib_cs17.fits" ? "DUST" : "SED");
+                if (!cs) { error("missing LAM and/or SED columns in the IR library file"); return 1; }
+                PL.nir_sed = cs->dims.size() == 2 ? (uint32_t)cs->dims[0] : 1;
+                if (PL.nir_sed == 1) PL.ir_lib = EGGPROPS_IR_SINGLE;                        // :1682
+                else if (base == "ir_lib_ce01.fits") PL.ir_lib = EGGPROPS_IR_CE01;
+                else if (base == "ir_lib_m12.fits") PL.ir_lib = EGGPROPS_IR_M12;
+                else if (base == "ir_lib_cs17.fits") {
+                    PL.ir_lib = EGGPROPS_IR_CS17;
+                    for (const char *k : {"TDUST", "LIR_DUST", "LIR_PAH", "L8_DUST", "L8_PAH"})
+                        if (!t.find(k)) { error(std::string("IR library '") + ir_lib_file + "' has no column " + k); return 1; }
+                    ct = fitscol::as_double(*t.find("TDUST")); cld = fitscol::as_double(*t.find("LIR_DUST")); clp = fitscol::as_double(*t.find("LIR_PAH"));
+                    c8d = fitscol::as_double(*t.find("L8_DUST")); c8p = fitscol::as_double(*t.find("L8_PAH"));
+                    PL.cs17_tdust = ct.data(); PL.cs17_lir_dust = cld.data(); PL.cs17_lir_pah = clp.data(); PL.cs17_l8_dust = c8d.data(); PL.cs17_l8_pah = c8p.data();
+                } else { error("no calibration code available for the IR library '" + ir_lib_file + "'"); return 1; } // :1702
+            }
+            eggprops_opts PO{};
+            PO.seed = (uint64_t)a.num("seed", 42);
+            PO.no_random = a.flag("no_random"); PO.no_stellar = no_stellar; PO.no_nebular = no_nebular;
+            PO.no_passive_lir = a.flag("no_passive_lir"); PO.magdis_tdust = a.flag("magdis_tdust");
+            PO.ms_disp = a.num("ms_disp", 0.3);
+            PO.igm = igm == "madau95" ? EGGPROPS_IGM_MADAU95 : (igm == "inoue14" ? EGGPROPS_IGM_INOUE14 : EGGPROPS_IGM_NONE);
+            PO.h0 = 70.0; PO.omega_m = 0.3; PO.omega_l = 0.7;
+            if (verbose) note("generating galaxy properties on the GPU...");
+            eggprops_ctx *pc = nullptr;
+            int rc = eggprops_create(&PL, &PO, &pc);
+            if (rc) { error(pc ? eggprops_last_error(pc) : "allocation failed"); eggprops_destroy(pc); return 1; }
+            struct F { const char *name; std::vector<float> v; size_t w; };
+            std::vector<F> f32 = {{"D", {}, 1}, {"BT", {}, 1}, {"M_BULGE", {}, 1}, {"M_DISK", {}, 1}, {"DISK_ANGLE", {}, 1}, {"BULGE_ANGLE", {}, 1},
+                {"DISK_RATIO", {}, 1}, {"BULGE_RATIO", {}, 1}, {"DISK_RADIUS", {}, 1}, {"BULGE_RADIUS", {}, 1}, {"SFR", {}, 1}, {"RSB", {}, 1}, {"IRX", {}, 1},
+                {"SFRIR", {}, 1}, {"SFRUV", {}, 1}, {"RFUV_DISK", {}, 1}, {"RFVJ_DISK", {}, 1}, {"RFUV_BULGE", {}, 1}, {"RFVJ_BULGE", {}, 1}, {"M2LCOR", {}, 1},
+                {"AV_DISK", {}, 1}, {"AV_BULGE", {}, 1}, {"TDUST", {}, 1}, {"IR8", {}, 1}, {"LIR", {}, 1}, {"FPAH", {}, 1}, {"MDUST", {}, 1}, {"IGM_ABS", {}, 3},
+                {"AVLINES_DISK", {}, 1}, {"AVLINES_BULGE", {}, 1}, {"VDISP", {}, 1}, {"LINE_LUM_DISK", {}, EGGPROPS_NLINE}, {"LINE_LUM_BULGE", {}, EGGPROPS_NLINE}};
+            for (F &f : f32) f.v.assign(n * f.w, 0.0f);
+            std::vector<uint64_t> od(n), ob(n), is(n);
+            eggprops_out E{};
+            float **slots[] = {&E.d, &E.bt, &E.m_bulge, &E.m_disk, &E.disk_angle, &E.bulge_angle, &E.disk_ratio, &E.bulge_ratio, &E.disk_radius, &E.bulge_radius,
+                &E.sfr, &E.rsb, &E.irx, &E.sfrir, &E.sfruv, &E.rfuv_disk, &E.rfvj_disk, &E.rfuv_bulge, &E.rfvj_bulge, &E.m2lcor, &E.av_disk, &E.av_bulge,
+                &E.tdust, &E.ir8, &E.lir, &E.fpah, &E.mdust, &E.igm_abs, &E.avlines_disk, &E.avlines_bulge, &E.vdisp, &E.line_lum_disk, &E.line_lum_bulge};
+            for (size_t k = 0; k < f32.size(); ++k) *slots[k] = f32[k].v.data();
+            E.opt_sed_disk = od.data(); E.opt_sed_bulge = ob.data(); E.ir_sed = is.data();
+            rc = eggprops_compute(pc, cz.data(), cm.data(), cp.data(), n, 0, &E);
+            if (rc) { error(eggprops_last_error(pc)); eggprops_destroy(pc); return 1; }
+            eggprops_destroy(pc);
+            for (const F &f : f32) {
+                const bool line_col = std::string(f.name).rfind("LINE_", 0) == 0 || std::string(f.name).rfind("AVLINES", 0) == 0 || std::string(f.name) == "VDISP";
+                if (line_col && no_nebular) continue;
+                cat.set(fitscol::make_f32(f.name, f.v, f.w > 1 ? std::vector<long>{(long)n, (long)f.w} : std::vector<long>{}));
+            }
+            cat.set(fitscol::make_u64("OPT_SED_DISK", od)); cat.set(fitscol::make_u64("OPT_SED_BULGE", ob)); cat.set(fitscol::make_u64("IR_SED", is));
+            if (!no_nebular) {
+                std::vector<std::string> names;
+                std::vector<float> lam(eggprops_line_lambda(), eggprops_line_lambda() + EGGPROPS_NLINE), tot(n * EGGPROPS_NLINE);
+                for (uint32_t l = 0; l < EGGPROPS_NLINE; ++l) names.push_back(eggprops_line_name(l));
+                const std::vector<float> &ld = f32[31].v, &lb = f32[32].v;
+                for (size_t i = 0; i < tot.size(); ++i) tot[i] = ld[i] + lb[i];                 // :2024
+                cat.set(fitscol::make_strings("LINES", names)); cat.set(fitscol::make_f32("LINE_LAMBDA", lam));
+                cat.set(fitscol::make_f32("LINE_LUM", tot, {(long)n, (long)EGGPROPS_NLINE}));
+            }
+        }
         auto need = [&](const char *name) -> const fitscol::Column & {
             const fitscol::Column *c = cat.find(name);
             if (!c) throw std::runtime_error(std::string("catalog '") + input + "' has no column " + name);

@@ -158,3 +158,48 @@ def test_two_gpu_shards_give_the_same_catalog(tmp_path):
     a, b = fitscol.read_table(str(tmp_path / "one.fits")), fitscol.read_table(str(tmp_path / "two.fits"))
     for k in ("FLUX", "FLUX_DISK", "FLUX_BULGE", "RFMAG", "RFMAG_DISK", "RFMAG_BULGE"):
         np.testing.assert_array_equal(a[k], b[k])
+
+
+@pytest.mark.gpu
+def test_input_cat_generates_the_properties_on_the_gpu(tmp_path):
+    """input_cat=: ID RA DEC Z M PASSIVE in, every property column (src/egg-gencat.cpp:1360-2022) and the fluxes out."""
+    import egg_b200
+    from egg_b200 import properties
+    _need_cli()
+    L = cases.libs()
+    opt, ir = L["opt"], L["ce01"]
+    n = 400
+    rng = np.random.default_rng(12)
+    z, m = rng.uniform(0.1, 6, n).astype(np.float32), rng.uniform(8, 11.5, n).astype(np.float32)
+    pas = rng.random(n) < 0.3
+    bands = synth.B4 + ["spitzer-irac1"]
+    db = _filter_db(tmp_path, bands)
+    fitscol.write_table(str(tmp_path / "opt_lib.fits"), {k.upper(): np.asarray(v) for k, v in opt.items()})
+    fitscol.write_table(str(tmp_path / "ir_lib_ce01.fits"), {"LAM": np.asarray(ir["lam"]), "SED": np.asarray(ir["sed"])})
+    fitscol.write_table(str(tmp_path / "zm.fits"), {"ID": np.arange(n, dtype=np.uint64), "RA": np.zeros(n), "DEC": np.zeros(n),
+                                                     "Z": z, "M": m, "PASSIVE": pas})
+    args = [f"input_cat={tmp_path}/zm.fits", f"filter_db={db}", f"opt_lib={tmp_path}/opt_lib.fits", f"ir_lib={tmp_path}/ir_lib_ce01.fits",
+            "bands=[" + ",".join(bands) + "]", f"out={tmp_path}/out.fits", "seed=7"]
+    r = _run(*args)
+    assert r.returncode == 0, r.stderr
+    t = fitscol.read_table(str(tmp_path / "out.fits"))
+    pr = properties.Properties(opt, seed=7)
+    want = pr.compute(z, m, pas)
+    pr.close()
+    for k, v in want.items():
+        np.testing.assert_array_equal(t[k.upper()], v, err_msg=k)                       # same library underneath
+    assert list(t["LINES"]) == properties.line_table()[0]
+    np.testing.assert_array_equal(t["LINE_LUM"], want["line_lum_disk"] + want["line_lum_bulge"])
+    np.testing.assert_array_equal(t["PASSIVE"], pas)                                   # input columns pass through
+    gal = {k: want[k] for k in ("d", "m_disk", "m_bulge", "m2lcor", "opt_sed_disk", "opt_sed_bulge", "ir_sed", "lir", "igm_abs",
+                                "vdisp", "line_lum_disk", "line_lum_bulge")}
+    gal["z"] = z
+    ph = egg_b200.Photometry(opt, ir, synth.get_filters(bands), line_lambda=properties.line_table()[1])
+    f = ph.compute(gal)
+    ph.close()
+    np.testing.assert_array_equal(t["FLUX"], f["flux"])
+    # the reference's input check (src/egg-gencat.cpp:769-774)
+    fitscol.write_table(str(tmp_path / "bad.fits"), {"ID": np.arange(2, dtype=np.uint64), "Z": np.array([0.5, -1.0], np.float32),
+                                                      "M": np.array([10.0, 10.0], np.float32), "PASSIVE": np.array([False, True])})
+    r = _run(*[x.replace("zm.fits", "bad.fits") for x in args])
+    assert r.returncode == 1 and "1 unphysical galaxy" in r.stderr
