@@ -4,7 +4,7 @@
 // photometry), results rounded once to the reference's column types.  Every formula cites the reference
 // line it restates (src/egg-gencat.cpp); constants are the reference's calibration values.  Random scatter
 // comes from Philox4x32-10 keyed by the seed with counter (galaxy index, draw slot): see eggprops.h.
-// The same algorithm, line by line, is oracle/props_oracle.py (test infrastructure).
+// The tests check this kernel against a numpy restatement of the same lines (same generator, same draw slots).
 #include <cuda_runtime.h>
 
 #include <cmath>
