@@ -507,6 +507,14 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
             EGG_PHASE(Blines)
         }
 
+        // disk lines whose nodes no band of the galaxy reads (far-IR and CO lines beyond the reddest band, mostly) need
+        // no deposit: their windows are emptied here, before the line phase reads them (a barrier away)
+        for (int idx = tid; idx < ng * nline; idx += NT) {
+            const int gi = idx / nline, l = idx - gi * nline;
+            int *w = lb + 2 * ((2 * gi + 1) * nline + l);
+            if (w[0] <= w[1] && (w[0] > jneed[gi][1] || w[1] < jneed[gi][0])) { w[0] = 1; w[1] = 0; }
+        }
+
         // ---- phase A2b: disk SEDs (get_opt_sed / get_ir_sed / merge_add / IGM, src/egg-gencat.cpp:2104-2140) and the
         //      bulge SED resampled on the disk grid (the same piece-wise linear function; lets phase B serve both
         //      components from one set of weights), stored as {disk, bulge} pairs
