@@ -59,14 +59,15 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // ---- per-galaxy scalars ----------------------------------------------------------------------------
-struct GalScal {
+struct alignas(16) GalScal {
+    // the four scalars every (band, galaxy) item reads, adjacent and 16-byte aligned: two 16-byte loads
     double opz;      // 1 + z
+    double iopz;     // 1/(1+z)
     double aflux;    // K (1+z) / d^2          [vif] lsun2uJy(z, d, ...)   (src/egg-gencat.cpp:2162)
     double a_bulge;  // 10^(m_bulge - m2lcor)  get_opt_sed mass scale      (:711, :2106)
     double a_disk;   // 10^(m_disk  - m2lcor)
     double c1, c2;   // IR: L_IR (generic, :2055) or Mdust(1-fPAH), Mdust fPAH (cs17, :2047-2051)
     double vdisp;
-    double iopz;     // 1/(1+z)
     float l2opz;     // log2(1+z) * kLutPerOctave
     float igm[3];
     uint32_t row_b, row_d, row_i;
@@ -233,7 +234,7 @@ __device__ __forceinline__ GridBD ldg_grid(const GridBD *g) {
 }
 
 struct SmemLayout {
-    uint32_t tab, res, rfres, lb, lt, win, wmid, wflag, total;
+    uint32_t tab, res, rfres, lb, lt, win, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(const FluxParams &p) {
     SmemLayout L;
@@ -245,9 +246,7 @@ __host__ __device__ inline SmemLayout smem_layout(const FluxParams &p) {
     L.rfres = o; o += up((size_t)p.batch * p.nrf * 2 * sizeof(double));           // [gal][rf][comp] rest-frame fluxes
     L.lb = o; o += up((size_t)p.batch * 2 * nl * 2 * sizeof(int));                // line windows [b0, b1]
     L.lt = o; o += up((size_t)p.batch * 2 * nl * 2 * sizeof(int));                // line tasks {first owned node, task offset}
-    L.win = o; o += up((size_t)p.batch * p.nband_total * sizeof(uint32_t));       // node windows (jlo | jhi << 16)
-    L.wmid = o; o += up((size_t)p.batch * p.nband_total * sizeof(uint16_t));      // node left of the band's split
-    L.wflag = o; o += up((size_t)p.batch * p.nband_total);                        // bit 0: bulge covered
+    L.win = o; o += up((size_t)p.batch * p.nband_total * sizeof(uint2));          // node windows {jlo | jhi << 16, split node | bulge flag << 16}
     L.total = o;
     return L;
 }
@@ -285,9 +284,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
     double *rfres = reinterpret_cast<double *>(smem + L.rfres);
     int *lb = reinterpret_cast<int *>(smem + L.lb); // [gal][comp][line][2]
     int *lt = reinterpret_cast<int *>(smem + L.lt); // [gal][comp][line][2]
-    uint32_t *win = reinterpret_cast<uint32_t *>(smem + L.win); // [band in group order][gal]
-    uint16_t *wmid = reinterpret_cast<uint16_t *>(smem + L.wmid);
-    uint8_t *wflag = smem + L.wflag;
+    uint2 *win = reinterpret_cast<uint2 *>(smem + L.win); // [band in group order][gal]: one 8-byte record per item
     const BandHeader *hdr = reinterpret_cast<const BandHeader *>(blob);
     const int ncomp = p.has_bulge ? 2 : 1;
     const bool cs17 = p.ir_kind == EGGPHOT_IR_CS17;
@@ -369,9 +366,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                     if (p.has_bulge && nB >= 2 && __ldg(p.xB) * s.opz <= full_first && __ldg(p.xB + nB - 1) * s.opz >= full_last) fl = 1;
                 }
             }
-            win[idx] = wv;
-            wmid[idx] = wm;
-            wflag[idx] = fl;
+            win[idx] = make_uint2(wv, (uint32_t)wm | ((uint32_t)fl << 16));
         }
         // emission-line windows ([vif] bounds, src/egg-gencat.cpp:2081-2084): one thread per (galaxy, component, line)
         for (int idx = tid; idx < ng * 2 * nline; idx += NT) {
@@ -654,10 +649,11 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                     const int gi = idx & (kBatch - 1), bi = idx / kBatch;
                     if (gi >= ng) continue;
                     const int widx = ((int)p.groups[grp].base + bi) * kBatch + gi;
-                    const uint32_t wv = win[widx];
+                    const uint2 wrec = win[widx];
+                    const uint32_t wv = wrec.x;
                     if (wv == 0) continue; // not covered, empty response or empty window: flux stays 0
-                    const int jlo = (int)(wv & 0xffffu), jhi = (int)(wv >> 16), b = (int)wmid[widx];
-                    const bool bulge_on = wflag[widx] != 0;
+                    const int jlo = (int)(wv & 0xffffu), jhi = (int)(wv >> 16), b = (int)(wrec.y & 0xffffu);
+                    const bool bulge_on = (wrec.y >> 16) != 0;
                     const BandHeader &h = hdr[bi];
                     const GalScal &s = sc[gi];
                     BandView<real> bv;

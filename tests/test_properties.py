@@ -223,3 +223,20 @@ def test_properties_feed_the_photometry_on_the_device():
     assert (want["flux"] > 0).mean() > 0.9
     pr.close()
     ph.close()
+
+
+def test_kernel_and_restatement_hold_the_same_calibration_tables():
+    """CPU tier cross-check of the constants the GPU tier compares through results: IGM quantile fits, line list,
+    axis-ratio densities (the kernel source is parsed, nothing is executed)."""
+    src = open(os.path.join(ROOT, "egg_b200", "csrc", "props_kernels.cu")).read()
+
+    def table(name):
+        body = re.search(name + r"[^=]*=\s*\{(.*?)\};", src, re.S).group(1)
+        return np.array([float(x.rstrip("f")) for x in re.findall(r"-?\d+\.?\d*(?:e-?\d+)?f?", body)], dtype=np.float32)
+    for name, ref in (("c_igm_z1", PO.IGM_Z1), ("c_igm_dz1", PO.IGM_DZ1), ("c_igm_z2", PO.IGM_Z2), ("c_igm_dz2", PO.IGM_DZ2), ("c_igm_q", PO.IGM_Q)):
+        np.testing.assert_array_equal(table(name).astype(np.float64), np.asarray(ref).ravel(), err_msg=name)
+    np.testing.assert_array_equal(table("h_line_lambda"), PO.LINE_LAMBDA)
+    np.testing.assert_array_equal(table("kBulgeP"), np.array(PO.BULGE_RATIO_P, np.float32))
+    np.testing.assert_array_equal(table("kDiskP"), np.array(PO.DISK_RATIO_P, np.float32))
+    np.testing.assert_array_equal(table("kRatioX"), np.array(PO.BULGE_RATIO_X, np.float32))
+    assert re.findall(r'"([a-z0-9_]+)"', re.search(r"h_line_name[^=]*=\s*\{(.*?)\};", src, re.S).group(1)) == PO.LINES
