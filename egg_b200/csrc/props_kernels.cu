@@ -292,21 +292,22 @@ __global__ void __launch_bounds__(128) props_kernel(const __grid_constant__ Prop
     // IGM transmission in the three bands below Ly-alpha, :1731-1824
     double igm_abs[3] = {0.0, 0.0, 0.0};
     if (p.igm == EGGPROPS_IGM_INOUE14) {
+        // transmission at quantile q of band l: product of two error-function steps in redshift (0 where the fit
+        // has no width); 0.5 erfc(-x) = 0.5 (erf(x) + 1) without the cancellation at small transmissions
+        auto quant = [&](int l, int q) {
+            if (c_igm_dz1[l][q] == 0.0f) return 0.0;
+            double t = 0.5 * erfc(-((double)c_igm_z1[l][q] - z) / (double)c_igm_dz1[l][q]);
+            if (c_igm_dz2[l][q] != 0.0f) t *= 0.5 * erfc(-((double)c_igm_z2[l][q] - z) / (double)c_igm_dz2[l][q]);
+            return t;
+        };
         for (int l = 0; l < 3; ++l) {
-            double tq[kNQ];
-            for (int q = 0; q < kNQ; ++q) {
-                tq[q] = 0.0;
-                if (c_igm_dz1[l][q] == 0.0f) continue;
-                tq[q] = 0.5 * erfc(-((double)c_igm_z1[l][q] - z) / (double)c_igm_dz1[l][q]); // = 0.5 (erf(x) + 1), without the cancellation
-                if (c_igm_dz2[l][q] == 0.0f) continue;
-                tq[q] *= 0.5 * erfc(-((double)c_igm_z2[l][q] - z) / (double)c_igm_dz2[l][q]);
-            }
-            if (!rnd) igm_abs[l] = tq[kNQ / 2]; // median transmission
-            else {
+            if (!rnd) igm_abs[l] = quant(l, kNQ / 2); // median transmission
+            else { // the two quantiles that bracket the uniform deviate
                 const double u = d.uniform(S_IGM0 + l);
                 int i = 0;
                 while (i < kNQ - 2 && u >= (double)c_igm_q[i + 1]) ++i;
-                igm_abs[l] = tq[i] + (tq[i + 1] - tq[i]) * (u - (double)c_igm_q[i]) / ((double)c_igm_q[i + 1] - (double)c_igm_q[i]);
+                const double t0 = quant(l, i), t1 = quant(l, i + 1);
+                igm_abs[l] = t0 + (t1 - t0) * (u - (double)c_igm_q[i]) / ((double)c_igm_q[i + 1] - (double)c_igm_q[i]);
             }
         }
     } else if (p.igm == EGGPROPS_IGM_MADAU95) { // FAST's implementation: mean of exp(-tau) over 100 wavelengths per band
