@@ -204,8 +204,19 @@ __device__ __forceinline__ Vec16<double> ldg16(const double *p) {
     const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
     return Vec16<double>{{a.x, a.y}};
 }
-__device__ __forceinline__ void st16(float *p, const Vec16<float> &q) { *reinterpret_cast<float4 *>(p) = make_float4(q.v[0], q.v[1], q.v[2], q.v[3]); }
-__device__ __forceinline__ void st16(double *p, const Vec16<double> &q) { *reinterpret_cast<double2 *>(p) = make_double2(q.v[0], q.v[1]); }
+// the same with an L2 evict-last hint: the scratch is re-read and rewritten every batch and should outlive the
+// streamed inputs and outputs in L2
+__device__ __forceinline__ uint64_t evict_last_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void st16_keep(float *p, const Vec16<float> &q, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(q.v[0]), "f"(q.v[1]), "f"(q.v[2]), "f"(q.v[3]), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st16_keep(double *p, const Vec16<double> &q, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(q.v[0]), "d"(q.v[1]), "l"(pol) : "memory");
+}
 // four consecutive elements of a 16-byte aligned row
 template <typename real> struct Quad { real v[4]; };
 __device__ __forceinline__ Quad<float> ldg4(const float *p) {
@@ -518,6 +529,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
             // to four galaxies: the disk -> optical maps of the nodes are loaded once per task (L1 is too small to
             // keep them).  Nodes that are optical nodes themselves carry a zero fraction: fma(0, b1 - b0, b0) = b0.
             constexpr int NPL = 16 / (int)sizeof(real), LG = NPL == 4 ? 7 : 6;
+            const uint64_t keep = evict_last_policy(); // scratch lines should outlive the streamed data in L2 (halves the write-backs)
             const real *ofrac = reinterpret_cast<const real *>(p.u_ofrac);
             // Only the nodes some band of the galaxy reads are built (jneed: union of its node windows).
             const int ncD = (nD + 32 * NPL - 1) >> LG, nq = (ng + 3) >> 2;
@@ -603,7 +615,7 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                     for (int h = 0; h < 2; ++h) {
 #pragma unroll
                         for (int k = 0; k < NPL / 2; ++k) { st.v[2 * k] = v[h * (NPL / 2) + k]; st.v[2 * k + 1] = w[h * (NPL / 2) + k]; }
-                        st16(DU + 2 * j0 + h * NPL, st);
+                        st16_keep(DU + 2 * j0 + h * NPL, st, keep);
                     }
                 }
             }
