@@ -76,7 +76,7 @@ constexpr int batch_of(int precision) { return precision == EGGPHOT_FP64 ? kBatc
 // Band tables are structure-of-arrays in shared memory (a warp's lanes sit on neighbouring filter cells:
 // 8-byte strides spread them over the banks).  Per band, n = nodes of the effective span:
 //   f[n+1]   double  centred node positions lambda_c - fc; f[n] = +inf (sentinel of the cell scan)
-//   lam[n]   double  Lambda at the node, k0[n] double K0 at the node (two-sided gauge, see above);
+//   lk[n]    double x2 {Lambda, K0} at the node (two-sided gauge, see above), one 16-byte record per cell;
 //                    entry n-1 is the open cell right of the last node (lam = k0 = 0 in its gauge)
 //   hr[n]    real    R_c / 2 (0 in the open cell)
 //   sdl[n]   real x2 slope of R in the cell (0 in zero-width cells and in the open cell), cell width (huge in the
@@ -120,8 +120,10 @@ struct __attribute__((aligned(16))) GridA { double x, idx; };
 struct __attribute__((aligned(16))) GridBD { double dx, dxo; };
 
 // Band seen through the kernel's real type.
+struct alignas(16) LamK0 { double lam, k0; }; // Lambda and K0 of a cell: one 16-byte shared-memory load
 template <typename real> struct BandView {
-    const double *f, *lam, *k0;
+    const double *f;
+    const LamK0 *lk;
     const real *hr;
     const Pair2<real> *sdl;
     const uint16_t *bkt;
@@ -132,8 +134,7 @@ template <typename real> struct BandView {
 };
 template <typename real> EGG_HD void make_band_view(const uint8_t *blob, const BandHeader &h, BandView<real> &v) {
     v.f = reinterpret_cast<const double *>(blob + h.f_off);
-    v.lam = reinterpret_cast<const double *>(blob + h.lam_off);
-    v.k0 = reinterpret_cast<const double *>(blob + h.k0_off);
+    v.lk = reinterpret_cast<const LamK0 *>(blob + h.lam_off);
     v.hr = reinterpret_cast<const real *>(blob + h.hr_off);
     v.sdl = reinterpret_cast<const Pair2<real> *>(blob + h.sdl_off);
     v.bkt = reinterpret_cast<const uint16_t *>(blob + h.bkt_off);
@@ -163,7 +164,8 @@ template <typename real> EGG_HD int find_cell(const BandView<real> &b, double t)
 template <typename real> EGG_HD double lambda_in_cell(const BandView<real> &b, int c, double t, double &u) {
     const int cs = cell_slot(c);
     u = t - b.f[cs];
-    return fma(u, fma(u, (double)b.hr[cs], b.k0[cs]), b.lam[cs]);
+    const LamK0 lk = b.lk[cs];
+    return fma(u, fma(u, (double)b.hr[cs], lk.k0), lk.lam);
 }
 
 // gamma = s b u (b - u), b = min(dt + u, dl): the trapezoid-error term of the union cell that starts at

@@ -714,7 +714,8 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                         const Pair2<real> sd = bv.sdl[cs];
                         const bool inner = j > jlo && j < jhi;
                         const double u = t - bv.f[cs];
-                        const double lam = inner ? fma(u, fma(u, (double)bv.hr[cs], bv.k0[cs]), bv.lam[cs]) : 0.0; // 0 at both window ends
+                        const LamK0 lk = bv.lk[cs];
+                        const double lam = inner ? fma(u, fma(u, (double)bv.hr[cs], lk.k0), lk.lam) : 0.0; // 0 at both window ends
                         const real ur = inner ? (real)u : real(0);
                         const real sr = sd.x, dlr = sd.y;
                         double dlam = __shfl_down_sync(kFull, lam, 1) - lam;

@@ -213,8 +213,8 @@ void append_band(std::vector<uint8_t> &blob, size_t header_pos, const BandTableD
     const auto &c = t.cells;
     if (n > 0) {
         h.f_off = append_cells<double>(blob, n + 1, 1, [&](size_t i, int) { return c[i].f; });
-        h.lam_off = append_cells<double>(blob, n, 1, [&](size_t i, int) { return c[i].lam; });
-        h.k0_off = append_cells<double>(blob, n, 1, [&](size_t i, int) { return c[i].k0; });
+        h.lam_off = append_cells<double>(blob, n, 2, [&](size_t i, int w) { return w ? c[i].k0 : c[i].lam; });
+        h.k0_off = h.lam_off + 8; // interleaved with Lambda: {Lambda, K0} records
         if (precision == EGGPHOT_FP64) {
             h.hr_off = append_cells<double>(blob, n, 1, [&](size_t i, int) { return c[i].hr; });
             h.sdl_off = append_cells<double>(blob, n, 2, [&](size_t i, int w) { return w ? c[i].dl : c[i].s; });
