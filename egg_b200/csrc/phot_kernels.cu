@@ -1,22 +1,25 @@
 // phot_kernels.cu — sm_100a kernels of the photometry path.
 //
 // flux_kernel<real> replaces the two get_flux passes and the totals of src/egg-gencat.cpp:2097-2239.
-// One persistent CTA walks batches of kBatch galaxies.  Per batch it
-//   A. derives the per-galaxy scalars ((1+z), K(1+z)/d^2, 10^(M - m2lcor), L_IR ...), builds the
-//      rest-frame SEDs of every disk (optical + IR on the merge_add grid, IGM applied) and bulge
-//      (get_opt_sed / get_ir_sed / merge_add / IGM block, src/egg-gencat.cpp:708-712, 2039-2057,
-//      2118-2140) into a per-CTA scratch that stays in L2, and deposits the emission lines
-//      (add_emission_line, :2078-2095) with a deterministic owner rule;
-//   B. for each band group: stages the group's filter tables (per filter cell: node position, Lambda,
-//      K0, R/2, slope, width; bucket index) into shared memory with TMA bulk copies (cp.async.bulk, SASS
-//      UBLKCP); warps pull (band, galaxy) items off a shared counter; an item = 32 lanes on 32 consecutive
-//      SED nodes: each lane finds its node's filter cell, evaluates the band's piece-wise quadratic
-//      Lambda there and multiplies it by the curvature of each component's SED at that node, formed from
-//      the node's own three SED values (phot_core.cuh, "curvature form": no data is exchanged between
-//      lanes); per-lane double sums, one shuffle reduction per item; rest-frame magnitudes are dot
+// One persistent CTA per SM walks batches of galaxies (32 in the fp32 mode, 16 in fp64).  Per batch it
+//   A. derives the per-galaxy scalars ((1+z), K(1+z)/d^2, 10^(M - m2lcor), L_IR ...), lays out the node window
+//      [jlo, jhi] and split node of every (band, galaxy) and the windows of the emission lines, and builds the
+//      rest-frame SED of every disk (optical + IR on the merge_add grid, IGM applied) together with the bulge
+//      SED resampled on the same grid (get_opt_sed / get_ir_sed / merge_add / IGM block,
+//      src/egg-gencat.cpp:708-712, 2039-2057, 2118-2140) into a per-CTA scratch that stays in L2 - only at the
+//      nodes some band of the galaxy reads - then deposits the emission lines (add_emission_line, :2078-2095)
+//      with a deterministic owner rule;
+//   B. for each band group: stages the group's filter tables (per filter cell: node position, {Lambda, K0},
+//      R/2, {slope, width}; bucket index) into shared memory with TMA bulk copies (cp.async.bulk, SASS UBLKCP);
+//      warps pull (band, galaxy) items off a shared counter; a pass of an item = 32 lanes on 32 consecutive SED
+//      nodes: each lane finds its node's filter cell (exact, in double), evaluates the band's piece-wise
+//      quadratic Lambda there, the lanes exchange Lambda and its first differences by shuffle and each owned
+//      node's quadrature weight W_j multiplies the disk and bulge SED values (phot_core.cuh, "weights form");
+//      per-lane sums, one shuffle reduction per item for both components; rest-frame magnitudes are dot
 //      products with precomputed z = 0 weights (:2150-2158);
 //   C. applies the reference's data conditions (uncovered band -> 0, non-finite mag -> 99), forms
-//      the totals (:2238-2239) and writes the f32 catalog columns with coalesced stores.
+//      the totals (:2238-2239) and writes the f32 catalog columns with coalesced streaming stores.
+// What limits it is the SM's load/store data pipe.
 #include "phot_kernels.cuh"
 
 #include <cooperative_groups.h>
