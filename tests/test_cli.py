@@ -203,3 +203,33 @@ def test_input_cat_generates_the_properties_on_the_gpu(tmp_path):
                                                       "M": np.array([10.0, 10.0], np.float32), "PASSIVE": np.array([False, True])})
     r = _run(*[x.replace("zm.fits", "bad.fits") for x in args])
     assert r.returncode == 1 and "1 unphysical galaxy" in r.stderr
+
+
+def test_input_cat_is_validated_before_the_device_is_touched(tmp_path):
+    """CPU tier: the reference's input checks (src/egg-gencat.cpp:714-779) and the loud failure without a GPU."""
+    _need_cli()
+    L = cases.libs()
+    fitscol.write_table(str(tmp_path / "opt_lib.fits"), {k.upper(): np.asarray(v) for k, v in L["opt"].items()})
+    fitscol.write_table(str(tmp_path / "ir_lib_ce01.fits"), {"LAM": np.asarray(L["ce01"]["lam"]), "SED": np.asarray(L["ce01"]["sed"])})
+    db = _filter_db(tmp_path, synth.B4)
+    common = [f"filter_db={db}", f"opt_lib={tmp_path}/opt_lib.fits", f"ir_lib={tmp_path}/ir_lib_ce01.fits",
+              "bands=[" + ",".join(synth.B4) + "]", f"out={tmp_path}/out.fits"]
+    ok = {"ID": np.arange(3, dtype=np.uint64), "Z": np.array([0.5, 1.0, 2.0], np.float32), "M": np.array([9.0, 10.0, 11.0], np.float32),
+          "PASSIVE": np.array([False, True, False])}
+    fitscol.write_table(str(tmp_path / "nom.fits"), {k: v for k, v in ok.items() if k != "M"})
+    r = _run(f"input_cat={tmp_path}/nom.fits", *common)
+    assert r.returncode == 1 and "no column M" in r.stderr
+    bad = dict(ok, M=np.array([9.0, 3.5, 14.0], np.float32))
+    fitscol.write_table(str(tmp_path / "bad.fits"), bad)
+    r = _run(f"input_cat={tmp_path}/bad.fits", *common)
+    assert r.returncode == 1 and "2 unphysical galaxies" in r.stderr and "4 < m < 13" in r.stdout + r.stderr
+    fitscol.write_table(str(tmp_path / "lir.fits"), dict(ok, LIR=np.ones(3, np.float32)))
+    r = _run(f"input_cat={tmp_path}/lir.fits", *common)
+    assert r.returncode == 1 and "LIR" in r.stderr
+    fitscol.write_table(str(tmp_path / "ok.fits"), ok)
+    r = _run(f"input_cat={tmp_path}/ok.fits", *[c.replace("ir_lib_ce01.fits", "ir_lib_other.fits") for c in common])
+    assert r.returncode == 1                                                           # unreadable / uncalibrated IR library
+    import torch
+    if not torch.cuda.is_available():
+        r = _run(f"input_cat={tmp_path}/ok.fits", *common)
+        assert r.returncode == 1 and "CUDA" in r.stderr and not os.path.exists(tmp_path / "out.fits")

@@ -240,3 +240,28 @@ def test_kernel_and_restatement_hold_the_same_calibration_tables():
     np.testing.assert_array_equal(table("kDiskP"), np.array(PO.DISK_RATIO_P, np.float32))
     np.testing.assert_array_equal(table("kRatioX"), np.array(PO.BULGE_RATIO_X, np.float32))
     assert re.findall(r'"([a-z0-9_]+)"', re.search(r"h_line_name[^=]*=\s*\{(.*?)\};", src, re.S).group(1)) == PO.LINES
+
+
+def test_ir_library_calibrations_without_scatter():
+    """The three IR-library branches of src/egg-gencat.cpp:1680-1725 on hand-picked galaxies."""
+    L = cases.libs()
+    z = np.array([0.0125, 0.8125, 2.0, 2.635, 5.0])
+    m = np.full(5, 10.0)
+    act = np.zeros(5, bool)
+    # m12: the template index follows the library's redshift grid (:1692-1697); beyond it the last segment is extended
+    o = PO.compute(z, m, act, opt_lib=L["opt"], ir_lib="m12", no_random=True)
+    assert list(o["ir_sed"][:4]) == [0, 3, 6, 7] and o["ir_sed"][4] == 7
+    assert (o["fpah"] == 0.04).all() and np.allclose(o["mdust"], o["lir"] / 1e3)       # placeholders, :1722-1724
+    # cs17: index from the dust temperature (:1699), exact f_PAH and M_dust from the library integrals (:1708-1719)
+    cs = L["cs17"]
+    aux = {k: cs[k] for k in ("tdust", "lir_dust", "lir_pah", "l8_dust", "l8_pah")}
+    o = PO.compute(z, m, act, opt_lib=L["opt"], ir_lib="cs17", ir_aux=aux, no_random=True)
+    want = np.clip(np.round(np.interp(o["tdust"], cs["tdust"], np.arange(len(cs["tdust"])))), 0, len(cs["tdust"]) - 1)
+    inside = (o["tdust"] >= cs["tdust"][0]) & (o["tdust"] <= cs["tdust"][-1])
+    assert inside.any() and list(o["ir_sed"][inside]) == list(want[inside].astype(int))
+    i = o["ir_sed"].astype(int)
+    fp = np.clip(1 / (1 - (cs["lir_pah"][i] - cs["l8_pah"][i] * o["ir8"]) / (cs["lir_dust"][i] - cs["l8_dust"][i] * o["ir8"])), 0, 1)
+    np.testing.assert_allclose(o["fpah"], fp, rtol=1e-13)
+    np.testing.assert_allclose(o["mdust"] * (cs["lir_dust"][i] * (1 - fp) + cs["lir_pah"][i] * fp), o["lir"], rtol=1e-13)
+    # a single-template library (:1682)
+    assert (PO.compute(z, m, act, opt_lib=L["opt"], ir_lib="single", no_random=True)["ir_sed"] == 0).all()
