@@ -698,10 +698,18 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                         }
                     };
                     NodeIn cur, nxt;
-                    fetch(jlo - 1, cur);
-                    for (int jb = jlo - 1; jb < jhi; jb += 30) {
+                    // fp32 mode: lanes 1..30 of a pass own their node and take E and gamma of the left neighbour by shuffle
+                    // (direct form, sum_j S_j W_j, float products: every term has the sign of the flux).  fp64 mode:
+                    // summation by parts, sum_j (E_j + g_j / 2) (S_j - S_{j+1}): a lane needs its right neighbour only
+                    // (two shuffles fewer, 31 owned lanes); the terms are larger than their sum, which double carries
+                    // (in fp32 the float -> double conversions it needs cost what the shuffles save).
+                    constexpr bool kByParts = sizeof(real) == 8;
+                    constexpr int kOwned = kByParts ? 31 : 30;
+                    const int jb0 = kByParts ? jlo : jlo - 1;
+                    fetch(jb0, cur);
+                    for (int jb = jb0; jb < jhi; jb += kOwned) {
                         const int j = jb + lane;
-                        if (jb + 30 < jhi) fetch(jb + 30, nxt);
+                        if (jb + kOwned < jhi) fetch(jb + kOwned, nxt);
                         const GridA g = cur.g;
                         const real2 su = cur.su;
                         real dt, dto, gidx; // observed widths to the next disk / optical node; 1/dx in the mode's type
@@ -721,20 +729,38 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                         const double lam = inner ? fma(u, fma(u, (double)bv.hr[cs], lk.k0), lk.lam) : 0.0; // 0 at both window ends
                         const real ur = inner ? (real)u : real(0);
                         const real sr = sd.x, dlr = sd.y;
-                        double dlam = __shfl_down_sync(kFull, lam, 1) - lam;
-                        if (j == b) dlam += asym_b1;
-                        const double E = dlam * g.idx; // 0 left of jlo and from jhi on: Lambda is 0 on both sides there
-                        double Ep = __shfl_up_sync(kFull, E, 1);
-                        if (j == b + 1) Ep -= tot0z;
-                        const real W = (real)(E - Ep);
-                        const bool own = lane >= 1 && lane <= 30 && j <= jhi;
-                        const real gD = gamma_term<real>(sr, dlr, ur, dt) * gidx;
-                        const real gDp = __shfl_up_sync(kFull, gD, 1);
-                        accd = fma(su.x, own ? fma(real(0.5), gD - gDp, W) : real(0), accd);
-                        if (bulge_on) {
-                            const real gB = gamma_term<real>(sr, dlr, ur, dto) * gidx;
-                            const real gBp = __shfl_up_sync(kFull, gB, 1);
-                            accb = fma(su.y, own ? fma(real(0.5), gB - gBp, W) : real(0), accb);
+                        if constexpr (kByParts) {
+                            const real sxn = __shfl_down_sync(kFull, su.x, 1);
+                            double dlam = __shfl_down_sync(kFull, lam, 1) - lam;
+                            if (j == b) dlam += asym_b1;
+                            const double E = dlam * g.idx;
+                            const bool own = lane <= 30 && j < jhi; // j >= jlo always
+                            const real gD = gamma_term<real>(sr, dlr, ur, dt) * gidx;
+                            accd = fma(E + 0.5 * gD, own ? su.x - sxn : real(0), accd);
+                            // the interval that holds the split node: W_{b+1} takes E_b in the right gauge, E_b - tot0 (1+z)
+                            if (j == b && own) accd = fma(sxn, tot0z, accd);
+                            if (bulge_on) { // warp-uniform
+                                const real syn = __shfl_down_sync(kFull, su.y, 1);
+                                const real gB = gamma_term<real>(sr, dlr, ur, dto) * gidx;
+                                accb = fma(E + 0.5 * gB, own ? su.y - syn : real(0), accb);
+                                if (j == b && own) accb = fma(syn, tot0z, accb);
+                            }
+                        } else {
+                            double dlam = __shfl_down_sync(kFull, lam, 1) - lam;
+                            if (j == b) dlam += asym_b1;
+                            const double E = dlam * g.idx; // 0 left of jlo and from jhi on: Lambda is 0 on both sides there
+                            double Ep = __shfl_up_sync(kFull, E, 1);
+                            if (j == b + 1) Ep -= tot0z;
+                            const real W = (real)(E - Ep);
+                            const bool own = lane >= 1 && lane <= 30 && j <= jhi;
+                            const real gD = gamma_term<real>(sr, dlr, ur, dt) * gidx;
+                            const real gDp = __shfl_up_sync(kFull, gD, 1);
+                            accd = fma(su.x, own ? fma(real(0.5), gD - gDp, W) : real(0), accd);
+                            if (bulge_on) {
+                                const real gB = gamma_term<real>(sr, dlr, ur, dto) * gidx;
+                                const real gBp = __shfl_up_sync(kFull, gB, 1);
+                                accb = fma(su.y, own ? fma(real(0.5), gB - gBp, W) : real(0), accb);
+                            }
                         }
                         cur = nxt;
                     }
