@@ -63,12 +63,12 @@
 namespace eggphot {
 
 // Galaxies a CTA carries through all band groups at a time (powers of two): the more, the fewer table loads per
-// galaxy, as long as the SEDs of all resident batches (148 CTAs x batch x ~14 KB in fp32, twice that in fp64) stay in L2.
+// galaxy, as long as the SEDs of all resident batches (148 CTAs x batch x ~14 KB in fp32, twice that in fp64) stay mostly in L2.
 #ifndef EGG_KBATCH_F32
 #define EGG_KBATCH_F32 32
 #endif
 #ifndef EGG_KBATCH_F64
-#define EGG_KBATCH_F64 16
+#define EGG_KBATCH_F64 32
 #endif
 constexpr int kBatchF32 = EGG_KBATCH_F32, kBatchF64 = EGG_KBATCH_F64;
 constexpr int batch_of(int precision) { return precision == EGGPHOT_FP64 ? kBatchF64 : kBatchF32; }
