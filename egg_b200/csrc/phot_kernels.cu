@@ -472,7 +472,10 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
                     double acc = 0.0;
                     for (int k = l; k < nline; ++k) {
                         const int k0 = wb[2 * k], k1 = wb[2 * k + 1];
-                        if (k0 > k1) continue; // empty window
+                        if (k0 > k1) { // empty window; the past-the-end marker of the skipped red lines ends the scan
+                            if (k0 >= n) break;
+                            continue;
+                        }
                         if (k0 > j) break;     // windows are ordered: no later line reaches back to j
                         if (j <= k1) {
                             const double l0 = (double)p.line_lambda[k], lw = l0 * (s.vdisp / 2.998e5);
@@ -521,7 +524,11 @@ __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ Flu
         for (int idx = tid; idx < ng * nline; idx += NT) {
             const int gi = idx / nline, l = idx - gi * nline;
             int *w = lb + 2 * ((2 * gi + 1) * nline + l);
-            if (w[0] <= w[1] && (w[0] > jneed[gi][1] || w[1] < jneed[gi][0])) { w[0] = 1; w[1] = 0; }
+            if (w[0] <= w[1]) {
+                // empty either way; a window that starts past every node also ends the ordered line scans of the deposit
+                if (w[0] > jneed[gi][1]) { w[0] = nD; w[1] = nD - 1; }
+                else if (w[1] < jneed[gi][0]) { w[0] = 1; w[1] = 0; }
+            }
         }
 
         // ---- phase A2b: disk SEDs (get_opt_sed / get_ir_sed / merge_add / IGM, src/egg-gencat.cpp:2104-2140) and the
