@@ -22,7 +22,6 @@
 // What limits it is the SM's load/store data pipe.
 #include "phot_kernels.cuh"
 
-#include <cooperative_groups.h>
 #include <cstdio>
 #include <cstdlib>
 

@@ -7,6 +7,7 @@
 // The tests check this kernel against a numpy restatement of the same lines (same generator, same draw slots).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>

@@ -17,7 +17,7 @@
  *
  * Not covered (reported as EGGPHOT_ERR_UNSUPPORTED where reachable): user-provided LIR / Tdust / IR8 columns of an
  * input catalog (:1639-1663, an O(n^2) nearest-neighbour swap), IR libraries without a calibration (:1702).
- * There is NO CPU fallback.
+ * There is NO CPU fallback.  A context belongs to one GPU and may be used from one host thread at a time.
  */
 #ifndef EGGPROPS_H
 #define EGGPROPS_H
