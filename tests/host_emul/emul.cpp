@@ -143,27 +143,43 @@ void run(const Prepared &P, const eggphot_galaxies &G, size_t ngal, double *fd, 
                             gD[j - jlo] = gamma_term<real>(sr, dlr, ur, dxr * opzr) * (real)gr.idx[j];
                             if (bulge_on) gB[j - jlo] = gamma_term<real>(sr, dlr, ur, (real)P.u_dxo[j] * opzr) * (real)gr.idx[j];
                         }
-                        // E_j for jlo <= j < jhi (0 outside); W_j = E_j - E_{j-1} (+ the float gamma terms)
-                        // the kernel keeps one partial sum per lane (node j sits on lane (j - jlo) % 30 + 1 of its pass)
-                        // in the mode's real type and adds the lanes in double
+                        // E_j for jlo <= j < jhi (0 outside).  fp32 mode: W_j = E_j - E_{j-1} (+ the float gamma terms), one
+                        // partial sum per lane in float (node j sits on lane (j - jlo) % 30 + 1 of its pass), lanes added in
+                        // double.  fp64 mode: summation by parts, (E_j + g_j / 2) (S_j - S_{j+1}) per interval (lane
+                        // (j - jlo) % 31 of its pass) plus S_{b+1} tot0 (1+z) in the interval that holds the split node.
                         real accd[32] = {0}, accb[32] = {0};
-                        double Ep = 0;
-                        real gDp = 0, gBp = 0;
-                        for (int j = jlo; j <= jhi; ++j) {
-                            const int k = j - jlo;
-                            double E = 0;
-                            if (j < jhi) {
+                        if (sizeof(real) == 8) {
+                            for (int j = jlo; j < jhi; ++j) {
+                                const int k = j - jlo, ln = k % 31;
                                 double dlam = lam[k + 1] - lam[k];
                                 if (j == b) dlam += asym_b1;
-                                E = dlam * gr.idx[j];
+                                const double E = dlam * gr.idx[j];
+                                accd[ln] = std::fma(E + 0.5 * gD[k], (real)SD[j] - (real)SD[j + 1], accd[ln]);
+                                if (j == b) accd[ln] = std::fma((real)SD[j + 1], (real)tot0z, accd[ln]);
+                                if (bulge_on) {
+                                    accb[ln] = std::fma(E + 0.5 * gB[k], (real)SBU[j] - (real)SBU[j + 1], accb[ln]);
+                                    if (j == b) accb[ln] = std::fma((real)SBU[j + 1], (real)tot0z, accb[ln]);
+                                }
                             }
-                            double Eprev = Ep;
-                            if (j == b + 1) Eprev -= tot0z;
-                            const real W = (real)(E - Eprev);
-                            const int ln = k % 30 + 1;
-                            accd[ln] = std::fma((real)SD[j], W + real(0.5) * (gD[k] - gDp), accd[ln]);
-                            if (bulge_on) accb[ln] = std::fma((real)SBU[j], W + real(0.5) * (gB[k] - gBp), accb[ln]);
-                            Ep = E; gDp = gD[k]; gBp = gB[k];
+                        } else {
+                            double Ep = 0;
+                            real gDp = 0, gBp = 0;
+                            for (int j = jlo; j <= jhi; ++j) {
+                                const int k = j - jlo;
+                                double E = 0;
+                                if (j < jhi) {
+                                    double dlam = lam[k + 1] - lam[k];
+                                    if (j == b) dlam += asym_b1;
+                                    E = dlam * gr.idx[j];
+                                }
+                                double Eprev = Ep;
+                                if (j == b + 1) Eprev -= tot0z;
+                                const real W = (real)(E - Eprev);
+                                const int ln = k % 30 + 1;
+                                accd[ln] = std::fma((real)SD[j], W + real(0.5) * (gD[k] - gDp), accd[ln]);
+                                if (bulge_on) accb[ln] = std::fma((real)SBU[j], W + real(0.5) * (gB[k] - gBp), accb[ln]);
+                                Ep = E; gDp = gD[k]; gBp = gB[k];
+                            }
                         }
                         const double iopz = 1.0 / opz;
                         double sd = 0, sb = 0;
