@@ -171,9 +171,11 @@ template <typename real> EGG_HD double lambda_in_cell(const BandView<real> &b, i
 // gamma = s b u (b - u), b = min(dt + u, dl): the trapezoid-error term of the union cell that starts at
 // an SED node at offset u inside a filter cell of slope s and width dl, the next node of the same SED
 // being dt further (0 for a node that does not start an interval of this SED: gamma = 0).
+// b - u is formed as min(dt, dl - u), not as (dt + u) - u: in a wide filter cell (u >> dt) the latter loses dt's
+// low bits in float (1.4e-5 on a three-node 35 um band found by fuzzing).
 template <typename real> EGG_HD real gamma_term(real s, real dl, real u, real dt) {
-    const real b = (dt + u) < dl ? (dt + u) : dl;
-    return s * b * u * (b - u);
+    const real rest = dl - u, bmu = dt < rest ? dt : rest; // b - u
+    return s * (u + bmu) * u * bmu;
 }
 
 // IGM factor of node j (src/egg-gencat.cpp:2128-2139): [0,lz) -> 0, [lz,l0) -> a0, [l0,l1) -> a1, [l1,l2) -> a2

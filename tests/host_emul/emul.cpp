@@ -163,7 +163,6 @@ void run(const Prepared &P, const eggphot_galaxies &G, size_t ngal, double *fd, 
                             }
                         } else {
                             double Ep = 0;
-                            real gDp = 0, gBp = 0;
                             for (int j = jlo; j <= jhi; ++j) {
                                 const int k = j - jlo;
                                 double E = 0;
@@ -176,9 +175,16 @@ void run(const Prepared &P, const eggphot_galaxies &G, size_t ngal, double *fd, 
                                 if (j == b + 1) Eprev -= tot0z;
                                 const real W = (real)(E - Eprev);
                                 const int ln = k % 30 + 1;
-                                accd[ln] = std::fma((real)SD[j], W + real(0.5) * (gD[k] - gDp), accd[ln]);
-                                if (bulge_on) accb[ln] = std::fma((real)SBU[j], W + real(0.5) * (gB[k] - gBp), accb[ln]);
-                                Ep = E; gDp = gD[k]; gBp = gB[k];
+                                accd[ln] = std::fma((real)SD[j], W, accd[ln]);
+                                if (bulge_on) accb[ln] = std::fma((real)SBU[j], W, accb[ln]);
+                                // the gamma terms by interval (lane ln of the same pass): g_j / 2 (S_j - S_{j+1}), the
+                                // difference of neighbouring SED values being exact in float
+                                if (j < jhi) {
+                                    const int li = ln == 30 ? 0 : ln; // lane 30's interval belongs to the next pass (its lane 0)
+                                    accd[li] = std::fma(real(0.5) * gD[k], (real)SD[j] - (real)SD[j + 1], accd[li]);
+                                    if (bulge_on) accb[li] = std::fma(real(0.5) * gB[k], (real)SBU[j] - (real)SBU[j + 1], accb[li]);
+                                }
+                                Ep = E;
                             }
                         }
                         const double iopz = 1.0 / opz;

@@ -33,6 +33,9 @@ def _edge_bands():
     # finely sampled and wide: thousands of cells per SED interval in the far IR
     lam = np.linspace(60.0, 240.0, 3500)
     bands["fine_fir"] = (lam, np.clip(1 - ((lam - 150) / 85) ** 4, 0, None) * (1 + 0.1 * np.cos(lam)))
+    # three nodes over 6 um in the mid-IR (found by fuzzing): few wide cells over a stretch where the optical grid of
+    # the bulge is much sparser than the disk grid it is evaluated on; the in-cell terms must not amplify rounding
+    bands["coarse_mir"] = (np.array([33.4, 36.65, 39.3]), np.array([0.01, 1.25, 0.01]))
     # reaches beyond the optical grid (160 um rest): bulge uncovered at low z, covered at high z
     bands["edge160"] = (np.linspace(150.0, 400.0, 50), np.hanning(50) + 1e-3)
     return bands
@@ -45,11 +48,18 @@ def _inputs(ngal=48):
     return L["opt"], L["ce01"], gal, list(bands), [bands[k] for k in bands]
 
 
+# Known limit of the fp32 mode: where a filter cell is wider than the spacing of the optical grid
+# (a handful of nodes over several um in the mid-IR) the bulge's in-cell term needs the slope of the bulge SED, which the
+# kernel takes from two neighbouring disk-grid values in float: 5e-5 on the slope, ~1e-5 on the bulge flux.
+LOOSE_FP32 = {"coarse_mir": 3e-5}
+
+
 def _check(out, ref, prec, names, order):
     for k in ("flux_disk", "flux_bulge"):
         e = cases.rel_err(out[k], ref[k], cases.FLOOR[prec])
-        worst = np.unravel_index(np.argmax(e), e.shape)
-        assert e.max() < cases.TOL[prec], f"{k} {prec}: {e.max():.2e} in band {names[order[worst[1]]]}"
+        tol = np.array([LOOSE_FP32.get(names[b], cases.TOL[prec]) if prec == "fp32c" else cases.TOL[prec] for b in order])
+        worst = np.unravel_index(np.argmax(e / tol[None, :]), e.shape)
+        assert (e < tol[None, :]).all(), f"{k} {prec}: {e[worst]:.2e} in band {names[order[worst[1]]]}"
 
 
 @pytest.mark.parametrize("prec", ["fp32c", "fp64"])
