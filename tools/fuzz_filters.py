@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Random filters (node counts 2..400, even / random / clustered sampling, zeroed wings, noisy responses) through the host
 emulation of the device algorithm against the oracle, both modes: `python tools/fuzz_filters.py [seed] [trials]`
-(CPU only; prints every entry above tolerance and the worst errors)."""
+(CPU only; FUZZ_GPU=1 runs the CUDA path instead; prints every entry above tolerance and the worst errors)."""
 import sys, os
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
@@ -37,13 +37,28 @@ for trial in range(int(sys.argv[2]) if len(sys.argv)>2 else 20):
     opts={}
     if rng.random()<0.3: opts['igm']='none'
     if rng.random()<0.3: opts['no_nebular']=True
+    if len(sys.argv)>3:  # wider option sampling
+        for k in ('trim_filters','filter_normalize','filter_flambda','filter_photons','no_dust'):
+            if rng.random()<0.25: opts[k]=True
+        if rng.random()<0.2: opts['igm']='madau95'
+        if rng.random()<0.2: opts['line_profile']='average'
+        if rng.random()<0.2: opts['opt_lib_imf']='chabrier'
     try:
         O=Oracle(opt,ir,bands,line_lambda=synth.LINE_LAMBDA,**opts)
     except Exception as e:
         print('oracle rejects',e); continue
     ref=O.compute(gal,f64=True)
     for prec in ('fp32c','fp64'):
-        out=emul.compute(opt,ir,bands,[],gal,line_lambda=synth.LINE_LAMBDA,precision=prec,**opts)
+        try:
+            if os.environ.get('FUZZ_GPU'):   # the CUDA path itself instead of its host emulation
+                import egg_b200
+                ph=egg_b200.Photometry(opt,ir,bands,line_lambda=synth.LINE_LAMBDA,precision=prec,**opts)
+                o=ph.compute(gal,f64=True); ph.close()
+                out={k:o[k+'_f64'] for k in ('flux_disk','flux_bulge')}
+            else:
+                out=emul.compute(opt,ir,bands,[],gal,line_lambda=synth.LINE_LAMBDA,precision=prec,**opts)
+        except Exception as e:
+            print('emul rejects',opts,str(e)[:80]); continue
         for k in ('flux_disk','flux_bulge'):
             e=cases.rel_err(out[k],ref[k],cases.FLOOR[prec])
             if e.max()>worst[prec]: worst[prec]=e.max()
