@@ -44,7 +44,8 @@ for trial in range(int(sys.argv[2]) if len(sys.argv)>2 else 20):
         if rng.random()<0.2: opts['line_profile']='average'
         if rng.random()<0.2: opts['opt_lib_imf']='chabrier'
     try:
-        O=Oracle(opt,ir,bands,line_lambda=synth.LINE_LAMBDA,**opts)
+        rf=[bands[i] for i in rng.choice(len(bands),2,replace=False)] if len(sys.argv)>3 and rng.random()<0.5 else []
+        O=Oracle(opt,ir,bands,rf,line_lambda=synth.LINE_LAMBDA,**opts)
     except Exception as e:
         print('oracle rejects',e); continue
     ref=O.compute(gal,f64=True)
@@ -52,11 +53,11 @@ for trial in range(int(sys.argv[2]) if len(sys.argv)>2 else 20):
         try:
             if os.environ.get('FUZZ_GPU'):   # the CUDA path itself instead of its host emulation
                 import egg_b200
-                ph=egg_b200.Photometry(opt,ir,bands,line_lambda=synth.LINE_LAMBDA,precision=prec,**opts)
+                ph=egg_b200.Photometry(opt,ir,bands,rf,line_lambda=synth.LINE_LAMBDA,precision=prec,**opts)
                 o=ph.compute(gal,f64=True); ph.close()
-                out={k:o[k+'_f64'] for k in ('flux_disk','flux_bulge')}
+                out={k:o[k+'_f64'] for k in ('flux_disk','flux_bulge')+(('rfmag_disk','rfmag_bulge') if rf else ())}
             else:
-                out=emul.compute(opt,ir,bands,[],gal,line_lambda=synth.LINE_LAMBDA,precision=prec,**opts)
+                out=emul.compute(opt,ir,bands,rf,gal,line_lambda=synth.LINE_LAMBDA,precision=prec,**opts)
         except Exception as e:
             print('emul rejects',opts,str(e)[:80]); continue
         for k in ('flux_disk','flux_bulge'):
@@ -65,4 +66,8 @@ for trial in range(int(sys.argv[2]) if len(sys.argv)>2 else 20):
             if e.max()>cases.TOL[prec]:
                 w=np.unravel_index(np.argmax(e),e.shape)
                 print('FAIL',trial,prec,k,e.max(),'band',O.band_order[w[1]],'n',len(bands[O.band_order[w[1]]][0]),'z',gal['z'][w[0]])
+        if rf:
+            for k in ('rfmag_disk','rfmag_bulge'):
+                dm=np.abs(np.asarray(out[k])-ref[k]); dm=dm[np.isfinite(dm)]
+                if dm.size and dm.max()>(1e-5 if prec=='fp32c' else 1e-9): print('FAIL rf',trial,prec,k,dm.max())
 print('worst',worst)
