@@ -17,6 +17,7 @@
 #include <iostream>
 #include <map>
 #include <regex>
+#include <sstream>
 #include <string>
 #include <thread>
 #include <vector>
@@ -278,7 +279,37 @@ int main(int argc, char *argv[]) {
 
         // ---- catalog
         if (verbose) note("reading galaxy properties from '" + input + "'...");
-        fitscol::Table cat = fitscol::read_table(input);
+        fitscol::Table cat;
+        const bool is_fits = input.size() >= 5 && input.compare(input.size() - 5, 5, ".fits") == 0;
+        if (from_cat && !is_fits) {
+            // plain text: columns ID RA DEC Z M PASSIVE, '#' comments ([vif] ascii::read_table, src/egg-gencat.cpp:765-767)
+            std::ifstream f(input);
+            if (!f) { error("could not open input catalog '" + input + "'"); return 1; }
+            std::vector<uint64_t> id;
+            std::vector<double> ra, dec;
+            std::vector<float> cz, cm;
+            std::vector<uint8_t> cp;
+            std::string line;
+            size_t lineno = 0;
+            while (std::getline(f, line)) {
+                ++lineno;
+                const size_t a = line.find_first_not_of(" \t\r");
+                if (a == std::string::npos || line[a] == '#') continue;
+                std::istringstream is(line);
+                double vid, vra, vdec, vz, vm, vp;
+                if (!(is >> vid >> vra >> vdec >> vz >> vm >> vp)) {
+                    error("input catalog '" + input + "', line " + std::to_string(lineno) + ": expected ID RA DEC Z M PASSIVE");
+                    return 1;
+                }
+                id.push_back((uint64_t)vid); ra.push_back(vra); dec.push_back(vdec);
+                cz.push_back((float)vz); cm.push_back((float)vm); cp.push_back(vp != 0 ? 'T' : 'F');
+            }
+            cat.set(fitscol::make_u64("ID", id)); cat.set(fitscol::make_f64("RA", ra)); cat.set(fitscol::make_f64("DEC", dec));
+            cat.set(fitscol::make_f32("Z", cz)); cat.set(fitscol::make_f32("M", cm));
+            fitscol::Column pc;
+            pc.name = "PASSIVE"; pc.type = 'L'; pc.dims = {(long)cp.size()}; pc.data = cp;
+            cat.set(pc);
+        } else cat = fitscol::read_table(input);
         if (from_cat) {
             // ---- galaxy properties on the GPU (src/egg-gencat.cpp:714-779 for the input, :1360-2022 for the recipes)
             for (const char *k : {"Z", "M", "PASSIVE"})

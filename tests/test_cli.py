@@ -233,3 +233,29 @@ def test_input_cat_is_validated_before_the_device_is_touched(tmp_path):
     if not torch.cuda.is_available():
         r = _run(f"input_cat={tmp_path}/ok.fits", *common)
         assert r.returncode == 1 and "CUDA" in r.stderr and not os.path.exists(tmp_path / "out.fits")
+
+
+def test_ascii_input_catalog_is_read_like_the_reference(tmp_path):
+    """Plain-text input_cat (ID RA DEC Z M PASSIVE, src/egg-gencat.cpp:765-767): same checks as the FITS form."""
+    _need_cli()
+    L = cases.libs()
+    fitscol.write_table(str(tmp_path / "opt_lib.fits"), {k.upper(): np.asarray(v) for k, v in L["opt"].items()})
+    fitscol.write_table(str(tmp_path / "ir_lib_ce01.fits"), {"LAM": np.asarray(L["ce01"]["lam"]), "SED": np.asarray(L["ce01"]["sed"])})
+    db = _filter_db(tmp_path, synth.B4)
+    common = [f"filter_db={db}", f"opt_lib={tmp_path}/opt_lib.fits", f"ir_lib={tmp_path}/ir_lib_ce01.fits",
+              "bands=[" + ",".join(synth.B4) + "]", f"out={tmp_path}/out.fits"]
+    (tmp_path / "bad.txt").write_text("# id ra dec z m passive\n1 53.1 -27.8 0.5 10.2 0\n2 53.1 -27.8 -0.1 10.0 1\n")
+    r = _run(f"input_cat={tmp_path}/bad.txt", *common)
+    assert r.returncode == 1 and "1 unphysical galaxy" in r.stderr
+    (tmp_path / "short.txt").write_text("1 53.1 -27.8 0.5\n")
+    r = _run(f"input_cat={tmp_path}/short.txt", *common)
+    assert r.returncode == 1 and "expected ID RA DEC Z M PASSIVE" in r.stderr
+    (tmp_path / "ok.txt").write_text("# id ra dec z m passive\n1 53.1 -27.8 0.5 10.2 0\n2 53.2 -27.9 1.5 11.0 1\n")
+    import torch
+    r = _run(f"input_cat={tmp_path}/ok.txt", *common, "seed=3")
+    if not torch.cuda.is_available():
+        assert r.returncode == 1 and "CUDA" in r.stderr                     # read and validated, then no device
+    else:
+        assert r.returncode == 0, r.stderr
+        t = fitscol.read_table(str(tmp_path / "out.fits"))
+        assert list(t["ID"]) == [1, 2] and list(t["PASSIVE"]) == [False, True] and t["FLUX"].shape == (2, 4)
