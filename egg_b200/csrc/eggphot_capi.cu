@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -31,10 +32,18 @@ struct DevBuf {
         if (e == cudaSuccess) bytes = n;
         return e;
     }
+    // Blocking copy on the legacy default stream.  The kernels run on non-blocking streams, which do not order
+    // themselves after it, and for small pageable sources the call may return before the DMA has landed: callers
+    // synchronise the device once after their last upload (eggphot_create) or use upload_async on the kernel's stream.
     cudaError_t upload(const void *src, size_t n) {
         cudaError_t e = alloc(n);
         if (e != cudaSuccess || n == 0) return e;
         return cudaMemcpy(p, src, n, cudaMemcpyHostToDevice);
+    }
+    cudaError_t upload_async(const void *src, size_t n, cudaStream_t st) {
+        cudaError_t e = alloc(n);
+        if (e != cudaSuccess || n == 0) return e;
+        return cudaMemcpyAsync(p, src, n, cudaMemcpyHostToDevice, st);
     }
 };
 
@@ -66,6 +75,15 @@ struct eggphot_ctx {
     uint64_t table_bytes = 0;
     Slot slots[kSlots];
     size_t chunk = 0;
+    // the lane-per-galaxy kernel (phot_lane_kernels.cu): its own band groups, grid records, scratch and, per scratch
+    // region, the redshift-bucketing buffers.  EGGPHOT_KERNEL=node selects the node-per-lane kernel of phot_kernels.cu.
+    bool use_lane = true;
+    std::vector<DevBuf> blobs2;
+    DevBuf gridN, nextOpt, lane_scratch;
+    DevBuf zhist[kSlots + 1], zperm[kSlots + 1];
+    LaneParams lbase{};
+    int lane_blocks = 0;
+    size_t lane_region_bytes = 0;
 
     int fail(int code, const std::string &m) { err = m; return code; }
     int cuda_fail(cudaError_t e, const char *what) {
@@ -145,6 +163,26 @@ int enqueue(eggphot_ctx *c, const eggphot_galaxies &g, size_t ngal, const eggpho
     p.scratch = (char *)c->scratch.p + (size_t)region * c->scratch_region_bytes;
     p.do_rf = c->P.rfbands.size() && (o.rfmag || o.rfmag_disk || o.rfmag_bulge || o.rfmag_disk_f64 || o.rfmag_bulge_f64);
     if (p.ngroups == 0 && !p.do_rf) return EGGPHOT_OK;
+    if (c->use_lane) {
+        if (ngal > 0xfffffff0ull) return c->fail(EGGPHOT_ERR_ARG, "more than 2^32 galaxies in one call; split the catalog");
+        cudaError_t ce = c->zperm[region].alloc(ngal * sizeof(uint32_t));
+        if (ce != cudaSuccess) return c->cuda_fail(ce, "allocating the redshift order");
+        LaneParams q = c->lbase;
+        const GroupDesc *groups2 = c->lbase.fp.groups;
+        const uint32_t ngroups2 = c->lbase.fp.ngroups, max_blob2 = c->lbase.fp.max_blob;
+        q.fp = p;
+        q.fp.ngroups = ngroups2; q.fp.max_blob = max_blob2;
+        for (int g = 0; g < kMaxGroups; ++g) q.fp.groups[g] = groups2[g];
+        q.fp.scratch = (char *)c->lane_scratch.p + (size_t)region * c->lane_region_bytes;
+        q.perm = (const uint32_t *)c->zperm[region].p;
+        int e = launch_zsort(g.z, (uint32_t)ngal, (uint32_t *)c->zhist[region].p, (uint32_t *)c->zperm[region].p, c->num_sms, st);
+        if (e != 0) return c->cuda_fail((cudaError_t)e, "redshift bucketing launch");
+        const size_t nbatch = (ngal + kLanes - 1) / kLanes;
+        e = launch_lane_flux_kernel(q, c->P.precision, (int)std::min<size_t>((size_t)c->lane_blocks, nbatch), st);
+        if (e != 0) return c->cuda_fail((cudaError_t)e, "flux kernel launch");
+        c->launches += 4;
+        return EGGPHOT_OK;
+    }
     const size_t nbatch = (ngal + p.batch - 1) / p.batch;
     const int blocks = (int)std::min<size_t>((size_t)c->grid_blocks, nbatch);
     int e = launch_flux_kernel(p, c->P.precision, blocks, st);
@@ -160,6 +198,8 @@ int read_error_flag(eggphot_ctx *c) {
     if (flag) {
         int zero = 0;
         cudaMemcpy(c->errflag.p, &zero, sizeof(int), cudaMemcpyHostToDevice);
+        cudaDeviceSynchronize(); // the reset must have landed before a kernel on a non-blocking stream can set it again
+        if (flag == EGGPHOT_ERR_CUDA) return c->fail(flag, "internal error: a wait inside the flux kernel ran into its spin limit");
         return c->fail(flag, "a galaxy points to a template outside the library or to an unusable optical SED (use = false)");
     }
     return EGGPHOT_OK;
@@ -326,9 +366,47 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
         c->grid_blocks = c->num_sms * occ;
         const size_t rs = P.precision == EGGPHOT_FP64 ? 8 : 4;
         c->scratch_region_bytes = ((size_t)c->grid_blocks * p.batch * (size_t)(2 * c->strideD + c->strideB) * rs + 255) & ~size_t(255);
-        CK(c->scratch.alloc(c->scratch_region_bytes * (kSlots + 1)));
+        const char *sel = getenv("EGGPHOT_KERNEL");
+        c->use_lane = !(sel && (std::string(sel) == "node" || std::string(sel) == "1"));
+        if (!c->use_lane) CK(c->scratch.alloc(c->scratch_region_bytes * (kSlots + 1)));
         p.scratch = c->scratch.p;
     }
+    // ---- the lane kernel's tables, scratch and bucketing buffers
+    {
+        if (P.groups2.size() > (size_t)kMaxGroups) return c->fail(EGGPHOT_ERR_UNSUPPORTED, "more than 16 band groups; raise smem_table_budget");
+        CK(c->gridN.upload(P.grid_nodes.data(), P.grid_nodes.size() * sizeof(GridNode)));
+        CK(c->nextOpt.upload(P.next_opt.data(), P.next_opt.size() * sizeof(int32_t)));
+        c->blobs2.resize(P.groups2.size());
+        LaneParams &q = c->lbase;
+        q.fp = c->base;
+        q.fp.ngroups = (uint32_t)P.groups2.size();
+        q.fp.max_blob = 0;
+        for (size_t g = 0; g < P.groups2.size(); ++g) {
+            CK(c->blobs2[g].upload(P.groups2[g].blob.data(), P.groups2[g].blob.size()));
+            c->table_bytes += c->blobs2[g].bytes;
+            q.fp.groups[g].blob = (const uint8_t *)c->blobs2[g].p;
+            q.fp.groups[g].bytes = (uint32_t)P.groups2[g].blob.size();
+            q.fp.groups[g].nb = (uint32_t)P.groups2[g].cols.size();
+            q.fp.groups[g].base = g ? q.fp.groups[g - 1].base + q.fp.groups[g - 1].nb : 0;
+            if (q.fp.groups[g].nb > (uint32_t)kMaxGroupBands) return c->fail(EGGPHOT_ERR_UNSUPPORTED, "more than 64 bands in one group");
+            q.fp.max_blob = std::max(q.fp.max_blob, q.fp.groups[g].bytes);
+        }
+        q.grid = (const GridNode *)c->gridN.p;
+        q.next_opt = (const int32_t *)c->nextOpt.p;
+        q.scratch_stride = (uint64_t)((size_t)(P.grid_disk.n() + 1) + (size_t)(P.grid_bulge.n() + 1)) * kLanes;
+        if (c->use_lane) {
+            const size_t smem = lane_kernel_smem(q) + kLaneStaticSmem;
+            if (smem > (size_t)prop.sharedMemPerBlockOptin + 1024)
+                return c->fail(EGGPHOT_ERR_UNSUPPORTED, "band tables need " + std::to_string(smem) + " B of shared memory, device offers " +
+                                                         std::to_string(prop.sharedMemPerBlockOptin) + "; lower smem_table_budget");
+            c->lane_blocks = c->num_sms;
+            const size_t rs = P.precision == EGGPHOT_FP64 ? 8 : 4;
+            c->lane_region_bytes = ((size_t)c->lane_blocks * q.scratch_stride * rs + 255) & ~size_t(255);
+            CK(c->lane_scratch.alloc(c->lane_region_bytes * (kSlots + 1)));
+            for (auto &h : c->zhist) CK(h.alloc(zsort_hist_bytes()));
+        }
+    }
+    CK(cudaDeviceSynchronize()); // every table upload has landed before a kernel on a non-blocking stream reads it
 #undef CK
     c->ready = true;
     return EGGPHOT_OK;
@@ -478,7 +556,7 @@ int eggphot_get_seds(eggphot_ctx *c, const eggphot_galaxies *gal, size_t first, 
                            nl ? gal->line_lum_bulge : nullptr, gal->opt_sed_disk, gal->opt_sed_bulge, gal->ir_sed};
     const size_t elem[15] = {4, 4, 4, 4, 4, 4, 4, 4, 12, 4, 4 * nl, 4 * nl, 8, 8, 8};
     for (int k = 0; k < 15; ++k)
-        if (src[k] && elem[k]) CK(cols[k].upload((const char *)src[k] + first * elem[k], count * elem[k]));
+        if (src[k] && elem[k]) CK(cols[k].upload_async((const char *)src[k] + first * elem[k], count * elem[k], c->stream));
     CK(dl.alloc(count * n * sizeof(float)));
     CK(ds.alloc(count * n * sizeof(float)));
     eggphot_galaxies dg{};
@@ -505,7 +583,7 @@ int eggphot_get_stats(const eggphot_ctx *c, eggphot_stats *s) {
     if (!c || !s) return EGGPHOT_ERR_ARG;
     std::memset(s, 0, sizeof(*s));
     s->kernel_launches = c->launches;
-    s->ngroups = (uint32_t)c->P.groups.size();
+    s->ngroups = (uint32_t)(c->use_lane ? c->P.groups2.size() : c->P.groups.size());
     s->nodes_disk = (uint32_t)c->P.grid_disk.n();
     s->nodes_bulge = (uint32_t)c->P.grid_bulge.n();
     s->nodes_ir = c->P.nir;

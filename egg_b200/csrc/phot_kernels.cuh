@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include "phot_core.cuh"
+#include "phot_lane.cuh"
 
 namespace eggphot {
 
@@ -78,6 +79,21 @@ size_t flux_kernel_smem(const FluxParams &p, int precision);
 // launches the flux kernel over all band groups; returns cudaError_t as int
 int launch_flux_kernel(const FluxParams &p, int precision, int grid_blocks, cudaStream_t stream);
 int flux_kernel_max_blocks_per_sm(const FluxParams &p, int precision);
+
+// ---- the lane-per-galaxy flux kernel (phot_lane_kernels.cu) ----
+// fp.groups point at the BandHeader2 blobs; fp.scratch at [grid][(nD + 1) + (nB + 1)][32 lanes] reals.
+struct LaneParams {
+    FluxParams fp;
+    const uint32_t *perm;     // [ngal] galaxies bucketed by redshift (zsort); batches are 32 consecutive entries
+    const GridNode *grid;     // [nD + 1]
+    const int32_t *next_opt;  // [nD + 1]
+    uint64_t scratch_stride;  // reals per CTA
+};
+size_t lane_kernel_smem(const LaneParams &q);
+int launch_lane_flux_kernel(const LaneParams &q, int precision, int grid_blocks, cudaStream_t stream);
+// counting sort of the galaxies by log2(1+z): hist is scratch of zsort_hist_bytes(), perm receives the order
+size_t zsort_hist_bytes();
+int launch_zsort(const float *z, uint32_t ngal, uint32_t *hist, uint32_t *perm, int num_sms, cudaStream_t stream);
 
 // save_sed: observed-frame lam / sed (f32) of galaxies [first, first+count) of one component
 struct SedParams {

@@ -53,6 +53,7 @@ double box_integral(const std::vector<double> &x, const std::vector<double> &y, 
 }
 
 void align16(std::vector<uint8_t> &b) { b.resize((b.size() + 15) & ~size_t(15), 0); }
+size_t up16(size_t v) { return (v + 15) & ~size_t(15); }
 
 // Double-precision band table, the source of both device layouts.
 struct FilterCellD {
@@ -176,7 +177,6 @@ Status build_band_table(const Filter &f, uint32_t out_col, int bucket_factor, Ba
     return Status();
 }
 
-size_t up16(size_t v) { return (v + 15) & ~size_t(15); }
 
 size_t band_bytes(const BandTableD &t, int precision) {
     const size_t n = t.h.n, rs = precision == EGGPHOT_FP64 ? 8 : 4;
@@ -280,6 +280,275 @@ Status make_grid_thresholds(Grid &g, bool apply_igm, const char *what) {
     g.l0 = last_le(g.x, 0.0912);
     g.l1 = last_le(g.x, 0.1026);
     g.l2 = last_le(g.x, 0.1216);
+    return Status();
+}
+
+// ---- tables of the lane kernel (phot_lane.cuh) --------------------------------------------------------------------
+struct BandTable2 {
+    BandHeader2 h{};
+    std::vector<RecA> ra;
+    std::vector<RecB> rb;
+    std::vector<double> s;
+    std::vector<uint16_t> bkt;
+};
+
+Status build_band_table2(const Filter &f, uint32_t out_col, int bucket_factor, BandTable2 &t) {
+    const int nf = (int)f.lam.size();
+    t = BandTable2();
+    t.h.out_col = out_col;
+    t.h.full_first = f.lam.front();
+    t.h.full_last = f.lam.back();
+    t.h.f_first = t.h.f_last = t.h.full_first;
+    t.bkt.assign(1, 0);
+    t.h.nbkt = 1;
+    // drop the wings where the response is identically zero (they add exactly nothing to the union-grid trapezoid)
+    int a = -1, b = -1;
+    for (int i = 0; i < nf; ++i)
+        if (f.res[i] != 0.0) { if (a < 0) a = i; b = i; }
+    if (a < 0) return Status(); // identically zero response: n = 0
+    a = std::max(a - 1, 0);
+    b = std::min(b + 1, nf - 1);
+    if (b == a) { b = std::min(a + 1, nf - 1); a = b - 1; }
+    if (!(f.lam[b] > f.lam[a])) return Status(); // no width: nothing to integrate
+    const int n = b - a + 1;
+    if (n > 64990) return Status::error(EGGPHOT_ERR_UNSUPPORTED, "filter with more than 64990 nodes");
+    t.h.n = (uint32_t)n;
+    t.h.f_first = f.lam[a];
+    t.h.f_last = f.lam[b];
+    // node positions are absolute wavelengths: u = t - f is formed from the same two doubles as in the reference
+    std::vector<double> fn(n), R(n), dl(n, 0.0), sl(n, 0.0);
+    for (int i = 0; i < n; ++i) { fn[i] = f.lam[a + i]; R[i] = f.res[a + i]; }
+    for (int i = 0; i + 1 < n; ++i) {
+        dl[i] = f.lam[a + i + 1] - f.lam[a + i];
+        sl[i] = dl[i] > 0 ? (R[i + 1] - R[i]) / dl[i] : 0.0;
+    }
+    // ---- anchors: the two ends, and the deepest node of every interior valley of |R| (widest valleys first)
+    std::vector<int> anchors;
+    {
+        double mx = 0;
+        for (double r : R) mx = std::max(mx, std::fabs(r));
+        const double thr = 1e-3 * mx;
+        struct Valley { int node; double width; };
+        std::vector<Valley> val;
+        int first_big = -1, last_big = -1;
+        for (int i = 0; i < n; ++i)
+            if (std::fabs(R[i]) > thr) { if (first_big < 0) first_big = i; last_big = i; }
+        for (int i = first_big + 1; i < last_big;) {
+            if (std::fabs(R[i]) > thr) { ++i; continue; }
+            int k = i;
+            while (k + 1 < last_big && std::fabs(R[k + 1]) <= thr) ++k;
+            // deepest node of the run [i, k]; the middle one among equals (an all-zero gap)
+            double lo = std::fabs(R[i]);
+            for (int q = i; q <= k; ++q) lo = std::min(lo, std::fabs(R[q]));
+            int c0 = -1, c1 = -1;
+            for (int q = i; q <= k; ++q)
+                if (std::fabs(R[q]) == lo) { if (c0 < 0) c0 = q; c1 = q; }
+            val.push_back(Valley{(c0 + c1) / 2, fn[k] - fn[i]});
+            i = k + 1;
+        }
+        std::stable_sort(val.begin(), val.end(), [](const Valley &x, const Valley &y) { return x.width > y.width; });
+        if ((int)val.size() > kMaxSplit - 1) val.resize(kMaxSplit - 1);
+        anchors.push_back(0);
+        for (const Valley &v : val) anchors.push_back(v.node);
+        anchors.push_back(n - 1);
+        std::sort(anchors.begin(), anchors.end());
+        anchors.erase(std::unique(anchors.begin(), anchors.end()), anchors.end());
+    }
+    const int nsplit = (int)anchors.size() - 1;
+    t.h.nsplit = (uint32_t)nsplit;
+    // ---- split nodes: the half-mass node (of |R|) between consecutive anchors, a_s < m_s <= a_{s+1}
+    std::vector<int> msp(nsplit);
+    for (int s = 0; s < nsplit; ++s) {
+        const int a0 = anchors[s], a1 = anchors[s + 1];
+        double tot = 0, run = 0;
+        for (int i = a0; i < a1; ++i) tot += 0.5 * (std::fabs(R[i]) + std::fabs(R[i + 1])) * dl[i];
+        int m = a1;
+        for (int i = a0; i < a1; ++i) {
+            run += 0.5 * (std::fabs(R[i]) + std::fabs(R[i + 1])) * dl[i];
+            if (run >= 0.5 * tot) { m = i + 1; break; }
+        }
+        msp[s] = m;
+    }
+    // ---- per region: (Lambda, K0) = (0, 0) at the anchor, accumulated outwards in long double.
+    //      K0 = running trapezoid of R; Lambda = L - G/6 advances by dl (K0 + R dl / 2) per cell (phot_core.cuh)
+    const int nrec = n + nsplit;
+    t.ra.resize(nrec); t.rb.resize(nrec); t.s.assign(nrec, 0.0);
+    std::vector<long double> K0(n), L(n);
+    std::vector<long double> Kat(nsplit), Lat(nsplit); // region s at its right end (split node m_s)
+    for (int s = 0; s <= nsplit; ++s) {
+        const int lo = s == 0 ? 0 : msp[s - 1], hi = s == nsplit ? n - 1 : msp[s], an = anchors[s];
+        K0[an] = 0; L[an] = 0;
+        for (int i = an; i < hi; ++i) {
+            L[i + 1] = L[i] + (long double)dl[i] * (K0[i] + 0.5L * (long double)R[i] * dl[i]);
+            K0[i + 1] = K0[i] + 0.5L * ((long double)R[i] + R[i + 1]) * dl[i];
+        }
+        for (int i = an - 1; i >= lo; --i) {
+            K0[i] = K0[i + 1] - 0.5L * ((long double)R[i] + R[i + 1]) * dl[i];
+            L[i] = L[i + 1] - (long double)dl[i] * (K0[i] + 0.5L * (long double)R[i] * dl[i]);
+        }
+        for (int i = lo; i <= hi; ++i) {
+            t.ra[i + s] = RecA{fn[i], (double)L[i]};
+            t.rb[i + s] = RecB{(double)K0[i], 0.5 * R[i]};
+            if (i < hi) t.s[i + s] = sl[i]; // the last record of a region opens no cell of it
+        }
+        if (s > 0) { // gauge jump across split s-1: Lambda_{s-1}(t) - Lambda_s(t) = C + D (t - F)
+            t.h.splitC[s - 1] = (double)(Lat[s - 1] - L[lo]);
+            t.h.splitD[s - 1] = (double)(Kat[s - 1] - K0[lo]);
+            t.h.splitF[s - 1] = fn[lo];
+        }
+        if (s < nsplit) { Kat[s] = K0[hi]; Lat[s] = L[hi]; t.h.msplit[s] = (uint32_t)(hi + s); }
+    }
+    for (int s = nsplit; s < kMaxSplit; ++s) t.h.msplit[s] = 0x7fffffffu;
+    // bucket table: bkt[k] = last record whose node is at or below the start of bucket k, the start lowered by 1e-6 of a
+    // bucket (the kernel's index is the rounding of a double product: it can exceed the exact one only for a t within
+    // ~1e-10 of a bucket of the boundary).  When buckets narrower than every cell are affordable one probe settles it.
+    const double span = fn[n - 1] - fn[0];
+    double min_dl = span;
+    for (int i = 0; i + 1 < n; ++i) min_dl = std::min(min_dl, dl[i]);
+    int nbkt = std::min(std::max(bucket_factor * n, 1), 65000);
+    if (min_dl > 0) {
+        const double need = std::ceil(span / min_dl * 1.02) + 1;
+        if (need <= 8.0 * n && need <= 65000.0) {
+            nbkt = std::max((int)need, 1);
+            t.h.one_probe = 1;
+        }
+    }
+    t.h.nbkt = (uint32_t)nbkt;
+    t.h.bk_scale = nbkt / span;
+    t.h.bk_c0 = -fn[0] * t.h.bk_scale - 0.5;
+    t.bkt.assign(nbkt, 0);
+    int r = 0;
+    for (int k = 0; k < nbkt; ++k) {
+        const double edge = fn[0] + ((double)k - 1e-6) / t.h.bk_scale;
+        while (r + 1 < nrec - 1 && t.ra[r + 1].f <= edge) ++r; // never the last record: it opens no cell
+        t.bkt[k] = (uint16_t)r;
+    }
+    return Status();
+}
+
+size_t band_bytes2(const BandTable2 &t) {
+    return up16(t.ra.size() * sizeof(RecA)) + up16(t.rb.size() * sizeof(RecB)) + up16(t.s.size() * sizeof(double)) +
+           up16(t.bkt.size() * sizeof(uint16_t));
+}
+
+template <typename T> uint32_t append_raw(std::vector<uint8_t> &blob, const std::vector<T> &v) {
+    align16(blob);
+    const uint32_t off = (uint32_t)blob.size();
+    const uint8_t *p = reinterpret_cast<const uint8_t *>(v.data());
+    blob.insert(blob.end(), p, p + v.size() * sizeof(T));
+    return off;
+}
+
+void append_band2(std::vector<uint8_t> &blob, size_t header_pos, const BandTable2 &t) {
+    BandHeader2 h = t.h;
+    h.ra_off = append_raw(blob, t.ra);
+    h.rb_off = append_raw(blob, t.rb);
+    h.s_off = append_raw(blob, t.s);
+    h.bkt_off = append_raw(blob, t.bkt);
+    align16(blob);
+    std::memcpy(blob.data() + header_pos, &h, sizeof(h));
+}
+
+// first-fit-decreasing packing of per-band byte sizes into as few groups as the budget allows, the groups kept even
+std::vector<std::vector<size_t>> pack_groups(const std::vector<size_t> &size, size_t budget) {
+    std::vector<size_t> bysize(size.size());
+    size_t total = 0;
+    for (size_t b = 0; b < size.size(); ++b) { bysize[b] = b; total += size[b]; }
+    std::stable_sort(bysize.begin(), bysize.end(), [&](size_t i, size_t j) { return size[i] > size[j]; });
+    std::vector<std::vector<size_t>> bins;
+    for (size_t ng = std::max<size_t>((total + budget - 1) / budget, 1); !size.empty(); ++ng) {
+        bins.assign(ng, {});
+        std::vector<size_t> fill(ng, 0);
+        bool ok = true;
+        for (size_t b : bysize) {
+            size_t best = ng;
+            for (size_t g = 0; g < ng; ++g)
+                if (fill[g] + size[b] <= budget && (best == ng || fill[g] < fill[best])) best = g;
+            if (best == ng) {
+                if (size[b] > budget && ng >= size.size()) { best = 0; for (size_t g = 1; g < ng; ++g) if (fill[g] < fill[best]) best = g; }
+                else { ok = false; break; }
+            }
+            bins[best].push_back(b);
+            fill[best] += size[b];
+        }
+        if (ok) break;
+    }
+    return bins;
+}
+
+Status build_lane_tables(Prepared &P, const eggphot_opts &opts) {
+    // ---- the disk grid as the walk reads it
+    const Grid &gd = P.grid_disk, &gb = P.grid_bulge;
+    const int nD = gd.n(), nB = gb.n();
+    P.grid_nodes.assign((size_t)nD + 1, GridNode{0, 0, 0, -1, -1});
+    P.next_opt.assign((size_t)nD + 1, nD);
+    P.opt_node.assign((size_t)nB, 0);
+    {
+        int o = 0, lasto = -1;
+        for (int j = 0; j < nD; ++j) {
+            GridNode &g = P.grid_nodes[j];
+            g.x = gd.x[j];
+            g.idxp = j > 0 ? 1.0 / (gd.x[j] - gd.x[j - 1]) : 0.0;
+            g.po = lasto;
+            if (P.has_bulge) {
+                while (o < nB && gb.x[o] < gd.x[j]) ++o;
+                if (o < nB && gb.x[o] == gd.x[j]) {
+                    g.o = o;
+                    g.idxpo = lasto >= 0 ? 1.0 / (gd.x[j] - gd.x[lasto]) : 0.0;
+                    P.opt_node[o] = j;
+                    lasto = j;
+                }
+            }
+        }
+        // the virtual node: far enough to the red that it is right of every filter the last real node is right of
+        GridNode &v = P.grid_nodes[nD];
+        const double xl = nD ? gd.x[nD - 1] : 1.0;
+        v.x = xl * 2.0 + 1.0;
+        v.idxp = 1.0 / (v.x - xl);
+        v.po = lasto;
+        v.o = P.has_bulge ? nB : -1;
+        v.idxpo = lasto >= 0 ? 1.0 / (v.x - gd.x[lasto]) : 0.0;
+        int nxt = nD;
+        for (int j = nD; j >= 0; --j) {
+            P.next_opt[j] = nxt;
+            if (j < nD && P.grid_nodes[j].o >= 0) nxt = j;
+        }
+        P.next_opt[nD] = nD;
+        if (P.has_bulge)
+            for (int o2 = 0; o2 < nB; ++o2)
+                if (P.grid_nodes[P.opt_node[o2]].o != o2)
+                    return Status::error(EGGPHOT_ERR_GRID, "an optical node is missing from the disk grid");
+    }
+    // ---- band tables in groups
+    const size_t nl = P.no_nebular ? 0 : P.line_lambda.size();
+    size_t budget = opts.smem_table_budget;
+    if (!budget) {
+        const size_t fixed = lane_smem_layout(0, P.bands.size(), P.rfbands.size(), nl).total + kLaneStaticSmem;
+        budget = fixed + 64u * 1024 < kSmemPerCta ? kSmemPerCta - fixed : 64u * 1024;
+    }
+    std::vector<BandTable2> tabs(P.bands.size());
+    std::vector<size_t> size(tabs.size());
+    for (size_t b = 0; b < P.bands.size(); ++b) {
+        Status st = build_band_table2(P.bands[b], (uint32_t)b, 2, tabs[b]);
+        if (!st.ok()) return st;
+        size[b] = band_bytes2(tabs[b]) + sizeof(BandHeader2) + 16;
+        if (size[b] > std::max<size_t>(budget, opts.smem_table_budget ? 204u * 1024 : 0))
+            return Status::error(EGGPHOT_ERR_UNSUPPORTED, "filter " + std::to_string(P.band_order[b]) +
+                                 " has too many nodes for the shared-memory band tables");
+        const int lo = last_le(gd.x, tabs[b].h.f_first / 2.0), hi = last_le(gd.x, tabs[b].h.f_last / 2.0);
+        tabs[b].h.cost = (float)std::max(hi - lo, 1);
+    }
+    for (auto &bin : pack_groups(size, budget)) {
+        if (bin.empty()) continue;
+        std::stable_sort(bin.begin(), bin.end(), [&](size_t i, size_t j) { return tabs[i].h.cost > tabs[j].h.cost; });
+        BandGroup g;
+        g.blob.assign(bin.size() * sizeof(BandHeader2), 0);
+        for (size_t k = 0; k < bin.size(); ++k) {
+            g.cols.push_back((uint32_t)bin[k]);
+            append_band2(g.blob, k * sizeof(BandHeader2), tabs[bin[k]]);
+        }
+        P.groups2.push_back(std::move(g));
+    }
     return Status();
 }
 
@@ -625,7 +894,7 @@ Status prepare(const eggphot_libs &L, const eggphot_filters *bands, const eggpho
         P.rf_bulge.push_back(P.has_bulge ? rf_weights(P.rfbands[b], P.grid_bulge) : RfWeights());
         P.rf_disk.push_back(rf_weights(P.rfbands[b], P.grid_disk));
     }
-    return Status();
+    return build_lane_tables(P, opts);
 }
 
 } // namespace eggphot

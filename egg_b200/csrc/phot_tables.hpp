@@ -20,6 +20,7 @@
 
 #include "../../include/eggphot.h"
 #include "phot_core.cuh"
+#include "phot_lane.cuh"
 
 namespace eggphot {
 
@@ -101,7 +102,14 @@ struct Prepared {
 
     std::vector<BandGroup> groups;
     std::vector<RfWeights> rf_bulge, rf_disk;    // [nrf]
+
+    // ---- tables of the lane kernel (phot_lane.cuh): band groups with node records, the disk grid as the walk reads it
+    std::vector<BandGroup> groups2;      // blobs hold BandHeader2 + records
+    std::vector<GridNode> grid_nodes;    // [nD + 1]: the last one is the virtual node far to the red
+    std::vector<int32_t> next_opt;       // [nD + 1]: first optical node after j (nD = the virtual node)
+    std::vector<int32_t> opt_node;       // [nB]: disk-grid index of every optical node
 };
+
 
 Status prepare(const eggphot_libs &libs, const eggphot_filters *bands, const eggphot_filters *rfbands,
                const eggphot_opts &opts, Prepared &out);

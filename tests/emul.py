@@ -14,7 +14,7 @@ _CSRC = os.path.join(_HERE, "..", "egg_b200", "csrc")
 
 
 def build():
-    deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("phot_tables.cpp", "phot_tables.hpp", "phot_core.cuh")]
+    deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("phot_tables.cpp", "phot_tables.hpp", "phot_core.cuh", "phot_lane.cuh")]
     if not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps):
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         subprocess.check_call([cxx, "-std=c++17", "-O2", "-fPIC", "-Wall", "-shared", "-o", _SO, _SRC,

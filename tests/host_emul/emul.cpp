@@ -7,6 +7,7 @@
 // (passes, reductions) is replaced by plain loops; everything numeric is shared.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -215,6 +216,134 @@ void run(const Prepared &P, const eggphot_galaxies &G, size_t ngal, double *fd, 
     }
 }
 
+// ---- the lane kernel's algorithm (phot_lane.cuh): batches of 32 z-sorted galaxies, union windows per band,
+//      blocks of 64 nodes walked per galaxy, block sums added in double in block order
+template <typename real> struct SedRef {
+    const real *d, *b;
+    real disk(int j) const { return d[j]; }
+    real bulge(int o) const { return b[o]; }
+};
+
+template <typename real>
+void run2(const Prepared &P, const eggphot_galaxies &G, size_t ngal, double *fd, double *fb, double *rd, double *rb) {
+    const size_t nb = P.bands.size(), nrf = P.rfbands.size();
+    const int nl = P.no_nebular ? 0 : (int)P.line_lambda.size();
+    const int nD = P.grid_disk.n(), nB = P.grid_bulge.n();
+    const GridNode *grid = P.grid_nodes.data();
+    std::vector<uint32_t> perm(ngal);
+    for (size_t g = 0; g < ngal; ++g) perm[g] = (uint32_t)g;
+    std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return G.z[a] < G.z[b]; });
+    std::vector<double> SDd(nD), SBd(nB);
+    std::vector<std::vector<real>> SD(kLanes, std::vector<real>(nD + 1, real(0))), SB(kLanes, std::vector<real>(nB + 1, real(0)));
+    for (size_t g0 = 0; g0 < ngal; g0 += kLanes) {
+        const int ng = (int)std::min<size_t>(kLanes, ngal - g0);
+        double opz[kLanes], aflux[kLanes], a_b[kLanes];
+        double omin = 1e300, omax = 0;
+        for (int l = 0; l < ng; ++l) {
+            const size_t g = perm[g0 + l];
+            const double z = G.z[g], d = G.d[g];
+            opz[l] = 1.0 + z;
+            omin = std::min(omin, opz[l]); omax = std::max(omax, opz[l]);
+            aflux[l] = EGGPHOT_LSUN2UJY * (1.0 + z) / (d * d);
+            a_b[l] = P.has_bulge ? std::pow(10.0, (double)(G.m_bulge[g] - G.m2lcor[g])) : 0.0;
+            const double a_d = P.disk_mode != DISK_IR ? std::pow(10.0, (double)(G.m_disk[g] - G.m2lcor[g])) : 0.0;
+            double c1 = 0, c2 = 0;
+            if (P.disk_mode != DISK_OPT) {
+                if (P.ir_kind == EGGPHOT_IR_CS17) { c1 = (1.0 - (double)G.fpah[g]) * G.mdust[g]; c2 = (double)G.fpah[g] * G.mdust[g]; }
+                else c1 = G.lir[g];
+            }
+            float ig[3] = {1, 1, 1};
+            if (P.apply_igm) for (int k = 0; k < 3; ++k) ig[k] = G.igm_abs[3 * g + k];
+            const real ad = (real)a_d, rc1 = (real)c1, rc2 = (real)c2;
+            for (int j = 0; j < nD; ++j) {
+                real v = 0;
+                const size_t ro = P.disk_mode != DISK_IR ? (size_t)G.opt_sed_disk[g] * nD + j : 0;
+                const size_t ri = P.disk_mode != DISK_OPT ? (size_t)G.ir_sed[g] * nD + j : 0;
+                if (P.disk_mode == DISK_BOTH) v = ad * (real)P.rows_disk_opt[ro] + rc1 * (real)P.rows_disk_ir[ri];
+                else if (P.disk_mode == DISK_OPT) v = ad * (real)P.rows_disk_opt[ro];
+                else v = rc1 * (real)P.rows_disk_ir[ri];
+                if (P.disk_mode != DISK_OPT && P.ir_kind == EGGPHOT_IR_CS17) v += rc2 * (real)P.rows_disk_pah[ri];
+                if (P.apply_igm)
+                    v *= igm_factor<real>(j, P.grid_disk.lz, P.grid_disk.l0, P.grid_disk.l1, P.grid_disk.l2, ig[0], ig[1], ig[2]);
+                SD[l][j] = v;
+            }
+            for (int j = 0; j < nB; ++j) {
+                real v = (real)P.rows_bulge_opt[(size_t)G.opt_sed_bulge[g] * nB + j];
+                if (P.apply_igm)
+                    v *= igm_factor<real>(j, P.grid_bulge.lz, P.grid_bulge.l0, P.grid_bulge.l1, P.grid_bulge.l2, ig[0], ig[1], ig[2]);
+                SB[l][j] = v;
+            }
+            if (nl) {
+                for (int j = 0; j < nD; ++j) SDd[j] = 0;
+                add_lines(P, P.grid_disk, SDd, G.line_lum_disk + g * nl, G.vdisp[g], 1.0);
+                for (int j = 0; j < nD; ++j) if (SDd[j] != 0) SD[l][j] += (real)SDd[j];
+                if (P.has_bulge && G.line_lum_bulge) {
+                    for (int j = 0; j < nB; ++j) SBd[j] = 0;
+                    add_lines(P, P.grid_bulge, SBd, G.line_lum_bulge + g * nl, G.vdisp[g], a_b[l] > 0 ? 1.0 / a_b[l] : 0.0);
+                    for (int j = 0; j < nB; ++j) if (SBd[j] != 0) SB[l][j] += (real)SBd[j];
+                }
+            }
+        }
+        for (const BandGroup &grp : P.groups2) {
+            const uint8_t *blob = grp.blob.data();
+            const BandHeader2 *hdr = reinterpret_cast<const BandHeader2 *>(blob);
+            for (size_t bi = 0; bi < grp.cols.size(); ++bi) {
+                const BandHeader2 &h = hdr[bi];
+                std::vector<double> resd(kLanes, 0.0), resb(kLanes, 0.0);
+                if (h.n >= 2 && nD >= 2) {
+                    Band2 bv;
+                    make_band2(blob, h, bv);
+                    // union window of the batch, with margins (extra nodes weigh exactly nothing)
+                    const double xlo = h.f_first / omax * (1.0 - 1e-9), xhi = h.f_last / omin * (1.0 + 1e-9);
+                    int jlo = std::max(last_le(P.grid_disk.x, xlo), 0);
+                    int jhi = (int)(std::lower_bound(P.grid_disk.x.begin(), P.grid_disk.x.end(), xhi) - P.grid_disk.x.begin());
+                    jhi = std::min(jhi, nD - 1);
+                    if (P.has_bulge) widen_window_for_bulge(grid, P.next_opt.data(), nD, jlo, jhi);
+                    for (int k = jlo / kLaneBlock; k <= jhi / kLaneBlock; ++k) {
+                        const int a = std::max(jlo, k * kLaneBlock), b = std::min(jhi, k * kLaneBlock + kLaneBlock - 1);
+                        int js, je;
+                        block_arrivals(grid, P.next_opt.data(), P.has_bulge, a, b, js, je);
+                        for (int l = 0; l < ng; ++l) {
+                            real accd = 0, accb = 0;
+                            SedRef<real> sr{SD[l].data(), SB[l].data()};
+                            walk_block<real>(bv, grid, opz[l], P.has_bulge, a, b, js, je, sr, accd, accb);
+                            resd[l] += (double)accd;
+                            resb[l] += (double)accb;
+                        }
+                    }
+                }
+                for (int l = 0; l < ng; ++l) {
+                    const size_t g = perm[g0 + l];
+                    const bool covered = nD >= 2 && P.grid_disk.x[0] * opz[l] <= h.full_first && P.grid_disk.x[nD - 1] * opz[l] >= h.full_last;
+                    const bool bulge_on = covered && P.has_bulge && nB >= 2 && P.grid_bulge.x[0] * opz[l] <= h.full_first &&
+                                          P.grid_bulge.x[nB - 1] * opz[l] >= h.full_last;
+                    double fdv = covered ? resd[l] / opz[l] * aflux[l] : 0.0;
+                    double fbv = bulge_on ? resb[l] / opz[l] * aflux[l] * a_b[l] : 0.0;
+                    if (!std::isfinite(fdv)) fdv = 0;
+                    if (!std::isfinite(fbv)) fbv = 0;
+                    fd[g * nb + h.out_col] = fdv;
+                    if (P.has_bulge) fb[g * nb + h.out_col] = fbv;
+                }
+            }
+        }
+        const double arf = EGGPHOT_LSUN2UJY / (1e-5 * 1e-5);
+        for (int l = 0; l < ng; ++l) {
+            const size_t g = perm[g0 + l];
+            for (size_t r = 0; r < nrf; ++r)
+                for (int comp = P.has_bulge ? 0 : 1; comp < 2; ++comp) {
+                    const RfWeights &w = comp ? P.rf_disk[r] : P.rf_bulge[r];
+                    const std::vector<real> &S = comp ? SD[l] : SB[l];
+                    CompSum<real> acc;
+                    acc.clear();
+                    for (size_t k = 0; k < w.w.size(); ++k) acc.add(S[w.j0 + k] * (real)w.w[k]);
+                    double fl = w.covered ? ((double)acc.s + (double)acc.c) * arf * (comp ? 1.0 : a_b[l]) : NAN;
+                    double m = -2.5 * std::log10(fl) + 23.9;
+                    (comp ? rd : rb)[g * nrf + r] = std::isfinite(m) ? m : 99.0;
+                }
+        }
+    }
+}
+
 } // namespace
 
 extern "C" {
@@ -232,14 +361,30 @@ int emul_compute(const eggphot_libs *libs, const eggphot_filters *bands, const e
         return st.code;
     }
     for (size_t k = 0; k < P.band_order.size(); ++k) { if (order) order[k] = P.band_order[k]; if (lambda) lambda[k] = P.band_lambda[k]; }
-    if (P.precision == EGGPHOT_FP64) run<double>(P, *gal, ngal, flux_disk, flux_bulge, rfmag_disk, rfmag_bulge);
-    else run<float>(P, *gal, ngal, flux_disk, flux_bulge, rfmag_disk, rfmag_bulge);
+    const char *algo = getenv("EGGPHOT_EMUL_ALGO"); // 1 = node-per-lane kernel (phot_kernels.cu), default: lane kernel
+    if (algo && algo[0] == '1') {
+        if (P.precision == EGGPHOT_FP64) run<double>(P, *gal, ngal, flux_disk, flux_bulge, rfmag_disk, rfmag_bulge);
+        else run<float>(P, *gal, ngal, flux_disk, flux_bulge, rfmag_disk, rfmag_bulge);
+    } else {
+        if (P.precision == EGGPHOT_FP64) run2<double>(P, *gal, ngal, flux_disk, flux_bulge, rfmag_disk, rfmag_bulge);
+        else run2<float>(P, *gal, ngal, flux_disk, flux_bulge, rfmag_disk, rfmag_bulge);
+    }
     return 0;
 }
 
 int emul_ngroups(const eggphot_libs *libs, const eggphot_filters *bands, const eggphot_opts *opts) {
     Prepared P;
     Status st = prepare(*libs, bands, nullptr, *opts, P);
-    return st.ok() ? (int)P.groups.size() : -st.code;
+    const char *algo = getenv("EGGPHOT_EMUL_ALGO");
+    return st.ok() ? (int)((algo && algo[0] == '1') ? P.groups.size() : P.groups2.size()) : -st.code;
+}
+
+// largest group blob of the lane kernel's tables (bytes)
+int emul_max_blob2(const eggphot_libs *libs, const eggphot_filters *bands, const eggphot_opts *opts) {
+    Prepared P;
+    Status st = prepare(*libs, bands, nullptr, *opts, P);
+    size_t m = 0;
+    for (const BandGroup &g : P.groups2) m = std::max(m, g.blob.size());
+    return st.ok() ? (int)m : -st.code;
 }
 }
