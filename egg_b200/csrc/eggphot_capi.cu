@@ -79,7 +79,7 @@ struct eggphot_ctx {
     // region, the redshift-bucketing buffers.  EGGPHOT_KERNEL=node selects the node-per-lane kernel of phot_kernels.cu.
     bool use_lane = true;
     std::vector<DevBuf> blobs2;
-    DevBuf gridN, nextOpt, lane_scratch;
+    DevBuf gridN, nextOpt, tabCol, lane_scratch;
     DevBuf zhist[kSlots + 1], zperm[kSlots + 1];
     LaneParams lbase{};
     int lane_blocks = 0;
@@ -393,13 +393,25 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
         }
         q.grid = (const GridNode *)c->gridN.p;
         q.next_opt = (const int32_t *)c->nextOpt.p;
-        q.scratch_stride = (uint64_t)((size_t)(P.grid_disk.n() + 1) + (size_t)(P.grid_bulge.n() + 1)) * kLanes;
+        {
+            std::vector<uint32_t> cols;
+            for (const BandGroup &g : P.groups2) cols.insert(cols.end(), g.cols.begin(), g.cols.end());
+            q.ntab = (uint32_t)cols.size();
+            if (cols.empty()) cols.push_back(0);
+            CK(c->tabCol.upload(cols.data(), cols.size() * sizeof(uint32_t)));
+            q.tab_col = (const uint32_t *)c->tabCol.p;
+        }
+        // block-sum slots: a batch whose galaxies span a wide range of redshift can make every table read the whole grid
+        q.max_slots = q.ntab * (uint32_t)(P.grid_disk.n() / kLaneBlock + 2);
+        q.scratch_stride = (uint64_t)((size_t)(P.grid_disk.n() + 2) + (size_t)(P.grid_bulge.n() + 2) + 2 * (size_t)q.max_slots) * kLanes;
         if (c->use_lane) {
-            const size_t smem = lane_kernel_smem(q) + kLaneStaticSmem;
-            if (smem > (size_t)prop.sharedMemPerBlockOptin + 1024)
+            const size_t smem = lane_kernel_smem(q);
+            if (smem + kLaneStaticSmem > (size_t)prop.sharedMemPerBlockOptin)
                 return c->fail(EGGPHOT_ERR_UNSUPPORTED, "band tables need " + std::to_string(smem) + " B of shared memory, device offers " +
                                                          std::to_string(prop.sharedMemPerBlockOptin) + "; lower smem_table_budget");
-            c->lane_blocks = c->num_sms;
+            const int occ = lane_kernel_max_blocks_per_sm(q, P.precision);
+            if (occ <= 0) return c->fail(EGGPHOT_ERR_CUDA, "flux kernel cannot be resident (occupancy query failed)");
+            c->lane_blocks = c->num_sms * std::min(occ, kLaneCtasPerSm);
             const size_t rs = P.precision == EGGPHOT_FP64 ? 8 : 4;
             c->lane_region_bytes = ((size_t)c->lane_blocks * q.scratch_stride * rs + 255) & ~size_t(255);
             CK(c->lane_scratch.alloc(c->lane_region_bytes * (kSlots + 1)));

@@ -89,8 +89,9 @@ Args read_args(int argc, char *argv[]) {
         std::string s = argv[i];
         while (!s.empty() && s[0] == '-') s = s.substr(1);
         const size_t eq = s.find('=');
-        if (eq == std::string::npos) a.kv[s] = "1";
-        else a.kv[s.substr(0, eq)] = s.substr(eq + 1);
+        std::string key = eq == std::string::npos ? s : s.substr(0, eq);
+        std::replace(key.begin(), key.end(), '-', '_'); // `filter-db=` is `filter_db=`
+        a.kv[key] = eq == std::string::npos ? "1" : s.substr(eq + 1);
     }
     if (a.has("list_band")) a.kv["list_bands"] = a.kv["list_band"]; // the manual uses both spellings
     return a;
@@ -198,6 +199,8 @@ int list_bands(const std::string &pattern, const std::string &db_file) {
 void print_help() {
     std::cout <<
         "egg-gencat-b200: the photometry stage of egg-gencat (fluxes and rest-frame magnitudes) on NVIDIA B200\n"
+        "This program replaces the block `if (!no_flux)` of egg-gencat only: catalog generation options (area, mmin, zmin,\n"
+        "...) are accepted and ignored, and without input_props= or input_cat= it exits with an error.\n"
         "usage: egg-gencat-b200 input_props=catalog.fits [options]\n"
         "       egg-gencat-b200 input_cat=catalog.fits [options]\n\n"
         "  input_cat=FILE     catalog holding ID RA DEC Z M PASSIVE: every other property is generated on the GPU\n"
@@ -213,9 +216,33 @@ void print_help() {
         "  trim_filters filter_flambda filter_photons filter_normalize\n"
         "  out=FILE verbose help list_bands[=regex]\n"
         "  precision=fp32c|fp64   arithmetic mode (1e-5 / 1e-10 per band against the reference algorithm)\n"
+        "  check [check_tol=1e-5] compare the computed FLUX* / RFMAG* with the columns already in input_props (any catalog\n"
+        "                         written by egg-gencat is a test vector); exit status 2 if a band differs by more\n"
+        "  sed2flux_nodes=merged|sed|filter  line_profile=integral|average   conventions of the vif library to try with check\n"
         "  gpus=N                 shard the galaxies over N GPUs of this box\n"
         "Catalog generation options of egg-gencat (area, mmin, zmin, ...) are accepted and ignored: this program\n"
         "replaces the block `if (!no_flux)` of egg-gencat only.\n";
+}
+
+// Column order of the reference's writer (src/egg-gencat.cpp:2253-2286): the main table, then the flux, line and
+// rest-frame groups; columns egg does not know keep their relative order after them.
+void order_like_the_reference(fitscol::Table &t) {
+    static const char *const order[] = {
+        "ID", "RA", "DEC", "CLUSTERED", "Z", "D", "M", "SFR", "RSB", "M2LCOR", "DISK_ANGLE", "DISK_RADIUS", "DISK_RATIO",
+        "BULGE_ANGLE", "BULGE_RADIUS", "BULGE_RATIO", "BT", "M_DISK", "M_BULGE", "AV_DISK", "AV_BULGE", "PASSIVE",
+        "RFUV_BULGE", "RFUV_DISK", "RFVJ_BULGE", "RFVJ_DISK", "SFRIR", "SFRUV", "IRX", "LIR", "IR_SED", "OPT_SED_BULGE",
+        "OPT_SED_DISK", "TDUST", "IR8", "FPAH", "MDUST", "IGM_ABS", "ZB", "CMD",
+        "FLUX", "FLUX_DISK", "FLUX_BULGE", "BANDS", "LAMBDA",
+        "VDISP", "AVLINES_DISK", "AVLINES_BULGE", "LINE_LUM", "LINE_LUM_DISK", "LINE_LUM_BULGE", "LINES", "LINE_LAMBDA",
+        "RFMAG", "RFMAG_DISK", "RFMAG_BULGE", "RFBANDS", "RFLAMBDA"};
+    std::vector<fitscol::Column> out;
+    std::vector<bool> used(t.cols.size(), false);
+    for (const char *name : order)
+        for (size_t i = 0; i < t.cols.size(); ++i)
+            if (!used[i] && t.cols[i].name == name) { out.push_back(std::move(t.cols[i])); used[i] = true; }
+    for (size_t i = 0; i < t.cols.size(); ++i)
+        if (!used[i]) out.push_back(std::move(t.cols[i]));
+    t.cols = std::move(out);
 }
 
 struct Shard {
@@ -433,10 +460,30 @@ int main(int argc, char *argv[]) {
             vdisp = fitscol::as_float(need("VDISP"));
             lld = fitscol::as_float(need("LINE_LUM_DISK"));
             if (cat.find("LINE_LUM_BULGE")) llb = fitscol::as_float(need("LINE_LUM_BULGE"));
-            if (lld.size() != ngal * line_lambda.size()) { error("LINE_LUM_DISK is not [ngal, nline]"); return 1; }
         }
-        for (const auto *v : {&d, &m2lcor})
-            if (v->size() != ngal) { error("catalog columns have inconsistent lengths"); return 1; }
+        {   // every column the kernels index by galaxy must have ngal entries (x its second dimension)
+            const size_t nl = line_lambda.size();
+            const struct { const char *name; size_t have, want; } chk[] = {
+                {"D", d.size(), ngal}, {"M2LCOR", m2lcor.size(), ngal},
+                {"M_DISK", m_disk.size(), no_stellar ? 0 : ngal}, {"M_BULGE", m_bulge.size(), no_stellar ? 0 : ngal},
+                {"OPT_SED_DISK", osd.size(), no_stellar ? 0 : ngal}, {"OPT_SED_BULGE", osb.size(), no_stellar ? 0 : ngal},
+                {"IR_SED", irs.size(), no_dust ? 0 : ngal}, {"LIR", lir.size(), (no_dust || cs17) ? 0 : ngal},
+                {"FPAH", fpah.size(), (!no_dust && cs17) ? ngal : 0}, {"MDUST", mdust.size(), (!no_dust && cs17) ? ngal : 0},
+                {"IGM_ABS", igm_abs.size(), (igm == "madau95" || igm == "inoue14") ? 3 * ngal : 0},
+                {"VDISP", vdisp.size(), nebular ? ngal : 0}, {"LINE_LUM_DISK", lld.size(), nebular ? ngal * nl : 0},
+                {"LINE_LUM_BULGE", llb.size(), llb.empty() ? 0 : ngal * nl}};
+            for (const auto &c : chk)
+                if (c.have != c.want) {
+                    error("catalog columns have inconsistent lengths (" + std::string(c.name) + " holds " + std::to_string(c.have) +
+                          " values, expected " + std::to_string(c.want) + ")");
+                    return 1;
+                }
+        }
+        if (ngal == 0) {
+            if (verbose) note("the catalog holds no galaxy: writing it unchanged");
+            fitscol::write_table(out_file, cat);
+            return 0;
+        }
 
         if (no_flux) {
             if (verbose) note("no_flux: writing the catalog unchanged");
@@ -488,8 +535,16 @@ int main(int argc, char *argv[]) {
         O.opt_lib_imf = imf.c_str();
         O.opt_lib_min_step = a.num("opt_lib_min_step", 0.001);
         O.filter_flambda = a.flag("filter_flambda"); O.filter_photons = a.flag("filter_photons");
-        O.filter_normalize = a.flag("filter_normalize"); O.trim_filters = a.flag("trim_filters");
+        O.filter_normalize = a.has("filter_normalize") ? a.flag("filter_normalize") : true; // default true (src/egg-gencat.cpp:98)
+        O.trim_filters = a.flag("trim_filters");
         O.nline = (uint32_t)line_lambda.size(); O.line_lambda = line_lambda.data();
+        {   // the two [vif] conventions the reference's own sources do not settle: switchable, for `check`
+            const std::string nodes = a.str("sed2flux_nodes", "merged"), prof = a.str("line_profile", "integral");
+            if (nodes != "merged" && nodes != "sed" && nodes != "filter") { error("sed2flux_nodes must be merged, sed or filter"); return 1; }
+            if (prof != "integral" && prof != "average") { error("line_profile must be integral or average"); return 1; }
+            O.sed2flux_nodes = nodes == "sed" ? EGGPHOT_NODES_SED : (nodes == "filter" ? EGGPHOT_NODES_FILTER : EGGPHOT_NODES_MERGED);
+            O.line_profile = prof == "average" ? EGGPHOT_LINE_AVERAGE : EGGPHOT_LINE_INTEGRAL;
+        }
 
         // ---- compute: one context (and host thread) per GPU, contiguous shards, no exchange between them
         const size_t nband = fb.size(), nrf = fr.size();
@@ -581,6 +636,72 @@ int main(int argc, char *argv[]) {
         }
         for (auto *c : ctxs) eggphot_destroy(c);
 
+        // ---- check: an egg output catalog holds every input column of this stage next to its
+        //      outputs, so any catalog of a real egg install is a test vector.  Compare what was just computed with the
+        //      FLUX* / RFMAG* columns found in the input, band by band (matched by name), before they are replaced.
+        int check_status = 0;
+        if (a.flag("check")) {
+            const double tol = a.num("check_tol", 1e-5);
+            auto trim = [](std::string v) { while (!v.empty() && v.back() == ' ') v.pop_back(); return v; };
+            auto compare = [&](const char *col, const char *names_col, const std::vector<float> &mine, size_t nmine,
+                               const std::vector<std::string> &names_mine, bool is_mag) {
+                const fitscol::Column *oc = cat.find(col), *nc = cat.find(names_col);
+                if (!oc || !nc) { warning(std::string("check: the catalog has no ") + col + " / " + names_col + " columns"); check_status = std::max(check_status, 1); return; }
+                const std::vector<float> old = fitscol::as_float(*oc);
+                std::vector<std::string> onames = fitscol::as_strings(*nc);
+                for (auto &v : onames) v = trim(v);
+                const size_t nold = onames.size();
+                if (old.size() != ngal * nold) { warning(std::string("check: ") + col + " is not [ngal, nband]"); check_status = std::max(check_status, 1); return; }
+                for (size_t k = 0; k < nmine; ++k) {
+                    const auto it = std::find(onames.begin(), onames.end(), names_mine[k]);
+                    if (it == onames.end()) { note(std::string("check: band ") + names_mine[k] + " is not in the catalog's " + names_col + ": skipped"); continue; }
+                    const size_t ko = (size_t)(it - onames.begin());
+                    std::vector<double> rel;
+                    size_t above = 0, zero_mismatch = 0;
+                    for (size_t g = 0; g < ngal; ++g) {
+                        const double x = mine[g * nmine + k], y = old[g * nold + ko];
+                        double e;
+                        if (is_mag) e = std::fabs(x - y);
+                        else if (y == 0.0) { zero_mismatch += x != 0.0; continue; }
+                        else e = std::fabs(x - y) / std::fabs(y);
+                        rel.push_back(e);
+                        above += e > tol;
+                    }
+                    double mx = 0, med = 0;
+                    if (!rel.empty()) {
+                        mx = *std::max_element(rel.begin(), rel.end());
+                        std::nth_element(rel.begin(), rel.begin() + rel.size() / 2, rel.end());
+                        med = rel[rel.size() / 2];
+                    }
+                    char line[256];
+                    std::snprintf(line, sizeof line, "check: %-12s %-22s max %s %.3e  median %.3e  above %.0e: %zu of %zu%s", col, names_mine[k].c_str(),
+                                  is_mag ? "abs" : "rel", mx, med, tol, above, rel.size(),
+                                  zero_mismatch ? (", non-zero where the catalog has 0: " + std::to_string(zero_mismatch)).c_str() : "");
+                    std::cout << line << std::endl;
+                    if (above || zero_mismatch) check_status = 2;
+                }
+            };
+            std::vector<std::string> bn, rn;
+            for (uint32_t k : order) bn.push_back(fb[k].name);
+            for (uint32_t k : rforder) rn.push_back(fr[k].name);
+            if (nband) {
+                compare("FLUX_DISK", "BANDS", flux_disk, nband, bn, false);
+                compare("FLUX_BULGE", "BANDS", flux_bulge, nband, bn, false);
+                compare("FLUX", "BANDS", flux, nband, bn, false);
+            }
+            if (nrf) {
+                compare("RFMAG_DISK", "RFBANDS", rfmag_disk, nrf, rn, true);
+                compare("RFMAG_BULGE", "RFBANDS", rfmag_bulge, nrf, rn, true);
+                compare("RFMAG", "RFBANDS", rfmag, nrf, rn, true);
+            }
+            std::cout << "check: " << (check_status == 0 ? "every compared band is within tolerance"
+                                       : check_status == 1 ? "nothing to compare against"
+                                                           : "DIFFERENCES above tolerance (try sed2flux_nodes= and line_profile=)")
+                      << " [sed2flux_nodes=" << a.str("sed2flux_nodes", "merged") << " line_profile=" << a.str("line_profile", "integral")
+                      << " precision=" << precision << "]" << std::endl;
+            if (!a.has("out")) return check_status; // nothing is written unless an output file is named
+        }
+
         // ---- output (src/egg-gencat.cpp:2249-2286): pass the catalog through, (re)write the flux groups
         if (verbose) note("saving catalog...");
         std::string cmd;
@@ -601,8 +722,14 @@ int main(int argc, char *argv[]) {
             cat.set(fitscol::make_f32("RFMAG_BULGE", rfmag_bulge, r2));
             cat.set(fitscol::make_strings("RFBANDS", names)); cat.set(fitscol::make_f32("RFLAMBDA", rflambda));
         }
+        if (from_cat && !cat.find("CLUSTERED")) { // src/egg-gencat.cpp:1356: no clustering without generated positions
+            fitscol::Column cc;
+            cc.name = "CLUSTERED"; cc.type = 'L'; cc.dims = {(long)ngal}; cc.data.assign(ngal, 'F');
+            cat.set(cc);
+        }
+        order_like_the_reference(cat);
         fitscol::write_table(out_file, cat);
-        return 0;
+        return check_status;
     } catch (const std::exception &e) {
         error(e.what());
         return 1;

@@ -81,15 +81,20 @@ int launch_flux_kernel(const FluxParams &p, int precision, int grid_blocks, cuda
 int flux_kernel_max_blocks_per_sm(const FluxParams &p, int precision);
 
 // ---- the lane-per-galaxy flux kernel (phot_lane_kernels.cu) ----
-// fp.groups point at the BandHeader2 blobs; fp.scratch at [grid][(nD + 1) + (nB + 1)][32 lanes] reals.
+// fp.groups point at the BandHeader2 blobs; fp.scratch at [grid][(nD + 2) + (nB + 2) rows][32 lanes] reals followed by
+// [max_slots][2][32 lanes] block sums.
 struct LaneParams {
     FluxParams fp;
     const uint32_t *perm;     // [ngal] galaxies bucketed by redshift (zsort); batches are 32 consecutive entries
     const GridNode *grid;     // [nD + 1]
     const int32_t *next_opt;  // [nD + 1]
-    uint64_t scratch_stride;  // reals per CTA
+    const uint32_t *tab_col;  // [ntab] output column of every band table, in group order
+    uint32_t ntab;            // band tables (a filter cut into pieces has several)
+    uint32_t max_slots;       // block-sum slots per CTA
+    uint64_t scratch_stride;  // reals per CTA: SED rows of the disk and bulge grids, then the block-sum slots
 };
 size_t lane_kernel_smem(const LaneParams &q);
+int lane_kernel_max_blocks_per_sm(const LaneParams &q, int precision);
 int launch_lane_flux_kernel(const LaneParams &q, int precision, int grid_blocks, cudaStream_t stream);
 // counting sort of the galaxies by log2(1+z): hist is scratch of zsort_hist_bytes(), perm receives the order
 size_t zsort_hist_bytes();

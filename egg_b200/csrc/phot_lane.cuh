@@ -17,10 +17,8 @@
 //      touches is 0 in the gauge of that end), in float and in double;
 //    - an interval inside one filter cell c:  E_j = K0_c + (u_j + u_{j+1}) R_c / 2 + s_c u_j u_{j+1} / 2  (direct, no
 //      difference at all);
-//  * two-sided gauge as before: records of nodes up to the split node m hold (Lambda, K0) accumulated from the left end,
-//    records right of it hold (Lambda - asym, K0 - tot0) accumulated from the right end; node m is stored twice (record m
-//    in the left gauge closes cell m-1, record m+1 in the right gauge opens cell m).  The interval that crosses the split
-//    adds asym(t_{j+1}), and the next weight sees E - tot0 (1+z);
+//  * gauges anchored at both ends of the span and in every deep interior valley of the response (see BandHeader2): table
+//    values are small wherever the response is, exactly 0 where it is 0;
 //  * the disk walks every node of the merge_add grid, the bulge only the optical nodes among them (its own SED intervals,
 //    so the union grid of the bulge is filter nodes + optical nodes, as when get_flux runs on the bulge alone,
 //    src/egg-gencat.cpp:2206-2209); both read the same per-node expansions.  Where two consecutive disk nodes are both
@@ -43,58 +41,65 @@ namespace eggphot {
 constexpr int kLaneBlock = 64;   // SED nodes per work item: block k holds nodes [64 k, 64 k + 63]
 constexpr int kLanes = 32;       // galaxies per batch (one per lane)
 
-struct alignas(16) RecA { double f, L; };    // node wavelength [um]; Lambda at the node (gauge of the record)
-struct alignas(16) RecB { double k0, hr; };  // K0 at the node (gauge of the record); R / 2 of the node
+// One record per filter node: wavelength, Lambda and K0 at the node in the gauge of the record, R / 2 of the node.
+struct alignas(32) Rec { double f, L, k0, hr; };
 
-// Header of one band inside a group blob of the lane kernel (offsets are bytes from the blob start).
+// Header of one band table inside a group blob of the lane kernel (offsets are bytes from the blob start).
+//
+// Nodes.  The table holds the nodes of the response with its identically-zero wings removed, plus a zero-response node
+// at either end where the response starts or stops abruptly (a jump is two nodes at one wavelength), so that R = 0 at
+// both ends and outside.  A filter too large for the shared-memory budget is cut at filter nodes into several tables
+// that feed the same output column (the union-node trapezoid is additive over such cuts).
 //
 // Gauges.  Adding a linear function to Lambda shifts every E by a constant and leaves the weights untouched, and a
 // weight is only as accurate as the table values it differences are small.  The span of a band is therefore cut into
 // regions, each with an ANCHOR node where (Lambda, K0) = (0, 0) and from which both are accumulated outwards: the two
 // ends of the span are anchors (a far wing only ever differences small numbers, however bright the SED is there), and so
-// is the deepest node of every interior valley of |R| below 1e-3 of its maximum (between the lobes of a two-lobe
+// is the deepest node of every interior valley of |R| below 1e-6 of its maximum (between the lobes of a two-lobe
 // response the tables are exactly 0 where R is: a bright line in the gap weighs exactly nothing).  Regions meet at SPLIT
 // nodes (the half-mass node between two anchors), stored twice: once in the gauge of the region on its left (closing
 // the last cell of that region) and once in the gauge of the region on its right.  An SED interval that crosses split s
 // adds the gauge jump  Lambda_s(t) - Lambda_{s+1}(t) = C_s + D_s (t - F_s), and the next weight sees E - D_s (1+z).
+//
+// Records: [left sentinel][nodes, split nodes twice][terminator].  The left sentinel opens the cell of everything blue
+// of the span, the last node that of everything red of it: all their table values are 0, so an SED node outside the
+// span needs no special case (its expansions are exactly 0).  bkt has one entry in front and one behind the real
+// buckets for those two cells.
 constexpr int kMaxSplit = 6;
 struct __attribute__((aligned(16))) BandHeader2 {
-    double full_first, full_last; // full filter span [um] for the coverage test ([vif] sed2flux NaN rule)
-    double f_first, f_last;       // span with the zero-response wings removed [um]
-    double bk_scale, bk_c0;       // bucket of t: round-to-nearest of fma(t, bk_scale, bk_c0)
+    double full_first, full_last; // full span of the whole filter [um] for the coverage test ([vif] sed2flux NaN rule)
+    double f_first, f_last;       // span of this table [um]
+    double bk_scale, bk_c0;       // bucket entry of t: round-to-nearest of fma(t, bk_scale, bk_c0), clamped to the table
     double splitC[kMaxSplit], splitD[kMaxSplit], splitF[kMaxSplit];
-    uint32_t n;                   // nodes in the effective span (>= 2), or 0: the band contributes nothing
-    uint32_t nsplit;              // regions - 1 (>= 1 when n >= 2)
-    uint32_t nbkt;
-    uint32_t one_probe;           // buckets are narrower than every cell: one comparison settles the lookup
-    uint32_t ra_off, rb_off, s_off, bkt_off;
+    uint32_t n;                   // records (0: the band contributes nothing)
+    uint32_t nsplit;              // regions - 1
+    uint32_t nbkt;                // bucket entries, the two end entries included
+    uint32_t two_probe;           // buckets are narrower than every cell: two comparisons settle the lookup
+    uint32_t rec_off, hs_off, bkt_off;
     uint32_t out_col;             // column in the sorted band list
     float cost;
-    uint32_t msplit[kMaxSplit];   // record of the left-gauge copy of each split node (ascending); records up to
-                                  // msplit[s] belong to regions <= s
+    uint32_t pad_;
+    uint32_t msplit[kMaxSplit];   // record of the left-gauge copy of each split node (ascending); 0x7fffffff if unused
 };
 static_assert(sizeof(BandHeader2) == 256, "BandHeader2 layout");
 
 struct Band2 {
     const BandHeader2 *h;  // split constants are read from the header when an interval crosses a split
-    const RecA *ra;
-    const RecB *rb;
-    const double *s;       // slope of R in the cell whose left node is record r (0 in zero-width cells)
+    const Rec *rec;
+    const double *hs;      // half the slope of R in the cell whose left node is record r (0 in zero-width cells)
     const uint16_t *bkt;   // last record whose node is at or below the (slightly lowered) start of the bucket
-    double f_first, f_last, bk_scale, bk_c0;
+    double bk_scale, bk_c0;
     int m0, nsplit, nbkt;  // m0 = msplit[0]
-    bool one_probe;
+    bool two_probe;
 };
 EGG_HD void make_band2(const uint8_t *blob, const BandHeader2 &h, Band2 &v) {
     v.h = &h;
-    v.ra = reinterpret_cast<const RecA *>(blob + h.ra_off);
-    v.rb = reinterpret_cast<const RecB *>(blob + h.rb_off);
-    v.s = reinterpret_cast<const double *>(blob + h.s_off);
+    v.rec = reinterpret_cast<const Rec *>(blob + h.rec_off);
+    v.hs = reinterpret_cast<const double *>(blob + h.hs_off);
     v.bkt = reinterpret_cast<const uint16_t *>(blob + h.bkt_off);
-    v.f_first = h.f_first; v.f_last = h.f_last;
     v.bk_scale = h.bk_scale; v.bk_c0 = h.bk_c0;
     v.m0 = (int)h.msplit[0]; v.nsplit = (int)h.nsplit; v.nbkt = (int)h.nbkt;
-    v.one_probe = h.one_probe != 0;
+    v.two_probe = h.two_probe != 0;
 }
 
 // One node of the disk grid as the walk reads it (the same for every galaxy: loaded with a warp-uniform address).
@@ -102,9 +107,13 @@ struct alignas(16) GridNode {
     double x;      // rest wavelength [um]
     double idxp;   // 1 / (x_j - x_{j-1}); 0 for j = 0
     double idxpo;  // optical node: 1 / (x_j - x of the previous optical node), 0 if there is none; else 0
-    int32_t o;     // index in the optical (bulge) grid, -1 if the node is not an optical node
+    int32_t o;     // index in the optical (bulge) grid, -1 if the node is not an optical node; bit 30 (kNextNotOptical):
+                   // node j + 1 is not an optical node (the walk then keeps the state of j for the bulge interval that
+                   // starts here; otherwise that interval is the disk interval [j, j + 1])
     int32_t po;    // disk-grid index of the last optical node before j, -1 if none
 };
+constexpr int32_t kNextNotOptical = 1 << 30;
+EGG_HD int grid_o(const GridNode &g) { return g.o < 0 ? -1 : (g.o & (kNextNotOptical - 1)); }
 static_assert(sizeof(GridNode) == 32, "GridNode layout");
 
 // Per-lane scalars of a batch (structure of arrays: lane l reads element l of each, no bank conflicts).
@@ -122,34 +131,33 @@ struct LaneScal {
 
 // Dynamic shared memory of the lane kernel; the table builder sizes the band groups against `tab_budget`.
 struct LaneSmem {
-    uint32_t tab, res, rfres, lwin, bwin, cov, total;
+    uint32_t tab, rfres, lwin, lrange, bwin, cov, total;
 };
 EGG_HD uint32_t lane_up128(size_t v) { return (uint32_t)((v + 127) & ~size_t(127)); }
-EGG_HD LaneSmem lane_smem_layout(size_t max_blob, size_t nband, size_t nrf, size_t nline) {
+EGG_HD LaneSmem lane_smem_layout(size_t max_blob, size_t ntab, size_t nband, size_t nrf, size_t nline) {
     LaneSmem L;
     uint32_t o = 0;
     L.tab = o; o += lane_up128(max_blob);                               // band tables of the current group
-    L.res = o; o += lane_up128(nband * kLanes * 2 * sizeof(double));    // [band][comp][lane] flux sums
     L.rfres = o; o += lane_up128(nrf * kLanes * 2 * sizeof(double));    // [rf][comp][lane]
     L.lwin = o; o += lane_up128(2 * nline * kLanes * sizeof(uint32_t)); // [comp][line][lane] line windows b0 | b1 << 16
-    L.bwin = o; o += lane_up128(nband * 16);                            // per band: window, first block, item base, ticket
+    L.lrange = o; o += lane_up128(2 * nline * sizeof(uint32_t));        // [comp][line] union of the lanes' windows
+    L.bwin = o; o += lane_up128(ntab * 16);                             // per table: window, first block, slot base, column
     L.cov = o; o += lane_up128(nband * 16);                             // per output column: full span of the filter
     L.total = o;
     return L;
 }
 constexpr size_t kLaneStaticSmem = sizeof(LaneScal) + 1024;             // __shared__ variables of the kernel
-constexpr size_t kSmemPerCta = 232448;                                  // 227 KB
-
-constexpr int kRightOfSpan = 0x7fffffff;
+constexpr size_t kSmemPerCta = 232448;                                  // 227 KB per CTA, 228 KB per SM
+constexpr size_t kSmemPerSm = 233472;
+constexpr int kLaneCtasPerSm = 2;                                       // two CTAs share an SM: one runs while the other waits at a barrier
 
 // What the intervals on either side need from an SED node at observed wavelength t.
 struct NodeEv {
-    double u;        // offset from the left node of its filter cell
-    double Lin;      // expansion about the left node of its cell  (0 outside the span)
-    double Lout;     // expansion about the right node of its cell (0 outside the span)
-    double k0, hr, s; // of the cell: for an interval that stays inside it
-    int r;           // record of the cell's left node; -1 left of the span, kRightOfSpan right of it
-    int reg;         // gauge region of the node
+    double u;         // offset from the left node of its filter cell
+    double Lin;       // expansion about the left node of its cell
+    double Lout;      // expansion about the right node of its cell
+    double k0, hr, hs; // of the cell: for an interval that stays inside it
+    int r;            // record of the cell's left node
 };
 
 // integer nearest to y (|y| < 2^31) without a conversion instruction: the low word of y + 1.5 * 2^52
@@ -165,40 +173,22 @@ EGG_HD int round_lo(double y) {
 }
 
 EGG_HD void eval_node(const Band2 &b, double t, NodeEv &e) {
-    const bool inner = t > b.f_first && t < b.f_last;
-    if (!inner) {
-        const bool right = t >= b.f_last;
-        e.reg = right ? b.nsplit : 0;
-        e.r = right ? kRightOfSpan : -1;
-        e.u = 0.0; e.Lin = 0.0; e.Lout = 0.0; e.k0 = 0.0; e.hr = 0.0; e.s = 0.0;
-        return;
-    }
     int k = round_lo(fma(t, b.bk_scale, b.bk_c0));
     k = k < 0 ? 0 : (k > b.nbkt - 1 ? b.nbkt - 1 : k);
     int r = b.bkt[k];
-    int reg;
-    if (b.one_probe) {
-        r += t >= b.ra[r + 1].f ? 1 : 0;
-        // the left-gauge copy of a split node opens a cell without width: step over it
-        if (b.nsplit == 1) { r += r == b.m0 ? 1 : 0; reg = r > b.m0 ? 1 : 0; }
-        else {
-            reg = 0;
-            for (int s = 0; s < b.nsplit; ++s) { const int ms = (int)b.h->msplit[s]; r += r == ms ? 1 : 0; reg += r > ms ? 1 : 0; }
-        }
+    if (b.two_probe) {
+        r += t >= b.rec[r + 1].f ? 1 : 0;
+        r += t >= b.rec[r + 1].f ? 1 : 0; // a split node or an abrupt end is two records at one wavelength
     } else {
-        while (t >= b.ra[r + 1].f) ++r;
-        reg = 0;
-        for (int s = 0; s < b.nsplit; ++s) reg += r > (int)b.h->msplit[s] ? 1 : 0;
+        while (t >= b.rec[r + 1].f) ++r;
     }
-    const RecA a0 = b.ra[r], a1 = b.ra[r + 1];
-    const RecB q0 = b.rb[r], q1 = b.rb[r + 1];
-    const double u = t - a0.f, v = t - a1.f;
+    const Rec q0 = b.rec[r], q1 = b.rec[r + 1];
+    const double u = t - q0.f, v = t - q1.f;
     e.u = u;
-    e.Lin = fma(u, fma(u, q0.hr, q0.k0), a0.L);
-    e.Lout = fma(v, fma(v, q1.hr, q1.k0), a1.L);
-    e.k0 = q0.k0; e.hr = q0.hr; e.s = b.s[r];
+    e.Lin = fma(u, fma(u, q0.hr, q0.k0), q0.L);
+    e.Lout = fma(v, fma(v, q1.hr, q1.k0), q1.L);
+    e.k0 = q0.k0; e.hr = q0.hr; e.hs = b.hs[r];
     e.r = r;
-    e.reg = reg;
 }
 
 // E (times 1+z) of the SED interval from node p to node e, in the gauge of p's region; idx = 1 / (x_e - x_p) in the
@@ -206,14 +196,16 @@ EGG_HD void eval_node(const Band2 &b, double t, NodeEv &e) {
 // splits the interval crosses): E - jump is the same quantity in the gauge of e's region.
 EGG_HD double interval_E(const Band2 &b, const NodeEv &p, const NodeEv &e, double te, double idx, double opz, double &jump) {
     jump = 0.0;
-    if (e.r == p.r && (unsigned)e.r < (unsigned)kRightOfSpan)
-        return opz * fma(0.5 * e.s * p.u, e.u, fma(p.u + e.u, e.hr, e.k0));
+    if (e.r == p.r) return opz * fma(e.hs * p.u, e.u, fma(p.u + e.u, e.hr, e.k0));
     double d = e.Lin - p.Lout;
-    if (e.reg != p.reg) {
+    if (b.nsplit > 0 && p.r <= (int)b.h->msplit[b.nsplit - 1] && e.r > b.m0) {
         double dsum = 0.0;
-        for (int s = p.reg; s < e.reg; ++s) {
-            d += fma(b.h->splitD[s], te - b.h->splitF[s], b.h->splitC[s]);
-            dsum += b.h->splitD[s];
+        for (int s = 0; s < b.nsplit; ++s) {
+            const int ms = (int)b.h->msplit[s];
+            if (p.r <= ms && e.r > ms) { // the interval crosses split s
+                d += fma(b.h->splitD[s], te - b.h->splitF[s], b.h->splitC[s]);
+                dsum += b.h->splitD[s];
+            }
         }
         jump = dsum * opz;
     }
@@ -223,39 +215,38 @@ EGG_HD double interval_E(const Band2 &b, const NodeEv &p, const NodeEv &e, doubl
 // Weighted sums of one block of SED nodes for one galaxy: accd += sum_{j in [a, b]} Sd_j W_j over the disk nodes and
 // accb += sum over the optical nodes among them of Sb_o W^b_o.  The walk arrives at nodes js..je (js <= a - 1 unless
 // a = 0, je >= b + 1; wide enough that the optical node before the first and after the last optical node of [a, b] are
-// visited): arriving at node j closes the interval [j-1, j] and settles the weight of node j-1.  grid has one virtual node
-// after the last real one (far to the red, flagged optical) so that je = b + 1 always exists.
+// visited): arriving at node j closes the interval [j-1, j] and settles the weight of node j-1.  grid has virtual nodes
+// after the last real one (far to the red, flagged optical) so that je = b + 1 always exists.  The walk starts from a
+// state blue of every filter: the first interval it closes weighs nothing it accumulates (its left node is before a,
+// or it is the first node of the grid, whose idxp is 0).
 template <typename real, typename Sed>
 EGG_HD void walk_block(const Band2 &bv, const GridNode *grid, double opz, bool bulge, int a, int b, int js, int je,
                        const Sed &sed, real &accd, real &accb) {
     NodeEv prev, prevo, cur;
-    bool have_prev = false, have_o = false;
-    double Eprev_d = 0.0, Eprev_b = 0.0, E_d = 0.0, jump_d = 0.0;
+    prev.u = 0.0; prev.Lin = 0.0; prev.Lout = 0.0; prev.k0 = 0.0; prev.hr = 0.0; prev.hs = 0.0; prev.r = -1;
+    prevo = prev;
+    double Eprev_d = 0.0, Eprev_b = 0.0;
     real Sprev_d = real(0), Sprev_b = real(0);
     int jprevo = -1;
-    prev.r = -1; prevo.r = -1;
     for (int j = js; j <= je; ++j) {
         const GridNode g = grid[j];
         const double t = opz * g.x; // the reference's lam = rlam * (1 + z) (src/egg-gencat.cpp:2161), in double
         eval_node(bv, t, cur);
         const real Sd = sed.disk(j);
-        if (have_prev) {
-            E_d = interval_E(bv, prev, cur, t, g.idxp, opz, jump_d);
-            if (j - 1 >= a && j - 1 <= b) accd = fma((real)(E_d - Eprev_d), Sprev_d, accd);
-            Eprev_d = E_d - jump_d;
-        }
+        double jump_d;
+        const double E_d = interval_E(bv, prev, cur, t, g.idxp, opz, jump_d);
+        if (j - 1 >= a && j - 1 <= b) accd = fma((real)(E_d - Eprev_d), Sprev_d, accd);
+        Eprev_d = E_d - jump_d;
         if (bulge && g.o >= 0) {
-            const real Sb = sed.bulge(g.o);
-            if (have_o) {
-                double E_b, jump_b;
-                if (g.po == j - 1 && have_prev) { E_b = E_d; jump_b = jump_d; } // the interval is a disk interval too
-                else E_b = interval_E(bv, prevo, cur, t, g.idxpo, opz, jump_b);
-                if (jprevo >= a && jprevo <= b) accb = fma((real)(E_b - Eprev_b), Sprev_b, accb);
-                Eprev_b = E_b - jump_b;
-            }
-            prevo = cur; have_o = true; Sprev_b = Sb; jprevo = j;
+            const real Sb = sed.bulge(grid_o(g));
+            double E_b, jump_b;
+            if (g.po == j - 1 && j > js) { E_b = E_d; jump_b = jump_d; } // the interval is a disk interval too
+            else E_b = interval_E(bv, prevo, cur, t, g.idxpo, opz, jump_b);
+            if (jprevo >= a && jprevo <= b) accb = fma((real)(E_b - Eprev_b), Sprev_b, accb);
+            Eprev_b = E_b - jump_b;
+            prevo = cur; Sprev_b = Sb; jprevo = j;
         }
-        prev = cur; Sprev_d = Sd; have_prev = true;
+        prev = cur; Sprev_d = Sd;
     }
 }
 

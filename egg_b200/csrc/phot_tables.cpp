@@ -286,48 +286,56 @@ Status make_grid_thresholds(Grid &g, bool apply_igm, const char *what) {
 // ---- tables of the lane kernel (phot_lane.cuh) --------------------------------------------------------------------
 struct BandTable2 {
     BandHeader2 h{};
-    std::vector<RecA> ra;
-    std::vector<RecB> rb;
-    std::vector<double> s;
+    std::vector<Rec> rec;
+    std::vector<double> hs;
     std::vector<uint16_t> bkt;
 };
 
-Status build_band_table2(const Filter &f, uint32_t out_col, int bucket_factor, BandTable2 &t) {
-    const int nf = (int)f.lam.size();
+// Table of the response (lam, res)[i0..i1] (a whole filter or a piece of one cut at filter nodes).
+Status build_band_table2(const Filter &f, int i0, int i1, uint32_t out_col, int bucket_factor, BandTable2 &t) {
     t = BandTable2();
     t.h.out_col = out_col;
     t.h.full_first = f.lam.front();
     t.h.full_last = f.lam.back();
-    t.h.f_first = t.h.f_last = t.h.full_first;
-    t.bkt.assign(1, 0);
-    t.h.nbkt = 1;
+    t.h.f_first = t.h.f_last = f.lam[i0];
+    for (int s = 0; s < kMaxSplit; ++s) t.h.msplit[s] = 0x7fffffffu;
     // drop the wings where the response is identically zero (they add exactly nothing to the union-grid trapezoid)
     int a = -1, b = -1;
-    for (int i = 0; i < nf; ++i)
+    for (int i = i0; i <= i1; ++i)
         if (f.res[i] != 0.0) { if (a < 0) a = i; b = i; }
     if (a < 0) return Status(); // identically zero response: n = 0
-    a = std::max(a - 1, 0);
-    b = std::min(b + 1, nf - 1);
-    if (b == a) { b = std::min(a + 1, nf - 1); a = b - 1; }
+    a = std::max(a - 1, i0);
+    b = std::min(b + 1, i1);
     if (!(f.lam[b] > f.lam[a])) return Status(); // no width: nothing to integrate
-    const int n = b - a + 1;
-    if (n > 64990) return Status::error(EGGPHOT_ERR_UNSUPPORTED, "filter with more than 64990 nodes");
-    t.h.n = (uint32_t)n;
-    t.h.f_first = f.lam[a];
-    t.h.f_last = f.lam[b];
-    // node positions are absolute wavelengths: u = t - f is formed from the same two doubles as in the reference
-    std::vector<double> fn(n), R(n), dl(n, 0.0), sl(n, 0.0);
-    for (int i = 0; i < n; ++i) { fn[i] = f.lam[a + i]; R[i] = f.res[a + i]; }
+    // nodes: absolute wavelengths (u = t - f is formed from the same two doubles as in the reference); a zero node at
+    // an end where the response starts or stops abruptly.  (No other node may be added: every filter node is a node of
+    // the union grid, and the trapezoid rule on it is not exact for the quadratic R S.)
+    std::vector<double> fn, R;
+    if (f.res[a] != 0.0) { fn.push_back(f.lam[a]); R.push_back(0.0); }
+    for (int i = a; i <= b; ++i) { fn.push_back(f.lam[i]); R.push_back(f.res[i]); }
+    if (f.res[b] != 0.0) { fn.push_back(f.lam[b]); R.push_back(0.0); }
+    const int n = (int)fn.size();
+    if (n > 64900) return Status::error(EGGPHOT_ERR_UNSUPPORTED, "filter piece with more than 64900 nodes");
+    t.h.f_first = fn[0];
+    t.h.f_last = fn[n - 1];
+    std::vector<double> dl(n, 0.0), sl(n, 0.0);
     for (int i = 0; i + 1 < n; ++i) {
-        dl[i] = f.lam[a + i + 1] - f.lam[a + i];
+        dl[i] = fn[i + 1] - fn[i];
         sl[i] = dl[i] > 0 ? (R[i + 1] - R[i]) / dl[i] : 0.0;
     }
+    // narrowest cell, the zero-width cell between an added end node and the first / last node of the response apart
+    // (that one is what the second probe of the lookup is for); any other repeated wavelength makes the scan necessary
+    const double span = fn[n - 1] - fn[0];
+    double min_dl = span;
+    for (int i = 0; i + 1 < n; ++i)
+        if (fn[i + 1] != fn[i] || !((i == 0 && R[0] == 0.0) || (i + 2 == n && R[n - 1] == 0.0))) min_dl = std::min(min_dl, dl[i]);
+    const bool can_probe = min_dl > 0;
     // ---- anchors: the two ends, and the deepest node of every interior valley of |R| (widest valleys first)
     std::vector<int> anchors;
     {
         double mx = 0;
         for (double r : R) mx = std::max(mx, std::fabs(r));
-        const double thr = 1e-3 * mx;
+        const double thr = 1e-6 * mx;
         struct Valley { int node; double width; };
         std::vector<Valley> val;
         int first_big = -1, last_big = -1;
@@ -343,7 +351,8 @@ Status build_band_table2(const Filter &f, uint32_t out_col, int bucket_factor, B
             int c0 = -1, c1 = -1;
             for (int q = i; q <= k; ++q)
                 if (std::fabs(R[q]) == lo) { if (c0 < 0) c0 = q; c1 = q; }
-            val.push_back(Valley{(c0 + c1) / 2, fn[k] - fn[i]});
+            const int node = (c0 + c1) / 2;
+            if (fn[node] > fn[0] && fn[node] < fn[n - 1]) val.push_back(Valley{node, fn[k] - fn[i]});
             i = k + 1;
         }
         std::stable_sort(val.begin(), val.end(), [](const Valley &x, const Valley &y) { return x.width > y.width; });
@@ -354,27 +363,62 @@ Status build_band_table2(const Filter &f, uint32_t out_col, int bucket_factor, B
         std::sort(anchors.begin(), anchors.end());
         anchors.erase(std::unique(anchors.begin(), anchors.end()), anchors.end());
     }
-    const int nsplit = (int)anchors.size() - 1;
-    t.h.nsplit = (uint32_t)nsplit;
-    // ---- split nodes: the half-mass node (of |R|) between consecutive anchors, a_s < m_s <= a_{s+1}
-    std::vector<int> msp(nsplit);
-    for (int s = 0; s < nsplit; ++s) {
-        const int a0 = anchors[s], a1 = anchors[s + 1];
-        double tot = 0, run = 0;
-        for (int i = a0; i < a1; ++i) tot += 0.5 * (std::fabs(R[i]) + std::fabs(R[i + 1])) * dl[i];
-        int m = a1;
-        for (int i = a0; i < a1; ++i) {
-            run += 0.5 * (std::fabs(R[i]) + std::fabs(R[i + 1])) * dl[i];
-            if (run >= 0.5 * tot) { m = i + 1; break; }
+    // ---- split nodes: the half-mass node (of |R|) between consecutive anchors, moved if need be so that its wavelength
+    //      lies strictly inside the span and no other node shares it (a split is two records at one wavelength: with an
+    //      abrupt end or a jump of the response there the two-probe lookup would not reach the cell)
+    std::vector<int> msp;
+    bool force_scan = false;
+    {
+        auto lone = [&](int i) {
+            if (!(fn[i] > fn[0] && fn[i] < fn[n - 1])) return false;
+            return !can_probe || ((i == 0 || fn[i - 1] != fn[i]) && (i == n - 1 || fn[i + 1] != fn[i])); // the scan passes any run
+        };
+        std::vector<int> keep{anchors[0]};
+        for (size_t s = 0; s + 1 < anchors.size(); ++s) {
+            const int a0 = keep.back(), a1 = anchors[s + 1];
+            double tot = 0, run = 0;
+            for (int i = a0; i < a1; ++i) tot += 0.5 * (std::fabs(R[i]) + std::fabs(R[i + 1])) * dl[i];
+            int m = a1;
+            for (int i = a0; i < a1; ++i) {
+                run += 0.5 * (std::fabs(R[i]) + std::fabs(R[i + 1])) * dl[i];
+                if (run >= 0.5 * tot) { m = i + 1; break; }
+            }
+            int best = -1; // the lone node of (a0, a1] nearest to m
+            for (int i = a0 + 1; i <= a1; ++i)
+                if (lone(i) && (best < 0 || std::abs(i - m) < std::abs(best - m))) best = i;
+            if (best < 0) continue; // no usable split between these anchors: a1 joins the region of a0
+            msp.push_back(best);
+            keep.push_back(a1);
         }
-        msp[s] = m;
+        anchors = keep;
+        if (msp.empty()) {
+            // no node strictly inside the span on its own wavelength (a two-node top-hat): split at the half-mass node
+            // wherever it is and let the scan pass the records that share its wavelength
+            double tot = 0, run = 0;
+            for (int i = 0; i + 1 < n; ++i) tot += 0.5 * (std::fabs(R[i]) + std::fabs(R[i + 1])) * dl[i];
+            int m = n - 2;
+            for (int i = 0; i + 1 < n; ++i) {
+                run += 0.5 * (std::fabs(R[i]) + std::fabs(R[i + 1])) * dl[i];
+                if (run >= 0.5 * tot) { m = i + 1; break; }
+            }
+            msp.push_back(std::min(std::max(m, 1), n - 2));
+            anchors = {0, n - 1};
+            force_scan = true;
+        }
     }
-    // ---- per region: (Lambda, K0) = (0, 0) at the anchor, accumulated outwards in long double.
-    //      K0 = running trapezoid of R; Lambda = L - G/6 advances by dl (K0 + R dl / 2) per cell (phot_core.cuh)
-    const int nrec = n + nsplit;
-    t.ra.resize(nrec); t.rb.resize(nrec); t.s.assign(nrec, 0.0);
+    const int nsplit = (int)msp.size();
+    t.h.nsplit = (uint32_t)nsplit;
+    // ---- records: [left sentinel][nodes; region s holds nodes msp[s-1]..msp[s], (Lambda, K0) = (0, 0) at its anchor,
+    //      accumulated outwards in long double: K0 = running trapezoid of R, Lambda = L - G/6 advances by
+    //      dl (K0 + R dl / 2) per cell (phot_core.cuh)][terminator]
+    const int nrec = 1 + n + nsplit + 1;
+    t.h.n = (uint32_t)nrec;
+    t.rec.assign(nrec, Rec{0, 0, 0, 0});
+    t.hs.assign(nrec, 0.0);
+    t.rec[0] = Rec{fn[0] - std::max(fn[n - 1] - fn[0], 1e-6), 0, 0, 0};
+    t.rec[nrec - 1] = Rec{1e300, 0, 0, 0};
     std::vector<long double> K0(n), L(n);
-    std::vector<long double> Kat(nsplit), Lat(nsplit); // region s at its right end (split node m_s)
+    std::vector<long double> Kat(nsplit), Lat(nsplit); // region s at its right end (split node msp[s])
     for (int s = 0; s <= nsplit; ++s) {
         const int lo = s == 0 ? 0 : msp[s - 1], hi = s == nsplit ? n - 1 : msp[s], an = anchors[s];
         K0[an] = 0; L[an] = 0;
@@ -387,52 +431,51 @@ Status build_band_table2(const Filter &f, uint32_t out_col, int bucket_factor, B
             L[i] = L[i + 1] - (long double)dl[i] * (K0[i] + 0.5L * (long double)R[i] * dl[i]);
         }
         for (int i = lo; i <= hi; ++i) {
-            t.ra[i + s] = RecA{fn[i], (double)L[i]};
-            t.rb[i + s] = RecB{(double)K0[i], 0.5 * R[i]};
-            if (i < hi) t.s[i + s] = sl[i]; // the last record of a region opens no cell of it
+            t.rec[1 + i + s] = Rec{fn[i], (double)L[i], (double)K0[i], 0.5 * R[i]};
+            if (i < hi) t.hs[1 + i + s] = 0.5 * sl[i]; // the last record of a region opens no cell of it
         }
         if (s > 0) { // gauge jump across split s-1: Lambda_{s-1}(t) - Lambda_s(t) = C + D (t - F)
             t.h.splitC[s - 1] = (double)(Lat[s - 1] - L[lo]);
             t.h.splitD[s - 1] = (double)(Kat[s - 1] - K0[lo]);
             t.h.splitF[s - 1] = fn[lo];
         }
-        if (s < nsplit) { Kat[s] = K0[hi]; Lat[s] = L[hi]; t.h.msplit[s] = (uint32_t)(hi + s); }
+        if (s < nsplit) { Kat[s] = K0[hi]; Lat[s] = L[hi]; t.h.msplit[s] = (uint32_t)(1 + hi + s); }
     }
-    for (int s = nsplit; s < kMaxSplit; ++s) t.h.msplit[s] = 0x7fffffffu;
-    // bucket table: bkt[k] = last record whose node is at or below the start of bucket k, the start lowered by 1e-6 of a
-    // bucket (the kernel's index is the rounding of a double product: it can exceed the exact one only for a t within
-    // ~1e-10 of a bucket of the boundary).  When buckets narrower than every cell are affordable one probe settles it.
-    const double span = fn[n - 1] - fn[0];
-    double min_dl = span;
-    for (int i = 0; i + 1 < n; ++i) min_dl = std::min(min_dl, dl[i]);
-    int nbkt = std::min(std::max(bucket_factor * n, 1), 65000);
-    if (min_dl > 0) {
+    // ---- bucket table: entry 0 -> the left sentinel, entries 1..nb -> bkt = last record whose node is at or below the
+    //      start of the bucket, the start lowered by 1e-6 of a bucket (the kernel's index is the rounding of a double
+    //      product: it can exceed the exact one only for a t within ~1e-10 of a bucket of the boundary), entry nb + 1 ->
+    //      the last node (everything red of the span).  When buckets narrower than every cell are affordable two probes
+    //      settle the lookup (two, because a split node or an abrupt end is two records at one wavelength).
+    int nb = std::min(std::max(bucket_factor * n, 1), 64000);
+    if (can_probe && !force_scan) {
         const double need = std::ceil(span / min_dl * 1.02) + 1;
-        if (need <= 8.0 * n && need <= 65000.0) {
-            nbkt = std::max((int)need, 1);
-            t.h.one_probe = 1;
+        if (need <= 8.0 * n && need <= 64000.0) {
+            nb = std::max((int)need, 1);
+            t.h.two_probe = 1;
         }
     }
-    t.h.nbkt = (uint32_t)nbkt;
-    t.h.bk_scale = nbkt / span;
-    t.h.bk_c0 = -fn[0] * t.h.bk_scale - 0.5;
-    t.bkt.assign(nbkt, 0);
-    int r = 0;
-    for (int k = 0; k < nbkt; ++k) {
+    t.h.nbkt = (uint32_t)(nb + 2);
+    t.h.bk_scale = nb / span;
+    t.h.bk_c0 = -fn[0] * t.h.bk_scale - 0.5 + 1.0; // entry = bucket + 1
+    t.bkt.assign(nb + 2, 0);
+    const int last_node = nrec - 2;
+    int r = 0; // the left sentinel: bucket 0 starts (just) blue of the span
+    for (int k = 0; k < nb; ++k) {
         const double edge = fn[0] + ((double)k - 1e-6) / t.h.bk_scale;
-        while (r + 1 < nrec - 1 && t.ra[r + 1].f <= edge) ++r; // never the last record: it opens no cell
-        t.bkt[k] = (uint16_t)r;
+        while (t.rec[r + 1].f <= edge) ++r; // edge < f_last: never reaches the last node, which opens the cell red of the span
+        t.bkt[k + 1] = (uint16_t)r;
     }
+    t.bkt[0] = 0;
+    t.bkt[nb + 1] = (uint16_t)last_node;
     return Status();
 }
 
 size_t band_bytes2(const BandTable2 &t) {
-    return up16(t.ra.size() * sizeof(RecA)) + up16(t.rb.size() * sizeof(RecB)) + up16(t.s.size() * sizeof(double)) +
-           up16(t.bkt.size() * sizeof(uint16_t));
+    return up16(t.rec.size() * sizeof(Rec)) + up16(t.hs.size() * sizeof(double)) + up16(t.bkt.size() * sizeof(uint16_t));
 }
 
-template <typename T> uint32_t append_raw(std::vector<uint8_t> &blob, const std::vector<T> &v) {
-    align16(blob);
+template <typename T> uint32_t append_raw(std::vector<uint8_t> &blob, const std::vector<T> &v, size_t align) {
+    blob.resize((blob.size() + align - 1) / align * align, 0);
     const uint32_t off = (uint32_t)blob.size();
     const uint8_t *p = reinterpret_cast<const uint8_t *>(v.data());
     blob.insert(blob.end(), p, p + v.size() * sizeof(T));
@@ -441,10 +484,9 @@ template <typename T> uint32_t append_raw(std::vector<uint8_t> &blob, const std:
 
 void append_band2(std::vector<uint8_t> &blob, size_t header_pos, const BandTable2 &t) {
     BandHeader2 h = t.h;
-    h.ra_off = append_raw(blob, t.ra);
-    h.rb_off = append_raw(blob, t.rb);
-    h.s_off = append_raw(blob, t.s);
-    h.bkt_off = append_raw(blob, t.bkt);
+    h.rec_off = append_raw(blob, t.rec, 32);
+    h.hs_off = append_raw(blob, t.hs, 16);
+    h.bkt_off = append_raw(blob, t.bkt, 16);
     align16(blob);
     std::memcpy(blob.data() + header_pos, &h, sizeof(h));
 }
@@ -480,8 +522,8 @@ Status build_lane_tables(Prepared &P, const eggphot_opts &opts) {
     // ---- the disk grid as the walk reads it
     const Grid &gd = P.grid_disk, &gb = P.grid_bulge;
     const int nD = gd.n(), nB = gb.n();
-    P.grid_nodes.assign((size_t)nD + 1, GridNode{0, 0, 0, -1, -1});
-    P.next_opt.assign((size_t)nD + 1, nD);
+    P.grid_nodes.assign((size_t)nD + 2, GridNode{0, 0, 0, -1, -1});
+    P.next_opt.assign((size_t)nD + 2, nD);
     P.opt_node.assign((size_t)nB, 0);
     {
         int o = 0, lasto = -1;
@@ -508,35 +550,67 @@ Status build_lane_tables(Prepared &P, const eggphot_opts &opts) {
         v.po = lasto;
         v.o = P.has_bulge ? nB : -1;
         v.idxpo = lasto >= 0 ? 1.0 / (v.x - gd.x[lasto]) : 0.0;
+        // a second virtual node: the unrolled walk of the kernel may arrive one node past the end of a block
+        GridNode &v2 = P.grid_nodes[nD + 1];
+        v2 = v;
+        v2.x = v.x * 2.0;
+        v2.idxp = 1.0 / (v2.x - v.x);
+        v2.po = nD;
+        v2.o = P.has_bulge ? nB + 1 : -1;
+        v2.idxpo = 1.0 / (v2.x - v.x);
         int nxt = nD;
         for (int j = nD; j >= 0; --j) {
             P.next_opt[j] = nxt;
             if (j < nD && P.grid_nodes[j].o >= 0) nxt = j;
         }
         P.next_opt[nD] = nD;
+        P.next_opt[nD + 1] = nD + 1;
         if (P.has_bulge)
             for (int o2 = 0; o2 < nB; ++o2)
                 if (P.grid_nodes[P.opt_node[o2]].o != o2)
                     return Status::error(EGGPHOT_ERR_GRID, "an optical node is missing from the disk grid");
+        for (int j = 0; j <= nD; ++j)
+            if (P.grid_nodes[j].o >= 0 && P.grid_nodes[j + 1].o < 0) P.grid_nodes[j].o |= kNextNotOptical;
     }
     // ---- band tables in groups
     const size_t nl = P.no_nebular ? 0 : P.line_lambda.size();
     size_t budget = opts.smem_table_budget;
     if (!budget) {
-        const size_t fixed = lane_smem_layout(0, P.bands.size(), P.rfbands.size(), nl).total + kLaneStaticSmem;
-        budget = fixed + 64u * 1024 < kSmemPerCta ? kSmemPerCta - fixed : 64u * 1024;
+        // two CTAs per SM (1 KB of each CTA's share is reserved by the system); up to ~1.5 tables per band after cuts
+        const size_t fixed = lane_smem_layout(0, P.bands.size() * 2 + 16, P.bands.size(), P.rfbands.size(), nl).total + kLaneStaticSmem + 1024;
+        const size_t share = kSmemPerSm / kLaneCtasPerSm;
+        budget = fixed + 32u * 1024 < share ? share - fixed : 32u * 1024;
     }
-    std::vector<BandTable2> tabs(P.bands.size());
-    std::vector<size_t> size(tabs.size());
+    // a filter whose table exceeds the budget is cut at filter nodes into pieces that feed the same output column
+    std::vector<BandTable2> tabs;
+    std::vector<size_t> size;
     for (size_t b = 0; b < P.bands.size(); ++b) {
-        Status st = build_band_table2(P.bands[b], (uint32_t)b, 2, tabs[b]);
-        if (!st.ok()) return st;
-        size[b] = band_bytes2(tabs[b]) + sizeof(BandHeader2) + 16;
-        if (size[b] > std::max<size_t>(budget, opts.smem_table_budget ? 204u * 1024 : 0))
-            return Status::error(EGGPHOT_ERR_UNSUPPORTED, "filter " + std::to_string(P.band_order[b]) +
-                                 " has too many nodes for the shared-memory band tables");
-        const int lo = last_le(gd.x, tabs[b].h.f_first / 2.0), hi = last_le(gd.x, tabs[b].h.f_last / 2.0);
-        tabs[b].h.cost = (float)std::max(hi - lo, 1);
+        const Filter &f = P.bands[b];
+        const int nf = (int)f.lam.size();
+        for (int pieces = 1;; ++pieces) {
+            if (pieces > 64) return Status::error(EGGPHOT_ERR_UNSUPPORTED, "filter " + std::to_string(P.band_order[b]) +
+                                                  " has too many nodes for the shared-memory band tables");
+            std::vector<BandTable2> cut(pieces);
+            bool fits = true;
+            for (int q = 0; q < pieces && fits; ++q) {
+                const int i0 = (int)((long)(nf - 1) * q / pieces), i1 = (int)((long)(nf - 1) * (q + 1) / pieces);
+                if (i1 <= i0) { fits = false; break; }
+                Status st = build_band_table2(f, i0, i1, (uint32_t)b, 2, cut[q]);
+                if (!st.ok()) return st;
+                fits = band_bytes2(cut[q]) + sizeof(BandHeader2) + 64 <= budget;
+            }
+            if (!fits && nf - 1 >= 2 * (pieces + 1)) continue;
+            if (!fits) return Status::error(EGGPHOT_ERR_UNSUPPORTED, "filter " + std::to_string(P.band_order[b]) +
+                                            " does not fit the shared-memory band tables; raise smem_table_budget");
+            for (auto &c : cut) {
+                if (c.h.n == 0 && pieces > 1) continue; // a piece without response
+                const int lo = last_le(gd.x, c.h.f_first / 2.0), hi = last_le(gd.x, c.h.f_last / 2.0);
+                c.h.cost = (float)std::max(hi - lo, 1);
+                size.push_back(band_bytes2(c) + sizeof(BandHeader2) + 64);
+                tabs.push_back(std::move(c));
+            }
+            break;
+        }
     }
     for (auto &bin : pack_groups(size, budget)) {
         if (bin.empty()) continue;
@@ -544,7 +618,7 @@ Status build_lane_tables(Prepared &P, const eggphot_opts &opts) {
         BandGroup g;
         g.blob.assign(bin.size() * sizeof(BandHeader2), 0);
         for (size_t k = 0; k < bin.size(); ++k) {
-            g.cols.push_back((uint32_t)bin[k]);
+            g.cols.push_back(tabs[bin[k]].h.out_col);
             append_band2(g.blob, k * sizeof(BandHeader2), tabs[bin[k]]);
         }
         P.groups2.push_back(std::move(g));

@@ -234,7 +234,7 @@ void run2(const Prepared &P, const eggphot_galaxies &G, size_t ngal, double *fd,
     for (size_t g = 0; g < ngal; ++g) perm[g] = (uint32_t)g;
     std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return G.z[a] < G.z[b]; });
     std::vector<double> SDd(nD), SBd(nB);
-    std::vector<std::vector<real>> SD(kLanes, std::vector<real>(nD + 1, real(0))), SB(kLanes, std::vector<real>(nB + 1, real(0)));
+    std::vector<std::vector<real>> SD(kLanes, std::vector<real>(nD + 2, real(0))), SB(kLanes, std::vector<real>(nB + 2, real(0)));
     for (size_t g0 = 0; g0 < ngal; g0 += kLanes) {
         const int ng = (int)std::min<size_t>(kLanes, ngal - g0);
         double opz[kLanes], aflux[kLanes], a_b[kLanes];
@@ -284,48 +284,51 @@ void run2(const Prepared &P, const eggphot_galaxies &G, size_t ngal, double *fd,
                 }
             }
         }
+        // block sums per output column (a filter cut into several tables adds them up), tables in group order
+        std::vector<double> resd(nb * kLanes, 0.0), resb(nb * kLanes, 0.0);
+        std::vector<double> cfirst(nb, 0.0), clast(nb, 0.0);
         for (const BandGroup &grp : P.groups2) {
             const uint8_t *blob = grp.blob.data();
             const BandHeader2 *hdr = reinterpret_cast<const BandHeader2 *>(blob);
             for (size_t bi = 0; bi < grp.cols.size(); ++bi) {
                 const BandHeader2 &h = hdr[bi];
-                std::vector<double> resd(kLanes, 0.0), resb(kLanes, 0.0);
-                if (h.n >= 2 && nD >= 2) {
-                    Band2 bv;
-                    make_band2(blob, h, bv);
-                    // union window of the batch, with margins (extra nodes weigh exactly nothing)
-                    const double xlo = h.f_first / omax * (1.0 - 1e-9), xhi = h.f_last / omin * (1.0 + 1e-9);
-                    int jlo = std::max(last_le(P.grid_disk.x, xlo), 0);
-                    int jhi = (int)(std::lower_bound(P.grid_disk.x.begin(), P.grid_disk.x.end(), xhi) - P.grid_disk.x.begin());
-                    jhi = std::min(jhi, nD - 1);
-                    if (P.has_bulge) widen_window_for_bulge(grid, P.next_opt.data(), nD, jlo, jhi);
-                    for (int k = jlo / kLaneBlock; k <= jhi / kLaneBlock; ++k) {
-                        const int a = std::max(jlo, k * kLaneBlock), b = std::min(jhi, k * kLaneBlock + kLaneBlock - 1);
-                        int js, je;
-                        block_arrivals(grid, P.next_opt.data(), P.has_bulge, a, b, js, je);
-                        for (int l = 0; l < ng; ++l) {
-                            real accd = 0, accb = 0;
-                            SedRef<real> sr{SD[l].data(), SB[l].data()};
-                            walk_block<real>(bv, grid, opz[l], P.has_bulge, a, b, js, je, sr, accd, accb);
-                            resd[l] += (double)accd;
-                            resb[l] += (double)accb;
-                        }
+                cfirst[h.out_col] = h.full_first; clast[h.out_col] = h.full_last;
+                if (h.n == 0 || nD < 2) continue;
+                Band2 bv;
+                make_band2(blob, h, bv);
+                // union window of the batch, with margins (extra nodes weigh exactly nothing)
+                const double xlo = h.f_first / omax * (1.0 - 1e-9), xhi = h.f_last / omin * (1.0 + 1e-9);
+                int jlo = std::max(last_le(P.grid_disk.x, xlo), 0);
+                int jhi = (int)(std::lower_bound(P.grid_disk.x.begin(), P.grid_disk.x.end(), xhi) - P.grid_disk.x.begin());
+                jhi = std::min(jhi, nD - 1);
+                if (P.has_bulge) widen_window_for_bulge(grid, P.next_opt.data(), nD, jlo, jhi);
+                for (int k = jlo / kLaneBlock; k <= jhi / kLaneBlock; ++k) {
+                    const int a = std::max(jlo, k * kLaneBlock), b = std::min(jhi, k * kLaneBlock + kLaneBlock - 1);
+                    int js, je;
+                    block_arrivals(grid, P.next_opt.data(), P.has_bulge, a, b, js, je);
+                    for (int l = 0; l < ng; ++l) {
+                        real accd = 0, accb = 0;
+                        SedRef<real> sr{SD[l].data(), SB[l].data()};
+                        walk_block<real>(bv, grid, opz[l], P.has_bulge, a, b, js, je, sr, accd, accb);
+                        resd[h.out_col * kLanes + l] += (double)accd;
+                        resb[h.out_col * kLanes + l] += (double)accb;
                     }
-                }
-                for (int l = 0; l < ng; ++l) {
-                    const size_t g = perm[g0 + l];
-                    const bool covered = nD >= 2 && P.grid_disk.x[0] * opz[l] <= h.full_first && P.grid_disk.x[nD - 1] * opz[l] >= h.full_last;
-                    const bool bulge_on = covered && P.has_bulge && nB >= 2 && P.grid_bulge.x[0] * opz[l] <= h.full_first &&
-                                          P.grid_bulge.x[nB - 1] * opz[l] >= h.full_last;
-                    double fdv = covered ? resd[l] / opz[l] * aflux[l] : 0.0;
-                    double fbv = bulge_on ? resb[l] / opz[l] * aflux[l] * a_b[l] : 0.0;
-                    if (!std::isfinite(fdv)) fdv = 0;
-                    if (!std::isfinite(fbv)) fbv = 0;
-                    fd[g * nb + h.out_col] = fdv;
-                    if (P.has_bulge) fb[g * nb + h.out_col] = fbv;
                 }
             }
         }
+        for (size_t col = 0; col < nb; ++col)
+            for (int l = 0; l < ng; ++l) {
+                const size_t g = perm[g0 + l];
+                const bool covered = nD >= 2 && P.grid_disk.x[0] * opz[l] <= cfirst[col] && P.grid_disk.x[nD - 1] * opz[l] >= clast[col];
+                const bool bulge_on = covered && P.has_bulge && nB >= 2 && P.grid_bulge.x[0] * opz[l] <= cfirst[col] &&
+                                      P.grid_bulge.x[nB - 1] * opz[l] >= clast[col];
+                double fdv = covered ? resd[col * kLanes + l] / opz[l] * aflux[l] : 0.0;
+                double fbv = bulge_on ? resb[col * kLanes + l] / opz[l] * aflux[l] * a_b[l] : 0.0;
+                if (!std::isfinite(fdv)) fdv = 0;
+                if (!std::isfinite(fbv)) fbv = 0;
+                fd[g * nb + col] = fdv;
+                if (P.has_bulge) fb[g * nb + col] = fbv;
+            }
         const double arf = EGGPHOT_LSUN2UJY / (1e-5 * 1e-5);
         for (int l = 0; l < ng; ++l) {
             const size_t g = perm[g0 + l];
