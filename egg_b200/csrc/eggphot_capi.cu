@@ -79,7 +79,7 @@ struct eggphot_ctx {
     // region, the redshift-bucketing buffers.  EGGPHOT_KERNEL=node selects the node-per-lane kernel of phot_kernels.cu.
     bool use_lane = true;
     std::vector<DevBuf> blobs2;
-    DevBuf gridN, nextOpt, tabCol, lane_scratch;
+    DevBuf gridN, nextOpt, tabCol, colSpan, lane_scratch;
     DevBuf zhist[kSlots + 1], zperm[kSlots + 1];
     LaneParams lbase{};
     int lane_blocks = 0;
@@ -172,13 +172,12 @@ int enqueue(eggphot_ctx *c, const eggphot_galaxies &g, size_t ngal, const eggpho
         const uint32_t ngroups2 = c->lbase.fp.ngroups, max_blob2 = c->lbase.fp.max_blob;
         q.fp = p;
         q.fp.ngroups = ngroups2; q.fp.max_blob = max_blob2;
-        for (int g = 0; g < kMaxGroups; ++g) q.fp.groups[g] = groups2[g];
+        for (int k = 0; k < kMaxGroups; ++k) q.fp.groups[k] = groups2[k];
         q.fp.scratch = (char *)c->lane_scratch.p + (size_t)region * c->lane_region_bytes;
         q.perm = (const uint32_t *)c->zperm[region].p;
         int e = launch_zsort(g.z, (uint32_t)ngal, (uint32_t *)c->zhist[region].p, (uint32_t *)c->zperm[region].p, c->num_sms, st);
         if (e != 0) return c->cuda_fail((cudaError_t)e, "redshift bucketing launch");
-        const size_t nbatch = (ngal + kLanes - 1) / kLanes;
-        e = launch_lane_flux_kernel(q, c->P.precision, (int)std::min<size_t>((size_t)c->lane_blocks, nbatch), st);
+        e = launch_lane_flux_kernel(q, c->P.precision, c->lane_blocks, st);
         if (e != 0) return c->cuda_fail((cudaError_t)e, "flux kernel launch");
         c->launches += 4;
         return EGGPHOT_OK;
@@ -401,19 +400,29 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
             CK(c->tabCol.upload(cols.data(), cols.size() * sizeof(uint32_t)));
             q.tab_col = (const uint32_t *)c->tabCol.p;
         }
-        // block-sum slots: a batch whose galaxies span a wide range of redshift can make every table read the whole grid
-        q.max_slots = q.ntab * (uint32_t)(P.grid_disk.n() / kLaneBlock + 2);
-        q.scratch_stride = (uint64_t)((size_t)(P.grid_disk.n() + 2) + (size_t)(P.grid_bulge.n() + 2) + 2 * (size_t)q.max_slots) * kLanes;
+        if (q.ntab > 64) return c->fail(EGGPHOT_ERR_UNSUPPORTED, "more than 64 band tables; raise smem_table_budget");
+        if (P.grid_disk.n() > 32000) return c->fail(EGGPHOT_ERR_UNSUPPORTED, "SED wavelength grid with more than 32000 nodes");
+        {
+            std::vector<double> span(2 * std::max<size_t>(P.bands.size(), 1), 0.0);
+            for (size_t b = 0; b < P.bands.size(); ++b) { span[2 * b] = P.bands[b].lam.front(); span[2 * b + 1] = P.bands[b].lam.back(); }
+            CK(c->colSpan.upload(span.data(), span.size() * sizeof(double)));
+            q.col_span = (const double2 *)c->colSpan.p;
+        }
+        {
+            const size_t rs = P.precision == EGGPHOT_FP64 ? 8 : 4;
+            const size_t rows = ((size_t)(P.grid_disk.n() + 2) + (size_t)(P.grid_bulge.n() + 2)) * kLanes * rs;
+            q.res_offset = (rows + 255) & ~size_t(255);
+            q.scratch_stride = (q.res_offset + (size_t)std::max<uint32_t>(q.ntab, 1) * 2 * kLanes * sizeof(double) + 255) & ~size_t(255);
+        }
         if (c->use_lane) {
             const size_t smem = lane_kernel_smem(q);
-            if (smem + kLaneStaticSmem > (size_t)prop.sharedMemPerBlockOptin)
+            if (smem + kLaneFixedSmem > (size_t)prop.sharedMemPerBlockOptin)
                 return c->fail(EGGPHOT_ERR_UNSUPPORTED, "band tables need " + std::to_string(smem) + " B of shared memory, device offers " +
                                                          std::to_string(prop.sharedMemPerBlockOptin) + "; lower smem_table_budget");
             const int occ = lane_kernel_max_blocks_per_sm(q, P.precision);
             if (occ <= 0) return c->fail(EGGPHOT_ERR_CUDA, "flux kernel cannot be resident (occupancy query failed)");
-            c->lane_blocks = c->num_sms * std::min(occ, kLaneCtasPerSm);
-            const size_t rs = P.precision == EGGPHOT_FP64 ? 8 : 4;
-            c->lane_region_bytes = ((size_t)c->lane_blocks * q.scratch_stride * rs + 255) & ~size_t(255);
+            c->lane_blocks = c->num_sms;
+            c->lane_region_bytes = (size_t)c->lane_blocks * (lane_kernel_threads() / 32) * q.scratch_stride;
             CK(c->lane_scratch.alloc(c->lane_region_bytes * (kSlots + 1)));
             for (auto &h : c->zhist) CK(h.alloc(zsort_hist_bytes()));
         }
@@ -589,6 +598,15 @@ int eggphot_get_seds(eggphot_ctx *c, const eggphot_galaxies *gal, size_t first, 
     CK(cudaStreamSynchronize(c->stream));
 #undef CK
     return read_error_flag(c);
+}
+
+int eggphot_measure_fma_peak(eggphot_ctx *c, double *fp32_tflops, double *fp64_tflops) {
+    if (!c || !c->ready || !fp32_tflops || !fp64_tflops) return c ? c->fail(EGGPHOT_ERR_ARG, "context is not ready") : EGGPHOT_ERR_ARG;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return c->cuda_fail(e, "cudaSetDevice");
+    const int rc = measure_fma_peak(c->num_sms, c->errflag.p ? (char *)c->zhist[0].p : nullptr, c->stream, fp32_tflops, fp64_tflops);
+    if (rc) return c->cuda_fail((cudaError_t)rc, "FMA micro-benchmark");
+    return EGGPHOT_OK;
 }
 
 int eggphot_get_stats(const eggphot_ctx *c, eggphot_stats *s) {

@@ -81,24 +81,30 @@ int launch_flux_kernel(const FluxParams &p, int precision, int grid_blocks, cuda
 int flux_kernel_max_blocks_per_sm(const FluxParams &p, int precision);
 
 // ---- the lane-per-galaxy flux kernel (phot_lane_kernels.cu) ----
-// fp.groups point at the BandHeader2 blobs; fp.scratch at [grid][(nD + 2) + (nB + 2) rows][32 lanes] reals followed by
-// [max_slots][2][32 lanes] block sums.
+// fp.groups point at the BandHeader2 blobs; fp.scratch at the per-warp scratch areas of `scratch_stride` bytes each:
+// [(nD + 2) + (nB + 2) rows][32 lanes] reals, then at res_offset [ntab][2][32 lanes] doubles.
 struct LaneParams {
     FluxParams fp;
     const uint32_t *perm;     // [ngal] galaxies bucketed by redshift (zsort); batches are 32 consecutive entries
-    const GridNode *grid;     // [nD + 1]
-    const int32_t *next_opt;  // [nD + 1]
+    const GridNode *grid;     // [nD + 2]
+    const int32_t *next_opt;  // [nD + 2]
     const uint32_t *tab_col;  // [ntab] output column of every band table, in group order
-    uint32_t ntab;            // band tables (a filter cut into pieces has several)
-    uint32_t max_slots;       // block-sum slots per CTA
-    uint64_t scratch_stride;  // reals per CTA: SED rows of the disk and bulge grids, then the block-sum slots
+    const double2 *col_span;  // [nband] full wavelength span of every filter (coverage test), by output column
+    uint32_t ntab;            // band tables (a filter cut into pieces has several); at most 64
+    uint32_t pad_;
+    uint64_t scratch_stride;  // bytes per warp
+    uint64_t res_offset;      // bytes from the start of a warp's area to its table sums
 };
 size_t lane_kernel_smem(const LaneParams &q);
 int lane_kernel_max_blocks_per_sm(const LaneParams &q, int precision);
+int lane_kernel_threads();
 int launch_lane_flux_kernel(const LaneParams &q, int precision, int grid_blocks, cudaStream_t stream);
 // counting sort of the galaxies by log2(1+z): hist is scratch of zsort_hist_bytes(), perm receives the order
 size_t zsort_hist_bytes();
 int launch_zsort(const float *z, uint32_t ngal, uint32_t *hist, uint32_t *perm, int num_sms, cudaStream_t stream);
+
+// FMA micro-benchmark (scratch: at least 16 bytes of device memory); returns cudaError_t as int
+int measure_fma_peak(int num_sms, void *scratch, cudaStream_t stream, double *fp32_tflops, double *fp64_tflops);
 
 // save_sed: observed-frame lam / sed (f32) of galaxies [first, first+count) of one component
 struct SedParams {

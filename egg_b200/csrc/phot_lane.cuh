@@ -116,40 +116,9 @@ constexpr int32_t kNextNotOptical = 1 << 30;
 EGG_HD int grid_o(const GridNode &g) { return g.o < 0 ? -1 : (g.o & (kNextNotOptical - 1)); }
 static_assert(sizeof(GridNode) == 32, "GridNode layout");
 
-// Per-lane scalars of a batch (structure of arrays: lane l reads element l of each, no bank conflicts).
-struct LaneScal {
-    double opz[kLanes], iopz[kLanes];   // 1 + z and its inverse
-    double aflux[kLanes];               // K (1+z) / d^2          [vif] lsun2uJy(z, d, ...)   (src/egg-gencat.cpp:2162)
-    double a_bulge[kLanes], a_disk[kLanes]; // 10^(m - m2lcor)   get_opt_sed mass scale      (:711, :2106)
-    double c1[kLanes], c2[kLanes];      // IR: L_IR (generic, :2055) or Mdust (1 - fPAH), Mdust fPAH (cs17, :2047-2051)
-    double vdisp[kLanes];
-    float igm[3][kLanes];
-    uint32_t row_b[kLanes], row_d[kLanes], row_i[kLanes];
-    uint32_t gal[kLanes];               // position of the lane's galaxy in the caller's arrays (batches are z-sorted)
-    uint32_t valid[kLanes];
-};
-
-// Dynamic shared memory of the lane kernel; the table builder sizes the band groups against `tab_budget`.
-struct LaneSmem {
-    uint32_t tab, rfres, lwin, lrange, bwin, cov, total;
-};
-EGG_HD uint32_t lane_up128(size_t v) { return (uint32_t)((v + 127) & ~size_t(127)); }
-EGG_HD LaneSmem lane_smem_layout(size_t max_blob, size_t ntab, size_t nband, size_t nrf, size_t nline) {
-    LaneSmem L;
-    uint32_t o = 0;
-    L.tab = o; o += lane_up128(max_blob);                               // band tables of the current group
-    L.rfres = o; o += lane_up128(nrf * kLanes * 2 * sizeof(double));    // [rf][comp][lane]
-    L.lwin = o; o += lane_up128(2 * nline * kLanes * sizeof(uint32_t)); // [comp][line][lane] line windows b0 | b1 << 16
-    L.lrange = o; o += lane_up128(2 * nline * sizeof(uint32_t));        // [comp][line] union of the lanes' windows
-    L.bwin = o; o += lane_up128(ntab * 16);                             // per table: window, first block, slot base, column
-    L.cov = o; o += lane_up128(nband * 16);                             // per output column: full span of the filter
-    L.total = o;
-    return L;
-}
-constexpr size_t kLaneStaticSmem = sizeof(LaneScal) + 1024;             // __shared__ variables of the kernel
-constexpr size_t kSmemPerCta = 232448;                                  // 227 KB per CTA, 228 KB per SM
-constexpr size_t kSmemPerSm = 233472;
-constexpr int kLaneCtasPerSm = 2;                                       // two CTAs share an SM: one runs while the other waits at a barrier
+// Shared memory of the lane kernel: the band tables of the current group, and a little besides.
+constexpr size_t kSmemPerCta = 232448;   // 227 KB
+constexpr size_t kLaneFixedSmem = 2048;  // barrier, per-warp odds and ends
 
 // What the intervals on either side need from an SED node at observed wavelength t.
 struct NodeEv {

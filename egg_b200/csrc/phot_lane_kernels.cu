@@ -70,6 +70,20 @@ __global__ void zsort_scatter(const float *__restrict__ z, uint32_t n, uint32_t 
         perm[atomicAdd(&cursor[zbucket(__ldg(z + g))], 1u)] = g;
 }
 
+// ---- FMA micro-benchmark: the measured peak of the CUDA-core FP32 / FP64 pipes (the roofline of SURVEY.md 8d) ---------
+template <typename T> __global__ void __launch_bounds__(1024) fma_peak_kernel(T *out, int iters, T a, T b) {
+    T x0 = (T)threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    const T s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == (T)123456789) out[0] = s; // never true: keeps the chains alive
+}
+
 // ---- helpers ------------------------------------------------------------------------------------------
 template <typename real> struct Vec16 { real v[16 / sizeof(real)]; };
 __device__ __forceinline__ Vec16<float> ldg16(const float *p) {
@@ -126,68 +140,81 @@ __device__ __forceinline__ int bis_first_ge(const double *__restrict__ x, int n,
     return hi;
 }
 
-struct BandWin { uint32_t w0, w1, w2, w3; }; // jlo | jhi << 16; first block | blocks << 16; item base in its group | bulge << 30; first slot
-
-// ---- the walk of one block (device form of walk_block, phot_lane.cuh: same arithmetic, scheduled by hand) ----------
-// Band constants of an item, addresses as 32-bit shared addresses.
+// ---- the walk of one band table (device form of walk_block, phot_lane.cuh: same arithmetic, scheduled by hand) -----
+// Band constants of a table, addresses as 32-bit shared addresses.
 struct BandDev {
     uint32_t rec, hs, bkt, hdr; // shared addresses of the record array, the half-slope array, the bucket table, the header
     double bk_scale, bk_c0;
-    int nbkt_m1, m0, mlast, nsplit;
+    int nbkt_m1, m0, nsplit;
     bool two_probe;
 };
-// what an interval needs from the node at its blue end
-struct NodeSt { double u, Lout; int r; };
+// what an interval needs from the node at its blue end; nsr = record of the next split node at or after the node's cell
+struct NodeSt { double u, Lout; int r, nsr; };
 
 template <typename real> __device__ __forceinline__ real to_real(double v);
 template <> __device__ __forceinline__ float to_real<float>(double v) { return (float)v; }
 template <> __device__ __forceinline__ double to_real<double>(double v) { return v; }
 
-// E of the interval p -> node at t with expansions (u, Lin) in cell r whose constants are (k0, hr, hs); returns E in the
-// gauge of p's region and sets Eadj to the same quantity in the gauge of the node's region (differs when the interval
-// crosses a split)
-__device__ __forceinline__ double interval_dev(const BandDev &B, const NodeSt &p, int r, double u, double Lin, double k0, double hr,
-                                               double hs, double t, double idx, double opz, double &Eadj) {
-    double E;
-    if (r == p.r) E = opz * fma(hs * p.u, u, fma(p.u + u, hr, k0));
-    else {
-        double d = Lin - p.Lout;
-        if (p.r <= B.mlast && r > B.m0) { // may cross a split (rare)
-            double dsum = 0.0;
-            for (int s = 0; s < B.nsplit; ++s) {
-                const uint32_t hb = B.hdr;
-                int ms;
-                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(ms) : "r"(hb + (uint32_t)offsetof(BandHeader2, msplit) + 4u * s));
-                if (p.r <= ms && r > ms) {
-                    const double C = lds_f64(hb + (uint32_t)offsetof(BandHeader2, splitC) + 8u * s);
-                    const double D = lds_f64(hb + (uint32_t)offsetof(BandHeader2, splitD) + 8u * s);
-                    const double F = lds_f64(hb + (uint32_t)offsetof(BandHeader2, splitF) + 8u * s);
-                    d += fma(D, t - F, C);
-                    dsum += D;
-                }
-            }
-            E = d * idx;
-            Eadj = E - dsum * opz;
-            return E;
+// The interval p -> node at t (cell r, expansions u / Lin, cell constants k0, hr, hs) crosses at least one split: add the
+// gauge jumps to d, return D summed over the crossed splits, and find the next split at or after r.
+__device__ __noinline__ double cross_splits(const BandDev &B, int pr, int r, double t, double &d, int &nsr) {
+    double dsum = 0.0;
+    nsr = 0x7fffffff;
+    for (int s = B.nsplit - 1; s >= 0; --s) {
+        const uint32_t hb = B.hdr;
+        int ms;
+        asm("ld.shared.s32 %0, [%1];" : "=r"(ms) : "r"(hb + (uint32_t)offsetof(BandHeader2, msplit) + 4u * s));
+        if (ms >= r) nsr = ms;
+        if (pr <= ms && r > ms) {
+            const double C = lds_f64(hb + (uint32_t)offsetof(BandHeader2, splitC) + 8u * s);
+            const double D = lds_f64(hb + (uint32_t)offsetof(BandHeader2, splitD) + 8u * s);
+            const double F = lds_f64(hb + (uint32_t)offsetof(BandHeader2, splitF) + 8u * s);
+            d += fma(D, t - F, C);
+            dsum += D;
         }
-        E = d * idx;
     }
+    return dsum;
+}
+
+// E of the interval p -> node at t, in the gauge of p's region; Eadj = the same quantity in the gauge of the node's region
+__device__ __forceinline__ double interval_dev(const BandDev &B, const NodeSt &p, int r, double u, double Lin, double k0, double hr,
+                                               double hs, double t, double idx, double opz, double &Eadj, int &nsr) {
+    nsr = p.nsr;
+    if (r == p.r) {
+        const double E = opz * fma(hs * p.u, u, fma(p.u + u, hr, k0));
+        Eadj = E;
+        return E;
+    }
+    double d = Lin - p.Lout;
+    if (r > p.nsr) { // crosses a split (once or twice per band)
+        const double dsum = cross_splits(B, p.r, r, t, d, nsr);
+        const double E = d * idx;
+        Eadj = E - dsum * opz;
+        return E;
+    }
+    const double E = d * idx;
     Eadj = E;
     return E;
 }
 
+// Walks nodes js..je of the disk grid for one galaxy (lane) and one band table; accumulates the nodes of [a, b].
+// totd / totb receive the sums of the blocks of 64 nodes (each summed in `real`, the blocks added in double, in order:
+// the same numbers whichever way the window is cut).
 template <typename real>
 __device__ __forceinline__ void walk_dev(const BandDev &B, const GridNode *__restrict__ grid, double opz, bool bulge, int a, int b,
-                                         int js, int je, const real *__restrict__ sd, const real *__restrict__ sb, real &accd_out,
-                                         real &accb_out) {
-    NodeSt s0{0.0, 0.0, -1}, s1{0.0, 0.0, -1}, so{0.0, 0.0, -1};
+                                         int js, int je, const real *__restrict__ sd, const real *__restrict__ sb, double &totd,
+                                         double &totb) {
+    NodeSt s0{0.0, 0.0, -1, B.m0}, s1 = s0, so = s0;
     double Eprev_d = 0.0, Eprev_b = 0.0;
     real Sprev_d = real(0), Sprev_b = real(0), accd = real(0), accb = real(0);
+    double td = 0.0, tb = 0.0;
+    int kb = 0; // block of the optical node the next bulge interval settles
     const unsigned span = (unsigned)(b - a);
     // one arrival: P = state of node j - 1, C receives the state of node j
     auto step = [&](const NodeSt &P, NodeSt &C, int j) {
-        const double4 ga = *reinterpret_cast<const double4 *>(grid + j); // x, idxp, idxpo, {o, po}
-        const int go = __double2loint(ga.w), gpo = __double2hiint(ga.w);
+        const double2 gxy = __ldg(reinterpret_cast<const double2 *>(grid + j)), gzw = __ldg(reinterpret_cast<const double2 *>(grid + j) + 1);
+        struct { double x, y, z; } ga{gxy.x, gxy.y, gzw.x}; // x, idxp, idxpo
+        const int go = __double2loint(gzw.y), gpo = __double2hiint(gzw.y); // {o, po}
         const double t = opz * ga.x; // the reference's lam = rlam * (1 + z) (src/egg-gencat.cpp:2161), in double
         const bool in_range = (unsigned)(j - a) <= span;
         real Sd = __ldcg(sd + (size_t)j * kLanes);
@@ -210,9 +237,10 @@ __device__ __forceinline__ void walk_dev(const BandDev &B, const GridNode *__res
         C.u = u;
         C.Lout = fma(v, fma(v, q1b.y, q1b.x), q1a.y);
         C.r = r;
-        // disk: close [j - 1, j], settle node j - 1
+        // disk: close [j - 1, j], settle node j - 1 (the block sums are flushed when node j - 1 starts a new block)
+        if (((j - 1) & (kLaneBlock - 1)) == 0) { td += (double)accd; accd = real(0); }
         double Eadj_d;
-        const double E_d = interval_dev(B, P, r, u, Lin, q0b.x, q0b.y, hs, t, ga.y, opz, Eadj_d);
+        const double E_d = interval_dev(B, P, r, u, Lin, q0b.x, q0b.y, hs, t, ga.y, opz, Eadj_d, C.nsr);
         accd = fma(to_real<real>(E_d - Eprev_d), Sprev_d, accd);
         Eprev_d = Eadj_d;
         Sprev_d = Sd;
@@ -222,7 +250,9 @@ __device__ __forceinline__ void walk_dev(const BandDev &B, const GridNode *__res
             Sb = in_range ? Sb : real(0);
             double E_b, Eadj_b;
             if (gpo == j - 1 && j > js) { E_b = E_d; Eadj_b = Eadj_d; } // the interval is a disk interval too
-            else E_b = interval_dev(B, so, r, u, Lin, q0b.x, q0b.y, hs, t, ga.z, opz, Eadj_b);
+            else { int dummy; E_b = interval_dev(B, so, r, u, Lin, q0b.x, q0b.y, hs, t, ga.z, opz, Eadj_b, dummy); }
+            const int kprev = gpo >> 6; // block of the optical node this interval settles (-1 >> 6 = -1: none yet)
+            if (kprev != kb) { tb += (double)accb; accb = real(0); kb = kprev; }
             accb = fma(to_real<real>(E_b - Eprev_b), Sprev_b, accb);
             Eprev_b = Eadj_b;
             Sprev_b = Sb;
@@ -235,453 +265,335 @@ __device__ __forceinline__ void walk_dev(const BandDev &B, const GridNode *__res
         step(s0, s1, j);
         step(s1, s0, j + 1);
     }
-    accd_out = accd;
-    accb_out = accb;
+    totd = td + (double)accd;
+    totb = tb + (double)accb;
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------
+// Per-warp scratch in global memory: SED rows of the disk grid [nD + 2][32], of the bulge grid [nB + 2][32] (reals), then
+// the sums of every band table [ntab][2][32] (doubles).
 template <typename real, int NT>
-__global__ void __launch_bounds__(NT, kLaneCtasPerSm) lane_flux_kernel(const __grid_constant__ LaneParams q) {
+__global__ void __launch_bounds__(NT, 1) lane_flux_kernel(const __grid_constant__ LaneParams q) {
     const FluxParams &p = q.fp;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ LaneScal sc;
     __shared__ __align__(8) uint64_t bar_tab;
-    __shared__ int item_ctr[kMaxGroups], group_items[kMaxGroups];
-    __shared__ int a2_ctr;
-    __shared__ int jn[4];        // disk nodes [jn0, jn1] and optical nodes [jn2, jn3] that some band of the batch reads
-    __shared__ double opzmm[2];  // smallest and largest (1+z) of the batch
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT / 32;
     const int nbt = (int)p.nband_total, ntab = (int)q.ntab, nrf = p.do_rf ? (int)p.nrf : 0;
     const int nD = p.nD, nB = p.nB, nline = p.nline;
-    const LaneSmem L = lane_smem_layout(p.max_blob, ntab, nbt, p.nrf, nline > 0 ? nline : 0);
-    const uint8_t *blob = smem + L.tab;
-    double *rfres = reinterpret_cast<double *>(smem + L.rfres);     // [rf][comp][lane]
-    uint32_t *lwin = reinterpret_cast<uint32_t *>(smem + L.lwin);   // [comp][line][lane]
-    uint32_t *lrange = reinterpret_cast<uint32_t *>(smem + L.lrange); // [comp][line]
-    BandWin *bwin = reinterpret_cast<BandWin *>(smem + L.bwin);      // [table in group order]
-    double2 *cov = reinterpret_cast<double2 *>(smem + L.cov);        // [col] full span of the filter (coverage test)
+    const uint8_t *blob = smem;
     const bool cs17 = p.ir_kind == EGGPHOT_IR_CS17;
     const bool has_bulge = p.has_bulge != 0;
-    const int ncomp = has_bulge ? 2 : 1;
-    real *SD = reinterpret_cast<real *>(p.scratch) + (size_t)blockIdx.x * q.scratch_stride;
+    uint8_t *wbase = reinterpret_cast<uint8_t *>(p.scratch) + ((size_t)blockIdx.x * NW + warp) * q.scratch_stride;
+    real *SD = reinterpret_cast<real *>(wbase);
     real *SB = SD + (size_t)(nD + 2) * kLanes;
-    real *part = SB + (size_t)(nB + 2) * kLanes; // [slot][comp][lane] block sums
+    double *RES = reinterpret_cast<double *>(wbase + q.res_offset);
     const real *rO = reinterpret_cast<const real *>(p.rowsDopt), *rI = reinterpret_cast<const real *>(p.rowsDir);
     const real *rP = reinterpret_cast<const real *>(p.rowsDpah), *rB = reinterpret_cast<const real *>(p.rowsB);
     const GridNode *grid = q.grid;
-    const uint32_t tab_sa = smem_u32(smem + L.tab);
+    const uint32_t tab_sa = smem_u32(smem);
 
     if (tid == 0) {
         mbar_init(&bar_tab, 1);
         fence_mbar_init();
-    }
-    // full spans of the filters by output column: the same for every batch
-    for (int fb = tid; fb < ntab; fb += NT) {
-        int grp = 0;
-        while (grp + 1 < (int)p.ngroups && fb >= (int)p.groups[grp + 1].base) ++grp;
-        const BandHeader2 *gh = reinterpret_cast<const BandHeader2 *>(p.groups[grp].blob) + (fb - (int)p.groups[grp].base);
-        cov[__ldg(&gh->out_col)] = make_double2(__ldg(&gh->full_first), __ldg(&gh->full_last));
     }
     __syncthreads();
     uint32_t tab_phase = 0;
     int loaded = -1;
     const uint64_t keep = evict_last_policy();
 
+    // the CTA's share of the batches (contiguous: neighbouring redshifts), NW at a time, one per warp
     const uint64_t nbatch = (p.ngal + kLanes - 1) / kLanes;
-    for (uint64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+    const uint64_t bfirst = nbatch * blockIdx.x / gridDim.x, bend = nbatch * (blockIdx.x + 1) / gridDim.x;
+    const int nround = (int)((bend - bfirst + NW - 1) / NW);
+    const int ngl = max((int)p.ngroups, 1);
+    for (int round = 0; round < nround; ++round) {
+        const uint64_t batch = bfirst + (uint64_t)round * NW + warp;
+        const bool active = batch < bend;
         const uint64_t g0 = batch * kLanes;
-        const int ng = (int)min((uint64_t)kLanes, p.ngal - g0);
-
-        // ---- phase A1: per-lane scalars, four warps (one piece each: the double-precision log / exp10 / divisions of
-        //      a batch run side by side); lanes beyond the end of the catalog repeat the batch's first galaxy
-        if (warp < 4) {
-            const uint64_t g = q.perm[g0 + (lane < ng ? lane : 0)];
-            if (warp == 0) {
-                const double z = __ldcs(p.z + g), d = __ldcs(p.d + g); // galaxy columns are read once: streaming loads
-                sc.opz[lane] = 1.0 + z;
-                sc.iopz[lane] = 1.0 / (1.0 + z);
-                sc.aflux[lane] = EGGPHOT_LSUN2UJY * (1.0 + z) / (d * d);
-                sc.gal[lane] = (uint32_t)g;
-                sc.valid[lane] = lane < ng;
-            } else if (warp == 1) {
-                // the reference passes the FLOAT difference m[i]-out.m2lcor[i] to e10 (src/egg-gencat.cpp:2106, 2114)
-                sc.a_bulge[lane] = has_bulge ? exp10((double)(p.m_bulge[g] - __ldcs(p.m2lcor + g))) : 0.0;
-            } else if (warp == 2) {
-                sc.a_disk[lane] = p.disk_mode != 2 ? exp10((double)(p.m_disk[g] - __ldcs(p.m2lcor + g))) : 0.0;
-            } else {
-                double c1 = 0.0, c2 = 0.0;
-                bool bad = false;
-                uint64_t ri = 0, rb = 0, rd = 0;
-                if (p.disk_mode != 1) {
-                    ri = p.ir_sed[g];
-                    if (ri >= p.nir_sed) { bad = true; ri = 0; }
-                    if (cs17) {
-                        const double fp = p.fpah[g], md = p.mdust[g];
-                        c1 = (1.0 - fp) * md;
-                        c2 = fp * md;
-                    } else {
-                        c1 = p.lir[g];
-                    }
-                }
-                if (has_bulge) {
-                    rb = p.opt_sed_bulge[g];
-                    if (rb >= p.nopt_sed || !p.opt_use[rb]) { bad = true; rb = 0; }
-                }
-                if (p.disk_mode != 2) {
-                    rd = p.opt_sed_disk[g];
-                    if (rd >= p.nopt_sed || !p.opt_use[rd]) { bad = true; rd = 0; }
-                }
-                sc.c1[lane] = c1; sc.c2[lane] = c2;
-                sc.row_b[lane] = (uint32_t)rb; sc.row_d[lane] = (uint32_t)rd; sc.row_i[lane] = (uint32_t)ri;
-                for (int k = 0; k < 3; ++k) sc.igm[k][lane] = p.apply_igm ? __ldcs(p.igm_abs + 3 * g + k) : 1.0f;
-                sc.vdisp[lane] = nline ? (double)p.vdisp[g] : 0.0;
-                if (bad) atomicExch(p.error_flag, EGGPHOT_ERR_INDEX);
-            }
-        } else if (warp == 4) {
-            if (lane < kMaxGroups) { item_ctr[lane] = 0; group_items[lane] = 0; }
-            if (lane == 16) a2_ctr = 0;
-            if (lane == 17) { // the rest-frame bands read fixed node ranges
-                int lo = nD, hi = -1, blo = nB, bhi = -1;
-                for (int r = 0; r < nrf; ++r) {
-                    if (p.rfD[r].n > 0) { lo = min(lo, (int)p.rfD[r].j0); hi = max(hi, (int)(p.rfD[r].j0 + p.rfD[r].n - 1)); }
-                    if (has_bulge && p.rfB[r].n > 0) { blo = min(blo, (int)p.rfB[r].j0); bhi = max(bhi, (int)(p.rfB[r].j0 + p.rfB[r].n - 1)); }
-                }
-                jn[0] = lo; jn[1] = hi; jn[2] = blo; jn[3] = bhi;
-            }
-        }
-        __syncthreads();
-        if (warp == 0) { // (1+z) range of the batch
-            double lo = sc.opz[lane], hi = lo;
+        const int ng = active ? (int)min((uint64_t)kLanes, p.ngal - g0) : 0;
+        // lanes beyond the end of the catalog repeat the batch's first galaxy (and write nothing)
+        const uint64_t g = active ? q.perm[g0 + (lane < ng ? lane : 0)] : 0;
+        double opz = 1.0, omin = 1.0, omax = 1.0;
+        if (active) {
+            opz = 1.0 + (double)__ldcs(p.z + g);
+            omin = opz; omax = opz;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                lo = fmin(lo, __shfl_xor_sync(kFull, lo, o));
-                hi = fmax(hi, __shfl_xor_sync(kFull, hi, o));
+                omin = fmin(omin, __shfl_xor_sync(kFull, omin, o));
+                omax = fmax(omax, __shfl_xor_sync(kFull, omax, o));
             }
-            if (lane == 0) { opzmm[0] = lo; opzmm[1] = hi; }
         }
-        // emission-line windows ([vif] bounds, src/egg-gencat.cpp:2081-2084): one thread per (component, line, lane)
-        for (int idx = tid; idx < 2 * nline * kLanes; idx += NT) {
-            const int ln = idx & 31, cl = idx >> 5, c = cl >= nline, l = cl - c * nline; // c: 0 bulge, 1 disk
-            const float *ll = c ? p.line_lum_disk : p.line_lum_bulge;
-            int b0 = 1, b1 = 0; // empty
-            if ((c || has_bulge) && ll != nullptr && sc.valid[ln] && ll[(uint64_t)sc.gal[ln] * nline + p.line_col[l]] != 0.0f) {
-                const double *x = c ? p.xD : p.xB;
-                const int n = c ? nD : nB;
-                const uint16_t *lut = c ? p.lutD : p.lutB;
-                const int nlut = c ? p.lutD_n : p.lutB_n, e0 = c ? p.lutD_e0 : p.lutB_e0;
-                const double l0 = (double)p.line_lambda[l], lw = l0 * (sc.vdisp[ln] / 2.998e5);
-                const int lo = lut_last_le(x, n, lut, nlut, lut_pos(l0 - 10 * lw, e0), l0 - 10 * lw);
-                const int hi = lut_last_le(x, n, lut, nlut, lut_pos(l0 + 10 * lw, e0), l0 + 10 * lw) + 1; // first > b, n if none
-                if (!(hi == 0 || lo == n - 1)) {
-                    b0 = lo < 0 ? 0 : lo;
-                    b1 = hi >= n ? n - 1 : hi;
-                }
-            }
-            lwin[idx] = (uint32_t)b0 | ((uint32_t)b1 << 16);
-        }
-        __syncthreads();
-
-        // ---- node window of every band table for the whole batch: one thread per table.  The window runs from the
-        //      last node at or left of the table's blue end for the largest (1+z) to the first node at or right of its
-        //      red end for the smallest, with a relative margin: nodes a galaxy does not weigh get the weight 0 exactly.
-        for (int fb = tid; fb < ntab; fb += NT) {
+        // node window of band table fb for the batch: from the last node at or left of the table's blue end for the largest
+        // (1+z) to the first node at or right of its red end for the smallest, with a relative margin (nodes a galaxy does
+        // not weigh get the weight 0 exactly); 0 = nothing to do.  jlo | jhi << 16 | bulge << 31 (jhi < 32768 * 2 ...)
+        auto table_window = [&](int fb) -> uint32_t {
             int grp = 0;
             while (grp + 1 < (int)p.ngroups && fb >= (int)p.groups[grp + 1].base) ++grp;
             const BandHeader2 *gh = reinterpret_cast<const BandHeader2 *>(p.groups[grp].blob) + (fb - (int)p.groups[grp].base);
-            const double omin = opzmm[0], omax = opzmm[1];
             const double ff = __ldg(&gh->full_first), fl = __ldg(&gh->full_last);
-            uint32_t w0 = 0, w1 = 0, w2 = 0;
             // [vif] sed2flux is NaN (-> flux 0, src/egg-gencat.cpp:2198) unless the SED covers the filter: a band no
             // galaxy of the batch covers is skipped
             const bool any_cov = nD >= 2 && __ldg(p.xD) * omin <= ff && __ldg(p.xD + nD - 1) * omax >= fl;
-            if (any_cov && __ldg(&gh->n) > 0) {
-                int jlo = max(bis_last_le(p.xD, nD, __ldg(&gh->f_first) / omax * (1.0 - 1e-9)), 0);
-                int jhi = min(bis_first_ge(p.xD, nD, __ldg(&gh->f_last) / omin * (1.0 + 1e-9)), nD - 1);
-                const bool bulge_any = has_bulge && nB >= 2 && __ldg(p.xB) * omin <= ff && __ldg(p.xB + nB - 1) * omax >= fl;
-                if (bulge_any) widen_window_for_bulge(grid, q.next_opt, nD, jlo, jhi);
-                const int kfirst = jlo / kLaneBlock, nblk = jhi / kLaneBlock - kfirst + 1;
-                w0 = (uint32_t)jlo | ((uint32_t)jhi << 16);
-                w1 = (uint32_t)kfirst | ((uint32_t)nblk << 16);
-                w2 = bulge_any ? (1u << 30) : 0u;
-                atomicMin(&jn[0], jlo);
-                atomicMax(&jn[1], jhi);
-                if (bulge_any) { // optical nodes inside the window
-                    const int jo0 = grid[jlo].o >= 0 ? jlo : q.next_opt[jlo], jo1 = grid[jhi].o >= 0 ? jhi : grid[jhi].po;
-                    if (jo0 <= jo1 && jo1 >= 0) { atomicMin(&jn[2], grid_o(grid[jo0])); atomicMax(&jn[3], grid_o(grid[jo1])); }
-                }
-            }
-            bwin[fb].w0 = w0; bwin[fb].w1 = w1; bwin[fb].w2 = w2; bwin[fb].w3 = 0;
-        }
-        // node range of every line over the batch (union of the lanes' windows): one warp per (component, line)
-        for (int cl = warp; cl < 2 * nline; cl += NT / 32) {
-            const uint32_t w = lwin[cl * kLanes + lane];
-            int b0 = (int)(w & 0xffffu), b1 = (int)(w >> 16);
-            if (b0 > b1) { b0 = 0xffff; b1 = 0; }
-            b0 = __reduce_min_sync(kFull, b0);
-            b1 = __reduce_max_sync(kFull, b1);
-            if (lane == 0) lrange[cl] = (uint32_t)b0 | ((uint32_t)b1 << 16);
-        }
-        __syncthreads();
-        // item numbering per group (one thread): item base inside the group, first slot of the block sums
-        if (tid == 0) {
-            int slot = 0;
-            for (int g = 0; g < (int)p.ngroups; ++g) {
-                const int base = (int)p.groups[g].base, nb = (int)p.groups[g].nb;
-                int run = 0;
-                for (int b = 0; b < nb; ++b) {
-                    const int nk = (int)(bwin[base + b].w1 >> 16);
-                    bwin[base + b].w2 |= (uint32_t)run;
-                    bwin[base + b].w3 = (uint32_t)slot;
-                    run += nk;
-                    slot += nk;
-                }
-                group_items[g] = run;
-            }
-            if (slot > (int)q.max_slots) atomicExch(p.error_flag, EGGPHOT_ERR_CUDA);
-        }
-        __syncthreads();
-        const int jn0 = jn[0], jn1 = jn[1], on0 = jn[2], on1 = jn[3];
+            if (!any_cov || __ldg(&gh->n) == 0) return 0u;
+            int jlo = max(bis_last_le(p.xD, nD, __ldg(&gh->f_first) / omax * (1.0 - 1e-9)), 0);
+            int jhi = min(bis_first_ge(p.xD, nD, __ldg(&gh->f_last) / omin * (1.0 + 1e-9)), nD - 1);
+            const bool bulge_any = has_bulge && nB >= 2 && __ldg(p.xB) * omin <= ff && __ldg(p.xB + nB - 1) * omax >= fl;
+            if (bulge_any) widen_window_for_bulge(grid, q.next_opt, nD, jlo, jhi);
+            return (uint32_t)jlo | ((uint32_t)jhi << 15) | (bulge_any ? 0x80000000u : 0u) | 0x40000000u;
+        };
+        uint32_t win_lo = 0, win_hi = 0; // lane t: windows of tables t and t + 32
 
-        // ---- phase A2: rest-frame SEDs with their emission lines, lane = galaxy: 16 bytes of each template row per load,
-        //      [node][lane] stores.  Only the nodes some band of the batch reads are built.  The bulge SED carries no
-        //      mass scale (applied at the end).
-        {
-            constexpr int NPL = 16 / (int)sizeof(real), CH = 16; // nodes per load, nodes per task
-            const int d0 = jn1 >= jn0 ? (jn0 & ~3) : 0, dn = jn1 >= jn0 ? (jn1 - d0 + CH) / CH : 0;
-            const int b0 = (has_bulge && on1 >= on0) ? (on0 & ~3) : 0, bn = (has_bulge && on1 >= on0) ? (on1 - b0 + CH) / CH : 0;
-            const real a_d = (real)sc.a_disk[lane], c1 = (real)sc.c1[lane], c2 = (real)sc.c2[lane];
-            const real g0f = sc.igm[0][lane], g1f = sc.igm[1][lane], g2f = sc.igm[2][lane];
-            const real *rowO = rO + (size_t)sc.row_d[lane] * p.strideD, *rowI = rI + (size_t)sc.row_i[lane] * p.strideD;
-            const real *rowP = rP + (size_t)sc.row_i[lane] * p.strideD, *rowB = rB + (size_t)sc.row_b[lane] * p.strideB;
-            const double vd = sc.vdisp[lane] / 2.998e5;
-            // the bulge SED carries no mass scale, so its line term is divided by it
-            const double inv_b = sc.a_bulge[lane] > 0 ? 1.0 / sc.a_bulge[lane] : 0.0;
-            // emission lines (add_emission_line, src/egg-gencat.cpp:2078-2095) at nodes j0 .. j0 + NPL - 1 of component c:
-            // the bin integrals of all lines whose window holds the node, summed in wavelength order
-            auto add_lines = [&](int c, int j0, real *v) {
-                const double *x = c ? p.xD : p.xB;
-                const int n = c ? nD : nB;
-                const uint32_t *wl = lwin + (size_t)c * nline * kLanes + lane;
-                const float *ll = (c ? p.line_lum_disk : p.line_lum_bulge);
-                for (int l = 0; l < nline; ++l) {
-                    const uint32_t lr = lrange[c * nline + l];
-                    if ((int)(lr & 0xffffu) > j0 + NPL - 1 || (int)(lr >> 16) < j0) continue; // no galaxy of the batch (uniform)
-                    const uint32_t w = wl[l * kLanes];
-                    const int w0 = (int)(w & 0xffffu), w1 = (int)(w >> 16);
-                    if (w0 > j0 + NPL - 1 || w1 < j0) continue;
-                    const double l0 = (double)p.line_lambda[l], lw = l0 * vd;
-                    const double amp = (double)ll[(uint64_t)sc.gal[lane] * nline + p.line_col[l]] * l0;
-#pragma unroll
-                    for (int k = 0; k < NPL; ++k) {
-                        const int j = j0 + k;
-                        if (j < w0 || j > w1 || j >= n) continue;
-                        const double xj = __ldg(x + j);
-                        const double xm = j > 0 ? __ldg(x + j - 1) : 0.0, xp = j < n - 1 ? __ldg(x + j + 1) : 0.0;
-                        const double llow = j != 0 ? 0.5 * (xm + xj) : xj - 0.5 * (xp - xj);     // :2090
-                        const double lup = j != n - 1 ? 0.5 * (xj + xp) : xj + 0.5 * (xj - xm); // :2091
-                        v[k] += (real)(xj * line_bin_t<real>(llow, lup, l0, lw, amp, p.line_average) * (c ? 1.0 : inv_b));
-                    }
-                }
-            };
-            for (;;) {
-                int task = 0;
-                if (lane == 0) task = atomicAdd(&a2_ctr, 1);
-                task = __shfl_sync(kFull, task, 0);
-                if (task >= dn + bn) break;
-                if (task < dn) {
-                    const int jt = d0 + task * CH;
-#pragma unroll
-                    for (int qd = 0; qd < CH / NPL; ++qd) {
-                        const int j0 = jt + qd * NPL;
-                        if (j0 >= p.strideD) break;
-                        Vec16<real> o, i, pq;
-#pragma unroll
-                        for (int k = 0; k < NPL; ++k) o.v[k] = i.v[k] = pq.v[k] = real(0);
-                        if (p.disk_mode != 2) o = ldg16(rowO + j0);
-                        if (p.disk_mode != 1) i = ldg16(rowI + j0);
-                        if (p.disk_mode != 1 && cs17) pq = ldg16(rowP + j0);
-                        real v[NPL];
-#pragma unroll
-                        for (int k = 0; k < NPL; ++k) {
-                            v[k] = a_d * o.v[k] + c1 * i.v[k]; // absent terms are zero
-                            if (p.disk_mode != 1 && cs17) v[k] += c2 * pq.v[k];
-                            if (p.apply_igm && j0 + k < p.igmD[3])
-                                v[k] *= igm_factor<real>(j0 + k, p.igmD[0], p.igmD[1], p.igmD[2], p.igmD[3], g0f, g1f, g2f);
-                        }
-                        if (nline > 0 && p.line_lum_disk != nullptr) add_lines(1, j0, v);
-#pragma unroll
-                        for (int k = 0; k < NPL; ++k)
-                            if (j0 + k <= nD + 1) st_keep(SD + (size_t)(j0 + k) * kLanes + lane, j0 + k < nD ? v[k] : real(0), keep);
-                    }
-                } else {
-                    const int jt = b0 + (task - dn) * CH;
-#pragma unroll
-                    for (int qd = 0; qd < CH / NPL; ++qd) {
-                        const int j0 = jt + qd * NPL;
-                        if (j0 >= p.strideB) break;
-                        const Vec16<real> o = ldg16(rowB + j0);
-                        real v[NPL];
-#pragma unroll
-                        for (int k = 0; k < NPL; ++k) {
-                            v[k] = o.v[k];
-                            if (p.apply_igm && j0 + k < p.igmB[3])
-                                v[k] *= igm_factor<real>(j0 + k, p.igmB[0], p.igmB[1], p.igmB[2], p.igmB[3], g0f, g1f, g2f);
-                        }
-                        if (nline > 0 && p.line_lum_bulge != nullptr) add_lines(0, j0, v);
-#pragma unroll
-                        for (int k = 0; k < NPL; ++k)
-                            if (j0 + k <= nB + 1) st_keep(SB + (size_t)(j0 + k) * kLanes + lane, j0 + k < nB ? v[k] : real(0), keep);
-                    }
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---- phase B: band groups
-        // consecutive batches walk the groups in opposite orders: the tables of the group a batch ends with are
-        // still in shared memory when the next batch starts with it (one table load less per batch)
-        const int ngl = max((int)p.ngroups, nrf > 0 ? 1 : 0);
-        const bool rev = ((batch - blockIdx.x) / gridDim.x) & 1;
-        const double opz = sc.opz[lane];
         for (int gstep = 0; gstep < ngl; ++gstep) {
-            const int grp = rev ? ngl - 1 - gstep : gstep;
+            // consecutive rounds walk the groups in opposite orders: the tables of the group a round ends with are still
+            // in shared memory when the next round starts with it (one table load less per round)
+            const int grp = (round & 1) ? ngl - 1 - gstep : gstep;
             const int nb = grp < (int)p.ngroups ? (int)p.groups[grp].nb : 0;
-            const int nband_items = grp < (int)p.ngroups ? group_items[grp] : 0;
-            if (nb > 0 && nband_items > 0 && loaded != grp) {
+            if (nb > 0 && loaded != grp) {
                 if (tid == 0) {
                     fence_proxy_async(); // earlier generic-proxy reads of the table region precede the async writes
                     const uint32_t bytes = p.groups[grp].bytes;
                     mbar_expect_tx(&bar_tab, bytes);
                     for (uint32_t o = 0; o < bytes; o += 32768u)
-                        bulk_g2s(smem + L.tab + o, p.groups[grp].blob + o, min(32768u, bytes - o), &bar_tab);
+                        bulk_g2s(smem + o, p.groups[grp].blob + o, min(32768u, bytes - o), &bar_tab);
                 }
                 mbar_wait(&bar_tab, tab_phase);
                 tab_phase ^= 1;
                 loaded = grp;
             }
-            const int gbase = grp < (int)p.ngroups ? (int)p.groups[grp].base : 0;
-            const int nitems = nband_items + (grp == 0 ? nrf * ncomp : 0);
-            for (;;) {
-                int idx = 0;
-                if (lane == 0) idx = atomicAdd(&item_ctr[grp], 1);
-                idx = __shfl_sync(kFull, idx, 0);
-                if (idx >= nitems) break;
-                if (idx < nband_items) {
-                    // (table, block): the table whose item range holds idx (tables are stored longest first)
-                    int bi = 0;
-                    for (int b = lane; b < nb; b += 32) {
-                        const BandWin &bw = bwin[gbase + b];
-                        const int ib = (int)(bw.w2 & 0x3fffffffu), nk = (int)(bw.w1 >> 16);
-                        if (idx >= ib && idx < ib + nk) bi = b + 1;
+            if (active) {
+                if (gstep == 0) {
+                    // ---- phase A: windows of all tables, rest-frame SEDs of the batch, emission lines, rest-frame magnitudes
+                    win_lo = lane < ntab ? table_window(lane) : 0u;
+                    win_hi = lane + 32 < ntab ? table_window(lane + 32) : 0u;
+                    int jn0 = nD, jn1 = -1, on0 = nB, on1 = -1; // disk / optical nodes some band of the batch reads
+                    for (int r = 0; r < nrf; ++r) { // the rest-frame bands read fixed node ranges
+                        if (p.rfD[r].n > 0) { jn0 = min(jn0, (int)p.rfD[r].j0); jn1 = max(jn1, (int)(p.rfD[r].j0 + p.rfD[r].n - 1)); }
+                        if (has_bulge && p.rfB[r].n > 0) { on0 = min(on0, (int)p.rfB[r].j0); on1 = max(on1, (int)(p.rfB[r].j0 + p.rfB[r].n - 1)); }
                     }
-                    bi = __reduce_max_sync(kFull, bi) - 1;
-                    const BandWin bw = bwin[gbase + bi];
-                    const int kk = idx - (int)(bw.w2 & 0x3fffffffu), k = (int)(bw.w1 & 0xffffu) + kk;
-                    const int jlo = (int)(bw.w0 & 0xffffu), jhi = (int)(bw.w0 >> 16);
-                    const bool bulge = (bw.w2 >> 30) & 1u;
-                    const uint32_t hsa = tab_sa + (uint32_t)bi * (uint32_t)sizeof(BandHeader2);
-                    const BandHeader2 &h = reinterpret_cast<const BandHeader2 *>(blob)[bi];
-                    BandDev B;
-                    B.hdr = hsa;
-                    B.rec = tab_sa + h.rec_off; B.hs = tab_sa + h.hs_off; B.bkt = tab_sa + h.bkt_off;
-                    B.bk_scale = h.bk_scale; B.bk_c0 = h.bk_c0;
-                    B.nbkt_m1 = (int)h.nbkt - 1;
-                    B.nsplit = (int)h.nsplit;
-                    B.m0 = (int)h.msplit[0];
-                    B.mlast = (int)h.msplit[B.nsplit > 0 ? B.nsplit - 1 : 0];
-                    B.two_probe = h.two_probe != 0;
-                    const int a = max(jlo, k * kLaneBlock), b = min(jhi, k * kLaneBlock + kLaneBlock - 1);
-                    int js, je;
-                    block_arrivals(grid, q.next_opt, bulge, a, b, js, je);
-                    real accd, accb;
-                    walk_dev<real>(B, grid, opz, bulge, a, b, js, je, SD + lane, SB + lane, accd, accb);
-                    real *ps = part + (size_t)(bw.w3 + (uint32_t)kk) * 2 * kLanes + lane;
-                    __stcg(ps + kLanes, accd);
-                    __stcg(ps, bulge ? accb : real(0));
-                } else {
-                    // rest-frame magnitude: dot product with the z = 0 weights (src/egg-gencat.cpp:2150-2158)
-                    const int t2 = idx - nband_items;
-                    const int comp = has_bulge ? (t2 & 1) : 1, rb = has_bulge ? (t2 >> 1) : t2;
-                    const RfDesc dsc = comp ? p.rfD[rb] : p.rfB[rb];
-                    const real *S = (comp ? SD : SB) + lane;
-                    const real *W = reinterpret_cast<const real *>(p.rfW) + dsc.off;
-                    CompSum<real> acc;
-                    acc.clear();
-                    for (int k = 0; k < dsc.n; ++k) acc.add(__ldcg(S + (size_t)(dsc.j0 + k) * kLanes) * __ldg(W + k));
-                    rfres[(rb * 2 + comp) * kLanes + lane] =
-                        dsc.covered ? ((double)acc.s + (double)acc.c) * (comp ? 1.0 : sc.a_bulge[lane]) : __longlong_as_double(0x7ff8000000000000LL);
-                }
-            }
-            __syncthreads(); // every item of the group is done; the table region may be overwritten
-        }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t w = h ? win_hi : win_lo;
+                        if (w) {
+                            const int jlo = (int)(w & 0x7fffu), jhi = (int)((w >> 15) & 0x7fffu);
+                            jn0 = min(jn0, jlo); jn1 = max(jn1, jhi);
+                            if (w & 0x80000000u) { // optical nodes inside the window
+                                const int jo0 = grid[jlo].o >= 0 ? jlo : q.next_opt[jlo], jo1 = grid[jhi].o >= 0 ? jhi : grid[jhi].po;
+                                if (jo0 <= jo1 && jo1 >= 0) { on0 = min(on0, grid_o(grid[jo0])); on1 = max(on1, grid_o(grid[jo1])); }
+                            }
+                        }
+                    }
+                    jn0 = __reduce_min_sync(kFull, jn0); jn1 = __reduce_max_sync(kFull, jn1);
+                    on0 = __reduce_min_sync(kFull, on0); on1 = __reduce_max_sync(kFull, on1);
 
-        // ---- phase C: block sums added per output column in a fixed order (tables in group order, blocks in node
-        //      order), data conditions, totals (src/egg-gencat.cpp:2238-2239), catalog columns (rows of one galaxy are
-        //      contiguous: consecutive threads write consecutive bands)
-        for (int i = tid; i < ng * nbt; i += NT) {
-            const int ln = i / nbt, col = i - ln * nbt;
-            double sd = 0.0, sb = 0.0;
-            for (int fb = 0; fb < ntab; ++fb) {
-                if ((int)q.tab_col[fb] != col) continue;
-                const BandWin bw = bwin[fb];
-                const int nk = (int)(bw.w1 >> 16);
-                const real *ps = part + (size_t)bw.w3 * 2 * kLanes + ln;
-                for (int kk = 0; kk < nk; ++kk, ps += 2 * kLanes) {
-                    sd += (double)__ldcg(ps + kLanes);
-                    sb += (double)__ldcg(ps);
+                    // per-lane scalars (src/egg-gencat.cpp:708-712, 2039-2057)
+                    // the reference passes the FLOAT difference m[i]-out.m2lcor[i] to e10 (:2106, :2114)
+                    const float m2l = __ldcs(p.m2lcor + g);
+                    const double a_bulge = has_bulge ? exp10((double)(p.m_bulge[g] - m2l)) : 0.0;
+                    const real a_d = p.disk_mode != 2 ? (real)exp10((double)(p.m_disk[g] - m2l)) : real(0);
+                    real c1 = real(0), c2 = real(0);
+                    bool bad = false;
+                    uint64_t ri = 0, rb = 0, rd = 0;
+                    if (p.disk_mode != 1) {
+                        ri = p.ir_sed[g];
+                        if (ri >= p.nir_sed) { bad = true; ri = 0; }
+                        if (cs17) {
+                            const double fp = p.fpah[g], md = p.mdust[g];
+                            c1 = (real)((1.0 - fp) * md);
+                            c2 = (real)(fp * md);
+                        } else {
+                            c1 = (real)(double)p.lir[g];
+                        }
+                    }
+                    if (has_bulge) {
+                        rb = p.opt_sed_bulge[g];
+                        if (rb >= p.nopt_sed || !p.opt_use[rb]) { bad = true; rb = 0; }
+                    }
+                    if (p.disk_mode != 2) {
+                        rd = p.opt_sed_disk[g];
+                        if (rd >= p.nopt_sed || !p.opt_use[rd]) { bad = true; rd = 0; }
+                    }
+                    if (bad) atomicExch(p.error_flag, EGGPHOT_ERR_INDEX);
+                    real g0f = real(1), g1f = real(1), g2f = real(1);
+                    if (p.apply_igm) { g0f = __ldcs(p.igm_abs + 3 * g); g1f = __ldcs(p.igm_abs + 3 * g + 1); g2f = __ldcs(p.igm_abs + 3 * g + 2); }
+
+                    // rest-frame SEDs, lane = galaxy: 16 bytes of each template row per load, [node][lane] stores.  Only the
+                    // nodes some band of the batch reads are built.  The bulge SED carries no mass scale (applied at the end).
+                    constexpr int NPL = 16 / (int)sizeof(real);
+                    {
+                        const real *rowO = rO + (size_t)rd * p.strideD, *rowI = rI + (size_t)ri * p.strideD, *rowP = rP + (size_t)ri * p.strideD;
+                        const int jend = jn1 >= jn0 ? min(jn1 + 1, p.strideD) : 0;
+                        for (int j0 = jn1 >= jn0 ? (jn0 & ~3) : 0; j0 < jend; j0 += NPL) {
+                            Vec16<real> o, i, pq;
+#pragma unroll
+                            for (int k = 0; k < NPL; ++k) o.v[k] = i.v[k] = pq.v[k] = real(0);
+                            if (p.disk_mode != 2) o = ldg16(rowO + j0);
+                            if (p.disk_mode != 1) i = ldg16(rowI + j0);
+                            if (p.disk_mode != 1 && cs17) pq = ldg16(rowP + j0);
+#pragma unroll
+                            for (int k = 0; k < NPL; ++k) {
+                                real v = a_d * o.v[k] + c1 * i.v[k]; // absent terms are zero
+                                if (p.disk_mode != 1 && cs17) v += c2 * pq.v[k];
+                                if (p.apply_igm && j0 + k < p.igmD[3])
+                                    v *= igm_factor<real>(j0 + k, p.igmD[0], p.igmD[1], p.igmD[2], p.igmD[3], g0f, g1f, g2f);
+                                if (j0 + k < nD) st_keep(SD + (size_t)(j0 + k) * kLanes + lane, v, keep);
+                            }
+                        }
+                    }
+                    if (has_bulge) {
+                        const real *rowB = rB + (size_t)rb * p.strideB;
+                        const int jend = on1 >= on0 ? min(on1 + 1, p.strideB) : 0;
+                        for (int j0 = on1 >= on0 ? (on0 & ~3) : 0; j0 < jend; j0 += NPL) {
+                            const Vec16<real> o = ldg16(rowB + j0);
+#pragma unroll
+                            for (int k = 0; k < NPL; ++k) {
+                                real v = o.v[k];
+                                if (p.apply_igm && j0 + k < p.igmB[3])
+                                    v *= igm_factor<real>(j0 + k, p.igmB[0], p.igmB[1], p.igmB[2], p.igmB[3], g0f, g1f, g2f);
+                                if (j0 + k < nB) st_keep(SB + (size_t)(j0 + k) * kLanes + lane, v, keep);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    // emission lines (add_emission_line, src/egg-gencat.cpp:2078-2095): every lane deposits the lines of its
+                    // own galaxy, in wavelength order, at the nodes some band reads
+                    if (nline > 0) {
+                        const double vd = (double)p.vdisp[g] / 2.998e5;
+                        for (int c = has_bulge && p.line_lum_bulge != nullptr ? 0 : 1; c < 2; ++c) { // 0 bulge, 1 disk
+                            const float *ll = c ? p.line_lum_disk : p.line_lum_bulge;
+                            if (ll == nullptr) continue;
+                            const double *x = c ? p.xD : p.xB;
+                            const int n = c ? nD : nB;
+                            const uint16_t *lut = c ? p.lutD : p.lutB;
+                            const int nlut = c ? p.lutD_n : p.lutB_n, e0 = c ? p.lutD_e0 : p.lutB_e0;
+                            const int lo = c ? jn0 : on0, hi = c ? jn1 : on1;
+                            real *S = (c ? SD : SB) + lane;
+                            // the bulge SED carries no mass scale, so its line term is divided by it
+                            const double inv = c ? 1.0 : (a_bulge > 0 ? 1.0 / a_bulge : 0.0);
+                            for (int l = 0; l < nline; ++l) {
+                                const float lum = ll[g * nline + p.line_col[l]];
+                                if (lum == 0.0f) continue;
+                                const double l0 = (double)p.line_lambda[l], lw = l0 * vd;
+                                // [vif] bounds (:2081-2084)
+                                const int blo = lut_last_le(x, n, lut, nlut, lut_pos(l0 - 10 * lw, e0), l0 - 10 * lw);
+                                const int bhi = lut_last_le(x, n, lut, nlut, lut_pos(l0 + 10 * lw, e0), l0 + 10 * lw) + 1; // first > b, n if none
+                                if (bhi == 0 || blo == n - 1) continue;
+                                const int j0 = max(blo < 0 ? 0 : blo, lo), j1 = min(bhi >= n ? n - 1 : bhi, hi);
+                                const double amp = (double)lum * l0;
+                                for (int j = j0; j <= j1; ++j) {
+                                    const double xj = __ldg(x + j);
+                                    const double xm = j > 0 ? __ldg(x + j - 1) : 0.0, xp = j < n - 1 ? __ldg(x + j + 1) : 0.0;
+                                    const double llow = j != 0 ? 0.5 * (xm + xj) : xj - 0.5 * (xp - xj);     // :2090
+                                    const double lup = j != n - 1 ? 0.5 * (xj + xp) : xj + 0.5 * (xj - xm); // :2091
+                                    real *sp = S + (size_t)j * kLanes;
+                                    st_keep(sp, __ldcg(sp) + (real)(xj * line_bin_t<real>(llow, lup, l0, lw, amp, p.line_average) * inv), keep);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    // rest-frame magnitudes: dot products with the z = 0 weights (src/egg-gencat.cpp:2150-2158), [vif]
+                    // lsun2uJy(0, 1e-5, ...) then uJy2mag; non-finite -> +99 (:2152-2156)
+                    for (int r = 0; r < nrf; ++r) {
+                        const double arf = EGGPHOT_LSUN2UJY / (1e-5 * 1e-5);
+                        double mg[2] = {0.0, 0.0}; // the bulge column stays 0 when there is no bulge pass (no_stellar)
+                        for (int comp = has_bulge ? 0 : 1; comp < 2; ++comp) {
+                            const RfDesc dsc = comp ? p.rfD[r] : p.rfB[r];
+                            const real *S = (comp ? SD : SB) + lane;
+                            const real *W = reinterpret_cast<const real *>(p.rfW) + dsc.off;
+                            CompSum<real> acc;
+                            acc.clear();
+                            for (int k = 0; k < dsc.n; ++k) acc.add(__ldcg(S + (size_t)(dsc.j0 + k) * kLanes) * __ldg(W + k));
+                            const double fl = dsc.covered ? ((double)acc.s + (double)acc.c) * (comp ? 1.0 : a_bulge) : __longlong_as_double(0x7ff8000000000000LL);
+                            const double m = -2.5 * log10(fl * arf) + 23.9;
+                            mg[comp] = isfinite(m) ? m : 99.0;
+                        }
+                        if (lane < ng) {
+                            const size_t oo = (size_t)g * nrf + r;
+                            const float md = (float)mg[1], mb = (float)mg[0];
+                            if (p.rfmag_disk) __stcs(p.rfmag_disk + oo, md);
+                            if (p.rfmag_bulge) __stcs(p.rfmag_bulge + oo, mb);
+                            if (p.rfmag) // uJy2mag(mag2uJy(disk) + mag2uJy(bulge)) on the f32 columns (src/egg-gencat.cpp:2239)
+                                __stcs(p.rfmag + oo, (float)(-2.5 * log10(exp10(0.4 * (23.9 - (double)md)) + exp10(0.4 * (23.9 - (double)mb))) + 23.9));
+                            if (p.rfmag_disk_f64) __stcs(p.rfmag_disk_f64 + oo, mg[1]);
+                            if (p.rfmag_bulge_f64) __stcs(p.rfmag_bulge_f64 + oo, mg[0]);
+                        }
+                    }
+                }
+
+                // ---- phase B: every band table of the group, one after the other, each lane walking its own galaxy
+                const int gbase = grp < (int)p.ngroups ? (int)p.groups[grp].base : 0;
+                for (int bi = 0; bi < nb; ++bi) {
+                    const int fb = gbase + bi;
+                    const uint32_t w = __shfl_sync(kFull, fb < 32 ? win_lo : win_hi, fb & 31);
+                    double totd = 0.0, totb = 0.0;
+                    if (w) {
+                        const int jlo = (int)(w & 0x7fffu), jhi = (int)((w >> 15) & 0x7fffu);
+                        const bool bulge = (w & 0x80000000u) != 0;
+                        const BandHeader2 &h = reinterpret_cast<const BandHeader2 *>(blob)[bi];
+                        BandDev B;
+                        B.hdr = tab_sa + (uint32_t)bi * (uint32_t)sizeof(BandHeader2);
+                        B.rec = tab_sa + h.rec_off; B.hs = tab_sa + h.hs_off; B.bkt = tab_sa + h.bkt_off;
+                        B.bk_scale = h.bk_scale; B.bk_c0 = h.bk_c0;
+                        B.nbkt_m1 = (int)h.nbkt - 1;
+                        B.nsplit = (int)h.nsplit;
+                        B.m0 = (int)h.msplit[0];
+                        B.two_probe = h.two_probe != 0;
+                        int js, je;
+                        block_arrivals(grid, q.next_opt, bulge, jlo, jhi, js, je);
+                        walk_dev<real>(B, grid, opz, bulge, jlo, jhi, js, je, SD + lane, SB + lane, totd, totb);
+                    }
+                    __stcg(RES + (size_t)(fb * 2 + 1) * kLanes + lane, totd);
+                    __stcg(RES + (size_t)(fb * 2) * kLanes + lane, totb);
+                }
+
+                if (gstep == ngl - 1 && lane < ng) {
+                    // ---- phase C: table sums added per output column in table order, data conditions, totals
+                    //      (src/egg-gencat.cpp:2238-2239), catalog columns
+                    const double d = __ldcs(p.d + g);
+                    const double sca = EGGPHOT_LSUN2UJY * opz / (d * d) / opz; // K (1+z) / d^2, and 1 / (1+z) of the walk's units
+                    const double a_bulge = has_bulge ? exp10((double)(p.m_bulge[g] - __ldcs(p.m2lcor + g))) : 0.0;
+                    const bool covd_any = nD >= 2, covb_any = has_bulge && nB >= 2;
+                    const double xd0 = covd_any ? __ldg(p.xD) * opz : 0.0, xd1 = covd_any ? __ldg(p.xD + nD - 1) * opz : 0.0;
+                    const double xb0 = covb_any ? __ldg(p.xB) * opz : 0.0, xb1 = covb_any ? __ldg(p.xB + nB - 1) * opz : 0.0;
+                    for (int col = 0; col < nbt; ++col) {
+                        double sd = 0.0, sb = 0.0;
+                        for (int fb = 0; fb < ntab; ++fb)
+                            if ((int)__ldg(q.tab_col + fb) == col) {
+                                sd += __ldcg(RES + (size_t)(fb * 2 + 1) * kLanes + lane);
+                                sb += __ldcg(RES + (size_t)(fb * 2) * kLanes + lane);
+                            }
+                        const double2 cv = __ldg(q.col_span + col);
+                        // [vif] sed2flux: NaN (-> flux 0, src/egg-gencat.cpp:2198) unless the SED covers the filter
+                        const bool covd = covd_any && xd0 <= cv.x && xd1 >= cv.y;
+                        const bool covb = covd && covb_any && xb0 <= cv.x && xb1 >= cv.y;
+                        double fd = covd ? sd * sca : 0.0;
+                        double fbv = covb ? sb * sca * a_bulge : 0.0;
+                        if (!isfinite(fd)) fd = 0.0;
+                        if (!isfinite(fbv)) fbv = 0.0;
+                        const float fdf = (float)fd, fbf = (float)fbv;
+                        const size_t oo = (size_t)g * nbt + col;
+                        // streaming stores: the catalog columns are written once
+                        if (p.flux_disk) __stcs(p.flux_disk + oo, fdf);
+                        if (p.flux_bulge) __stcs(p.flux_bulge + oo, fbf);
+                        if (p.flux) __stcs(p.flux + oo, fdf + fbf); // vec2f sum
+                        if (p.flux_disk_f64) __stcs(p.flux_disk_f64 + oo, fd);
+                        if (p.flux_bulge_f64) __stcs(p.flux_bulge_f64 + oo, fbv);
+                    }
                 }
             }
-            const double o = sc.opz[ln];
-            const double2 cv = cov[col];
-            // [vif] sed2flux: NaN (-> flux 0, src/egg-gencat.cpp:2198) unless the SED covers the filter
-            const bool covd = nD >= 2 && __ldg(p.xD) * o <= cv.x && __ldg(p.xD + nD - 1) * o >= cv.y;
-            const bool covb = covd && has_bulge && nB >= 2 && __ldg(p.xB) * o <= cv.x && __ldg(p.xB + nB - 1) * o >= cv.y;
-            const double sca = sc.iopz[ln] * sc.aflux[ln];
-            double fd = covd ? sd * sca : 0.0;
-            double fbv = covb ? sb * sca * sc.a_bulge[ln] : 0.0;
-            if (!isfinite(fd)) fd = 0.0;
-            if (!isfinite(fbv)) fbv = 0.0;
-            const float fdf = (float)fd, fbf = (float)fbv;
-            const size_t oo = (size_t)sc.gal[ln] * nbt + col;
-            // streaming stores: the catalog columns are written once and must not evict the scratch from L2
-            if (p.flux_disk) __stcs(p.flux_disk + oo, fdf);
-            if (p.flux_bulge) __stcs(p.flux_bulge + oo, fbf);
-            if (p.flux) __stcs(p.flux + oo, fdf + fbf); // vec2f sum
-            if (p.flux_disk_f64) __stcs(p.flux_disk_f64 + oo, fd);
-            if (p.flux_bulge_f64) __stcs(p.flux_bulge_f64 + oo, fbv);
+            __syncthreads(); // every warp is done with the group's tables; the table region may be overwritten
         }
-        for (int i = tid; i < ng * nrf; i += NT) {
-            const int ln = i / nrf, r = i - ln * nrf;
-            // [vif] lsun2uJy(0, 1e-5, ...) then uJy2mag; non-finite -> +99 (src/egg-gencat.cpp:2152-2156)
-            const double arf = EGGPHOT_LSUN2UJY / (1e-5 * 1e-5);
-            double mg[2] = {0.0, 0.0}; // the bulge column stays 0 when there is no bulge pass (no_stellar)
-            for (int comp = has_bulge ? 0 : 1; comp < 2; ++comp) {
-                const double m = -2.5 * log10(rfres[(r * 2 + comp) * kLanes + ln] * arf) + 23.9;
-                mg[comp] = isfinite(m) ? m : 99.0;
-            }
-            const size_t oo = (size_t)sc.gal[ln] * nrf + r;
-            const float md = (float)mg[1], mb = (float)mg[0];
-            if (p.rfmag_disk) __stcs(p.rfmag_disk + oo, md);
-            if (p.rfmag_bulge) __stcs(p.rfmag_bulge + oo, mb);
-            if (p.rfmag) // uJy2mag(mag2uJy(disk) + mag2uJy(bulge)) on the f32 columns (src/egg-gencat.cpp:2239)
-                __stcs(p.rfmag + oo, (float)(-2.5 * log10(exp10(0.4 * (23.9 - (double)md)) + exp10(0.4 * (23.9 - (double)mb))) + 23.9));
-            if (p.rfmag_disk_f64) __stcs(p.rfmag_disk_f64 + oo, mg[1]);
-            if (p.rfmag_bulge_f64) __stcs(p.rfmag_bulge_f64 + oo, mg[0]);
-        }
-        __syncthreads(); // sc / windows / slots are rewritten by the next batch
     }
 }
 
 #ifndef EGG_LANE_THREADS
-#define EGG_LANE_THREADS 384
+#define EGG_LANE_THREADS 512
 #endif
 constexpr int kLaneThreads = EGG_LANE_THREADS;
 
-size_t lane_smem_bytes(const LaneParams &q) {
-    const FluxParams &p = q.fp;
-    return lane_smem_layout(p.max_blob, q.ntab, p.nband_total, p.nrf, p.nline > 0 ? p.nline : 0).total;
-}
+size_t lane_smem_bytes(const LaneParams &q) { return (q.fp.max_blob + 127) & ~size_t(127); }
 
 template <typename real> int launch_lane(const LaneParams &q, int blocks, cudaStream_t st) {
     const size_t smem = lane_smem_bytes(q);
@@ -719,6 +631,37 @@ int launch_zsort(const float *z, uint32_t ngal, uint32_t *hist, uint32_t *perm, 
     return (int)cudaGetLastError();
 }
 size_t zsort_hist_bytes() { return kZBuckets * sizeof(uint32_t); }
+
+// TFLOP/s (2 flops per FMA) of back-to-back independent FMA chains on every SM, best of five runs
+template <typename T> static int fma_peak(int num_sms, void *scratch, cudaStream_t st, double &tflops) {
+    const int iters = sizeof(T) == 4 ? 4096 : 1024, blocks = num_sms * 2;
+    cudaEvent_t e0, e1;
+    cudaError_t e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    if (e != cudaSuccess) return (int)e;
+    double best = 0.0;
+    for (int rep = 0; rep < 6 && e == cudaSuccess; ++rep) {
+        cudaEventRecord(e0, st);
+        fma_peak_kernel<T><<<blocks, 1024, 0, st>>>((T *)scratch, iters, (T)0.999999, (T)1e-7);
+        cudaEventRecord(e1, st);
+        e = cudaEventSynchronize(e1);
+        float ms = 0;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        const double fl = 2.0 * 64.0 * iters * 1024.0 * blocks;
+        if (rep > 0 && ms > 0) best = fmax(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    tflops = best;
+    return (int)e;
+}
+int measure_fma_peak(int num_sms, void *scratch, cudaStream_t st, double *fp32_tflops, double *fp64_tflops) {
+    int e = fma_peak<float>(num_sms, scratch, st, *fp32_tflops);
+    if (e == 0) e = fma_peak<double>(num_sms, scratch, st, *fp64_tflops);
+    return e;
+}
+
+int lane_kernel_threads() { return kLaneThreads; }
 
 int launch_lane_flux_kernel(const LaneParams &q, int precision, int grid_blocks, cudaStream_t stream) {
     return precision == EGGPHOT_FP64 ? launch_lane<double>(q, grid_blocks, stream) : launch_lane<float>(q, grid_blocks, stream);

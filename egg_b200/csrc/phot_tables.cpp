@@ -355,6 +355,17 @@ Status build_band_table2(const Filter &f, int i0, int i1, uint32_t out_col, int 
             if (fn[node] > fn[0] && fn[node] < fn[n - 1]) val.push_back(Valley{node, fn[k] - fn[i]});
             i = k + 1;
         }
+        // a valley matters only if the response carries weight on both sides of it: a node in it differences table values of
+        // the size of the lighter side's integral (the split between two anchors sits at the half-mass node), which the
+        // zero runs in the noisy wings of measured curves never do
+        {
+            std::vector<double> cum(n, 0.0);
+            for (int i = 0; i + 1 < n; ++i) cum[i + 1] = cum[i] + 0.5 * (std::fabs(R[i]) + std::fabs(R[i + 1])) * dl[i];
+            std::vector<Valley> keepv;
+            for (const Valley &v : val)
+                if (std::min(cum[v.node], cum[n - 1] - cum[v.node]) > 1e-4 * cum[n - 1]) keepv.push_back(v);
+            val.swap(keepv);
+        }
         std::stable_sort(val.begin(), val.end(), [](const Valley &x, const Valley &y) { return x.width > y.width; });
         if ((int)val.size() > kMaxSplit - 1) val.resize(kMaxSplit - 1);
         anchors.push_back(0);
@@ -573,13 +584,9 @@ Status build_lane_tables(Prepared &P, const eggphot_opts &opts) {
             if (P.grid_nodes[j].o >= 0 && P.grid_nodes[j + 1].o < 0) P.grid_nodes[j].o |= kNextNotOptical;
     }
     // ---- band tables in groups
-    const size_t nl = P.no_nebular ? 0 : P.line_lambda.size();
     size_t budget = opts.smem_table_budget;
     if (!budget) {
-        // two CTAs per SM (1 KB of each CTA's share is reserved by the system); up to ~1.5 tables per band after cuts
-        const size_t fixed = lane_smem_layout(0, P.bands.size() * 2 + 16, P.bands.size(), P.rfbands.size(), nl).total + kLaneStaticSmem + 1024;
-        const size_t share = kSmemPerSm / kLaneCtasPerSm;
-        budget = fixed + 32u * 1024 < share ? share - fixed : 32u * 1024;
+        budget = kSmemPerCta - kLaneFixedSmem;
     }
     // a filter whose table exceeds the budget is cut at filter nodes into pieces that feed the same output column
     std::vector<BandTable2> tabs;

@@ -68,7 +68,7 @@ def load_library(path: str = _LIB_PATH):
 
 EXPORTS = ("eggphot_create", "eggphot_destroy", "eggphot_last_error", "eggphot_nband", "eggphot_band_order",
            "eggphot_compute", "eggphot_compute_device", "eggphot_synchronize", "eggphot_sed_size",
-           "eggphot_get_seds", "eggphot_get_stats")
+           "eggphot_get_seds", "eggphot_get_stats", "eggphot_measure_fma_peak")
 
 
 class Photometry:
@@ -171,6 +171,13 @@ class Photometry:
         sed = np.empty((count, n), np.float32)
         self._check(self._L.eggphot_get_seds(self._ctx, C.byref(G), first, count, comp, lam.ctypes.data, sed.ctypes.data))
         return lam, sed
+
+    def fma_peak(self):
+        """Measured FP32 / FP64 FMA peak of the context's GPU in TFLOP/s (the roofline denominators of bench.py)."""
+        a, b = C.c_double(0.0), C.c_double(0.0)
+        self._L.eggphot_measure_fma_peak.restype = C.c_int
+        self._check(self._L.eggphot_measure_fma_peak(self._ctx, C.byref(a), C.byref(b)))
+        return {"fp32_tflops": a.value, "fp64_tflops": b.value}
 
     def stats(self):
         s = A.Stats()

@@ -165,6 +165,11 @@ typedef struct eggphot_stats {
 } eggphot_stats;
 int eggphot_get_stats(const eggphot_ctx *ctx, eggphot_stats *stats);
 
+/* Measured peak of the CUDA-core FMA pipes of ctx's device, the roofline this quadrature is compared with (SURVEY.md
+ * section 8d asks for a measured, not a nominal, denominator): independent FMA chains on every SM timed with CUDA
+ * events, best of five launches.  TFLOP/s counting 2 flops per FMA. */
+int eggphot_measure_fma_peak(eggphot_ctx *ctx, double *fp32_tflops, double *fp64_tflops);
+
 #ifdef __cplusplus
 }
 #endif

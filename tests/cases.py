@@ -47,21 +47,25 @@ def make(name, ngal=96, seed=11):
                 opts=dict(opts), gal=gal, lines=synth.LINE_LAMBDA)
 
 
-FLOOR = {"fp32c": 1e-5, "fp64": 1e-9}
+FLOOR = {"fp32c": 0.0, "fp64": 0.0}   # no faint-band floor: the tolerance holds relative to every band itself
 
 
-def rel_err(a, b, floor_frac=1e-9):
-    """|a-b| / max(|b|, floor) per entry; floor = floor_frac x the galaxy's brightest band.  A band that
-    far below the brightest one (an IGM-erased band seen only through the 1e-6 wing of its filter) is
-    held to the tolerance in absolute terms relative to that floor, not relative to itself.  Measured
-    worst cases relative to the band itself: fp32c 4e-5 for a band 4e-7 of the brightest whose flux is a
-    strong emission line seen through the 1e-6 wing of an HST filter (the hi+lo prefix tables hold
-    2^-48 of the band total), < 3e-6 for every band above 1e-6 of the brightest; fp64 2e-12."""
+def rel_err(a, b, floor_frac=0.0):
+    """|a-b| / |b| per entry (BASELINE.json north_star: relative, per band).  Where the reference value is exactly 0
+    (uncovered band, or every SED node under the band erased by the IGM) the result must be exactly 0 too: anything
+    else counts as an infinite error.  floor_frac > 0 (not used by the parity tests any more) measures faint entries
+    against that fraction of the galaxy's brightest band instead."""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     if b.size == 0:
         return np.zeros_like(b)
-    floor = floor_frac * np.abs(b).max(axis=1, keepdims=True)
-    return np.abs(a - b) / np.maximum(np.maximum(np.abs(b), floor), 1e-300)
+    den = np.abs(b)
+    if floor_frac > 0:
+        den = np.maximum(den, floor_frac * np.abs(b).max(axis=1, keepdims=True))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        e = np.abs(a - b) / den
+    e[(den == 0) & (a == b)] = 0.0
+    e[(den == 0) & (a != b)] = np.inf
+    return e
 
 
 TOL = {"fp32c": 1e-5, "fp64": 1e-10}   # BASELINE.json north_star tolerances (relative, per band)

@@ -218,6 +218,30 @@ void run(const Prepared &P, const eggphot_galaxies &G, size_t ngal, double *fd, 
 
 // ---- the lane kernel's algorithm (phot_lane.cuh): batches of 32 z-sorted galaxies, union windows per band,
 //      blocks of 64 nodes walked per galaxy, block sums added in double in block order
+// emission lines as the lane kernel deposits them: line by line in wavelength order, each bin integral rounded to the
+// kernel's real type and added to the node
+template <typename real>
+void add_lines_lane(const Prepared &P, const Grid &g, std::vector<real> &S, const float *ll, double vdisp, double inv) {
+    const int n = g.n(), nl = (int)P.line_lambda.size();
+    std::vector<int> ord(nl);
+    for (int l = 0; l < nl; ++l) ord[l] = l;
+    std::stable_sort(ord.begin(), ord.end(), [&](int i, int j) { return P.line_lambda[i] < P.line_lambda[j]; });
+    for (int q = 0; q < nl; ++q) {
+        const int l = ord[q];
+        if (ll[l] == 0.0f) continue;
+        const double l0 = P.line_lambda[l], lw = l0 * (vdisp / 2.998e5);
+        int lo = last_le(g.x, l0 - 10 * lw), hi = last_le(g.x, l0 + 10 * lw) + 1;
+        if (hi == 0 || lo == n - 1) continue;
+        const int b0 = lo < 0 ? 0 : lo, b1 = hi >= n ? n - 1 : hi;
+        for (int j = b0; j <= b1; ++j) {
+            const double xj = g.x[j], xm = j > 0 ? g.x[j - 1] : 0.0, xp = j < n - 1 ? g.x[j + 1] : 0.0;
+            const double llow = j != 0 ? 0.5 * (xm + xj) : xj - 0.5 * (xp - xj);
+            const double lup = j != n - 1 ? 0.5 * (xj + xp) : xj + 0.5 * (xj - xm);
+            S[j] += (real)(xj * line_bin_t<real>(llow, lup, l0, lw, (double)ll[l] * l0, P.line_profile == EGGPHOT_LINE_AVERAGE) * inv);
+        }
+    }
+}
+
 template <typename real> struct SedRef {
     const real *d, *b;
     real disk(int j) const { return d[j]; }
@@ -274,14 +298,9 @@ void run2(const Prepared &P, const eggphot_galaxies &G, size_t ngal, double *fd,
                 SB[l][j] = v;
             }
             if (nl) {
-                for (int j = 0; j < nD; ++j) SDd[j] = 0;
-                add_lines(P, P.grid_disk, SDd, G.line_lum_disk + g * nl, G.vdisp[g], 1.0);
-                for (int j = 0; j < nD; ++j) if (SDd[j] != 0) SD[l][j] += (real)SDd[j];
-                if (P.has_bulge && G.line_lum_bulge) {
-                    for (int j = 0; j < nB; ++j) SBd[j] = 0;
-                    add_lines(P, P.grid_bulge, SBd, G.line_lum_bulge + g * nl, G.vdisp[g], a_b[l] > 0 ? 1.0 / a_b[l] : 0.0);
-                    for (int j = 0; j < nB; ++j) if (SBd[j] != 0) SB[l][j] += (real)SBd[j];
-                }
+                add_lines_lane<real>(P, P.grid_disk, SD[l], G.line_lum_disk + g * nl, G.vdisp[g], 1.0);
+                if (P.has_bulge && G.line_lum_bulge)
+                    add_lines_lane<real>(P, P.grid_bulge, SB[l], G.line_lum_bulge + g * nl, G.vdisp[g], a_b[l] > 0 ? 1.0 / a_b[l] : 0.0);
             }
         }
         // block sums per output column (a filter cut into several tables adds them up), tables in group order
