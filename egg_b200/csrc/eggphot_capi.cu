@@ -423,7 +423,7 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
             if (occ <= 0) return c->fail(EGGPHOT_ERR_CUDA, "flux kernel cannot be resident (occupancy query failed)");
             c->lane_blocks = c->num_sms;
             c->lane_region_bytes = (size_t)c->lane_blocks * (lane_kernel_threads() / 32) * q.scratch_stride;
-            CK(c->lane_scratch.alloc(c->lane_region_bytes * (kSlots + 1)));
+            CK(c->lane_scratch.alloc(c->lane_region_bytes * (kSlots + 1) + 65536)); // (+ room for the prefetches that run past the last row)
             for (auto &h : c->zhist) CK(h.alloc(zsort_hist_bytes()));
         }
     }
@@ -490,6 +490,12 @@ int eggphot_compute(eggphot_ctx *c, const eggphot_galaxies *gal, size_t ngal, co
     // chunks: large enough to fill every SM several times over, small enough that the copies of one
     // chunk overlap the kernel of the other (two streams): an eighth of the catalog, within [2^15, 2^18]
     size_t chunk = std::min<size_t>(std::max<size_t>((ngal + 7) / 8, 1u << 15), 1u << 18);
+    if (c->use_lane) {
+        // the lane kernel works in rounds of one batch of 32 galaxies per warp: a chunk is a whole number of rounds of
+        // the whole GPU, two at least (the last round of a launch is rarely full)
+        const size_t unit = (size_t)c->lane_blocks * (lane_kernel_threads() / 32) * kLanes;
+        chunk = std::max<size_t>((std::min<size_t>((ngal + 7) / 8, 1u << 20) + unit - 1) / unit, 2) * unit;
+    }
     chunk = std::min(chunk, ngal);
     if (chunk == 0) return EGGPHOT_OK;
 #define CK(x) do { if ((e = (x)) != cudaSuccess) return c->cuda_fail(e, #x); } while (0)
@@ -598,6 +604,13 @@ int eggphot_get_seds(eggphot_ctx *c, const eggphot_galaxies *gal, size_t first, 
     CK(cudaStreamSynchronize(c->stream));
 #undef CK
     return read_error_flag(c);
+}
+
+int eggphot_get_grid(const eggphot_ctx *c, int component, double *x) {
+    if (!c || !x) return EGGPHOT_ERR_ARG;
+    const Grid &g = component ? c->P.grid_disk : c->P.grid_bulge;
+    std::copy(g.x.begin(), g.x.end(), x);
+    return EGGPHOT_OK;
 }
 
 int eggphot_measure_fma_peak(eggphot_ctx *c, double *fp32_tflops, double *fp64_tflops) {

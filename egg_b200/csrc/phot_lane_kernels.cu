@@ -106,6 +106,11 @@ __device__ __forceinline__ void st_keep(float *p, float v, uint64_t pol) {
 __device__ __forceinline__ void st_keep(double *p, double v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
 }
+// The SED rows of a batch live in HBM by the time the bands read them (16 batches per SM are in flight): every trip of
+// the walk asks L2 for the rows it will need kPrefetchRows nodes later, so that the loads themselves hit L2.
+constexpr int kPrefetchRows = 16;
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // shared-memory loads by 32-bit shared address (all address arithmetic of the walk stays in 32 bits)
 __device__ __forceinline__ double lds_f64(uint32_t a) {
     double v;
@@ -198,12 +203,14 @@ __device__ __forceinline__ double interval_dev(const BandDev &B, const NodeSt &p
 }
 
 // Walks nodes js..je of the disk grid for one galaxy (lane) and one band table; accumulates the nodes of [a, b].
+// ob0 = first optical node at or after js (index in the bulge grid), obn = optical nodes per 256 disk nodes of the walk
+// (only for prefetching the bulge rows ahead of the walk).
 // totd / totb receive the sums of the blocks of 64 nodes (each summed in `real`, the blocks added in double, in order:
 // the same numbers whichever way the window is cut).
 template <typename real>
 __device__ __forceinline__ void walk_dev(const BandDev &B, const GridNode *__restrict__ grid, double opz, bool bulge, int a, int b,
-                                         int js, int je, const real *__restrict__ sd, const real *__restrict__ sb, double &totd,
-                                         double &totb) {
+                                         int js, int je, const real *__restrict__ sd, const real *__restrict__ sb, int ob0, int obn,
+                                         double &totd, double &totb) {
     NodeSt s0{0.0, 0.0, -1, B.m0}, s1 = s0, so = s0;
     double Eprev_d = 0.0, Eprev_b = 0.0;
     real Sprev_d = real(0), Sprev_b = real(0), accd = real(0), accb = real(0);
@@ -259,9 +266,20 @@ __device__ __forceinline__ void walk_dev(const BandDev &B, const GridNode *__res
             if (go & kNextNotOptical) so = C; // the next bulge interval does not start as a disk interval
         }
     };
+    // rows of the first nodes, one per lane (a row is 32 lanes x sizeof(real): one or two 128-byte lines)
+    const int lane = threadIdx.x & 31;
+    constexpr int kLinesPerRow = (int)sizeof(real) / 4;
+    if (lane < kPrefetchRows * kLinesPerRow) {
+        prefetch_l2(reinterpret_cast<const char *>(sd - lane + (size_t)js * kLanes) + 128 * lane);
+        if (bulge && ob0 >= 0) prefetch_l2(reinterpret_cast<const char *>(sb - lane + (size_t)ob0 * kLanes) + 128 * lane);
+    }
     // two arrivals per trip, the two states swapping roles (no register moves); an odd count runs one node past je,
     // which weighs nothing in range (the grid has two virtual nodes behind the last real one)
     for (int j = js; j <= je; j += 2) {
+        if (lane < 2 * kLinesPerRow) { // the two rows this trip will need kPrefetchRows nodes later (past the end: harmless)
+            prefetch_l2(reinterpret_cast<const char *>(sd - lane + (size_t)(j + kPrefetchRows) * kLanes) + 128 * lane);
+            if (bulge) prefetch_l2(reinterpret_cast<const char *>(sb - lane + (size_t)(ob0 + ((j - js) * obn >> 8) + kPrefetchRows) * kLanes) + 128 * lane);
+        }
         step(s0, s1, j);
         step(s1, s0, j + 1);
     }
@@ -301,7 +319,6 @@ __global__ void __launch_bounds__(NT, 1) lane_flux_kernel(const __grid_constant_
     __syncthreads();
     uint32_t tab_phase = 0;
     int loaded = -1;
-    const uint64_t keep = evict_last_policy();
 
     // the CTA's share of the batches (contiguous: neighbouring redshifts), NW at a time, one per warp
     const uint64_t nbatch = (p.ngal + kLanes - 1) / kLanes;
@@ -437,7 +454,7 @@ __global__ void __launch_bounds__(NT, 1) lane_flux_kernel(const __grid_constant_
                                 if (p.disk_mode != 1 && cs17) v += c2 * pq.v[k];
                                 if (p.apply_igm && j0 + k < p.igmD[3])
                                     v *= igm_factor<real>(j0 + k, p.igmD[0], p.igmD[1], p.igmD[2], p.igmD[3], g0f, g1f, g2f);
-                                if (j0 + k < nD) st_keep(SD + (size_t)(j0 + k) * kLanes + lane, v, keep);
+                                if (j0 + k < nD) __stcg(SD + (size_t)(j0 + k) * kLanes + lane, v);
                             }
                         }
                     }
@@ -451,7 +468,7 @@ __global__ void __launch_bounds__(NT, 1) lane_flux_kernel(const __grid_constant_
                                 real v = o.v[k];
                                 if (p.apply_igm && j0 + k < p.igmB[3])
                                     v *= igm_factor<real>(j0 + k, p.igmB[0], p.igmB[1], p.igmB[2], p.igmB[3], g0f, g1f, g2f);
-                                if (j0 + k < nB) st_keep(SB + (size_t)(j0 + k) * kLanes + lane, v, keep);
+                                if (j0 + k < nB) __stcg(SB + (size_t)(j0 + k) * kLanes + lane, v);
                             }
                         }
                     }
@@ -487,7 +504,7 @@ __global__ void __launch_bounds__(NT, 1) lane_flux_kernel(const __grid_constant_
                                     const double llow = j != 0 ? 0.5 * (xm + xj) : xj - 0.5 * (xp - xj);     // :2090
                                     const double lup = j != n - 1 ? 0.5 * (xj + xp) : xj + 0.5 * (xj - xm); // :2091
                                     real *sp = S + (size_t)j * kLanes;
-                                    st_keep(sp, __ldcg(sp) + (real)(xj * line_bin_t<real>(llow, lup, l0, lw, amp, p.line_average) * inv), keep);
+                                    __stcg(sp, __ldcg(sp) + (real)(xj * line_bin_t<real>(llow, lup, l0, lw, amp, p.line_average) * inv));
                                 }
                             }
                         }
@@ -542,7 +559,15 @@ __global__ void __launch_bounds__(NT, 1) lane_flux_kernel(const __grid_constant_
                         B.two_probe = h.two_probe != 0;
                         int js, je;
                         block_arrivals(grid, q.next_opt, bulge, jlo, jhi, js, je);
-                        walk_dev<real>(B, grid, opz, bulge, jlo, jhi, js, je, SD + lane, SB + lane, totd, totb);
+                        int ob0 = -1, obn = 0;
+                        if (bulge) { // optical nodes the walk visits: for the prefetch of the bulge rows
+                            const int jo0 = grid[js].o >= 0 ? js : q.next_opt[js], jo1 = grid[je].o >= 0 ? je : grid[je].po;
+                            if (jo0 <= jo1 && jo1 >= 0) {
+                                ob0 = grid_o(grid[jo0]);
+                                obn = ((grid_o(grid[jo1]) - ob0 + 1) << 8) / (je - js + 1);
+                            }
+                        }
+                        walk_dev<real>(B, grid, opz, bulge, jlo, jhi, js, je, SD + lane, SB + lane, ob0, obn, totd, totb);
                     }
                     __stcg(RES + (size_t)(fb * 2 + 1) * kLanes + lane, totd);
                     __stcg(RES + (size_t)(fb * 2) * kLanes + lane, totb);

@@ -68,7 +68,7 @@ def load_library(path: str = _LIB_PATH):
 
 EXPORTS = ("eggphot_create", "eggphot_destroy", "eggphot_last_error", "eggphot_nband", "eggphot_band_order",
            "eggphot_compute", "eggphot_compute_device", "eggphot_synchronize", "eggphot_sed_size",
-           "eggphot_get_seds", "eggphot_get_stats", "eggphot_measure_fma_peak")
+           "eggphot_get_seds", "eggphot_get_stats", "eggphot_measure_fma_peak", "eggphot_get_grid")
 
 
 class Photometry:
@@ -171,6 +171,14 @@ class Photometry:
         sed = np.empty((count, n), np.float32)
         self._check(self._L.eggphot_get_seds(self._ctx, C.byref(G), first, count, comp, lam.ctypes.data, sed.ctypes.data))
         return lam, sed
+
+    def grid(self, comp):
+        """Rest wavelengths of the prepared SED grid of a component ('bulge' | 'disk')."""
+        ci = 0 if comp == "bulge" else 1
+        self._L.eggphot_sed_size.restype = C.c_uint32
+        x = np.zeros(int(self._L.eggphot_sed_size(self._ctx, ci)), np.float64)
+        self._check(self._L.eggphot_get_grid(self._ctx, ci, C.c_void_p(x.ctypes.data)))
+        return x
 
     def fma_peak(self):
         """Measured FP32 / FP64 FMA peak of the context's GPU in TFLOP/s (the roofline denominators of bench.py)."""

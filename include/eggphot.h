@@ -154,6 +154,10 @@ uint32_t eggphot_sed_size(const eggphot_ctx *ctx, int component);
 int eggphot_get_seds(eggphot_ctx *ctx, const eggphot_galaxies *gal, size_t first, size_t count, int component,
                      float *lam, float *sed);
 
+/* Rest wavelengths [um] of the prepared SED grid of one component (0 bulge = the optical library's grid after
+ * re-binning, 1 disk = the merge_add union with the IR grid); x receives eggphot_sed_size(ctx, component) values. */
+int eggphot_get_grid(const eggphot_ctx *ctx, int component, double *x);
+
 /* Introspection for benchmarks: kernels launched by the last compute call, number of band groups,
  * and the algorithmic work of the last call (quadrature nodes). */
 typedef struct eggphot_stats {

@@ -25,11 +25,3 @@ def libs():
     from egg_b200 import synth
     return {"opt": synth.make_opt_lib(), "ce01": synth.ce01_lib(), "cs17": synth.make_cs17_lib(),
             "opt_hd": None}
-
-
-def rel_err(a, b, floor_frac=1e-9):
-    """per-entry |a-b| / max(|b|, floor) with floor = floor_frac * brightest band of the same galaxy"""
-    b = np.asarray(b, np.float64)
-    a = np.asarray(a, np.float64)
-    floor = floor_frac * np.abs(b).max(axis=1, keepdims=True)
-    return np.abs(a - b) / np.maximum(np.maximum(np.abs(b), floor), 1e-300)

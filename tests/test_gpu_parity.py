@@ -36,8 +36,10 @@ def test_cuda_matches_oracle(name, prec):
         e = cases.rel_err(out[k + "_f64"], ref[k], cases.FLOOR[prec])
         assert e.max() < cases.TOL[prec], f"{name} {k}: {e.max():.2e}"
         # the f32 catalog columns: same numbers after rounding (1 ulp slack for values on a rounding edge)
-        e32 = cases.rel_err(out[k], ref32[k], 1e-6)
-        assert e32.max() < 2e-5 if prec == "fp32c" else e32.max() < 1.3e-7
+        normal = np.abs(ref32[k]) > 1e-36  # (below that the f32 column itself is denormal and carries fewer digits)
+        e32 = cases.rel_err(out[k], ref32[k])[normal]
+        assert e32.size == 0 or (e32.max() < 1.1e-5 if prec == "fp32c" else e32.max() < 1.3e-7)
+        assert np.abs(out[k][~normal].astype(np.float64) - ref32[k][~normal]).max(initial=0.0) < 1e-40
     for k in ("rfmag_disk", "rfmag_bulge"):
         if ref[k].size:
             assert np.abs(out[k + "_f64"] - ref[k]).max() < cases.MAGTOL[prec], f"{name} {k}"
@@ -71,7 +73,8 @@ def test_ragged_and_empty_batches(n):
     assert out["flux"].shape == (n, 4)
     if n:
         ref = Oracle(c["opt"], c["ir"], c["bands"], line_lambda=c["lines"]).compute(gal, f64=True)
-        assert cases.rel_err(out["flux_disk"], ref["flux_disk"], 1e-6).max() < 2e-5
+        ok = np.abs(ref["flux_disk"]) > 1e-36
+        assert cases.rel_err(out["flux_disk"], ref["flux_disk"])[ok].max() < 1.1e-5
     ph.close()
 
 
