@@ -401,6 +401,12 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
             q.tab_col = (const uint32_t *)c->tabCol.p;
         }
         if (q.ntab > 64) return c->fail(EGGPHOT_ERR_UNSUPPORTED, "more than 64 band tables; raise smem_table_budget");
+        {   // a walk starts at the optical node before its window and ends at the one after it (plus the unrolled trip's extra node)
+            int gap = 1, last = -1;
+            for (int j = 0; j < P.grid_disk.n(); ++j)
+                if (P.grid_nodes[j].o >= 0) { if (last >= 0) gap = std::max(gap, j - last); last = j; }
+            q.row_margin = (uint32_t)(P.has_bulge ? gap + 3 : 3);
+        }
         if (P.grid_disk.n() > 32000) return c->fail(EGGPHOT_ERR_UNSUPPORTED, "SED wavelength grid with more than 32000 nodes");
         {
             std::vector<double> span(2 * std::max<size_t>(P.bands.size(), 1), 0.0);

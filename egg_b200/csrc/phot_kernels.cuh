@@ -91,7 +91,7 @@ struct LaneParams {
     const uint32_t *tab_col;  // [ntab] output column of every band table, in group order
     const double2 *col_span;  // [nband] full wavelength span of every filter (coverage test), by output column
     uint32_t ntab;            // band tables (a filter cut into pieces has several); at most 64
-    uint32_t pad_;
+    uint32_t row_margin;      // disk-grid rows built on either side of the nodes the bands read (see the kernel)
     uint64_t scratch_stride;  // bytes per warp
     uint64_t res_offset;      // bytes from the start of a warp's area to its table sums
 };

@@ -202,13 +202,13 @@ __device__ __forceinline__ double interval_dev(const BandDev &B, const NodeSt &p
     return E;
 }
 
-// Walks nodes js..je of the disk grid for one galaxy (lane) and one band table; accumulates the nodes of [a, b].
+// Walks nodes js..je of the disk grid for one galaxy (lane) and one band table.
 // ob0 = first optical node at or after js (index in the bulge grid), obn = optical nodes per 256 disk nodes of the walk
 // (only for prefetching the bulge rows ahead of the walk).
 // totd / totb receive the sums of the blocks of 64 nodes (each summed in `real`, the blocks added in double, in order:
 // the same numbers whichever way the window is cut).
 template <typename real>
-__device__ __forceinline__ void walk_dev(const BandDev &B, const GridNode *__restrict__ grid, double opz, bool bulge, int a, int b,
+__device__ __forceinline__ void walk_dev(const BandDev &B, const GridNode *__restrict__ grid, uint32_t gx_sa, double opz, bool bulge,
                                          int js, int je, const real *__restrict__ sd, const real *__restrict__ sb, int ob0, int obn,
                                          double &totd, double &totb) {
     NodeSt s0{0.0, 0.0, -1, B.m0}, s1 = s0, so = s0;
@@ -216,16 +216,16 @@ __device__ __forceinline__ void walk_dev(const BandDev &B, const GridNode *__res
     real Sprev_d = real(0), Sprev_b = real(0), accd = real(0), accb = real(0);
     double td = 0.0, tb = 0.0;
     int kb = 0; // block of the optical node the next bulge interval settles
-    const unsigned span = (unsigned)(b - a);
     // one arrival: P = state of node j - 1, C receives the state of node j
     auto step = [&](const NodeSt &P, NodeSt &C, int j) {
-        const double2 gxy = __ldg(reinterpret_cast<const double2 *>(grid + j)), gzw = __ldg(reinterpret_cast<const double2 *>(grid + j) + 1);
-        struct { double x, y, z; } ga{gxy.x, gxy.y, gzw.x}; // x, idxp, idxpo
-        const int go = __double2loint(gzw.y), gpo = __double2hiint(gzw.y); // {o, po}
-        const double t = opz * ga.x; // the reference's lam = rlam * (1 + z) (src/egg-gencat.cpp:2161), in double
-        const bool in_range = (unsigned)(j - a) <= span;
-        real Sd = __ldcg(sd + (size_t)j * kLanes);
-        Sd = in_range ? Sd : real(0);
+        // {x, idxp} from shared memory (the sign of idxp flags an optical node); the rest of the node's record is needed
+        // for the bulge only
+        const double2 gx = lds_v2f64(gx_sa + 16u * (uint32_t)j);
+        const bool optical = __double2hiint(gx.y) < 0;
+        const double t = opz * gx.x; // the reference's lam = rlam * (1 + z) (src/egg-gencat.cpp:2161), in double
+        // Nodes outside the band's window need no mask: every interval next to them lies outside the span for every lane of
+        // the batch, so their weights are exactly 0 (and the rows the walk can touch are always built: finite values).
+        const real Sd = __ldcg(sd + (size_t)j * kLanes);
         // filter cell of t
         int k = round_lo(fma(t, B.bk_scale, B.bk_c0));
         k = min(max(k, 0), B.nbkt_m1);
@@ -247,17 +247,18 @@ __device__ __forceinline__ void walk_dev(const BandDev &B, const GridNode *__res
         // disk: close [j - 1, j], settle node j - 1 (the block sums are flushed when node j - 1 starts a new block)
         if (((j - 1) & (kLaneBlock - 1)) == 0) { td += (double)accd; accd = real(0); }
         double Eadj_d;
-        const double E_d = interval_dev(B, P, r, u, Lin, q0b.x, q0b.y, hs, t, ga.y, opz, Eadj_d, C.nsr);
+        const double E_d = interval_dev(B, P, r, u, Lin, q0b.x, q0b.y, hs, t, fabs(gx.y), opz, Eadj_d, C.nsr);
         accd = fma(to_real<real>(E_d - Eprev_d), Sprev_d, accd);
         Eprev_d = Eadj_d;
         Sprev_d = Sd;
         // bulge: its SED intervals run between optical nodes
-        if (bulge && go >= 0) {
-            real Sb = __ldcg(sb + (size_t)(go & (kNextNotOptical - 1)) * kLanes);
-            Sb = in_range ? Sb : real(0);
+        if (bulge && optical) {
+            const double2 gzw = __ldg(reinterpret_cast<const double2 *>(grid + j) + 1); // idxpo, {o, po}
+            const int go = __double2loint(gzw.y), gpo = __double2hiint(gzw.y);
+            const real Sb = __ldcg(sb + (size_t)(go & (kNextNotOptical - 1)) * kLanes);
             double E_b, Eadj_b;
             if (gpo == j - 1 && j > js) { E_b = E_d; Eadj_b = Eadj_d; } // the interval is a disk interval too
-            else { int dummy; E_b = interval_dev(B, so, r, u, Lin, q0b.x, q0b.y, hs, t, ga.z, opz, Eadj_b, dummy); }
+            else { int dummy; E_b = interval_dev(B, so, r, u, Lin, q0b.x, q0b.y, hs, t, gzw.x, opz, Eadj_b, dummy); }
             const int kprev = gpo >> 6; // block of the optical node this interval settles (-1 >> 6 = -1: none yet)
             if (kprev != kb) { tb += (double)accb; accb = real(0); kb = kprev; }
             accb = fma(to_real<real>(E_b - Eprev_b), Sprev_b, accb);
@@ -311,6 +312,10 @@ __global__ void __launch_bounds__(NT, 1) lane_flux_kernel(const __grid_constant_
     const real *rP = reinterpret_cast<const real *>(p.rowsDpah), *rB = reinterpret_cast<const real *>(p.rowsB);
     const GridNode *grid = q.grid;
     const uint32_t tab_sa = smem_u32(smem);
+    // behind the band tables: {x, idxp} of every node of the disk grid, idxp negated at optical nodes
+    double2 *gxs = reinterpret_cast<double2 *>(smem + ((p.max_blob + 127) & ~127u));
+    const uint32_t gx_sa = smem_u32(gxs);
+    for (int j = tid; j < nD + 2; j += NT) gxs[j] = make_double2(grid[j].x, grid[j].o >= 0 ? -grid[j].idxp : grid[j].idxp);
 
     if (tid == 0) {
         mbar_init(&bar_tab, 1);
@@ -438,37 +443,44 @@ __global__ void __launch_bounds__(NT, 1) lane_flux_kernel(const __grid_constant_
                     // rest-frame SEDs, lane = galaxy: 16 bytes of each template row per load, [node][lane] stores.  Only the
                     // nodes some band of the batch reads are built.  The bulge SED carries no mass scale (applied at the end).
                     constexpr int NPL = 16 / (int)sizeof(real);
-                    {
+                    // (rows a walk can touch beyond the needed nodes - the node before a window, the optical nodes around it, the
+                    //  node an unrolled trip runs over - are built as well: their weights are exactly 0, their values must be finite)
+                    if (jn1 >= jn0) {
                         const real *rowO = rO + (size_t)rd * p.strideD, *rowI = rI + (size_t)ri * p.strideD, *rowP = rP + (size_t)ri * p.strideD;
-                        const int jend = jn1 >= jn0 ? min(jn1 + 1, p.strideD) : 0;
-                        for (int j0 = jn1 >= jn0 ? (jn0 & ~3) : 0; j0 < jend; j0 += NPL) {
+                        const int jb0 = max(jn0 - (int)q.row_margin, 0) & ~3, jb1 = min(jn1 + (int)q.row_margin, nD + 1);
+                        for (int j0 = jb0; j0 <= jb1; j0 += NPL) {
                             Vec16<real> o, i, pq;
 #pragma unroll
                             for (int k = 0; k < NPL; ++k) o.v[k] = i.v[k] = pq.v[k] = real(0);
-                            if (p.disk_mode != 2) o = ldg16(rowO + j0);
-                            if (p.disk_mode != 1) i = ldg16(rowI + j0);
-                            if (p.disk_mode != 1 && cs17) pq = ldg16(rowP + j0);
+                            if (j0 < p.strideD) {
+                                if (p.disk_mode != 2) o = ldg16(rowO + j0);
+                                if (p.disk_mode != 1) i = ldg16(rowI + j0);
+                                if (p.disk_mode != 1 && cs17) pq = ldg16(rowP + j0);
+                            }
 #pragma unroll
                             for (int k = 0; k < NPL; ++k) {
                                 real v = a_d * o.v[k] + c1 * i.v[k]; // absent terms are zero
                                 if (p.disk_mode != 1 && cs17) v += c2 * pq.v[k];
                                 if (p.apply_igm && j0 + k < p.igmD[3])
                                     v *= igm_factor<real>(j0 + k, p.igmD[0], p.igmD[1], p.igmD[2], p.igmD[3], g0f, g1f, g2f);
-                                if (j0 + k < nD) __stcg(SD + (size_t)(j0 + k) * kLanes + lane, v);
+                                if (j0 + k <= nD + 1) __stcg(SD + (size_t)(j0 + k) * kLanes + lane, j0 + k < nD ? v : real(0));
                             }
                         }
                     }
-                    if (has_bulge) {
+                    if (has_bulge && on1 >= on0) {
                         const real *rowB = rB + (size_t)rb * p.strideB;
-                        const int jend = on1 >= on0 ? min(on1 + 1, p.strideB) : 0;
-                        for (int j0 = on1 >= on0 ? (on0 & ~3) : 0; j0 < jend; j0 += NPL) {
-                            const Vec16<real> o = ldg16(rowB + j0);
+                        const int jb0 = max(on0 - 2, 0) & ~3, jb1 = min(on1 + 2, nB + 1);
+                        for (int j0 = jb0; j0 <= jb1; j0 += NPL) {
+                            Vec16<real> o;
+#pragma unroll
+                            for (int k = 0; k < NPL; ++k) o.v[k] = real(0);
+                            if (j0 < p.strideB) o = ldg16(rowB + j0);
 #pragma unroll
                             for (int k = 0; k < NPL; ++k) {
                                 real v = o.v[k];
                                 if (p.apply_igm && j0 + k < p.igmB[3])
                                     v *= igm_factor<real>(j0 + k, p.igmB[0], p.igmB[1], p.igmB[2], p.igmB[3], g0f, g1f, g2f);
-                                if (j0 + k < nB) __stcg(SB + (size_t)(j0 + k) * kLanes + lane, v);
+                                if (j0 + k <= nB + 1) __stcg(SB + (size_t)(j0 + k) * kLanes + lane, j0 + k < nB ? v : real(0));
                             }
                         }
                     }
@@ -567,7 +579,7 @@ __global__ void __launch_bounds__(NT, 1) lane_flux_kernel(const __grid_constant_
                                 obn = ((grid_o(grid[jo1]) - ob0 + 1) << 8) / (je - js + 1);
                             }
                         }
-                        walk_dev<real>(B, grid, opz, bulge, jlo, jhi, js, je, SD + lane, SB + lane, ob0, obn, totd, totb);
+                        walk_dev<real>(B, grid, gx_sa, opz, bulge, js, je, SD + lane, SB + lane, ob0, obn, totd, totb);
                     }
                     __stcg(RES + (size_t)(fb * 2 + 1) * kLanes + lane, totd);
                     __stcg(RES + (size_t)(fb * 2) * kLanes + lane, totb);
@@ -618,7 +630,7 @@ __global__ void __launch_bounds__(NT, 1) lane_flux_kernel(const __grid_constant_
 #endif
 constexpr int kLaneThreads = EGG_LANE_THREADS;
 
-size_t lane_smem_bytes(const LaneParams &q) { return (q.fp.max_blob + 127) & ~size_t(127); }
+size_t lane_smem_bytes(const LaneParams &q) { return ((q.fp.max_blob + 127) & ~size_t(127)) + (size_t)(q.fp.nD + 2) * 16; }
 
 template <typename real> int launch_lane(const LaneParams &q, int blocks, cudaStream_t st) {
     const size_t smem = lane_smem_bytes(q);

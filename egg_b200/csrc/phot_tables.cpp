@@ -586,7 +586,7 @@ Status build_lane_tables(Prepared &P, const eggphot_opts &opts) {
     // ---- band tables in groups
     size_t budget = opts.smem_table_budget;
     if (!budget) {
-        budget = kSmemPerCta - kLaneFixedSmem;
+        budget = kSmemPerCta - kLaneFixedSmem - ((size_t)(nD + 2) * 16 + 128); // the grid's {x, idxp} live behind the tables
     }
     // a filter whose table exceeds the budget is cut at filter nodes into pieces that feed the same output column
     std::vector<BandTable2> tabs;
