@@ -215,17 +215,26 @@ __device__ __forceinline__ void walk_dev(const BandDev &B, const GridNode *__res
     double Eprev_d = 0.0, Eprev_b = 0.0;
     real Sprev_d = real(0), Sprev_b = real(0), accd = real(0), accb = real(0);
     double td = 0.0, tb = 0.0;
-    int kb = 0; // block of the optical node the next bulge interval settles
+    int kb = 0;           // block of the optical node the next bulge interval settles
+    int jo_prev = -1;     // the last optical node the walk arrived at
+    int o_run = ob0 - 1;  // its index in the bulge grid (optical nodes are met in order)
+    bool prev_opt = false; // node j - 1 is an optical node
     // one arrival: P = state of node j - 1, C receives the state of node j
     auto step = [&](const NodeSt &P, NodeSt &C, int j) {
-        // {x, idxp} from shared memory (the sign of idxp flags an optical node); the rest of the node's record is needed
-        // for the bulge only
+        // {x, idxp} from shared memory; the sign of idxp flags an optical node
         const double2 gx = lds_v2f64(gx_sa + 16u * (uint32_t)j);
-        const bool optical = __double2hiint(gx.y) < 0;
+        const bool optical = bulge && __double2hiint(gx.y) < 0;
         const double t = opz * gx.x; // the reference's lam = rlam * (1 + z) (src/egg-gencat.cpp:2161), in double
+        // the bulge interval that ends here starts at the last optical node: the previous node (then it is the disk interval
+        // too) or an earlier one, whose state was kept when the walk left it
+        const bool own_interval = optical && !prev_opt;
+        const double idxpo = own_interval ? __ldg(&grid[j].idxpo) : 0.0;
+        if (bulge && !optical && prev_opt) so = P;
         // Nodes outside the band's window need no mask: every interval next to them lies outside the span for every lane of
         // the batch, so their weights are exactly 0 (and the rows the walk can touch are always built: finite values).
         const real Sd = __ldcg(sd + (size_t)j * kLanes);
+        real Sb = real(0);
+        if (optical) { ++o_run; Sb = __ldcg(sb + (size_t)o_run * kLanes); }
         // filter cell of t
         int k = round_lo(fma(t, B.bk_scale, B.bk_c0));
         k = min(max(k, 0), B.nbkt_m1);
@@ -252,20 +261,17 @@ __device__ __forceinline__ void walk_dev(const BandDev &B, const GridNode *__res
         Eprev_d = Eadj_d;
         Sprev_d = Sd;
         // bulge: its SED intervals run between optical nodes
-        if (bulge && optical) {
-            const double2 gzw = __ldg(reinterpret_cast<const double2 *>(grid + j) + 1); // idxpo, {o, po}
-            const int go = __double2loint(gzw.y), gpo = __double2hiint(gzw.y);
-            const real Sb = __ldcg(sb + (size_t)(go & (kNextNotOptical - 1)) * kLanes);
-            double E_b, Eadj_b;
-            if (gpo == j - 1 && j > js) { E_b = E_d; Eadj_b = Eadj_d; } // the interval is a disk interval too
-            else { int dummy; E_b = interval_dev(B, so, r, u, Lin, q0b.x, q0b.y, hs, t, gzw.x, opz, Eadj_b, dummy); }
-            const int kprev = gpo >> 6; // block of the optical node this interval settles (-1 >> 6 = -1: none yet)
+        if (optical) {
+            double E_b = E_d, Eadj_b = Eadj_d;
+            if (own_interval) { int dummy; E_b = interval_dev(B, so, r, u, Lin, q0b.x, q0b.y, hs, t, idxpo, opz, Eadj_b, dummy); }
+            const int kprev = jo_prev >> 6; // block of the optical node this interval settles (-1: none yet)
             if (kprev != kb) { tb += (double)accb; accb = real(0); kb = kprev; }
             accb = fma(to_real<real>(E_b - Eprev_b), Sprev_b, accb);
             Eprev_b = Eadj_b;
             Sprev_b = Sb;
-            if (go & kNextNotOptical) so = C; // the next bulge interval does not start as a disk interval
+            jo_prev = j;
         }
+        prev_opt = optical;
     };
     // rows of the first nodes, one per lane (a row is 32 lanes x sizeof(real): one or two 128-byte lines)
     const int lane = threadIdx.x & 31;
@@ -625,26 +631,32 @@ __global__ void __launch_bounds__(NT, 1) lane_flux_kernel(const __grid_constant_
     }
 }
 
-#ifndef EGG_LANE_THREADS
-#define EGG_LANE_THREADS 512
-#endif
-constexpr int kLaneThreads = EGG_LANE_THREADS;
+// Warps per CTA trade registers per thread (128 at 16 warps, 80 at 24) against batches in flight; both are built and
+// EGGPHOT_LANE_THREADS (512 | 768) selects one for experiments.
+static int lane_threads() {
+    static int nt = [] {
+        const char *e = getenv("EGGPHOT_LANE_THREADS");
+        const int v = e ? atoi(e) : 0;
+        return v == 768 ? 768 : 512;
+    }();
+    return nt;
+}
 
 size_t lane_smem_bytes(const LaneParams &q) { return ((q.fp.max_blob + 127) & ~size_t(127)) + (size_t)(q.fp.nD + 2) * 16; }
 
-template <typename real> int launch_lane(const LaneParams &q, int blocks, cudaStream_t st) {
+template <typename real, int NT> int launch_lane(const LaneParams &q, int blocks, cudaStream_t st) {
     const size_t smem = lane_smem_bytes(q);
-    cudaError_t e = cudaFuncSetAttribute(lane_flux_kernel<real, kLaneThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(lane_flux_kernel<real, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    lane_flux_kernel<real, kLaneThreads><<<blocks, kLaneThreads, smem, st>>>(q);
+    lane_flux_kernel<real, NT><<<blocks, NT, smem, st>>>(q);
     return (int)cudaGetLastError();
 }
 
-template <typename real> int lane_occupancy(const LaneParams &q) {
+template <typename real, int NT> int lane_occupancy(const LaneParams &q) {
     const size_t smem = lane_smem_bytes(q);
     int nb = 0;
-    cudaError_t e = cudaFuncSetAttribute(lane_flux_kernel<real, kLaneThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lane_flux_kernel<real, kLaneThreads>, kLaneThreads, smem);
+    cudaError_t e = cudaFuncSetAttribute(lane_flux_kernel<real, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lane_flux_kernel<real, NT>, NT, smem);
     return e == cudaSuccess ? nb : -(int)e;
 }
 
@@ -653,7 +665,8 @@ template <typename real> int lane_occupancy(const LaneParams &q) {
 size_t lane_kernel_smem(const LaneParams &q) { return lane_smem_bytes(q); }
 
 int lane_kernel_max_blocks_per_sm(const LaneParams &q, int precision) {
-    return precision == EGGPHOT_FP64 ? lane_occupancy<double>(q) : lane_occupancy<float>(q);
+    if (lane_threads() == 768) return precision == EGGPHOT_FP64 ? lane_occupancy<double, 768>(q) : lane_occupancy<float, 768>(q);
+    return precision == EGGPHOT_FP64 ? lane_occupancy<double, 512>(q) : lane_occupancy<float, 512>(q);
 }
 
 int launch_zsort(const float *z, uint32_t ngal, uint32_t *hist, uint32_t *perm, int num_sms, cudaStream_t st) {
@@ -698,10 +711,12 @@ int measure_fma_peak(int num_sms, void *scratch, cudaStream_t st, double *fp32_t
     return e;
 }
 
-int lane_kernel_threads() { return kLaneThreads; }
+int lane_kernel_threads() { return lane_threads(); }
 
 int launch_lane_flux_kernel(const LaneParams &q, int precision, int grid_blocks, cudaStream_t stream) {
-    return precision == EGGPHOT_FP64 ? launch_lane<double>(q, grid_blocks, stream) : launch_lane<float>(q, grid_blocks, stream);
+    if (lane_threads() == 768)
+        return precision == EGGPHOT_FP64 ? launch_lane<double, 768>(q, grid_blocks, stream) : launch_lane<float, 768>(q, grid_blocks, stream);
+    return precision == EGGPHOT_FP64 ? launch_lane<double, 512>(q, grid_blocks, stream) : launch_lane<float, 512>(q, grid_blocks, stream);
 }
 
 } // namespace eggphot
