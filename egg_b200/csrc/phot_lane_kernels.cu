@@ -160,41 +160,42 @@ template <typename real> __device__ __forceinline__ real to_real(double v);
 template <> __device__ __forceinline__ float to_real<float>(double v) { return (float)v; }
 template <> __device__ __forceinline__ double to_real<double>(double v) { return v; }
 
-// The interval p -> node at t (cell r, expansions u / Lin, cell constants k0, hr, hs) crosses at least one split: add the
-// gauge jumps to d, return D summed over the crossed splits, and find the next split at or after r.
-__device__ __noinline__ double cross_splits(const BandDev &B, int pr, int r, double t, double &d, int &nsr) {
-    double dsum = 0.0;
-    nsr = 0x7fffffff;
-    for (int s = B.nsplit - 1; s >= 0; --s) {
-        const uint32_t hb = B.hdr;
+// The interval from a node in cell pr to a node at t in cell r crosses at least one split: the gauge jumps to add to the
+// difference of the expansions, D summed over the crossed splits, and the next split at or after r.  (Returned by value:
+// a reference parameter of a function that is not inlined would pin the walk's state in local memory.)
+struct Cross { double dadd, dsum; int nsr; };
+__device__ __noinline__ Cross cross_splits(uint32_t hb, int nsplit, int pr, int r, double t) {
+    Cross c{0.0, 0.0, 0x7fffffff};
+    for (int s = nsplit - 1; s >= 0; --s) {
         int ms;
         asm("ld.shared.s32 %0, [%1];" : "=r"(ms) : "r"(hb + (uint32_t)offsetof(BandHeader2, msplit) + 4u * s));
-        if (ms >= r) nsr = ms;
+        if (ms >= r) c.nsr = ms;
         if (pr <= ms && r > ms) {
             const double C = lds_f64(hb + (uint32_t)offsetof(BandHeader2, splitC) + 8u * s);
             const double D = lds_f64(hb + (uint32_t)offsetof(BandHeader2, splitD) + 8u * s);
             const double F = lds_f64(hb + (uint32_t)offsetof(BandHeader2, splitF) + 8u * s);
-            d += fma(D, t - F, C);
-            dsum += D;
+            c.dadd += fma(D, t - F, C);
+            c.dsum += D;
         }
     }
-    return dsum;
+    return c;
 }
 
 // E of the interval p -> node at t, in the gauge of p's region; Eadj = the same quantity in the gauge of the node's region
-__device__ __forceinline__ double interval_dev(const BandDev &B, const NodeSt &p, int r, double u, double Lin, double k0, double hr,
-                                               double hs, double t, double idx, double opz, double &Eadj, int &nsr) {
-    nsr = p.nsr;
-    if (r == p.r) {
-        const double E = opz * fma(hs * p.u, u, fma(p.u + u, hr, k0));
+__device__ __forceinline__ double interval_dev(const BandDev &B, double pu, double pLout, int pr, int pnsr, int r, double u, double Lin,
+                                               double k0, double hr, double hs, double t, double idx, double opz, double &Eadj, int &nsr) {
+    nsr = pnsr;
+    if (r == pr) {
+        const double E = opz * fma(hs * pu, u, fma(pu + u, hr, k0));
         Eadj = E;
         return E;
     }
-    double d = Lin - p.Lout;
-    if (r > p.nsr) { // crosses a split (once or twice per band)
-        const double dsum = cross_splits(B, p.r, r, t, d, nsr);
-        const double E = d * idx;
-        Eadj = E - dsum * opz;
+    const double d = Lin - pLout;
+    if (r > pnsr) { // crosses a split (once or twice per band)
+        const Cross c = cross_splits(B.hdr, B.nsplit, pr, r, t);
+        nsr = c.nsr;
+        const double E = (d + c.dadd) * idx;
+        Eadj = E - c.dsum * opz;
         return E;
     }
     const double E = d * idx;
@@ -256,14 +257,16 @@ __device__ __forceinline__ void walk_dev(const BandDev &B, const GridNode *__res
         // disk: close [j - 1, j], settle node j - 1 (the block sums are flushed when node j - 1 starts a new block)
         if (((j - 1) & (kLaneBlock - 1)) == 0) { td += (double)accd; accd = real(0); }
         double Eadj_d;
-        const double E_d = interval_dev(B, P, r, u, Lin, q0b.x, q0b.y, hs, t, fabs(gx.y), opz, Eadj_d, C.nsr);
+        int nsr_c;
+        const double E_d = interval_dev(B, P.u, P.Lout, P.r, P.nsr, r, u, Lin, q0b.x, q0b.y, hs, t, fabs(gx.y), opz, Eadj_d, nsr_c);
+        C.nsr = nsr_c;
         accd = fma(to_real<real>(E_d - Eprev_d), Sprev_d, accd);
         Eprev_d = Eadj_d;
         Sprev_d = Sd;
         // bulge: its SED intervals run between optical nodes
         if (optical) {
             double E_b = E_d, Eadj_b = Eadj_d;
-            if (own_interval) { int dummy; E_b = interval_dev(B, so, r, u, Lin, q0b.x, q0b.y, hs, t, idxpo, opz, Eadj_b, dummy); }
+            if (own_interval) { int dummy; E_b = interval_dev(B, so.u, so.Lout, so.r, so.nsr, r, u, Lin, q0b.x, q0b.y, hs, t, idxpo, opz, Eadj_b, dummy); }
             const int kprev = jo_prev >> 6; // block of the optical node this interval settles (-1: none yet)
             if (kprev != kb) { tb += (double)accb; accb = real(0); kb = kprev; }
             accb = fma(to_real<real>(E_b - Eprev_b), Sprev_b, accb);
