@@ -38,7 +38,6 @@
 
 namespace eggphot {
 
-constexpr int kLaneBlock = 64;   // SED nodes per work item: block k holds nodes [64 k, 64 k + 63]
 constexpr int kLanes = 32;       // galaxies per batch (one per lane)
 
 // One record per filter node: wavelength, Lambda and K0 at the node in the gauge of the record, R / 2 of the node.
@@ -181,22 +180,24 @@ EGG_HD double interval_E(const Band2 &b, const NodeEv &p, const NodeEv &e, doubl
     return d * idx;
 }
 
-// Weighted sums of one block of SED nodes for one galaxy: accd += sum_{j in [a, b]} Sd_j W_j over the disk nodes and
-// accb += sum over the optical nodes among them of Sb_o W^b_o.  The walk arrives at nodes js..je (js <= a - 1 unless
-// a = 0, je >= b + 1; wide enough that the optical node before the first and after the last optical node of [a, b] are
-// visited): arriving at node j closes the interval [j-1, j] and settles the weight of node j-1.  grid has virtual nodes
-// after the last real one (far to the red, flagged optical) so that je = b + 1 always exists.  The walk starts from a
-// state blue of every filter: the first interval it closes weighs nothing it accumulates (its left node is before a,
-// or it is the first node of the grid, whose idxp is 0).
+// Weighted sums of one band table for one galaxy: totd = sum_j Sd_j W_j over the disk nodes and totb = sum over the
+// optical nodes of Sb_o W^b_o.  The walk arrives at nodes js..je: arriving at node j closes the interval [j-1, j] and
+// settles the weight of node j-1 (disk), and, at an optical node, closes the bulge interval from the optical node before
+// and settles that one.  js is at or before the node left of the window (and at or before the optical node left of it),
+// je at or after the node right of it: every node outside the window has the weight 0 exactly for every galaxy of the
+// batch, so the window may be wider than a galaxy needs.  The walk starts from a state blue of every filter.  Terms are
+// summed in `real` over strips of 16 arrivals cut at absolute node numbers ((16 k, 16 k + 16]) and the strips added in
+// double: the sums do not depend on where the walk starts.
+constexpr int kLaneStrip = 16;
 template <typename real, typename Sed>
-EGG_HD void walk_block(const Band2 &bv, const GridNode *grid, double opz, bool bulge, int a, int b, int js, int je,
-                       const Sed &sed, real &accd, real &accb) {
+EGG_HD void walk_window(const Band2 &bv, const GridNode *grid, double opz, bool bulge, int js, int je, const Sed &sed,
+                        double &totd, double &totb) {
     NodeEv prev, prevo, cur;
     prev.u = 0.0; prev.Lin = 0.0; prev.Lout = 0.0; prev.k0 = 0.0; prev.hr = 0.0; prev.hs = 0.0; prev.r = -1;
     prevo = prev;
     double Eprev_d = 0.0, Eprev_b = 0.0;
-    real Sprev_d = real(0), Sprev_b = real(0);
-    int jprevo = -1;
+    real Sprev_d = real(0), Sprev_b = real(0), accd = real(0), accb = real(0);
+    totd = 0.0; totb = 0.0;
     for (int j = js; j <= je; ++j) {
         const GridNode g = grid[j];
         const double t = opz * g.x; // the reference's lam = rlam * (1 + z) (src/egg-gencat.cpp:2161), in double
@@ -204,18 +205,22 @@ EGG_HD void walk_block(const Band2 &bv, const GridNode *grid, double opz, bool b
         const real Sd = sed.disk(j);
         double jump_d;
         const double E_d = interval_E(bv, prev, cur, t, g.idxp, opz, jump_d);
-        if (j - 1 >= a && j - 1 <= b) accd = fma((real)(E_d - Eprev_d), Sprev_d, accd);
+        accd = fma((real)(E_d - Eprev_d), Sprev_d, accd);
         Eprev_d = E_d - jump_d;
         if (bulge && g.o >= 0) {
             const real Sb = sed.bulge(grid_o(g));
             double E_b, jump_b;
             if (g.po == j - 1 && j > js) { E_b = E_d; jump_b = jump_d; } // the interval is a disk interval too
             else E_b = interval_E(bv, prevo, cur, t, g.idxpo, opz, jump_b);
-            if (jprevo >= a && jprevo <= b) accb = fma((real)(E_b - Eprev_b), Sprev_b, accb);
+            accb = fma((real)(E_b - Eprev_b), Sprev_b, accb);
             Eprev_b = E_b - jump_b;
-            prevo = cur; Sprev_b = Sb; jprevo = j;
+            prevo = cur; Sprev_b = Sb;
         }
         prev = cur; Sprev_d = Sd;
+        if ((j & (kLaneStrip - 1)) == 0 || j == je) {
+            totd += (double)accd; accd = real(0);
+            totb += (double)accb; accb = real(0);
+        }
     }
 }
 

@@ -108,7 +108,6 @@ __device__ __forceinline__ void st_keep(double *p, double v, uint64_t pol) {
 }
 // The SED rows of a batch live in HBM by the time the bands read them (16 batches per SM are in flight): every trip of
 // the walk asks L2 for the rows it will need kPrefetchRows nodes later, so that the loads themselves hit L2.
-constexpr int kPrefetchRows = 16;
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // shared-memory loads by 32-bit shared address (all address arithmetic of the walk stays in 32 bits)
@@ -216,9 +215,7 @@ __device__ __forceinline__ void walk_dev(const BandDev &B, const GridNode *__res
     double Eprev_d = 0.0, Eprev_b = 0.0;
     real Sprev_d = real(0), Sprev_b = real(0), accd = real(0), accb = real(0);
     double td = 0.0, tb = 0.0;
-    int kb = 0;           // block of the optical node the next bulge interval settles
-    int jo_prev = -1;     // the last optical node the walk arrived at
-    int o_run = ob0 - 1;  // its index in the bulge grid (optical nodes are met in order)
+    int o_run = ob0 - 1;   // index in the bulge grid of the last optical node the walk arrived at (they are met in order)
     bool prev_opt = false; // node j - 1 is an optical node
     // one arrival: P = state of node j - 1, C receives the state of node j
     auto step = [&](const NodeSt &P, NodeSt &C, int j) {
@@ -230,7 +227,10 @@ __device__ __forceinline__ void walk_dev(const BandDev &B, const GridNode *__res
         // too) or an earlier one, whose state was kept when the walk left it
         const bool own_interval = optical && !prev_opt;
         const double idxpo = own_interval ? __ldg(&grid[j].idxpo) : 0.0;
-        if (bulge && !optical && prev_opt) so = P;
+        if (bulge && !optical && prev_opt) { // (warp-uniform: a property of the grid)
+            asm volatile("" ::: "memory");     // keep it a branch: predicated copies would run at every node
+            so = P;
+        }
         // Nodes outside the band's window need no mask: every interval next to them lies outside the span for every lane of
         // the batch, so their weights are exactly 0 (and the rows the walk can touch are always built: finite values).
         const real Sd = __ldcg(sd + (size_t)j * kLanes);
@@ -254,8 +254,7 @@ __device__ __forceinline__ void walk_dev(const BandDev &B, const GridNode *__res
         C.u = u;
         C.Lout = fma(v, fma(v, q1b.y, q1b.x), q1a.y);
         C.r = r;
-        // disk: close [j - 1, j], settle node j - 1 (the block sums are flushed when node j - 1 starts a new block)
-        if (((j - 1) & (kLaneBlock - 1)) == 0) { td += (double)accd; accd = real(0); }
+        // disk: close [j - 1, j], settle node j - 1
         double Eadj_d;
         int nsr_c;
         const double E_d = interval_dev(B, P.u, P.Lout, P.r, P.nsr, r, u, Lin, q0b.x, q0b.y, hs, t, fabs(gx.y), opz, Eadj_d, nsr_c);
@@ -263,38 +262,44 @@ __device__ __forceinline__ void walk_dev(const BandDev &B, const GridNode *__res
         accd = fma(to_real<real>(E_d - Eprev_d), Sprev_d, accd);
         Eprev_d = Eadj_d;
         Sprev_d = Sd;
-        // bulge: its SED intervals run between optical nodes
+        // bulge: its SED intervals run between optical nodes; the interval that ends here settles the optical node before
         if (optical) {
             double E_b = E_d, Eadj_b = Eadj_d;
             if (own_interval) { int dummy; E_b = interval_dev(B, so.u, so.Lout, so.r, so.nsr, r, u, Lin, q0b.x, q0b.y, hs, t, idxpo, opz, Eadj_b, dummy); }
-            const int kprev = jo_prev >> 6; // block of the optical node this interval settles (-1: none yet)
-            if (kprev != kb) { tb += (double)accb; accb = real(0); kb = kprev; }
             accb = fma(to_real<real>(E_b - Eprev_b), Sprev_b, accb);
             Eprev_b = Eadj_b;
             Sprev_b = Sb;
-            jo_prev = j;
         }
         prev_opt = optical;
     };
-    // rows of the first nodes, one per lane (a row is 32 lanes x sizeof(real): one or two 128-byte lines)
     const int lane = threadIdx.x & 31;
-    constexpr int kLinesPerRow = (int)sizeof(real) / 4;
-    if (lane < kPrefetchRows * kLinesPerRow) {
-        prefetch_l2(reinterpret_cast<const char *>(sd - lane + (size_t)js * kLanes) + 128 * lane);
-        if (bulge && ob0 >= 0) prefetch_l2(reinterpret_cast<const char *>(sb - lane + (size_t)ob0 * kLanes) + 128 * lane);
-    }
-    // two arrivals per trip, the two states swapping roles (no register moves); an odd count runs one node past je,
-    // which weighs nothing in range (the grid has two virtual nodes behind the last real one)
-    for (int j = js; j <= je; j += 2) {
-        if (lane < 2 * kLinesPerRow) { // the two rows this trip will need kPrefetchRows nodes later (past the end: harmless)
-            prefetch_l2(reinterpret_cast<const char *>(sd - lane + (size_t)(j + kPrefetchRows) * kLanes) + 128 * lane);
-            if (bulge) prefetch_l2(reinterpret_cast<const char *>(sb - lane + (size_t)(ob0 + ((j - js) * obn >> 8) + kPrefetchRows) * kLanes) + 128 * lane);
+    constexpr int kLinesPerRow = (int)sizeof(real) / 4; // a row is 32 lanes x sizeof(real): one or two 128-byte lines
+    const char *sd_rows = reinterpret_cast<const char *>(sd - lane) + 128 * lane, *sb_rows = reinterpret_cast<const char *>(sb - lane) + 128 * lane;
+    // the rows of the first strip, one line per lane
+    if (lane < kLaneStrip * kLinesPerRow) prefetch_l2(sd_rows + (size_t)js * (kLanes * sizeof(real)));
+    if (bulge && ob0 >= 0) prefetch_l2(sb_rows + (size_t)ob0 * (kLanes * sizeof(real)));
+    // trips start at odd nodes: a strip of 16 arrivals (16 k, 16 k + 16] is then eight whole trips
+    int j = js;
+    if ((j & 1) == 0) { step(s0, s1, j); s0 = s1; ++j; }
+    while (j <= je) {
+        const int jend = (j + kLaneStrip - 1) & ~(kLaneStrip - 1); // last arrival of the strip
+        // ask L2 for the rows of the next strip (the SED rows of a batch live in HBM by the time the bands read them)
+        if (lane < kLaneStrip * kLinesPerRow) prefetch_l2(sd_rows + (size_t)(jend + 1) * (kLanes * sizeof(real)));
+        if (bulge) prefetch_l2(sb_rows + (size_t)(o_run + 1 + kLaneStrip / 2) * (kLanes * sizeof(real)));
+        // two arrivals per trip, the two states swapping roles (no register moves); the last trip may run one node past je,
+        // which weighs nothing (the grid has two virtual nodes behind the last real one)
+#pragma unroll 1
+        for (; j <= min(jend, je); j += 2) {
+            step(s0, s1, j);
+            step(s1, s0, j + 1);
         }
-        step(s0, s1, j);
-        step(s1, s0, j + 1);
+        // the sums of a strip are formed in `real`, the strips added in double: strips are cut at absolute node numbers, so
+        // the result does not depend on where the walk started
+        td += (double)accd; accd = real(0);
+        tb += (double)accb; accb = real(0);
     }
-    totd = td + (double)accd;
-    totb = tb + (double)accb;
+    totd = td;
+    totb = tb;
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------

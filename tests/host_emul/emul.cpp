@@ -321,17 +321,14 @@ void run2(const Prepared &P, const eggphot_galaxies &G, size_t ngal, double *fd,
                 int jhi = (int)(std::lower_bound(P.grid_disk.x.begin(), P.grid_disk.x.end(), xhi) - P.grid_disk.x.begin());
                 jhi = std::min(jhi, nD - 1);
                 if (P.has_bulge) widen_window_for_bulge(grid, P.next_opt.data(), nD, jlo, jhi);
-                for (int k = jlo / kLaneBlock; k <= jhi / kLaneBlock; ++k) {
-                    const int a = std::max(jlo, k * kLaneBlock), b = std::min(jhi, k * kLaneBlock + kLaneBlock - 1);
-                    int js, je;
-                    block_arrivals(grid, P.next_opt.data(), P.has_bulge, a, b, js, je);
-                    for (int l = 0; l < ng; ++l) {
-                        real accd = 0, accb = 0;
-                        SedRef<real> sr{SD[l].data(), SB[l].data()};
-                        walk_block<real>(bv, grid, opz[l], P.has_bulge, a, b, js, je, sr, accd, accb);
-                        resd[h.out_col * kLanes + l] += (double)accd;
-                        resb[h.out_col * kLanes + l] += (double)accb;
-                    }
+                int js, je;
+                block_arrivals(grid, P.next_opt.data(), P.has_bulge, jlo, jhi, js, je);
+                for (int l = 0; l < ng; ++l) {
+                    double td, tb;
+                    SedRef<real> sr{SD[l].data(), SB[l].data()};
+                    walk_window<real>(bv, grid, opz[l], P.has_bulge, js, je, sr, td, tb);
+                    resd[h.out_col * kLanes + l] += td;
+                    resb[h.out_col * kLanes + l] += tb;
                 }
             }
         }
