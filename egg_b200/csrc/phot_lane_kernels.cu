@@ -312,13 +312,13 @@ __global__ void __launch_bounds__(NT, 1) lane_flux_kernel(const __grid_constant_
     __shared__ __align__(8) uint64_t bar_tab;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = NT / 32;
+    const int NW = (int)blockDim.x >> 5; // warps of this launch (the host picks the count that fills the last round best)
     const int nbt = (int)p.nband_total, ntab = (int)q.ntab, nrf = p.do_rf ? (int)p.nrf : 0;
     const int nD = p.nD, nB = p.nB, nline = p.nline;
     const uint8_t *blob = smem;
     const bool cs17 = p.ir_kind == EGGPHOT_IR_CS17;
     const bool has_bulge = p.has_bulge != 0;
-    uint8_t *wbase = reinterpret_cast<uint8_t *>(p.scratch) + ((size_t)blockIdx.x * NW + warp) * q.scratch_stride;
+    uint8_t *wbase = reinterpret_cast<uint8_t *>(p.scratch) + ((size_t)blockIdx.x * (NT / 32) + warp) * q.scratch_stride;
     real *SD = reinterpret_cast<real *>(wbase);
     real *SB = SD + (size_t)(nD + 2) * kLanes;
     double *RES = reinterpret_cast<double *>(wbase + q.res_offset);
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(NT, 1) lane_flux_kernel(const __grid_constant_
     // behind the band tables: {x, idxp} of every node of the disk grid, idxp negated at optical nodes
     double2 *gxs = reinterpret_cast<double2 *>(smem + ((p.max_blob + 127) & ~127u));
     const uint32_t gx_sa = smem_u32(gxs);
-    for (int j = tid; j < nD + 2; j += NT) gxs[j] = make_double2(grid[j].x, grid[j].o >= 0 ? -grid[j].idxp : grid[j].idxp);
+    for (int j = tid; j < nD + 2; j += (int)blockDim.x) gxs[j] = make_double2(grid[j].x, grid[j].o >= 0 ? -grid[j].idxp : grid[j].idxp);
 
     if (tid == 0) {
         mbar_init(&bar_tab, 1);
@@ -462,7 +462,8 @@ __global__ void __launch_bounds__(NT, 1) lane_flux_kernel(const __grid_constant_
                     if (jn1 >= jn0) {
                         const real *rowO = rO + (size_t)rd * p.strideD, *rowI = rI + (size_t)ri * p.strideD, *rowP = rP + (size_t)ri * p.strideD;
                         const int jb0 = max(jn0 - (int)q.row_margin, 0) & ~3, jb1 = min(jn1 + (int)q.row_margin, nD + 1);
-                        for (int j0 = jb0; j0 <= jb1; j0 += NPL) {
+#pragma unroll 4
+                        for (int j0 = jb0; j0 <= jb1; j0 += NPL) { // (unrolled: a dozen row loads in flight)
                             Vec16<real> o, i, pq;
 #pragma unroll
                             for (int k = 0; k < NPL; ++k) o.v[k] = i.v[k] = pq.v[k] = real(0);
@@ -484,6 +485,7 @@ __global__ void __launch_bounds__(NT, 1) lane_flux_kernel(const __grid_constant_
                     if (has_bulge && on1 >= on0) {
                         const real *rowB = rB + (size_t)rb * p.strideB;
                         const int jb0 = max(on0 - 2, 0) & ~3, jb1 = min(on1 + 2, nB + 1);
+#pragma unroll 4
                         for (int j0 = jb0; j0 <= jb1; j0 += NPL) {
                             Vec16<real> o;
 #pragma unroll
@@ -652,11 +654,18 @@ static int lane_threads() {
 
 size_t lane_smem_bytes(const LaneParams &q) { return ((q.fp.max_blob + 127) & ~size_t(127)) + (size_t)(q.fp.nD + 2) * 16; }
 
+// Every warp takes one batch of 32 galaxies per round and a round lasts as long as its slowest warp: the launch uses the
+// fewest warps (not below three quarters of NT / 32) that still need the fewest rounds, so that the last round is as full
+// as it can be and the warps share the SM with as few others as possible.
 template <typename real, int NT> int launch_lane(const LaneParams &q, int blocks, cudaStream_t st) {
     const size_t smem = lane_smem_bytes(q);
     cudaError_t e = cudaFuncSetAttribute(lane_flux_kernel<real, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    lane_flux_kernel<real, NT><<<blocks, NT, smem, st>>>(q);
+    const uint64_t nbatch = (q.fp.ngal + kLanes - 1) / kLanes, per_cta = (nbatch + blocks - 1) / blocks;
+    int nw = NT / 32;
+    const uint64_t rounds = (per_cta + nw - 1) / nw;
+    while (nw - 1 >= (NT / 32) * 3 / 4 && (per_cta + nw - 2) / (nw - 1) == rounds) --nw;
+    lane_flux_kernel<real, NT><<<blocks, 32 * nw, smem, st>>>(q);
     return (int)cudaGetLastError();
 }
 

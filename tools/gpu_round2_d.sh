@@ -1,7 +1,7 @@
 set -x
 mkdir -p gpurun_out
 timeout 600 python tools/parity_sweep.py b30_rf3_defaults 20000 > gpurun_out/p_b30.txt 2>&1; echo "rc=$?" >> gpurun_out/p_b30.txt; tail -8 gpurun_out/p_b30.txt
-for nt in 512 768; do
+for nt in 512; do
 EGGPHOT_LANE_THREADS=$nt timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_lane_$nt.json 2> gpurun_out/bench_lane_$nt.err; tail -2 gpurun_out/bench_lane_$nt.err
 EGGPHOT_LANE_THREADS=$nt timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e --ngal 2000000 > gpurun_out/bench_lane_2M_$nt.json 2> gpurun_out/bench_lane_2M_$nt.err
 done
