@@ -180,48 +180,38 @@ __device__ __noinline__ Cross cross_splits(uint32_t hb, int nsplit, int pr, int 
     return c;
 }
 
-// E of the interval p -> node at t, in the gauge of p's region; Eadj = the same quantity in the gauge of the node's region.
-// Straight-line code (both forms of E are evaluated and one is selected): the two arrivals of a trip then sit in one
-// basic block and the scheduler overlaps their dependency chains.  ONE_SPLIT: the band has a single split node (two
-// gauge regions, the common case): its jump constants are in registers and crossing it costs two selects; otherwise the
-// rare crossing is a call.
-struct SplitRegs { double C, D, F, Dopz; };
-template <bool ONE_SPLIT>
-__device__ __forceinline__ double interval_dev(const BandDev &B, const SplitRegs &S, double pu, double pLout, int pr, int pnsr, int r, double u,
-                                               double Lin, double k0, double hr, double hs, double t, double idx, double opz, double &Eadj,
-                                               int &nsr) {
-    const double Esame = opz * fma(hs * pu, u, fma(pu + u, hr, k0));
-    double d = Lin - pLout, jump = 0.0;
+// E of the interval p -> node at t, in the gauge of p's region; Eadj = the same quantity in the gauge of the node's region
+__device__ __forceinline__ double interval_dev(const BandDev &B, double pu, double pLout, int pr, int pnsr, int r, double u, double Lin,
+                                               double k0, double hr, double hs, double t, double idx, double opz, double &Eadj, int &nsr) {
     nsr = pnsr;
-    if (ONE_SPLIT) {
-        const bool cross = pr <= B.m0 && r > B.m0;
-        d += cross ? fma(S.D, t - S.F, S.C) : 0.0;
-        jump = cross ? S.Dopz : 0.0;
-    } else if (r > pnsr) { // crosses a split (a few times per band)
+    if (r == pr) {
+        const double E = opz * fma(hs * pu, u, fma(pu + u, hr, k0));
+        Eadj = E;
+        return E;
+    }
+    const double d = Lin - pLout;
+    if (r > pnsr) { // crosses a split (once or twice per band)
         const Cross c = cross_splits(B.hdr, B.nsplit, pr, r, t);
         nsr = c.nsr;
-        d += c.dadd;
-        jump = c.dsum * opz;
+        const double E = (d + c.dadd) * idx;
+        Eadj = E - c.dsum * opz;
+        return E;
     }
-    const double E = r == pr ? Esame : d * idx;
-    Eadj = E - jump;
+    const double E = d * idx;
+    Eadj = E;
     return E;
 }
 
 // Walks nodes js..je of the disk grid for one galaxy (lane) and one band table.
-// ob0 = first optical node at or after js (index in the bulge grid): only for prefetching the bulge rows ahead of the walk.
-template <typename real, bool TWO_PROBE, bool ONE_SPLIT>
+// ob0 = first optical node at or after js (index in the bulge grid), obn = optical nodes per 256 disk nodes of the walk
+// (only for prefetching the bulge rows ahead of the walk).
+// totd / totb receive the sums of the blocks of 64 nodes (each summed in `real`, the blocks added in double, in order:
+// the same numbers whichever way the window is cut).
+template <typename real>
 __device__ __forceinline__ void walk_dev(const BandDev &B, const GridNode *__restrict__ grid, uint32_t gx_sa, double opz, bool bulge,
-                                         int js, int je, const real *__restrict__ sd, const real *__restrict__ sb, int ob0,
+                                         int js, int je, const real *__restrict__ sd, const real *__restrict__ sb, int ob0, int obn,
                                          double &totd, double &totb) {
     NodeSt s0{0.0, 0.0, -1, B.m0}, s1 = s0, so = s0;
-    SplitRegs SR{0.0, 0.0, 0.0, 0.0};
-    if (ONE_SPLIT) {
-        SR.C = lds_f64(B.hdr + (uint32_t)offsetof(BandHeader2, splitC));
-        SR.D = lds_f64(B.hdr + (uint32_t)offsetof(BandHeader2, splitD));
-        SR.F = lds_f64(B.hdr + (uint32_t)offsetof(BandHeader2, splitF));
-        SR.Dopz = SR.D * opz;
-    }
     double Eprev_d = 0.0, Eprev_b = 0.0;
     real Sprev_d = real(0), Sprev_b = real(0), accd = real(0), accb = real(0);
     double td = 0.0, tb = 0.0;
@@ -250,7 +240,7 @@ __device__ __forceinline__ void walk_dev(const BandDev &B, const GridNode *__res
         int k = round_lo(fma(t, B.bk_scale, B.bk_c0));
         k = min(max(k, 0), B.nbkt_m1);
         uint32_t ra = B.rec + 32u * (uint32_t)lds_u16(B.bkt + 2u * (uint32_t)k);
-        if (TWO_PROBE) {
+        if (B.two_probe) {
             ra += t >= lds_f64(ra + 32u) ? 32u : 0u;
             ra += t >= lds_f64(ra + 32u) ? 32u : 0u; // a split node or an abrupt end is two records at one wavelength
         } else {
@@ -267,7 +257,7 @@ __device__ __forceinline__ void walk_dev(const BandDev &B, const GridNode *__res
         // disk: close [j - 1, j], settle node j - 1
         double Eadj_d;
         int nsr_c;
-        const double E_d = interval_dev<ONE_SPLIT>(B, SR, P.u, P.Lout, P.r, P.nsr, r, u, Lin, q0b.x, q0b.y, hs, t, fabs(gx.y), opz, Eadj_d, nsr_c);
+        const double E_d = interval_dev(B, P.u, P.Lout, P.r, P.nsr, r, u, Lin, q0b.x, q0b.y, hs, t, fabs(gx.y), opz, Eadj_d, nsr_c);
         C.nsr = nsr_c;
         accd = fma(to_real<real>(E_d - Eprev_d), Sprev_d, accd);
         Eprev_d = Eadj_d;
@@ -275,10 +265,7 @@ __device__ __forceinline__ void walk_dev(const BandDev &B, const GridNode *__res
         // bulge: its SED intervals run between optical nodes; the interval that ends here settles the optical node before
         if (optical) {
             double E_b = E_d, Eadj_b = Eadj_d;
-            if (own_interval) {
-                int dummy;
-                E_b = interval_dev<ONE_SPLIT>(B, SR, so.u, so.Lout, so.r, so.nsr, r, u, Lin, q0b.x, q0b.y, hs, t, idxpo, opz, Eadj_b, dummy);
-            }
+            if (own_interval) { int dummy; E_b = interval_dev(B, so.u, so.Lout, so.r, so.nsr, r, u, Lin, q0b.x, q0b.y, hs, t, idxpo, opz, Eadj_b, dummy); }
             accb = fma(to_real<real>(E_b - Eprev_b), Sprev_b, accb);
             Eprev_b = Eadj_b;
             Sprev_b = Sb;
@@ -600,15 +587,15 @@ __global__ void __launch_bounds__(NT, 1) lane_flux_kernel(const __grid_constant_
                         B.two_probe = h.two_probe != 0;
                         int js, je;
                         block_arrivals(grid, q.next_opt, bulge, jlo, jhi, js, je);
-                        int ob0 = -1;
-                        if (bulge) { // first optical node the walk visits: for the prefetch of the bulge rows
-                            const int jo0 = grid[js].o >= 0 ? js : q.next_opt[js];
-                            if (jo0 <= je) ob0 = grid_o(grid[jo0]);
+                        int ob0 = -1, obn = 0;
+                        if (bulge) { // optical nodes the walk visits: for the prefetch of the bulge rows
+                            const int jo0 = grid[js].o >= 0 ? js : q.next_opt[js], jo1 = grid[je].o >= 0 ? je : grid[je].po;
+                            if (jo0 <= jo1 && jo1 >= 0) {
+                                ob0 = grid_o(grid[jo0]);
+                                obn = ((grid_o(grid[jo1]) - ob0 + 1) << 8) / (je - js + 1);
+                            }
                         }
-                        const real *sdl = SD + lane, *sbl = SB + lane;
-                        if (B.two_probe && B.nsplit == 1) walk_dev<real, true, true>(B, grid, gx_sa, opz, bulge, js, je, sdl, sbl, ob0, totd, totb);
-                        else if (B.two_probe) walk_dev<real, true, false>(B, grid, gx_sa, opz, bulge, js, je, sdl, sbl, ob0, totd, totb);
-                        else walk_dev<real, false, false>(B, grid, gx_sa, opz, bulge, js, je, sdl, sbl, ob0, totd, totb);
+                        walk_dev<real>(B, grid, gx_sa, opz, bulge, js, je, SD + lane, SB + lane, ob0, obn, totd, totb);
                     }
                     __stcg(RES + (size_t)(fb * 2 + 1) * kLanes + lane, totd);
                     __stcg(RES + (size_t)(fb * 2) * kLanes + lane, totb);
