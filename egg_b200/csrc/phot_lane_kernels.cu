@@ -339,14 +339,14 @@ __global__ void __launch_bounds__(NT, 1) lane_flux_kernel(const __grid_constant_
     uint32_t tab_phase = 0;
     int loaded = -1;
 
-    // the CTA's share of the batches (contiguous: neighbouring redshifts), NW at a time, one per warp
+    // batches are dealt round-robin, NW consecutive ones (neighbouring redshifts) per CTA and round: the cost of a batch
+    // varies with redshift (bands covered, nodes under them), and every CTA gets its share of every redshift
     const uint64_t nbatch = (p.ngal + kLanes - 1) / kLanes;
-    const uint64_t bfirst = nbatch * blockIdx.x / gridDim.x, bend = nbatch * (blockIdx.x + 1) / gridDim.x;
-    const int nround = (int)((bend - bfirst + NW - 1) / NW);
+    const int nround = (int)((nbatch + (uint64_t)gridDim.x * NW - 1) / ((uint64_t)gridDim.x * NW));
     const int ngl = max((int)p.ngroups, 1);
     for (int round = 0; round < nround; ++round) {
-        const uint64_t batch = bfirst + (uint64_t)round * NW + warp;
-        const bool active = batch < bend;
+        const uint64_t batch = ((uint64_t)round * gridDim.x + blockIdx.x) * NW + warp;
+        const bool active = batch < nbatch;
         const uint64_t g0 = batch * kLanes;
         const int ng = active ? (int)min((uint64_t)kLanes, p.ngal - g0) : 0;
         // lanes beyond the end of the catalog repeat the batch's first galaxy (and write nothing)

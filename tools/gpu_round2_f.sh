@@ -4,5 +4,5 @@ timeout 600 python tools/parity_sweep.py b30_rf3_defaults 20000 > gpurun_out/p_b
 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --no-extra > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; tail -2 gpurun_out/bench_quick.err
 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e --no-extra --ngal 2000000 > gpurun_out/bench_2M.json 2> gpurun_out/bench_2M.err
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.txt 2>&1; tail -5 gpurun_out/pytest_gpu.txt
-timeout 1200 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; tail -3 gpurun_out/bench_full.err
+timeout 1200 python bench.py --no-cpu > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; tail -3 gpurun_out/bench_full.err
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:lane_flux_kernel -s 3 -c 1 -o gpurun_out/lane_full -f python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-extra > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log
