@@ -306,7 +306,7 @@ __device__ __forceinline__ void walk_dev(const BandDev &B, const GridNode *__res
 // Per-warp scratch in global memory: SED rows of the disk grid [nD + 2][32], of the bulge grid [nB + 2][32] (reals), then
 // the sums of every band table [ntab][2][32] (doubles).
 template <typename real, int NT>
-__global__ void __launch_bounds__(NT, 1) lane_flux_kernel(const __grid_constant__ LaneParams q) {
+__global__ void __maxnreg__((65536 / NT) & ~7) lane_flux_kernel(const __grid_constant__ LaneParams q) {
     const FluxParams &p = q.fp;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_tab;
@@ -641,13 +641,16 @@ __global__ void __launch_bounds__(NT, 1) lane_flux_kernel(const __grid_constant_
     }
 }
 
-// Warps per CTA trade registers per thread (128 at 16 warps, 80 at 24) against batches in flight; both are built and
-// EGGPHOT_LANE_THREADS (512 | 768) selects one for experiments.
+#ifndef EGG_LANE_THREADS
+#define EGG_LANE_THREADS 512
+#endif
+// Warps per CTA trade registers per thread (128 at 16 warps, 112 at 18, 104 at 19) against batches in flight; the
+// variants are built side by side and EGGPHOT_LANE_THREADS (512 | 576 | 608) selects one.
 static int lane_threads() {
     static int nt = [] {
         const char *e = getenv("EGGPHOT_LANE_THREADS");
         const int v = e ? atoi(e) : 0;
-        return v == 768 ? 768 : 512;
+        return v == 512 ? 512 : (v == 608 ? 608 : (v == 576 ? 576 : EGG_LANE_THREADS));
     }();
     return nt;
 }
@@ -682,8 +685,12 @@ template <typename real, int NT> int lane_occupancy(const LaneParams &q) {
 size_t lane_kernel_smem(const LaneParams &q) { return lane_smem_bytes(q); }
 
 int lane_kernel_max_blocks_per_sm(const LaneParams &q, int precision) {
-    if (lane_threads() == 768) return precision == EGGPHOT_FP64 ? lane_occupancy<double, 768>(q) : lane_occupancy<float, 768>(q);
-    return precision == EGGPHOT_FP64 ? lane_occupancy<double, 512>(q) : lane_occupancy<float, 512>(q);
+    const bool d = precision == EGGPHOT_FP64;
+    switch (lane_threads()) {
+    case 576: return d ? lane_occupancy<double, 576>(q) : lane_occupancy<float, 576>(q);
+    case 608: return d ? lane_occupancy<double, 608>(q) : lane_occupancy<float, 608>(q);
+    default: return d ? lane_occupancy<double, 512>(q) : lane_occupancy<float, 512>(q);
+    }
 }
 
 int launch_zsort(const float *z, uint32_t ngal, uint32_t *hist, uint32_t *perm, int num_sms, cudaStream_t st) {
@@ -731,9 +738,12 @@ int measure_fma_peak(int num_sms, void *scratch, cudaStream_t st, double *fp32_t
 int lane_kernel_threads() { return lane_threads(); }
 
 int launch_lane_flux_kernel(const LaneParams &q, int precision, int grid_blocks, cudaStream_t stream) {
-    if (lane_threads() == 768)
-        return precision == EGGPHOT_FP64 ? launch_lane<double, 768>(q, grid_blocks, stream) : launch_lane<float, 768>(q, grid_blocks, stream);
-    return precision == EGGPHOT_FP64 ? launch_lane<double, 512>(q, grid_blocks, stream) : launch_lane<float, 512>(q, grid_blocks, stream);
+    const bool d = precision == EGGPHOT_FP64;
+    switch (lane_threads()) {
+    case 576: return d ? launch_lane<double, 576>(q, grid_blocks, stream) : launch_lane<float, 576>(q, grid_blocks, stream);
+    case 608: return d ? launch_lane<double, 608>(q, grid_blocks, stream) : launch_lane<float, 608>(q, grid_blocks, stream);
+    default: return d ? launch_lane<double, 512>(q, grid_blocks, stream) : launch_lane<float, 512>(q, grid_blocks, stream);
+    }
 }
 
 } // namespace eggphot
