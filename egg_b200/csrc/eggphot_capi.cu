@@ -79,11 +79,12 @@ struct eggphot_ctx {
     // region, the redshift-bucketing buffers.  EGGPHOT_KERNEL=node selects the node-per-lane kernel of phot_kernels.cu.
     bool use_lane = true;
     std::vector<DevBuf> blobs2;
-    DevBuf gridN, nextOpt, tabCol, colSpan, lane_scratch;
+    DevBuf gridN, nextOpt, tabCol, colSpan;
     DevBuf zhist[kSlots + 1], zperm[kSlots + 1];
+    // per region: SED rows, band-table windows, build ranges, table sums and item counters of one chunk of batches
+    DevBuf lrows[kSlots + 1], lwin[kSlots + 1], lplan[kSlots + 1], lres[kSlots + 1], lcnt[kSlots + 1];
     LaneParams lbase{};
-    int lane_blocks = 0;
-    size_t lane_region_bytes = 0;
+    size_t lane_cap_batches = 0; // batches per chunk (bounds the SED rows of a region)
 
     int fail(int code, const std::string &m) { err = m; return code; }
     int cuda_fail(cudaError_t e, const char *what) {
@@ -173,13 +174,32 @@ int enqueue(eggphot_ctx *c, const eggphot_galaxies &g, size_t ngal, const eggpho
         q.fp = p;
         q.fp.ngroups = ngroups2; q.fp.max_blob = max_blob2;
         for (int k = 0; k < kMaxGroups; ++k) q.fp.groups[k] = groups2[k];
-        q.fp.scratch = (char *)c->lane_scratch.p + (size_t)region * c->lane_region_bytes;
+        q.fp.scratch = nullptr;
         q.perm = (const uint32_t *)c->zperm[region].p;
         int e = launch_zsort(g.z, (uint32_t)ngal, (uint32_t *)c->zhist[region].p, (uint32_t *)c->zperm[region].p, c->num_sms, st);
         if (e != 0) return c->cuda_fail((cudaError_t)e, "redshift bucketing launch");
-        e = launch_lane_flux_kernel(q, c->P.precision, c->lane_blocks, st);
-        if (e != 0) return c->cuda_fail((cudaError_t)e, "flux kernel launch");
-        c->launches += 4;
+        c->launches += 3;
+        // the call is worked off in chunks of batches whose SED rows fit the region's buffer
+        const size_t nbatch = (ngal + kLanes - 1) / kLanes, cap = std::min(nbatch, c->lane_cap_batches);
+        const size_t ntab = std::max<uint32_t>(q.ntab, 1);
+        ce = c->lrows[region].alloc(cap * q.rows_stride + 65536); // (+ room for the L2 prefetches that run past the last row)
+        if (ce == cudaSuccess) ce = c->lwin[region].alloc(cap * 64 * sizeof(uint32_t));
+        if (ce == cudaSuccess) ce = c->lplan[region].alloc(cap * sizeof(int4));
+        if (ce == cudaSuccess) ce = c->lres[region].alloc(cap * ntab * 2 * kLanes * sizeof(double));
+        if (ce == cudaSuccess) ce = c->lcnt[region].alloc(kMaxGroups * sizeof(uint32_t));
+        if (ce != cudaSuccess) return c->cuda_fail(ce, "allocating the chunk buffers of the flux pipeline");
+        q.rows = c->lrows[region].p;
+        q.win = (uint32_t *)c->lwin[region].p;
+        q.plan = (int4 *)c->lplan[region].p;
+        q.res = (double *)c->lres[region].p;
+        q.counters = (uint32_t *)c->lcnt[region].p;
+        for (size_t b0 = 0; b0 < nbatch; b0 += cap) {
+            q.batch0 = b0;
+            q.nbatch = (uint32_t)std::min(cap, nbatch - b0);
+            e = launch_lane_chunk(q, c->P.precision, c->num_sms, st);
+            if (e != 0) return c->cuda_fail((cudaError_t)e, "flux pipeline launch");
+            c->launches += (q.fp.ngroups > 0 && q.ntab > 0) ? 4 : 3;
+        }
         return EGGPHOT_OK;
     }
     const size_t nbatch = (ngal + p.batch - 1) / p.batch;
@@ -416,9 +436,14 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
         }
         {
             const size_t rs = P.precision == EGGPHOT_FP64 ? 8 : 4;
-            const size_t rows = ((size_t)(P.grid_disk.n() + 2) + (size_t)(P.grid_bulge.n() + 2)) * kLanes * rs;
-            q.res_offset = (rows + 255) & ~size_t(255);
-            q.scratch_stride = (q.res_offset + (size_t)std::max<uint32_t>(q.ntab, 1) * 2 * kLanes * sizeof(double) + 255) & ~size_t(255);
+            q.rowsD = (uint32_t)lane_grid_rows(P.grid_disk.n());
+            q.rowsB = (uint32_t)lane_grid_rows(P.grid_bulge.n());
+            q.rows_stride = ((size_t)q.rowsD + q.rowsB) * kLanes * rs;
+            for (int g = 0; g < kMaxGroups; ++g) q.group_cost[g] = 0.f;
+            for (size_t g = 0; g < P.groups2.size(); ++g) {
+                const BandHeader2 *hdr = reinterpret_cast<const BandHeader2 *>(P.groups2[g].blob.data());
+                for (size_t k = 0; k < P.groups2[g].cols.size(); ++k) q.group_cost[g] += std::max(hdr[k].cost, 1.0f);
+            }
         }
         if (c->use_lane) {
             const size_t smem = lane_kernel_smem(q);
@@ -427,9 +452,10 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
                                                          std::to_string(prop.sharedMemPerBlockOptin) + "; lower smem_table_budget");
             const int occ = lane_kernel_max_blocks_per_sm(q, P.precision);
             if (occ <= 0) return c->fail(EGGPHOT_ERR_CUDA, "flux kernel cannot be resident (occupancy query failed)");
-            c->lane_blocks = c->num_sms;
-            c->lane_region_bytes = (size_t)c->lane_blocks * (lane_kernel_threads() / 32) * q.scratch_stride;
-            CK(c->lane_scratch.alloc(c->lane_region_bytes * (kSlots + 1) + 65536)); // (+ room for the prefetches that run past the last row)
+            // SED rows of a chunk: 4 GiB per region unless EGGPHOT_LANE_SCRATCH_MB says otherwise, 2048 batches at least
+            size_t cap_bytes = size_t(4) << 30;
+            if (const char *e = getenv("EGGPHOT_LANE_SCRATCH_MB")) { const long v = atol(e); if (v > 0) cap_bytes = (size_t)v << 20; }
+            c->lane_cap_batches = std::max<size_t>(cap_bytes / q.rows_stride, 2048);
             for (auto &h : c->zhist) CK(h.alloc(zsort_hist_bytes()));
         }
     }
@@ -496,12 +522,7 @@ int eggphot_compute(eggphot_ctx *c, const eggphot_galaxies *gal, size_t ngal, co
     // chunks: large enough to fill every SM several times over, small enough that the copies of one
     // chunk overlap the kernel of the other (two streams): an eighth of the catalog, within [2^15, 2^18]
     size_t chunk = std::min<size_t>(std::max<size_t>((ngal + 7) / 8, 1u << 15), 1u << 18);
-    if (c->use_lane) {
-        // the lane kernel works in rounds of one batch of 32 galaxies per warp: a chunk is a whole number of rounds of
-        // the whole GPU, two at least (the last round of a launch is rarely full)
-        const size_t unit = (size_t)c->lane_blocks * (lane_kernel_threads() / 32) * kLanes;
-        chunk = std::max<size_t>((std::min<size_t>((ngal + 7) / 8, 1u << 20) + unit - 1) / unit, 2) * unit;
-    }
+    if (c->use_lane) chunk = (std::min<size_t>(std::max<size_t>((ngal + 7) / 8, 1u << 15), 1u << 20) + kLanes - 1) / kLanes * kLanes;
     chunk = std::min(chunk, ngal);
     if (chunk == 0) return EGGPHOT_OK;
 #define CK(x) do { if ((e = (x)) != cudaSuccess) return c->cuda_fail(e, #x); } while (0)

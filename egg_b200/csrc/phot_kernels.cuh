@@ -80,25 +80,33 @@ size_t flux_kernel_smem(const FluxParams &p, int precision);
 int launch_flux_kernel(const FluxParams &p, int precision, int grid_blocks, cudaStream_t stream);
 int flux_kernel_max_blocks_per_sm(const FluxParams &p, int precision);
 
-// ---- the lane-per-galaxy flux kernel (phot_lane_kernels.cu) ----
-// fp.groups point at the BandHeader2 blobs; fp.scratch at the per-warp scratch areas of `scratch_stride` bytes each:
-// [(nD + 2) + (nB + 2) rows][32 lanes] reals, then at res_offset [ntab][2][32 lanes] doubles.
+// ---- the lane-per-galaxy flux pipeline (phot_lane_kernels.cu) ----
+// fp.groups point at the BandHeader2 blobs.  A call is worked off in chunks of `nbatch` batches of 32 galaxies (in the
+// order of `perm`); the chunk's buffers: SED rows, band-table windows, build ranges, table sums, item counters.
 struct LaneParams {
     FluxParams fp;
     const uint32_t *perm;     // [ngal] galaxies bucketed by redshift (zsort); batches are 32 consecutive entries
-    const GridNode *grid;     // [nD + 2]
-    const int32_t *next_opt;  // [nD + 2]
+    const GridNode *grid;     // [rowsD] the disk grid, two virtual nodes and padding (lane_grid_rows)
+    const int32_t *next_opt;  // [rowsD]
     const uint32_t *tab_col;  // [ntab] output column of every band table, in group order
     const double2 *col_span;  // [nband] full wavelength span of every filter (coverage test), by output column
     uint32_t ntab;            // band tables (a filter cut into pieces has several); at most 64
-    uint32_t row_margin;      // disk-grid rows built on either side of the nodes the bands read (see the kernel)
-    uint64_t scratch_stride;  // bytes per warp
-    uint64_t res_offset;      // bytes from the start of a warp's area to its table sums
+    uint32_t row_margin;      // disk-grid rows built on either side of the nodes the bands read (see the plan kernel)
+    uint64_t batch0;          // first batch of the chunk (index into perm / 32)
+    uint32_t nbatch;          // batches of the chunk
+    uint32_t rowsD, rowsB;    // rows per batch of the disk / bulge SED arrays (lane_grid_rows of nD / nB)
+    uint64_t rows_stride;     // bytes per batch of `rows`
+    void *rows;               // [nbatch][rowsD + rowsB][32 lanes] reals: rest-frame SEDs, node-major
+    uint32_t *win;            // [nbatch][64] node window of every band table (0: nothing to do)
+    int4 *plan;               // [nbatch] rows to build: disk first / last, bulge first / last
+    double *res;              // [nbatch][ntab][2][32 lanes] table sums (bulge, disk)
+    uint32_t *counters;       // [kMaxGroups] items handed out per band group
+    float group_cost[kMaxGroups]; // relative work of the groups (deals the CTAs to the groups)
 };
 size_t lane_kernel_smem(const LaneParams &q);
 int lane_kernel_max_blocks_per_sm(const LaneParams &q, int precision);
-int lane_kernel_threads();
-int launch_lane_flux_kernel(const LaneParams &q, int precision, int grid_blocks, cudaStream_t stream);
+// plan + build + walk + finish of one chunk; returns cudaError_t as int
+int launch_lane_chunk(const LaneParams &q, int precision, int num_sms, cudaStream_t stream);
 // counting sort of the galaxies by log2(1+z): hist is scratch of zsort_hist_bytes(), perm receives the order
 size_t zsort_hist_bytes();
 int launch_zsort(const float *z, uint32_t ngal, uint32_t *hist, uint32_t *perm, int num_sms, cudaStream_t stream);

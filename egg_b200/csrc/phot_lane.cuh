@@ -112,6 +112,9 @@ struct alignas(16) GridNode {
     int32_t po;    // disk-grid index of the last optical node before j, -1 if none
 };
 constexpr int32_t kNextNotOptical = 1 << 30;
+// rows of the disk grid as the lane kernel holds it: the real nodes, two virtual nodes far to the red, and padding to a
+// multiple of 8 (the walk works in strips of 8 arrivals cut at multiples of 8); the same for the optical grid
+EGG_HD int lane_grid_rows(int n) { return (n + 2 + 7) & ~7; }
 EGG_HD int grid_o(const GridNode &g) { return g.o < 0 ? -1 : (g.o & (kNextNotOptical - 1)); }
 static_assert(sizeof(GridNode) == 32, "GridNode layout");
 
@@ -186,7 +189,7 @@ EGG_HD double interval_E(const Band2 &b, const NodeEv &p, const NodeEv &e, doubl
 // and settles that one.  js is at or before the node left of the window (and at or before the optical node left of it),
 // je at or after the node right of it: every node outside the window has the weight 0 exactly for every galaxy of the
 // batch, so the window may be wider than a galaxy needs.  The walk starts from a state blue of every filter.  Terms are
-// summed in `real` over strips of 16 arrivals cut at absolute node numbers ((16 k, 16 k + 16]) and the strips added in
+// summed in `real` over strips of 16 arrivals cut at absolute node numbers ([16 k, 16 k + 15]) and the strips added in
 // double: the sums do not depend on where the walk starts.
 constexpr int kLaneStrip = 16;
 template <typename real, typename Sed>
@@ -217,7 +220,7 @@ EGG_HD void walk_window(const Band2 &bv, const GridNode *grid, double opz, bool 
             prevo = cur; Sprev_b = Sb;
         }
         prev = cur; Sprev_d = Sd;
-        if ((j & (kLaneStrip - 1)) == 0 || j == je) {
+        if ((j & (kLaneStrip - 1)) == kLaneStrip - 1 || j == je) {
             totd += (double)accd; accd = real(0);
             totb += (double)accb; accb = real(0);
         }

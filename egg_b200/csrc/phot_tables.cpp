@@ -424,10 +424,11 @@ Status build_band_table2(const Filter &f, int i0, int i1, uint32_t out_col, int 
     //      dl (K0 + R dl / 2) per cell (phot_core.cuh)][terminator]
     const int nrec = 1 + n + nsplit + 1;
     t.h.n = (uint32_t)nrec;
-    t.rec.assign(nrec, Rec{0, 0, 0, 0});
-    t.hs.assign(nrec, 0.0);
+    t.rec.assign(nrec + 1, Rec{0, 0, 0, 0}); // (a second terminator: the lookup reads both probes at once)
+    t.hs.assign(nrec + 1, 0.0);
     t.rec[0] = Rec{fn[0] - std::max(fn[n - 1] - fn[0], 1e-6), 0, 0, 0};
     t.rec[nrec - 1] = Rec{1e300, 0, 0, 0};
+    t.rec[nrec] = Rec{1e300, 0, 0, 0};
     std::vector<long double> K0(n), L(n);
     std::vector<long double> Kat(nsplit), Lat(nsplit); // region s at its right end (split node msp[s])
     for (int s = 0; s <= nsplit; ++s) {
@@ -533,8 +534,9 @@ Status build_lane_tables(Prepared &P, const eggphot_opts &opts) {
     // ---- the disk grid as the walk reads it
     const Grid &gd = P.grid_disk, &gb = P.grid_bulge;
     const int nD = gd.n(), nB = gb.n();
-    P.grid_nodes.assign((size_t)nD + 2, GridNode{0, 0, 0, -1, -1});
-    P.next_opt.assign((size_t)nD + 2, nD);
+    const int nG = lane_grid_rows(nD); // nD real nodes, two virtual ones, padding to the walk's strips of 8 arrivals
+    P.grid_nodes.assign((size_t)nG, GridNode{0, 0, 0, -1, -1});
+    P.next_opt.assign((size_t)nG, nD);
     P.opt_node.assign((size_t)nB, 0);
     {
         int o = 0, lasto = -1;
@@ -576,17 +578,26 @@ Status build_lane_tables(Prepared &P, const eggphot_opts &opts) {
         }
         P.next_opt[nD] = nD;
         P.next_opt[nD + 1] = nD + 1;
+        // padding nodes: further and further to the red, never optical (the walk works in strips of 8 arrivals cut at
+        // multiples of 8; nodes beyond a window weigh exactly nothing)
+        for (int j = nD + 2; j < nG; ++j) {
+            GridNode &w = P.grid_nodes[j];
+            w.x = P.grid_nodes[j - 1].x * 2.0;
+            w.idxp = 1.0 / (w.x - P.grid_nodes[j - 1].x);
+            w.idxpo = 0.0;
+            w.o = -1;
+            w.po = nD + 1;
+            P.next_opt[j] = j;
+        }
         if (P.has_bulge)
             for (int o2 = 0; o2 < nB; ++o2)
                 if (P.grid_nodes[P.opt_node[o2]].o != o2)
                     return Status::error(EGGPHOT_ERR_GRID, "an optical node is missing from the disk grid");
-        for (int j = 0; j <= nD; ++j)
-            if (P.grid_nodes[j].o >= 0 && P.grid_nodes[j + 1].o < 0) P.grid_nodes[j].o |= kNextNotOptical;
     }
     // ---- band tables in groups
     size_t budget = opts.smem_table_budget;
     if (!budget) {
-        budget = kSmemPerCta - kLaneFixedSmem - ((size_t)(nD + 2) * 16 + 128); // the grid's {x, idxp} live behind the tables
+        budget = kSmemPerCta - kLaneFixedSmem - (((size_t)nG + 2) * 18 + 16 + 128); // the grid's {x, idxp} live behind the tables
     }
     // a filter whose table exceeds the budget is cut at filter nodes into pieces that feed the same output column
     std::vector<BandTable2> tabs;
