@@ -183,7 +183,7 @@ int enqueue(eggphot_ctx *c, const eggphot_galaxies &g, size_t ngal, const eggpho
         const size_t nbatch = (ngal + kLanes - 1) / kLanes, cap = std::min(nbatch, c->lane_cap_batches);
         const size_t ntab = std::max<uint32_t>(q.ntab, 1);
         ce = c->lrows[region].alloc(cap * q.rows_stride + 65536); // (+ room for the L2 prefetches that run past the last row)
-        if (ce == cudaSuccess) ce = c->lwin[region].alloc(cap * 64 * sizeof(uint32_t));
+        if (ce == cudaSuccess) ce = c->lwin[region].alloc(cap * 128 * sizeof(uint32_t));
         if (ce == cudaSuccess) ce = c->lplan[region].alloc(cap * sizeof(int4));
         if (ce == cudaSuccess) ce = c->lres[region].alloc(cap * ntab * 2 * kLanes * sizeof(double));
         if (ce == cudaSuccess) ce = c->lcnt[region].alloc(kMaxGroups * sizeof(uint32_t));
@@ -393,8 +393,14 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
     // ---- the lane kernel's tables, scratch and bucketing buffers
     {
         if (P.groups2.size() > (size_t)kMaxGroups) return c->fail(EGGPHOT_ERR_UNSUPPORTED, "more than 16 band groups; raise smem_table_budget");
-        CK(c->gridN.upload(P.grid_nodes.data(), P.grid_nodes.size() * sizeof(GridNode)));
-        CK(c->nextOpt.upload(P.next_opt.data(), P.next_opt.size() * sizeof(int32_t)));
+        {   // {x, 1 / dx} of the two component grids as the walk reads them
+            std::vector<double> gx;
+            for (const GridNode &g : P.grid_nodes) { gx.push_back(g.x); gx.push_back(g.idxp); }
+            CK(c->gridN.upload(gx.data(), gx.size() * sizeof(double)));
+            gx.clear();
+            for (const GridNode &g : P.grid_nodes_b) { gx.push_back(g.x); gx.push_back(g.idxp); }
+            CK(c->nextOpt.upload(gx.data(), gx.size() * sizeof(double)));
+        }
         c->blobs2.resize(P.groups2.size());
         LaneParams &q = c->lbase;
         q.fp = c->base;
@@ -410,8 +416,9 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
             if (q.fp.groups[g].nb > (uint32_t)kMaxGroupBands) return c->fail(EGGPHOT_ERR_UNSUPPORTED, "more than 64 bands in one group");
             q.fp.max_blob = std::max(q.fp.max_blob, q.fp.groups[g].bytes);
         }
-        q.grid = (const GridNode *)c->gridN.p;
-        q.next_opt = (const int32_t *)c->nextOpt.p;
+        q.gxD = (const double2 *)c->gridN.p;
+        q.gxB = (const double2 *)c->nextOpt.p;
+        q.gx_in_smem = lane_gx_in_smem(P.precision == EGGPHOT_FP64, P.grid_disk.n(), P.grid_bulge.n(), kSmemPerCta) ? 1 : 0;
         {
             std::vector<uint32_t> cols;
             for (const BandGroup &g : P.groups2) cols.insert(cols.end(), g.cols.begin(), g.cols.end());
@@ -421,12 +428,6 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
             q.tab_col = (const uint32_t *)c->tabCol.p;
         }
         if (q.ntab > 64) return c->fail(EGGPHOT_ERR_UNSUPPORTED, "more than 64 band tables; raise smem_table_budget");
-        {   // a walk starts at the optical node before its window and ends at the one after it (plus the unrolled trip's extra node)
-            int gap = 1, last = -1;
-            for (int j = 0; j < P.grid_disk.n(); ++j)
-                if (P.grid_nodes[j].o >= 0) { if (last >= 0) gap = std::max(gap, j - last); last = j; }
-            q.row_margin = (uint32_t)(P.has_bulge ? gap + 3 : 3);
-        }
         if (P.grid_disk.n() > 32000) return c->fail(EGGPHOT_ERR_UNSUPPORTED, "SED wavelength grid with more than 32000 nodes");
         {
             std::vector<double> span(2 * std::max<size_t>(P.bands.size(), 1), 0.0);
@@ -446,12 +447,10 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
             }
         }
         if (c->use_lane) {
-            const size_t smem = lane_kernel_smem(q);
+            const size_t smem = lane_kernel_smem(q, P.precision);
             if (smem + kLaneFixedSmem > (size_t)prop.sharedMemPerBlockOptin)
                 return c->fail(EGGPHOT_ERR_UNSUPPORTED, "band tables need " + std::to_string(smem) + " B of shared memory, device offers " +
                                                          std::to_string(prop.sharedMemPerBlockOptin) + "; lower smem_table_budget");
-            const int occ = lane_kernel_max_blocks_per_sm(q, P.precision);
-            if (occ <= 0) return c->fail(EGGPHOT_ERR_CUDA, "flux kernel cannot be resident (occupancy query failed)");
             // SED rows of a chunk: 4 GiB per region unless EGGPHOT_LANE_SCRATCH_MB says otherwise, 2048 batches at least
             size_t cap_bytes = size_t(4) << 30;
             if (const char *e = getenv("EGGPHOT_LANE_SCRATCH_MB")) { const long v = atol(e); if (v > 0) cap_bytes = (size_t)v << 20; }

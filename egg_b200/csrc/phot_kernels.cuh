@@ -86,25 +86,24 @@ int flux_kernel_max_blocks_per_sm(const FluxParams &p, int precision);
 struct LaneParams {
     FluxParams fp;
     const uint32_t *perm;     // [ngal] galaxies bucketed by redshift (zsort); batches are 32 consecutive entries
-    const GridNode *grid;     // [rowsD] the disk grid, two virtual nodes and padding (lane_grid_rows)
-    const int32_t *next_opt;  // [rowsD]
+    const double2 *gxD, *gxB; // [rowsD], [rowsB] {x, 1 / (x - x of the node before)} of the disk / optical grid, two virtual
+                              // nodes far to the red and padding behind the real ones (lane_grid_rows)
+    int32_t gx_in_smem;       // the walk kernel keeps both in shared memory
     const uint32_t *tab_col;  // [ntab] output column of every band table, in group order
     const double2 *col_span;  // [nband] full wavelength span of every filter (coverage test), by output column
     uint32_t ntab;            // band tables (a filter cut into pieces has several); at most 64
-    uint32_t row_margin;      // disk-grid rows built on either side of the nodes the bands read (see the plan kernel)
     uint64_t batch0;          // first batch of the chunk (index into perm / 32)
     uint32_t nbatch;          // batches of the chunk
     uint32_t rowsD, rowsB;    // rows per batch of the disk / bulge SED arrays (lane_grid_rows of nD / nB)
     uint64_t rows_stride;     // bytes per batch of `rows`
     void *rows;               // [nbatch][rowsD + rowsB][32 lanes] reals: rest-frame SEDs, node-major
-    uint32_t *win;            // [nbatch][64] node window of every band table (0: nothing to do)
+    uint32_t *win;            // [nbatch][64][2] node window of every band table on the disk / optical grid (0: nothing to do)
     int4 *plan;               // [nbatch] rows to build: disk first / last, bulge first / last
     double *res;              // [nbatch][ntab][2][32 lanes] table sums (bulge, disk)
     uint32_t *counters;       // [kMaxGroups] items handed out per band group
     float group_cost[kMaxGroups]; // relative work of the groups (deals the CTAs to the groups)
 };
-size_t lane_kernel_smem(const LaneParams &q);
-int lane_kernel_max_blocks_per_sm(const LaneParams &q, int precision);
+size_t lane_kernel_smem(const LaneParams &q, int precision);
 // plan + build + walk + finish of one chunk; returns cudaError_t as int
 int launch_lane_chunk(const LaneParams &q, int precision, int num_sms, cudaStream_t stream);
 // counting sort of the galaxies by log2(1+z): hist is scratch of zsort_hist_bytes(), perm receives the order

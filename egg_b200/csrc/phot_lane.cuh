@@ -101,22 +101,36 @@ EGG_HD void make_band2(const uint8_t *blob, const BandHeader2 &h, Band2 &v) {
     v.two_probe = h.two_probe != 0;
 }
 
-// One node of the disk grid as the walk reads it (the same for every galaxy: loaded with a warp-uniform address).
+// One node of a component grid as the walk reads it (the same for every galaxy: loaded with a warp-uniform address).
+// o / po / idxpo tie the disk grid to the optical grid (kept for the table builder's checks).
 struct alignas(16) GridNode {
     double x;      // rest wavelength [um]
     double idxp;   // 1 / (x_j - x_{j-1}); 0 for j = 0
-    double idxpo;  // optical node: 1 / (x_j - x of the previous optical node), 0 if there is none; else 0
-    int32_t o;     // index in the optical (bulge) grid, -1 if the node is not an optical node; bit 30 (kNextNotOptical):
-                   // node j + 1 is not an optical node (the walk then keeps the state of j for the bulge interval that
-                   // starts here; otherwise that interval is the disk interval [j, j + 1])
+    double idxpo;  // optical node of the disk grid: 1 / (x_j - x of the previous optical node), 0 if there is none; else 0
+    int32_t o;     // disk grid: index in the optical (bulge) grid, -1 if the node is not an optical node
     int32_t po;    // disk-grid index of the last optical node before j, -1 if none
 };
 constexpr int32_t kNextNotOptical = 1 << 30;
-// rows of the disk grid as the lane kernel holds it: the real nodes, two virtual nodes far to the red, and padding to a
-// multiple of 8 (the walk works in strips of 8 arrivals cut at multiples of 8); the same for the optical grid
-EGG_HD int lane_grid_rows(int n) { return (n + 2 + 7) & ~7; }
 EGG_HD int grid_o(const GridNode &g) { return g.o < 0 ? -1 : (g.o & (kNextNotOptical - 1)); }
 static_assert(sizeof(GridNode) == 32, "GridNode layout");
+// rows of a component grid as the lane kernels hold it: the real nodes, two virtual nodes far to the red, and padding to a
+// multiple of 8
+EGG_HD int lane_grid_rows(int n) { return (n + 2 + 7) & ~7; }
+
+// The walk kernel (phot_lane_kernels.cu): warps per CTA, arrivals per strip (their cell lookups run ahead of the
+// arithmetic as independent chains), SED rows per staging buffer (two buffers per warp).
+#ifndef EGG_WALK_THREADS
+#define EGG_WALK_THREADS 640
+#endif
+constexpr int kWalkThreads = EGG_WALK_THREADS; // 20 warps at 96 registers
+constexpr int kSub = 4;
+constexpr int kStage = 8;
+// Shared memory of the walk kernel that is not band tables: the staging buffers, and {x, 1 / dx} of the two component
+// grids unless they would leave less than half of the shared memory to the band tables (then they are read from global
+// memory through L1).
+EGG_HD size_t lane_stage_bytes(bool fp64) { return (size_t)(kWalkThreads / 32) * 2 * kStage * 32 * (fp64 ? 8 : 4); }
+EGG_HD size_t lane_gx_bytes(int nD, int nB) { return ((size_t)lane_grid_rows(nD) + lane_grid_rows(nB)) * 16; }
+EGG_HD bool lane_gx_in_smem(bool fp64, int nD, int nB, size_t limit) { return lane_gx_bytes(nD, nB) + lane_stage_bytes(fp64) <= limit / 2; }
 
 // Shared memory of the lane kernel: the band tables of the current group, and a little besides.
 constexpr size_t kSmemPerCta = 232448;   // 227 KB
@@ -183,71 +197,33 @@ EGG_HD double interval_E(const Band2 &b, const NodeEv &p, const NodeEv &e, doubl
     return d * idx;
 }
 
-// Weighted sums of one band table for one galaxy: totd = sum_j Sd_j W_j over the disk nodes and totb = sum over the
-// optical nodes of Sb_o W^b_o.  The walk arrives at nodes js..je: arriving at node j closes the interval [j-1, j] and
-// settles the weight of node j-1 (disk), and, at an optical node, closes the bulge interval from the optical node before
-// and settles that one.  js is at or before the node left of the window (and at or before the optical node left of it),
-// je at or after the node right of it: every node outside the window has the weight 0 exactly for every galaxy of the
-// batch, so the window may be wider than a galaxy needs.  The walk starts from a state blue of every filter.  Terms are
-// summed in `real` over strips of 16 arrivals cut at absolute node numbers ([16 k, 16 k + 15]) and the strips added in
-// double: the sums do not depend on where the walk starts.
+// Weighted sum of one band table for one galaxy and ONE component grid (the disk on the merge_add grid, the bulge on the
+// optical grid: its SED intervals run between optical nodes, as when get_flux runs on the bulge alone,
+// src/egg-gencat.cpp:2206-2209): tot = sum_j S_j W_j.  The walk arrives at nodes js..je: arriving at node j closes the
+// interval [j-1, j] and settles the weight of node j-1.  js is at or before the last node left of the table's span, je
+// after the first node right of it: every node outside the span has the weight 0 exactly for every galaxy of the batch,
+// so the window may be wider than a galaxy needs.  The walk starts from a state blue of every filter.  Terms are summed
+// in `real` over strips of 16 arrivals cut at absolute node numbers ([16 k, 16 k + 15]) and the strips added in double:
+// the sum does not depend on where the walk starts.
 constexpr int kLaneStrip = 16;
-template <typename real, typename Sed>
-EGG_HD void walk_window(const Band2 &bv, const GridNode *grid, double opz, bool bulge, int js, int je, const Sed &sed,
-                        double &totd, double &totb) {
-    NodeEv prev, prevo, cur;
+template <typename real>
+EGG_HD double walk_window(const Band2 &bv, const GridNode *grid, double opz, int js, int je, const real *sed) {
+    NodeEv prev, cur;
     prev.u = 0.0; prev.Lin = 0.0; prev.Lout = 0.0; prev.k0 = 0.0; prev.hr = 0.0; prev.hs = 0.0; prev.r = -1;
-    prevo = prev;
-    double Eprev_d = 0.0, Eprev_b = 0.0;
-    real Sprev_d = real(0), Sprev_b = real(0), accd = real(0), accb = real(0);
-    totd = 0.0; totb = 0.0;
+    double Eprev = 0.0, tot = 0.0;
+    real Sprev = real(0), acc = real(0);
     for (int j = js; j <= je; ++j) {
         const GridNode g = grid[j];
         const double t = opz * g.x; // the reference's lam = rlam * (1 + z) (src/egg-gencat.cpp:2161), in double
         eval_node(bv, t, cur);
-        const real Sd = sed.disk(j);
-        double jump_d;
-        const double E_d = interval_E(bv, prev, cur, t, g.idxp, opz, jump_d);
-        accd = fma((real)(E_d - Eprev_d), Sprev_d, accd);
-        Eprev_d = E_d - jump_d;
-        if (bulge && g.o >= 0) {
-            const real Sb = sed.bulge(grid_o(g));
-            double E_b, jump_b;
-            if (g.po == j - 1 && j > js) { E_b = E_d; jump_b = jump_d; } // the interval is a disk interval too
-            else E_b = interval_E(bv, prevo, cur, t, g.idxpo, opz, jump_b);
-            accb = fma((real)(E_b - Eprev_b), Sprev_b, accb);
-            Eprev_b = E_b - jump_b;
-            prevo = cur; Sprev_b = Sb;
-        }
-        prev = cur; Sprev_d = Sd;
-        if ((j & (kLaneStrip - 1)) == kLaneStrip - 1 || j == je) {
-            totd += (double)accd; accd = real(0);
-            totb += (double)accb; accb = real(0);
-        }
+        double jump;
+        const double E = interval_E(bv, prev, cur, t, g.idxp, opz, jump);
+        acc = fma((real)(E - Eprev), Sprev, acc);
+        Eprev = E - jump;
+        prev = cur; Sprev = sed[j];
+        if ((j & (kLaneStrip - 1)) == kLaneStrip - 1 || j == je) { tot += (double)acc; acc = real(0); }
     }
-}
-
-// The nodes a band can weigh for a batch whose (1+z) spans [opz_min, opz_max]: from the last node at or left of the
-// filter's blue end to the first node at or right of its red end, for the disk grid, widened to the optical nodes around
-// them for the bulge (its own SED intervals straddle the ends).  jlo / jhi are those two disk nodes, found by the caller
-// with a relative margin (extra nodes weigh exactly nothing).
-EGG_HD void widen_window_for_bulge(const GridNode *grid, const int32_t *next_opt, int nD, int &jlo, int &jhi) {
-    if (grid[jlo].o < 0 && grid[jlo].po >= 0) jlo = grid[jlo].po;
-    if (grid[jhi].o < 0) jhi = next_opt[jhi] < nD ? next_opt[jhi] : nD - 1;
-}
-
-// next_opt[j] = first optical node after j (the virtual node nD counts as one).
-EGG_HD void block_arrivals(const GridNode *grid, const int32_t *next_opt, bool bulge, int a, int b, int &js, int &je) {
-    js = a > 0 ? a - 1 : 0;
-    je = b + 1; // <= nD
-    if (bulge) {
-        // the optical node before the first optical node of [a, b] is the last optical node before a, whether a is
-        // optical or not
-        const int first_prev = grid[a].po;
-        if (first_prev >= 0 && first_prev < js) js = first_prev;
-        const int q = next_opt[b]; // the optical node after the last optical node of [a, b]
-        if (q > je) je = q;
-    }
+    return tot;
 }
 
 } // namespace eggphot

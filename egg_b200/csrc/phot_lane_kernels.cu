@@ -202,140 +202,128 @@ __device__ __forceinline__ Recs load_recs(const BandDev &B, uint32_t ra) {
     R.hs = lds_f64(B.hs + ((ra - B.rec) >> 2));
     return R;
 }
-__device__ __forceinline__ int lds_s16(uint32_t a) {
-    int16_t v;
-    asm("ld.shared.s16 %0, [%1];" : "=h"(v) : "r"(a));
-    return (int)v;
+template <typename real> __device__ __forceinline__ real lds_real(uint32_t a);
+template <> __device__ __forceinline__ float lds_real<float>(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); // (volatile: the staging buffers are rewritten by bulk copies)
+    return v;
+}
+template <> __device__ __forceinline__ double lds_real<double>(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+// mbarrier / bulk copy by 32-bit shared address
+__device__ __forceinline__ void mbar_expect_tx_sa(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_sa(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s_sa(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-#ifndef EGG_LANE_SUB
-#define EGG_LANE_SUB 4
-#endif
-constexpr int kSub = EGG_LANE_SUB; // arrivals per strip of the walk, strips cut at multiples of kSub
 
-// Walks nodes js..je of the disk grid (js a multiple of kSub, je + 1 too) for one galaxy (lane) and one band table.  Per
-// strip: (1) the filter cell of every node is looked up - independent chains of shared-memory loads, no branch - and
-// (2) the nodes are taken in order: records of the cell, the two expansions, the interval that ends at the node, the
-// weight of the node before it.  Loads run ahead of the arithmetic: the records of the next node, the SED values two
-// nodes on (they come from L2, asked for two strips ahead: the rows of a batch live in HBM by the time the bands read
-// them).  The bulge's SED intervals run between optical nodes: at an optical node the interval from the last optical
-// node is closed (from the state kept of that node) and settles its weight.  totd / totb receive the sums of the strips
-// of 16 arrivals (each summed in `real`, the strips added in double, in order: the same numbers whichever way the window
-// is cut).
-template <typename real, bool TWOP, bool BULGE>
-__device__ __forceinline__ void walk_table(const BandDev &B, const GridNode *__restrict__ grid, uint32_t gx_sa, uint32_t on_sa, double opz,
-                                           int js, int je, const real *__restrict__ sd, const real *__restrict__ sb, double &totd, double &totb) {
+// Walks nodes js..je (js a multiple of 4, je + 1 too) of ONE component grid for one galaxy (lane) and one band table:
+// the disk on the merge_add grid, the bulge on the optical grid (its SED intervals run between optical nodes, as when
+// get_flux runs on the bulge alone, src/egg-gencat.cpp:2206-2209).
+//  * The SED rows [node][lane] of the walk are staged in shared memory by TMA bulk copies, eight rows (1 KB in fp32) per
+//    copy, two buffers per warp: lane 0 requests the next eight rows before the warp starts on the current ones; an
+//    mbarrier per buffer says when they have landed.  (The rows live in HBM by the time the bands read them.)
+//  * Per strip of four arrivals: (1) the filter cell of every node is looked up - four independent chains of
+//    shared-memory loads, no branch - and (2) the nodes are taken in order: records of the cell, the two expansions, the
+//    interval that ends at the node, the weight of the node before it.
+// Returns the sum over the strips of 16 arrivals (each summed in `real`, the strips added in double, in order: the same
+// number whichever way the window is cut).  gx = {x, 1 / dx} of the grid: shared address (GXS) or global pointer.
+template <typename real, bool TWOP, bool GXS>
+__device__ __forceinline__ double walk_comp(const BandDev &B, uint32_t gx_sa, const double2 *__restrict__ gxg, double opz, int js, int je,
+                                            const real *__restrict__ rows, uint32_t stage_sa, uint32_t bar_sa, uint32_t &phases) {
     const int lane = threadIdx.x & 31;
-    double Pu = 0.0, PLout = 0.0, Ou = 0.0, OLout = 0.0; // state of the previous node / of the last optical node
-    uint32_t Pra = 0u, Pnsa = B.nsa0, Ora = 0u, Onsa = B.nsa0;
-    double Eprev_d = 0.0, Eprev_b = 0.0, td = 0.0, tb = 0.0;
-    real Sprev_d = real(0), Sprev_b = real(0), accd = real(0), accb = real(0);
-    constexpr int kLinesPerRow = (int)sizeof(real) / 4; // a row is 32 lanes x sizeof(real): one or two 128-byte lines
-    constexpr uint32_t kRowBytes = kLanes * sizeof(real);
-    constexpr int kAhead = 16;                          // rows asked of L2 ahead of the walk
-    const char *sd_rows = reinterpret_cast<const char *>(sd - lane), *sb_rows = reinterpret_cast<const char *>(sb - lane);
-    const char *sdl = reinterpret_cast<const char *>(sd), *sbl = reinterpret_cast<const char *>(sb);
-    const int pf_row = lane / kLinesPerRow, pf_off = 128 * (lane % kLinesPerRow);
-    if (lane < kAhead * kLinesPerRow) prefetch_l2(sd_rows + (size_t)(js + pf_row) * kRowBytes + pf_off);
-    int o_pf = 0; // bulge rows asked of L2 so far
-    if (BULGE) {
-        o_pf = __ldg(&grid[js].o) >= 0 ? grid_o(grid[js]) : (grid[js].po >= 0 ? grid_o(grid[grid[js].po]) + 1 : 0);
-        if (lane < kAhead * kLinesPerRow) prefetch_l2(sb_rows + (size_t)(o_pf + pf_row) * kRowBytes + pf_off);
-        o_pf += kAhead;
+    constexpr uint32_t kRowBytes = kLanes * sizeof(real), kStageBytes = kStage * kRowBytes;
+    auto load_gx = [&](int j) -> double2 { return GXS ? lds_v2f64(gx_sa + 16u * (uint32_t)j) : __ldg(gxg + j); };
+    double Pu = 0.0, PLout = 0.0, Eprev = 0.0, tot = 0.0; // state of the previous node
+    uint32_t Pra = 0u, Pnsa = B.nsa0;
+    real Sprev = real(0), acc = real(0);
+    const char *src = reinterpret_cast<const char *>(rows) + (size_t)js * kRowBytes;
+    __syncwarp(); // every lane is done with the buffers (the previous walk of this warp)
+    if (lane == 0) {
+        fence_proxy_async();
+        mbar_expect_tx_sa(bar_sa, kStageBytes);
+        bulk_g2s_sa(stage_sa, src, kStageBytes, bar_sa);
     }
-    // the pipeline of SED values: node j (0) and node j + 1 (1); o = index in the bulge grid, -1 if the node is not optical
-    int o0 = BULGE ? lds_s16(on_sa + 2u * (uint32_t)js) : -1, o1 = BULGE ? lds_s16(on_sa + 2u * (uint32_t)(js + 1)) : -1;
-    real Sd0 = __ldcg(reinterpret_cast<const real *>(sdl + (uint32_t)js * kRowBytes));
-    real Sd1 = __ldcg(reinterpret_cast<const real *>(sdl + (uint32_t)(js + 1) * kRowBytes));
-    real Sb0 = real(0), Sb1 = real(0);
-    if (BULGE && o0 >= 0) Sb0 = __ldcg(reinterpret_cast<const real *>(sbl + (uint32_t)o0 * kRowBytes));
-    if (BULGE && o1 >= 0) Sb1 = __ldcg(reinterpret_cast<const real *>(sbl + (uint32_t)o1 * kRowBytes));
-    double idxpo = (BULGE && o0 >= 0) ? __ldg(&grid[js].idxpo) : 0.0;
+    uint32_t buf = 0;
 #pragma unroll 1
-    for (int j0 = js; j0 <= je; j0 += kSub) {
-        if ((j0 & (kAhead / 2 - 1)) == 0 && lane < (kAhead / 2) * kLinesPerRow) {
-            prefetch_l2(sd_rows + (size_t)(j0 + kAhead + pf_row) * kRowBytes + pf_off);
-            if (BULGE) {
-                // the optical nodes run at most as fast as the disk nodes: stay kAhead rows ahead of the last one met
-                const int cur = max(o0, o1);
-                if (cur >= 0 && cur + kAhead > o_pf) { prefetch_l2(sb_rows + (size_t)(o_pf + pf_row) * kRowBytes + pf_off); o_pf += kAhead / 2; }
-            }
+    for (int jg = js; jg <= je; jg += kStage, buf ^= 1u) {
+        __syncwarp(); // every lane is done with the other buffer
+        if (lane == 0 && jg + kStage <= je) {
+            src += kStageBytes;
+            fence_proxy_async();
+            mbar_expect_tx_sa(bar_sa + 8u * (buf ^ 1u), kStageBytes);
+            bulk_g2s_sa(stage_sa + (buf ^ 1u) * kStageBytes, src, kStageBytes, bar_sa + 8u * (buf ^ 1u));
         }
-        // (1) filter cells
-        uint32_t ra[kSub];
+        mbar_wait_sa(bar_sa + 8u * buf, (phases >> buf) & 1u);
+        phases ^= 1u << buf;
+        const uint32_t srow = stage_sa + buf * kStageBytes + (uint32_t)lane * (uint32_t)sizeof(real);
+#pragma unroll 1
+        for (int h = 0; h < kStage / kSub; ++h) {
+            const int j0 = jg + h * kSub;
+            if (j0 > je) break;
+            // (1) filter cells
+            uint32_t ra[kSub];
 #pragma unroll
-        for (int k = 0; k < kSub; ++k) {
-            const double t = opz * lds_f64(gx_sa + 16u * (uint32_t)(j0 + k));
-            int kk = round_lo(fma(t, B.bk_scale, B.bk_c0));
-            kk = min(max(kk, 0), B.nbkt_m1);
-            uint32_t a = B.rec + 32u * lds_u16(B.bkt + 2u * (uint32_t)kk);
-            if (TWOP) {
-                // a split node or an abrupt end is two records at one wavelength: two probes, both read at once
-                const double f1 = lds_f64(a + 32u), f2 = lds_f64(a + 64u);
-                a += (t >= f1 ? 32u : 0u) + (t >= f2 ? 32u : 0u);
-            } else {
-                while (t >= lds_f64(a + 32u)) a += 32u;
+            for (int k = 0; k < kSub; ++k) {
+                const double t = opz * load_gx(j0 + k).x;
+                int kk = round_lo(fma(t, B.bk_scale, B.bk_c0));
+                kk = min(max(kk, 0), B.nbkt_m1);
+                uint32_t a = B.rec + 32u * lds_u16(B.bkt + 2u * (uint32_t)kk);
+                if (TWOP) {
+                    // a split node or an abrupt end is two records at one wavelength: two probes, both read at once
+                    const double f1 = lds_f64(a + 32u), f2 = lds_f64(a + 64u);
+                    a += (t >= f1 ? 32u : 0u) + (t >= f2 ? 32u : 0u);
+                } else {
+                    while (t >= lds_f64(a + 32u)) a += 32u;
+                }
+                ra[k] = a;
             }
-            ra[k] = a;
-        }
-        // (2) intervals and weights
-        Recs R = load_recs(B, ra[0]);
-        double2 G = lds_v2f64(gx_sa + 16u * (uint32_t)j0);
+            // (2) intervals and weights
 #pragma unroll
-        for (int k = 0; k < kSub; ++k) {
-            const uint32_t j = (uint32_t)(j0 + k);
-            // loads that run ahead
-            Recs Rn = R;
-            double2 Gn = G;
-            if (k + 1 < kSub) {
-                Rn = load_recs(B, ra[k + 1]);
-                Gn = lds_v2f64(gx_sa + 16u * (j + 1u));
+            for (int k = 0; k < kSub; ++k) {
+                const Recs R = load_recs(B, ra[k]);
+                const double2 G = load_gx(j0 + k);
+                const real S = lds_real<real>(srow + (uint32_t)(h * kSub + k) * kRowBytes);
+                const double t = opz * G.x; // the reference's lam = rlam * (1 + z) (src/egg-gencat.cpp:2161), in double
+                const double u = t - R.a0.x, v = t - R.a1.x;
+                const double Lin = fma(u, fma(u, R.b0.y, R.b0.x), R.a0.y);
+                const double Lout = fma(v, fma(v, R.b1.y, R.b1.x), R.a1.y);
+                // close [j - 1, j], settle node j - 1
+                double Eadj;
+                uint32_t nsa_c;
+                const double E = interval_dev(B, Pu, PLout, Pra, Pnsa, ra[k], u, Lin, R.b0.x, R.b0.y, R.hs, t, G.y, opz, Eadj, nsa_c);
+                acc = fma(to_real<real>(E - Eprev), Sprev, acc);
+                Eprev = Eadj;
+                Sprev = S;
+                Pu = u; PLout = Lout; Pra = ra[k]; Pnsa = nsa_c;
             }
-            const int o2 = BULGE ? lds_s16(on_sa + 2u * (j + 2u)) : -1;
-            const real Sd2 = __ldcg(reinterpret_cast<const real *>(sdl + (j + 2u) * kRowBytes));
-            real Sb2 = real(0);
-            if (BULGE && o2 >= 0) Sb2 = __ldcg(reinterpret_cast<const real *>(sbl + (uint32_t)o2 * kRowBytes));
-            double idxpo_n = 0.0;
-            if (BULGE && o1 >= 0) idxpo_n = __ldg(&grid[j + 1u].idxpo);
-            // the node
-            const double t = opz * G.x; // the reference's lam = rlam * (1 + z) (src/egg-gencat.cpp:2161), in double
-            const double u = t - R.a0.x, v = t - R.a1.x;
-            const double Lin = fma(u, fma(u, R.b0.y, R.b0.x), R.a0.y);
-            const double Lout = fma(v, fma(v, R.b1.y, R.b1.x), R.a1.y);
-            // disk: close [j - 1, j], settle node j - 1
-            double Eadj_d;
-            uint32_t nsa_c;
-            const double E_d = interval_dev(B, Pu, PLout, Pra, Pnsa, ra[k], u, Lin, R.b0.x, R.b0.y, R.hs, t, G.y, opz, Eadj_d, nsa_c);
-            accd = fma(to_real<real>(E_d - Eprev_d), Sprev_d, accd);
-            Eprev_d = Eadj_d;
-            Sprev_d = Sd0;
-            // bulge: the interval from the last optical node ends here and settles that node
-            if (BULGE && o0 >= 0) {
-                double Eadj_b;
-                uint32_t dummy;
-                const double E_b = interval_dev(B, Ou, OLout, Ora, Onsa, ra[k], u, Lin, R.b0.x, R.b0.y, R.hs, t, idxpo, opz, Eadj_b, dummy);
-                accb = fma(to_real<real>(E_b - Eprev_b), Sprev_b, accb);
-                Eprev_b = Eadj_b;
-                Sprev_b = Sb0;
-                Ou = u; OLout = Lout; Ora = ra[k]; Onsa = nsa_c;
-            }
-            Pu = u; PLout = Lout; Pra = ra[k]; Pnsa = nsa_c;
-            R = Rn; G = Gn; idxpo = idxpo_n;
-            o0 = o1; o1 = o2; Sd0 = Sd1; Sd1 = Sd2; Sb0 = Sb1; Sb1 = Sb2;
-        }
-        // the sums of a strip of 16 arrivals are formed in `real`, the strips added in double: strips are cut at absolute node
-        // numbers, so the result does not depend on where the walk started
-        if ((j0 & 15) == 16 - kSub) {
-            td += (double)accd; accd = real(0);
-            if (BULGE) { tb += (double)accb; accb = real(0); }
+            // the sums of a strip of 16 arrivals are formed in `real`, the strips added in double: strips are cut at absolute
+            // node numbers, so the result does not depend on where the walk started
+            if ((j0 & 15) == 16 - kSub) { tot += (double)acc; acc = real(0); }
         }
     }
-    totd = td + (double)accd;
-    totb = BULGE ? tb + (double)accb : 0.0;
+    return tot + (double)acc;
 }
 
 // ---- the kernels --------------------------------------------------------------------------------------
-constexpr int kWinStride = 64;  // window words per batch in LaneParams::win (at most 64 band tables)
+constexpr int kWinStride = 128; // window words per batch in LaneParams::win: {disk, bulge} of at most 64 band tables
+
 constexpr int kSegRows = 256;   // rows per warp of the build kernel
 
 // lane -> galaxy of batch bl of the chunk (lanes beyond the end of the catalog repeat the batch's first galaxy)
@@ -345,7 +333,8 @@ __device__ __forceinline__ uint64_t lane_galaxy(const LaneParams &q, uint32_t bl
     return __ldg(q.perm + g0 + (lane < ng ? lane : 0));
 }
 
-// A warp per batch: the node window of every band table for the batch and the node ranges to build.
+// A warp per batch: the node windows of every band table for the batch, on the disk grid and on the optical grid, and
+// the node ranges to build.
 __global__ void __launch_bounds__(256) lane_plan_kernel(const __grid_constant__ LaneParams q) {
     const FluxParams &p = q.fp;
     const int lane = threadIdx.x & 31;
@@ -354,7 +343,6 @@ __global__ void __launch_bounds__(256) lane_plan_kernel(const __grid_constant__ 
     const int ntab = (int)q.ntab, nrf = p.do_rf ? (int)p.nrf : 0;
     const int nD = p.nD, nB = p.nB;
     const bool has_bulge = p.has_bulge != 0;
-    const GridNode *grid = q.grid;
     int ng;
     const uint64_t g = lane_galaxy(q, bl, lane, ng);
     double omin = 1.0 + (double)__ldg(p.z + g), omax = omin;
@@ -363,57 +351,48 @@ __global__ void __launch_bounds__(256) lane_plan_kernel(const __grid_constant__ 
         omin = fmin(omin, __shfl_xor_sync(kFull, omin, o));
         omax = fmax(omax, __shfl_xor_sync(kFull, omax, o));
     }
-    // node window of band table fb for the batch: from the last node at or left of the table's blue end for the largest
-    // (1+z) to the first node at or right of its red end for the smallest, with a relative margin (nodes a galaxy does
-    // not weigh get the weight 0 exactly); 0 = nothing to do.  jlo | jhi << 15 | 1 << 30 | bulge << 31
-    auto table_window = [&](int fb) -> uint32_t {
-        int grp = 0;
-        while (grp + 1 < (int)p.ngroups && fb >= (int)p.groups[grp + 1].base) ++grp;
-        const BandHeader2 *gh = reinterpret_cast<const BandHeader2 *>(p.groups[grp].blob) + (fb - (int)p.groups[grp].base);
-        const double ff = __ldg(&gh->full_first), fl = __ldg(&gh->full_last);
-        // [vif] sed2flux is NaN (-> flux 0, src/egg-gencat.cpp:2198) unless the SED covers the filter: a band no
-        // galaxy of the batch covers is skipped
-        const bool any_cov = nD >= 2 && __ldg(p.xD) * omin <= ff && __ldg(p.xD + nD - 1) * omax >= fl;
-        if (!any_cov || __ldg(&gh->n) == 0) return 0u;
-        int jlo = max(bis_last_le(p.xD, nD, __ldg(&gh->f_first) / omax * (1.0 - 1e-9)), 0);
-        int jhi = min(bis_first_ge(p.xD, nD, __ldg(&gh->f_last) / omin * (1.0 + 1e-9)), nD - 1);
-        const bool bulge_any = has_bulge && nB >= 2 && __ldg(p.xB) * omin <= ff && __ldg(p.xB + nB - 1) * omax >= fl;
-        if (bulge_any) widen_window_for_bulge(grid, q.next_opt, nD, jlo, jhi);
-        return (uint32_t)jlo | ((uint32_t)jhi << 15) | (bulge_any ? 0x80000000u : 0u) | 0x40000000u;
-    };
     int jn0 = nD, jn1 = -1, on0 = nB, on1 = -1; // disk / optical nodes some band of the batch reads
     for (int r = 0; r < nrf; ++r) {             // the rest-frame bands read fixed node ranges
         if (p.rfD[r].n > 0) { jn0 = min(jn0, (int)p.rfD[r].j0); jn1 = max(jn1, (int)(p.rfD[r].j0 + p.rfD[r].n - 1)); }
         if (has_bulge && p.rfB[r].n > 0) { on0 = min(on0, (int)p.rfB[r].j0); on1 = max(on1, (int)(p.rfB[r].j0 + p.rfB[r].n - 1)); }
     }
+    // window of band table fb on a grid: from the last node at or left of the table's blue end for the largest (1+z) of the
+    // batch to the first node at or right of its red end for the smallest, with a relative margin (nodes a galaxy does
+    // not weigh get the weight 0 exactly); the walk arrives at lo .. hi + 1.  0 = nothing to do, else lo | hi << 15 | 1 << 30
     uint32_t *win = q.win + (size_t)bl * kWinStride;
-    for (int fb = lane; fb < kWinStride; fb += 32) {
-        const uint32_t w = fb < ntab ? table_window(fb) : 0u;
-        win[fb] = w;
-        if (w) {
-            jn0 = min(jn0, (int)(w & 0x7fffu));
-            jn1 = max(jn1, (int)((w >> 15) & 0x7fffu));
+    for (int fb = lane; fb < kWinStride / 2; fb += 32) {
+        uint32_t wd = 0u, wb = 0u;
+        if (fb < ntab) {
+            int grp = 0;
+            while (grp + 1 < (int)p.ngroups && fb >= (int)p.groups[grp + 1].base) ++grp;
+            const BandHeader2 *gh = reinterpret_cast<const BandHeader2 *>(p.groups[grp].blob) + (fb - (int)p.groups[grp].base);
+            const double ff = __ldg(&gh->full_first), fl = __ldg(&gh->full_last);
+            // [vif] sed2flux is NaN (-> flux 0, src/egg-gencat.cpp:2198) unless the SED covers the filter: a band no
+            // galaxy of the batch covers is skipped
+            const bool any_cov = nD >= 2 && __ldg(p.xD) * omin <= ff && __ldg(p.xD + nD - 1) * omax >= fl;
+            if (any_cov && __ldg(&gh->n) != 0) {
+                const double xlo = __ldg(&gh->f_first) / omax * (1.0 - 1e-9), xhi = __ldg(&gh->f_last) / omin * (1.0 + 1e-9);
+                const int lo = max(bis_last_le(p.xD, nD, xlo), 0), hi = min(bis_first_ge(p.xD, nD, xhi), nD - 1);
+                wd = (uint32_t)lo | ((uint32_t)hi << 15) | 0x40000000u;
+                jn0 = min(jn0, lo); jn1 = max(jn1, hi + 1);
+                if (has_bulge && nB >= 2 && __ldg(p.xB) * omin <= ff && __ldg(p.xB + nB - 1) * omax >= fl) {
+                    const int blo = max(bis_last_le(p.xB, nB, xlo), 0), bhi = min(bis_first_ge(p.xB, nB, xhi), nB - 1);
+                    wb = (uint32_t)blo | ((uint32_t)bhi << 15) | 0x40000000u;
+                    on0 = min(on0, blo); on1 = max(on1, bhi + 1);
+                }
+            }
         }
+        win[2 * fb] = wd;
+        win[2 * fb + 1] = wb;
     }
     jn0 = __reduce_min_sync(kFull, jn0); jn1 = __reduce_max_sync(kFull, jn1);
     on0 = __reduce_min_sync(kFull, on0); on1 = __reduce_max_sync(kFull, on1);
     if (lane == 0) {
-        // rows to build: the walks start at the optical node before a window and end at the one after it, in strips of 8
-        // arrivals cut at multiples of 8 (rows a walk touches beyond the nodes a band weighs must hold finite values: their
-        // weights are exactly 0); rows at or beyond nD are zero
+        // rows to build: whole strips of four arrivals (rows a walk touches beyond the nodes a band weighs must hold finite
+        // values: their weights are exactly 0); rows at or beyond the end of a grid are zero
         int4 pl = make_int4(0, -1, 0, -1);
-        if (jn1 >= jn0) {
-            pl.x = max(jn0 - (int)q.row_margin, 0) & ~(kSub - 1);
-            pl.y = min((jn1 + (int)q.row_margin) | (kSub - 1), (int)q.rowsD - 1);
-            if (has_bulge) { // the optical nodes among them
-                const int jo0 = grid[pl.x].o >= 0 ? pl.x : q.next_opt[pl.x], jo1 = grid[pl.y].o >= 0 ? pl.y : grid[pl.y].po;
-                if (jo0 <= jo1 && jo1 >= 0 && grid[jo0].o >= 0) { on0 = min(on0, grid_o(grid[jo0])); on1 = max(on1, grid_o(grid[jo1])); }
-            }
-        }
-        if (has_bulge && on1 >= on0) {
-            pl.z = max(on0 - 2, 0) & ~3;
-            pl.w = min((on1 + 2) | 3, (int)q.rowsB - 1);
-        }
+        if (jn1 >= jn0) { pl.x = jn0 & ~(kSub - 1); pl.y = min(jn1 | (kSub - 1), (int)q.rowsD - 1); }
+        if (has_bulge && on1 >= on0) { pl.z = on0 & ~(kSub - 1); pl.w = min(on1 | (kSub - 1), (int)q.rowsB - 1); }
         q.plan[bl] = pl;
     }
 }
@@ -554,31 +533,37 @@ __global__ void __launch_bounds__(512) lane_build_kernel(const __grid_constant__
     }
 }
 
-// One persistent CTA per SM.  Dynamic shared memory: the band tables of the CTA's current group, then {x, 1 / dx} of every
-// node of the disk grid.
-template <typename real>
-__global__ void __launch_bounds__(512, 1) lane_walk_kernel(const __grid_constant__ LaneParams q) {
+// One persistent CTA per SM.  Dynamic shared memory: the band tables of the CTA's current group, {x, 1 / dx} of every node of
+// the two component grids (GXS; read from global memory through L1 when they do not fit), and per warp two staging
+// buffers for SED rows with an mbarrier each.
+template <typename real, bool GXS>
+__global__ void __launch_bounds__(kWalkThreads, 1) lane_walk_kernel(const __grid_constant__ LaneParams q) {
     const FluxParams &p = q.fp;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_tab;
+    __shared__ __align__(8) uint64_t bar_rows[2 * (kWalkThreads / 32)];
     __shared__ int s_next;
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ngroups = (int)p.ngroups;
-    const GridNode *grid = q.grid;
     const uint32_t tab_sa = smem_u32(smem);
-    double2 *gxs = reinterpret_cast<double2 *>(smem + ((p.max_blob + 127) & ~127u));
-    const uint32_t gx_sa = smem_u32(gxs);
-    int16_t *ons = reinterpret_cast<int16_t *>(gxs + q.rowsD + 2); // index in the bulge grid of every disk node, -1 if not optical
-    const uint32_t on_sa = smem_u32(ons);
-    for (int j = tid; j < (int)q.rowsD + 2; j += (int)blockDim.x) {
-        const bool in = j < (int)q.rowsD;
-        gxs[j] = in ? make_double2(grid[j].x, grid[j].idxp) : make_double2(0.0, 0.0);
-        ons[j] = (int16_t)(in ? grid_o(grid[j]) : -1);
+    constexpr uint32_t kStageBytes = kStage * kLanes * sizeof(real);
+    uint8_t *after = smem + ((p.max_blob + 127) & ~127u);
+    const uint32_t stage_sa = smem_u32(after) + (uint32_t)warp * 2u * kStageBytes;
+    after += (size_t)(kWalkThreads / 32) * 2 * kStageBytes;
+    double2 *gxs = reinterpret_cast<double2 *>(after);
+    const uint32_t gxD_sa = smem_u32(gxs), gxB_sa = gxD_sa + 16u * q.rowsD;
+    if (GXS) {
+        for (int j = tid; j < (int)q.rowsD; j += (int)blockDim.x) gxs[j] = q.gxD[j];
+        for (int j = tid; j < (int)q.rowsB; j += (int)blockDim.x) gxs[q.rowsD + j] = q.gxB[j];
+    }
+    const uint32_t bar_sa = smem_u32(&bar_rows[2 * warp]);
+    if (lane == 0) {
+        mbar_init(&bar_rows[2 * warp], 1);
+        mbar_init(&bar_rows[2 * warp + 1], 1);
     }
     if (tid == 0) {
         mbar_init(&bar_tab, 1);
-        fence_mbar_init();
         // the CTAs are dealt to the groups in proportion to the groups' work
         float tot = 0.f;
         for (int k = 0; k < ngroups; ++k) tot += q.group_cost[k];
@@ -591,9 +576,10 @@ __global__ void __launch_bounds__(512, 1) lane_walk_kernel(const __grid_constant
         }
         s_next = grp;
     }
+    fence_mbar_init();
     __syncthreads();
     int grp = s_next;
-    uint32_t tab_phase = 0;
+    uint32_t tab_phase = 0, row_phases = 0;
     while (grp >= 0) {
         if (tid == 0) {
             fence_proxy_async(); // earlier generic-proxy reads of the table region precede the async writes
@@ -613,13 +599,11 @@ __global__ void __launch_bounds__(512, 1) lane_walk_kernel(const __grid_constant
             it = __shfl_sync(kFull, it, 0);
             if (it >= nitems) break;
             const uint32_t bl = it / nb, bi = it - bl * nb, fb = gbase + bi;
-            const uint32_t w = __ldg(q.win + (size_t)bl * kWinStride + fb);
-            if (!w) continue;
+            const uint2 w = __ldg(reinterpret_cast<const uint2 *>(q.win + (size_t)bl * kWinStride) + fb);
+            if (!w.x) continue;
             int ng;
             const uint64_t g = lane_galaxy(q, bl, lane, ng);
             const double opz = 1.0 + (double)__ldg(p.z + g);
-            const int jlo = (int)(w & 0x7fffu), jhi = (int)((w >> 15) & 0x7fffu);
-            const bool bulge = (w & 0x80000000u) != 0;
             const BandHeader2 &h = reinterpret_cast<const BandHeader2 *>(smem)[bi];
             BandDev B;
             B.hdr = tab_sa + bi * (uint32_t)sizeof(BandHeader2);
@@ -629,23 +613,23 @@ __global__ void __launch_bounds__(512, 1) lane_walk_kernel(const __grid_constant
             B.nsplit = (int)h.nsplit;
             B.nsa0 = h.nsplit > 0 ? B.rec + 32u * h.msplit[0] : 0xffffffffu;
             const bool two_probe = h.two_probe != 0;
-            int js, je;
-            block_arrivals(grid, q.next_opt, bulge, jlo, jhi, js, je);
-            js &= ~(kSub - 1);
-            je |= kSub - 1;
-            const real *SD = reinterpret_cast<const real *>(reinterpret_cast<const uint8_t *>(q.rows) + (size_t)bl * q.rows_stride) + lane;
-            const real *SB = SD + (size_t)q.rowsD * kLanes;
-            double totd, totb;
-            if (bulge) {
-                if (two_probe) walk_table<real, true, true>(B, grid, gx_sa, on_sa, opz, js, je, SD, SB, totd, totb);
-                else walk_table<real, false, true>(B, grid, gx_sa, on_sa, opz, js, je, SD, SB, totd, totb);
-            } else {
-                if (two_probe) walk_table<real, true, false>(B, grid, gx_sa, on_sa, opz, js, je, SD, SB, totd, totb);
-                else walk_table<real, false, false>(B, grid, gx_sa, on_sa, opz, js, je, SD, SB, totd, totb);
+            const real *SD = reinterpret_cast<const real *>(reinterpret_cast<const uint8_t *>(q.rows) + (size_t)bl * q.rows_stride);
+            double tot[2] = {0.0, 0.0}; // bulge, disk
+            // the disk on the merge_add grid, then the bulge on the optical grid
+#pragma unroll 1
+            for (int comp = 1; comp >= 0; --comp) {
+                const uint32_t wc = comp ? w.x : w.y;
+                if (!wc) continue;
+                const int js = (int)(wc & 0x7fffu) & ~(kSub - 1), je = (int)(((wc >> 15) & 0x7fffu) + 1u) | (kSub - 1);
+                const real *rows = comp ? SD : SD + (size_t)q.rowsD * kLanes;
+                const uint32_t gx_sa = comp ? gxD_sa : gxB_sa;
+                const double2 *gxg = comp ? q.gxD : q.gxB;
+                tot[comp] = two_probe ? walk_comp<real, true, GXS>(B, gx_sa, gxg, opz, js, je, rows, stage_sa, bar_sa, row_phases)
+                                      : walk_comp<real, false, GXS>(B, gx_sa, gxg, opz, js, je, rows, stage_sa, bar_sa, row_phases);
             }
             double *res = q.res + ((size_t)bl * q.ntab + fb) * 2 * kLanes + lane;
-            __stcg(res + kLanes, totd);
-            __stcg(res, totb);
+            __stcg(res + kLanes, tot[1]);
+            __stcg(res, tot[0]);
         }
         __syncthreads(); // every warp is done with the group's tables
         if (tid == 0) {
@@ -723,7 +707,7 @@ __global__ void __launch_bounds__(256) lane_finish_kernel(const __grid_constant_
     for (int col = 0; col < nbt; ++col) {
         double sd = 0.0, sb = 0.0;
         for (int fb = 0; fb < ntab; ++fb)
-            if ((int)__ldg(q.tab_col + fb) == col && __ldg(win + fb) != 0u) {
+            if ((int)__ldg(q.tab_col + fb) == col && __ldg(win + 2 * fb) != 0u) {
                 sd += __ldcg(res + (size_t)(fb * 2 + 1) * kLanes);
                 sb += __ldcg(res + (size_t)(fb * 2) * kLanes);
             }
@@ -746,7 +730,11 @@ __global__ void __launch_bounds__(256) lane_finish_kernel(const __grid_constant_
     }
 }
 
-size_t walk_smem_bytes(const LaneParams &q) { return ((q.fp.max_blob + 127) & ~size_t(127)) + ((size_t)q.rowsD + 2) * 18 + 16; }
+// shared memory of the walk kernel without / with the grids
+template <typename real> size_t walk_smem_base(const LaneParams &q) {
+    return ((q.fp.max_blob + 127) & ~size_t(127)) + (size_t)(kWalkThreads / 32) * 2 * kStage * kLanes * sizeof(real);
+}
+size_t walk_grid_bytes(const LaneParams &q) { return ((size_t)q.rowsD + q.rowsB) * 16; }
 
 template <typename real> int launch_chunk(const LaneParams &q, int num_sms, cudaStream_t st) {
     if (q.nbatch == 0) return 0;
@@ -755,10 +743,17 @@ template <typename real> int launch_chunk(const LaneParams &q, int num_sms, cuda
     lane_plan_kernel<<<(q.nbatch + 7) / 8, 256, 0, st>>>(q);
     lane_build_kernel<real><<<q.nbatch, 512, 0, st>>>(q);
     if (q.fp.ngroups > 0 && q.ntab > 0) {
-        const size_t smem = walk_smem_bytes(q);
-        e = cudaFuncSetAttribute(lane_walk_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        lane_walk_kernel<real><<<num_sms, 512, smem, st>>>(q);
+        if (q.gx_in_smem) {
+            const size_t smem = walk_smem_base<real>(q) + walk_grid_bytes(q);
+            e = cudaFuncSetAttribute(lane_walk_kernel<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            lane_walk_kernel<real, true><<<num_sms, kWalkThreads, smem, st>>>(q);
+        } else {
+            const size_t smem = walk_smem_base<real>(q);
+            e = cudaFuncSetAttribute(lane_walk_kernel<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            lane_walk_kernel<real, false><<<num_sms, kWalkThreads, smem, st>>>(q);
+        }
     }
     lane_finish_kernel<real><<<(q.nbatch + 7) / 8, 256, 0, st>>>(q);
     return (int)cudaGetLastError();
@@ -766,22 +761,10 @@ template <typename real> int launch_chunk(const LaneParams &q, int num_sms, cuda
 
 } // namespace
 
-size_t lane_kernel_smem(const LaneParams &q) { return walk_smem_bytes(q); }
-
-int lane_kernel_max_blocks_per_sm(const LaneParams &q, int precision) {
-    const size_t smem = walk_smem_bytes(q);
-    int nb = 0;
-    cudaError_t e;
-    if (precision == EGGPHOT_FP64) {
-        e = cudaFuncSetAttribute(lane_walk_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lane_walk_kernel<double>, 512, smem);
-    } else {
-        e = cudaFuncSetAttribute(lane_walk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lane_walk_kernel<float>, 512, smem);
-    }
-    return e == cudaSuccess ? nb : -(int)e;
+size_t lane_kernel_smem(const LaneParams &q, int precision) {
+    const size_t base = precision == EGGPHOT_FP64 ? walk_smem_base<double>(q) : walk_smem_base<float>(q);
+    return base + (q.gx_in_smem ? walk_grid_bytes(q) : 0);
 }
-
 int launch_lane_chunk(const LaneParams &q, int precision, int num_sms, cudaStream_t stream) {
     return precision == EGGPHOT_FP64 ? launch_chunk<double>(q, num_sms, stream) : launch_chunk<float>(q, num_sms, stream);
 }

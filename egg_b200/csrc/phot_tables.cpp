@@ -594,10 +594,23 @@ Status build_lane_tables(Prepared &P, const eggphot_opts &opts) {
                 if (P.grid_nodes[P.opt_node[o2]].o != o2)
                     return Status::error(EGGPHOT_ERR_GRID, "an optical node is missing from the disk grid");
     }
+    // ---- the optical grid as the bulge's walk reads it: its own nodes, two virtual ones, padding
+    {
+        const int nGB = lane_grid_rows(nB);
+        P.grid_nodes_b.assign((size_t)nGB, GridNode{0, 0, 0, -1, -1});
+        for (int o = 0; o < nGB; ++o) {
+            GridNode &g = P.grid_nodes_b[o];
+            if (o < nB) g.x = gb.x[o];
+            else g.x = (o == nB ? (nB ? gb.x[nB - 1] : 1.0) * 2.0 + 1.0 : P.grid_nodes_b[o - 1].x * 2.0);
+            g.idxp = o > 0 ? 1.0 / (g.x - P.grid_nodes_b[o - 1].x) : 0.0;
+        }
+    }
     // ---- band tables in groups
     size_t budget = opts.smem_table_budget;
     if (!budget) {
-        budget = kSmemPerCta - kLaneFixedSmem - (((size_t)nG + 2) * 18 + 16 + 128); // the grid's {x, idxp} live behind the tables
+        const bool fp64 = opts.precision == EGGPHOT_FP64;
+        budget = kSmemPerCta - kLaneFixedSmem - 256 - lane_stage_bytes(fp64) -
+                 (lane_gx_in_smem(fp64, nD, nB, kSmemPerCta) ? lane_gx_bytes(nD, nB) : 0); // the grid's {x, idxp} live behind the tables
     }
     // a filter whose table exceeds the budget is cut at filter nodes into pieces that feed the same output column
     std::vector<BandTable2> tabs;

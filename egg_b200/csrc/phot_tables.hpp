@@ -105,8 +105,9 @@ struct Prepared {
 
     // ---- tables of the lane kernel (phot_lane.cuh): band groups with node records, the disk grid as the walk reads it
     std::vector<BandGroup> groups2;      // blobs hold BandHeader2 + records
-    std::vector<GridNode> grid_nodes;    // [nD + 1]: the last one is the virtual node far to the red
-    std::vector<int32_t> next_opt;       // [nD + 1]: first optical node after j (nD = the virtual node)
+    std::vector<GridNode> grid_nodes;    // [lane_grid_rows(nD)]: the disk grid, two virtual nodes far to the red, padding
+    std::vector<GridNode> grid_nodes_b;  // [lane_grid_rows(nB)]: the optical grid alone, likewise ({x, idxp} only)
+    std::vector<int32_t> next_opt;       // [lane_grid_rows(nD)]: first optical node after j (nD = the virtual node)
     std::vector<int32_t> opt_node;       // [nB]: disk-grid index of every optical node
 };
 

@@ -242,18 +242,11 @@ void add_lines_lane(const Prepared &P, const Grid &g, std::vector<real> &S, cons
     }
 }
 
-template <typename real> struct SedRef {
-    const real *d, *b;
-    real disk(int j) const { return d[j]; }
-    real bulge(int o) const { return b[o]; }
-};
-
 template <typename real>
 void run2(const Prepared &P, const eggphot_galaxies &G, size_t ngal, double *fd, double *fb, double *rd, double *rb) {
     const size_t nb = P.bands.size(), nrf = P.rfbands.size();
     const int nl = P.no_nebular ? 0 : (int)P.line_lambda.size();
     const int nD = P.grid_disk.n(), nB = P.grid_bulge.n();
-    const GridNode *grid = P.grid_nodes.data();
     std::vector<uint32_t> perm(ngal);
     for (size_t g = 0; g < ngal; ++g) perm[g] = (uint32_t)g;
     std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return G.z[a] < G.z[b]; });
@@ -315,20 +308,19 @@ void run2(const Prepared &P, const eggphot_galaxies &G, size_t ngal, double *fd,
                 if (h.n == 0 || nD < 2) continue;
                 Band2 bv;
                 make_band2(blob, h, bv);
-                // union window of the batch, with margins (extra nodes weigh exactly nothing)
+                // windows of the batch on the two component grids, with margins (extra nodes weigh exactly nothing);
+                // the walk arrives at lo .. hi + 1
                 const double xlo = h.f_first / omax * (1.0 - 1e-9), xhi = h.f_last / omin * (1.0 + 1e-9);
-                int jlo = std::max(last_le(P.grid_disk.x, xlo), 0);
-                int jhi = (int)(std::lower_bound(P.grid_disk.x.begin(), P.grid_disk.x.end(), xhi) - P.grid_disk.x.begin());
-                jhi = std::min(jhi, nD - 1);
-                if (P.has_bulge) widen_window_for_bulge(grid, P.next_opt.data(), nD, jlo, jhi);
-                int js, je;
-                block_arrivals(grid, P.next_opt.data(), P.has_bulge, jlo, jhi, js, je);
-                for (int l = 0; l < ng; ++l) {
-                    double td, tb;
-                    SedRef<real> sr{SD[l].data(), SB[l].data()};
-                    walk_window<real>(bv, grid, opz[l], P.has_bulge, js, je, sr, td, tb);
-                    resd[h.out_col * kLanes + l] += td;
-                    resb[h.out_col * kLanes + l] += tb;
+                for (int comp = P.has_bulge && nB >= 2 ? 0 : 1; comp < 2; ++comp) {
+                    const Grid &gr = comp ? P.grid_disk : P.grid_bulge;
+                    const GridNode *nodes = comp ? P.grid_nodes.data() : P.grid_nodes_b.data();
+                    const int n = gr.n();
+                    const int lo = std::max(last_le(gr.x, xlo), 0);
+                    const int hi = std::min((int)(std::lower_bound(gr.x.begin(), gr.x.end(), xhi) - gr.x.begin()), n - 1);
+                    for (int l = 0; l < ng; ++l) {
+                        const double t = walk_window<real>(bv, nodes, opz[l], lo, hi + 1, comp ? SD[l].data() : SB[l].data());
+                        (comp ? resd : resb)[h.out_col * kLanes + l] += t;
+                    }
                 }
             }
         }
