@@ -178,7 +178,7 @@ int enqueue(eggphot_ctx *c, const eggphot_galaxies &g, size_t ngal, const eggpho
         q.perm = (const uint32_t *)c->zperm[region].p;
         int e = launch_zsort(g.z, (uint32_t)ngal, (uint32_t *)c->zhist[region].p, (uint32_t *)c->zperm[region].p, c->num_sms, st);
         if (e != 0) return c->cuda_fail((cudaError_t)e, "redshift bucketing launch");
-        c->launches += 3;
+        c->launches += 4;
         // the call is worked off in chunks of batches whose SED rows fit the region's buffer
         const size_t nbatch = (ngal + kLanes - 1) / kLanes, cap = std::min(nbatch, c->lane_cap_batches);
         const size_t ntab = std::max<uint32_t>(q.ntab, 1);
@@ -423,7 +423,14 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
             std::vector<uint32_t> cols;
             for (const BandGroup &g : P.groups2) cols.insert(cols.end(), g.cols.begin(), g.cols.end());
             q.ntab = (uint32_t)cols.size();
-            if (cols.empty()) cols.push_back(0);
+            // the tables of every output column, in table order
+            std::vector<uint32_t> lists(P.bands.size() + 1, 0);
+            for (size_t col = 0; col < P.bands.size(); ++col) {
+                for (size_t fb = 0; fb < cols.size(); ++fb)
+                    if (cols[fb] == col) lists.push_back((uint32_t)fb);
+                lists[col + 1] = (uint32_t)(lists.size() - P.bands.size() - 1);
+            }
+            cols = lists;
             CK(c->tabCol.upload(cols.data(), cols.size() * sizeof(uint32_t)));
             q.tab_col = (const uint32_t *)c->tabCol.p;
         }

@@ -89,7 +89,7 @@ struct LaneParams {
     const double2 *gxD, *gxB; // [rowsD], [rowsB] {x, 1 / (x - x of the node before)} of the disk / optical grid, two virtual
                               // nodes far to the red and padding behind the real ones (lane_grid_rows)
     int32_t gx_in_smem;       // the walk kernel keeps both in shared memory
-    const uint32_t *tab_col;  // [ntab] output column of every band table, in group order
+    const uint32_t *tab_col;  // [nband + 1] offsets, then [ntab] the band tables of every output column (table = index in group order)
     const double2 *col_span;  // [nband] full wavelength span of every filter (coverage test), by output column
     uint32_t ntab;            // band tables (a filter cut into pieces has several); at most 64
     uint64_t batch0;          // first batch of the chunk (index into perm / 32)

@@ -36,24 +36,55 @@ namespace eggphot {
 namespace {
 
 // ---- redshift bucketing -----------------------------------------------------------------------------
-constexpr int kZBuckets = 1 << 16;
-__device__ __forceinline__ int zbucket(float z) {
-    // log2(1+z) in [0, 8) -> 65536 buckets: (1+z) resolved to 8.5e-5; anything else (NaN, z < 0, z > 255) to the ends
-    const float v = __log2f(1.0f + fmaxf(z, 0.0f)) * (float)(kZBuckets / 8);
+// Counting sort by log2(1+z) in [0, 8): 2^16 buckets ((1+z) resolved to 8.5e-5) for small catalogs, up to 2^22 for large
+// ones (about two galaxies per bucket: the lanes of a batch then sit as close in redshift as the catalog allows).
+// Anything else (NaN, z < 0, z > 255) goes to the ends.
+constexpr int kZBucketsMin = 1 << 16, kZBucketsMax = 1 << 22;
+constexpr int kScanBlock = 2048; // counters per block of the scan
+__device__ __forceinline__ int zbucket(float z, int nbuckets) {
+    const float v = __log2f(1.0f + fmaxf(z, 0.0f)) * (float)(nbuckets / 8);
     int k = (int)v;
-    return k < 0 ? 0 : (k > kZBuckets - 1 ? kZBuckets - 1 : k);
+    return k < 0 ? 0 : (k > nbuckets - 1 ? nbuckets - 1 : k);
 }
-__global__ void zsort_count(const float *__restrict__ z, uint32_t n, uint32_t *__restrict__ hist) {
+__global__ void zsort_count(const float *__restrict__ z, uint32_t n, uint32_t *__restrict__ hist, int nbuckets) {
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x)
-        atomicAdd(&hist[zbucket(__ldg(z + g))], 1u);
+        atomicAdd(&hist[zbucket(__ldg(z + g), nbuckets)], 1u);
 }
-// exclusive prefix sums of the 65536 counters, one block of 1024 threads (64 counters each)
-__global__ void __launch_bounds__(1024) zsort_scan(uint32_t *__restrict__ hist) {
+// exclusive prefix sums inside blocks of 2048 counters (256 threads, eight consecutive counters each); the block totals go
+// to bsum
+__global__ void __launch_bounds__(256) zsort_scan_blocks(uint32_t *__restrict__ hist, uint32_t *__restrict__ bsum) {
+    __shared__ uint32_t wsum[8];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    uint4 *h4 = reinterpret_cast<uint4 *>(hist + (size_t)blockIdx.x * kScanBlock) + 2 * t;
+    uint4 a = h4[0], b = h4[1];
+    const uint32_t c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += c[k];
+    uint32_t inc = s; // inclusive scan over the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int k = 0; k < w; ++k) base += wsum[k];
+    if (t == 255) bsum[blockIdx.x] = base + inc;
+    uint32_t run = base + inc - s;
+    uint32_t e[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { e[k] = run; run += c[k]; }
+    h4[0] = make_uint4(e[0], e[1], e[2], e[3]);
+    h4[1] = make_uint4(e[4], e[5], e[6], e[7]);
+}
+// exclusive prefix sums of the block totals (at most 2048: one block of 1024 threads, two each)
+__global__ void __launch_bounds__(1024) zsort_scan_totals(uint32_t *__restrict__ bsum, int nblk) {
     __shared__ uint32_t part[1024];
     const int t = threadIdx.x;
-    uint32_t s = 0;
-    for (int k = 0; k < kZBuckets / 1024; ++k) s += hist[t * (kZBuckets / 1024) + k];
-    part[t] = s;
+    const uint32_t c0 = 2 * t < nblk ? bsum[2 * t] : 0u, c1 = 2 * t + 1 < nblk ? bsum[2 * t + 1] : 0u;
+    part[t] = c0 + c1;
     __syncthreads();
     for (int o = 1; o < 1024; o <<= 1) {
         const uint32_t v = t >= o ? part[t - o] : 0u;
@@ -61,16 +92,16 @@ __global__ void __launch_bounds__(1024) zsort_scan(uint32_t *__restrict__ hist) 
         part[t] += v;
         __syncthreads();
     }
-    uint32_t run = part[t] - s;
-    for (int k = 0; k < kZBuckets / 1024; ++k) {
-        const uint32_t c = hist[t * (kZBuckets / 1024) + k];
-        hist[t * (kZBuckets / 1024) + k] = run;
-        run += c;
-    }
+    const uint32_t run = part[t] - (c0 + c1);
+    if (2 * t < nblk) bsum[2 * t] = run;
+    if (2 * t + 1 < nblk) bsum[2 * t + 1] = run + c0;
 }
-__global__ void zsort_scatter(const float *__restrict__ z, uint32_t n, uint32_t *__restrict__ cursor, uint32_t *__restrict__ perm) {
-    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x)
-        perm[atomicAdd(&cursor[zbucket(__ldg(z + g))], 1u)] = g;
+__global__ void zsort_scatter(const float *__restrict__ z, uint32_t n, uint32_t *__restrict__ cursor, const uint32_t *__restrict__ bsum,
+                              uint32_t *__restrict__ perm, int nbuckets) {
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
+        const int k = zbucket(__ldg(z + g), nbuckets);
+        perm[__ldg(bsum + k / kScanBlock) + atomicAdd(&cursor[k], 1u)] = g;
+    }
 }
 
 // ---- FMA micro-benchmark: the measured peak of the CUDA-core FP32 / FP64 pipes (the roofline of SURVEY.md 8d) ---------
@@ -294,24 +325,47 @@ __device__ __forceinline__ double walk_comp(const BandDev &B, uint32_t gx_sa, co
                 }
                 ra[k] = a;
             }
-            // (2) intervals and weights
+            // (2) intervals and weights.  Most strips have, for every lane, each node in a filter cell of its own and no split
+            // node under them: then E = (Lambda_in - Lambda_out of the node before) / dt and nothing else is needed.
+            bool plain = ra[kSub - 1] <= Pnsa && ra[0] != Pra; // (the cells of a walk never go back: the last one is the reddest)
 #pragma unroll
-            for (int k = 0; k < kSub; ++k) {
-                const Recs R = load_recs(B, ra[k]);
-                const double2 G = load_gx(j0 + k);
-                const real S = lds_real<real>(srow + (uint32_t)(h * kSub + k) * kRowBytes);
-                const double t = opz * G.x; // the reference's lam = rlam * (1 + z) (src/egg-gencat.cpp:2161), in double
-                const double u = t - R.a0.x, v = t - R.a1.x;
-                const double Lin = fma(u, fma(u, R.b0.y, R.b0.x), R.a0.y);
-                const double Lout = fma(v, fma(v, R.b1.y, R.b1.x), R.a1.y);
-                // close [j - 1, j], settle node j - 1
-                double Eadj;
-                uint32_t nsa_c;
-                const double E = interval_dev(B, Pu, PLout, Pra, Pnsa, ra[k], u, Lin, R.b0.x, R.b0.y, R.hs, t, G.y, opz, Eadj, nsa_c);
-                acc = fma(to_real<real>(E - Eprev), Sprev, acc);
-                Eprev = Eadj;
-                Sprev = S;
-                Pu = u; PLout = Lout; Pra = ra[k]; Pnsa = nsa_c;
+            for (int k = 1; k < kSub; ++k) plain = plain && ra[k] != ra[k - 1];
+            if (__all_sync(kFull, plain)) {
+#pragma unroll
+                for (int k = 0; k < kSub; ++k) {
+                    const double2 a0 = lds_v2f64(ra[k]), b0 = lds_v2f64(ra[k] + 16u), a1 = lds_v2f64(ra[k] + 32u), b1 = lds_v2f64(ra[k] + 48u);
+                    const double2 G = load_gx(j0 + k);
+                    const real S = lds_real<real>(srow + (uint32_t)(h * kSub + k) * kRowBytes);
+                    const double t = opz * G.x;
+                    const double u = t - a0.x, v = t - a1.x;
+                    const double Lin = fma(u, fma(u, b0.y, b0.x), a0.y);
+                    const double E = (Lin - PLout) * G.y;
+                    PLout = fma(v, fma(v, b1.y, b1.x), a1.y);
+                    acc = fma(to_real<real>(E - Eprev), Sprev, acc);
+                    Eprev = E;
+                    Sprev = S;
+                    Pu = u;
+                }
+                Pra = ra[kSub - 1];
+            } else {
+#pragma unroll
+                for (int k = 0; k < kSub; ++k) {
+                    const Recs R = load_recs(B, ra[k]);
+                    const double2 G = load_gx(j0 + k);
+                    const real S = lds_real<real>(srow + (uint32_t)(h * kSub + k) * kRowBytes);
+                    const double t = opz * G.x; // the reference's lam = rlam * (1 + z) (src/egg-gencat.cpp:2161), in double
+                    const double u = t - R.a0.x, v = t - R.a1.x;
+                    const double Lin = fma(u, fma(u, R.b0.y, R.b0.x), R.a0.y);
+                    const double Lout = fma(v, fma(v, R.b1.y, R.b1.x), R.a1.y);
+                    // close [j - 1, j], settle node j - 1
+                    double Eadj;
+                    uint32_t nsa_c;
+                    const double E = interval_dev(B, Pu, PLout, Pra, Pnsa, ra[k], u, Lin, R.b0.x, R.b0.y, R.hs, t, G.y, opz, Eadj, nsa_c);
+                    acc = fma(to_real<real>(E - Eprev), Sprev, acc);
+                    Eprev = Eadj;
+                    Sprev = S;
+                    Pu = u; PLout = Lout; Pra = ra[k]; Pnsa = nsa_c;
+                }
             }
             // the sums of a strip of 16 arrivals are formed in `real`, the strips added in double: strips are cut at absolute
             // node numbers, so the result does not depend on where the walk started
@@ -325,6 +379,7 @@ __device__ __forceinline__ double walk_comp(const BandDev &B, uint32_t gx_sa, co
 constexpr int kWinStride = 128; // window words per batch in LaneParams::win: {disk, bulge} of at most 64 band tables
 
 constexpr int kSegRows = 256;   // rows per warp of the build kernel
+constexpr int kBuildThreads = 128;
 
 // lane -> galaxy of batch bl of the chunk (lanes beyond the end of the catalog repeat the batch's first galaxy)
 __device__ __forceinline__ uint64_t lane_galaxy(const LaneParams &q, uint32_t bl, int lane, int &ng) {
@@ -397,14 +452,56 @@ __global__ void __launch_bounds__(256) lane_plan_kernel(const __grid_constant__ 
     }
 }
 
+// Rows s0..s1 of one component for the 32 galaxies of a warp: v = a * rowA (+ b * rowB (+ c * rowC)), times the IGM factor
+// below node igm[3]; 16 bytes of every template row per load, [node][lane] stores.  The template rows are zero from the
+// end of the grid to their stride, and rows beyond the stride are written as zeros.
+template <typename real, int NROW>
+__device__ __forceinline__ void build_rows(real *__restrict__ dst, int s0, int s1, int stride, const real *__restrict__ rowA, real a,
+                                           const real *__restrict__ rowB, real b, const real *__restrict__ rowC, real c, bool apply_igm,
+                                           const int32_t *igm, real g0f, real g1f, real g2f) {
+    constexpr int NPL = 16 / (int)sizeof(real);
+    const int igm_end = apply_igm ? igm[3] : 0;
+    real *d = dst + (size_t)s0 * kLanes;
+#pragma unroll 4
+    for (int j0 = s0; j0 <= s1; j0 += NPL, d += NPL * kLanes) { // (unrolled: a dozen row loads in flight)
+        real v[NPL];
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) v[k] = real(0);
+        if (j0 < stride) {
+            const Vec16<real> A = ldg16(rowA + j0);
+#pragma unroll
+            for (int k = 0; k < NPL; ++k) v[k] = a * A.v[k];
+            if (NROW >= 2) {
+                const Vec16<real> B = ldg16(rowB + j0);
+#pragma unroll
+                for (int k = 0; k < NPL; ++k) v[k] = a * A.v[k] + b * B.v[k];
+            }
+            if (NROW >= 3) {
+                const Vec16<real> C = ldg16(rowC + j0);
+#pragma unroll
+                for (int k = 0; k < NPL; ++k) v[k] += c * C.v[k];
+            }
+            if (j0 < igm_end) { // (a few rows in the far UV)
+#pragma unroll
+                for (int k = 0; k < NPL; ++k)
+                    if (j0 + k < igm_end) v[k] *= igm_factor<real>(j0 + k, igm[0], igm[1], igm[2], igm[3], g0f, g1f, g2f);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) __stcg(d + k * kLanes, v[k]);
+    }
+}
+
 // A CTA per batch, a warp per segment of 256 rows: rest-frame SEDs, lane = galaxy, 16 bytes of each template row per
 // load, [node][lane] stores; then the emission lines of the segment's nodes.  The bulge SED carries no mass scale
 // (applied at the end).
 template <typename real>
-__global__ void __launch_bounds__(512) lane_build_kernel(const __grid_constant__ LaneParams q) {
+__global__ void __launch_bounds__(kBuildThreads) lane_build_kernel(const __grid_constant__ LaneParams q) {
     const FluxParams &p = q.fp;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const uint32_t bl = blockIdx.x;
+    // gridDim.x / nbatch CTAs share a batch: together they have a warp for every segment the grids can have
+    const uint32_t per_batch = gridDim.x / q.nbatch, bl = blockIdx.x / per_batch;
+    const int lane = threadIdx.x & 31, warp = (int)(blockIdx.x - bl * per_batch) * (kBuildThreads / 32) + (threadIdx.x >> 5);
+    const int nwarp = (int)per_batch * (kBuildThreads / 32);
     const int4 pl = q.plan[bl];
     const int nsegD = pl.y >= pl.x ? (pl.y - pl.x + kSegRows) / kSegRows : 0;
     const int nsegB = pl.w >= pl.z ? (pl.w - pl.z + kSegRows) / kSegRows : 0;
@@ -458,41 +555,20 @@ __global__ void __launch_bounds__(512) lane_build_kernel(const __grid_constant__
         const int s1 = min(s0 + kSegRows - 1, disk ? pl.y : pl.w);
         if (disk) {
             const real *rowO = rO + (size_t)rd * p.strideD, *rowI = rI + (size_t)ri * p.strideD, *rowP = rP + (size_t)ri * p.strideD;
-#pragma unroll 4
-            for (int j0 = s0; j0 <= s1; j0 += NPL) { // (unrolled: a dozen row loads in flight)
-                Vec16<real> o, i, pq;
-#pragma unroll
-                for (int k = 0; k < NPL; ++k) o.v[k] = i.v[k] = pq.v[k] = real(0);
-                if (j0 < p.strideD) {
-                    if (p.disk_mode != 2) o = ldg16(rowO + j0);
-                    if (p.disk_mode != 1) i = ldg16(rowI + j0);
-                    if (p.disk_mode != 1 && cs17) pq = ldg16(rowP + j0);
-                }
-#pragma unroll
-                for (int k = 0; k < NPL; ++k) {
-                    real v = a_d * o.v[k] + c1 * i.v[k]; // absent terms are zero
-                    if (p.disk_mode != 1 && cs17) v += c2 * pq.v[k];
-                    if (p.apply_igm && j0 + k < p.igmD[3])
-                        v *= igm_factor<real>(j0 + k, p.igmD[0], p.igmD[1], p.igmD[2], p.igmD[3], g0f, g1f, g2f);
-                    __stcg(SD + (size_t)(j0 + k) * kLanes + lane, j0 + k < nD ? v : real(0));
-                }
+            // a_d * optical + c1 * IR (+ c2 * PAH): the reference's sums in its order (absent terms are absent)
+            if (p.disk_mode == 2) {
+                if (cs17) build_rows<real, 2>(SD + lane, s0, s1, p.strideD, rowI, c1, rowP, c2, rowP, real(0), p.apply_igm, p.igmD, g0f, g1f, g2f);
+                else build_rows<real, 1>(SD + lane, s0, s1, p.strideD, rowI, c1, rowI, real(0), rowI, real(0), p.apply_igm, p.igmD, g0f, g1f, g2f);
+            } else if (p.disk_mode == 1) {
+                build_rows<real, 1>(SD + lane, s0, s1, p.strideD, rowO, a_d, rowO, real(0), rowO, real(0), p.apply_igm, p.igmD, g0f, g1f, g2f);
+            } else if (cs17) {
+                build_rows<real, 3>(SD + lane, s0, s1, p.strideD, rowO, a_d, rowI, c1, rowP, c2, p.apply_igm, p.igmD, g0f, g1f, g2f);
+            } else {
+                build_rows<real, 2>(SD + lane, s0, s1, p.strideD, rowO, a_d, rowI, c1, rowI, real(0), p.apply_igm, p.igmD, g0f, g1f, g2f);
             }
         } else {
-            const real *rowB = rB + (size_t)rb * p.strideB;
-#pragma unroll 4
-            for (int j0 = s0; j0 <= s1; j0 += NPL) {
-                Vec16<real> o;
-#pragma unroll
-                for (int k = 0; k < NPL; ++k) o.v[k] = real(0);
-                if (j0 < p.strideB) o = ldg16(rowB + j0);
-#pragma unroll
-                for (int k = 0; k < NPL; ++k) {
-                    real v = o.v[k];
-                    if (p.apply_igm && j0 + k < p.igmB[3])
-                        v *= igm_factor<real>(j0 + k, p.igmB[0], p.igmB[1], p.igmB[2], p.igmB[3], g0f, g1f, g2f);
-                    __stcg(SB + (size_t)(j0 + k) * kLanes + lane, j0 + k < nB ? v : real(0));
-                }
-            }
+            build_rows<real, 1>(SB + lane, s0, s1, p.strideB, rB + (size_t)rb * p.strideB, real(1), rB, real(0), rB, real(0), p.apply_igm, p.igmB,
+                                g0f, g1f, g2f);
         }
         // emission lines (add_emission_line, src/egg-gencat.cpp:2078-2095): every lane deposits the lines of its own
         // galaxy, in wavelength order, on the nodes of the segment (its own stores: no synchronisation needed)
@@ -658,7 +734,7 @@ __global__ void __launch_bounds__(256) lane_finish_kernel(const __grid_constant_
     const int lane = threadIdx.x & 31;
     const uint32_t bl = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (bl >= q.nbatch) return;
-    const int nbt = (int)p.nband_total, ntab = (int)q.ntab, nrf = p.do_rf ? (int)p.nrf : 0;
+    const int nbt = (int)p.nband_total, nrf = p.do_rf ? (int)p.nrf : 0;
     const int nD = p.nD, nB = p.nB;
     const bool has_bulge = p.has_bulge != 0;
     int ng;
@@ -706,11 +782,14 @@ __global__ void __launch_bounds__(256) lane_finish_kernel(const __grid_constant_
     const double *res = q.res + (size_t)bl * q.ntab * 2 * kLanes + lane;
     for (int col = 0; col < nbt; ++col) {
         double sd = 0.0, sb = 0.0;
-        for (int fb = 0; fb < ntab; ++fb)
-            if ((int)__ldg(q.tab_col + fb) == col && __ldg(win + 2 * fb) != 0u) {
+        // the tables of the column, in table order (q.tab_col: [nband + 1] offsets, then the lists)
+        for (uint32_t k = __ldg(q.tab_col + col), k1 = __ldg(q.tab_col + col + 1); k < k1; ++k) {
+            const uint32_t fb = __ldg(q.tab_col + nbt + 1 + k);
+            if (__ldg(win + 2 * fb) != 0u) {
                 sd += __ldcg(res + (size_t)(fb * 2 + 1) * kLanes);
                 sb += __ldcg(res + (size_t)(fb * 2) * kLanes);
             }
+        }
         const double2 cv = __ldg(q.col_span + col);
         // [vif] sed2flux: NaN (-> flux 0, src/egg-gencat.cpp:2198) unless the SED covers the filter
         const bool covd = covd_any && xd0 <= cv.x && xd1 >= cv.y;
@@ -741,7 +820,11 @@ template <typename real> int launch_chunk(const LaneParams &q, int num_sms, cuda
     cudaError_t e = cudaMemsetAsync(q.counters, 0, kMaxGroups * sizeof(uint32_t), st);
     if (e != cudaSuccess) return (int)e;
     lane_plan_kernel<<<(q.nbatch + 7) / 8, 256, 0, st>>>(q);
-    lane_build_kernel<real><<<q.nbatch, 512, 0, st>>>(q);
+    {
+        const uint32_t nseg = (q.rowsD + kSegRows - 1) / kSegRows + (q.rowsB + kSegRows - 1) / kSegRows;
+        const uint32_t per_batch = (nseg + kBuildThreads / 32 - 1) / (kBuildThreads / 32);
+        lane_build_kernel<real><<<q.nbatch * per_batch, kBuildThreads, 0, st>>>(q);
+    }
     if (q.fp.ngroups > 0 && q.ntab > 0) {
         if (q.gx_in_smem) {
             const size_t smem = walk_smem_base<real>(q) + walk_grid_bytes(q);
@@ -770,17 +853,22 @@ int launch_lane_chunk(const LaneParams &q, int precision, int num_sms, cudaStrea
 }
 
 int launch_zsort(const float *z, uint32_t ngal, uint32_t *hist, uint32_t *perm, int num_sms, cudaStream_t st) {
-    cudaError_t e = cudaMemsetAsync(hist, 0, kZBuckets * sizeof(uint32_t), st);
+    int nbuckets = kZBucketsMin;
+    while (nbuckets < kZBucketsMax && (uint32_t)nbuckets * 2u <= ngal) nbuckets *= 2;
+    const int nblk = nbuckets / kScanBlock;
+    uint32_t *bsum = hist + kZBucketsMax;
+    cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)nbuckets * sizeof(uint32_t), st);
     if (e != cudaSuccess) return (int)e;
     if (ngal == 0) return 0;
     const uint32_t want = (ngal + 255) / 256, cap = (uint32_t)num_sms * 8;
     const int blocks = (int)(want < cap ? want : cap);
-    zsort_count<<<blocks, 256, 0, st>>>(z, ngal, hist);
-    zsort_scan<<<1, 1024, 0, st>>>(hist);
-    zsort_scatter<<<blocks, 256, 0, st>>>(z, ngal, hist, perm);
+    zsort_count<<<blocks, 256, 0, st>>>(z, ngal, hist, nbuckets);
+    zsort_scan_blocks<<<nblk, 256, 0, st>>>(hist, bsum);
+    zsort_scan_totals<<<1, 1024, 0, st>>>(bsum, nblk);
+    zsort_scatter<<<blocks, 256, 0, st>>>(z, ngal, hist, bsum, perm, nbuckets);
     return (int)cudaGetLastError();
 }
-size_t zsort_hist_bytes() { return kZBuckets * sizeof(uint32_t); }
+size_t zsort_hist_bytes() { return ((size_t)kZBucketsMax + kZBucketsMax / kScanBlock) * sizeof(uint32_t); }
 
 // TFLOP/s (2 flops per FMA) of back-to-back independent FMA chains on every SM, best of five runs
 template <typename T> static int fma_peak(int num_sms, void *scratch, cudaStream_t st, double &tflops) {

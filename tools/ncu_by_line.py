@@ -18,13 +18,13 @@ for r in rows:
     if r and r[0] == "Line No":
         hdr = r
         ii, si = hdr.index("Instructions Executed"), hdr.index("# Samples")
-        wi = hdr.index("L1 Wavefronts Shared")
+        wi = hdr.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in hdr else -1
         gi = hdr.index("L2 Theoretical Sectors Global")
         continue
     if hdr is None or len(r) != len(hdr) or r[0].strip() == "":
         continue  # rows without a line number are the SASS children of the preceding source row
     try:
-        inst, samp, wf, gs = int(r[ii]), int(r[si]), int(r[wi]), int(r[gi])
+        inst, samp, wf, gs = int(r[ii]), int(r[si]), (int(r[wi]) if wi >= 0 else 0), int(r[gi])
     except ValueError:
         continue
     a = agg[(cur_file, r[0])]
