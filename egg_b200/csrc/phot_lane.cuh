@@ -203,9 +203,9 @@ EGG_HD double interval_E(const Band2 &b, const NodeEv &p, const NodeEv &e, doubl
 // interval [j-1, j] and settles the weight of node j-1.  js is at or before the last node left of the table's span, je
 // after the first node right of it: every node outside the span has the weight 0 exactly for every galaxy of the batch,
 // so the window may be wider than a galaxy needs.  The walk starts from a state blue of every filter.  Terms are summed
-// in `real` over strips of 16 arrivals cut at absolute node numbers ([16 k, 16 k + 15]) and the strips added in double:
+// in `real` over strips of four arrivals cut at absolute node numbers ([4 k, 4 k + 3]) and the strips added in double:
 // the sum does not depend on where the walk starts.
-constexpr int kLaneStrip = 16;
+constexpr int kLaneStrip = 4;
 template <typename real>
 EGG_HD double walk_window(const Band2 &bv, const GridNode *grid, double opz, int js, int je, const real *sed) {
     NodeEv prev, cur;

@@ -304,10 +304,10 @@ __device__ __forceinline__ double walk_comp(const BandDev &B, uint32_t gx_sa, co
         mbar_wait_sa(bar_sa + 8u * buf, (phases >> buf) & 1u);
         phases ^= 1u << buf;
         const uint32_t srow = stage_sa + buf * kStageBytes + (uint32_t)lane * (uint32_t)sizeof(real);
-#pragma unroll 1
+#pragma unroll
         for (int h = 0; h < kStage / kSub; ++h) {
             const int j0 = jg + h * kSub;
-            if (j0 > je) break;
+            if (h > 0 && j0 > je) break;
             // (1) filter cells
             uint32_t ra[kSub];
 #pragma unroll
@@ -347,7 +347,8 @@ __device__ __forceinline__ double walk_comp(const BandDev &B, uint32_t gx_sa, co
                     Pu = u;
                 }
                 Pra = ra[kSub - 1];
-            } else {
+            } else if (__all_sync(kFull, ra[kSub - 1] <= Pnsa)) {
+                // no split node under the strip: shared cells only
 #pragma unroll
                 for (int k = 0; k < kSub; ++k) {
                     const Recs R = load_recs(B, ra[k]);
@@ -356,23 +357,43 @@ __device__ __forceinline__ double walk_comp(const BandDev &B, uint32_t gx_sa, co
                     const double t = opz * G.x; // the reference's lam = rlam * (1 + z) (src/egg-gencat.cpp:2161), in double
                     const double u = t - R.a0.x, v = t - R.a1.x;
                     const double Lin = fma(u, fma(u, R.b0.y, R.b0.x), R.a0.y);
+                    const double Esame = opz * fma(R.hs * Pu, u, fma(Pu + u, R.b0.y, R.b0.x));
+                    const double E = ra[k] == Pra ? Esame : (Lin - PLout) * G.y;
+                    PLout = fma(v, fma(v, R.b1.y, R.b1.x), R.a1.y);
+                    acc = fma(to_real<real>(E - Eprev), Sprev, acc);
+                    Eprev = E;
+                    Sprev = S;
+                    Pu = u; Pra = ra[k];
+                }
+            } else {
+                // a split node under the strip (once or twice per walk)
+#pragma unroll 1
+                for (int k = 0; k < kSub; ++k) {
+                    const uint32_t rak = k == 0 ? ra[0] : (k == 1 ? ra[1] : (k == 2 ? ra[2] : ra[3]));
+                    const Recs R = load_recs(B, rak);
+                    const double2 G = load_gx(j0 + k);
+                    const real S = lds_real<real>(srow + (uint32_t)(h * kSub + k) * kRowBytes);
+                    const double t = opz * G.x;
+                    const double u = t - R.a0.x, v = t - R.a1.x;
+                    const double Lin = fma(u, fma(u, R.b0.y, R.b0.x), R.a0.y);
                     const double Lout = fma(v, fma(v, R.b1.y, R.b1.x), R.a1.y);
                     // close [j - 1, j], settle node j - 1
                     double Eadj;
                     uint32_t nsa_c;
-                    const double E = interval_dev(B, Pu, PLout, Pra, Pnsa, ra[k], u, Lin, R.b0.x, R.b0.y, R.hs, t, G.y, opz, Eadj, nsa_c);
+                    const double E = interval_dev(B, Pu, PLout, Pra, Pnsa, rak, u, Lin, R.b0.x, R.b0.y, R.hs, t, G.y, opz, Eadj, nsa_c);
                     acc = fma(to_real<real>(E - Eprev), Sprev, acc);
                     Eprev = Eadj;
                     Sprev = S;
-                    Pu = u; PLout = Lout; Pra = ra[k]; Pnsa = nsa_c;
+                    Pu = u; PLout = Lout; Pra = rak; Pnsa = nsa_c;
                 }
             }
-            // the sums of a strip of 16 arrivals are formed in `real`, the strips added in double: strips are cut at absolute
-            // node numbers, so the result does not depend on where the walk started
-            if ((j0 & 15) == 16 - kSub) { tot += (double)acc; acc = real(0); }
+            // the sum of a strip of four arrivals is formed in `real`, the strips are added in double: strips are cut at
+            // absolute node numbers, so the result does not depend on where the walk started
+            tot += (double)acc;
+            acc = real(0);
         }
     }
-    return tot + (double)acc;
+    return tot;
 }
 
 // ---- the kernels --------------------------------------------------------------------------------------
@@ -380,6 +401,7 @@ constexpr int kWinStride = 128; // window words per batch in LaneParams::win: {d
 
 constexpr int kSegRows = 256;   // rows per warp of the build kernel
 constexpr int kBuildThreads = 128;
+constexpr int kFinishThreads = 128;
 
 // lane -> galaxy of batch bl of the chunk (lanes beyond the end of the catalog repeat the batch's first galaxy)
 __device__ __forceinline__ uint64_t lane_galaxy(const LaneParams &q, uint32_t bl, int lane, int &ng) {
@@ -729,11 +751,12 @@ __global__ void __launch_bounds__(kWalkThreads, 1) lane_walk_kernel(const __grid
 // A warp per batch: rest-frame magnitudes; table sums added per output column in table order, data conditions, totals
 // (src/egg-gencat.cpp:2238-2239), catalog columns.
 template <typename real>
-__global__ void __launch_bounds__(256) lane_finish_kernel(const __grid_constant__ LaneParams q) {
+__global__ void __launch_bounds__(kFinishThreads) lane_finish_kernel(const __grid_constant__ LaneParams q) {
     const FluxParams &p = q.fp;
-    const int lane = threadIdx.x & 31;
-    const uint32_t bl = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (bl >= q.nbatch) return;
+    // a CTA per batch: its warps share the output columns (and the rest-frame bands) of the batch's 32 galaxies
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kWarps = kFinishThreads / 32;
+    const uint32_t bl = blockIdx.x;
     const int nbt = (int)p.nband_total, nrf = p.do_rf ? (int)p.nrf : 0;
     const int nD = p.nD, nB = p.nB;
     const bool has_bulge = p.has_bulge != 0;
@@ -746,7 +769,7 @@ __global__ void __launch_bounds__(256) lane_finish_kernel(const __grid_constant_
     if (nrf > 0) {
         const real *SD = reinterpret_cast<const real *>(reinterpret_cast<const uint8_t *>(q.rows) + (size_t)bl * q.rows_stride);
         const real *SB = SD + (size_t)q.rowsD * kLanes;
-        for (int r = 0; r < nrf; ++r) {
+        for (int r = warp; r < nrf; r += kWarps) {
             const double arf = EGGPHOT_LSUN2UJY / (1e-5 * 1e-5);
             double mg[2] = {0.0, 0.0}; // the bulge column stays 0 when there is no bulge pass (no_stellar)
             for (int comp = has_bulge ? 0 : 1; comp < 2; ++comp) {
@@ -780,7 +803,7 @@ __global__ void __launch_bounds__(256) lane_finish_kernel(const __grid_constant_
     const double xb0 = covb_any ? __ldg(p.xB) * opz : 0.0, xb1 = covb_any ? __ldg(p.xB + nB - 1) * opz : 0.0;
     const uint32_t *win = q.win + (size_t)bl * kWinStride;
     const double *res = q.res + (size_t)bl * q.ntab * 2 * kLanes + lane;
-    for (int col = 0; col < nbt; ++col) {
+    for (int col = warp; col < nbt; col += kWarps) {
         double sd = 0.0, sb = 0.0;
         // the tables of the column, in table order (q.tab_col: [nband + 1] offsets, then the lists)
         for (uint32_t k = __ldg(q.tab_col + col), k1 = __ldg(q.tab_col + col + 1); k < k1; ++k) {
@@ -838,7 +861,7 @@ template <typename real> int launch_chunk(const LaneParams &q, int num_sms, cuda
             lane_walk_kernel<real, false><<<num_sms, kWalkThreads, smem, st>>>(q);
         }
     }
-    lane_finish_kernel<real><<<(q.nbatch + 7) / 8, 256, 0, st>>>(q);
+    lane_finish_kernel<real><<<q.nbatch, kFinishThreads, 0, st>>>(q);
     return (int)cudaGetLastError();
 }
 
