@@ -47,11 +47,12 @@ struct DevBuf {
     }
 };
 
-constexpr int kSlots = 2;
+constexpr int kSlots = 4;   // staging slots of the host-memory entry point (chunks in flight: copy in / compute / copy out)
+constexpr int kLanesC = 2;  // compute streams (consecutive chunks alternate: the tail of one chunk's kernels overlaps the next's)
 
 // device staging of one chunk of galaxies for the host-memory entry point
 struct Slot {
-    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr; // inputs landed / kernels done / outputs back on the host
     DevBuf z, d, m_disk, m_bulge, m2lcor, lir, fpah, mdust, igm_abs, vdisp, lld, llb, osd, osb, irs;
     DevBuf flux, flux_disk, flux_bulge, rfmag, rfmag_disk, rfmag_bulge, fd64, fb64, rd64, rb64;
 };
@@ -74,15 +75,16 @@ struct eggphot_ctx {
     uint64_t launches = 0;
     uint64_t table_bytes = 0;
     Slot slots[kSlots];
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_c[kLanesC] = {nullptr, nullptr};
     size_t chunk = 0;
     // the lane-per-galaxy kernel (phot_lane_kernels.cu): its own band groups, grid records, scratch and, per scratch
     // region, the redshift-bucketing buffers.  EGGPHOT_KERNEL=node selects the node-per-lane kernel of phot_kernels.cu.
     bool use_lane = true;
     std::vector<DevBuf> blobs2;
     DevBuf gridN, nextOpt, tabCol, colSpan;
-    DevBuf zhist[kSlots + 1], zperm[kSlots + 1];
+    DevBuf zhist[kLanesC + 1], zperm[kLanesC + 1];
     // per region: SED rows, band-table windows, build ranges, table sums and item counters of one chunk of batches
-    DevBuf lrows[kSlots + 1], lwin[kSlots + 1], lplan[kSlots + 1], lres[kSlots + 1], lcnt[kSlots + 1];
+    DevBuf lrows[kLanesC + 1], lwin[kLanesC + 1], lplan[kLanesC + 1], lres[kLanesC + 1], lcnt[kLanesC + 1];
     LaneParams lbase{};
     size_t lane_cap_batches = 0; // batches per chunk (bounds the SED rows of a region)
 
@@ -253,8 +255,11 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
     if (prop.major < 10) return c->fail(EGGPHOT_ERR_CUDA, "device is not sm_100 class (kernels are built for sm_100a only)");
     c->num_sms = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return c->cuda_fail(e, "cudaStreamCreate");
+    for (cudaStream_t *st : {&c->s_in, &c->s_out, &c->s_c[0], &c->s_c[1]})
+        if ((e = cudaStreamCreateWithFlags(st, cudaStreamNonBlocking)) != cudaSuccess) return c->cuda_fail(e, "cudaStreamCreate");
     for (auto &s : c->slots)
-        if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess) return c->cuda_fail(e, "cudaStreamCreate");
+        for (cudaEvent_t *ev : {&s.ev_in, &s.ev_k, &s.ev_out})
+            if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return c->cuda_fail(e, "cudaEventCreate");
 
     // ---- tables
     uint64_t tb = 0;
@@ -387,7 +392,7 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
         c->scratch_region_bytes = ((size_t)c->grid_blocks * p.batch * (size_t)(2 * c->strideD + c->strideB) * rs + 255) & ~size_t(255);
         const char *sel = getenv("EGGPHOT_KERNEL");
         c->use_lane = !(sel && (std::string(sel) == "node" || std::string(sel) == "1"));
-        if (!c->use_lane) CK(c->scratch.alloc(c->scratch_region_bytes * (kSlots + 1)));
+        if (!c->use_lane) CK(c->scratch.alloc(c->scratch_region_bytes * (kLanesC + 1)));
         p.scratch = c->scratch.p;
     }
     // ---- the lane kernel's tables, scratch and bucketing buffers
@@ -418,6 +423,7 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
         }
         q.gxD = (const double2 *)c->gridN.p;
         q.gxB = (const double2 *)c->nextOpt.p;
+        q.item_mode = getenv("EGGPHOT_ITEM_MODE") ? (uint32_t)atoi(getenv("EGGPHOT_ITEM_MODE")) : 2u;
         q.gx_in_smem = lane_gx_in_smem(P.precision == EGGPHOT_FP64, P.grid_disk.n(), P.grid_bulge.n(), kSmemPerCta) ? 1 : 0;
         {
             std::vector<uint32_t> cols;
@@ -474,7 +480,9 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
 void eggphot_destroy(eggphot_ctx *c) {
     if (!c) return;
     if (c->stream) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
-    for (auto &s : c->slots) if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+    for (cudaStream_t st : {c->s_in, c->s_out, c->s_c[0], c->s_c[1]}) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (auto &s : c->slots)
+        for (cudaEvent_t ev : {s.ev_in, s.ev_k, s.ev_out}) if (ev) cudaEventDestroy(ev);
     delete c;
 }
 
@@ -525,10 +533,14 @@ int eggphot_compute(eggphot_ctx *c, const eggphot_galaxies *gal, size_t ngal, co
     c->launches = 0;
     const Prepared &P = c->P;
     const size_t nb = P.bands.size(), nrf = P.rfbands.size(), nl = P.no_nebular ? 0 : P.line_lambda.size();
-    // chunks: large enough to fill every SM several times over, small enough that the copies of one
-    // chunk overlap the kernel of the other (two streams): an eighth of the catalog, within [2^15, 2^18]
-    size_t chunk = std::min<size_t>(std::max<size_t>((ngal + 7) / 8, 1u << 15), 1u << 18);
-    if (c->use_lane) chunk = (std::min<size_t>(std::max<size_t>((ngal + 7) / 8, 1u << 15), 1u << 20) + kLanes - 1) / kLanes * kLanes;
+    // chunks: large enough that the kernels run at their large-catalog rate (the walk kernel is persistent: 2^15 galaxies
+    // are seven items per warp), small enough that the first copy in and the last copy out, which nothing overlaps, are a
+    // small part of the call: a quarter of the catalog, within [2^15, 2^20]
+    size_t chunk = (std::min<size_t>(std::max<size_t>((ngal + 3) / 4, 1u << 15), 1u << 20) + kLanes - 1) / kLanes * kLanes;
+    if (const char *ev = getenv("EGGPHOT_CHUNK")) { // tuning knob: galaxies per chunk of the host-memory entry point
+        const long long v = atoll(ev);
+        if (v > 0) chunk = ((size_t)v + kLanes - 1) / kLanes * kLanes;
+    }
     chunk = std::min(chunk, ngal);
     if (chunk == 0) return EGGPHOT_OK;
 #define CK(x) do { if ((e = (x)) != cudaSuccess) return c->cuda_fail(e, #x); } while (0)
@@ -549,16 +561,54 @@ int eggphot_compute(eggphot_ctx *c, const eggphot_galaxies *gal, size_t ngal, co
         for (const Col &k : ins) if (k.src && k.elem) CK((s.*(k.buf)).alloc(chunk * k.elem));
         for (const OCol &k : outs) if (k.dst && k.elem) CK((s.*(k.buf)).alloc(chunk * k.elem));
     }
-    // chunk k: H2D, kernels, D2H all on slot (k mod 2)'s stream; the two streams overlap each other's
-    // copies and kernels
-    size_t k = 0;
-    for (size_t first = 0; first < ngal; first += chunk, ++k) {
+    // Three stages on their own streams: copies in (s_in), kernels (s_c, consecutive chunks alternating between two streams so
+    // that the tail of one chunk's kernels overlaps the head of the next's), copies out (s_out).  Chunk k stages through slot
+    // k mod 4: its inputs may be overwritten once the kernels of chunk k - 4 are done, its outputs once they are back on the
+    // host.  PCIe runs in both directions under the kernels; only the first copy in and the last copy out are exposed.
+    // EGGPHOT_TRACE=1: device-side timeline of the chunks (events on the chunk streams), printed to stderr after the call
+    const bool trace = getenv("EGGPHOT_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, st);
+        tev.push_back(ev);
+    };
+    // The chunks: half a chunk first and last (the first copy in and the last copy out are the only ones nothing overlaps),
+    // whole chunks between them.
+    std::vector<size_t> sizes;
+    {
+        const bool taper = !getenv("EGGPHOT_NO_TAPER");
+        const size_t half = ((chunk / 2) + kLanes - 1) / kLanes * kLanes;
+        size_t left = ngal;
+        if (taper && ngal > 2 * chunk) { sizes.push_back(half); left -= half; }
+        while (left > 0) {
+            if (taper && ngal > 2 * chunk && left <= chunk + half) {
+                if (left > half + 8192) { sizes.push_back(left - half); left = half; }
+                sizes.push_back(left);
+                left = 0;
+            } else {
+                const size_t n = std::min(chunk, left);
+                sizes.push_back(n);
+                left -= n;
+            }
+        }
+    }
+    // kernels of consecutive chunks: one stream (chunk k is done, and on its way out, before chunk k + 1 starts) unless
+    // EGGPHOT_CSTREAMS=2
+    const int ncs = getenv("EGGPHOT_CSTREAMS") && atoi(getenv("EGGPHOT_CSTREAMS")) == 1 ? 1 : 2;
+    size_t first = 0;
+    for (size_t k = 0; k < sizes.size(); first += sizes[k], ++k) {
         Slot &s = c->slots[k % kSlots];
-        const size_t n = std::min(chunk, ngal - first);
+        cudaStream_t sc = c->s_c[k % ncs];
+        const size_t n = sizes[k];
+        if (k >= (size_t)kSlots) CK(cudaStreamWaitEvent(c->s_in, s.ev_k, 0));
+        mark(c->s_in);
         for (const Col &col : ins)
             if (col.src && col.elem)
                 CK(cudaMemcpyAsync((s.*(col.buf)).p, (const char *)col.src + first * col.elem, n * col.elem,
-                                   cudaMemcpyHostToDevice, s.stream));
+                                   cudaMemcpyHostToDevice, c->s_in));
         eggphot_galaxies dg{};
         dg.z = (const float *)s.z.p; dg.d = (const float *)s.d.p; dg.m_disk = (const float *)s.m_disk.p;
         dg.m_bulge = (const float *)s.m_bulge.p; dg.m2lcor = (const float *)s.m2lcor.p; dg.lir = (const float *)s.lir.p;
@@ -578,14 +628,32 @@ int eggphot_compute(eggphot_ctx *c, const eggphot_galaxies *gal, size_t ngal, co
         dout.flux_bulge_f64 = out->flux_bulge_f64 ? (double *)s.fb64.p : nullptr;
         dout.rfmag_disk_f64 = out->rfmag_disk_f64 ? (double *)s.rd64.p : nullptr;
         dout.rfmag_bulge_f64 = out->rfmag_bulge_f64 ? (double *)s.rb64.p : nullptr;
-        rc = enqueue(c, dg, n, dout, s.stream, 1 + (int)(k % kSlots));
+        mark(c->s_in);
+        CK(cudaEventRecord(s.ev_in, c->s_in));
+        CK(cudaStreamWaitEvent(sc, s.ev_in, 0));
+        if (k >= (size_t)kSlots) CK(cudaStreamWaitEvent(sc, s.ev_out, 0));
+        rc = enqueue(c, dg, n, dout, sc, 1 + (int)(k % ncs));
         if (rc) return rc;
+        mark(sc);
+        CK(cudaEventRecord(s.ev_k, sc));
+        CK(cudaStreamWaitEvent(c->s_out, s.ev_k, 0));
         for (const OCol &col : outs)
             if (col.dst && col.elem)
                 CK(cudaMemcpyAsync((char *)col.dst + first * col.elem, (s.*(col.buf)).p, n * col.elem,
-                                   cudaMemcpyDeviceToHost, s.stream));
+                                   cudaMemcpyDeviceToHost, c->s_out));
+        mark(c->s_out);
+        CK(cudaEventRecord(s.ev_out, c->s_out));
     }
-    for (auto &s : c->slots) CK(cudaStreamSynchronize(s.stream));
+    CK(cudaStreamSynchronize(c->s_out));
+    for (cudaStream_t st : {c->s_in, c->s_c[0], c->s_c[1]}) CK(cudaStreamSynchronize(st));
+    if (trace) {
+        for (size_t i = 0; i + 3 < tev.size(); i += 4) {
+            float t[4];
+            for (int j = 0; j < 4; ++j) cudaEventElapsedTime(&t[j], tev[0], tev[i + j]);
+            fprintf(stderr, "eggphot trace: chunk %zu  h2d %.3f-%.3f  kernels -%.3f  d2h -%.3f ms\n", i / 4, t[0], t[1], t[2], t[3]);
+        }
+        for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
+    }
 #undef CK
     return read_error_flag(c);
 }

@@ -102,6 +102,8 @@ struct LaneParams {
     double *res;              // [nbatch][ntab][2][32 lanes] table sums (bulge, disk)
     uint32_t *counters;       // [kMaxGroups] items handed out per band group
     float group_cost[kMaxGroups]; // relative work of the groups (deals the CTAs to the groups)
+    uint32_t item_mode;       // order of a group's (batch, table) items: 0 batches outermost, 1 the heavier half of the tables for
+                              // every batch and then the lighter half, 2 tables outermost (heaviest first)
 };
 size_t lane_kernel_smem(const LaneParams &q, int precision);
 // plan + build + walk + finish of one chunk; returns cudaError_t as int

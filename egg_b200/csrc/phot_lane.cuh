@@ -65,6 +65,7 @@ struct alignas(32) Rec { double f, L, k0, hr; };
 // span needs no special case (its expansions are exactly 0).  bkt has one entry in front and one behind the real
 // buckets for those two cells.
 constexpr int kMaxSplit = 6;
+constexpr uint32_t kBktRecMask = 0x7fffu, kBktStep2 = 0x8000u; // a bucket entry: record number, "step two records" flag
 struct __attribute__((aligned(16))) BandHeader2 {
     double full_first, full_last; // full span of the whole filter [um] for the coverage test ([vif] sed2flux NaN rule)
     double f_first, f_last;       // span of this table [um]
@@ -86,7 +87,8 @@ struct Band2 {
     const BandHeader2 *h;  // split constants are read from the header when an interval crosses a split
     const Rec *rec;
     const double *hs;      // half the slope of R in the cell whose left node is record r (0 in zero-width cells)
-    const uint16_t *bkt;   // last record whose node is at or below the (slightly lowered) start of the bucket
+    const uint16_t *bkt;   // last record whose node is at or below the (slightly lowered) start of the bucket; bit 15
+                           // (kBktStep2): the next node is two records at one wavelength
     double bk_scale, bk_c0;
     int m0, nsplit, nbkt;  // m0 = msplit[0]
     bool two_probe;
@@ -160,10 +162,11 @@ EGG_HD int round_lo(double y) {
 EGG_HD void eval_node(const Band2 &b, double t, NodeEv &e) {
     int k = round_lo(fma(t, b.bk_scale, b.bk_c0));
     k = k < 0 ? 0 : (k > b.nbkt - 1 ? b.nbkt - 1 : k);
-    int r = b.bkt[k];
+    const int be = b.bkt[k];
+    int r = be & (int)kBktRecMask;
     if (b.two_probe) {
-        r += t >= b.rec[r + 1].f ? 1 : 0;
-        r += t >= b.rec[r + 1].f ? 1 : 0; // a split node or an abrupt end is two records at one wavelength
+        // one probe; a split node or an abrupt end is two records at one wavelength, and the entry says so
+        if (t >= b.rec[r + 1].f) r += (be & (int)kBktStep2) ? 2 : 1;
     } else {
         while (t >= b.rec[r + 1].f) ++r;
     }

@@ -280,7 +280,10 @@ __device__ __forceinline__ double walk_comp(const BandDev &B, uint32_t gx_sa, co
                                             const real *__restrict__ rows, uint32_t stage_sa, uint32_t bar_sa, uint32_t &phases) {
     const int lane = threadIdx.x & 31;
     constexpr uint32_t kRowBytes = kLanes * sizeof(real), kStageBytes = kStage * kRowBytes;
-    auto load_gx = [&](int j) -> double2 { return GXS ? lds_v2f64(gx_sa + 16u * (uint32_t)j) : __ldg(gxg + j); };
+    // x of node j for the cell lookups, 1 / dx for the intervals: one 8-byte load each (a warp-uniform 16-byte load costs two
+    // wavefronts of the shared-memory pipe, and the walk is bound by that pipe)
+    auto load_x = [&](int j) -> double { return GXS ? lds_f64(gx_sa + 16u * (uint32_t)j) : __ldg(&gxg[j].x); };
+    auto load_idx = [&](int j) -> double { return GXS ? lds_f64(gx_sa + 16u * (uint32_t)j + 8u) : __ldg(&gxg[j].y); };
     double Pu = 0.0, PLout = 0.0, Eprev = 0.0, tot = 0.0; // state of the previous node
     uint32_t Pra = 0u, Pnsa = B.nsa0;
     real Sprev = real(0), acc = real(0);
@@ -310,20 +313,24 @@ __device__ __forceinline__ double walk_comp(const BandDev &B, uint32_t gx_sa, co
             if (h > 0 && j0 > je) break;
             // (1) filter cells
             uint32_t ra[kSub];
+            double tn[kSub]; // observed wavelengths of the strip's nodes: the reference's lam = rlam * (1 + z) (src/egg-gencat.cpp:2161), in double
 #pragma unroll
             for (int k = 0; k < kSub; ++k) {
-                const double t = opz * load_gx(j0 + k).x;
+                const double t = opz * load_x(j0 + k);
                 int kk = round_lo(fma(t, B.bk_scale, B.bk_c0));
                 kk = min(max(kk, 0), B.nbkt_m1);
-                uint32_t a = B.rec + 32u * lds_u16(B.bkt + 2u * (uint32_t)kk);
+                const uint32_t e = lds_u16(B.bkt + 2u * (uint32_t)kk);
+                uint32_t a = B.rec + 32u * (e & kBktRecMask);
                 if (TWOP) {
-                    // a split node or an abrupt end is two records at one wavelength: two probes, both read at once
-                    const double f1 = lds_f64(a + 32u), f2 = lds_f64(a + 64u);
-                    a += (t >= f1 ? 32u : 0u) + (t >= f2 ? 32u : 0u);
+                    // one probe: the bucket entry says how far to step when t is at or beyond the next node (two records where
+                    // that node is a split node or an abrupt end: two records at one wavelength)
+                    const double f1 = lds_f64(a + 32u);
+                    a += t >= f1 ? 32u + ((e >> 10) & 32u) : 0u;
                 } else {
                     while (t >= lds_f64(a + 32u)) a += 32u;
                 }
                 ra[k] = a;
+                tn[k] = t;
             }
             // (2) intervals and weights.  Most strips have, for every lane, each node in a filter cell of its own and no split
             // node under them: then E = (Lambda_in - Lambda_out of the node before) / dt and nothing else is needed.
@@ -334,12 +341,12 @@ __device__ __forceinline__ double walk_comp(const BandDev &B, uint32_t gx_sa, co
 #pragma unroll
                 for (int k = 0; k < kSub; ++k) {
                     const double2 a0 = lds_v2f64(ra[k]), b0 = lds_v2f64(ra[k] + 16u), a1 = lds_v2f64(ra[k] + 32u), b1 = lds_v2f64(ra[k] + 48u);
-                    const double2 G = load_gx(j0 + k);
+                    const double idx = load_idx(j0 + k);
                     const real S = lds_real<real>(srow + (uint32_t)(h * kSub + k) * kRowBytes);
-                    const double t = opz * G.x;
+                    const double t = tn[k];
                     const double u = t - a0.x, v = t - a1.x;
                     const double Lin = fma(u, fma(u, b0.y, b0.x), a0.y);
-                    const double E = (Lin - PLout) * G.y;
+                    const double E = (Lin - PLout) * idx;
                     PLout = fma(v, fma(v, b1.y, b1.x), a1.y);
                     acc = fma(to_real<real>(E - Eprev), Sprev, acc);
                     Eprev = E;
@@ -352,13 +359,13 @@ __device__ __forceinline__ double walk_comp(const BandDev &B, uint32_t gx_sa, co
 #pragma unroll
                 for (int k = 0; k < kSub; ++k) {
                     const Recs R = load_recs(B, ra[k]);
-                    const double2 G = load_gx(j0 + k);
+                    const double idx = load_idx(j0 + k);
                     const real S = lds_real<real>(srow + (uint32_t)(h * kSub + k) * kRowBytes);
-                    const double t = opz * G.x; // the reference's lam = rlam * (1 + z) (src/egg-gencat.cpp:2161), in double
+                    const double t = tn[k];
                     const double u = t - R.a0.x, v = t - R.a1.x;
                     const double Lin = fma(u, fma(u, R.b0.y, R.b0.x), R.a0.y);
                     const double Esame = opz * fma(R.hs * Pu, u, fma(Pu + u, R.b0.y, R.b0.x));
-                    const double E = ra[k] == Pra ? Esame : (Lin - PLout) * G.y;
+                    const double E = ra[k] == Pra ? Esame : (Lin - PLout) * idx;
                     PLout = fma(v, fma(v, R.b1.y, R.b1.x), R.a1.y);
                     acc = fma(to_real<real>(E - Eprev), Sprev, acc);
                     Eprev = E;
@@ -371,16 +378,16 @@ __device__ __forceinline__ double walk_comp(const BandDev &B, uint32_t gx_sa, co
                 for (int k = 0; k < kSub; ++k) {
                     const uint32_t rak = k == 0 ? ra[0] : (k == 1 ? ra[1] : (k == 2 ? ra[2] : ra[3]));
                     const Recs R = load_recs(B, rak);
-                    const double2 G = load_gx(j0 + k);
+                    const double idx = load_idx(j0 + k);
                     const real S = lds_real<real>(srow + (uint32_t)(h * kSub + k) * kRowBytes);
-                    const double t = opz * G.x;
+                    const double t = opz * load_x(j0 + k);
                     const double u = t - R.a0.x, v = t - R.a1.x;
                     const double Lin = fma(u, fma(u, R.b0.y, R.b0.x), R.a0.y);
                     const double Lout = fma(v, fma(v, R.b1.y, R.b1.x), R.a1.y);
                     // close [j - 1, j], settle node j - 1
                     double Eadj;
                     uint32_t nsa_c;
-                    const double E = interval_dev(B, Pu, PLout, Pra, Pnsa, rak, u, Lin, R.b0.x, R.b0.y, R.hs, t, G.y, opz, Eadj, nsa_c);
+                    const double E = interval_dev(B, Pu, PLout, Pra, Pnsa, rak, u, Lin, R.b0.x, R.b0.y, R.hs, t, idx, opz, Eadj, nsa_c);
                     acc = fma(to_real<real>(E - Eprev), Sprev, acc);
                     Eprev = Eadj;
                     Sprev = S;
@@ -696,7 +703,16 @@ __global__ void __launch_bounds__(kWalkThreads, 1) lane_walk_kernel(const __grid
             if (lane == 0) it = atomicAdd(q.counters + grp, 1u);
             it = __shfl_sync(kFull, it, 0);
             if (it >= nitems) break;
-            const uint32_t bl = it / nb, bi = it - bl * nb, fb = gbase + bi;
+            // Tables are stored heaviest first.  Handing out the heavy tables of every batch before the light ones keeps the
+            // items that are in flight when the counter runs out short (a long item started last is the kernel's tail).
+            uint32_t bl, bi;
+            if (q.item_mode == 2u) { bi = it / q.nbatch; bl = it - bi * q.nbatch; }
+            else if (q.item_mode == 1u && nb > 1u) {
+                const uint32_t nbh = nb / 2u, first = q.nbatch * nbh;
+                if (it < first) { bl = it / nbh; bi = it - bl * nbh; }
+                else { const uint32_t i2 = it - first, nbl = nb - nbh; bl = i2 / nbl; bi = nbh + (i2 - bl * nbl); }
+            } else { bl = it / nb; bi = it - bl * nb; }
+            const uint32_t fb = gbase + bi;
             const uint2 w = __ldg(reinterpret_cast<const uint2 *>(q.win + (size_t)bl * kWinStride) + fb);
             if (!w.x) continue;
             int ng;

@@ -479,6 +479,16 @@ Status build_band_table2(const Filter &f, int i0, int i1, uint32_t out_col, int 
     }
     t.bkt[0] = 0;
     t.bkt[nb + 1] = (uint16_t)last_node;
+    if (nrec > (int)kBktRecMask) return Status::error(EGGPHOT_ERR_UNSUPPORTED, "a band table with more than 32767 records");
+    if (t.h.two_probe) {
+        // one probe settles the lookup when the entry also says how far to step: two records where the next node is stored
+        // twice (a split node, an abrupt end: two records at one wavelength), one otherwise.  A bucket that starts in cell r
+        // ends before the node after next (it is narrower than every cell of non-zero width).
+        for (int k = 0; k < nb + 2; ++k) {
+            const int rr = t.bkt[k];
+            if (rr + 2 <= nrec && t.rec[rr + 1].f == t.rec[rr + 2].f) t.bkt[k] = (uint16_t)(rr | kBktStep2);
+        }
+    }
     return Status();
 }
 

@@ -29,12 +29,15 @@ class EggphotError(RuntimeError):
         self.code = code
 
 
-def load_library(path: str = _LIB_PATH):
+def load_library(path: str = None):
     """dlopen libeggphot.so and declare its entry points.  Raises if it is missing (build it with
-    ``make -C egg_b200/csrc`` or ``__graft_entry__.build()``)."""
+    ``make -C egg_b200/csrc`` or ``__graft_entry__.build()``).  EGGPHOT_LIB names another build of the same library
+    (tools/build_variant.sh: kernel tuning experiments)."""
     global _lib
     if _lib is not None:
         return _lib
+    if path is None:
+        path = os.environ.get("EGGPHOT_LIB") or _LIB_PATH
     if not os.path.exists(path):
         raise ImportError(f"{path} is missing: the CUDA extension has not been built; there is no CPU fallback")
     L = C.CDLL(path)

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Key numbers of one kernel from an ncu report: `python tools/ncu_summary.py rep.ncu-rep`
+"""Key numbers of one kernel from an ncu report: `python tools/ncu_summary.py rep.ncu-rep [launch]`
 (time, instructions, issue utilisation, pipe utilisation, stall reasons, memory traffic)."""
 import csv
 import subprocess
@@ -8,7 +8,9 @@ import sys
 rep = sys.argv[1]
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-h, u, v = rows[0], rows[1], rows[2]
+h, u = rows[0], rows[1]
+v = rows[2 + (int(sys.argv[2]) if len(sys.argv) > 2 else 0)]  # optional second argument: which launch of the report
+print("kernel:", v[h.index("Kernel Name")])
 d = {n: (v[i], u[i]) for i, n in enumerate(h)}
 keys = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "smsp__warps_eligible.avg.per_cycle_active", "smsp__warps_active.avg.per_cycle_active",
