@@ -81,7 +81,7 @@ struct eggphot_ctx {
     // region, the redshift-bucketing buffers.  EGGPHOT_KERNEL=node selects the node-per-lane kernel of phot_kernels.cu.
     bool use_lane = true;
     std::vector<DevBuf> blobs2;
-    DevBuf gridN, nextOpt, tabCol, colSpan;
+    DevBuf gridN, nextOpt, tabCol, colSpan, altFl, altFr, altOff;
     DevBuf zhist[kLanesC + 1], zperm[kLanesC + 1];
     // per region: SED rows, band-table windows, build ranges, table sums and item counters of one chunk of batches
     DevBuf lrows[kLanesC + 1], lwin[kLanesC + 1], lplan[kLanesC + 1], lres[kLanesC + 1], lcnt[kLanesC + 1];
@@ -420,6 +420,14 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
             q.fp.groups[g].base = g ? q.fp.groups[g - 1].base + q.fp.groups[g - 1].nb : 0;
             if (q.fp.groups[g].nb > (uint32_t)kMaxGroupBands) return c->fail(EGGPHOT_ERR_UNSUPPORTED, "more than 64 bands in one group");
             q.fp.max_blob = std::max(q.fp.max_blob, q.fp.groups[g].bytes);
+        }
+        q.nodes_mode = (uint32_t)P.nodes_mode;
+        if (P.nodes_mode != EGGPHOT_NODES_MERGED) {
+            if (!c->use_lane) return c->fail(EGGPHOT_ERR_UNSUPPORTED, "sed2flux_nodes=sed|filter needs the lane pipeline (unset EGGPHOT_KERNEL)");
+            CK(c->altFl.upload(P.alt_fl.data(), P.alt_fl.size() * sizeof(double)));
+            CK(c->altFr.upload(P.alt_fr.data(), P.alt_fr.size() * sizeof(double)));
+            CK(c->altOff.upload(P.alt_off.data(), P.alt_off.size() * sizeof(uint32_t)));
+            q.alt_fl = (const double *)c->altFl.p; q.alt_fr = (const double *)c->altFr.p; q.alt_off = (const uint32_t *)c->altOff.p;
         }
         q.gxD = (const double2 *)c->gridN.p;
         q.gxB = (const double2 *)c->nextOpt.p;

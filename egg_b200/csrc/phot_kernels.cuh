@@ -102,6 +102,10 @@ struct LaneParams {
     double *res;              // [nbatch][ntab][2][32 lanes] table sums (bulge, disk)
     uint32_t *counters;       // [kMaxGroups] items handed out per band group
     float group_cost[kMaxGroups]; // relative work of the groups (deals the CTAs to the groups)
+    // node sets `sed` / `filter` of [vif] sed2flux (EGGPHOT_NODES_*; 0 = merged: the walk kernel): the filters as they are
+    uint32_t nodes_mode;
+    const double *alt_fl, *alt_fr; // wavelengths / responses of the sorted bands, concatenated
+    const uint32_t *alt_off;       // [nband + 1]
     uint32_t item_mode;       // order of a group's (batch, table) items: 0 batches outermost, 1 the heavier half of the tables for
                               // every batch and then the lighter half, 2 tables outermost (heaviest first)
 };

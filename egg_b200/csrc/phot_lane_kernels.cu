@@ -128,9 +128,6 @@ __device__ __forceinline__ Vec16<double> ldg16(const double *p) {
     const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
     return Vec16<double>{{a.x, a.y}};
 }
-// The SED rows of a batch live in HBM by the time the bands read them (16 batches per SM are in flight): every trip of
-// the walk asks L2 for the rows it will need kPrefetchRows nodes later, so that the loads themselves hit L2.
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // last j in [0, n) with x[j] <= v (-1 if none) / first j with x[j] >= v (n if none): plain bisection in double
 __device__ __forceinline__ int bis_last_le(const double *__restrict__ x, int n, double v) {
@@ -576,7 +573,6 @@ __global__ void __launch_bounds__(kBuildThreads) lane_build_kernel(const __grid_
     real g0f = real(1), g1f = real(1), g2f = real(1);
     if (p.apply_igm) { g0f = __ldg(p.igm_abs + 3 * g); g1f = __ldg(p.igm_abs + 3 * g + 1); g2f = __ldg(p.igm_abs + 3 * g + 2); }
     const double vd = nline > 0 ? (double)__ldg(p.vdisp + g) / 2.998e5 : 0.0;
-    constexpr int NPL = 16 / (int)sizeof(real);
 
     for (int seg = warp; seg < nsegD + nsegB; seg += nwarp) {
         const bool disk = seg < nsegD;
@@ -764,6 +760,94 @@ __global__ void __launch_bounds__(kWalkThreads, 1) lane_walk_kernel(const __grid
     }
 }
 
+// ---- node sets `sed` and `filter` of [vif] sed2flux ------------------------------------------------------------
+// The reference's sources do not say on which nodes vif's sed2flux (src/egg-gencat.cpp:2197) applies the trapezoid rule
+// (SURVEY.md 8c).  The contract is the merged set (the walk kernel above); the two other readings are computed here so
+// that `egg-gencat-b200 check sed2flux_nodes=...` can try them against a catalog written by the real program:
+//   sed    - the SED nodes strictly inside the filter span and the span's two ends, the response interpolated at them;
+//   filter - the filter's own nodes, the SED interpolated at them.
+// Plain two-cursor walks of the filter as given, lane = galaxy, a warp per (batch, band), everything in double: this is
+// a diagnostic path, not a hot one.  Returns (1 + z) times the integral over observed wavelength of R times the rows'
+// Y = lambda L, the unit of the walk kernel's sums (the finish kernel applies K / d^2).
+__device__ __forceinline__ double lerp2d(double y1, double y2, double x1, double x2, double x) { return y1 + (y2 - y1) * (x - x1) / (x2 - x1); }
+template <typename real>
+__device__ double alt_nodes_sum(int mode, int nf, const double *__restrict__ fl, const double *__restrict__ fr, const double *__restrict__ x, int n,
+                                double opz, const real *__restrict__ S) {
+    auto lam = [&](int j) -> double { return __ldg(x + j) * opz; }; // lam = rlam * (1 + z), src/egg-gencat.cpp:2161
+    auto sed = [&](int j) -> double { return (double)__ldcg(S + (size_t)j * kLanes); };
+    if (nf < 2 || n < 2) return 0.0;
+    const double f0 = __ldg(fl), xend = __ldg(fl + nf - 1);
+    if (!(lam(0) <= f0 && lam(n - 1) >= xend)) return 0.0; // not covered: [vif] sed2flux is NaN, the flux 0 (:2198)
+    int k; // last node at or below the filter's first wavelength
+    {
+        int lo = 0, hi = n;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (lam(mid) <= f0) lo = mid; else hi = mid;
+        }
+        k = lo;
+    }
+    double acc = 0.0;
+    if (mode == EGGPHOT_NODES_FILTER) {
+        double pg = 0.0, px = f0;
+        for (int i = 0; i < nf; ++i) {
+            const double fi = __ldg(fl + i);
+            while (k + 2 < n && lam(k + 1) <= fi) ++k;
+            const double g = __ldg(fr + i) * lerp2d(sed(k), sed(k + 1), lam(k), lam(k + 1), fi);
+            if (i > 0) acc += 0.5 * (pg + g) * (fi - px);
+            pg = g; px = fi;
+        }
+        return acc * opz;
+    }
+    if (k >= n - 1) k = n - 2;
+    int fi = 0;
+    double px = f0;
+    double pg = __ldg(fr) * lerp2d(sed(k), sed(k + 1), lam(k), lam(k + 1), px);
+    int si = k + 1;
+    while (si < n && lam(si) <= px) ++si;
+    while (px < xend) {
+        const double xs = si < n ? lam(si) : __longlong_as_double(0x7ff0000000000000LL);
+        const bool at_sed = xs < xend; // else the walk closes at the filter's last wavelength
+        const double xx = at_sed ? xs : xend;
+        while (fi + 2 < nf && __ldg(fl + fi + 1) <= xx) ++fi;
+        const double r = xx >= xend ? __ldg(fr + nf - 1) : lerp2d(__ldg(fr + fi), __ldg(fr + fi + 1), __ldg(fl + fi), __ldg(fl + fi + 1), xx);
+        double sv;
+        if (at_sed || xs == xend) sv = sed(si);
+        else {
+            const int j = max(si - 1, 0), j1 = j + 1 < n ? j + 1 : j;
+            sv = j1 == j ? sed(j) : lerp2d(sed(j), sed(j1), lam(j), lam(j1), xx);
+        }
+        const double g = r * sv;
+        acc += 0.5 * (pg + g) * (xx - px);
+        px = xx; pg = g;
+        if (at_sed || xs == xend) ++si;
+    }
+    return acc * opz;
+}
+
+template <typename real>
+__global__ void __launch_bounds__(128) lane_alt_kernel(const __grid_constant__ LaneParams q) {
+    const FluxParams &p = q.fp;
+    const int lane = threadIdx.x & 31;
+    const uint32_t item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t nbt = p.nband_total;
+    if (item >= q.nbatch * nbt) return;
+    const uint32_t bl = item / nbt, col = item - bl * nbt; // (one header-only table per band: table = column)
+    const uint2 w = __ldg(reinterpret_cast<const uint2 *>(q.win + (size_t)bl * kWinStride) + col);
+    int ng;
+    const uint64_t g = lane_galaxy(q, bl, lane, ng);
+    const double opz = 1.0 + (double)__ldg(p.z + g);
+    const uint32_t o0 = __ldg(q.alt_off + col), o1 = __ldg(q.alt_off + col + 1);
+    const real *SD = reinterpret_cast<const real *>(reinterpret_cast<const uint8_t *>(q.rows) + (size_t)bl * q.rows_stride) + lane;
+    const real *SB = SD + (size_t)q.rowsD * kLanes;
+    double td = 0.0, tb = 0.0;
+    if (w.x) td = alt_nodes_sum<real>((int)q.nodes_mode, (int)(o1 - o0), q.alt_fl + o0, q.alt_fr + o0, p.xD, p.nD, opz, SD);
+    if (w.y) tb = alt_nodes_sum<real>((int)q.nodes_mode, (int)(o1 - o0), q.alt_fl + o0, q.alt_fr + o0, p.xB, p.nB, opz, SB);
+    double *res = q.res + ((size_t)bl * q.ntab + col) * 2 * kLanes + lane;
+    __stcg(res + kLanes, td);
+    __stcg(res, tb);
+}
+
 // A warp per batch: rest-frame magnitudes; table sums added per output column in table order, data conditions, totals
 // (src/egg-gencat.cpp:2238-2239), catalog columns.
 template <typename real>
@@ -864,7 +948,9 @@ template <typename real> int launch_chunk(const LaneParams &q, int num_sms, cuda
         const uint32_t per_batch = (nseg + kBuildThreads / 32 - 1) / (kBuildThreads / 32);
         lane_build_kernel<real><<<q.nbatch * per_batch, kBuildThreads, 0, st>>>(q);
     }
-    if (q.fp.ngroups > 0 && q.ntab > 0) {
+    if (q.nodes_mode != EGGPHOT_NODES_MERGED) {
+        if (q.ntab > 0) lane_alt_kernel<real><<<(q.nbatch * q.ntab + 3) / 4, 128, 0, st>>>(q);
+    } else if (q.fp.ngroups > 0 && q.ntab > 0) {
         if (q.gx_in_smem) {
             const size_t smem = walk_smem_base<real>(q) + walk_grid_bytes(q);
             e = cudaFuncSetAttribute(lane_walk_kernel<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -230,7 +230,7 @@ void append_band(std::vector<uint8_t> &blob, size_t header_pos, const BandTableD
 
 // Rest-frame weights of one band on one grid (flux_rf = sum_j S_j w_j): the union-node trapezoid of
 // [vif] sed2flux walked directly in double at z = 0, applied to the hat function of every node.
-RfWeights rf_weights(const Filter &f, const Grid &g) {
+RfWeights rf_weights(const Filter &f, const Grid &g, int nodes_mode) {
     RfWeights r;
     const int N = g.n(), nf = (int)f.lam.size();
     r.covered = N >= 2 && nf >= 2 && g.x.front() <= f.lam.front() && g.x.back() >= f.lam.back();
@@ -241,9 +241,11 @@ RfWeights rf_weights(const Filter &f, const Grid &g) {
     if (jhi <= jlo) return r;
     r.j0 = jlo;
     r.w.assign(jhi - jlo + 1, 0.0);
-    // union nodes: filter nodes and the SED nodes strictly inside the filter span
+    // nodes of the trapezoid: filter nodes and the SED nodes strictly inside the filter span (merged); the two ends of
+    // the filter and the SED nodes inside (sed); the filter nodes alone (filter)
     std::vector<double> u(f.lam);
-    for (int j = jlo; j <= jhi; ++j)
+    if (nodes_mode == EGGPHOT_NODES_SED) u = {f.lam.front(), f.lam.back()};
+    for (int j = jlo; j <= jhi && nodes_mode != EGGPHOT_NODES_FILTER; ++j)
         if (g.x[j] > f.lam.front() && g.x[j] < f.lam.back()) u.push_back(g.x[j]);
     std::sort(u.begin(), u.end());
     u.erase(std::unique(u.begin(), u.end()), u.end());
@@ -258,7 +260,15 @@ RfWeights rf_weights(const Filter &f, const Grid &g) {
         const int i = std::min(std::max(last_le(f.lam, 0.5 * (u[k] + u[k + 1])), 0), nf - 2);
         const double d = f.lam[i + 1] - f.lam[i], sl = d > 0 ? (f.res[i + 1] - f.res[i]) / d : 0.0;
         for (int e = 0; e < 2; ++e) {
-            const double q = u[k + e], w = 0.5 * h * (f.res[i] + sl * (q - f.lam[i]));
+            const double q = u[k + e];
+            double rq = f.res[i] + sl * (q - f.lam[i]);
+            if (nodes_mode == EGGPHOT_NODES_SED) {
+                // a cell between SED nodes spans several filter cells: the response at the node itself
+                const int iq = q >= f.lam.back() ? nf - 2 : std::min(std::max(last_le(f.lam, q), 0), nf - 2);
+                const double dq = f.lam[iq + 1] - f.lam[iq];
+                rq = q >= f.lam.back() ? f.res[nf - 1] : (dq > 0 ? f.res[iq] + (f.res[iq + 1] - f.res[iq]) / dq * (q - f.lam[iq]) : f.res[iq + 1]);
+            }
+            const double w = 0.5 * h * rq;
             int j; double al;
             hat(q, j, al);
             r.w[j - jlo] += w * (1.0 - al);
@@ -615,6 +625,32 @@ Status build_lane_tables(Prepared &P, const eggphot_opts &opts) {
             g.idxp = o > 0 ? 1.0 / (g.x - P.grid_nodes_b[o - 1].x) : 0.0;
         }
     }
+    if (P.nodes_mode != EGGPHOT_NODES_MERGED) {
+        // node sets `sed` and `filter` (conventions to try against a real catalog): the filters go to the
+        // device as they are and a plain two-cursor kernel walks them; one header per band (no records) gives the plan
+        // kernel the spans it needs for the node windows
+        if (P.bands.size() > 64) return Status::error(EGGPHOT_ERR_UNSUPPORTED, "more than 64 bands with sed2flux_nodes=sed|filter");
+        BandGroup g;
+        g.blob.assign(P.bands.size() * sizeof(BandHeader2), 0);
+        P.alt_off.assign(1, 0u);
+        for (size_t b = 0; b < P.bands.size(); ++b) {
+            const Filter &f = P.bands[b];
+            BandHeader2 h{};
+            h.full_first = h.f_first = f.lam.front();
+            h.full_last = h.f_last = f.lam.back();
+            h.n = (uint32_t)f.lam.size();
+            h.out_col = (uint32_t)b;
+            h.cost = 1.0f;
+            for (int s = 0; s < kMaxSplit; ++s) h.msplit[s] = 0x7fffffffu;
+            std::memcpy(g.blob.data() + b * sizeof(BandHeader2), &h, sizeof(h));
+            g.cols.push_back((uint32_t)b);
+            P.alt_fl.insert(P.alt_fl.end(), f.lam.begin(), f.lam.end());
+            P.alt_fr.insert(P.alt_fr.end(), f.res.begin(), f.res.end());
+            P.alt_off.push_back((uint32_t)P.alt_fl.size());
+        }
+        if (!P.bands.empty()) P.groups2.push_back(std::move(g));
+        return Status();
+    }
     // ---- band tables in groups
     size_t budget = opts.smem_table_budget;
     if (!budget) {
@@ -815,8 +851,9 @@ Status prepare(const eggphot_libs &L, const eggphot_filters *bands, const eggpho
     P.line_profile = opts.line_profile;
     if (opts.no_stellar && opts.no_dust) // gencat:247-249 turns the whole stage off
         return Status::error(EGGPHOT_ERR_ARG, "no_stellar and no_dust together disable the flux stage (no_flux)");
-    if (opts.sed2flux_nodes != EGGPHOT_NODES_MERGED)
-        return Status::error(EGGPHOT_ERR_UNSUPPORTED, "only sed2flux_nodes=merged is implemented on the device");
+    if (opts.sed2flux_nodes != EGGPHOT_NODES_MERGED && opts.sed2flux_nodes != EGGPHOT_NODES_SED && opts.sed2flux_nodes != EGGPHOT_NODES_FILTER)
+        return Status::error(EGGPHOT_ERR_ARG, "sed2flux_nodes must be merged, sed or filter");
+    P.nodes_mode = opts.sed2flux_nodes;
     if (opts.nline && opts.line_lambda) P.line_lambda.assign(opts.line_lambda, opts.line_lambda + opts.nline);
     if (P.line_lambda.size() > 64) return Status::error(EGGPHOT_ERR_UNSUPPORTED, "more than 64 emission lines");
 
@@ -1006,8 +1043,8 @@ Status prepare(const eggphot_libs &L, const eggphot_filters *bands, const eggpho
 
     // ---- rest-frame weights
     for (size_t b = 0; b < P.rfbands.size(); ++b) {
-        P.rf_bulge.push_back(P.has_bulge ? rf_weights(P.rfbands[b], P.grid_bulge) : RfWeights());
-        P.rf_disk.push_back(rf_weights(P.rfbands[b], P.grid_disk));
+        P.rf_bulge.push_back(P.has_bulge ? rf_weights(P.rfbands[b], P.grid_bulge, P.nodes_mode) : RfWeights());
+        P.rf_disk.push_back(rf_weights(P.rfbands[b], P.grid_disk, P.nodes_mode));
     }
     return build_lane_tables(P, opts);
 }

@@ -68,6 +68,7 @@ struct Prepared {
     int precision = EGGPHOT_FP32C;
     bool apply_igm = false, no_stellar = false, no_dust = false, no_nebular = false;
     int line_profile = EGGPHOT_LINE_INTEGRAL;
+    int nodes_mode = EGGPHOT_NODES_MERGED;       // node set of [vif] sed2flux: merged is the contract
     std::vector<float> line_lambda;
 
     std::vector<Filter> bands, rfbands;          // sorted
@@ -109,6 +110,9 @@ struct Prepared {
     std::vector<GridNode> grid_nodes_b;  // [lane_grid_rows(nB)]: the optical grid alone, likewise ({x, idxp} only)
     std::vector<int32_t> next_opt;       // [lane_grid_rows(nD)]: first optical node after j (nD = the virtual node)
     std::vector<int32_t> opt_node;       // [nB]: disk-grid index of every optical node
+    // node sets `sed` and `filter`: the sorted filters as they are (wavelength, response), concatenated; alt_off[nband + 1]
+    std::vector<double> alt_fl, alt_fr;
+    std::vector<uint32_t> alt_off;
 };
 
 

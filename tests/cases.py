@@ -23,6 +23,8 @@ CASES = {
     "b30_no_nebular": ("opt", "ce01", synth.B30, synth.RF3, {"no_nebular": True}),
     "b40_hd_cs17": ("opt_hd", "cs17", synth.B40, synth.RF3, {}),
     "b30_igm_none": ("opt", "ce01", synth.B30, [], {"igm": "none"}),
+    # BASELINE.json configs[4]: the high-definition library without IGM (opt_lib_fast_hd_noigm), run in fp64 with save_sed
+    "b30_hd_noigm": ("opt_hd", "ce01", synth.B30, synth.RF3, {"igm": "none"}),
     "b30_line_average": ("opt", "ce01", synth.B30, [], {"line_profile": "average"}),
     "b23_no_dust": ("opt", "ce01", synth.B23, synth.RF3, {"no_dust": True}),
     "b23_no_stellar": ("opt", "ce01", synth.B23, synth.RF3, {"no_stellar": True, "igm": "none"}),

@@ -127,6 +127,48 @@ def test_save_sed_payload_matches_oracle():
     ph.close()
 
 
+def test_config5_save_sed_fp64_hd_noigm():
+    """BASELINE.json configs[4]: opt_lib_fast_hd_noigm (hd library, igm=none), fp64 mode, save_sed: the spectra
+    (src/egg-gencat.cpp:2164-2193) and the fluxes of the same context against the oracle."""
+    c = cases.make("b30_hd_noigm", ngal=300)
+    O = Oracle(c["opt"], c["ir"], c["bands"], c["rfbands"], line_lambda=c["lines"], **c["opts"])
+    ph = egg_b200.Photometry(c["opt"], c["ir"], c["bands"], c["rfbands"], line_lambda=c["lines"], precision="fp64", **c["opts"])
+    out = ph.compute(c["gal"], f64=True)
+    ref = O.compute(c["gal"], f64=True)
+    for k in ("flux_disk", "flux_bulge"):
+        assert cases.rel_err(out[k + "_f64"], ref[k]).max() < cases.TOL["fp64"], k
+    for comp in ("bulge", "disk"):
+        lam, sed = ph.get_seds(c["gal"], 100, 64, comp)
+        for k in (0, 31, 63):
+            rl, rs = O.get_sed(c["gal"], 100 + k, comp)
+            assert lam.shape[1] == len(rl)
+            np.testing.assert_allclose(lam[k], rl, rtol=1.3e-7)
+            np.testing.assert_allclose(sed[k], rs, rtol=3e-7, atol=1e-30)
+    ph.close()
+
+
+@pytest.mark.parametrize("nodes", ["sed", "filter"])
+@pytest.mark.parametrize("name", ["b4_defaults", "b30_rf3_defaults", "b40_hd_cs17", "b23_no_stellar"])
+def test_other_sed2flux_node_sets_match_oracle(name, nodes):
+    """The two other readings of [vif] sed2flux's node set (`check sed2flux_nodes=` of the CLI): SED nodes
+    plus the filter's end points, and filter nodes alone.  Same tolerances as the contract's merged set."""
+    c = cases.make(name, ngal=300, seed=5)
+    opts = dict(c["opts"], sed2flux_nodes=nodes)
+    ref = Oracle(c["opt"], c["ir"], c["bands"], c["rfbands"], line_lambda=c["lines"], **opts).compute(c["gal"], f64=True)
+    merged = Oracle(c["opt"], c["ir"], c["bands"], c["rfbands"], line_lambda=c["lines"], **c["opts"]).compute(c["gal"], f64=True)
+    assert cases.rel_err(merged["flux_disk"], ref["flux_disk"]).max() > 1e-6  # the node sets do differ
+    for prec in ("fp32c", "fp64"):
+        ph = egg_b200.Photometry(c["opt"], c["ir"], c["bands"], c["rfbands"], line_lambda=c["lines"], precision=prec, **opts)
+        out = ph.compute(c["gal"], f64=True)
+        ph.close()
+        for k in ("flux_disk", "flux_bulge"):
+            e = cases.rel_err(out[k + "_f64"], ref[k])
+            assert e.max() < cases.TOL[prec], f"{name} {nodes} {prec} {k}: {e.max():.2e}"
+        for k in ("rfmag_disk", "rfmag_bulge"):
+            if ref[k].size:
+                assert np.abs(out[k + "_f64"] - ref[k]).max() < cases.MAGTOL[prec], f"{name} {nodes} {prec} {k}"
+
+
 def test_full_size_properties():
     """BASELINE configs[1] size (1.95e5 galaxies x 30 bands), no oracle: determinism, chunk invariance
     (host path in 2^18 chunks vs small catalogs), linearity in mass, additivity of components."""
