@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/eggphot.h"
+#include "../../include/eggprops.h"
 #include "phot_kernels.cuh"
 #include "phot_tables.hpp"
 
@@ -728,6 +729,49 @@ int eggphot_measure_fma_peak(eggphot_ctx *c, double *fp32_tflops, double *fp64_t
     if (e != cudaSuccess) return c->cuda_fail(e, "cudaSetDevice");
     const int rc = measure_fma_peak(c->num_sms, c->errflag.p ? (char *)c->zhist[0].p : nullptr, c->stream, fp32_tflops, fp64_tflops);
     if (rc) return c->cuda_fail((cudaError_t)rc, "FMA micro-benchmark");
+    return EGGPHOT_OK;
+}
+
+int eggphot_maglim(eggphot_ctx *c, eggprops_ctx *props, const double *zb_lo, const double *zb_hi, uint32_t nz, double maglim,
+                   double mmin_strict, double mmax, uint32_t ntrial, float *z_mmin) {
+    if (!c || !c->ready) return c ? c->fail(EGGPHOT_ERR_ARG, "context is not ready") : EGGPHOT_ERR_ARG;
+    if (!props || !zb_lo || !zb_hi || !z_mmin || ntrial < 2) return c->fail(EGGPHOT_ERR_ARG, "maglim: null argument or fewer than 2 trial masses");
+    const Prepared &P = c->P;
+    if (P.bands.size() != 1 || P.disk_mode != DISK_OPT || !P.no_nebular || P.apply_igm || !P.has_bulge)
+        return c->fail(EGGPHOT_ERR_ARG, "maglim: the context must hold the selection band alone, with no_dust, no_nebular and igm=none "
+                                        "(the estimator sees stellar light only, src/egg-gencat.cpp:943-952)");
+    if (nz == 0) return EGGPHOT_OK;
+    const size_t n = (size_t)nz * ntrial;
+    std::vector<float> z(n), m(n), d(n), m2l(n), mb(n, -60.0f); // (a bulge of 10^-60 Msun: its flux underflows to 0)
+    std::vector<uint8_t> passive(n, 0);
+    std::vector<uint64_t> sed(n);
+    for (uint32_t k = 0; k < nz; ++k)
+        for (uint32_t i = 0; i < ntrial; ++i) {
+            z[(size_t)k * ntrial + i] = (float)(0.5 * (zb_lo[k] + zb_hi[k]));                                  // bin_center, :928
+            m[(size_t)k * ntrial + i] = (float)(mmin_strict + (mmax - mmin_strict) * (double)i / (ntrial - 1)); // rgen, :931
+        }
+    eggprops_out E{};
+    E.d = d.data(); E.m2lcor = m2l.data(); E.opt_sed_disk = sed.data();
+    int rc = eggprops_compute(props, z.data(), m.data(), passive.data(), n, 0, &E);
+    if (rc) return c->fail(rc, std::string("maglim: ") + eggprops_last_error(props));
+    eggphot_galaxies g{};
+    g.z = z.data(); g.d = d.data(); g.m2lcor = m2l.data();
+    g.m_disk = m.data(); g.opt_sed_disk = sed.data();   // the whole trial mass in the template of the trial colours (:945)
+    g.m_bulge = mb.data(); g.opt_sed_bulge = sed.data();
+    std::vector<double> flux(n);
+    eggphot_outputs o{};
+    o.flux_disk_f64 = flux.data();
+    rc = eggphot_compute(c, &g, n, &o);
+    if (rc) return rc;
+    const double flim = exp10(0.4 * (23.9 - maglim)); // mag2uJy
+    for (uint32_t k = 0; k < nz; ++k) {
+        z_mmin[k] = (float)mmax;
+        for (uint32_t i = 0; i < ntrial; ++i)
+            if (flux[(size_t)k * ntrial + i] - flim > 0) { // where_first, :955
+                z_mmin[k] = (float)std::max(mmin_strict, (double)m[(size_t)k * ntrial + i] - 0.2);
+                break;
+            }
+    }
     return EGGPHOT_OK;
 }
 

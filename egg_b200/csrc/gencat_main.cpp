@@ -220,6 +220,9 @@ void print_help() {
         "                         written by egg-gencat is a test vector); exit status 2 if a band differs by more\n"
         "  sed2flux_nodes=merged|sed|filter  line_profile=integral|average   conventions of the vif library to try with check\n"
         "  gpus=N                 shard the galaxies over N GPUs of this box\n"
+        "  maglim=M selection_band=B [zmin= zmax= dz= min_dz= max_dz= mmin_strict=4 mmax=12]   without an input catalog: print\n"
+        "                         the redshift-dependent mass limit z_mmin of egg-gencat's magnitude-limited mode per redshift\n"
+        "                         slice (src/egg-gencat.cpp:903-969) and exit\n"
         "Catalog generation options of egg-gencat (area, mmin, zmin, ...) are accepted and ignored: this program\n"
         "replaces the block `if (!no_flux)` of egg-gencat only.\n";
 }
@@ -243,6 +246,87 @@ void order_like_the_reference(fitscol::Table &t) {
     for (size_t i = 0; i < t.cols.size(); ++i)
         if (!used[i]) out.push_back(std::move(t.cols[i]));
     t.cols = std::move(out);
+}
+
+// `maglim= selection_band=` without an input catalog: the redshift-dependent mass limit of src/egg-gencat.cpp:903-969,
+// printed per redshift slice (the slices are those of :803-839; the strict lower mass, which the reference takes from its
+// mass-function file, :885, is the option mmin_strict).
+int run_maglim(const Args &a, const std::string &filter_db_file, const std::string &opt_lib_file, bool verbose) {
+    const double maglim = a.num("maglim", 0.0), zmin = a.num("zmin", 0.05), zmax = a.num("zmax", 10.5); // :34-35
+    const double dz = a.num("dz", 0.05), min_dz = a.num("min_dz", 0.001), max_dz = a.num("max_dz", 0.5); // :37-39
+    const double mmin_strict = a.num("mmin_strict", 4.0), mmax = a.num("mmax", 12.0);                 // :33
+    const std::string selection_band = a.str("selection_band");
+    if (selection_band.empty()) { // :240-243
+        error("requesting a magnitude limited catalog, please provide the selection band (selection_band=...)");
+        return 1;
+    }
+    if (min_dz > max_dz) { error("min_dz must be smaller than max_dz"); return 1; }
+    if (!(zmin > 0) || !(zmax > zmin)) { error("need 0 < zmin < zmax"); return 1; }
+    // make_zbins(zmin, zmax, dz, min_dz, max_dz), :803-836
+    std::vector<double> tzb;
+    for (double z1 = zmin; z1 < zmax;) {
+        tzb.push_back(z1);
+        z1 *= 1.0 + dz;
+        if (z1 - tzb.back() < min_dz) z1 = tzb.back() + min_dz;
+        else if (z1 - tzb.back() > max_dz) z1 = tzb.back() + max_dz;
+    }
+    const double min_end_dz = std::min(0.5 * zmax * dz, min_dz);
+    if (tzb.size() > 1 && zmax - tzb.back() < min_end_dz) tzb.back() = zmax; else tzb.push_back(zmax);
+    const size_t nz = tzb.size() - 1;
+    std::vector<double> lo(tzb.begin(), tzb.end() - 1), hi(tzb.begin() + 1, tzb.end());
+
+    const auto db = fitscol::read_filter_db(filter_db_file);
+    std::vector<Curve> fsel;
+    if (!get_filters(db, {selection_band}, fsel)) return 1;
+    fitscol::Table t = fitscol::read_table(opt_lib_file);
+    const fitscol::Column *cl = t.find("LAM"), *cs = t.find("SED"), *cu = t.find("USE"), *bu = t.find("BUV"), *bv = t.find("BVJ"), *ca = t.find("AV");
+    if (!cl || !cs || !cu || !bu || !bv || !ca || cl->dims.size() != 3 || bu->dims.size() != 2) {
+        error("optical library '" + opt_lib_file + "' must hold LAM, SED [nuv][nvj][nlam], USE, BUV, BVJ and AV");
+        return 1;
+    }
+    const std::vector<float> olam = fitscol::as_float(*cl), osed = fitscol::as_float(*cs), buv = fitscol::as_float(*bu), bvj = fitscol::as_float(*bv),
+                             av = fitscol::as_float(*ca);
+    const std::vector<uint8_t> ouse = fitscol::as_bool(*cu);
+    eggphot_libs L{};
+    L.nuv = (uint32_t)cl->dims[0]; L.nvj = (uint32_t)cl->dims[1]; L.nopt = (uint32_t)cl->dims[2];
+    L.opt_lam = olam.data(); L.opt_sed = osed.data(); L.opt_use = ouse.data();
+    const uint32_t nf = (uint32_t)fsel[0].lam.size();
+    const double *fl = fsel[0].lam.data(), *fr = fsel[0].res.data();
+    const eggphot_filters B{1, &nf, &fl, &fr};
+    const std::string imf = a.str("opt_lib_imf", "salpeter");
+    eggphot_opts O{};
+    O.precision = a.str("precision", "fp32c") == "fp64" ? EGGPHOT_FP64 : EGGPHOT_FP32C;
+    O.igm = "none"; O.no_dust = 1; O.no_nebular = 1; // the estimator sees stellar light only (:943-952)
+    O.opt_lib_imf = imf.c_str();
+    O.opt_lib_min_step = a.num("opt_lib_min_step", 0.001);
+    O.filter_flambda = a.flag("filter_flambda"); O.filter_photons = a.flag("filter_photons");
+    O.filter_normalize = a.has("filter_normalize") ? a.flag("filter_normalize") : true;
+    O.trim_filters = a.flag("trim_filters");
+    eggphot_ctx *pc = nullptr;
+    int rc = eggphot_create(&L, &B, nullptr, &O, &pc);
+    if (rc) { error(pc ? eggphot_last_error(pc) : "allocation failed"); eggphot_destroy(pc); return 1; }
+    eggprops_libs PL{};
+    PL.nuv = L.nuv; PL.nvj = L.nvj; PL.buv = buv.data(); PL.bvj = bvj.data(); PL.av = av.data(); PL.use = ouse.data();
+    PL.ir_lib = EGGPROPS_IR_SINGLE; PL.nir_sed = 1; // (the trial galaxies have no dust emission)
+    eggprops_opts PO{};
+    PO.no_random = 1; PO.no_nebular = 1; PO.ms_disp = 0.3; PO.igm = EGGPROPS_IGM_NONE;
+    PO.h0 = 70.0; PO.omega_m = 0.3; PO.omega_l = 0.7;
+    eggprops_ctx *qc = nullptr;
+    rc = eggprops_create(&PL, &PO, &qc);
+    if (rc) { error(qc ? eggprops_last_error(qc) : "allocation failed"); eggprops_destroy(qc); eggphot_destroy(pc); return 1; }
+    if (verbose) note("estimating redshift-dependent mass limit...");
+    std::vector<float> z_mmin(nz);
+    rc = eggphot_maglim(pc, qc, lo.data(), hi.data(), (uint32_t)nz, maglim, mmin_strict, mmax, 1000, z_mmin.data());
+    if (rc) error(eggphot_last_error(pc));
+    eggprops_destroy(qc);
+    eggphot_destroy(pc);
+    if (rc) return 1;
+    std::cout.precision(12);
+    std::cout << "# z_low z_up z_mmin   (maglim=" << maglim << " in " << selection_band << ")\n";
+    for (size_t k = 0; k < nz; ++k) std::cout << lo[k] << ' ' << hi[k] << ' ' << z_mmin[k] << '\n';
+    const float mmin = *std::min_element(z_mmin.begin(), z_mmin.end());
+    note("will generate masses from as low as " + std::to_string(mmin) + ", up to " + std::to_string(mmax)); // :967
+    return 0;
 }
 
 struct Shard {
@@ -285,6 +369,10 @@ int main(int argc, char *argv[]) {
         if (verbose) note("will save catalog in '" + out_file + "'");
         const bool from_cat = !a.has("input_props") && a.has("input_cat");
         const std::string input = a.str("input_props", a.str("input_cat"));
+        if (input.empty() && a.has("maglim")) {
+            const std::string lib = a.str("opt_lib", share + (igm == "constant" ? "opt_lib_fast.fits" : "opt_lib_fast_noigm.fits")); // :296-302
+            return run_maglim(a, filter_db_file, lib, verbose);
+        }
         if (input.empty()) {
             error("this program replaces the photometry stage of egg-gencat only (src/egg-gencat.cpp:2024-2240)");
             error("pass input_props=<egg catalog> holding the per-galaxy columns, or input_cat=<catalog with Z, M, PASSIVE>; drawing galaxies from the mass functions (area=, mmin=, ...) is out of scope");

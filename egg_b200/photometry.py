@@ -71,7 +71,7 @@ def load_library(path: str = None):
 
 EXPORTS = ("eggphot_create", "eggphot_destroy", "eggphot_last_error", "eggphot_nband", "eggphot_band_order",
            "eggphot_compute", "eggphot_compute_device", "eggphot_synchronize", "eggphot_sed_size",
-           "eggphot_get_seds", "eggphot_get_stats", "eggphot_measure_fma_peak", "eggphot_get_grid")
+           "eggphot_get_seds", "eggphot_get_stats", "eggphot_measure_fma_peak", "eggphot_get_grid", "eggphot_maglim")
 
 
 class Photometry:
@@ -182,6 +182,19 @@ class Photometry:
         x = np.zeros(int(self._L.eggphot_sed_size(self._ctx, ci)), np.float64)
         self._check(self._L.eggphot_get_grid(self._ctx, ci, C.c_void_p(x.ctypes.data)))
         return x
+
+    def maglim(self, props, zb_lo, zb_hi, maglim, mmin_strict=4.0, mmax=12.0, ntrial=1000):
+        """egg-gencat's mass-limit estimator (src/egg-gencat.cpp:903-969): the lowest mass worth generating per redshift
+        slice for a magnitude limit in this context's single band.  The context must have been created with bands = [the
+        selection band], no_dust, no_nebular, igm='none'; `props` is a Properties object created with no_random=True."""
+        lo, hi = np.ascontiguousarray(zb_lo, np.float64), np.ascontiguousarray(zb_hi, np.float64)
+        out = np.empty(len(lo), np.float32)
+        self._L.eggphot_maglim.restype = C.c_int
+        self._L.eggphot_maglim.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.c_double,
+                                           C.c_double, C.c_uint32, C.c_void_p]
+        self._check(self._L.eggphot_maglim(self._ctx, props._ctx, lo.ctypes.data, hi.ctypes.data, len(lo), float(maglim),
+                                           float(mmin_strict), float(mmax), int(ntrial), out.ctypes.data))
+        return out
 
     def fma_peak(self):
         """Measured FP32 / FP64 FMA peak of the context's GPU in TFLOP/s (the roofline denominators of bench.py)."""

@@ -174,6 +174,19 @@ int eggphot_get_stats(const eggphot_ctx *ctx, eggphot_stats *stats);
  * events, best of five launches.  TFLOP/s counting 2 flops per FMA. */
 int eggphot_measure_fma_peak(eggphot_ctx *ctx, double *fp32_tflops, double *fp64_tflops);
 
+/* The `maglim` mass-limit estimator of egg-gencat (src/egg-gencat.cpp:903-969): for every redshift slice, 1000 trial
+ * masses from mmin_strict to mmax get the colours of an active galaxy without scatter (gen_blue_uvj(..., true), :935), the
+ * optical template of those colours (get_sed_uvj, :939), the mass-to-light correction of the slice (:941) and their flux
+ * in the selection band (get_opt_sed / lsun2uJy / sed2flux, :943-952: stellar light only, no IGM, no lines, no dust);
+ * z_mmin = max(mmin_strict, first trial mass whose flux exceeds the limit - 0.2), mmax if none does (:955-962).
+ *   phot : a context over the optical library with bands = {selection band}, no_dust, no_nebular, igm = "none";
+ *   props: a property context (include/eggprops.h) over the same library, created with no_random;
+ *   zb_lo, zb_hi [nz]: the redshift slices ([vif] bin_center = their mean); ntrial: 1000 in the reference;
+ *   z_mmin [nz] receives the limits (the vec1f of :901). */
+struct eggprops_ctx;
+int eggphot_maglim(eggphot_ctx *phot, struct eggprops_ctx *props, const double *zb_lo, const double *zb_hi, uint32_t nz,
+                   double maglim, double mmin_strict, double mmax, uint32_t ntrial, float *z_mmin);
+
 #ifdef __cplusplus
 }
 #endif

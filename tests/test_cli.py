@@ -259,3 +259,36 @@ def test_ascii_input_catalog_is_read_like_the_reference(tmp_path):
         assert r.returncode == 0, r.stderr
         t = fitscol.read_table(str(tmp_path / "out.fits"))
         assert list(t["ID"]) == [1, 2] and list(t["PASSIVE"]) == [False, True] and t["FLUX"].shape == (2, 4)
+
+
+def test_maglim_needs_a_selection_band(tmp_path):
+    """src/egg-gencat.cpp:240-243: a magnitude limit without a selection band is a user error (exit 1, no device touched)."""
+    _need_cli()
+    r = _run("maglim=26", f"filter_db={_filter_db(tmp_path, ['hst-f160w'])}")
+    assert r.returncode == 1 and "selection band" in r.stderr
+
+
+@pytest.mark.gpu
+def test_maglim_prints_the_mass_limit_per_redshift_slice(tmp_path):
+    """`maglim= selection_band=` without a catalog: z_mmin per slice of make_zbins (src/egg-gencat.cpp:803-839, 903-969),
+    the same numbers as the library entry point on the same slices."""
+    import egg_b200
+    from egg_b200 import properties
+    _need_cli()
+    opt = cases.libs()["opt"]
+    db = _filter_db(tmp_path, ["hst-f160w"])
+    fitscol.write_table(str(tmp_path / "opt_lib.fits"), {k.upper(): np.asarray(v) for k, v in opt.items()})
+    r = _run("maglim=26", "selection_band=hst-f160w", f"filter_db={db}", f"opt_lib={tmp_path}/opt_lib.fits", "zmin=0.1", "zmax=6", "dz=0.3",
+             "mmin_strict=6", "verbose")
+    assert r.returncode == 0, r.stderr
+    rows = np.array([[float(v) for v in line.split()] for line in r.stdout.splitlines() if line and not line.startswith("#")])
+    lo, hi, zm = rows[:, 0], rows[:, 1], rows[:, 2]
+    assert lo[0] == pytest.approx(0.1) and hi[-1] == pytest.approx(6.0) and np.all(lo[1:] == hi[:-1])
+    assert np.all(np.diff(lo) <= 0.5 + 1e-9)                          # max_dz
+    assert "will generate masses from as low as" in r.stderr
+    ph = egg_b200.Photometry(opt, cases.libs()["ce01"], synth.get_filters(["hst-f160w"]), no_dust=True, no_nebular=True, igm="none")
+    pr = properties.Properties(opt, no_random=True)
+    want = ph.maglim(pr, lo, hi, 26.0, 6.0, 12.0, 1000)
+    pr.close()
+    ph.close()
+    np.testing.assert_allclose(zm, want, rtol=0, atol=2e-5)            # (printed with six significant digits)
