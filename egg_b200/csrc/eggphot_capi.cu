@@ -83,6 +83,11 @@ struct eggphot_ctx {
     bool use_lane = true;
     std::vector<DevBuf> blobs2;
     DevBuf gridN, nextOpt, tabCol, colSpan, altFl, altFr, altOff;
+    // save_sed staging: the columns of one range of galaxies and two output buffers (the copy out of one range overlaps the
+    // kernel of the next), kept between calls
+    DevBuf sedCols[2][15], sedOut[2], sedLamTmp;
+    cudaEvent_t sedDone[2] = {nullptr, nullptr};
+    int sedSlot = 0;
     DevBuf zhist[kLanesC + 1], zperm[kLanesC + 1];
     // per region: SED rows, band-table windows, build ranges, table sums and item counters of one chunk of batches
     DevBuf lrows[kLanesC + 1], lwin[kLanesC + 1], lplan[kLanesC + 1], lres[kLanesC + 1], lcnt[kLanesC + 1];
@@ -492,6 +497,7 @@ void eggphot_destroy(eggphot_ctx *c) {
     for (cudaStream_t st : {c->s_in, c->s_out, c->s_c[0], c->s_c[1]}) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     for (auto &s : c->slots)
         for (cudaEvent_t ev : {s.ev_in, s.ev_k, s.ev_out}) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : c->sedDone) if (ev) cudaEventDestroy(ev);
     delete c;
 }
 
@@ -672,48 +678,107 @@ uint32_t eggphot_sed_size(const eggphot_ctx *c, int component) {
     return (uint32_t)(component ? c->P.grid_disk.n() : c->P.grid_bulge.n());
 }
 
-int eggphot_get_seds(eggphot_ctx *c, const eggphot_galaxies *gal, size_t first, size_t count, int component,
-                     float *lam, float *sed) {
-    if (!c || !c->ready) return c ? c->fail(EGGPHOT_ERR_ARG, "context is not ready") : EGGPHOT_ERR_ARG;
-    if (!lam || !sed) return c->fail(EGGPHOT_ERR_ARG, "lam and sed are required");
-    if (component == 0 && !c->P.has_bulge) return c->fail(EGGPHOT_ERR_ARG, "no bulge component (no_stellar)");
-    int rc = check_galaxies(c, gal);
-    if (rc) return rc;
-    if (count == 0) return EGGPHOT_OK;
-    cudaError_t e = cudaSetDevice(c->device);
-    if (e != cudaSuccess) return c->cuda_fail(e, "cudaSetDevice");
+// save_sed of galaxies [first, first + count) of one component, enqueued on the context's stream: columns in, sed_kernel,
+// spectra out to lam / sed with row strides of `stride` floats.  Staging slot `slot` (0 / 1) must be free.
+static int enqueue_seds(eggphot_ctx *c, const eggphot_galaxies *gal, size_t first, size_t count, int component, int slot,
+                        float *lam, float *sed, bool packed) {
+    cudaError_t e;
+    cudaStream_t st = c->s_c[slot]; // a stream per staging slot: the copy out of one range overlaps the kernel of the next
 #define CK(x) do { if ((e = (x)) != cudaSuccess) return c->cuda_fail(e, #x); } while (0)
     const Prepared &P = c->P;
     const size_t nl = P.no_nebular ? 0 : P.line_lambda.size();
     const size_t n = eggphot_sed_size(c, component);
-    // stage just this range of galaxies
-    DevBuf cols[15], dl, ds;
+    DevBuf *cols = c->sedCols[slot];
     const void *src[15] = {gal->z, gal->d, gal->m_disk, gal->m_bulge, gal->m2lcor, gal->lir, gal->fpah, gal->mdust,
                            P.apply_igm ? gal->igm_abs : nullptr, nl ? gal->vdisp : nullptr, nl ? gal->line_lum_disk : nullptr,
                            nl ? gal->line_lum_bulge : nullptr, gal->opt_sed_disk, gal->opt_sed_bulge, gal->ir_sed};
     const size_t elem[15] = {4, 4, 4, 4, 4, 4, 4, 4, 12, 4, 4 * nl, 4 * nl, 8, 8, 8};
     for (int k = 0; k < 15; ++k)
-        if (src[k] && elem[k]) CK(cols[k].upload_async((const char *)src[k] + first * elem[k], count * elem[k], c->stream));
-    CK(dl.alloc(count * n * sizeof(float)));
-    CK(ds.alloc(count * n * sizeof(float)));
+        if (src[k] && elem[k]) CK(cols[k].upload_async((const char *)src[k] + first * elem[k], count * elem[k], st));
+    CK(c->sedOut[slot].alloc(count * 2 * n * sizeof(float)));
     eggphot_galaxies dg{};
     dg.z = (const float *)cols[0].p; dg.d = (const float *)cols[1].p; dg.m_disk = (const float *)cols[2].p;
     dg.m_bulge = (const float *)cols[3].p; dg.m2lcor = (const float *)cols[4].p; dg.lir = (const float *)cols[5].p;
-    dg.fpah = (const float *)cols[6].p; dg.mdust = (const float *)cols[7].p; dg.igm_abs = (const float *)cols[8].p;
-    dg.vdisp = (const float *)cols[9].p; dg.line_lum_disk = (const float *)cols[10].p; dg.line_lum_bulge = (const float *)cols[11].p;
+    dg.fpah = src[6] ? (const float *)cols[6].p : nullptr; dg.mdust = src[7] ? (const float *)cols[7].p : nullptr;
+    dg.igm_abs = (const float *)cols[8].p;
+    dg.vdisp = (const float *)cols[9].p; dg.line_lum_disk = src[10] ? (const float *)cols[10].p : nullptr;
+    dg.line_lum_bulge = src[11] ? (const float *)cols[11].p : nullptr;
     dg.opt_sed_disk = (const uint64_t *)cols[12].p; dg.opt_sed_bulge = (const uint64_t *)cols[13].p; dg.ir_sed = (const uint64_t *)cols[14].p;
     SedParams q{};
     eggphot_outputs none{};
     fill_params(c, dg, count, none, q.fp);
     q.first = 0; q.count = count; q.component = component;
-    q.lam = (float *)dl.p; q.sed = (float *)ds.p;
-    int le = launch_sed_kernel(q, P.precision, c->stream);
+    float *dev = (float *)c->sedOut[slot].p;
+    if (packed) { q.lam = dev; q.sed = dev + n; q.row_stride = 2 * n; }               // [count][lam | sed]: the file's layout
+    else { q.lam = dev; q.sed = dev + count * n; q.row_stride = n; }                 // two [count][n] arrays
+    int le = launch_sed_kernel(q, P.precision, st);
     if (le) return c->cuda_fail((cudaError_t)le, "sed kernel launch");
-    CK(cudaMemcpyAsync(lam, dl.p, count * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(sed, ds.p, count * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    if (packed) CK(cudaMemcpyAsync(lam, dev, count * 2 * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    else {
+        CK(cudaMemcpyAsync(lam, dev, count * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(sed, dev + count * n, count * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    if (!c->sedDone[slot]) CK(cudaEventCreateWithFlags(&c->sedDone[slot], cudaEventDisableTiming));
+    CK(cudaEventRecord(c->sedDone[slot], st));
 #undef CK
-    return read_error_flag(c);
+    return EGGPHOT_OK;
+}
+
+int eggphot_get_seds_packed_wait(eggphot_ctx *c, int which);
+static int seds_args(eggphot_ctx *c, const eggphot_galaxies *gal, int component, const void *a, const void *b) {
+    if (!c || !c->ready) return c ? c->fail(EGGPHOT_ERR_ARG, "context is not ready") : EGGPHOT_ERR_ARG;
+    if (!a || !b) return c->fail(EGGPHOT_ERR_ARG, "output arrays are required");
+    if (component == 0 && !c->P.has_bulge) return c->fail(EGGPHOT_ERR_ARG, "no bulge component (no_stellar)");
+    int rc = check_galaxies(c, gal);
+    if (rc) return rc;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return c->cuda_fail(e, "cudaSetDevice");
+    return EGGPHOT_OK;
+}
+
+int eggphot_get_seds(eggphot_ctx *c, const eggphot_galaxies *gal, size_t first, size_t count, int component,
+                     float *lam, float *sed) {
+    int rc = seds_args(c, gal, component, lam, sed);
+    if (rc || count == 0) return rc;
+    rc = eggphot_get_seds_packed_wait(c, 1); // (ranges begun with eggphot_get_seds_packed_begin share the staging slots)
+    if (rc) return rc;
+    rc = enqueue_seds(c, gal, first, count, component, 0, lam, sed, false);
+    if (rc) return rc;
+    return eggphot_get_seds_packed_wait(c, 1);
+}
+
+int eggphot_get_seds_packed_begin(eggphot_ctx *c, const eggphot_galaxies *gal, size_t first, size_t count, int component,
+                                  float *out) {
+    int rc = seds_args(c, gal, component, out, out);
+    if (rc || count == 0) return rc;
+    const int slot = c->sedSlot;
+    c->sedSlot ^= 1;
+    return enqueue_seds(c, gal, first, count, component, slot, out, nullptr, true);
+}
+
+int eggphot_get_seds_packed_wait(eggphot_ctx *c, int which) {
+    if (!c || !c->ready) return EGGPHOT_ERR_ARG;
+    // `which` = 0: the oldest range still in flight (the one begun before the last), 1: everything
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e == cudaSuccess) {
+        if (which == 0) { if (c->sedDone[c->sedSlot]) e = cudaEventSynchronize(c->sedDone[c->sedSlot]); }
+        else { e = cudaStreamSynchronize(c->s_c[0]); if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_c[1]); }
+    }
+    if (e != cudaSuccess) return c->cuda_fail(e, "waiting for the spectra");
+    return which == 0 ? EGGPHOT_OK : read_error_flag(c);
+}
+
+int eggphot_host_register(void *ptr, size_t bytes) {
+    if (!ptr || !bytes) return EGGPHOT_OK;
+    const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return EGGPHOT_ERR_CUDA; }
+    return EGGPHOT_OK;
+}
+int eggphot_host_unregister(void *ptr) {
+    if (!ptr) return EGGPHOT_OK;
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return EGGPHOT_ERR_CUDA; }
+    return EGGPHOT_OK;
 }
 
 int eggphot_get_grid(const eggphot_ctx *c, int component, double *x) {

@@ -694,23 +694,31 @@ int main(int argc, char *argv[]) {
             std::vector<uint64_t> nbyte[2] = {std::vector<uint64_t>(ngal, 0), std::vector<uint64_t>(ngal, 0)};
             const eggphot_galaxies G = galaxies(0);
             uint64_t pos = 0;
+            // Ranges of 4096 galaxies, two in flight: while the GPU builds range k + 1 and copies it out, this thread writes
+            // range k, which arrives in the file's own layout (per galaxy lam then sed) in one of two pinned buffers.
             for (int comp = no_stellar ? 1 : 0; comp < 2; ++comp) { // bulge pass first (:2206-2212)
                 const size_t n = eggphot_sed_size(ctxs[0], comp), chunk = 4096;
-                std::vector<float> lam(chunk * n), sed(chunk * n);
-                for (size_t first = 0; first < ngal; first += chunk) {
-                    const size_t cnt = std::min(chunk, ngal - first);
-                    if (eggphot_get_seds(ctxs[0], &G, first, cnt, comp, lam.data(), sed.data())) {
-                        error(eggphot_last_error(ctxs[0]));
-                        return 1;
+                std::vector<float> buf[2] = {std::vector<float>(chunk * 2 * n), std::vector<float>(chunk * 2 * n)};
+                for (auto &b : buf) eggphot_host_register(b.data(), b.size() * sizeof(float));
+                auto fail = [&]() { error(eggphot_last_error(ctxs[0])); for (auto &b : buf) eggphot_host_unregister(b.data()); return 1; };
+                const size_t nrange = (ngal + chunk - 1) / chunk;
+                for (size_t r = 0; r <= nrange; ++r) {
+                    if (r < nrange) {
+                        const size_t first = r * chunk, cnt = std::min(chunk, ngal - first);
+                        if (eggphot_get_seds_packed_begin(ctxs[0], &G, first, cnt, comp, buf[r & 1].data())) return fail();
                     }
+                    if (r == 0) continue;
+                    // range r - 1 has landed once the range begun before the last is done (all of them after the last begin)
+                    if (eggphot_get_seds_packed_wait(ctxs[0], r < nrange ? 0 : 1)) return fail();
+                    const size_t first = (r - 1) * chunk, cnt = std::min(chunk, ngal - first);
+                    f.write(reinterpret_cast<const char *>(buf[(r - 1) & 1].data()), (std::streamsize)(cnt * 2 * n * sizeof(float)));
                     for (size_t k = 0; k < cnt; ++k) {
-                        f.write(reinterpret_cast<const char *>(lam.data() + k * n), (std::streamsize)(n * sizeof(float)));
-                        f.write(reinterpret_cast<const char *>(sed.data() + k * n), (std::streamsize)(n * sizeof(float)));
                         start[comp][first + k] = pos;
                         nbyte[comp][first + k] = 2 * n * sizeof(float);
                         pos += 2 * n * sizeof(float);
                     }
                 }
+                for (auto &b : buf) eggphot_host_unregister(b.data());
             }
             fitscol::Table lk;
             std::vector<uint64_t> id(ngal);

@@ -886,7 +886,7 @@ __global__ void __launch_bounds__(256) sed_kernel(const __grid_constant__ SedPar
         }
     }
     __syncthreads();
-    float *lam = q.lam + (size_t)blockIdx.x * n, *sed = q.sed + (size_t)blockIdx.x * n;
+    float *lam = q.lam + (size_t)blockIdx.x * q.row_stride, *sed = q.sed + (size_t)blockIdx.x * q.row_stride;
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
         lam[j] = (float)(x[j] * s.opz);      // src/egg-gencat.cpp:2161
         sed[j] = (float)(S[j] * s.aflux);    // :2162  (S = lambda_rest * L)

@@ -124,7 +124,8 @@ struct SedParams {
     FluxParams fp;
     uint64_t first, count;
     int32_t component; // 0 bulge, 1 disk
-    float *lam, *sed;  // [count][n]
+    float *lam, *sed;  // row g of either starts at g * row_stride floats (n for two [count][n] arrays, 2 n for the packed
+    uint64_t row_stride; // [count][lam | sed] layout of the save_sed file with sed = lam + n)
 };
 int launch_sed_kernel(const SedParams &p, int precision, cudaStream_t stream);
 

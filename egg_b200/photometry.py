@@ -71,7 +71,8 @@ def load_library(path: str = None):
 
 EXPORTS = ("eggphot_create", "eggphot_destroy", "eggphot_last_error", "eggphot_nband", "eggphot_band_order",
            "eggphot_compute", "eggphot_compute_device", "eggphot_synchronize", "eggphot_sed_size",
-           "eggphot_get_seds", "eggphot_get_stats", "eggphot_measure_fma_peak", "eggphot_get_grid", "eggphot_maglim")
+           "eggphot_get_seds", "eggphot_get_stats", "eggphot_measure_fma_peak", "eggphot_get_grid", "eggphot_maglim",
+           "eggphot_get_seds_packed_begin", "eggphot_get_seds_packed_wait", "eggphot_host_register", "eggphot_host_unregister")
 
 
 class Photometry:

@@ -153,6 +153,19 @@ int eggphot_synchronize(eggphot_ctx *ctx);
 uint32_t eggphot_sed_size(const eggphot_ctx *ctx, int component);
 int eggphot_get_seds(eggphot_ctx *ctx, const eggphot_galaxies *gal, size_t first, size_t count, int component,
                      float *lam, float *sed);
+/* The same spectra in the layout of the save_sed file (gencat:2164-2193, read by egg-getsed): per galaxy lam then sed,
+ * out = [count][2 * eggphot_sed_size()] floats in host memory (pinned memory makes the copy asynchronous).  _begin
+ * enqueues one range and returns; two ranges may be in flight (the copy out of one overlaps the kernel of the next).
+ * _wait(ctx, 0) returns when the range begun before the last one has landed in its buffer, _wait(ctx, 1) when all have
+ * (and reports data errors). */
+int eggphot_get_seds_packed_begin(eggphot_ctx *ctx, const eggphot_galaxies *gal, size_t first, size_t count, int component,
+                                  float *out);
+int eggphot_get_seds_packed_wait(eggphot_ctx *ctx, int which);
+/* cudaHostRegister / cudaHostUnregister of a caller's buffer, for programs that do not link the CUDA runtime themselves:
+ * pinned host columns make the copies of eggphot_compute asynchronous.  Failure is not fatal (the copies are then staged). */
+int eggphot_host_register(void *ptr, size_t bytes);
+int eggphot_host_unregister(void *ptr);
+
 
 /* Rest wavelengths [um] of the prepared SED grid of one component (0 bulge = the optical library's grid after
  * re-binning, 1 disk = the merge_add union with the IR grid); x receives eggphot_sed_size(ctx, component) values. */

@@ -198,6 +198,28 @@ def test_input_cat_generates_the_properties_on_the_gpu(tmp_path):
     f = ph.compute(gal)
     ph.close()
     np.testing.assert_array_equal(t["FLUX"], f["flux"])
+    # the column contract of the output catalog (src/egg-gencat.cpp:2253-2286): the writer's order, and the lists the
+    # downstream programs ask for by name (src/egg-2skymaker.cpp:99-104, src/egg-genmap.cpp:94-102), with their types
+    ref_order = ["ID", "RA", "DEC", "CLUSTERED", "Z", "D", "M", "SFR", "RSB", "M2LCOR", "DISK_ANGLE", "DISK_RADIUS", "DISK_RATIO",
+                 "BULGE_ANGLE", "BULGE_RADIUS", "BULGE_RATIO", "BT", "M_DISK", "M_BULGE", "AV_DISK", "AV_BULGE", "PASSIVE",
+                 "RFUV_BULGE", "RFUV_DISK", "RFVJ_BULGE", "RFVJ_DISK", "SFRIR", "SFRUV", "IRX", "LIR", "IR_SED",
+                 "OPT_SED_BULGE", "OPT_SED_DISK", "TDUST", "IR8", "FPAH", "MDUST", "IGM_ABS", "ZB", "CMD",
+                 "FLUX", "FLUX_DISK", "FLUX_BULGE", "BANDS", "LAMBDA",
+                 "VDISP", "AVLINES_DISK", "AVLINES_BULGE", "LINE_LUM", "LINE_LUM_DISK", "LINE_LUM_BULGE", "LINES", "LINE_LAMBDA"]
+    names = list(t)
+    assert [c for c in names if c in ref_order] == [c for c in ref_order if c in names]
+    assert set(ref_order) - set(names) <= {"ZB", "CMD"}      # (written by the generation stage only: redshift bins, command line)
+    for c in ("ID", "RA", "DEC", "DISK_ANGLE", "DISK_RADIUS", "DISK_RATIO", "BULGE_ANGLE", "BULGE_RADIUS", "BULGE_RATIO",
+              "FLUX_DISK", "FLUX_BULGE", "BANDS", "LAMBDA"):   # egg-2skymaker
+        assert c in t, c
+    for c in ("RA", "DEC", "FLUX", "BANDS"):                   # egg-genmap
+        assert c in t, c
+    assert t["ID"].dtype == np.uint64 and t["OPT_SED_DISK"].dtype == np.uint64 and t["IR_SED"].dtype == np.uint64   # TFORM K
+    assert t["RA"].dtype == np.float64 and t["DEC"].dtype == np.float64                                             # D
+    assert t["CLUSTERED"].dtype == bool and t["PASSIVE"].dtype == bool and not t["CLUSTERED"].any()                  # L (:1356)
+    for c in ("Z", "D", "M", "FLUX", "FLUX_DISK", "FLUX_BULGE", "LAMBDA", "IGM_ABS", "LINE_LUM"):
+        assert t[c].dtype == np.float32, c                                                                           # E
+    assert t["FLUX"].shape == (n, len(bands)) and t["IGM_ABS"].shape == (n, 3) and len(t["BANDS"]) == len(bands)
     # the reference's input check (src/egg-gencat.cpp:769-774)
     fitscol.write_table(str(tmp_path / "bad.fits"), {"ID": np.arange(2, dtype=np.uint64), "Z": np.array([0.5, -1.0], np.float32),
                                                       "M": np.array([10.0, 10.0], np.float32), "PASSIVE": np.array([False, True])})
@@ -281,11 +303,11 @@ def test_maglim_prints_the_mass_limit_per_redshift_slice(tmp_path):
     r = _run("maglim=26", "selection_band=hst-f160w", f"filter_db={db}", f"opt_lib={tmp_path}/opt_lib.fits", "zmin=0.1", "zmax=6", "dz=0.3",
              "mmin_strict=6", "verbose")
     assert r.returncode == 0, r.stderr
-    rows = np.array([[float(v) for v in line.split()] for line in r.stdout.splitlines() if line and not line.startswith("#")])
+    rows = np.array([[float(v) for v in line.split()] for line in r.stdout.splitlines() if line[:1].isdigit()])
     lo, hi, zm = rows[:, 0], rows[:, 1], rows[:, 2]
     assert lo[0] == pytest.approx(0.1) and hi[-1] == pytest.approx(6.0) and np.all(lo[1:] == hi[:-1])
     assert np.all(np.diff(lo) <= 0.5 + 1e-9)                          # max_dz
-    assert "will generate masses from as low as" in r.stderr
+    assert "will generate masses from as low as" in r.stdout + r.stderr
     ph = egg_b200.Photometry(opt, cases.libs()["ce01"], synth.get_filters(["hst-f160w"]), no_dust=True, no_nebular=True, igm="none")
     pr = properties.Properties(opt, no_random=True)
     want = ph.maglim(pr, lo, hi, 26.0, 6.0, 12.0, 1000)
