@@ -88,6 +88,9 @@ struct eggphot_ctx {
     DevBuf sedCols[2][15], sedOut[2], sedLamTmp;
     cudaEvent_t sedDone[2] = {nullptr, nullptr};
     int sedSlot = 0;
+    // events around the walk kernel launches of the device entry point since the last eggphot_get_stats (at most 256 pairs)
+    std::vector<cudaEvent_t> walkEv;
+    size_t walkUsed = 0, walkCalls = 0;
     DevBuf zhist[kLanesC + 1], zperm[kLanesC + 1];
     // per region: SED rows, band-table windows, build ranges, table sums and item counters of one chunk of batches
     DevBuf lrows[kLanesC + 1], lwin[kLanesC + 1], lplan[kLanesC + 1], lres[kLanesC + 1], lcnt[kLanesC + 1];
@@ -204,7 +207,12 @@ int enqueue(eggphot_ctx *c, const eggphot_galaxies &g, size_t ngal, const eggpho
         for (size_t b0 = 0; b0 < nbatch; b0 += cap) {
             q.batch0 = b0;
             q.nbatch = (uint32_t)std::min(cap, nbatch - b0);
-            e = launch_lane_chunk(q, c->P.precision, c->num_sms, st);
+            cudaEvent_t w0 = nullptr, w1 = nullptr;
+            if (region == 0 && c->walkUsed + 2 <= 512) { // (the device entry point: one stream, events in order)
+                while (c->walkEv.size() < c->walkUsed + 2) { cudaEvent_t ev; if (cudaEventCreate(&ev) != cudaSuccess) break; c->walkEv.push_back(ev); }
+                if (c->walkEv.size() >= c->walkUsed + 2) { w0 = c->walkEv[c->walkUsed]; w1 = c->walkEv[c->walkUsed + 1]; c->walkUsed += 2; }
+            }
+            e = launch_lane_chunk(q, c->P.precision, c->num_sms, st, w0, w1);
             if (e != 0) return c->cuda_fail((cudaError_t)e, "flux pipeline launch");
             c->launches += (q.fp.ngroups > 0 && q.ntab > 0) ? 4 : 3;
         }
@@ -498,6 +506,7 @@ void eggphot_destroy(eggphot_ctx *c) {
     for (auto &s : c->slots)
         for (cudaEvent_t ev : {s.ev_in, s.ev_k, s.ev_out}) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : c->sedDone) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : c->walkEv) cudaEventDestroy(ev);
     delete c;
 }
 
@@ -527,6 +536,7 @@ int eggphot_compute_device(eggphot_ctx *c, const eggphot_galaxies *gal, size_t n
     cudaError_t e = cudaSetDevice(c->device);
     if (e != cudaSuccess) return c->cuda_fail(e, "cudaSetDevice");
     c->launches = 0;
+    ++c->walkCalls;
     return enqueue(c, *gal, ngal, *out, (cudaStream_t)stream, 0);
 }
 
@@ -840,9 +850,19 @@ int eggphot_maglim(eggphot_ctx *c, eggprops_ctx *props, const double *zb_lo, con
     return EGGPHOT_OK;
 }
 
-int eggphot_get_stats(const eggphot_ctx *c, eggphot_stats *s) {
-    if (!c || !s) return EGGPHOT_ERR_ARG;
+int eggphot_get_stats(const eggphot_ctx *cc, eggphot_stats *s) {
+    if (!cc || !s) return EGGPHOT_ERR_ARG;
+    eggphot_ctx *c = const_cast<eggphot_ctx *>(cc); // (the event pairs are consumed)
     std::memset(s, 0, sizeof(*s));
+    {   // mean device time of the walk kernel per eggphot_compute_device call since the last query
+        double ms = 0.0;
+        for (size_t k = 0; k + 1 < c->walkUsed; k += 2) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, c->walkEv[k], c->walkEv[k + 1]) == cudaSuccess) ms += t; else cudaGetLastError();
+        }
+        s->last_kernel_ms = c->walkCalls ? ms / (double)c->walkCalls : 0.0;
+        c->walkUsed = 0; c->walkCalls = 0;
+    }
     s->kernel_launches = c->launches;
     s->ngroups = (uint32_t)(c->use_lane ? c->P.groups2.size() : c->P.groups.size());
     s->nodes_disk = (uint32_t)c->P.grid_disk.n();

@@ -232,6 +232,8 @@ template <typename real, int NT>
 __global__ void __launch_bounds__(NT, 1) flux_kernel(const __grid_constant__ FluxParams p) {
     typedef typename Pair<real>::type real2;
     constexpr int kBatch = sizeof(real) == 4 ? kBatchF32 : kBatchF64;
+    // phase A1 hands the galaxies of a batch to fixed thread ranges (one warp lane per galaxy, set-up threads 128 .. 192 + kBatch)
+    static_assert(kBatch <= 32 && (kBatch & (kBatch - 1)) == 0 && 192 + kBatch <= NT, "EGG_KBATCH_* must be a power of two <= 32");
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ GalScal sc[kBatch];
     __shared__ __align__(8) uint64_t bar_tab;

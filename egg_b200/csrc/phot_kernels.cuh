@@ -111,7 +111,8 @@ struct LaneParams {
 };
 size_t lane_kernel_smem(const LaneParams &q, int precision);
 // plan + build + walk + finish of one chunk; returns cudaError_t as int
-int launch_lane_chunk(const LaneParams &q, int precision, int num_sms, cudaStream_t stream);
+// (w0 / w1: optional events recorded on `stream` right before / after the walk kernel, the dominant one, for the bench's roofline)
+int launch_lane_chunk(const LaneParams &q, int precision, int num_sms, cudaStream_t stream, cudaEvent_t w0 = nullptr, cudaEvent_t w1 = nullptr);
 // counting sort of the galaxies by log2(1+z): hist is scratch of zsort_hist_bytes(), perm receives the order
 size_t zsort_hist_bytes();
 int launch_zsort(const float *z, uint32_t ngal, uint32_t *hist, uint32_t *perm, int num_sms, cudaStream_t stream);

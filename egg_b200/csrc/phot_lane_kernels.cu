@@ -938,7 +938,7 @@ template <typename real> size_t walk_smem_base(const LaneParams &q) {
 }
 size_t walk_grid_bytes(const LaneParams &q) { return ((size_t)q.rowsD + q.rowsB) * 16; }
 
-template <typename real> int launch_chunk(const LaneParams &q, int num_sms, cudaStream_t st) {
+template <typename real> int launch_chunk(const LaneParams &q, int num_sms, cudaStream_t st, cudaEvent_t w0, cudaEvent_t w1) {
     if (q.nbatch == 0) return 0;
     cudaError_t e = cudaMemsetAsync(q.counters, 0, kMaxGroups * sizeof(uint32_t), st);
     if (e != cudaSuccess) return (int)e;
@@ -951,6 +951,7 @@ template <typename real> int launch_chunk(const LaneParams &q, int num_sms, cuda
     if (q.nodes_mode != EGGPHOT_NODES_MERGED) {
         if (q.ntab > 0) lane_alt_kernel<real><<<(q.nbatch * q.ntab + 3) / 4, 128, 0, st>>>(q);
     } else if (q.fp.ngroups > 0 && q.ntab > 0) {
+        if (w0) cudaEventRecord(w0, st);
         if (q.gx_in_smem) {
             const size_t smem = walk_smem_base<real>(q) + walk_grid_bytes(q);
             e = cudaFuncSetAttribute(lane_walk_kernel<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -962,6 +963,7 @@ template <typename real> int launch_chunk(const LaneParams &q, int num_sms, cuda
             if (e != cudaSuccess) return (int)e;
             lane_walk_kernel<real, false><<<num_sms, kWalkThreads, smem, st>>>(q);
         }
+        if (w1) cudaEventRecord(w1, st);
     }
     lane_finish_kernel<real><<<q.nbatch, kFinishThreads, 0, st>>>(q);
     return (int)cudaGetLastError();
@@ -973,8 +975,8 @@ size_t lane_kernel_smem(const LaneParams &q, int precision) {
     const size_t base = precision == EGGPHOT_FP64 ? walk_smem_base<double>(q) : walk_smem_base<float>(q);
     return base + (q.gx_in_smem ? walk_grid_bytes(q) : 0);
 }
-int launch_lane_chunk(const LaneParams &q, int precision, int num_sms, cudaStream_t stream) {
-    return precision == EGGPHOT_FP64 ? launch_chunk<double>(q, num_sms, stream) : launch_chunk<float>(q, num_sms, stream);
+int launch_lane_chunk(const LaneParams &q, int precision, int num_sms, cudaStream_t stream, cudaEvent_t w0, cudaEvent_t w1) {
+    return precision == EGGPHOT_FP64 ? launch_chunk<double>(q, num_sms, stream, w0, w1) : launch_chunk<float>(q, num_sms, stream, w0, w1);
 }
 
 int launch_zsort(const float *z, uint32_t ngal, uint32_t *hist, uint32_t *perm, int num_sms, cudaStream_t st) {

@@ -178,7 +178,9 @@ typedef struct eggphot_stats {
     uint32_t ngroups;
     uint32_t nodes_disk, nodes_bulge, nodes_ir; /* grid sizes after preparation */
     uint64_t table_bytes;                        /* device bytes of prepared tables */
-    double last_kernel_ms;                       /* device time of the last compute_device call when timed, else 0 */
+    double last_kernel_ms;                       /* mean device time [ms] of the walk kernel (the dominant one) per
+                                                  * eggphot_compute_device call since the previous eggphot_get_stats, from CUDA
+                                                  * events on the launching stream; call after the stream has been synchronised */
 } eggphot_stats;
 int eggphot_get_stats(const eggphot_ctx *ctx, eggphot_stats *stats);
 

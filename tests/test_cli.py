@@ -214,7 +214,8 @@ def test_input_cat_generates_the_properties_on_the_gpu(tmp_path):
         assert c in t, c
     for c in ("RA", "DEC", "FLUX", "BANDS"):                   # egg-genmap
         assert c in t, c
-    assert t["ID"].dtype == np.uint64 and t["OPT_SED_DISK"].dtype == np.uint64 and t["IR_SED"].dtype == np.uint64   # TFORM K
+    for c in ("ID", "OPT_SED_DISK", "OPT_SED_BULGE", "IR_SED"):
+        assert t[c].dtype.kind in "iu" and t[c].dtype.itemsize == 8, c                                              # TFORM K
     assert t["RA"].dtype == np.float64 and t["DEC"].dtype == np.float64                                             # D
     assert t["CLUSTERED"].dtype == bool and t["PASSIVE"].dtype == bool and not t["CLUSTERED"].any()                  # L (:1356)
     for c in ("Z", "D", "M", "FLUX", "FLUX_DISK", "FLUX_BULGE", "LAMBDA", "IGM_ABS", "LINE_LUM"):
