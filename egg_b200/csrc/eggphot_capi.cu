@@ -91,6 +91,7 @@ struct eggphot_ctx {
     // events around the walk kernel launches of the device entry point since the last eggphot_get_stats (at most 256 pairs)
     std::vector<cudaEvent_t> walkEv;
     size_t walkUsed = 0, walkCalls = 0;
+    bool walk_split = false;
     DevBuf zhist[kLanesC + 1], zperm[kLanesC + 1];
     // per region: SED rows, band-table windows, build ranges, table sums and item counters of one chunk of batches
     DevBuf lrows[kLanesC + 1], lwin[kLanesC + 1], lplan[kLanesC + 1], lres[kLanesC + 1], lcnt[kLanesC + 1];
@@ -212,7 +213,12 @@ int enqueue(eggphot_ctx *c, const eggphot_galaxies &g, size_t ngal, const eggpho
                 while (c->walkEv.size() < c->walkUsed + 2) { cudaEvent_t ev; if (cudaEventCreate(&ev) != cudaSuccess) break; c->walkEv.push_back(ev); }
                 if (c->walkEv.size() >= c->walkUsed + 2) { w0 = c->walkEv[c->walkUsed]; w1 = c->walkEv[c->walkUsed + 1]; c->walkUsed += 2; }
             }
-            e = launch_lane_chunk(q, c->P.precision, c->num_sms, st, w0, w1);
+            // The walk kernel is persistent, one CTA per SM.  The chunks of the host entry point run on two streams: giving
+            // each walk half of the SMs lets two chunks' walks run side by side, so that the tail of one (its last items, its
+            // group changes) is covered by the body of the other instead of idling the device.
+            int walk_ctas = c->num_sms;
+            if (region != 0 && c->walk_split) walk_ctas = std::max(1, c->num_sms / 2);
+            e = launch_lane_chunk(q, c->P.precision, walk_ctas, st, w0, w1);
             if (e != 0) return c->cuda_fail((cudaError_t)e, "flux pipeline launch");
             c->launches += (q.fp.ngroups > 0 && q.ntab > 0) ? 4 : 3;
         }
@@ -623,6 +629,7 @@ int eggphot_compute(eggphot_ctx *c, const eggphot_galaxies *gal, size_t ngal, co
     // kernels of consecutive chunks: one stream (chunk k is done, and on its way out, before chunk k + 1 starts) unless
     // EGGPHOT_CSTREAMS=2
     const int ncs = getenv("EGGPHOT_CSTREAMS") && atoi(getenv("EGGPHOT_CSTREAMS")) == 1 ? 1 : 2;
+    c->walk_split = ncs == 2 && sizes.size() > 1 && getenv("EGGPHOT_WALK_SPLIT") && atoi(getenv("EGGPHOT_WALK_SPLIT")) == 1;
     size_t first = 0;
     for (size_t k = 0; k < sizes.size(); first += sizes[k], ++k) {
         Slot &s = c->slots[k % kSlots];
