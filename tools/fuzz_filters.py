@@ -13,6 +13,7 @@ np.seterr(all='ignore')
 L=cases.libs(); opt, ir = L['opt'], L['ce01']
 rng=np.random.default_rng(int(sys.argv[1]) if len(sys.argv)>1 else 0)
 worst={'fp32c':0,'fp64':0}
+underflow=0
 for trial in range(int(sys.argv[2]) if len(sys.argv)>2 else 20):
     bands=[]
     for b in range(6):
@@ -62,6 +63,12 @@ for trial in range(int(sys.argv[2]) if len(sys.argv)>2 else 20):
             print('emul rejects',opts,str(e)[:80]); continue
         for k in ('flux_disk','flux_bulge'):
             e=cases.rel_err(out[k],ref[k],cases.FLOOR[prec])
+            if prec=='fp32c':
+                # the fp32 mode forms S*W in float: a flux below ~1e-30 uJy (responses of 1e-40, which (1-x^2)^p produces at the
+                # ends of a two-node band) underflows into float denormals; such entries are counted, not judged
+                tiny=np.abs(ref[k])<1e-30
+                underflow+=int(np.count_nonzero(tiny & (e>cases.TOL[prec])))
+                e=np.where(tiny,0.0,e)
             if e.max()>worst[prec]: worst[prec]=e.max()
             if e.max()>cases.TOL[prec]:
                 w=np.unravel_index(np.argmax(e),e.shape)
@@ -70,4 +77,4 @@ for trial in range(int(sys.argv[2]) if len(sys.argv)>2 else 20):
             for k in ('rfmag_disk','rfmag_bulge'):
                 dm=np.abs(np.asarray(out[k])-ref[k]); dm=dm[np.isfinite(dm)]
                 if dm.size and dm.max()>(1e-5 if prec=='fp32c' else 1e-9): print('FAIL rf',trial,prec,k,dm.max())
-print('worst',worst)
+print('worst',worst,'; fp32c entries below 1e-30 uJy off by more than the tolerance (float underflow, not judged):',underflow)
