@@ -405,6 +405,13 @@ constexpr int kWinStride = 128; // window words per batch in LaneParams::win: {d
 
 constexpr int kSegRows = 256;   // rows per warp of the build kernel
 constexpr int kBuildThreads = 128;
+#ifndef EGG_BUILD_MINBLOCKS
+#define EGG_BUILD_MINBLOCKS 8   // (64 registers, no spills: 1.358e9 against 1.352e9 with the compiler's own 72; 10 / 12 / 16 spill and lose 2 - 5 %; tuning knobs of the build kernel: resident CTAs per SM the register allocation aims at, row-loop unroll)
+#endif
+#ifndef EGG_BUILD_UNROLL
+#define EGG_BUILD_UNROLL 4
+#endif
+constexpr int kBuildUnroll = EGG_BUILD_UNROLL;
 constexpr int kFinishThreads = 128;
 
 // lane -> galaxy of batch bl of the chunk (lanes beyond the end of the catalog repeat the batch's first galaxy)
@@ -488,7 +495,7 @@ __device__ __forceinline__ void build_rows(real *__restrict__ dst, int s0, int s
     constexpr int NPL = 16 / (int)sizeof(real);
     const int igm_end = apply_igm ? igm[3] : 0;
     real *d = dst + (size_t)s0 * kLanes;
-#pragma unroll 4
+#pragma unroll kBuildUnroll
     for (int j0 = s0; j0 <= s1; j0 += NPL, d += NPL * kLanes) { // (unrolled: a dozen row loads in flight)
         real v[NPL];
 #pragma unroll
@@ -522,7 +529,7 @@ __device__ __forceinline__ void build_rows(real *__restrict__ dst, int s0, int s
 // load, [node][lane] stores; then the emission lines of the segment's nodes.  The bulge SED carries no mass scale
 // (applied at the end).
 template <typename real>
-__global__ void __launch_bounds__(kBuildThreads) lane_build_kernel(const __grid_constant__ LaneParams q) {
+__global__ void __launch_bounds__(kBuildThreads, (sizeof(real) == 4 ? EGG_BUILD_MINBLOCKS : 6)) lane_build_kernel(const __grid_constant__ LaneParams q) {
     const FluxParams &p = q.fp;
     // gridDim.x / nbatch CTAs share a batch: together they have a warp for every segment the grids can have
     const uint32_t per_batch = gridDim.x / q.nbatch, bl = blockIdx.x / per_batch;

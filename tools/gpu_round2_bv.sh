@@ -1,0 +1,6 @@
+mkdir -p gpurun_out
+for v in "" _mb8 _mb10 _mb12 _mb16 _u8 _mb10u2 _mb12u8; do
+  lib=egg_b200/libeggphot$v.so
+  EGGPHOT_LIB=$PWD/$lib timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --no-extra --no-e2e > gpurun_out/bench_bv$v.json 2> gpurun_out/bench_bv$v.err
+  python -c "import json;d=json.load(open('gpurun_out/bench_bv$v.json'));print('variant[$v]', '%.4g'%d['value'], 'step %.3f walk %.3f'%(d['ms_per_step'], d['roofline']['kernel_ms']))"
+done
