@@ -564,10 +564,11 @@ int eggphot_compute(eggphot_ctx *c, const eggphot_galaxies *gal, size_t ngal, co
     c->launches = 0;
     const Prepared &P = c->P;
     const size_t nb = P.bands.size(), nrf = P.rfbands.size(), nl = P.no_nebular ? 0 : P.line_lambda.size();
-    // chunks: large enough that the kernels run at their large-catalog rate (the walk kernel is persistent: 2^15 galaxies
-    // are seven items per warp), small enough that the first copy in and the last copy out, which nothing overlaps, are a
-    // small part of the call: a quarter of the catalog, within [2^15, 2^20]
-    size_t chunk = (std::min<size_t>(std::max<size_t>((ngal + 3) / 4, 1u << 15), 1u << 20) + kLanes - 1) / kLanes * kLanes;
+    // chunks: every chunk pays the pipeline's fixed cost once (about 0.37 ms of tails and small kernels),
+    // and the first copy in and the last copy out are exposed.  Measured at 1.95e5 galaxies: three equal chunks 5.49 ms, four
+    // 5.7 - 5.8, half chunks first and last around three or four whole ones 5.7 - 5.9, two 6.2, one 6.6.  So: a third of the
+    // catalog, within [2^15, 2^20] galaxies.
+    size_t chunk = (std::min<size_t>(std::max<size_t>((ngal + 2) / 3, 1u << 15), 1u << 20) + kLanes - 1) / kLanes * kLanes;
     if (const char *ev = getenv("EGGPHOT_CHUNK")) { // tuning knob: galaxies per chunk of the host-memory entry point
         const long long v = atoll(ev);
         if (v > 0) chunk = ((size_t)v + kLanes - 1) / kLanes * kLanes;
@@ -606,28 +607,13 @@ int eggphot_compute(eggphot_ctx *c, const eggphot_galaxies *gal, size_t ngal, co
         cudaEventRecord(ev, st);
         tev.push_back(ev);
     };
-    // The chunks: half a chunk first and last (the first copy in and the last copy out are the only ones nothing overlaps),
-    // whole chunks between them.
     std::vector<size_t> sizes;
-    {
-        const bool taper = !getenv("EGGPHOT_NO_TAPER");
-        const size_t half = ((chunk / 2) + kLanes - 1) / kLanes * kLanes;
-        size_t left = ngal;
-        if (taper && ngal > 2 * chunk) { sizes.push_back(half); left -= half; }
-        while (left > 0) {
-            if (taper && ngal > 2 * chunk && left <= chunk + half) {
-                if (left > half + 8192) { sizes.push_back(left - half); left = half; }
-                sizes.push_back(left);
-                left = 0;
-            } else {
-                const size_t n = std::min(chunk, left);
-                sizes.push_back(n);
-                left -= n;
-            }
-        }
+    for (size_t left = ngal; left > 0;) {
+        const size_t n = std::min(chunk, left);
+        sizes.push_back(n);
+        left -= n;
     }
-    // kernels of consecutive chunks: one stream (chunk k is done, and on its way out, before chunk k + 1 starts) unless
-    // EGGPHOT_CSTREAMS=2
+    // kernels of consecutive chunks alternate between two streams (EGGPHOT_CSTREAMS=1: one stream, measured 6.2 ms against 5.75)
     const int ncs = getenv("EGGPHOT_CSTREAMS") && atoi(getenv("EGGPHOT_CSTREAMS")) == 1 ? 1 : 2;
     c->walk_split = ncs == 2 && sizes.size() > 1 && getenv("EGGPHOT_WALK_SPLIT") && atoi(getenv("EGGPHOT_WALK_SPLIT")) == 1;
     size_t first = 0;
