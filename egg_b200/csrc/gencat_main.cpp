@@ -384,7 +384,7 @@ int main(int argc, char *argv[]) {
             "hst-f105w", "hst-f125w", "hst-f140w", "hst-f160w", "hawki-Ks", "spitzer-irac1", "spitzer-irac2", "spitzer-irac3",
             "spitzer-irac4", "spitzer-irs16", "spitzer-mips24", "herschel-pacs70", "herschel-pacs100", "herschel-pacs160",
             "herschel-spire250", "herschel-spire350", "herschel-spire500"}; // :125-130
-        const std::vector<std::string> bands = a.list("bands", dflt_bands), rfbands = a.list("rfbands", {});
+        std::vector<std::string> bands = a.list("bands", dflt_bands), rfbands = a.list("rfbands", {});
         const std::string ir_lib_file = a.str("ir_lib", share + "ir_lib_cs17.fits"); // :88
         const std::string opt_lib_file = a.str("opt_lib", share + (igm == "constant" ? "opt_lib_fast.fits" : "opt_lib_fast_noigm.fits")); // :296-302
         const std::string imf = a.str("opt_lib_imf", "salpeter");
@@ -425,6 +425,17 @@ int main(int argc, char *argv[]) {
             pc.name = "PASSIVE"; pc.type = 'L'; pc.dims = {(long)cp.size()}; pc.data = cp;
             cat.set(pc);
         } else cat = fitscol::read_table(input);
+        if (a.flag("check")) {
+            // check without bands= / rfbands=: the bands the catalog itself was written with (its BANDS / RFBANDS columns)
+            auto from_column = [&](const char *col, const char *key, std::vector<std::string> &dst) {
+                const fitscol::Column *c = cat.find(col);
+                if (a.has(key) || !c) return;
+                dst = fitscol::as_strings(*c);
+                for (auto &v : dst) while (!v.empty() && v.back() == ' ') v.pop_back();
+            };
+            from_column("BANDS", "bands", bands);
+            from_column("RFBANDS", "rfbands", rfbands);
+        }
         if (from_cat) {
             // ---- galaxy properties on the GPU (src/egg-gencat.cpp:714-779 for the input, :1360-2022 for the recipes)
             for (const char *k : {"Z", "M", "PASSIVE"})

@@ -315,3 +315,44 @@ def test_maglim_prints_the_mass_limit_per_redshift_slice(tmp_path):
     pr.close()
     ph.close()
     np.testing.assert_allclose(zm, want, rtol=0, atol=2e-5)            # (printed with six significant digits)
+
+
+@pytest.mark.gpu
+def test_check_mode_compares_with_the_fluxes_already_in_the_catalog(tmp_path):
+    """an egg output catalog holds every input column of this stage next to FLUX* / RFMAG*, so it is a
+    test vector.  `check` recomputes and compares per band: exit 0 within tolerance, 2 above it; `sed2flux_nodes=` selects the
+    convention (a catalog written under another node set fails under `merged` and passes under its own)."""
+    from oracle.oracle import Oracle
+    _need_cli()
+    opt, ir, gal, bands, rf, args = _write_inputs(tmp_path, ngal=200)
+    fb, fr = synth.get_filters(bands), synth.get_filters(rf)
+    cat = dict(fitscol.read_table(str(tmp_path / "cat.fits")))
+
+    def write(name, nodes, spoil=None):
+        O = Oracle(opt, ir, fb, fr, line_lambda=synth.LINE_LAMBDA, sed2flux_nodes=nodes)
+        ref = O.compute(gal)
+        c = dict(cat)
+        for k in ("flux", "flux_disk", "flux_bulge", "rfmag", "rfmag_disk", "rfmag_bulge"):
+            c[k.upper()] = np.asarray(ref[k], np.float32)
+        c["BANDS"] = np.array([bands[k] for k in O.band_order])
+        c["RFBANDS"] = np.array([rf[k] for k in O.rfband_order])
+        if spoil is not None:
+            c["FLUX_DISK"] = c["FLUX_DISK"].copy()
+            c["FLUX_DISK"][:, spoil] *= np.float32(1.001)
+        fitscol.write_table(str(tmp_path / name), c)
+        return [x.replace("cat.fits", name) for x in args if not x.startswith(("bands=", "rfbands="))]   # bands from the catalog itself
+
+    ok = write("egg_merged.fits", "merged")
+    r = _run(*ok, "check", "check_tol=2e-5")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "every compared band is within tolerance" in r.stdout and r.stdout.count("check: FLUX_DISK") == len(bands)
+    assert not any(p.name.startswith("egg-2") for p in tmp_path.iterdir())          # nothing is written without out=
+    bad = write("egg_spoiled.fits", "merged", spoil=2)
+    r = _run(*bad, "check", "check_tol=2e-5")
+    assert r.returncode == 2 and "DIFFERENCES above tolerance" in r.stdout
+    lines = [l for l in r.stdout.splitlines() if l.startswith("check: FLUX_DISK")]
+    assert sum("above 2e-05: 0 of" not in l for l in lines) == 1                     # exactly the spoiled band
+    other = write("egg_sed_nodes.fits", "sed")
+    assert _run(*other, "check", "check_tol=2e-5").returncode == 2                  # the node sets differ by more than the tolerance
+    r = _run(*other, "check", "check_tol=2e-5", "sed2flux_nodes=sed")
+    assert r.returncode == 0, r.stdout + r.stderr
