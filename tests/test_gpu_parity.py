@@ -211,3 +211,22 @@ def test_large_sample_has_no_outliers(name):
         out = _run(c, prec)
         for k in ("flux_disk", "flux_bulge"):
             assert cases.rel_err(out[k + "_f64"], ref[k], cases.FLOOR[prec]).max() < cases.TOL[prec], (prec, k)
+
+
+def test_large_catalog_spot_check_against_the_oracle():
+    """2e6 galaxies x 30 bands through the host-memory entry point (three chunks of 6.7e5 galaxies, each worked off in
+    sub-chunks of 8 800 batches: the paths configs[3] takes per GPU), 1e5 of them drawn at random checked against the oracle."""
+    n, ns = 2_000_000, 100_000
+    opt, ir = synth.make_opt_lib(), synth.ce01_lib()
+    gal = synth.draw_galaxies(n, opt_lib=opt, ir_lib=ir, mmin=7.5, seed=99)
+    bands = synth.get_filters(synth.B30)
+    ph = egg_b200.Photometry(opt, ir, bands, line_lambda=synth.LINE_LAMBDA)
+    out = ph.compute(gal, f64=True)
+    ph.close()
+    pick = np.sort(np.random.default_rng(1).choice(n, ns, replace=False))
+    sub = {k: (v[pick] if isinstance(v, np.ndarray) and v.shape[:1] == (n,) else v) for k, v in gal.items()}
+    ref = Oracle(opt, ir, bands, line_lambda=synth.LINE_LAMBDA).compute(sub, f64=True)
+    for k in ("flux_disk", "flux_bulge"):
+        e = cases.rel_err(out[k + "_f64"][pick], ref[k])
+        assert e.max() < cases.TOL["fp32c"], f"{k}: {e.max():.2e} at {np.unravel_index(np.argmax(e), e.shape)}"
+    np.testing.assert_array_equal(out["flux"], out["flux_disk"] + out["flux_bulge"])

@@ -1,5 +1,5 @@
 # final evidence of the round: tests, bench lines, launch list, full captures of the three kernels that carry the step
-mkdir -p gpurun_out/r2b
+mkdir -p gpurun_out/r2b  # run from the repo root: gpurun -- bash tools/gpu_scripts/<this file>
 O=gpurun_out/r2b
 timeout 1500 python -m pytest tests -m gpu -q > $O/pytest_gpu.txt 2>&1; tail -3 $O/pytest_gpu.txt
 ( time timeout 1500 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err ) 2> $O/bench_n1.time; tail -3 $O/bench_n1.time

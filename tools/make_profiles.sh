@@ -1,5 +1,5 @@
 #!/bin/sh
-# Turns the scratch outputs of tools/gpu_round2_s.sh (gpurun_out/r2b) into the tracked summaries under profiles/.
+# Turns the scratch outputs of tools/gpu_scripts/gpu_round2_s.sh (gpurun_out/r2b) into the tracked summaries under profiles/.
 # usage: tools/make_profiles.sh [tag]   (tag defaults to r2b)
 set -e
 cd "$(dirname "$0")/.."

@@ -42,7 +42,7 @@ if walk is not None:
               "fma_pipe_pct": val(walk, "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
               "alu_pipe_pct": val(walk, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active")})
 d["source"] = ("ncu --set full --clock-control none -k regex:lane_(plan|build|walk|finish)_kernel of one step of "
-               "`python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-extra` (tools/gpu_round2_s.sh); the pipe numbers are the "
+               "`python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-extra` (tools/gpu_scripts/gpu_round2_s.sh); the pipe numbers are the "
                "walk kernel's, the DRAM bytes the sum over the step's four kernels")
 d["note"] = ("the DRAM traffic above the catalog columns (0.114 GB) is the rest-frame SED rows [node][32 galaxies] of every batch: written "
              "once by the build kernel, read by every band table whose window covers them (about 30 KB per galaxy read in total); "
