@@ -576,14 +576,15 @@ int eggphot_compute(eggphot_ctx *c, const eggphot_galaxies *gal, size_t ngal, co
     chunk = std::min(chunk, ngal);
     if (chunk == 0) return EGGPHOT_OK;
 #define CK(x) do { if ((e = (x)) != cudaSuccess) return c->cuda_fail(e, #x); } while (0)
-    struct Col { DevBuf Slot::*buf; const void *src; size_t elem; };
+    using SlotBuf = DevBuf Slot::*;
+    struct Col { SlotBuf buf; const void *src; size_t elem; };
     const Col ins[] = {
         {&Slot::z, gal->z, 4}, {&Slot::d, gal->d, 4}, {&Slot::m_disk, gal->m_disk, 4}, {&Slot::m_bulge, gal->m_bulge, 4},
         {&Slot::m2lcor, gal->m2lcor, 4}, {&Slot::lir, gal->lir, 4}, {&Slot::fpah, gal->fpah, 4}, {&Slot::mdust, gal->mdust, 4},
         {&Slot::igm_abs, P.apply_igm ? gal->igm_abs : nullptr, 12}, {&Slot::vdisp, nl ? gal->vdisp : nullptr, 4},
         {&Slot::lld, nl ? gal->line_lum_disk : nullptr, 4 * nl}, {&Slot::llb, nl ? gal->line_lum_bulge : nullptr, 4 * nl},
         {&Slot::osd, gal->opt_sed_disk, 8}, {&Slot::osb, gal->opt_sed_bulge, 8}, {&Slot::irs, gal->ir_sed, 8}};
-    struct OCol { DevBuf Slot::*buf; void *dst; size_t elem; };
+    struct OCol { SlotBuf buf; void *dst; size_t elem; };
     const OCol outs[] = {
         {&Slot::flux, out->flux, 4 * nb}, {&Slot::flux_disk, out->flux_disk, 4 * nb}, {&Slot::flux_bulge, out->flux_bulge, 4 * nb},
         {&Slot::rfmag, out->rfmag, 4 * nrf}, {&Slot::rfmag_disk, out->rfmag_disk, 4 * nrf}, {&Slot::rfmag_bulge, out->rfmag_bulge, 4 * nrf},
