@@ -132,7 +132,10 @@ constexpr int kStage = 8;
 // memory through L1).
 EGG_HD size_t lane_stage_bytes(bool fp64) { return (size_t)(kWalkThreads / 32) * 2 * kStage * 32 * (fp64 ? 8 : 4); }
 EGG_HD size_t lane_gx_bytes(int nD, int nB) { return ((size_t)lane_grid_rows(nD) + lane_grid_rows(nB)) * 16; }
-EGG_HD bool lane_gx_in_smem(bool fp64, int nD, int nB, size_t limit) { return lane_gx_bytes(nD, nB) + lane_stage_bytes(fp64) <= limit / 2; }
+#ifndef EGG_GX_SMEM_DIVISOR
+#define EGG_GX_SMEM_DIVISOR 2   // (tuning knob: a huge value keeps the grids out of shared memory, fewer and larger band groups)
+#endif
+EGG_HD bool lane_gx_in_smem(bool fp64, int nD, int nB, size_t limit) { return lane_gx_bytes(nD, nB) + lane_stage_bytes(fp64) <= limit / EGG_GX_SMEM_DIVISOR; }
 
 // Shared memory of the lane kernel: the band tables of the current group, and a little besides.
 constexpr size_t kSmemPerCta = 232448;   // 227 KB
