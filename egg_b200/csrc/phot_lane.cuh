@@ -126,7 +126,10 @@ EGG_HD int lane_grid_rows(int n) { return (n + 2 + 7) & ~7; }
 #endif
 constexpr int kWalkThreads = EGG_WALK_THREADS; // 20 warps at 96 registers
 constexpr int kSub = 4;
-constexpr int kStage = 8;
+#ifndef EGG_WALK_STAGE
+#define EGG_WALK_STAGE 8
+#endif
+constexpr int kStage = EGG_WALK_STAGE;
 // Shared memory of the walk kernel that is not band tables: the staging buffers, and {x, 1 / dx} of the two component
 // grids unless they would leave less than half of the shared memory to the band tables (then they are read from global
 // memory through L1).
