@@ -492,8 +492,8 @@ int eggphot_create(const eggphot_libs *libs, const eggphot_filters *bands, const
             if (smem + kLaneFixedSmem > (size_t)prop.sharedMemPerBlockOptin)
                 return c->fail(EGGPHOT_ERR_UNSUPPORTED, "band tables need " + std::to_string(smem) + " B of shared memory, device offers " +
                                                          std::to_string(prop.sharedMemPerBlockOptin) + "; lower smem_table_budget");
-            // SED rows of a chunk: 4 GiB per region unless EGGPHOT_LANE_SCRATCH_MB says otherwise, 2048 batches at least
-            size_t cap_bytes = size_t(4) << 30;
+            // SED rows of a chunk: 16 GiB per region (three regions at most; 180 GB of HBM) unless EGGPHOT_LANE_SCRATCH_MB says otherwise, 2048 batches at least
+            size_t cap_bytes = size_t(16) << 30; // (every chunk pays the pipeline's fixed cost: 4 / 8 / 16 / 32 GiB give 1.303 / 1.323 / 1.331 / 1.340e9 on the 1.4e7-galaxy shard)
             if (const char *e = getenv("EGGPHOT_LANE_SCRATCH_MB")) { const long v = atol(e); if (v > 0) cap_bytes = (size_t)v << 20; }
             c->lane_cap_batches = std::max<size_t>(cap_bytes / q.rows_stride, 2048);
             for (auto &h : c->zhist) CK(h.alloc(zsort_hist_bytes()));

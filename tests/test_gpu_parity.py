@@ -213,9 +213,11 @@ def test_large_sample_has_no_outliers(name):
             assert cases.rel_err(out[k + "_f64"], ref[k], cases.FLOOR[prec]).max() < cases.TOL[prec], (prec, k)
 
 
-def test_large_catalog_spot_check_against_the_oracle():
+def test_large_catalog_spot_check_against_the_oracle(monkeypatch):
     """2e6 galaxies x 30 bands through the host-memory entry point (three chunks of 6.7e5 galaxies, each worked off in
-    sub-chunks of 8 800 batches: the paths configs[3] takes per GPU), 1e5 of them drawn at random checked against the oracle."""
+    sub-chunks of 4 400 batches with the SED-row buffer capped at 2 GiB: the paths configs[3] takes per GPU), 1e5 of them
+    drawn at random checked against the oracle."""
+    monkeypatch.setenv("EGGPHOT_LANE_SCRATCH_MB", "2048")
     n, ns = 2_000_000, 100_000
     opt, ir = synth.make_opt_lib(), synth.ce01_lib()
     gal = synth.draw_galaxies(n, opt_lib=opt, ir_lib=ir, mmin=7.5, seed=99)
