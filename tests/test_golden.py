@@ -9,7 +9,7 @@ import cases
 import emul
 from oracle.oracle import Oracle
 
-GOLDEN = ("b4_defaults", "b30_rf3_defaults", "b40_hd_cs17", "b23_no_dust")
+GOLDEN = ("b4_defaults", "b30_rf3_defaults", "b40_hd_cs17", "b23_no_dust", "b30_hd_noigm")  # (the last: BASELINE configs[4])
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 

@@ -51,7 +51,7 @@ def test_cuda_matches_oracle(name, prec):
         np.testing.assert_allclose(out["rfmag"], tot, rtol=0, atol=2e-6)
 
 
-@pytest.mark.parametrize("name", ["b4_defaults", "b30_rf3_defaults", "b40_hd_cs17", "b23_no_dust"])
+@pytest.mark.parametrize("name", ["b4_defaults", "b30_rf3_defaults", "b40_hd_cs17", "b23_no_dust", "b30_hd_noigm"])
 def test_cuda_matches_golden(name):
     c = cases.make(name, ngal=256, seed=2024)
     g = np.load(os.path.join(HERE, "golden", f"{name}.npz"))

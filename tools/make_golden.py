@@ -17,8 +17,8 @@ import cases  # noqa: E402
 from oracle.oracle import Oracle  # noqa: E402
 
 np.seterr(all="ignore")
-GOLDEN = ("b4_defaults", "b30_rf3_defaults", "b40_hd_cs17", "b23_no_dust")
-for name in GOLDEN:
+GOLDEN = ("b4_defaults", "b30_rf3_defaults", "b40_hd_cs17", "b23_no_dust", "b30_hd_noigm")
+for name in (sys.argv[1:] or GOLDEN):  # (names on the command line: only those files are rewritten)
     c = cases.make(name, ngal=256, seed=2024)
     ref = Oracle(c["opt"], c["ir"], c["bands"], c["rfbands"], line_lambda=c["lines"], **c["opts"]).compute(c["gal"], f64=True)
     out = {k: ref[k] for k in ("flux_disk", "flux_bulge", "rfmag_disk", "rfmag_bulge")}
